@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — frame-pair aligns/s of the B200-native PL-SVO alignment path (BASELINE.json metric).
+
+A "step" is one pass of the hot path (plsvo::SparseImgAlign::run, coarse-to-fine levels 4->2,
+<=30 GN iterations per level) over one batch of synthetic frame pairs: VGA, 5-level pyramid,
+300 point patches + 80 line segments per pair.  Per-GPU work is fixed (weak scaling): every rank
+aligns its own batch, no data-path collective; poses are gathered with one NCCL all_gather.
+
+  value      : pairs/s, inputs resident in HBM, kernel time from CUDA events on the launch stream
+  e2e        : pairs/s through the C-ABI call with pinned HOST buffers (H2D + kernel + D2H timed)
+  roofline   : algorithmic bytes (241 B per patch-iteration + 281 B per patch-level)
+               / kernel time, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline: the CPU oracle (a restatement of the reference; "port") on this box's host cores
+
+`--impl reference` times the CPU oracle alone (rank 0), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frame-pair aligns/sec (VGA 5-lvl pyr, ~300pt+80ln)"
+BYTES_PATCH_ITER = 241
+BYTES_PATCH_LEVEL = 281
+BYTES_PAIR_FIXED = 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="frame pairs per GPU per step")
+    ap.add_argument("--n-pts", type=int, default=300)
+    ap.add_argument("--n-segs", type=int, default=80)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs per CPU-baseline pass (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "SparseImgAlign::run, VGA 640x480, 5-level pyramid (levels 4->2 used), "
+                    f"{args.n_pts} point patches + {args.n_segs} line segments per pair, <=30 GN iters/level",
+        "pairs_per_gpu_per_step": args.batch,
+        "global_batch": args.batch * n_gpus,
+        "parallelism": f"dp{n_gpus} (independent frame pairs, no data-path collective)",
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
+    """pairs/s of the CPU oracle with all host threads on the first n_pairs of `data`."""
+    import copy
+
+    sub = copy.copy(data)
+    sl = slice(0, n_pairs)
+    for name in ("T_ref_w", "T_cur_w", "T_cur_w_gt", "pt_px", "pt_f", "pt_pos", "seg_spx", "seg_epx", "seg_sf", "seg_ef",
+                 "seg_spos", "seg_epos", "seg_length"):
+        setattr(sub, name, np.ascontiguousarray(getattr(data, name)[sl]))
+    sub.ref_pyr = {l: np.ascontiguousarray(v[sl]) for l, v in data.ref_pyr.items()}
+    sub.cur_pyr = {l: np.ascontiguousarray(v[sl]) for l, v in data.cur_pyr.items()}
+    threads = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+    oracle_lib.align(abi, sub, n_threads=threads)  # warm
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        oracle_lib.align(abi, sub, n_threads=threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return reps * n_pairs / dt, threads, dt, reps
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(world, 1)
+
+    import plsvo_b200
+    from plsvo_b200 import abi, synth
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import oracle_lib
+        import torch
+
+        n = args.cpu_sample or min(args.batch, 256)
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        data = synth.make_align_batch(batch=n, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=3000)
+        threads = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+        for _ in range(args.warmup):
+            oracle_lib.align(abi, data, n_threads=threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle_lib.align(abi, data, n_threads=threads)
+        dt = time.perf_counter() - t0
+        val = args.steps * n / dt
+        cfg = workload_config(args, n_gpus)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 residuals / f64 accumulate", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} pairs per step x {args.steps} steps, oracle restatement of sparse_img_align.cpp "
+                                       "(the reference itself cannot be compiled in this image)"},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    B = args.batch
+    data = synth.make_align_batch(batch=B, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=3000 + 100000 * rank)
+
+    # pinned host copies of every input array (the e2e leg copies from these every step)
+    def pin(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t.numpy(), t
+
+    keep = []
+    for name in ("T_ref_w", "T_cur_w", "pt_px", "pt_f", "pt_pos", "seg_spx", "seg_epx", "seg_sf", "seg_ef", "seg_spos",
+                 "seg_epos", "seg_length"):
+        arr, t = pin(getattr(data, name))
+        setattr(data, name, arr)
+        keep.append(t)
+    for pyr in (data.ref_pyr, data.cur_pyr):
+        for l in list(pyr):
+            arr, t = pin(pyr[l])
+            pyr[l] = arr
+            keep.append(t)
+    h2d = sum(getattr(data, n).nbytes for n in ("T_ref_w", "T_cur_w", "pt_px", "pt_f", "pt_pos", "seg_spx", "seg_epx", "seg_sf",
+                                                "seg_ef", "seg_spos", "seg_epos", "seg_length"))
+    h2d += sum(v.nbytes for v in data.ref_pyr.values()) + sum(v.nbytes for v in data.cur_pyr.values())
+
+    stream = torch.cuda.current_stream(dev)
+    ctx = plsvo_b200.Context(local_rank, stream.cuda_stream)
+    al = plsvo_b200.SparseImgAlign(4, 2, 30, plsvo_b200.SparseImgAlign.GaussNewton, False, False, ctx=ctx)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- device-resident leg ----
+    al.upload(data)
+    for _ in range(args.warmup):
+        al.launch()
+    ctx.sync()
+    out0 = al.download()
+    d2h = sum(getattr(out0, n).nbytes for n in ("T_cur_w", "n_tracked", "H", "seg_killed", "iters", "status", "patch_iters",
+                                                "patch_levels"))
+    launches0 = ctx.launch_count()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        for s, e in ev:
+            flush.fill_(1)  # evict the batch from L2 (outside the timed events)
+            s.record(stream)
+            al.launch()
+            e.record(stream)
+        torch.cuda.synchronize(dev)
+    kernel_ms = [s.elapsed_time(e) for s, e in ev]
+    launches = ctx.launch_count() - launches0
+    total_ms = float(sum(kernel_ms))
+    out = al.download()
+    t_total = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        gathered = torch.empty(world * B * 7, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, torch.from_numpy(out.T_cur_w.reshape(-1)).to(dev))  # gather poses
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    max_ms = float(t_total.item())
+    value = n_gpus * B * args.steps / (max_ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers -> C ABI -> host results, every step ----
+    for _ in range(2):
+        al.run(data)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e_s, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e_s.record(stream)
+    for _ in range(args.steps):
+        out_e2e = al.run(data)
+    e_e.record(stream)
+    torch.cuda.synchronize(dev)
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = torch.tensor([max(e_s.elapsed_time(e_e), 1e3 * e2e_wall)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * B * args.steps / (float(e2e_ms.item()) * 1e-3)
+
+    # ---- roofline of the alignment kernel (the only kernel in the step) ----
+    alg_bytes = float(out.patch_iters.astype(np.float64).sum() * BYTES_PATCH_ITER
+                      + out.patch_levels.astype(np.float64).sum() * BYTES_PATCH_LEVEL + B * BYTES_PAIR_FIXED)
+    avg_kernel_s = (total_ms / args.steps) * 1e-3
+    peak, peak_src = measured_hbm_peak()
+    achieved = alg_bytes / avg_kernel_s / 1e9
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            import oracle_lib
+
+            n = args.cpu_sample or B
+            rate, threads, secs, reps = cpu_oracle_rate(abi, oracle_lib, data, min(n, B))
+            # parity of the timed batch against the oracle on the same inputs
+            ref = oracle_lib.align(abi, data, n_threads=threads)
+            ang, rel = synth.pose_error(out.T_cur_w, ref.T_cur_w)
+            cpu = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port",
+                   "sample": f"{min(n, B)} pairs x {reps} passes ({secs:.1f} s), all host threads, CPU oracle "
+                             "(restatement of sparse_img_align.cpp; the reference cannot be compiled in this image)",
+                   "parity_vs_gpu": {"max_rot_rad": float(ang.max()), "max_rel_t": float(rel.max()),
+                                     "pairs_within_tol": int(((ang <= 1e-5) & (rel <= 1e-4)).sum()), "pairs": int(B)}}
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 residuals / f64 accumulate", "data": "synthetic", "config": workload_config(args, n_gpus),
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "sparse_img_align_kernel",
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_kernel_ms": total_ms / args.steps,
+                         "mean_gn_passes_per_pair": float(out.iters.sum(axis=1).mean())},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

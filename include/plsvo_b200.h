@@ -1,0 +1,218 @@
+/*
+ * plsvo_b200.h — C ABI of the B200-native PL-SVO per-frame optimisation path.
+ *
+ * Two entry-point families, one per reference symbol they replace:
+ *
+ *   plsvo_align_*    replaces  plsvo::SparseImgAlign::run()
+ *                    (reference: include/plsvo/sparse_img_align.h:56-70,
+ *                     src/sparse_img_align.cpp:54-95; call sites
+ *                     src/frame_handler_mono.cpp:272-274 and :418-420)
+ *   plsvo_poseopt_*  replaces  plsvo::pose_optimizer::optimizeGaussNewton()
+ *                    (reference: include/plsvo/pose_optimizer.h:47-64,
+ *                     src/pose_optimizer.cpp:38-260 (9-arg) and :262-582 (10-arg);
+ *                     call site src/frame_handler_mono.cpp:327-329)
+ *
+ * The reference has no FFI layer: its boundary is two C++ link-time symbols that take
+ * boost::shared_ptr<Frame>.  The C++ shim in pl-svo_b200/host/ keeps those two signatures
+ * and packs Frame / Feature lists into the flat arrays declared here.
+ *
+ * Conventions
+ *   - plain C types only, caller-allocated outputs, int return codes, no exceptions.
+ *   - a batch is B independent frame pairs (align) or B independent frames (pose-opt).
+ *   - SE3 poses are 7 doubles {qx,qy,qz,qw,tx,ty,tz}: the unit quaternion (Eigen coeffs()
+ *     order) and translation that the reference's Sophus::SE3 stores (include/plsvo/frame.h:62).
+ *   - 6x6 matrices are 36 doubles (symmetric, so row/column order is immaterial).
+ *   - every call is stream-ordered on the context's stream; *_download and *_batch
+ *     synchronise before returning.
+ *   - there is NO CPU fallback: without a CUDA device every call returns PLSVO_ERR_NO_DEVICE.
+ */
+#ifndef PLSVO_B200_H_
+#define PLSVO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLSVO_MAX_LEVELS 8   /* pyramid levels addressable through the ABI (reference uses 5) */
+#define PLSVO_PATCH_AREA 16  /* 4x4 patch, include/plsvo/sparse_img_align.h:48-50 */
+
+/* return codes */
+#define PLSVO_OK 0
+#define PLSVO_ERR_INVALID (-1)    /* bad argument / inconsistent batch description */
+#define PLSVO_ERR_CUDA (-2)       /* CUDA runtime error, see plsvo_last_error() */
+#define PLSVO_ERR_NO_DEVICE (-3)  /* no usable CUDA device: there is no CPU path */
+#define PLSVO_ERR_STATE (-4)      /* launch/download without a prior upload */
+
+typedef struct plsvo_ctx plsvo_ctx;
+
+/* Undistorted pinhole camera: what vk::PinholeCamera::world2cam / errorMultiplier2 /
+ * isInFrame use when the handler is given the undistorted model (app/run_pipeline.cpp:786-795). */
+typedef struct plsvo_camera {
+  int32_t width, height; /* level-0 image size */
+  int32_t reserved0, reserved1;
+  double fx, fy, cx, cy;
+} plsvo_camera;
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse image alignment
+ * ---------------------------------------------------------------------------------------- */
+
+/* SparseImgAlign constructor arguments (src/sparse_img_align.cpp:40-52); defaults at the call
+ * site are max_level=4, min_level=2, n_iter=30 (src/frame_handler_mono.cpp:272-273,
+ * src/config.cpp:98-99); eps is hard-coded 1e-6 in the reference (:51). */
+typedef struct plsvo_align_params {
+  int32_t max_level;
+  int32_t min_level;
+  int32_t n_iter;
+  int32_t reserved;
+  double eps;
+} plsvo_align_params;
+
+/* One batch of B frame pairs.  All pairs share the camera and the array strides n_pts/n_segs;
+ * per-pair feature counts may be smaller (pt_count/seg_count) and individual features may be
+ * flagged invalid (feat3D == NULL in the reference).
+ *
+ * Images: for pyramid level l in [min_level,max_level], image of pair b starts at
+ * ref_img[l] + b*img_stride[l] with row pitch img_pitch[l] bytes and (width>>l) x (height>>l)
+ * u8 pixels (Frame::img_pyr_, include/plsvo/frame.h:64).  Levels outside the range may be NULL.
+ */
+typedef struct plsvo_align_batch {
+  int32_t batch;   /* B */
+  int32_t n_pts;   /* array stride: points per pair   (Frame::pt_fts_,  frame.h:65) */
+  int32_t n_segs;  /* array stride: segments per pair (Frame::seg_fts_, frame.h:66) */
+  int32_t reserved;
+  plsvo_camera cam;
+
+  const uint8_t* ref_img[PLSVO_MAX_LEVELS];
+  const uint8_t* cur_img[PLSVO_MAX_LEVELS];
+  size_t img_pitch[PLSVO_MAX_LEVELS];
+  size_t img_stride[PLSVO_MAX_LEVELS];
+
+  const double* T_ref_w; /* [B][7]  ref_frame->T_f_w_ */
+  const double* T_cur_w; /* [B][7]  cur_frame->T_f_w_ on entry (initial guess) */
+
+  const int32_t* pt_count;  /* [B] or NULL (= n_pts)  : pt_fts_.size() */
+  const double* pt_px;      /* [B][n_pts][2]  PointFeat::px  (level-0 pixels) */
+  const double* pt_f;       /* [B][n_pts][3]  PointFeat::f   (unit bearing)   */
+  const double* pt_pos;     /* [B][n_pts][3]  PointFeat::feat3D->pos_ (world) */
+  const uint8_t* pt_valid;  /* [B][n_pts] or NULL (= all valid): feat3D != NULL */
+
+  const int32_t* seg_count; /* [B] or NULL (= n_segs) : seg_fts_.size() */
+  const double* seg_spx;    /* [B][n_segs][2] LineFeat::spx */
+  const double* seg_epx;    /* [B][n_segs][2] LineFeat::epx */
+  const double* seg_sf;     /* [B][n_segs][3] LineFeat::sf  */
+  const double* seg_ef;     /* [B][n_segs][3] LineFeat::ef  */
+  const double* seg_spos;   /* [B][n_segs][3] LineFeat::feat3D->spos_ */
+  const double* seg_epos;   /* [B][n_segs][3] LineFeat::feat3D->epos_ */
+  const double* seg_length; /* [B][n_segs]    LineFeat::length */
+  const uint8_t* seg_valid; /* [B][n_segs] or NULL: feat3D != NULL */
+} plsvo_align_batch;
+
+/* Caller-allocated outputs; any pointer may be NULL to skip that output. */
+typedef struct plsvo_align_result {
+  double* T_cur_w;        /* [B][7]  cur_frame->T_f_w_ on return (sparse_img_align.cpp:92) */
+  int64_t* n_tracked;     /* [B]     return value of run(): n_meas_/16 (:94) */
+  double* H;              /* [B][36] H_ of the last evaluated iteration (getFisherInformation, :97-102) */
+  uint8_t* seg_killed;    /* [B][n_segs] 1 where the reference sets ref seg feat3D = NULL (:687-688) */
+  int32_t* iters;         /* [B][PLSVO_MAX_LEVELS] residual passes executed at each level (index = level) */
+  int32_t* status;        /* [B] bit0: early-out "no features" (:58-62); bit1: solver stop_ was raised */
+  uint32_t* patch_iters;  /* [B] sum over executed passes of patches evaluated (roofline accounting) */
+  uint32_t* patch_levels; /* [B] sum over levels of patches precomputed (roofline accounting) */
+} plsvo_align_result;
+
+/* ------------------------------------------------------------------------------------------
+ * Pose optimiser
+ * ---------------------------------------------------------------------------------------- */
+
+/* Arguments of pose_optimizer::optimizeGaussNewton (pose_optimizer.h:47-64); defaults
+ * reproj_thresh=2.0, n_iter=10, n_iter_ref=3 (src/config.cpp:102-104).  n_iter_ref < 0
+ * selects the 9-argument overload (no refinement loop). */
+typedef struct plsvo_poseopt_params {
+  double reproj_thresh;
+  int32_t n_iter;
+  int32_t n_iter_ref;
+} plsvo_poseopt_params;
+
+typedef struct plsvo_poseopt_batch {
+  int32_t batch;   /* B frames */
+  int32_t n_pts;   /* array stride */
+  int32_t n_segs;  /* array stride */
+  int32_t reserved;
+  double fx;       /* frame->cam_->errorMultiplier2() */
+
+  const double* T_f_w;      /* [B][7] frame->T_f_w_ on entry */
+
+  const int32_t* pt_count;  /* [B] or NULL */
+  const double* pt_f;       /* [B][n_pts][3]  PointFeat::f */
+  const double* pt_pos;     /* [B][n_pts][3]  feat3D->pos_ */
+  const int32_t* pt_level;  /* [B][n_pts]     Feature::level */
+  const uint8_t* pt_valid;  /* [B][n_pts] or NULL */
+
+  const int32_t* seg_count; /* [B] or NULL */
+  const double* seg_line;   /* [B][n_segs][3] LineFeat::line */
+  const double* seg_spos;   /* [B][n_segs][3] feat3D->spos_ */
+  const double* seg_epos;   /* [B][n_segs][3] feat3D->epos_ */
+  const int32_t* seg_level; /* [B][n_segs] */
+  const uint8_t* seg_valid; /* [B][n_segs] or NULL */
+} plsvo_poseopt_batch;
+
+typedef struct plsvo_poseopt_result {
+  double* T_f_w;            /* [B][7]  frame->T_f_w_ on return */
+  double* cov;              /* [B][36] frame->Cov_ (pose_optimizer.cpp:199) */
+  double* estimated_scale;  /* [B] */
+  double* error_init;       /* [B] */
+  double* error_final;      /* [B] */
+  int64_t* num_obs_pt;      /* [B] */
+  int64_t* num_obs_ls;      /* [B] */
+  uint8_t* pt_outlier;      /* [B][n_pts]  1 where the reference sets feat3D = NULL (:218) */
+  uint8_t* seg_outlier;     /* [B][n_segs] (:239) */
+  int32_t* iters;           /* [B][2] GN passes executed in the main / refinement loop */
+  int32_t* status;          /* [B] bit0: early return "no observations" (:88-89), outputs untouched */
+} plsvo_poseopt_result;
+
+/* ------------------------------------------------------------------------------------------
+ * Context, memory, execution
+ * ---------------------------------------------------------------------------------------- */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on, or NULL to create a private one. */
+int plsvo_ctx_create(int device, void* stream, plsvo_ctx** out);
+void plsvo_ctx_destroy(plsvo_ctx* ctx);
+/* last error text of this context (or of ctx creation when ctx == NULL) */
+const char* plsvo_last_error(const plsvo_ctx* ctx);
+/* the cudaStream_t all work of this context is ordered on */
+void* plsvo_ctx_stream(plsvo_ctx* ctx);
+int plsvo_sync(plsvo_ctx* ctx);
+
+/* page-locked host memory for batch arrays (keeps the H2D/D2H legs at PCIe speed) */
+int plsvo_host_alloc(void** ptr, size_t bytes);
+int plsvo_host_free(void* ptr);
+
+/* Alignment.  upload: host arrays -> device layout (async).  launch: the whole coarse-to-fine
+ * optimisation of every pair, device-resident in and out (async).  download: device -> host
+ * outputs, then synchronise.  plsvo_align_batch_run = upload + launch + download. */
+int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* batch);
+int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* params);
+int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* out);
+int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* batch,
+                          const plsvo_align_params* params, const plsvo_align_result* out);
+
+/* Pose optimiser, same three legs. */
+int plsvo_poseopt_upload(plsvo_ctx* ctx, const plsvo_poseopt_batch* batch);
+int plsvo_poseopt_launch(plsvo_ctx* ctx, const plsvo_poseopt_params* params);
+int plsvo_poseopt_download(plsvo_ctx* ctx, const plsvo_poseopt_result* out);
+int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* batch,
+                            const plsvo_poseopt_params* params, const plsvo_poseopt_result* out);
+
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+int64_t plsvo_launch_count(const plsvo_ctx* ctx);
+
+/* library build info: "plsvo_b200 <version> sm_100a" */
+const char* plsvo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSVO_B200_H_ */

@@ -1,0 +1,90 @@
+"""Loader of the CPU oracle (oracle/libplsvo_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (pl-svo_b200/) never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplsvo_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "plsvo_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "plsvo_b200.h")
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in (src, hdr)
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"] + ([] if force else []))
+    return LIB_PATH
+
+
+def load(abi):
+    """abi = the pl-svo_b200.abi module (struct definitions are shared with the product header)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.plsvo_oracle_align_batch.restype = C.c_int
+    lib.plsvo_oracle_align_batch.argtypes = [P(abi.AlignBatch), P(abi.AlignParams), P(abi.AlignResult), C.c_int, C.c_int]
+    lib.plsvo_oracle_align_trace.restype = C.c_int
+    lib.plsvo_oracle_align_trace.argtypes = [P(abi.AlignBatch), P(abi.AlignParams), C.c_int, P(C.c_double), C.c_int, P(C.c_int)]
+    lib.plsvo_oracle_trace_stride.restype = C.c_int
+    lib.plsvo_oracle_poseopt_batch.restype = C.c_int
+    lib.plsvo_oracle_poseopt_batch.argtypes = [P(abi.PoseOptBatch), P(abi.PoseOptParams), P(abi.PoseOptResult), C.c_int]
+    for name, n_in in (("plsvo_oracle_se3_exp", 1), ("plsvo_oracle_se3_inverse", 1), ("plsvo_oracle_se3_mul", 2),
+                       ("plsvo_oracle_solve6", 2), ("plsvo_oracle_inverse6", 1)):
+        fn = getattr(lib, name)
+        fn.restype = None
+        fn.argtypes = [P(C.c_double)] * (n_in + 1)
+    lib.plsvo_oracle_hardware_threads.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def align(abi, data, params=None, n_threads: int = 1, flags: int = 0):
+    """Run the oracle's SparseImgAlign restatement on an AlignData batch -> abi.AlignOut."""
+    lib = load(abi)
+    params = params or abi.align_params(data.max_level, data.min_level)
+    batch, keep = abi.make_align_batch(data)
+    out = abi.AlignOut(data.batch, data.n_segs)
+    rc = lib.plsvo_oracle_align_batch(C.byref(batch), C.byref(params), C.byref(out.struct), n_threads, flags)
+    if rc != 0:
+        raise RuntimeError(f"oracle align failed rc={rc}")
+    return out
+
+
+def align_trace(abi, data, pair: int, params=None, max_records: int = 512):
+    lib = load(abi)
+    params = params or abi.align_params(data.max_level, data.min_level)
+    batch, keep = abi.make_align_batch(data)
+    stride = lib.plsvo_oracle_trace_stride()
+    rec = np.zeros((max_records, stride))
+    n = C.c_int(0)
+    rc = lib.plsvo_oracle_align_trace(C.byref(batch), C.byref(params), pair,
+                                      rec.ctypes.data_as(C.POINTER(C.c_double)), max_records, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle trace failed rc={rc}")
+    return rec[: n.value]
+
+
+def poseopt(abi, data, params=None, n_threads: int = 1):
+    lib = load(abi)
+    params = params or abi.poseopt_params()
+    batch, keep = abi.make_poseopt_batch(data)
+    out = abi.PoseOptOut(data.batch, data.n_pts, data.n_segs)
+    rc = lib.plsvo_oracle_poseopt_batch(C.byref(batch), C.byref(params), C.byref(out.struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle poseopt failed rc={rc}")
+    return out

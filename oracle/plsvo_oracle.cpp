@@ -1,0 +1,1041 @@
+// plsvo_oracle.cpp — CPU restatement of PL-SVO's per-frame optimisation path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library; the product
+// (pl-svo_b200/csrc) never links, loads or calls it.
+//
+// PARITY UNPINNED: the reference (rubengooj/pl-svo @ 5d4ca39) ships no tests, golden vectors or
+// fixtures for this path, and it cannot be compiled here (Eigen, Sophus, OpenCV C++, boost and
+// rpg_vikit are absent; no network).  This file is therefore a line-by-line restatement:
+//   * of the code that IS in /root/reference — each function cites the file:line it follows;
+//   * of the un-vendored third-party arithmetic the path calls (uzh-rpg/rpg_vikit vikit_common:
+//     NLLSSolver<6,SE3>, robust_cost, math_utils, PinholeCamera; strasdat/Sophus non-templated
+//     SE3/SO3; Eigen LDLT / inverse) restated from their published sources.  Neither is version
+//     pinned by the reference (CMakeLists.txt:40-41,57), see SURVEY.md §8c.
+// It is pinned instead by an independent NumPy restatement (oracle/np_oracle.py), analytic
+// properties (tests/test_oracle_*.py) and frozen traces under tests/golden/.
+//
+// Arithmetic follows the source text as strict IEEE-754 without FMA contraction (build with
+// -ffp-contract=off): float where the reference uses float, double where it uses double.
+//
+// Build: see oracle/Makefile  (g++ -O3 -march=x86-64-v3 -ffp-contract=off -shared -fPIC).
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "../include/plsvo_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Sophus (old, non-templated) SO3/SE3 — restated from strasdat/Sophus sophus/so3.cpp, se3.cpp.
+// Rotation is a unit quaternion (Eigen::Quaterniond), every product re-normalises.
+// ------------------------------------------------------------------------------------------------
+constexpr double kSmallEps = 1e-10;  // Sophus SMALL_EPS
+
+struct Quat {
+  double x, y, z, w;
+};
+struct Vec3 {
+  double x, y, z;
+};
+inline Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Vec3 operator*(Vec3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline Vec3 cross(Vec3 a, Vec3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+inline double norm(Vec3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+
+inline Quat qnormalized(Quat q) {  // Eigen: coeffs() /= coeffs().norm()
+  const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+inline Quat qmul(Quat a, Quat b) {  // Eigen quaternion product
+  return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+          a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x,
+          a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+inline Vec3 qrot(Quat q, Vec3 v) {  // Eigen QuaternionBase::_transformVector
+  const Vec3 qv{q.x, q.y, q.z};
+  Vec3 uv = cross(qv, v);
+  uv = uv + uv;
+  return v + uv * q.w + cross(qv, uv);
+}
+
+struct SE3 {
+  Quat q{0, 0, 0, 1};
+  Vec3 t{0, 0, 0};
+};
+inline SE3 se3_from_pose7(const double* p) {
+  SE3 T;
+  T.q = qnormalized(Quat{p[0], p[1], p[2], p[3]});  // SO3(const Quaterniond&) normalises
+  T.t = {p[4], p[5], p[6]};
+  return T;
+}
+inline void se3_to_pose7(const SE3& T, double* p) {
+  p[0] = T.q.x, p[1] = T.q.y, p[2] = T.q.z, p[3] = T.q.w;
+  p[4] = T.t.x, p[5] = T.t.y, p[6] = T.t.z;
+}
+inline SE3 se3_mul(const SE3& a, const SE3& b) {  // SE3::operator*=
+  SE3 r;
+  r.t = a.t + qrot(a.q, b.t);
+  r.q = qnormalized(qmul(a.q, b.q));
+  return r;
+}
+inline SE3 se3_inverse(const SE3& a) {  // SE3::inverse
+  SE3 r;
+  r.q = qnormalized(Quat{-a.q.x, -a.q.y, -a.q.z, a.q.w});
+  r.t = qrot(r.q, a.t * -1.0);
+  return r;
+}
+inline Vec3 se3_act(const SE3& T, Vec3 p) { return qrot(T.q, p) + T.t; }
+
+// SE3::exp( [upsilon, omega] ), SO3::expAndTheta
+inline SE3 se3_exp(const double u[6]) {
+  const Vec3 upsilon{u[0], u[1], u[2]};
+  const Vec3 omega{u[3], u[4], u[5]};
+  const double theta = norm(omega);
+  const double half_theta = 0.5 * theta;
+  double imag_factor;
+  const double real_factor = std::cos(half_theta);
+  if (theta < kSmallEps) {
+    const double theta_sq = theta * theta;
+    const double theta_po4 = theta_sq * theta_sq;
+    imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
+  } else {
+    imag_factor = std::sin(half_theta) / theta;
+  }
+  SE3 r;
+  r.q = qnormalized(Quat{imag_factor * omega.x, imag_factor * omega.y, imag_factor * omega.z, real_factor});
+  // V = I + (1-cos)/theta^2 * Omega + (theta - sin)/theta^3 * Omega^2 ;  t = V * upsilon
+  if (theta < kSmallEps) {
+    r.t = qrot(r.q, upsilon);  // V = so3.matrix()
+  } else {
+    const double theta_sq = theta * theta;
+    const double a = (1 - std::cos(theta)) / theta_sq;
+    const double b = (theta - std::sin(theta)) / (theta_sq * theta);
+    const Vec3 wu = cross(omega, upsilon);  // Omega * upsilon
+    const Vec3 wwu = cross(omega, wu);      // Omega^2 * upsilon
+    r.t = upsilon + wu * a + wwu * b;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Eigen fixed-size 6x6 helpers — LDLT with diagonal pivoting (Eigen/src/Cholesky/LDLT.h,
+// ldlt_inplace<Lower>::unblocked + _solve_impl) and inverse via partial-pivot LU.
+// ------------------------------------------------------------------------------------------------
+struct Ldlt6 {
+  double m[6][6];  // lower: L (unit diag implied) + D on the diagonal
+  int tr[6];       // transpositions
+};
+inline void ldlt6_compute(const double A[36], Ldlt6& f) {
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) f.m[i][j] = A[i * 6 + j];
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double big = std::fabs(f.m[k][k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (std::fabs(f.m[i][i]) > big) big = std::fabs(f.m[i][i]), piv = i;
+    f.tr[k] = piv;
+    if (piv != k) {
+      // symmetric swap of rows/cols k and piv restricted to the lower triangle
+      for (int j = 0; j < k; ++j) std::swap(f.m[k][j], f.m[piv][j]);
+      for (int i = piv + 1; i < 6; ++i) std::swap(f.m[i][k], f.m[i][piv]);
+      std::swap(f.m[k][k], f.m[piv][piv]);
+      for (int i = k + 1; i < piv; ++i) std::swap(f.m[i][k], f.m[piv][i]);
+    }
+    if (k > 0) {
+      double temp[6];
+      for (int j = 0; j < k; ++j) temp[j] = f.m[j][j] * f.m[k][j];
+      double s = 0;
+      for (int j = 0; j < k; ++j) s += f.m[k][j] * temp[j];
+      f.m[k][k] -= s;
+      for (int i = k + 1; i < 6; ++i) {
+        double s2 = 0;
+        for (int j = 0; j < k; ++j) s2 += f.m[i][j] * temp[j];
+        f.m[i][k] -= s2;
+      }
+    }
+    const double akk = f.m[k][k];
+    const bool pivot_is_valid = std::fabs(akk) > 0.0;
+    if (k == 0 && !pivot_is_valid) {
+      for (int j = 0; j < 6; ++j) f.tr[j] = j;
+      return;
+    }
+    if (pivot_is_valid)
+      for (int i = k + 1; i < 6; ++i) f.m[i][k] /= akk;
+  }
+}
+inline void ldlt6_solve(const Ldlt6& f, const double b[6], double x[6]) {
+  for (int i = 0; i < 6; ++i) x[i] = b[i];
+  for (int k = 0; k < 6; ++k) std::swap(x[k], x[f.tr[k]]);  // P b
+  for (int i = 0; i < 6; ++i)                               // L^-1
+    for (int j = 0; j < i; ++j) x[i] -= f.m[i][j] * x[j];
+  const double tol = 1.0 / std::numeric_limits<double>::max();  // Eigen >= 3.3 pseudo-inverse of D
+  for (int i = 0; i < 6; ++i) {
+    if (std::fabs(f.m[i][i]) > tol)
+      x[i] /= f.m[i][i];
+    else
+      x[i] = 0.0;
+  }
+  for (int i = 5; i >= 0; --i)  // L^-T
+    for (int j = i + 1; j < 6; ++j) x[i] -= f.m[j][i] * x[j];
+  for (int k = 5; k >= 0; --k) std::swap(x[k], x[f.tr[k]]);  // P^T
+}
+inline void solve6(const double A[36], const double b[6], double x[6]) {
+  Ldlt6 f;
+  ldlt6_compute(A, f);
+  ldlt6_solve(f, b, x);
+}
+// Matrix6d::inverse(): Eigen uses PartialPivLU for fixed sizes > 4.
+inline void inverse6(const double A[36], double out[36]) {
+  double lu[6][6];
+  int perm[6];
+  for (int i = 0; i < 6; ++i) {
+    perm[i] = i;
+    for (int j = 0; j < 6; ++j) lu[i][j] = A[i * 6 + j];
+  }
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double big = std::fabs(lu[k][k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (std::fabs(lu[i][k]) > big) big = std::fabs(lu[i][k]), piv = i;
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) std::swap(lu[k][j], lu[piv][j]);
+      std::swap(perm[k], perm[piv]);
+    }
+    for (int i = k + 1; i < 6; ++i) {
+      lu[i][k] /= lu[k][k];
+      for (int j = k + 1; j < 6; ++j) lu[i][j] -= lu[i][k] * lu[k][j];
+    }
+  }
+  for (int c = 0; c < 6; ++c) {
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+      y[i] = (perm[i] == c) ? 1.0 : 0.0;
+      for (int j = 0; j < i; ++j) y[i] -= lu[i][j] * y[j];
+    }
+    for (int i = 5; i >= 0; --i) {
+      for (int j = i + 1; j < 6; ++j) y[i] -= lu[i][j] * y[j];
+      y[i] /= lu[i][i];
+    }
+    for (int i = 0; i < 6; ++i) out[i * 6 + c] = y[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vikit_common pieces (math_utils.h, robust_cost.cpp)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+inline T get_median(std::vector<T>& v) {  // vk::getMedian: nth_element at floor(n/2)
+  auto it = v.begin() + v.size() / 2;
+  std::nth_element(v.begin(), it, v.end());
+  return *it;
+}
+inline float mad_scale(std::vector<float>& errors) {  // MADScaleEstimator::compute, NORMALIZER=1.48f
+  return 1.48f * get_median(errors);
+}
+inline float tukey_value(const float& x) {  // TukeyWeightFunction::value, b = 4.6851f
+  const float b = 4.6851f;
+  const float b_square = b * b;
+  const float x_square = x * x;
+  if (x_square <= b_square) {
+    const float tmp = 1.0f - x_square / b_square;
+    return tmp * tmp;
+  }
+  return 0.0f;
+}
+inline double norm_max6(const double x[6]) {  // vk::norm_max
+  double m = 0;
+  for (int i = 0; i < 6; ++i) m = std::max(m, std::fabs(x[i]));
+  return m;
+}
+
+// Frame::jacobian_xyz2uv — include/plsvo/frame.h:138-160
+inline void jacobian_xyz2uv(Vec3 p, double J[2][6]) {
+  const double x = p.x, y = p.y;
+  const double z_inv = 1. / p.z;
+  const double z_inv_2 = z_inv * z_inv;
+  J[0][0] = -z_inv;
+  J[0][1] = 0.0;
+  J[0][2] = x * z_inv_2;
+  J[0][3] = y * J[0][2];
+  J[0][4] = -(1.0 + x * J[0][2]);
+  J[0][5] = y * z_inv;
+  J[1][0] = 0.0;
+  J[1][1] = -z_inv;
+  J[1][2] = y * z_inv_2;
+  J[1][3] = 1.0 + y * J[1][2];
+  J[1][4] = -J[0][3];
+  J[1][5] = -x * z_inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch — src/feature.cpp:175-218, include/plsvo/feature.h:107-147
+// ------------------------------------------------------------------------------------------------
+struct Image {
+  const uint8_t* data;
+  int cols, rows;
+  int stride;
+};
+struct Patch {
+  static constexpr int size = 4, halfsize = 2, area = 16;
+  Image img;
+  float u_ref, v_ref;
+  int u_ref_i, v_ref_i;
+  float wTL, wTR, wBL, wBR;
+  const uint8_t* roi;  // top-left pixel of the 4x4 ROI
+  explicit Patch(const Image& im) : img(im) {}
+  void setPosition(double px0, double px1) {  // feature.cpp:189-197
+    u_ref = (float)px0;
+    v_ref = (float)px1;
+    u_ref_i = (int)floorf(u_ref);
+    v_ref_i = (int)floorf(v_ref);
+  }
+  void computeInterpWeights() {  // feature.cpp:199-208
+    const float subpix_u_ref = u_ref - u_ref_i;
+    const float subpix_v_ref = v_ref - v_ref_i;
+    wTL = (float)((1.0 - subpix_u_ref) * (1.0 - subpix_v_ref));
+    wTR = (float)(subpix_u_ref * (1.0 - subpix_v_ref));
+    wBL = (float)((1.0 - subpix_u_ref) * subpix_v_ref);
+    wBR = subpix_u_ref * subpix_v_ref;  // float*float in the source
+  }
+  void setRoi() {  // feature.cpp:210-218
+    roi = img.data + (size_t)(v_ref_i - halfsize) * img.stride + (u_ref_i - halfsize);
+  }
+  bool isInFrame(int boundary) const {  // feature.h:139-144
+    return !(u_ref_i < boundary || v_ref_i < boundary || u_ref_i >= img.cols - boundary ||
+             v_ref_i >= img.rows - boundary);
+  }
+};
+
+// vk::AbstractCamera::isInFrame(obs, boundary, level)
+inline bool cam_is_in_frame(const plsvo_camera& cam, int ox, int oy, int boundary, int level) {
+  return ox >= boundary && ox < cam.width / (1 << level) - boundary && oy >= boundary &&
+         oy < cam.height / (1 << level) - boundary;
+}
+
+// LineFeat::setupSampling — src/feature.cpp:160-173
+inline size_t setup_sampling(size_t patch_size, const double spx[2], const double epx[2], double length,
+                             double dif[2]) {
+  dif[0] = epx[0] - spx[0];
+  dif[1] = epx[1] - spx[1];
+  const double tan_dir = std::min(std::fabs(dif[0]), std::fabs(dif[1])) / std::max(std::fabs(dif[0]), std::fabs(dif[1]));
+  const double sin_dir = tan_dir / std::sqrt(1.0 + tan_dir * tan_dir);
+  const double correction = 2.0 * std::sqrt(1.0 + sin_dir * sin_dir);
+  return (size_t)std::max(1.0, length / (2.0 * patch_size * correction));
+}
+
+// ------------------------------------------------------------------------------------------------
+// SparseImgAlign (src/sparse_img_align.cpp) on top of vk::NLLSSolver<6,SE3>
+// ------------------------------------------------------------------------------------------------
+constexpr int kTraceStride = 64;  // doubles per trace record
+// record: [0]=level [1]=iter [2]=new_chi2 [3]=n_meas [4]=accepted [5..40]=H [41..46]=Jres [47..52]=x [53..59]=T(model after)
+
+struct AlignOptions {
+  bool chi2_double = false;  // experiment switch: accumulate chi2 in double (NOT the reference behaviour)
+};
+
+struct SparseImgAlign {
+  // inputs of one pair
+  const plsvo_align_batch* B;
+  int b;
+  int n_pts, n_segs;
+  const double *pt_px, *pt_f, *pt_pos;
+  const uint8_t* pt_valid;
+  const double *seg_spx, *seg_epx, *seg_sf, *seg_ef, *seg_spos, *seg_epos, *seg_length;
+  std::vector<uint8_t> seg_alive;  // feat3D != NULL (mutated: sparse_img_align.cpp:687-688)
+  AlignOptions opt;
+
+  // solver state (vk::NLLSSolver members)
+  int n_iter_, n_iter_init_;
+  double eps_;
+  bool stop_ = false, use_weights_ = false;
+  double chi2_ = 1e10;
+  size_t n_meas_ = 0;
+  int iter_ = 0;
+  double H_[36], Jres_[6], x_[6];
+  int max_level_, min_level_, level_ = 0;
+  bool have_ref_patch_cache_ = false;
+  Vec3 ref_pos;
+
+  struct Cache {
+    std::vector<float> ref_patch;
+    std::vector<double> jacobian;  // 6 x (N*16), column major
+    std::vector<uint8_t> visible;
+  } pt_cache_, seg_cache_;
+  std::vector<size_t> patch_offset;
+
+  // accounting + trace
+  int iters_at_level[PLSVO_MAX_LEVELS] = {0};
+  uint32_t patch_iters = 0, patch_levels = 0;
+  double* trace = nullptr;
+  int trace_cap = 0, trace_n = 0;
+
+  Image level_image(const uint8_t* const* imgs, int level) const {
+    Image im;
+    im.data = imgs[level] + (size_t)b * B->img_stride[level];
+    im.cols = B->cam.width >> level;
+    im.rows = B->cam.height >> level;
+    im.stride = (int)B->img_pitch[level];
+    return im;
+  }
+  Vec3 world2cam_px(Vec3 p) const {  // vk::PinholeCamera::world2cam(xyz) without distortion
+    const double u = p.x / p.z, v = p.y / p.z;
+    return {B->cam.fx * u + B->cam.cx, B->cam.fy * v + B->cam.cy, 0};
+  }
+
+  // sparse_img_align.cpp:195-268
+  void precomputePoints() {
+    Patch patch(level_image(B->ref_img, level_));
+    const float scale = 1.0f / (1 << level_);
+    const double focal_length = std::fabs(B->cam.fx);  // errorMultiplier2()
+    for (int i = 0; i < n_pts; ++i) {
+      if (pt_valid && !pt_valid[i]) continue;
+      patch.setPosition(pt_px[2 * i] * scale, pt_px[2 * i + 1] * scale);
+      if (!patch.isInFrame(patch.halfsize + 1)) continue;
+      patch.computeInterpWeights();
+      patch.setRoi();
+      pt_cache_.visible[i] = 1;
+      ++patch_levels;
+      const Vec3 pos{pt_pos[3 * i], pt_pos[3 * i + 1], pt_pos[3 * i + 2]};
+      const double depth = norm(pos - ref_pos);
+      const Vec3 xyz_ref = Vec3{pt_f[3 * i], pt_f[3 * i + 1], pt_f[3 * i + 2]} * depth;
+      double frame_jac[2][6];
+      jacobian_xyz2uv(xyz_ref, frame_jac);
+      fill_patch(patch, &pt_cache_.ref_patch[(size_t)16 * i], &pt_cache_.jacobian[(size_t)6 * 16 * i], frame_jac,
+                 focal_length);
+    }
+  }
+  // the 16-pixel body shared by :243-264 and :354-375
+  void fill_patch(const Patch& patch, float* cache_ptr, double* jac_cols, const double frame_jac[2][6],
+                  double focal_length) const {
+    const int stride = patch.img.stride;
+    const double jscale = focal_length / (1 << level_);
+    for (int y = 0; y < 4; ++y) {
+      const uint8_t* img_ptr = patch.roi + (size_t)y * stride;
+      for (int x = 0; x < 4; ++x, ++img_ptr, ++cache_ptr, jac_cols += 6) {
+        *cache_ptr = patch.wTL * img_ptr[0] + patch.wTR * img_ptr[1] + patch.wBL * img_ptr[stride] +
+                     patch.wBR * img_ptr[stride + 1];
+        float dx = 0.5f * ((patch.wTL * img_ptr[1] + patch.wTR * img_ptr[2] + patch.wBL * img_ptr[stride + 1] +
+                            patch.wBR * img_ptr[stride + 2]) -
+                           (patch.wTL * img_ptr[-1] + patch.wTR * img_ptr[0] + patch.wBL * img_ptr[stride - 1] +
+                            patch.wBR * img_ptr[stride]));
+        float dy = 0.5f * ((patch.wTL * img_ptr[stride] + patch.wTR * img_ptr[1 + stride] +
+                            patch.wBL * img_ptr[stride * 2] + patch.wBR * img_ptr[stride * 2 + 1]) -
+                           (patch.wTL * img_ptr[-stride] + patch.wTR * img_ptr[1 - stride] + patch.wBL * img_ptr[0] +
+                            patch.wBR * img_ptr[1]));
+        for (int k = 0; k < 6; ++k) jac_cols[k] = (dx * frame_jac[0][k] + dy * frame_jac[1][k]) * jscale;
+      }
+    }
+  }
+
+  // sparse_img_align.cpp:270-378
+  void precomputeSegments() {
+    Patch patch(level_image(B->ref_img, level_));
+    const float scale = 1.0f / (1 << level_);
+    const double focal_length = std::fabs(B->cam.fx);
+    patch_offset.assign(n_segs, 0);
+    size_t cache_idx = 0;
+    for (int j = 0; j < n_segs; ++j) {
+      patch_offset[j] = cache_idx;
+      if (!seg_alive[j]) continue;
+      const double* spx = seg_spx + 2 * j;
+      const double* epx = seg_epx + 2 * j;
+      if (!cam_is_in_frame(B->cam, (int)(spx[0] * scale), (int)(spx[1] * scale), patch.halfsize + 1, level_) ||
+          !cam_is_in_frame(B->cam, (int)(epx[0] * scale), (int)(epx[1] * scale), patch.halfsize + 1, level_))
+        continue;
+      seg_cache_.visible[j] = 1;
+      double inc2d[2];
+      size_t N_samples = setup_sampling(patch.size, spx, epx, seg_length[j], inc2d);
+      N_samples = 1 + (N_samples - 1) / (1 << level_);
+      inc2d[0] = inc2d[0] * scale / (N_samples - 1);
+      inc2d[1] = inc2d[1] * scale / (N_samples - 1);
+      double px_ref[2] = {spx[0] * scale, spx[1] * scale};
+      const Vec3 spos{seg_spos[3 * j], seg_spos[3 * j + 1], seg_spos[3 * j + 2]};
+      const Vec3 epos{seg_epos[3 * j], seg_epos[3 * j + 1], seg_epos[3 * j + 2]};
+      const double p_depth = norm(spos - ref_pos);
+      const Vec3 p_ref = Vec3{seg_sf[3 * j], seg_sf[3 * j + 1], seg_sf[3 * j + 2]} * p_depth;
+      const double q_depth = norm(epos - ref_pos);
+      const Vec3 q_ref = Vec3{seg_ef[3 * j], seg_ef[3 * j + 1], seg_ef[3 * j + 2]} * q_depth;
+      const double nm1 = (double)(N_samples - 1);
+      const Vec3 d = q_ref - p_ref;
+      const Vec3 inc3d{d.x / nm1, d.y / nm1, d.z / nm1};
+      Vec3 xyz_ref = p_ref;
+      ensure_seg_capacity(cache_idx / 16 + N_samples);
+      for (unsigned sample = 0; sample < N_samples;
+           ++sample, px_ref[0] += inc2d[0], px_ref[1] += inc2d[1], xyz_ref = xyz_ref + inc3d) {
+        patch.setPosition(px_ref[0], px_ref[1]);
+        patch.computeInterpWeights();
+        patch.setRoi();
+        double frame_jac[2][6];
+        jacobian_xyz2uv(xyz_ref, frame_jac);
+        fill_patch(patch, &seg_cache_.ref_patch[cache_idx], &seg_cache_.jacobian[6 * cache_idx], frame_jac,
+                   focal_length);
+        cache_idx += 16;
+        ++patch_levels;
+      }
+    }
+  }
+  void ensure_seg_capacity(size_t n_patches) {
+    // The reference sizes the cache as ceil(total_length/4) patches (sparse_img_align.cpp:69-78)
+    // and never checks it; we grow instead of overflowing.
+    if (seg_cache_.ref_patch.size() < n_patches * 16) {
+      seg_cache_.ref_patch.resize(n_patches * 16, 0.f);
+      seg_cache_.jacobian.resize(n_patches * 16 * 6, 0.0);
+    }
+  }
+
+  // sparse_img_align.cpp:380-502  (linearize_system=true, compute_weight_scale=false, use_weights_=true)
+  void computePoints(const SE3& T_cur_from_ref, double H[36], double Jres[6], float& chi2, double& chi2d) {
+    Patch patch(level_image(B->cur_img, level_));
+    const float scale = 1.0f / (1 << level_);
+    chi2 = 0.0f;
+    chi2d = 0.0;
+    std::fill(H, H + 36, 0.0);
+    std::fill(Jres, Jres + 6, 0.0);
+    for (int i = 0; i < n_pts; ++i) {
+      if (!pt_cache_.visible[i]) continue;
+      const Vec3 pos{pt_pos[3 * i], pt_pos[3 * i + 1], pt_pos[3 * i + 2]};
+      const double depth = norm(pos - ref_pos);
+      const Vec3 xyz_ref = Vec3{pt_f[3 * i], pt_f[3 * i + 1], pt_f[3 * i + 2]} * depth;
+      const Vec3 xyz_cur = se3_act(T_cur_from_ref, xyz_ref);
+      const Vec3 uv = world2cam_px(xyz_cur);
+      patch.setPosition(uv.x * scale, uv.y * scale);
+      if (!patch.isInFrame(patch.halfsize)) continue;
+      patch.computeInterpWeights();
+      patch.setRoi();
+      ++patch_iters;
+      const float* cache_ptr = &pt_cache_.ref_patch[(size_t)16 * i];
+      const double* Jc = &pt_cache_.jacobian[(size_t)6 * 16 * i];
+      const int stride = patch.img.stride;
+      for (int y = 0; y < 4; ++y) {
+        const uint8_t* img_ptr = patch.roi + (size_t)y * stride;
+        for (int x = 0; x < 4; ++x, ++img_ptr, ++cache_ptr, Jc += 6) {
+          const float intensity_cur = patch.wTL * img_ptr[0] + patch.wTR * img_ptr[1] + patch.wBL * img_ptr[stride] +
+                                      patch.wBR * img_ptr[stride + 1];
+          const float res = intensity_cur - (*cache_ptr);
+          float weight = 1.0;
+          weight = 1.0 / (1.0 + fabsf(res));  // :479
+          chi2 += res * res * weight;         // :484
+          chi2d += (double)(res * res * weight);
+          n_meas_++;
+          for (int r = 0; r < 6; ++r) {
+            for (int c = 0; c < 6; ++c) H[r * 6 + c] += Jc[r] * Jc[c] * weight;  // :491
+            Jres[r] -= Jc[r] * res * weight;                                       // :492
+          }
+        }
+      }
+    }
+  }
+
+  // sparse_img_align.cpp:504-695
+  void computeSegments(const SE3& T_cur_from_ref, double H[36], double Jres[6], float& chi2, double& chi2d) {
+    Patch patch(level_image(B->cur_img, level_));
+    const float scale = 1.0f / (1 << level_);
+    chi2 = 0.0f;
+    chi2d = 0.0;
+    std::fill(H, H + 36, 0.0);
+    std::fill(Jres, Jres + 6, 0.0);
+    std::vector<float> ls_res;
+    for (int j = 0; j < n_segs; ++j) {
+      if (!seg_alive[j]) continue;
+      if (!seg_cache_.visible[j]) continue;
+      size_t cache_idx = patch_offset[j];
+      double inc2d[2];
+      size_t N_samples = setup_sampling(patch.size, seg_spx + 2 * j, seg_epx + 2 * j, seg_length[j], inc2d);
+      N_samples = 1 + (N_samples - 1) / (1 << level_);
+      const Vec3 spos{seg_spos[3 * j], seg_spos[3 * j + 1], seg_spos[3 * j + 2]};
+      const Vec3 epos{seg_epos[3 * j], seg_epos[3 * j + 1], seg_epos[3 * j + 2]};
+      const double p_depth = norm(spos - ref_pos);
+      const Vec3 p_ref = Vec3{seg_sf[3 * j], seg_sf[3 * j + 1], seg_sf[3 * j + 2]} * p_depth;
+      const double q_depth = norm(epos - ref_pos);
+      const Vec3 q_ref = Vec3{seg_ef[3 * j], seg_ef[3 * j + 1], seg_ef[3 * j + 2]} * q_depth;
+      const double nm1 = (double)(N_samples - 1);
+      const Vec3 d = q_ref - p_ref;
+      const Vec3 inc3d{d.x / nm1, d.y / nm1, d.z / nm1};
+      Vec3 xyz_ref = p_ref;
+      double Hs[36] = {0}, Js[6] = {0};
+      ls_res.clear();
+      bool good_line = true;
+      ensure_seg_capacity(cache_idx / 16 + N_samples + 1);
+      for (unsigned sample = 0; sample < N_samples; ++sample, xyz_ref = xyz_ref + inc3d) {
+        const Vec3 xyz_cur = se3_act(T_cur_from_ref, xyz_ref);
+        const Vec3 uv = world2cam_px(xyz_cur);
+        patch.setPosition(uv.x * scale, uv.y * scale);
+        if (!patch.isInFrame(patch.halfsize)) {
+          cache_idx += patch.size;
+          good_line = false;
+          sample = (unsigned)N_samples;
+          continue;
+        }
+        patch.computeInterpWeights();
+        patch.setRoi();
+        ++patch_iters;
+        const int stride = patch.img.stride;
+        for (int y = 0; y < 4; ++y) {
+          const uint8_t* img_ptr = patch.roi + (size_t)y * stride;
+          for (int x = 0; x < 4; ++x, ++img_ptr, ++cache_idx) {
+            const float intensity_cur = patch.wTL * img_ptr[0] + patch.wTR * img_ptr[1] +
+                                        patch.wBL * img_ptr[stride] + patch.wBR * img_ptr[stride + 1];
+            const float res = intensity_cur - seg_cache_.ref_patch[cache_idx];
+            ls_res.push_back(res);
+            const double* Jc = &seg_cache_.jacobian[6 * cache_idx];
+            for (int r = 0; r < 6; ++r) {
+              for (int c = 0; c < 6; ++c) Hs[r * 6 + c] += Jc[r] * Jc[c];  // :628
+              Js[r] -= Jc[r] * res;                                          // :629
+            }
+          }
+        }
+      }
+      float res_ = 0.0;
+      for (float r : ls_res) res_ += fabsf(r);
+      res_ = res_ / double(N_samples);  // :647
+      if (good_line && res_ < 200.0) {
+        float weight = 1.0;
+        weight = 1.0 / (1.0 + res_);  // :675
+        for (int k = 0; k < 36; ++k) H[k] += Hs[k] * weight / res_;  // :681
+        for (int k = 0; k < 6; ++k) Jres[k] += Js[k] * weight;        // :682
+        chi2 += res_ * res_ * weight;                                  // :683
+        chi2d += (double)(res_ * res_ * weight);
+        n_meas_++;
+      } else {
+        seg_alive[j] = 0;  // it->feat3D = NULL  (:688)
+      }
+    }
+  }
+
+  // sparse_img_align.cpp:112-193
+  double computeResiduals(const SE3& T_cur_from_ref) {
+    if (!have_ref_patch_cache_) {  // :126-127, :104-110
+      precomputePoints();
+      precomputeSegments();
+      have_ref_patch_cache_ = true;
+    }
+    use_weights_ = true;  // :132
+    double pt_H[36], pt_J[6], seg_H[36], seg_J[6];
+    float pt_chi2, seg_chi2;
+    double pt_chi2d, seg_chi2d;
+    computePoints(T_cur_from_ref, pt_H, pt_J, pt_chi2, pt_chi2d);
+    computeSegments(T_cur_from_ref, seg_H, seg_J, seg_chi2, seg_chi2d);
+    for (int k = 0; k < 36; ++k) H_[k] = pt_H[k] + seg_H[k];  // :167
+    for (int k = 0; k < 6; ++k) Jres_[k] = pt_J[k] + seg_J[k];
+    if (opt.chi2_double) return (double)((float)(pt_chi2d + seg_chi2d) / (float)n_meas_);
+    float chi2 = pt_chi2 + seg_chi2;  // :171
+    return chi2 / n_meas_;            // :192  (float / size_t -> float)
+  }
+
+  // vk::NLLSSolver<6,SE3>::optimizeGaussNewton + SparseImgAlign::solve/update (:697-710)
+  void optimize(SE3& model) {
+    if (use_weights_) {  // pre-pass: computeResiduals(model, false, true)
+      computeResiduals(model);
+    }
+    SE3 old_model = model;
+    for (iter_ = 0; iter_ < n_iter_; ++iter_) {
+      std::fill(H_, H_ + 36, 0.0);
+      std::fill(Jres_, Jres_ + 6, 0.0);
+      n_meas_ = 0;
+      const double new_chi2 = computeResiduals(model);
+      ++iters_at_level[level_];
+      solve6(H_, Jres_, x_);  // :699
+      if (std::isnan(x_[0])) stop_ = true;
+      const bool reject = (iter_ > 0 && new_chi2 > chi2_) || stop_;
+      if (trace && trace_n < trace_cap) {
+        double* r = trace + (size_t)trace_n * kTraceStride;
+        std::fill(r, r + kTraceStride, 0.0);
+        r[0] = level_, r[1] = iter_, r[2] = new_chi2, r[3] = (double)n_meas_, r[4] = reject ? 0 : 1;
+        std::copy(H_, H_ + 36, r + 5);
+        std::copy(Jres_, Jres_ + 6, r + 41);
+        std::copy(x_, x_ + 6, r + 47);
+      }
+      if (reject) {
+        model = old_model;
+        if (trace && trace_n < trace_cap) se3_to_pose7(model, trace + (size_t)trace_n++ * kTraceStride + 53);
+        break;
+      }
+      double mx[6];
+      for (int k = 0; k < 6; ++k) mx[k] = -x_[k];
+      const SE3 new_model = se3_mul(model, se3_exp(mx));  // :709
+      old_model = model;
+      model = new_model;
+      chi2_ = new_chi2;
+      if (trace && trace_n < trace_cap) se3_to_pose7(model, trace + (size_t)trace_n++ * kTraceStride + 53);
+      if (norm_max6(x_) <= eps_) break;
+    }
+  }
+
+  // sparse_img_align.cpp:54-95.  Returns n_meas_/16; writes T_cur_w.
+  size_t run(const plsvo_align_params& P, const SE3& T_ref_w, SE3& T_cur_w, int n_pts_list, int n_segs_list) {
+    // reset()
+    chi2_ = 1e10, n_meas_ = 0, iter_ = 0, stop_ = false;
+    n_iter_ = n_iter_init_ = P.n_iter;
+    eps_ = P.eps;
+    max_level_ = P.max_level, min_level_ = P.min_level;
+    std::fill(H_, H_ + 36, 0.0);
+    if (n_pts_list == 0 && n_segs_list == 0) return 0;  // :58-62
+    float total_length = 0;
+    for (int j = 0; j < n_segs; ++j) total_length += seg_length[j];  // :69-73
+    const int max_num_seg_samples = (int)std::ceil(total_length / 4);
+    pt_cache_.ref_patch.assign((size_t)n_pts * 16, 0.f);
+    pt_cache_.jacobian.assign((size_t)n_pts * 16 * 6, 0.0);
+    pt_cache_.visible.assign(n_pts, 0);
+    seg_cache_.ref_patch.assign((size_t)max_num_seg_samples * 16, 0.f);
+    seg_cache_.jacobian.assign((size_t)max_num_seg_samples * 16 * 6, 0.0);
+    seg_cache_.visible.assign(n_segs, 0);
+    ref_pos = se3_inverse(T_ref_w).t;                              // Frame::pos(), frame.h:131
+    SE3 T_cur_from_ref = se3_mul(T_cur_w, se3_inverse(T_ref_w));  // :80
+    for (level_ = max_level_; level_ >= min_level_; --level_) {
+      std::fill(pt_cache_.jacobian.begin(), pt_cache_.jacobian.end(), 0.0);   // :85
+      std::fill(seg_cache_.jacobian.begin(), seg_cache_.jacobian.end(), 0.0); // :86
+      have_ref_patch_cache_ = false;
+      optimize(T_cur_from_ref);  // :90
+    }
+    T_cur_w = se3_mul(T_cur_from_ref, T_ref_w);  // :92
+    return n_meas_ / 16;                         // :94
+  }
+};
+
+void align_one(const plsvo_align_batch* B, const plsvo_align_params* P, const plsvo_align_result* out, int b,
+               const AlignOptions& opt, double* trace, int trace_cap, int* trace_n) {
+  SparseImgAlign s;
+  s.B = B, s.b = b, s.opt = opt;
+  const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
+  const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
+  s.n_pts = np, s.n_segs = ns;
+  const size_t po = (size_t)b * B->n_pts, so = (size_t)b * B->n_segs;
+  s.pt_px = B->pt_px ? B->pt_px + 2 * po : nullptr;
+  s.pt_f = B->pt_f ? B->pt_f + 3 * po : nullptr;
+  s.pt_pos = B->pt_pos ? B->pt_pos + 3 * po : nullptr;
+  s.pt_valid = B->pt_valid ? B->pt_valid + po : nullptr;
+  s.seg_spx = B->seg_spx ? B->seg_spx + 2 * so : nullptr;
+  s.seg_epx = B->seg_epx ? B->seg_epx + 2 * so : nullptr;
+  s.seg_sf = B->seg_sf ? B->seg_sf + 3 * so : nullptr;
+  s.seg_ef = B->seg_ef ? B->seg_ef + 3 * so : nullptr;
+  s.seg_spos = B->seg_spos ? B->seg_spos + 3 * so : nullptr;
+  s.seg_epos = B->seg_epos ? B->seg_epos + 3 * so : nullptr;
+  s.seg_length = B->seg_length ? B->seg_length + so : nullptr;
+  s.seg_alive.assign(ns, 1);
+  if (B->seg_valid)
+    for (int j = 0; j < ns; ++j) s.seg_alive[j] = B->seg_valid[so + j] ? 1 : 0;
+  std::vector<uint8_t> alive0 = s.seg_alive;
+  s.trace = trace, s.trace_cap = trace_cap;
+
+  const SE3 T_ref_w = se3_from_pose7(B->T_ref_w + 7 * (size_t)b);
+  SE3 T_cur_w = se3_from_pose7(B->T_cur_w + 7 * (size_t)b);
+  const bool empty = (np == 0 && ns == 0);
+  const size_t n_tracked = s.run(*P, T_ref_w, T_cur_w, np, ns);
+  if (trace_n) *trace_n = s.trace_n;
+
+  if (out->T_cur_w) {
+    if (empty)  // early-out leaves cur_frame->T_f_w_ untouched
+      std::memcpy(out->T_cur_w + 7 * (size_t)b, B->T_cur_w + 7 * (size_t)b, 7 * sizeof(double));
+    else
+      se3_to_pose7(T_cur_w, out->T_cur_w + 7 * (size_t)b);
+  }
+  if (out->n_tracked) out->n_tracked[b] = (int64_t)n_tracked;
+  if (out->H) std::memcpy(out->H + 36 * (size_t)b, s.H_, 36 * sizeof(double));
+  if (out->seg_killed) {
+    for (int j = 0; j < B->n_segs; ++j) out->seg_killed[so + j] = 0;
+    for (int j = 0; j < ns; ++j) out->seg_killed[so + j] = (alive0[j] && !s.seg_alive[j]) ? 1 : 0;
+  }
+  if (out->iters)
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) out->iters[(size_t)b * PLSVO_MAX_LEVELS + l] = s.iters_at_level[l];
+  if (out->status) out->status[b] = (empty ? 1 : 0) | (s.stop_ ? 2 : 0);
+  if (out->patch_iters) out->patch_iters[b] = s.patch_iters;
+  if (out->patch_levels) out->patch_levels[b] = s.patch_levels;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose_optimizer::optimizeGaussNewton — src/pose_optimizer.cpp:38-260 and :262-582
+// ------------------------------------------------------------------------------------------------
+inline void project2d(Vec3 p, double uv[2]) {  // vk::project2d
+  uv[0] = p.x / p.z;
+  uv[1] = p.y / p.z;
+}
+
+void poseopt_one(const plsvo_poseopt_batch* B, const plsvo_poseopt_params* P, const plsvo_poseopt_result* out, int b) {
+  const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
+  const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
+  const size_t po = (size_t)b * B->n_pts, so = (size_t)b * B->n_segs;
+  const double* pt_f = B->pt_f + 3 * po;
+  const double* pt_pos = B->pt_pos + 3 * po;
+  const int32_t* pt_level = B->pt_level + po;
+  const double* seg_line = B->seg_line ? B->seg_line + 3 * so : nullptr;
+  const double* seg_spos = B->seg_spos ? B->seg_spos + 3 * so : nullptr;
+  const double* seg_epos = B->seg_epos ? B->seg_epos + 3 * so : nullptr;
+  const int32_t* seg_level = B->seg_level ? B->seg_level + so : nullptr;
+  std::vector<uint8_t> pt_alive(np, 1), seg_alive(ns, 1);
+  if (B->pt_valid)
+    for (int i = 0; i < np; ++i) pt_alive[i] = B->pt_valid[po + i] ? 1 : 0;
+  if (B->seg_valid)
+    for (int j = 0; j < ns; ++j) seg_alive[j] = B->seg_valid[so + j] ? 1 : 0;
+  const std::vector<uint8_t> pt_alive0 = pt_alive, seg_alive0 = seg_alive;
+  const double fx = B->fx;
+  SE3 T = se3_from_pose7(B->T_f_w + 7 * (size_t)b);
+
+  if (out->iters) out->iters[2 * (size_t)b] = out->iters[2 * (size_t)b + 1] = 0;
+  if (out->pt_outlier) std::memset(out->pt_outlier + po, 0, B->n_pts);
+  if (out->seg_outlier && B->n_segs) std::memset(out->seg_outlier + so, 0, B->n_segs);
+
+  double chi2 = 0.0;
+  std::vector<double> chi2_vec_init, chi2_vec_final;
+  SE3 T_old = T;
+  double A[36], bvec[6];
+
+  // :58-71 MAD scale on point errors
+  std::vector<float> errors;
+  errors.reserve(np + ns);
+  for (int i = 0; i < np; ++i) {
+    if (!pt_alive[i]) continue;
+    double uvf[2], uvp[2];
+    project2d({pt_f[3 * i], pt_f[3 * i + 1], pt_f[3 * i + 2]}, uvf);
+    project2d(se3_act(T, {pt_pos[3 * i], pt_pos[3 * i + 1], pt_pos[3 * i + 2]}), uvp);
+    double e[2] = {uvf[0] - uvp[0], uvf[1] - uvp[1]};
+    const double s = 1.0 / (1 << pt_level[i]);
+    e[0] *= s, e[1] *= s;
+    errors.push_back((float)std::sqrt(e[0] * e[0] + e[1] * e[1]));
+  }
+  // NOTE: the reference calls getMedian on an empty vector (UB) when there are no valid points but
+  // there are lines; we define that case as scale 0 (the assert in vk::getMedian would fire).
+  double estimated_scale_pt = errors.empty() ? 0.0 : (double)mad_scale(errors);
+  size_t num_obs_pt = errors.size();
+  // :73-87
+  std::vector<float> errors_ls;
+  for (int j = 0; j < ns; ++j) {
+    if (!seg_alive[j]) continue;
+    double s2[2], e2[2];
+    project2d(se3_act(T, {seg_spos[3 * j], seg_spos[3 * j + 1], seg_spos[3 * j + 2]}), s2);
+    project2d(se3_act(T, {seg_epos[3 * j], seg_epos[3 * j + 1], seg_epos[3 * j + 2]}), e2);
+    const double* l = seg_line + 3 * j;
+    float es = (float)(l[0] * s2[0] + l[1] * s2[1] + l[2] * 1.0);
+    float ee = (float)(l[0] * e2[0] + l[1] * e2[1] + l[2] * 1.0);
+    errors.push_back(std::sqrt(es * es + ee * ee));
+    errors_ls.push_back(std::sqrt(es * es + ee * ee));
+  }
+  if (errors.empty()) {  // :88-89: return with outputs untouched
+    if (out->status) out->status[b] = 1;
+    if (out->T_f_w) std::memcpy(out->T_f_w + 7 * (size_t)b, B->T_f_w + 7 * (size_t)b, 7 * sizeof(double));
+    return;
+  }
+  if (out->status) out->status[b] = 0;
+  size_t num_obs_ls = errors_ls.size();
+  double estimated_scale_ls = 1.f;
+  if (!errors_ls.empty()) estimated_scale_ls = mad_scale(errors_ls);
+  double estimated_scale = estimated_scale_pt;
+  const double scale_pt = estimated_scale_pt, scale_ls = estimated_scale_ls;
+
+  // one GN loop (:103-195 and, for the 10-arg overload, :473-563)
+  auto gn_loop = [&](size_t n_iter, int which) {
+    for (size_t iter = 0; iter < n_iter; iter++) {
+      std::fill(A, A + 36, 0.0);
+      std::fill(bvec, bvec + 6, 0.0);
+      double new_chi2 = 0.0;
+      for (int i = 0; i < np; ++i) {
+        if (!pt_alive[i]) continue;
+        double J[2][6];
+        const Vec3 xyz_f = se3_act(T, {pt_pos[3 * i], pt_pos[3 * i + 1], pt_pos[3 * i + 2]});
+        jacobian_xyz2uv(xyz_f, J);
+        double uvf[2], uvp[2];
+        project2d({pt_f[3 * i], pt_f[3 * i + 1], pt_f[3 * i + 2]}, uvf);
+        project2d(xyz_f, uvp);
+        double e[2] = {uvf[0] - uvp[0], uvf[1] - uvp[1]};
+        const double sqrt_inv_cov = 1.0 / (1 << pt_level[i]);
+        e[0] *= sqrt_inv_cov, e[1] *= sqrt_inv_cov;
+        const double e_sq = e[0] * e[0] + e[1] * e[1];
+        if (iter == 0) chi2_vec_init.push_back(e_sq);
+        for (int k = 0; k < 6; ++k) J[0][k] *= sqrt_inv_cov, J[1][k] *= sqrt_inv_cov;
+        const double weight = tukey_value((float)(std::sqrt(e_sq) / scale_pt));
+        for (int r = 0; r < 6; ++r) {
+          for (int c = 0; c < 6; ++c) A[r * 6 + c] += (J[0][r] * J[0][c] + J[1][r] * J[1][c]) * weight;
+          bvec[r] -= (J[0][r] * e[0] + J[1][r] * e[1]) * weight;
+        }
+        new_chi2 += e_sq * weight;
+      }
+      for (int j = 0; j < ns; ++j) {
+        if (!seg_alive[j]) continue;
+        double J_s[2][6], J_e[2][6], J[2][6];
+        const Vec3 xyz_f_s = se3_act(T, {seg_spos[3 * j], seg_spos[3 * j + 1], seg_spos[3 * j + 2]});
+        const Vec3 xyz_f_e = se3_act(T, {seg_epos[3 * j], seg_epos[3 * j + 1], seg_epos[3 * j + 2]});
+        jacobian_xyz2uv(xyz_f_s, J_s);
+        jacobian_xyz2uv(xyz_f_e, J_e);
+        double s2[2], e2[2];
+        project2d(xyz_f_s, s2);
+        project2d(xyz_f_e, e2);
+        const double* l = seg_line + 3 * j;
+        const float ds = (float)(l[0] * s2[0] + l[1] * s2[1] + l[2] * 1.0);
+        const float de = (float)(l[0] * e2[0] + l[1] * e2[1] + l[2] * 1.0);
+        double e[2] = {ds, de};
+        const double sqrt_inv_cov = 1.0 / (1 << seg_level[j]);
+        e[0] *= sqrt_inv_cov, e[1] *= sqrt_inv_cov;
+        const double e_sq = e[0] * e[0] + e[1] * e[1];
+        if (iter == 0) chi2_vec_init.push_back(e_sq);
+        const double e_norm = std::sqrt(e_sq);
+        const double js = sqrt_inv_cov * ds / e_norm;  // :157-158: ds for BOTH endpoints [sic]
+        for (int k = 0; k < 6; ++k) {
+          J_s[0][k] *= js, J_s[1][k] *= js;
+          J_e[0][k] *= js, J_e[1][k] *= js;
+        }
+        for (int k = 0; k < 6; ++k) {
+          J[0][k] = l[0] * J_s[0][k] + l[1] * J_s[1][k];
+          J[1][k] = l[0] * J_e[0][k] + l[1] * J_e[1][k];
+        }
+        const double weight = tukey_value((float)(e_norm / scale_ls));
+        for (int r = 0; r < 6; ++r) {
+          for (int c = 0; c < 6; ++c) A[r * 6 + c] += (J[0][r] * J[0][c] + J[1][r] * J[1][c]) * weight;
+          bvec[r] -= (J[0][r] * e[0] + J[1][r] * e[1]) * weight;
+        }
+        new_chi2 += e_sq * weight;
+      }
+      double dT[6];
+      solve6(A, bvec, dT);
+      if (out->iters) out->iters[2 * (size_t)b + which] += 1;
+      if ((iter > 0 && new_chi2 > chi2) || std::isnan(dT[0])) {
+        T = T_old;
+        break;
+      }
+      const SE3 T_new = se3_mul(se3_exp(dT), T);
+      T_old = T;
+      T = T_new;
+      chi2 = new_chi2;
+      if (norm_max6(dT) <= 0.0000000001) break;  // EPS, global.h:99
+    }
+  };
+
+  gn_loop((size_t)P->n_iter, 0);
+
+  // :197-199 covariance from the last evaluated A
+  double Afx[36], cov[36];
+  const double fx2 = std::pow(fx, 2);
+  for (int k = 0; k < 36; ++k) Afx[k] = A[k] * fx2;
+  inverse6(Afx, cov);
+
+  // :201-242 outlier removal at the final pose
+  const double reproj_thresh_scaled_pt = P->reproj_thresh / fx;
+  const double reproj_thresh_scaled_ls = reproj_thresh_scaled_pt * estimated_scale_ls / estimated_scale_pt;
+  size_t n_deleted_refs_pt = 0, n_deleted_refs_ls = 0;
+  for (int i = 0; i < np; ++i) {
+    if (!pt_alive[i]) continue;
+    double uvf[2], uvp[2];
+    project2d({pt_f[3 * i], pt_f[3 * i + 1], pt_f[3 * i + 2]}, uvf);
+    project2d(se3_act(T, {pt_pos[3 * i], pt_pos[3 * i + 1], pt_pos[3 * i + 2]}), uvp);
+    double e[2] = {uvf[0] - uvp[0], uvf[1] - uvp[1]};
+    const double s = 1.0 / (1 << pt_level[i]);
+    e[0] *= s, e[1] *= s;
+    const double e_sq = e[0] * e[0] + e[1] * e[1];
+    chi2_vec_final.push_back(e_sq);
+    if (std::sqrt(e_sq) > reproj_thresh_scaled_pt) {
+      pt_alive[i] = 0;
+      ++n_deleted_refs_pt;
+    }
+  }
+  for (int j = 0; j < ns; ++j) {
+    if (!seg_alive[j]) continue;
+    double s2[2], e2[2];
+    project2d(se3_act(T, {seg_spos[3 * j], seg_spos[3 * j + 1], seg_spos[3 * j + 2]}), s2);
+    project2d(se3_act(T, {seg_epos[3 * j], seg_epos[3 * j + 1], seg_epos[3 * j + 2]}), e2);
+    const double* l = seg_line + 3 * j;
+    double e[2] = {l[0] * s2[0] + l[1] * s2[1] + l[2] * 1.0, l[0] * e2[0] + l[1] * e2[1] + l[2] * 1.0};
+    const double s = 1.0 / (1 << seg_level[j]);
+    e[0] *= s, e[1] *= s;
+    const double e_sq = e[0] * e[0] + e[1] * e[1];
+    chi2_vec_final.push_back(e_sq);
+    if (std::sqrt(e_sq) > reproj_thresh_scaled_ls) {
+      seg_alive[j] = 0;
+      ++n_deleted_refs_ls;
+    }
+  }
+
+  if (P->n_iter_ref >= 0) gn_loop((size_t)P->n_iter_ref, 1);  // :469-563 refinement with inliers
+
+  double error_init = 0.0, error_final = 0.0;
+  if (!chi2_vec_init.empty()) error_init = std::sqrt(get_median(chi2_vec_init)) * fx;
+  if (!chi2_vec_final.empty()) error_final = std::sqrt(get_median(chi2_vec_final)) * fx;
+  estimated_scale *= fx;
+  num_obs_pt -= n_deleted_refs_pt;
+  num_obs_ls -= n_deleted_refs_ls;
+
+  if (out->T_f_w) se3_to_pose7(T, out->T_f_w + 7 * (size_t)b);
+  if (out->cov) std::memcpy(out->cov + 36 * (size_t)b, cov, sizeof(cov));
+  if (out->estimated_scale) out->estimated_scale[b] = estimated_scale;
+  if (out->error_init) out->error_init[b] = error_init;
+  if (out->error_final) out->error_final[b] = error_final;
+  if (out->num_obs_pt) out->num_obs_pt[b] = (int64_t)num_obs_pt;
+  if (out->num_obs_ls) out->num_obs_ls[b] = (int64_t)num_obs_ls;
+  if (out->pt_outlier)
+    for (int i = 0; i < np; ++i) out->pt_outlier[po + i] = (pt_alive0[i] && !pt_alive[i]) ? 1 : 0;
+  if (out->seg_outlier)
+    for (int j = 0; j < ns; ++j) out->seg_outlier[so + j] = (seg_alive0[j] && !seg_alive[j]) ? 1 : 0;
+}
+
+template <class F>
+void parallel_for(int n, int n_threads, F f) {
+  if (n_threads <= 1 || n <= 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  std::vector<std::thread> pool;
+  const int nt = std::min(n_threads, n);
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([&] {
+      for (int i; (i = next.fetch_add(1)) < n;) f(i);
+    });
+  for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+// flags: bit0 = accumulate chi2 in double (experiment; NOT the reference behaviour)
+int plsvo_oracle_align_batch(const plsvo_align_batch* batch, const plsvo_align_params* params,
+                             const plsvo_align_result* out, int n_threads, int flags) {
+  if (!batch || !params || !out) return PLSVO_ERR_INVALID;
+  if (params->max_level < params->min_level || params->min_level < 0 || params->max_level >= PLSVO_MAX_LEVELS)
+    return PLSVO_ERR_INVALID;
+  AlignOptions opt;
+  opt.chi2_double = (flags & 1) != 0;
+  parallel_for(batch->batch, n_threads, [&](int b) { align_one(batch, params, out, b, opt, nullptr, 0, nullptr); });
+  return PLSVO_OK;
+}
+
+// Per-iteration trace of one pair: records of plsvo_oracle_trace_stride() doubles, laid out
+// [level, iter, new_chi2, n_meas, accepted, H(36), Jres(6), x(6), T_cur_from_ref after the step(7)].
+int plsvo_oracle_trace_stride(void) { return kTraceStride; }
+int plsvo_oracle_align_trace(const plsvo_align_batch* batch, const plsvo_align_params* params, int pair,
+                             double* records, int max_records, int* n_records) {
+  if (!batch || !params || pair < 0 || pair >= batch->batch) return PLSVO_ERR_INVALID;
+  plsvo_align_result out;
+  std::memset(&out, 0, sizeof(out));
+  align_one(batch, params, &out, pair, AlignOptions{}, records, max_records, n_records);
+  return PLSVO_OK;
+}
+
+int plsvo_oracle_poseopt_batch(const plsvo_poseopt_batch* batch, const plsvo_poseopt_params* params,
+                               const plsvo_poseopt_result* out, int n_threads) {
+  if (!batch || !params || !out) return PLSVO_ERR_INVALID;
+  parallel_for(batch->batch, n_threads, [&](int b) { poseopt_one(batch, params, out, b); });
+  return PLSVO_OK;
+}
+
+// SE3 helpers exposed so tests can pin the Sophus restatement against closed forms.
+void plsvo_oracle_se3_exp(const double* xi6, double* pose7) { se3_to_pose7(se3_exp(xi6), pose7); }
+void plsvo_oracle_se3_mul(const double* a7, const double* b7, double* out7) {
+  se3_to_pose7(se3_mul(se3_from_pose7(a7), se3_from_pose7(b7)), out7);
+}
+void plsvo_oracle_se3_inverse(const double* a7, double* out7) { se3_to_pose7(se3_inverse(se3_from_pose7(a7)), out7); }
+void plsvo_oracle_solve6(const double* A36, const double* b6, double* x6) { solve6(A36, b6, x6); }
+void plsvo_oracle_inverse6(const double* A36, double* out36) { inverse6(A36, out36); }
+
+int plsvo_oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+}

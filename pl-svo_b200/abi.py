@@ -1,0 +1,324 @@
+"""ctypes mirror of include/plsvo_b200.h and the loader of the CUDA library.
+
+There is no CPU fallback: `load_library()` raises if libplsvo_b200.so has not been built, and
+every entry point of the library itself returns PLSVO_ERR_NO_DEVICE without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_LEVELS = 8
+PATCH_AREA = 16
+
+OK = 0
+ERR_INVALID = -1
+ERR_CUDA = -2
+ERR_NO_DEVICE = -3
+ERR_STATE = -4
+
+_u8p = C.POINTER(C.c_uint8)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("reserved1", C.c_int32),
+        ("fx", C.c_double),
+        ("fy", C.c_double),
+        ("cx", C.c_double),
+        ("cy", C.c_double),
+    ]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [
+        ("max_level", C.c_int32),
+        ("min_level", C.c_int32),
+        ("n_iter", C.c_int32),
+        ("reserved", C.c_int32),
+        ("eps", C.c_double),
+    ]
+
+
+class AlignBatch(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("n_pts", C.c_int32),
+        ("n_segs", C.c_int32),
+        ("reserved", C.c_int32),
+        ("cam", Camera),
+        ("ref_img", _u8p * MAX_LEVELS),
+        ("cur_img", _u8p * MAX_LEVELS),
+        ("img_pitch", C.c_size_t * MAX_LEVELS),
+        ("img_stride", C.c_size_t * MAX_LEVELS),
+        ("T_ref_w", _f64p),
+        ("T_cur_w", _f64p),
+        ("pt_count", _i32p),
+        ("pt_px", _f64p),
+        ("pt_f", _f64p),
+        ("pt_pos", _f64p),
+        ("pt_valid", _u8p),
+        ("seg_count", _i32p),
+        ("seg_spx", _f64p),
+        ("seg_epx", _f64p),
+        ("seg_sf", _f64p),
+        ("seg_ef", _f64p),
+        ("seg_spos", _f64p),
+        ("seg_epos", _f64p),
+        ("seg_length", _f64p),
+        ("seg_valid", _u8p),
+    ]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [
+        ("T_cur_w", _f64p),
+        ("n_tracked", _i64p),
+        ("H", _f64p),
+        ("seg_killed", _u8p),
+        ("iters", _i32p),
+        ("status", _i32p),
+        ("patch_iters", _u32p),
+        ("patch_levels", _u32p),
+    ]
+
+
+class PoseOptParams(C.Structure):
+    _fields_ = [("reproj_thresh", C.c_double), ("n_iter", C.c_int32), ("n_iter_ref", C.c_int32)]
+
+
+class PoseOptBatch(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("n_pts", C.c_int32),
+        ("n_segs", C.c_int32),
+        ("reserved", C.c_int32),
+        ("fx", C.c_double),
+        ("T_f_w", _f64p),
+        ("pt_count", _i32p),
+        ("pt_f", _f64p),
+        ("pt_pos", _f64p),
+        ("pt_level", _i32p),
+        ("pt_valid", _u8p),
+        ("seg_count", _i32p),
+        ("seg_line", _f64p),
+        ("seg_spos", _f64p),
+        ("seg_epos", _f64p),
+        ("seg_level", _i32p),
+        ("seg_valid", _u8p),
+    ]
+
+
+class PoseOptResult(C.Structure):
+    _fields_ = [
+        ("T_f_w", _f64p),
+        ("cov", _f64p),
+        ("estimated_scale", _f64p),
+        ("error_init", _f64p),
+        ("error_final", _f64p),
+        ("num_obs_pt", _i64p),
+        ("num_obs_ls", _i64p),
+        ("pt_outlier", _u8p),
+        ("seg_outlier", _u8p),
+        ("iters", _i32p),
+        ("status", _i32p),
+    ]
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy <-> struct helpers
+# ------------------------------------------------------------------------------------------------
+
+_CT = {np.dtype(np.uint8): _u8p, np.dtype(np.float64): _f64p, np.dtype(np.int32): _i32p,
+       np.dtype(np.int64): _i64p, np.dtype(np.uint32): _u32p}
+
+
+def _ptr(a, dtype):
+    """Pointer to a C-contiguous numpy array of `dtype`, or NULL for None."""
+    if a is None:
+        return _CT[np.dtype(dtype)]()
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous:
+        raise TypeError(f"expected C-contiguous {np.dtype(dtype)} array, got {type(a)} {getattr(a, 'dtype', None)}")
+    return a.ctypes.data_as(_CT[np.dtype(dtype)])
+
+
+def align_params(max_level=4, min_level=2, n_iter=30, eps=1e-6) -> AlignParams:
+    return AlignParams(max_level, min_level, n_iter, 0, eps)
+
+
+def poseopt_params(reproj_thresh=2.0, n_iter=10, n_iter_ref=-1) -> PoseOptParams:
+    return PoseOptParams(reproj_thresh, n_iter, n_iter_ref)
+
+
+def make_align_batch(d):
+    """Build a plsvo_align_batch from an AlignData-like object.  Returns (struct, keepalive)."""
+    b = AlignBatch()
+    keep = [d]
+    b.batch, b.n_pts, b.n_segs = d.batch, d.n_pts, d.n_segs
+    cam = d.cam
+    b.cam = Camera(cam.width, cam.height, 0, 0, cam.fx, cam.fy, cam.cx, cam.cy)
+    for l in range(MAX_LEVELS):
+        if l in d.ref_pyr:
+            r, c = d.ref_pyr[l], d.cur_pyr[l]
+            assert r.dtype == np.uint8 and r.ndim == 3 and r.shape == c.shape
+            assert r.strides[2] == 1 and c.strides == r.strides
+            b.ref_img[l] = r.ctypes.data_as(_u8p)
+            b.cur_img[l] = c.ctypes.data_as(_u8p)
+            b.img_pitch[l] = r.strides[1]
+            b.img_stride[l] = r.strides[0]
+    b.T_ref_w = _ptr(d.T_ref_w, np.float64)
+    b.T_cur_w = _ptr(d.T_cur_w, np.float64)
+    b.pt_count = _ptr(d.pt_count, np.int32)
+    b.pt_px = _ptr(d.pt_px, np.float64)
+    b.pt_f = _ptr(d.pt_f, np.float64)
+    b.pt_pos = _ptr(d.pt_pos, np.float64)
+    b.pt_valid = _ptr(d.pt_valid, np.uint8)
+    b.seg_count = _ptr(d.seg_count, np.int32)
+    if d.n_segs > 0:
+        b.seg_spx = _ptr(d.seg_spx, np.float64)
+        b.seg_epx = _ptr(d.seg_epx, np.float64)
+        b.seg_sf = _ptr(d.seg_sf, np.float64)
+        b.seg_ef = _ptr(d.seg_ef, np.float64)
+        b.seg_spos = _ptr(d.seg_spos, np.float64)
+        b.seg_epos = _ptr(d.seg_epos, np.float64)
+        b.seg_length = _ptr(d.seg_length, np.float64)
+        b.seg_valid = _ptr(d.seg_valid, np.uint8)
+    return b, keep
+
+
+class AlignOut:
+    """Owns the output arrays of one alignment batch and the plsvo_align_result pointing at them."""
+
+    def __init__(self, batch: int, n_segs: int):
+        self.T_cur_w = np.zeros((batch, 7))
+        self.n_tracked = np.zeros(batch, np.int64)
+        self.H = np.zeros((batch, 36))
+        self.seg_killed = np.zeros((batch, max(n_segs, 1)), np.uint8)
+        self.iters = np.zeros((batch, MAX_LEVELS), np.int32)
+        self.status = np.zeros(batch, np.int32)
+        self.patch_iters = np.zeros(batch, np.uint32)
+        self.patch_levels = np.zeros(batch, np.uint32)
+        r = AlignResult()
+        r.T_cur_w = _ptr(self.T_cur_w, np.float64)
+        r.n_tracked = _ptr(self.n_tracked, np.int64)
+        r.H = _ptr(self.H, np.float64)
+        r.seg_killed = _ptr(self.seg_killed, np.uint8) if n_segs > 0 else _u8p()
+        r.iters = _ptr(self.iters, np.int32)
+        r.status = _ptr(self.status, np.int32)
+        r.patch_iters = _ptr(self.patch_iters, np.uint32)
+        r.patch_levels = _ptr(self.patch_levels, np.uint32)
+        self.struct = r
+        if n_segs == 0:
+            self.seg_killed = self.seg_killed[:, :0]
+
+
+def make_poseopt_batch(d):
+    b = PoseOptBatch()
+    b.batch, b.n_pts, b.n_segs = d.batch, d.n_pts, d.n_segs
+    b.fx = d.fx
+    b.T_f_w = _ptr(d.T_f_w, np.float64)
+    b.pt_count = _ptr(d.pt_count, np.int32)
+    b.pt_f = _ptr(d.pt_f, np.float64)
+    b.pt_pos = _ptr(d.pt_pos, np.float64)
+    b.pt_level = _ptr(d.pt_level, np.int32)
+    b.pt_valid = _ptr(d.pt_valid, np.uint8)
+    b.seg_count = _ptr(d.seg_count, np.int32)
+    if d.n_segs > 0:
+        b.seg_line = _ptr(d.seg_line, np.float64)
+        b.seg_spos = _ptr(d.seg_spos, np.float64)
+        b.seg_epos = _ptr(d.seg_epos, np.float64)
+        b.seg_level = _ptr(d.seg_level, np.int32)
+        b.seg_valid = _ptr(d.seg_valid, np.uint8)
+    return b, [d]
+
+
+class PoseOptOut:
+    def __init__(self, batch: int, n_pts: int, n_segs: int):
+        self.T_f_w = np.zeros((batch, 7))
+        self.cov = np.zeros((batch, 36))
+        self.estimated_scale = np.zeros(batch)
+        self.error_init = np.zeros(batch)
+        self.error_final = np.zeros(batch)
+        self.num_obs_pt = np.zeros(batch, np.int64)
+        self.num_obs_ls = np.zeros(batch, np.int64)
+        self.pt_outlier = np.zeros((batch, max(n_pts, 1)), np.uint8)
+        self.seg_outlier = np.zeros((batch, max(n_segs, 1)), np.uint8)
+        self.iters = np.zeros((batch, 2), np.int32)
+        self.status = np.zeros(batch, np.int32)
+        r = PoseOptResult()
+        r.T_f_w = _ptr(self.T_f_w, np.float64)
+        r.cov = _ptr(self.cov, np.float64)
+        r.estimated_scale = _ptr(self.estimated_scale, np.float64)
+        r.error_init = _ptr(self.error_init, np.float64)
+        r.error_final = _ptr(self.error_final, np.float64)
+        r.num_obs_pt = _ptr(self.num_obs_pt, np.int64)
+        r.num_obs_ls = _ptr(self.num_obs_ls, np.int64)
+        r.pt_outlier = _ptr(self.pt_outlier, np.uint8)
+        r.seg_outlier = _ptr(self.seg_outlier, np.uint8) if n_segs > 0 else _u8p()
+        r.iters = _ptr(self.iters, np.int32)
+        r.status = _ptr(self.status, np.int32)
+        self.struct = r
+        if n_segs == 0:
+            self.seg_outlier = self.seg_outlier[:, :0]
+
+
+# ------------------------------------------------------------------------------------------------
+# library loading
+# ------------------------------------------------------------------------------------------------
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libplsvo_b200.so")
+
+# every symbol include/plsvo_b200.h declares: (name, restype, argtypes)
+_P = C.POINTER
+ABI_SYMBOLS = [
+    ("plsvo_ctx_create", C.c_int, [C.c_int, C.c_void_p, _P(C.c_void_p)]),
+    ("plsvo_ctx_destroy", None, [C.c_void_p]),
+    ("plsvo_last_error", C.c_char_p, [C.c_void_p]),
+    ("plsvo_ctx_stream", C.c_void_p, [C.c_void_p]),
+    ("plsvo_sync", C.c_int, [C.c_void_p]),
+    ("plsvo_host_alloc", C.c_int, [_P(C.c_void_p), C.c_size_t]),
+    ("plsvo_host_free", C.c_int, [C.c_void_p]),
+    ("plsvo_align_upload", C.c_int, [C.c_void_p, _P(AlignBatch)]),
+    ("plsvo_align_launch", C.c_int, [C.c_void_p, _P(AlignParams)]),
+    ("plsvo_align_download", C.c_int, [C.c_void_p, _P(AlignResult)]),
+    ("plsvo_align_batch_run", C.c_int, [C.c_void_p, _P(AlignBatch), _P(AlignParams), _P(AlignResult)]),
+    ("plsvo_poseopt_upload", C.c_int, [C.c_void_p, _P(PoseOptBatch)]),
+    ("plsvo_poseopt_launch", C.c_int, [C.c_void_p, _P(PoseOptParams)]),
+    ("plsvo_poseopt_download", C.c_int, [C.c_void_p, _P(PoseOptResult)]),
+    ("plsvo_poseopt_batch_run", C.c_int, [C.c_void_p, _P(PoseOptBatch), _P(PoseOptParams), _P(PoseOptResult)]),
+    ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
+    ("plsvo_version", C.c_char_p, []),
+]
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen libplsvo_b200.so and type every ABI symbol.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: the CUDA extension has not been built (run `python __graft_entry__.py build`). "
+            "There is no CPU fallback for the PL-SVO hot path."
+        )
+    lib = C.CDLL(p)
+    for name, res, args in ABI_SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib

@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+The reference's boundary is two C++ symbols:
+
+    plsvo::SparseImgAlign(max_level, min_level, n_iter, method, display, verbose).run(ref, cur)
+        include/plsvo/sparse_img_align.h:56-70, src/sparse_img_align.cpp:40-95
+    plsvo::pose_optimizer::optimizeGaussNewton(reproj_thresh, n_iter[, n_iter_ref], verbose, frame, ...)
+        include/plsvo/pose_optimizer.h:47-64
+
+This module keeps the same names and argument meaning for *batches* of frame pairs / frames held
+in flat arrays (synth.AlignData / synth.PoseOptData).  The C++ shim that keeps the exact
+FramePtr signatures lives in pl-svo_b200/host/.  All compute happens in libplsvo_b200.so on
+the GPU; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import abi
+
+
+class PlsvoError(RuntimeError):
+    pass
+
+
+class Context:
+    """A device context (plsvo_ctx): one CUDA device + stream + reusable device buffers."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.plsvo_ctx_create(device, C.c_void_p(stream or 0), C.byref(h))
+        if rc != abi.OK:
+            msg = self.lib.plsvo_last_error(None)
+            raise PlsvoError(f"plsvo_ctx_create failed rc={rc}: {msg.decode() if msg else ''}")
+        self.handle = h
+
+    def check(self, rc: int, what: str):
+        if rc != abi.OK:
+            msg = self.lib.plsvo_last_error(self.handle)
+            raise PlsvoError(f"{what} failed rc={rc}: {msg.decode() if msg else ''}")
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.plsvo_ctx_stream(self.handle) or 0)
+
+    def sync(self):
+        self.check(self.lib.plsvo_sync(self.handle), "plsvo_sync")
+
+    def launch_count(self) -> int:
+        return int(self.lib.plsvo_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.plsvo_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class SparseImgAlign:
+    """Batched counterpart of plsvo::SparseImgAlign (src/sparse_img_align.cpp:40-52)."""
+
+    GaussNewton = 0
+    LevenbergMarquardt = 1  # accepted for signature parity; the reference only ever passes GaussNewton
+
+    def __init__(self, max_level: int, min_level: int, n_iter: int, method: int = 0,
+                 display: bool = False, verbose: bool = False, ctx: Context | None = None, eps: float = 1e-6):
+        if method != self.GaussNewton:
+            raise PlsvoError("only Method::GaussNewton is on the hot path (frame_handler_mono.cpp:272-273)")
+        self.params = abi.align_params(max_level, min_level, n_iter, eps)
+        self.ctx = ctx or default_context()
+        self.last = None
+
+    # three-leg form (device-resident between legs)
+    def upload(self, data):
+        batch, self._keep = abi.make_align_batch(data)
+        self._shape = (data.batch, data.n_segs)
+        self.ctx.check(self.ctx.lib.plsvo_align_upload(self.ctx.handle, C.byref(batch)), "plsvo_align_upload")
+
+    def launch(self):
+        self.ctx.check(self.ctx.lib.plsvo_align_launch(self.ctx.handle, C.byref(self.params)), "plsvo_align_launch")
+
+    def download(self) -> abi.AlignOut:
+        out = abi.AlignOut(*self._shape)
+        self.ctx.check(self.ctx.lib.plsvo_align_download(self.ctx.handle, C.byref(out.struct)), "plsvo_align_download")
+        self.last = out
+        return out
+
+    def run(self, data) -> abi.AlignOut:
+        """run(ref_frames, cur_frames) for a whole batch: returns poses, n_tracked (the reference's
+        return value, sparse_img_align.cpp:94), H, killed-segment flags."""
+        batch, keep = abi.make_align_batch(data)
+        out = abi.AlignOut(data.batch, data.n_segs)
+        self.ctx.check(
+            self.ctx.lib.plsvo_align_batch_run(self.ctx.handle, C.byref(batch), C.byref(self.params), C.byref(out.struct)),
+            "plsvo_align_batch_run",
+        )
+        self.last = out
+        return out
+
+    def getFisherInformation(self):
+        """H_ / (5e-4 * 255^2), sparse_img_align.cpp:97-102 (per pair)."""
+        if self.last is None:
+            raise PlsvoError("run() has not been called")
+        return self.last.H.reshape(-1, 6, 6) / (5e-4 * 255 * 255)
+
+
+class pose_optimizer:
+    """Namespace mirror of plsvo::pose_optimizer (include/plsvo/pose_optimizer.h:47-64)."""
+
+    @staticmethod
+    def optimizeGaussNewton(reproj_thresh: float, n_iter: int, verbose: bool, data, n_iter_ref: int | None = None,
+                            ctx: Context | None = None) -> abi.PoseOptOut:
+        """9-argument overload when n_iter_ref is None, 10-argument overload otherwise."""
+        ctx = ctx or default_context()
+        params = abi.poseopt_params(reproj_thresh, n_iter, -1 if n_iter_ref is None else n_iter_ref)
+        batch, keep = abi.make_poseopt_batch(data)
+        out = abi.PoseOptOut(data.batch, data.n_pts, data.n_segs)
+        ctx.check(
+            ctx.lib.plsvo_poseopt_batch_run(ctx.handle, C.byref(batch), C.byref(params), C.byref(out.struct)),
+            "plsvo_poseopt_batch_run",
+        )
+        return out

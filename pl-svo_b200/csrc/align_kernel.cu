@@ -1,0 +1,693 @@
+// align_kernel.cu — sparse image alignment (plsvo::SparseImgAlign::run, src/sparse_img_align.cpp:54-95)
+// as ONE persistent sm_100a kernel: a CTA owns a frame pair for its whole coarse-to-fine
+// Gauss-Newton optimisation, so a pair costs no host round trips and no re-launches.
+//
+// Mapping:
+//   * work queue: CTAs pull pair indices from an atomic counter (iteration counts vary per pair).
+//   * per level: one thread issues a bulk async copy (TMA engine, cp.async.bulk -> UBLKCP) of the
+//     current image level into shared memory while all threads precompute the reference-patch
+//     cache (4x4 bilinear intensities + central-difference gradients: sparse_img_align.cpp:195-378)
+//     from the reference image in global memory.
+//   * per GN iteration: thread-per-patch residual pass (:380-502 points, :504-695 segment samples):
+//     warp the patch centre with T_cur_from_ref (double), bilinear 4x4 residuals in float with the
+//     reference's exact operation order, five per-patch sums (w*dx*dx, w*dx*dy, w*dy*dy, w*dx*r,
+//     w*dy*r) in double, then a rank-2 update of the thread's 21+6 accumulators using the two
+//     projection-Jacobian rows of the patch (J_px = (dx*row0 + dy*row1)*fx/2^l, :261-262) — this
+//     factorisation replaces the reference's 6x(N*16) double Jacobian cache (768 B/patch) by
+//     128 B/patch of float gradients.  Accumulators are reduced with a register-halving warp
+//     shuffle tree, then across warps through shared memory in fixed order (deterministic).
+//   * thread 0 solves the 6x6 system (pivoted LDLT), applies T <- T*exp(-x) and the vikit
+//     NLLSSolver accept / rollback / convergence logic on chip.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_math.cuh"
+#include "internal.h"
+
+namespace plsvo {
+
+namespace {
+
+struct SegStash {  // per segment-sample scratch: unweighted sums of one pass (or sample px during precompute)
+  double S[5];
+  float sumabs;
+  int ok;
+};
+
+struct PairCtl {
+  double R[9];
+  double t[3];
+  double model[7];      // T_cur_from_ref (q, t)
+  double old_model[7];
+  double T_ref[7];
+  double ref_pos[3];
+  double chi2_prev;
+  double H_last[36];
+  double scratch[36];
+  double g[6];
+  double x[6];
+  unsigned long long mbar;
+  long long n_meas_last;
+  int pair;
+  int flag;
+  int stop;
+  int iter;
+  int n_seg_patches;
+  unsigned int patch_iters;
+  unsigned int patch_levels;
+  int iters_level[PLSVO_MAX_LEVELS];
+};
+
+struct Layout {
+  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, patch_seg, stash, pt_vis, xyz, cache, img, total;
+};
+
+__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_patches, int max_seg_patches,
+                                              int img_bytes, bool cache_in_smem) {
+  Layout L;
+  uint32_t o = 0;
+  L.ctl = o;
+  o = align_up(o + (uint32_t)sizeof(PairCtl), 16);
+  L.red = o;
+  o += kAlignWarps * 32 * 8;
+  L.tot = o;
+  o += 32 * 8;
+  L.seg_N = o;
+  o += 4u * (uint32_t)n_segs;
+  L.seg_off = o;
+  o += 4u * (uint32_t)n_segs;
+  L.stash = align_up(o, 8);
+  o = L.stash + (uint32_t)sizeof(SegStash) * (uint32_t)max_seg_patches;
+  L.patch_seg = o;
+  o += 2u * (uint32_t)max_seg_patches;
+  L.seg_alive = o;
+  o += (uint32_t)n_segs;
+  L.pt_vis = o;
+  o += (uint32_t)n_pts;
+  o = align_up(o, 16);
+  L.xyz = o;
+  if (cache_in_smem) o += 3u * 8u * (uint32_t)max_patches;
+  o = align_up(o, 16);
+  L.cache = o;
+  if (cache_in_smem) o += (uint32_t)kCacheRows * 16u * (uint32_t)max_patches;
+  o = align_up(o, 128);
+  L.img = o;
+  o += (uint32_t)img_bytes;
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ float u8f(uint8_t v) { return (float)v; }
+
+// bilinear sample with the reference's operation order: ((wTL*a + wTR*b) + wBL*c) + wBR*d,
+// every product and sum rounded separately (no FMA contraction) — sparse_img_align.cpp:458
+__device__ __forceinline__ float bilin(float wTL, float wTR, float wBL, float wBR, float a, float b, float c, float d) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, a), __fmul_rn(wTR, b)), __fmul_rn(wBL, c)), __fmul_rn(wBR, d));
+}
+
+// Patch::setPosition + isInFrame + computeInterpWeights (src/feature.cpp:189-208, feature.h:139-144).
+// The weights are computed in float: for accepted patches (floor >= boundary >= 2) 1-subpix is
+// exact in float and each product is rounded once, which equals the reference's double-then-narrow.
+__device__ __forceinline__ bool patch_setup(double u, double v, int cols, int rows, int boundary, int& ui, int& vi,
+                                            float& wTL, float& wTR, float& wBL, float& wBR) {
+  const float uf = (float)u, vf = (float)v;
+  const float fu = floorf(uf), fv = floorf(vf);
+  ui = (int)fu;
+  vi = (int)fv;
+  if (ui < boundary || vi < boundary || ui >= cols - boundary || vi >= rows - boundary) return false;
+  const float su = __fsub_rn(uf, fu), sv = __fsub_rn(vf, fv);
+  const float omu = __fsub_rn(1.0f, su), omv = __fsub_rn(1.0f, sv);
+  wTL = __fmul_rn(omu, omv);
+  wTR = __fmul_rn(su, omv);
+  wBL = __fmul_rn(omu, sv);
+  wBR = __fmul_rn(su, sv);
+  return true;
+}
+
+// LineFeat::setupSampling (src/feature.cpp:160-173) followed by the per-level decimation (:320)
+__device__ __forceinline__ int seg_num_samples(const double* spx, const double* epx, double length, int level,
+                                               double* dif) {
+  dif[0] = epx[0] - spx[0];
+  dif[1] = epx[1] - spx[1];
+  const double a0 = fabs(dif[0]), a1 = fabs(dif[1]);
+  const double tan_dir = fmin(a0, a1) / fmax(a0, a1);
+  const double sin_dir = tan_dir / sqrt(1.0 + tan_dir * tan_dir);
+  const double correction = 2.0 * sqrt(1.0 + sin_dir * sin_dir);
+  const double nd = fmax(1.0, length / (2.0 * 4 * correction));
+  const unsigned long long n0 = (unsigned long long)nd;
+  return (int)(1 + (n0 - 1) / (unsigned long long)(1 << level));
+}
+
+__device__ __forceinline__ bool cam_in_frame(int ox, int oy, int boundary, int level, int width, int height) {
+  return ox >= boundary && ox < width / (1 << level) - boundary && oy >= boundary &&
+         oy < height / (1 << level) - boundary;
+}
+
+// rank-2 update of the 21 (upper-triangular H) + 6 (Jres) accumulators of one thread:
+//   H += Sxx r0 r0^T + Sxy (r0 r1^T + r1 r0^T) + Syy r1 r1^T ,  Jres -= Sxr r0 + Syr r1
+__device__ __forceinline__ void rank2_update(double* acc, double X, double Y, double Z, double Sxx, double Sxy,
+                                             double Syy, double Sxr, double Syr) {
+  double r0[6], r1[6];
+  jacobian_rows(X, Y, Z, r0, r1);
+  double p[6], q[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    p[i] = Sxx * r0[i] + Sxy * r1[i];
+    q[i] = Sxy * r0[i] + Syy * r1[i];
+  }
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) acc[idx++] += p[i] * r0[j] + q[i] * r1[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc[21 + i] -= Sxr * r0[i] + Syr * r1[i];
+}
+
+// One patch of the residual pass.  WEIGHTED = point patch (:450-500: w = 1/(1+|r|)), otherwise a
+// segment sample (:612-637: unweighted sums, |r| collected).  Returns false if the warped patch
+// is not fully inside the current image (isInFrame(halfsize)).
+template <bool WEIGHTED>
+__device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
+                                           const float4* cache, int MP, int p, double u, double v,
+                                           double* S /*[5]*/, float& chi2_or_sumabs) {
+  int ui, vi;
+  float wTL, wTR, wBL, wBR;
+  if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
+  const uint8_t* base = img + (size_t)(vi - 2) * pitch + (ui - 2);
+  float f[5][5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) f[r][c] = u8f(base[r * pitch + c]);
+  double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0;
+  float acc_f = 0.f;
+  double chi2 = 0.0;
+#pragma unroll
+  for (int y = 0; y < 4; ++y) {
+    const float4 ref4 = cache[(0 + y) * MP + p];
+    const float4 dx4 = cache[(4 + y) * MP + p];
+    const float4 dy4 = cache[(8 + y) * MP + p];
+    const float refv[4] = {ref4.x, ref4.y, ref4.z, ref4.w};
+    const float dxv[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
+    const float dyv[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const float cur = bilin(wTL, wTR, wBL, wBR, f[y][x], f[y][x + 1], f[y + 1][x], f[y + 1][x + 1]);
+      const float res = __fsub_rn(cur, refv[x]);
+      const double dxd = (double)dxv[x], dyd = (double)dyv[x], rd = (double)res;
+      if (WEIGHTED) {
+        const float w = (float)(1.0 / (1.0 + (double)fabsf(res)));  // :479
+        chi2 += (double)__fmul_rn(__fmul_rn(res, res), w);          // :484 (terms in float, sum in double)
+        const double wdx = (double)w * dxd, wdy = (double)w * dyd;
+        Sxx += wdx * dxd;
+        Sxy += wdx * dyd;
+        Syy += wdy * dyd;
+        Sxr += wdx * rd;
+        Syr += wdy * rd;
+      } else {
+        acc_f = __fadd_rn(acc_f, fabsf(res));  // :643
+        Sxx += dxd * dxd;
+        Sxy += dxd * dyd;
+        Syy += dyd * dyd;
+        Sxr += dxd * rd;
+        Syr += dyd * rd;
+      }
+    }
+  }
+  S[0] = Sxx, S[1] = Sxy, S[2] = Syy, S[3] = Sxr, S[4] = Syr;
+  chi2_or_sumabs = WEIGHTED ? (float)0 : acc_f;
+  if (WEIGHTED) S[5] = chi2;
+  return true;
+}
+
+// Reference-patch precompute for one patch (:243-264 / :354-375): 16 interpolated intensities and
+// central-difference gradients of the interpolated image, written as 12 float4 rows.
+__device__ __forceinline__ void precompute_patch(const uint8_t* __restrict__ img, int pitch, int ui, int vi, float wTL,
+                                                 float wTR, float wBL, float wBR, float4* __restrict__ cache, int MP,
+                                                 int p) {
+  const uint8_t* base = img + (size_t)(vi - 3) * pitch + (ui - 3);
+  float g[7][7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int c = 0; c < 7; ++c) g[r][c] = u8f(__ldg(base + r * pitch + c));
+#pragma unroll
+  for (int y = 0; y < 4; ++y) {
+    float refv[4], dxv[4], dyv[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int r = y + 1, c = x + 1;
+#define PLSVO_IAT(dr, dc) \
+  bilin(wTL, wTR, wBL, wBR, g[r + (dr)][c + (dc)], g[r + (dr)][c + (dc) + 1], g[r + (dr) + 1][c + (dc)], g[r + (dr) + 1][c + (dc) + 1])
+      refv[x] = PLSVO_IAT(0, 0);
+      dxv[x] = __fmul_rn(0.5f, __fsub_rn(PLSVO_IAT(0, 1), PLSVO_IAT(0, -1)));
+      dyv[x] = __fmul_rn(0.5f, __fsub_rn(PLSVO_IAT(1, 0), PLSVO_IAT(-1, 0)));
+#undef PLSVO_IAT
+    }
+    cache[(0 + y) * MP + p] = make_float4(refv[0], refv[1], refv[2], refv[3]);
+    cache[(4 + y) * MP + p] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
+    cache[(8 + y) * MP + p] = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+  }
+}
+
+__device__ __forceinline__ void zero_gradients(float4* cache, int MP, int p) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int y = 0; y < 8; ++y) cache[(4 + y) * MP + p] = z;
+}
+
+// Thread 0: one Gauss-Newton step of vk::NLLSSolver::optimizeGaussNewton with SparseImgAlign's
+// solve()/update() (:697-710).  tot = block totals [0..20]=H upper, [21..26]=Jres, [27]=chi2,
+// [28]=n_meas, [29]=patches evaluated.
+__device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level, int n_iter, double eps) {
+  double* H = ctl->H_last;
+  int idx = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      H[i * 6 + j] = tot[idx];
+      H[j * 6 + i] = tot[idx];
+      ++idx;
+    }
+  for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
+  const long long n_meas = (long long)tot[28];
+  ctl->n_meas_last = n_meas;
+  ctl->patch_iters += (unsigned int)tot[29];
+  ctl->iters_level[level] += 1;
+  // chi2/n_meas_ : float / size_t -> float (:192)
+  const double new_chi2 = (double)((float)tot[27] / (float)(unsigned long long)n_meas);
+  ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
+  if (isnan(ctl->x[0])) ctl->stop = 1;
+  const bool reject = (ctl->iter > 0 && new_chi2 > ctl->chi2_prev) || ctl->stop;
+  int flag;
+  if (reject) {
+    for (int i = 0; i < 7; ++i) ctl->model[i] = ctl->old_model[i];
+    flag = 1;
+  } else {
+    double mx[6];
+    double nm = 0.0;
+    for (int i = 0; i < 6; ++i) {
+      mx[i] = -ctl->x[i];
+      nm = fmax(nm, fabs(ctl->x[i]));
+    }
+    SE3q model;
+    model.q.x = ctl->model[0], model.q.y = ctl->model[1], model.q.z = ctl->model[2], model.q.w = ctl->model[3];
+    model.t = v3(ctl->model[4], ctl->model[5], ctl->model[6]);
+    const SE3q nm_model = se3_mul(model, se3_exp(mx));
+    for (int i = 0; i < 7; ++i) ctl->old_model[i] = ctl->model[i];
+    se3_store(nm_model, ctl->model);
+    ctl->chi2_prev = new_chi2;
+    flag = (nm <= eps) ? 1 : 0;
+  }
+  ctl->iter += 1;
+  if (ctl->iter >= n_iter) flag = 1;
+  Quat q;
+  q.x = ctl->model[0], q.y = ctl->model[1], q.z = ctl->model[2], q.w = ctl->model[3];
+  quat_to_R(q, ctl->R);
+  ctl->t[0] = ctl->model[4], ctl->t[1] = ctl->model[5], ctl->t[2] = ctl->model[6];
+  ctl->flag = flag;
+}
+
+template <bool CACHE_SMEM>
+__global__ void __launch_bounds__(kAlignThreads) sparse_img_align_kernel(const AlignArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int MP = a.max_patches;
+  const Layout L = make_layout(a.n_pts, a.n_segs, MP, a.max_seg_patches, a.smem_img_bytes, CACHE_SMEM);
+  PairCtl* ctl = reinterpret_cast<PairCtl*>(smem + L.ctl);
+  double* red = reinterpret_cast<double*>(smem + L.red);
+  double* tot = reinterpret_cast<double*>(smem + L.tot);
+  uint8_t* seg_alive = smem + L.seg_alive;
+  int* seg_N = reinterpret_cast<int*>(smem + L.seg_N);
+  int* seg_off = reinterpret_cast<int*>(smem + L.seg_off);
+  uint16_t* patch_seg = reinterpret_cast<uint16_t*>(smem + L.patch_seg);
+  SegStash* stash = reinterpret_cast<SegStash*>(smem + L.stash);
+  uint8_t* pt_vis = smem + L.pt_vis;
+  uint8_t* img_s = smem + L.img;
+  float4* cache;
+  double* xyz;
+  if (CACHE_SMEM) {
+    cache = reinterpret_cast<float4*>(smem + L.cache);
+    xyz = reinterpret_cast<double*>(smem + L.xyz);
+  } else {
+    cache = a.ws_cache + (size_t)blockIdx.x * kCacheRows * MP;
+    xyz = a.ws_xyz + (size_t)blockIdx.x * 3 * MP;
+  }
+  uint64_t* bar = reinterpret_cast<uint64_t*>(&ctl->mbar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbarrier_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  uint32_t bar_parity = 0;
+
+  for (;;) {
+    __syncthreads();  // everyone is done with ctl of the previous pair
+    if (tid == 0) ctl->pair = (int)atomicAdd(a.work_counter, 1u);
+    __syncthreads();
+    const int b = ctl->pair;
+    if (b >= a.B) break;
+
+    const int np = a.pt_count ? a.pt_count[b] : a.n_pts;
+    const int ns = a.seg_count ? a.seg_count[b] : a.n_segs;
+    const size_t po = (size_t)b * a.n_pts, so = (size_t)b * a.n_segs;
+
+    if (np == 0 && ns == 0) {  // :58-62 early-out: return 0, cur pose untouched
+      if (tid == 0) {
+        for (int i = 0; i < 7; ++i) a.out_T[(size_t)b * 7 + i] = a.T_cur_w[(size_t)b * 7 + i];
+        a.out_n_tracked[b] = 0;
+        for (int i = 0; i < 36; ++i) a.out_H[(size_t)b * 36 + i] = 0.0;
+        for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.out_iters[(size_t)b * PLSVO_MAX_LEVELS + l] = 0;
+        a.out_status[b] = 1;
+        a.out_patch_iters[b] = 0;
+        a.out_patch_levels[b] = 0;
+      }
+      for (int j = tid; j < a.n_segs; j += kAlignThreads) a.out_seg_killed[so + j] = 0;
+      continue;
+    }
+
+    if (tid == 0) {
+      const SE3q T_ref = se3_load(a.T_ref_w + (size_t)b * 7);
+      const SE3q T_cur = se3_load(a.T_cur_w + (size_t)b * 7);
+      const SE3q T_ref_inv = se3_inverse(T_ref);
+      const SE3q model = se3_mul(T_cur, T_ref_inv);  // :80
+      se3_store(T_ref, ctl->T_ref);
+      se3_store(model, ctl->model);
+      ctl->ref_pos[0] = T_ref_inv.t.x, ctl->ref_pos[1] = T_ref_inv.t.y, ctl->ref_pos[2] = T_ref_inv.t.z;
+      quat_to_R(model.q, ctl->R);
+      ctl->t[0] = model.t.x, ctl->t[1] = model.t.y, ctl->t[2] = model.t.z;
+      ctl->chi2_prev = 1e10;
+      ctl->stop = 0;
+      ctl->n_meas_last = 0;
+      ctl->patch_iters = 0;
+      ctl->patch_levels = 0;
+      for (int i = 0; i < 36; ++i) ctl->H_last[i] = 0.0;
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) ctl->iters_level[l] = 0;
+    }
+    __syncthreads();
+    const double rpx = ctl->ref_pos[0], rpy = ctl->ref_pos[1], rpz = ctl->ref_pos[2];
+
+    // per-pair point setup: xyz_ref = f * |pos - ref_pos|  (:229-230), visibility cleared
+    for (int i = tid; i < np; i += kAlignThreads) {
+      pt_vis[i] = 0;
+      const double* pos = a.pt_pos + (po + i) * 3;
+      const double* f = a.pt_f + (po + i) * 3;
+      const double dx = pos[0] - rpx, dy = pos[1] - rpy, dz = pos[2] - rpz;
+      const double depth = sqrt(dx * dx + dy * dy + dz * dz);
+      xyz[0 * MP + i] = f[0] * depth;
+      xyz[1 * MP + i] = f[1] * depth;
+      xyz[2 * MP + i] = f[2] * depth;
+    }
+    for (int j = tid; j < ns; j += kAlignThreads) seg_alive[j] = a.seg_valid ? (a.seg_valid[so + j] ? 1 : 0) : 1;
+    unsigned int my_patch_levels = 0;
+
+    for (int level = a.max_level; level >= a.min_level; --level) {
+      const int cols = a.width >> level, rows = a.height >> level;
+      const int pitch = (int)a.pitch[level];
+      const float scale = 1.0f / (float)(1 << level);
+      const double dscale = (double)scale;
+      const uint8_t* ref_img = a.ref_img[level] + (size_t)b * a.stride[level];
+      const uint8_t* cur_img_g = a.cur_img[level] + (size_t)b * a.stride[level];
+      const bool stage = a.img_in_smem[level] != 0;
+      const uint8_t* cur_img = stage ? img_s : cur_img_g;
+      __syncthreads();  // previous level's readers of img_s / stash are done
+      if (tid == 0) {
+        if (stage) {
+          const uint32_t bytes = (uint32_t)rows * (uint32_t)pitch;
+          fence_proxy_async();
+          mbar_expect_tx(bar, bytes);
+          bulk_g2s(img_s, cur_img_g, bytes, bar);
+        }
+        ctl->iter = 0;
+        for (int i = 0; i < 7; ++i) ctl->old_model[i] = ctl->model[i];
+      }
+      // ---- segment sampling at this level (:285-332) ----
+      for (int j = tid; j < ns; j += kAlignThreads) {
+        int N = 0;
+        if (seg_alive[j]) {
+          const double* spx = a.seg_spx + (so + j) * 2;
+          const double* epx = a.seg_epx + (so + j) * 2;
+          const int sx = (int)(spx[0] * dscale), sy = (int)(spx[1] * dscale);
+          const int ex = (int)(epx[0] * dscale), ey = (int)(epx[1] * dscale);
+          if (cam_in_frame(sx, sy, 3, level, a.width, a.height) && cam_in_frame(ex, ey, 3, level, a.width, a.height)) {
+            double dif[2];
+            N = seg_num_samples(spx, epx, a.seg_length[so + j], level, dif);
+          }
+        }
+        seg_N[j] = N;
+      }
+      __syncthreads();
+      if (warp == 0) {  // exclusive scan of seg_N -> seg_off (cache offsets in patches, :282-292)
+        int carry = 0;
+        for (int base = 0; base < ns; base += 32) {
+          const int j = base + lane;
+          const int v = (j < ns) ? seg_N[j] : 0;
+          int incl = v;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          if (j < ns) seg_off[j] = carry + incl - v;
+          carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) ctl->n_seg_patches = carry;
+      }
+      __syncthreads();
+      const int n_sp = min(ctl->n_seg_patches, a.max_seg_patches);
+      const int n_patches = np + n_sp;
+      // ---- expand segments into sample patches: 2D centre and 3D point by repeated addition (:323-335) ----
+      for (int j = tid; j < ns; j += kAlignThreads) {
+        const int N = seg_N[j];
+        if (N == 0) continue;
+        const double* spx = a.seg_spx + (so + j) * 2;
+        const double* epx = a.seg_epx + (so + j) * 2;
+        double dif[2];
+        seg_num_samples(spx, epx, a.seg_length[so + j], level, dif);
+        const double nm1 = (double)(unsigned long long)(N - 1);
+        const double inc2d0 = dif[0] * dscale / nm1, inc2d1 = dif[1] * dscale / nm1;
+        double px0 = spx[0] * dscale, px1 = spx[1] * dscale;
+        const double* sp = a.seg_spos + (so + j) * 3;
+        const double* ep = a.seg_epos + (so + j) * 3;
+        const double* sf = a.seg_sf + (so + j) * 3;
+        const double* ef = a.seg_ef + (so + j) * 3;
+        double d0 = sp[0] - rpx, d1 = sp[1] - rpy, d2 = sp[2] - rpz;
+        const double p_depth = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        d0 = ep[0] - rpx, d1 = ep[1] - rpy, d2 = ep[2] - rpz;
+        const double q_depth = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        const double P0 = sf[0] * p_depth, P1 = sf[1] * p_depth, P2 = sf[2] * p_depth;
+        const double Q0 = ef[0] * q_depth, Q1 = ef[1] * q_depth, Q2 = ef[2] * q_depth;
+        const double i0 = (Q0 - P0) / nm1, i1 = (Q1 - P1) / nm1, i2 = (Q2 - P2) / nm1;
+        double X = P0, Y = P1, Z = P2;
+        const int off = seg_off[j];
+        for (int n = 0; n < N; ++n) {
+          const int sp_idx = off + n;
+          if (sp_idx < n_sp) {
+            patch_seg[sp_idx] = (uint16_t)j;
+            stash[sp_idx].S[0] = px0;
+            stash[sp_idx].S[1] = px1;
+            xyz[0 * MP + np + sp_idx] = X;
+            xyz[1 * MP + np + sp_idx] = Y;
+            xyz[2 * MP + np + sp_idx] = Z;
+          }
+          px0 += inc2d0, px1 += inc2d1;
+          X += i0, Y += i1, Z += i2;
+        }
+      }
+      __syncthreads();
+      // ---- reference patch cache (:195-378) ----
+      for (int p = tid; p < n_patches; p += kAlignThreads) {
+        double u, v;
+        const bool is_pt = p < np;
+        if (is_pt) {
+          if (a.pt_valid && !a.pt_valid[po + p]) continue;
+          const double* px = a.pt_px + (po + p) * 2;
+          u = px[0] * dscale, v = px[1] * dscale;
+        } else {
+          u = stash[p - np].S[0], v = stash[p - np].S[1];
+        }
+        int ui, vi;
+        float wTL, wTR, wBL, wBR;
+        const bool in = patch_setup(u, v, cols, rows, 3, ui, vi, wTL, wTR, wBL, wBR);
+        if (!in) {
+          // points: skipped at this level (:218-219); their Jacobian columns were zeroed (:85).
+          // segment samples are inside by construction; guard only protects against malformed input.
+          if (!is_pt || pt_vis[p]) zero_gradients(cache, MP, p);
+          continue;
+        }
+        if (is_pt) pt_vis[p] = 1;
+        precompute_patch(ref_img, pitch, ui, vi, wTL, wTR, wBL, wBR, cache, MP, p);
+        ++my_patch_levels;
+      }
+      if (stage) {
+        mbar_wait(bar, bar_parity);
+        bar_parity ^= 1u;
+      }
+      __syncthreads();
+
+      // ---- Gauss-Newton iterations at this level (vk::NLLSSolver::optimizeGaussNewton) ----
+      const double cJ = fabs(a.fx) / (double)(1 << level);  // focal_length / 2^level (:262)
+      const double cJ2 = cJ * cJ;
+      for (;;) {
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+        const double R0 = ctl->R[0], R1 = ctl->R[1], R2 = ctl->R[2], R3 = ctl->R[3], R4 = ctl->R[4], R5 = ctl->R[5],
+                     R6 = ctl->R[6], R7 = ctl->R[7], R8 = ctl->R[8];
+        const double t0 = ctl->t[0], t1 = ctl->t[1], t2 = ctl->t[2];
+        for (int p = tid; p < n_patches; p += kAlignThreads) {
+          const bool is_pt = p < np;
+          if (is_pt && !pt_vis[p]) continue;
+          const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
+          const double xc = R0 * X + R1 * Y + R2 * Z + t0;
+          const double yc = R3 * X + R4 * Y + R5 * Z + t1;
+          const double zc = R6 * X + R7 * Y + R8 * Z + t2;
+          const double u = (a.fx * (xc / zc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
+          const double v = (a.fy * (yc / zc) + a.cy) * dscale;
+          double S[6];
+          float aux;
+          if (is_pt) {
+            if (!eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) continue;
+            rank2_update(acc, X, Y, Z, S[0] * cJ2, S[1] * cJ2, S[2] * cJ2, S[3] * cJ, S[4] * cJ);
+            acc[27] += S[5];
+            acc[28] += 16.0;
+            acc[29] += 1.0;
+          } else {
+            SegStash& st = stash[p - np];
+            const bool ok = seg_alive[patch_seg[p - np]] &&
+                            eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux);
+            st.ok = ok ? 1 : 0;
+            if (ok) {
+              st.S[0] = S[0], st.S[1] = S[1], st.S[2] = S[2], st.S[3] = S[3], st.S[4] = S[4];
+              st.sumabs = aux;
+            }
+          }
+        }
+        if (n_sp > 0) {
+          __syncthreads();
+          // ---- per-segment gate + weight (:640-688), applied by every sample thread of the segment ----
+          for (int sp_idx = tid; sp_idx < n_sp; sp_idx += kAlignThreads) {
+            const int j = patch_seg[sp_idx];
+            if (!seg_alive[j]) continue;
+            const int off = seg_off[j], N = seg_N[j];
+            float res_ = 0.f;
+            bool good = true;
+            int n_eval = 0;
+            for (int n = 0; n < N; ++n) {
+              const SegStash& s = stash[off + n];
+              if (!s.ok) {
+                good = false;
+                break;
+              }
+              res_ = __fadd_rn(res_, s.sumabs);
+              ++n_eval;
+            }
+            res_ = (float)((double)res_ / (double)(unsigned long long)N);  // :647
+            const bool first = (sp_idx == off);
+            if (good && (double)res_ < 200.0) {
+              const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
+              const SegStash& s = stash[sp_idx];
+              const double sH = (double)w / (double)res_ * cJ2;  // H += H_*weight/res_ (:681)
+              const double sJ = (double)w * cJ;                  // Jres += Jres_*weight (:682)
+              const int p = np + sp_idx;
+              rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], s.S[0] * sH, s.S[1] * sH,
+                           s.S[2] * sH, s.S[3] * sJ, s.S[4] * sJ);
+              if (first) {
+                acc[27] += (double)__fmul_rn(__fmul_rn(res_, res_), w);  // :683
+                acc[28] += 1.0;                                         // :684
+                acc[29] += (double)n_eval;
+              }
+            } else if (first) {
+              acc[29] += (double)n_eval;
+              patch_seg[sp_idx] |= 0x8000u;  // kill marker, applied after the barrier below
+            }
+          }
+          __syncthreads();
+          for (int sp_idx = tid; sp_idx < n_sp; sp_idx += kAlignThreads) {
+            const uint16_t v = patch_seg[sp_idx];
+            if (v & 0x8000u) {
+              patch_seg[sp_idx] = v & 0x7fffu;
+              seg_alive[v & 0x7fffu] = 0;  // it->feat3D = NULL (:688)
+            }
+          }
+        }
+        // ---- block reduction (deterministic order) ----
+        const double mine = warp_reduce32(acc, lane);
+        red[warp * 32 + lane] = mine;
+        __syncthreads();
+        if (warp == 0) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < kAlignWarps; ++w) s += red[w * 32 + lane];
+          tot[lane] = s;
+          __syncwarp();
+          if (lane == 0) gn_step(ctl, tot, level, a.n_iter, a.eps);
+        }
+        __syncthreads();
+        if (ctl->flag) break;
+      }
+    }  // levels
+
+    // ---- results ----
+    {
+      unsigned int v = my_patch_levels;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0 && v) atomicAdd(&ctl->patch_levels, v);
+    }
+    for (int j = tid; j < a.n_segs; j += kAlignThreads) {
+      const bool valid0 = (j < ns) && (a.seg_valid ? a.seg_valid[so + j] != 0 : true);
+      a.out_seg_killed[so + j] = (valid0 && !seg_alive[j]) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      SE3q model, T_ref;
+      model.q.x = ctl->model[0], model.q.y = ctl->model[1], model.q.z = ctl->model[2], model.q.w = ctl->model[3];
+      model.t = v3(ctl->model[4], ctl->model[5], ctl->model[6]);
+      T_ref.q.x = ctl->T_ref[0], T_ref.q.y = ctl->T_ref[1], T_ref.q.z = ctl->T_ref[2], T_ref.q.w = ctl->T_ref[3];
+      T_ref.t = v3(ctl->T_ref[4], ctl->T_ref[5], ctl->T_ref[6]);
+      const SE3q T_cur = se3_mul(model, T_ref);  // :92
+      se3_store(T_cur, a.out_T + (size_t)b * 7);
+      a.out_n_tracked[b] = ctl->n_meas_last / 16;  // :94
+      for (int i = 0; i < 36; ++i) a.out_H[(size_t)b * 36 + i] = ctl->H_last[i];
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.out_iters[(size_t)b * PLSVO_MAX_LEVELS + l] = ctl->iters_level[l];
+      a.out_status[b] = ctl->stop ? 2 : 0;
+      a.out_patch_iters[b] = ctl->patch_iters;
+      a.out_patch_levels[b] = ctl->patch_levels;
+    }
+  }
+}
+
+}  // namespace
+
+size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_patches, int img_bytes,
+                        bool cache_in_smem) {
+  return make_layout(n_pts, n_segs, max_patches, max_seg_patches, img_bytes, cache_in_smem).total;
+}
+
+cudaError_t align_kernel_prepare(bool cache_in_smem, size_t smem_bytes, int* ctas_per_sm) {
+  cudaError_t e;
+  if (cache_in_smem) {
+    e = cudaFuncSetAttribute(sparse_img_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<true>, kAlignThreads,
+                                                         smem_bytes);
+  }
+  e = cudaFuncSetAttribute(sparse_img_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<false>, kAlignThreads,
+                                                       smem_bytes);
+}
+
+cudaError_t align_kernel_launch(const AlignArgs& a, int grid, size_t smem_bytes, bool cache_in_smem, cudaStream_t s) {
+  if (cache_in_smem)
+    sparse_img_align_kernel<true><<<grid, kAlignThreads, smem_bytes, s>>>(a);
+  else
+    sparse_img_align_kernel<false><<<grid, kAlignThreads, smem_bytes, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace plsvo

@@ -1,0 +1,333 @@
+// device_math.cuh — small fixed-size double-precision helpers shared by the kernels:
+// Sophus-style quaternion SE3 (what plsvo::Frame::T_f_w_ stores, include/plsvo/frame.h:62),
+// 6x6 pivoted LDLT solve (Eigen's ldlt().solve used at src/sparse_img_align.cpp:699 and
+// src/pose_optimizer.cpp:170) and 6x6 inverse (src/pose_optimizer.cpp:199).
+// Written for one thread operating on registers / shared memory; no dynamic indexing into
+// register arrays after unrolling.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace plsvo {
+
+struct Quat {
+  double x, y, z, w;
+};
+struct Vec3 {
+  double x, y, z;
+};
+struct SE3q {
+  Quat q;
+  Vec3 t;
+};
+
+__device__ __forceinline__ Vec3 v3(double x, double y, double z) {
+  Vec3 r;
+  r.x = x, r.y = y, r.z = z;
+  return r;
+}
+__device__ __forceinline__ Vec3 vadd(Vec3 a, Vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ Vec3 vsub(Vec3 a, Vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ Vec3 vscale(Vec3 a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ Vec3 vcross(Vec3 a, Vec3 b) {
+  return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double vnorm(Vec3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+
+__device__ __forceinline__ Quat qnormalized(Quat q) {
+  const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  Quat r;
+  r.x = q.x / n, r.y = q.y / n, r.z = q.z / n, r.w = q.w / n;
+  return r;
+}
+__device__ __forceinline__ Quat qmul(Quat a, Quat b) {
+  Quat r;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  return r;
+}
+// rotate v by unit quaternion q (same operation order as Eigen's _transformVector)
+__device__ __forceinline__ Vec3 qrot(Quat q, Vec3 v) {
+  const Vec3 qv = v3(q.x, q.y, q.z);
+  Vec3 uv = vcross(qv, v);
+  uv = vadd(uv, uv);
+  return vadd(vadd(v, vscale(uv, q.w)), vcross(qv, uv));
+}
+__device__ __forceinline__ SE3q se3_load(const double* p) {
+  SE3q T;
+  Quat q;
+  q.x = p[0], q.y = p[1], q.z = p[2], q.w = p[3];
+  T.q = qnormalized(q);
+  T.t = v3(p[4], p[5], p[6]);
+  return T;
+}
+__device__ __forceinline__ void se3_store(const SE3q& T, double* p) {
+  p[0] = T.q.x, p[1] = T.q.y, p[2] = T.q.z, p[3] = T.q.w;
+  p[4] = T.t.x, p[5] = T.t.y, p[6] = T.t.z;
+}
+__device__ __forceinline__ SE3q se3_mul(const SE3q& a, const SE3q& b) {
+  SE3q r;
+  r.t = vadd(a.t, qrot(a.q, b.t));
+  r.q = qnormalized(qmul(a.q, b.q));
+  return r;
+}
+__device__ __forceinline__ SE3q se3_inverse(const SE3q& a) {
+  SE3q r;
+  Quat c;
+  c.x = -a.q.x, c.y = -a.q.y, c.z = -a.q.z, c.w = a.q.w;
+  r.q = qnormalized(c);
+  r.t = qrot(r.q, vscale(a.t, -1.0));
+  return r;
+}
+__device__ __forceinline__ Vec3 se3_act(const SE3q& T, Vec3 p) { return vadd(qrot(T.q, p), T.t); }
+
+// SE3::exp([upsilon, omega]) — Sophus (non-templated) se3.cpp / so3.cpp
+__device__ __forceinline__ SE3q se3_exp(const double* u) {
+  const Vec3 upsilon = v3(u[0], u[1], u[2]);
+  const Vec3 omega = v3(u[3], u[4], u[5]);
+  const double theta = vnorm(omega);
+  const double half_theta = 0.5 * theta;
+  double imag_factor;
+  double s_half, c_half;
+  sincos(half_theta, &s_half, &c_half);
+  if (theta < 1e-10) {
+    const double theta_sq = theta * theta;
+    const double theta_po4 = theta_sq * theta_sq;
+    imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
+  } else {
+    imag_factor = s_half / theta;
+  }
+  SE3q r;
+  Quat q;
+  q.x = imag_factor * omega.x, q.y = imag_factor * omega.y, q.z = imag_factor * omega.z, q.w = c_half;
+  r.q = qnormalized(q);
+  if (theta < 1e-10) {
+    r.t = qrot(r.q, upsilon);
+  } else {
+    double s, c;
+    sincos(theta, &s, &c);
+    const double theta_sq = theta * theta;
+    const double a = (1 - c) / theta_sq;
+    const double b = (theta - s) / (theta_sq * theta);
+    const Vec3 wu = vcross(omega, upsilon);
+    const Vec3 wwu = vcross(omega, wu);
+    r.t = vadd(vadd(upsilon, vscale(wu, a)), vscale(wwu, b));
+  }
+  return r;
+}
+// rotation matrix of a unit quaternion (Eigen toRotationMatrix), row-major R[9]
+__device__ __forceinline__ void quat_to_R(Quat q, double* R) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz), R[1] = txy - twz, R[2] = txz + twy;
+  R[3] = txy + twz, R[4] = 1 - (txx + tzz), R[5] = tyz - twx;
+  R[6] = txz - twy, R[7] = tyz + twx, R[8] = 1 - (txx + tyy);
+}
+
+// ---- 6x6 LDLT with diagonal pivoting, same algorithm as Eigen's ldlt_inplace<Lower>::unblocked +
+// solve (pseudo-inverse of D with tolerance 1/highest).  m is a 6x6 row-major scratch in memory
+// (shared or local); A is the full symmetric matrix. ----
+static __device__ __noinline__ void ldlt6_solve(const double* A, const double* b, double* x, double* m /*[36]*/) {
+  int tr[6];
+#pragma unroll 1
+  for (int i = 0; i < 36; ++i) m[i] = A[i];
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double big = fabs(m[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i) {
+      const double v = fabs(m[i * 6 + i]);
+      if (v > big) big = v, piv = i;
+    }
+    tr[k] = piv;
+    if (piv != k) {
+      for (int j = 0; j < k; ++j) {
+        const double t = m[k * 6 + j];
+        m[k * 6 + j] = m[piv * 6 + j];
+        m[piv * 6 + j] = t;
+      }
+      for (int i = piv + 1; i < 6; ++i) {
+        const double t = m[i * 6 + k];
+        m[i * 6 + k] = m[i * 6 + piv];
+        m[i * 6 + piv] = t;
+      }
+      {
+        const double t = m[k * 6 + k];
+        m[k * 6 + k] = m[piv * 6 + piv];
+        m[piv * 6 + piv] = t;
+      }
+      for (int i = k + 1; i < piv; ++i) {
+        const double t = m[i * 6 + k];
+        m[i * 6 + k] = m[piv * 6 + i];
+        m[piv * 6 + i] = t;
+      }
+    }
+    if (k > 0) {
+      double temp[6];
+      double s = 0;
+      for (int j = 0; j < k; ++j) {
+        temp[j] = m[j * 6 + j] * m[k * 6 + j];
+        s += m[k * 6 + j] * temp[j];
+      }
+      m[k * 6 + k] -= s;
+      for (int i = k + 1; i < 6; ++i) {
+        double s2 = 0;
+        for (int j = 0; j < k; ++j) s2 += m[i * 6 + j] * temp[j];
+        m[i * 6 + k] -= s2;
+      }
+    }
+    const double akk = m[k * 6 + k];
+    const bool valid = fabs(akk) > 0.0;
+    if (k == 0 && !valid) {
+      for (int j = 0; j < 6; ++j) tr[j] = j;
+      break;
+    }
+    if (valid)
+      for (int i = k + 1; i < 6; ++i) m[i * 6 + k] /= akk;
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) y[i] = b[i];
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    const double t = y[k];
+    y[k] = y[tr[k]];
+    y[tr[k]] = t;
+  }
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= m[i * 6 + j] * y[j];
+  const double tol = 1.0 / 1.7976931348623157e308;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) y[i] = (fabs(m[i * 6 + i]) > tol) ? y[i] / m[i * 6 + i] : 0.0;
+#pragma unroll 1
+  for (int i = 5; i >= 0; --i)
+    for (int j = i + 1; j < 6; ++j) y[i] -= m[j * 6 + i] * y[j];
+#pragma unroll 1
+  for (int k = 5; k >= 0; --k) {
+    const double t = y[k];
+    y[k] = y[tr[k]];
+    y[tr[k]] = t;
+  }
+  for (int i = 0; i < 6; ++i) x[i] = y[i];
+}
+
+// 6x6 inverse by partial-pivot LU (Eigen: PartialPivLU for fixed sizes > 4).  lu: 36-double scratch.
+static __device__ __noinline__ void inverse6(const double* A, double* out, double* lu) {
+  int perm[6];
+#pragma unroll 1
+  for (int i = 0; i < 36; ++i) lu[i] = A[i];
+  for (int i = 0; i < 6; ++i) perm[i] = i;
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double big = fabs(lu[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i) {
+      const double v = fabs(lu[i * 6 + k]);
+      if (v > big) big = v, piv = i;
+    }
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) {
+        const double t = lu[k * 6 + j];
+        lu[k * 6 + j] = lu[piv * 6 + j];
+        lu[piv * 6 + j] = t;
+      }
+      const int t = perm[k];
+      perm[k] = perm[piv];
+      perm[piv] = t;
+    }
+    for (int i = k + 1; i < 6; ++i) {
+      lu[i * 6 + k] /= lu[k * 6 + k];
+      for (int j = k + 1; j < 6; ++j) lu[i * 6 + j] -= lu[i * 6 + k] * lu[k * 6 + j];
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < 6; ++c) {
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+      y[i] = (perm[i] == c) ? 1.0 : 0.0;
+      for (int j = 0; j < i; ++j) y[i] -= lu[i * 6 + j] * y[j];
+    }
+    for (int i = 5; i >= 0; --i) {
+      for (int j = i + 1; j < 6; ++j) y[i] -= lu[i * 6 + j] * y[j];
+      y[i] /= lu[i * 6 + i];
+    }
+    for (int i = 0; i < 6; ++i) out[i * 6 + c] = y[i];
+  }
+}
+
+// Frame::jacobian_xyz2uv rows (include/plsvo/frame.h:138-160)
+__device__ __forceinline__ void jacobian_rows(double x, double y, double z, double* r0, double* r1) {
+  const double z_inv = 1. / z;
+  const double z_inv_2 = z_inv * z_inv;
+  r0[0] = -z_inv;
+  r0[1] = 0.0;
+  r0[2] = x * z_inv_2;
+  r0[3] = y * r0[2];
+  r0[4] = -(1.0 + x * r0[2]);
+  r0[5] = y * z_inv;
+  r1[0] = 0.0;
+  r1[1] = -z_inv;
+  r1[2] = y * z_inv_2;
+  r1[3] = 1.0 + y * r1[2];
+  r1[4] = -r0[3];
+  r1[5] = -x * z_inv;
+}
+
+// ---- shared-memory address + mbarrier + bulk async copy (TMA engine, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global -> shared bulk copy, completion signalled on the mbarrier (bytes % 16 == 0, 16B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// register-halving warp reduction of 32 doubles: afterwards lane L holds the warp-wide sum of v[L]
+// (fixed summation order -> bitwise reproducible).
+__device__ __forceinline__ double warp_reduce32(double* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const double send = upper ? v[i] : v[i + s];
+      const double keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+}  // namespace plsvo

@@ -1,0 +1,105 @@
+// internal.h — kernel argument blocks and launch entry points shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/plsvo_b200.h"
+
+namespace plsvo {
+
+constexpr int kAlignThreads = 256;  // threads per CTA of the alignment kernel (8 warps)
+constexpr int kAlignWarps = kAlignThreads / 32;
+constexpr int kCacheRows = 12;  // float4 rows per patch: 4 ref + 4 dx + 4 dy
+
+// Device-layout description of one alignment batch (all pointers are device pointers).
+struct AlignArgs {
+  int B, n_pts, n_segs;
+  int max_level, min_level, n_iter;
+  double eps;
+  int width, height;
+  double fx, fy, cx, cy;
+  // pyramid level l of pair b: img[l] + b*stride[l], rows pitch[l] bytes (pitch multiple of 16)
+  const uint8_t* ref_img[PLSVO_MAX_LEVELS];
+  const uint8_t* cur_img[PLSVO_MAX_LEVELS];
+  uint32_t pitch[PLSVO_MAX_LEVELS];
+  size_t stride[PLSVO_MAX_LEVELS];
+  uint8_t img_in_smem[PLSVO_MAX_LEVELS];  // stage the cur level in shared memory with a bulk copy
+  const double* T_ref_w;
+  const double* T_cur_w;
+  const int32_t* pt_count;
+  const double* pt_px;
+  const double* pt_f;
+  const double* pt_pos;
+  const uint8_t* pt_valid;
+  const int32_t* seg_count;
+  const double* seg_spx;
+  const double* seg_epx;
+  const double* seg_sf;
+  const double* seg_ef;
+  const double* seg_spos;
+  const double* seg_epos;
+  const double* seg_length;
+  const uint8_t* seg_valid;
+  // outputs
+  double* out_T;
+  long long* out_n_tracked;
+  double* out_H;
+  uint8_t* out_seg_killed;
+  int32_t* out_iters;
+  int32_t* out_status;
+  uint32_t* out_patch_iters;
+  uint32_t* out_patch_levels;
+  // work distribution + per-CTA workspace
+  unsigned int* work_counter;
+  int max_patches;      // patch slots per pair: n_pts + max segment samples
+  int max_seg_patches;  // segment sample slots per pair
+  int smem_img_bytes;   // bytes of the image staging buffer
+  float4* ws_cache;     // [grid][kCacheRows][max_patches] when the patch cache lives in global memory
+  double* ws_xyz;       // [grid][3][max_patches]
+};
+
+struct AlignLaunchInfo {
+  int grid;
+  int ctas_per_sm;
+  size_t smem_bytes;
+  bool cache_in_smem;
+};
+
+// shared memory the kernel needs for a configuration (host + device agree through this)
+size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_patches, int img_bytes, bool cache_in_smem);
+cudaError_t align_kernel_prepare(bool cache_in_smem, size_t smem_bytes, int* ctas_per_sm);
+cudaError_t align_kernel_launch(const AlignArgs& a, int grid, size_t smem_bytes, bool cache_in_smem, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+struct PoseOptArgs {
+  int B, n_pts, n_segs;
+  double fx, reproj_thresh;
+  int n_iter, n_iter_ref;
+  const double* T_f_w;
+  const int32_t* pt_count;
+  const double* pt_f;
+  const double* pt_pos;
+  const int32_t* pt_level;
+  const uint8_t* pt_valid;
+  const int32_t* seg_count;
+  const double* seg_line;
+  const double* seg_spos;
+  const double* seg_epos;
+  const int32_t* seg_level;
+  const uint8_t* seg_valid;
+  double* out_T;
+  double* out_cov;
+  double* out_scale;
+  double* out_err_init;
+  double* out_err_final;
+  long long* out_num_pt;
+  long long* out_num_ls;
+  uint8_t* out_pt_outlier;
+  uint8_t* out_seg_outlier;
+  int32_t* out_iters;
+  int32_t* out_status;
+};
+size_t poseopt_smem_bytes(int n_pts, int n_segs);
+cudaError_t poseopt_kernel_launch(const PoseOptArgs& a, size_t smem_bytes, cudaStream_t s);
+
+}  // namespace plsvo

@@ -1,0 +1,529 @@
+// plsvo_abi.cu — the C ABI of include/plsvo_b200.h: context, host<->device staging, launches.
+// Host-side only; the kernels are in align_kernel.cu and poseopt_kernel.cu.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+using namespace plsvo;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct plsvo_ctx_impl {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  int smem_optin = 0;
+  std::string err;
+  long long launches = 0;
+
+  // ---- alignment state ----
+  bool align_ready = false;
+  AlignArgs aa;
+  plsvo_camera cam;
+  int a_max_seg_patches_l0 = 0;  // bound at level 0 (levels >= 0 never need more)
+  std::vector<int> seg_patch_bound;  // per level: max over pairs of the number of segment samples
+  DevBuf d_ref_img, d_cur_img, d_T_ref, d_T_cur, d_pt_count, d_pt_px, d_pt_f, d_pt_pos, d_pt_valid, d_seg_count,
+      d_seg_spx, d_seg_epx, d_seg_sf, d_seg_ef, d_seg_spos, d_seg_epos, d_seg_length, d_seg_valid;
+  DevBuf d_out_T, d_out_ntr, d_out_H, d_out_killed, d_out_iters, d_out_status, d_out_pi, d_out_pl, d_counter,
+      d_ws_cache, d_ws_xyz;
+  size_t level_off[PLSVO_MAX_LEVELS];
+
+  // ---- pose-opt state ----
+  bool po_ready = false;
+  PoseOptArgs pa;
+  DevBuf p_T, p_pt_count, p_pt_f, p_pt_pos, p_pt_level, p_pt_valid, p_seg_count, p_seg_line, p_seg_spos, p_seg_epos,
+      p_seg_level, p_seg_valid;
+  DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
+      p_out_status;
+};
+
+#define CTX(c) reinterpret_cast<plsvo_ctx_impl*>(c)
+
+int fail(plsvo_ctx_impl* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess)
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  else
+    snprintf(buf, sizeof buf, "%s", what);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) return fail(c, PLSVO_ERR_CUDA, #call, e_);   \
+  } while (0)
+
+cudaError_t ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return cudaSuccess;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = std::max<size_t>(bytes, 256);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e == cudaSuccess) b.cap = want;
+  return e;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+// upload a host array (or leave the device pointer NULL when the host pointer is NULL)
+template <class T>
+cudaError_t up(DevBuf& b, const T* host, size_t count, cudaStream_t s, const T** dev) {
+  if (!host || count == 0) {
+    *dev = nullptr;
+    return cudaSuccess;
+  }
+  cudaError_t e = ensure(b, count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  *dev = static_cast<const T*>(b.p);
+  return cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+// LineFeat::setupSampling + per-level decimation on the host, to size the segment-sample slots
+// (reference: src/feature.cpp:160-173, src/sparse_img_align.cpp:318-320)
+int host_seg_samples(const double* spx, const double* epx, double length, int level) {
+  const double d0 = fabs(epx[0] - spx[0]), d1 = fabs(epx[1] - spx[1]);
+  const double tan_dir = std::min(d0, d1) / std::max(d0, d1);
+  const double sin_dir = tan_dir / sqrt(1.0 + tan_dir * tan_dir);
+  const double correction = 2.0 * sqrt(1.0 + sin_dir * sin_dir);
+  double nd = length / (2.0 * 4 * correction);
+  if (!(nd >= 1.0)) nd = 1.0;  // also catches NaN
+  if (nd > 1e6) nd = 1e6;
+  const unsigned long long n0 = (unsigned long long)nd;
+  return (int)(1 + (n0 - 1) / (unsigned long long)(1 << level));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* plsvo_version(void) { return "plsvo_b200 0.1.0 sm_100a"; }
+
+int plsvo_ctx_create(int device, void* stream, plsvo_ctx** out) {
+  if (!out) return PLSVO_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, PLSVO_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)", e);
+  if (device < 0 || device >= n) return fail(nullptr, PLSVO_ERR_INVALID, "device ordinal out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, PLSVO_ERR_CUDA, "cudaSetDevice", e);
+  plsvo_ctx_impl* c = new plsvo_ctx_impl();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (stream) {
+    c->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail(nullptr, PLSVO_ERR_CUDA, "cudaStreamCreate", e);
+    }
+    c->own_stream = true;
+  }
+  memset(&c->aa, 0, sizeof c->aa);
+  memset(&c->pa, 0, sizeof c->pa);
+  *out = reinterpret_cast<plsvo_ctx*>(c);
+  return PLSVO_OK;
+}
+
+void plsvo_ctx_destroy(plsvo_ctx* ctx) {
+  if (!ctx) return;
+  plsvo_ctx_impl* c = CTX(ctx);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->d_ref_img,   &c->d_cur_img,  &c->d_T_ref,     &c->d_T_cur,      &c->d_pt_count,  &c->d_pt_px,
+                    &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
+                    &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
+                    &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->p_T,
+                    &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
+                    &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
+                    &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
+                    &c->p_out_pto,   &c->p_out_sgo,  &c->p_out_iters, &c->p_out_status};
+  for (DevBuf* b : bufs) release(*b);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* plsvo_last_error(const plsvo_ctx* ctx) {
+  if (!ctx) return g_create_error.c_str();
+  return reinterpret_cast<const plsvo_ctx_impl*>(ctx)->err.c_str();
+}
+
+void* plsvo_ctx_stream(plsvo_ctx* ctx) { return ctx ? (void*)CTX(ctx)->stream : nullptr; }
+
+int plsvo_sync(plsvo_ctx* ctx) {
+  if (!ctx) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  CK(cudaStreamSynchronize(c->stream));
+  return PLSVO_OK;
+}
+
+int plsvo_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return PLSVO_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    return fail(nullptr, e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? PLSVO_ERR_NO_DEVICE : PLSVO_ERR_CUDA,
+                "cudaHostAlloc", e);
+  }
+  return PLSVO_OK;
+}
+int plsvo_host_free(void* ptr) {
+  if (!ptr) return PLSVO_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? PLSVO_OK : PLSVO_ERR_CUDA;
+}
+
+int64_t plsvo_launch_count(const plsvo_ctx* ctx) {
+  return ctx ? reinterpret_cast<const plsvo_ctx_impl*>(ctx)->launches : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// alignment
+// ------------------------------------------------------------------------------------------------
+int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
+  if (!ctx || !h) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  c->align_ready = false;
+  if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0 || h->n_segs > 32767)
+    return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
+  if (!h->T_ref_w || !h->T_cur_w) return fail(c, PLSVO_ERR_INVALID, "T_ref_w/T_cur_w missing");
+  if (h->n_pts > 0 && (!h->pt_px || !h->pt_f || !h->pt_pos)) return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
+  if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || !h->seg_sf || !h->seg_ef || !h->seg_spos || !h->seg_epos ||
+                        !h->seg_length))
+    return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
+  if (h->cam.width <= 0 || h->cam.height <= 0) return fail(c, PLSVO_ERR_INVALID, "camera size");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  AlignArgs& a = c->aa;
+  const size_t B = (size_t)h->batch;
+  a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs;
+  a.width = h->cam.width, a.height = h->cam.height;
+  a.fx = h->cam.fx, a.fy = h->cam.fy, a.cx = h->cam.cx, a.cy = h->cam.cy;
+  c->cam = h->cam;
+
+  // images: every provided level is packed as [B][rows][pitch16]
+  size_t total = 0;
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    a.ref_img[l] = a.cur_img[l] = nullptr;
+    a.pitch[l] = 0, a.stride[l] = 0;
+    c->level_off[l] = 0;
+    if (!h->ref_img[l] || !h->cur_img[l]) continue;
+    const int cols = h->cam.width >> l, rows = h->cam.height >> l;
+    if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
+    if (h->img_pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "img_pitch smaller than the level width");
+    const uint32_t pitch = (uint32_t)((cols + 15) / 16 * 16);
+    a.pitch[l] = pitch;
+    a.stride[l] = (size_t)rows * pitch;
+    total = (total + 255) / 256 * 256;
+    c->level_off[l] = total;
+    total += a.stride[l] * B;
+  }
+  CK(ensure(c->d_ref_img, total + 256));
+  CK(ensure(c->d_cur_img, total + 256));
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    if (!a.pitch[l]) continue;
+    const int cols = h->cam.width >> l, rows = h->cam.height >> l;
+    uint8_t* dr = static_cast<uint8_t*>(c->d_ref_img.p) + c->level_off[l];
+    uint8_t* dc = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
+    a.ref_img[l] = dr;
+    a.cur_img[l] = dc;
+    if (h->img_stride[l] == (size_t)rows * h->img_pitch[l]) {  // uniformly pitched stack: one 2D copy
+      CK(cudaMemcpy2DAsync(dr, a.pitch[l], h->ref_img[l], h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpy2DAsync(dc, a.pitch[l], h->cur_img[l], h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyHostToDevice, s));
+    } else {
+      for (size_t b = 0; b < B; ++b) {
+        CK(cudaMemcpy2DAsync(dr + b * a.stride[l], a.pitch[l], h->ref_img[l] + b * h->img_stride[l], h->img_pitch[l], cols,
+                             rows, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpy2DAsync(dc + b * a.stride[l], a.pitch[l], h->cur_img[l] + b * h->img_stride[l], h->img_pitch[l], cols,
+                             rows, cudaMemcpyHostToDevice, s));
+      }
+    }
+  }
+
+  CK(up(c->d_T_ref, h->T_ref_w, B * 7, s, &a.T_ref_w));
+  CK(up(c->d_T_cur, h->T_cur_w, B * 7, s, &a.T_cur_w));
+  CK(up(c->d_pt_count, h->pt_count, B, s, &a.pt_count));
+  CK(up(c->d_pt_px, h->pt_px, B * h->n_pts * 2, s, &a.pt_px));
+  CK(up(c->d_pt_f, h->pt_f, B * h->n_pts * 3, s, &a.pt_f));
+  CK(up(c->d_pt_pos, h->pt_pos, B * h->n_pts * 3, s, &a.pt_pos));
+  CK(up(c->d_pt_valid, h->pt_valid, B * h->n_pts, s, &a.pt_valid));
+  CK(up(c->d_seg_count, h->seg_count, B, s, &a.seg_count));
+  CK(up(c->d_seg_spx, h->seg_spx, B * h->n_segs * 2, s, &a.seg_spx));
+  CK(up(c->d_seg_epx, h->seg_epx, B * h->n_segs * 2, s, &a.seg_epx));
+  CK(up(c->d_seg_sf, h->seg_sf, B * h->n_segs * 3, s, &a.seg_sf));
+  CK(up(c->d_seg_ef, h->seg_ef, B * h->n_segs * 3, s, &a.seg_ef));
+  CK(up(c->d_seg_spos, h->seg_spos, B * h->n_segs * 3, s, &a.seg_spos));
+  CK(up(c->d_seg_epos, h->seg_epos, B * h->n_segs * 3, s, &a.seg_epos));
+  CK(up(c->d_seg_length, h->seg_length, B * h->n_segs, s, &a.seg_length));
+  CK(up(c->d_seg_valid, h->seg_valid, B * h->n_segs, s, &a.seg_valid));
+
+  // per-level bound on segment samples per pair (sizes the sample slots; host arrays are still valid here)
+  c->seg_patch_bound.assign(PLSVO_MAX_LEVELS, 0);
+  if (h->n_segs > 0) {
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+      int worst = 0;
+      for (size_t b = 0; b < B; ++b) {
+        const int ns = h->seg_count ? std::min(h->seg_count[b], h->n_segs) : h->n_segs;
+        int sum = 0;
+        for (int j = 0; j < ns; ++j) {
+          const size_t k = b * h->n_segs + j;
+          sum += host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], l);
+        }
+        worst = std::max(worst, sum);
+      }
+      c->seg_patch_bound[l] = worst;
+    }
+  }
+
+  CK(ensure(c->d_out_T, B * 7 * sizeof(double)));
+  CK(ensure(c->d_out_ntr, B * sizeof(long long)));
+  CK(ensure(c->d_out_H, B * 36 * sizeof(double)));
+  CK(ensure(c->d_out_killed, B * std::max(1, h->n_segs)));
+  CK(ensure(c->d_out_iters, B * PLSVO_MAX_LEVELS * sizeof(int32_t)));
+  CK(ensure(c->d_out_status, B * sizeof(int32_t)));
+  CK(ensure(c->d_out_pi, B * sizeof(uint32_t)));
+  CK(ensure(c->d_out_pl, B * sizeof(uint32_t)));
+  CK(ensure(c->d_counter, 256));
+  a.out_T = static_cast<double*>(c->d_out_T.p);
+  a.out_n_tracked = static_cast<long long*>(c->d_out_ntr.p);
+  a.out_H = static_cast<double*>(c->d_out_H.p);
+  a.out_seg_killed = static_cast<uint8_t*>(c->d_out_killed.p);
+  a.out_iters = static_cast<int32_t*>(c->d_out_iters.p);
+  a.out_status = static_cast<int32_t*>(c->d_out_status.p);
+  a.out_patch_iters = static_cast<uint32_t*>(c->d_out_pi.p);
+  a.out_patch_levels = static_cast<uint32_t*>(c->d_out_pl.p);
+  a.work_counter = static_cast<unsigned int*>(c->d_counter.p);
+  c->align_ready = true;
+  return PLSVO_OK;
+}
+
+int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
+  if (!ctx || !p) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_launch before plsvo_align_upload");
+  if (p->min_level < 0 || p->max_level < p->min_level || p->max_level >= PLSVO_MAX_LEVELS || p->n_iter < 1)
+    return fail(c, PLSVO_ERR_INVALID, "level range / n_iter");
+  AlignArgs& a = c->aa;
+  for (int l = p->min_level; l <= p->max_level; ++l)
+    if (!a.pitch[l]) return fail(c, PLSVO_ERR_INVALID, "a pyramid level in [min_level,max_level] was not uploaded");
+  CK(cudaSetDevice(c->device));
+  a.max_level = p->max_level, a.min_level = p->min_level, a.n_iter = p->n_iter, a.eps = p->eps;
+  a.max_seg_patches = c->seg_patch_bound[p->min_level];
+  a.max_patches = (a.n_pts + a.max_seg_patches + 3) / 4 * 4;
+  if (a.max_patches == 0) a.max_patches = 4;
+
+  // shared-memory plan: stage the current image level when it fits; keep the patch cache on chip
+  // when that still leaves room for >= 2 CTAs per SM, otherwise stream it from a per-CTA global
+  // workspace (L2 resident) with coalesced 128-bit loads.
+  const char* mode = getenv("PLSVO_CACHE_MODE");  // "smem" | "global" | unset (= auto)
+  const int limit = c->smem_optin;                // 227 KB on sm_100a
+  const int img_budget = 64 * 1024;
+  int img_bytes = 0;
+  for (int l = p->min_level; l <= p->max_level; ++l) {
+    const size_t bytes = a.stride[l];
+    a.img_in_smem[l] = (bytes <= (size_t)img_budget && bytes < (1u << 20)) ? 1 : 0;
+    if (a.img_in_smem[l]) img_bytes = std::max(img_bytes, (int)bytes);
+  }
+  a.smem_img_bytes = img_bytes;
+  size_t smem_s = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, img_bytes, true);
+  size_t smem_g = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, img_bytes, false);
+  bool cache_in_smem = smem_s <= (size_t)(limit / 2 - 1024);
+  if (mode && !strcmp(mode, "smem")) cache_in_smem = smem_s <= (size_t)limit;
+  if (mode && !strcmp(mode, "global")) cache_in_smem = false;
+  size_t smem = cache_in_smem ? smem_s : smem_g;
+  if (smem > (size_t)limit) {  // drop image staging as a last resort
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.img_in_smem[l] = 0;
+    a.smem_img_bytes = 0;
+    smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, 0, false);
+    cache_in_smem = false;
+    if (smem > (size_t)limit) return fail(c, PLSVO_ERR_INVALID, "feature counts exceed the shared-memory plan");
+  }
+  int ctas_per_sm = 0;
+  CK(align_kernel_prepare(cache_in_smem, smem, &ctas_per_sm));
+  if (ctas_per_sm < 1) return fail(c, PLSVO_ERR_INVALID, "kernel does not fit on an SM");
+  const char* cap = getenv("PLSVO_CTAS_PER_SM");
+  if (cap && atoi(cap) > 0) ctas_per_sm = std::min(ctas_per_sm, atoi(cap));
+  const int grid = std::min(a.B, c->num_sms * ctas_per_sm);
+  if (!cache_in_smem) {
+    CK(ensure(c->d_ws_cache, (size_t)grid * kCacheRows * a.max_patches * sizeof(float4)));
+    CK(ensure(c->d_ws_xyz, (size_t)grid * 3 * a.max_patches * sizeof(double)));
+  }
+  a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
+  a.ws_xyz = static_cast<double*>(c->d_ws_xyz.p);
+  CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), c->stream));
+  CK(align_kernel_launch(a, grid, smem, cache_in_smem, c->stream));
+  c->launches += 1;
+  return PLSVO_OK;
+}
+
+int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* o) {
+  if (!ctx || !o) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_download before plsvo_align_upload");
+  CK(cudaSetDevice(c->device));
+  const AlignArgs& a = c->aa;
+  const size_t B = (size_t)a.B;
+  cudaStream_t s = c->stream;
+  if (o->T_cur_w) CK(cudaMemcpyAsync(o->T_cur_w, a.out_T, B * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->n_tracked) CK(cudaMemcpyAsync(o->n_tracked, a.out_n_tracked, B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (o->H) CK(cudaMemcpyAsync(o->H, a.out_H, B * 36 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->seg_killed && a.n_segs > 0)
+    CK(cudaMemcpyAsync(o->seg_killed, a.out_seg_killed, B * a.n_segs, cudaMemcpyDeviceToHost, s));
+  if (o->iters) CK(cudaMemcpyAsync(o->iters, a.out_iters, B * PLSVO_MAX_LEVELS * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (o->status) CK(cudaMemcpyAsync(o->status, a.out_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (o->patch_iters) CK(cudaMemcpyAsync(o->patch_iters, a.out_patch_iters, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (o->patch_levels) CK(cudaMemcpyAsync(o->patch_levels, a.out_patch_levels, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
+}
+
+int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsvo_align_params* p,
+                          const plsvo_align_result* o) {
+  int rc = plsvo_align_upload(ctx, b);
+  if (rc != PLSVO_OK) return rc;
+  rc = plsvo_align_launch(ctx, p);
+  if (rc != PLSVO_OK) return rc;
+  return plsvo_align_download(ctx, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose optimiser
+// ------------------------------------------------------------------------------------------------
+int plsvo_poseopt_upload(plsvo_ctx* ctx, const plsvo_poseopt_batch* h) {
+  if (!ctx || !h) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  c->po_ready = false;
+  if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0) return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
+  if (!h->T_f_w) return fail(c, PLSVO_ERR_INVALID, "T_f_w missing");
+  if (h->n_pts > 0 && (!h->pt_f || !h->pt_pos || !h->pt_level)) return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
+  if (h->n_segs > 0 && (!h->seg_line || !h->seg_spos || !h->seg_epos || !h->seg_level))
+    return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  PoseOptArgs& a = c->pa;
+  const size_t B = (size_t)h->batch;
+  a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs, a.fx = h->fx;
+  CK(up(c->p_T, h->T_f_w, B * 7, s, &a.T_f_w));
+  CK(up(c->p_pt_count, h->pt_count, B, s, &a.pt_count));
+  CK(up(c->p_pt_f, h->pt_f, B * h->n_pts * 3, s, &a.pt_f));
+  CK(up(c->p_pt_pos, h->pt_pos, B * h->n_pts * 3, s, &a.pt_pos));
+  CK(up(c->p_pt_level, h->pt_level, B * h->n_pts, s, &a.pt_level));
+  CK(up(c->p_pt_valid, h->pt_valid, B * h->n_pts, s, &a.pt_valid));
+  CK(up(c->p_seg_count, h->seg_count, B, s, &a.seg_count));
+  CK(up(c->p_seg_line, h->seg_line, B * h->n_segs * 3, s, &a.seg_line));
+  CK(up(c->p_seg_spos, h->seg_spos, B * h->n_segs * 3, s, &a.seg_spos));
+  CK(up(c->p_seg_epos, h->seg_epos, B * h->n_segs * 3, s, &a.seg_epos));
+  CK(up(c->p_seg_level, h->seg_level, B * h->n_segs, s, &a.seg_level));
+  CK(up(c->p_seg_valid, h->seg_valid, B * h->n_segs, s, &a.seg_valid));
+  CK(ensure(c->p_out_T, B * 7 * sizeof(double)));
+  CK(ensure(c->p_out_cov, B * 36 * sizeof(double)));
+  CK(ensure(c->p_out_scale, B * sizeof(double)));
+  CK(ensure(c->p_out_ei, B * sizeof(double)));
+  CK(ensure(c->p_out_ef, B * sizeof(double)));
+  CK(ensure(c->p_out_npt, B * sizeof(long long)));
+  CK(ensure(c->p_out_nls, B * sizeof(long long)));
+  CK(ensure(c->p_out_pto, B * std::max(1, h->n_pts)));
+  CK(ensure(c->p_out_sgo, B * std::max(1, h->n_segs)));
+  CK(ensure(c->p_out_iters, B * 2 * sizeof(int32_t)));
+  CK(ensure(c->p_out_status, B * sizeof(int32_t)));
+  a.out_T = static_cast<double*>(c->p_out_T.p);
+  a.out_cov = static_cast<double*>(c->p_out_cov.p);
+  a.out_scale = static_cast<double*>(c->p_out_scale.p);
+  a.out_err_init = static_cast<double*>(c->p_out_ei.p);
+  a.out_err_final = static_cast<double*>(c->p_out_ef.p);
+  a.out_num_pt = static_cast<long long*>(c->p_out_npt.p);
+  a.out_num_ls = static_cast<long long*>(c->p_out_nls.p);
+  a.out_pt_outlier = static_cast<uint8_t*>(c->p_out_pto.p);
+  a.out_seg_outlier = static_cast<uint8_t*>(c->p_out_sgo.p);
+  a.out_iters = static_cast<int32_t*>(c->p_out_iters.p);
+  a.out_status = static_cast<int32_t*>(c->p_out_status.p);
+  c->po_ready = true;
+  return PLSVO_OK;
+}
+
+int plsvo_poseopt_launch(plsvo_ctx* ctx, const plsvo_poseopt_params* p) {
+  if (!ctx || !p) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (!c->po_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_poseopt_launch before plsvo_poseopt_upload");
+  if (p->n_iter < 0) return fail(c, PLSVO_ERR_INVALID, "n_iter");
+  CK(cudaSetDevice(c->device));
+  PoseOptArgs& a = c->pa;
+  a.reproj_thresh = p->reproj_thresh, a.n_iter = p->n_iter, a.n_iter_ref = p->n_iter_ref;
+  const size_t smem = poseopt_smem_bytes(a.n_pts, a.n_segs);
+  if (smem > (size_t)c->smem_optin) return fail(c, PLSVO_ERR_INVALID, "feature counts exceed shared memory");
+  // outputs of frames that return early keep their previous contents: clear the ones we always report
+  const size_t B = (size_t)a.B;
+  CK(cudaMemsetAsync(a.out_cov, 0, B * 36 * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(a.out_scale, 0, B * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(a.out_err_init, 0, B * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(a.out_err_final, 0, B * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(a.out_num_pt, 0, B * sizeof(long long), c->stream));
+  CK(cudaMemsetAsync(a.out_num_ls, 0, B * sizeof(long long), c->stream));
+  CK(poseopt_kernel_launch(a, smem, c->stream));
+  c->launches += 1;
+  return PLSVO_OK;
+}
+
+int plsvo_poseopt_download(plsvo_ctx* ctx, const plsvo_poseopt_result* o) {
+  if (!ctx || !o) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (!c->po_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_poseopt_download before plsvo_poseopt_upload");
+  CK(cudaSetDevice(c->device));
+  const PoseOptArgs& a = c->pa;
+  const size_t B = (size_t)a.B;
+  cudaStream_t s = c->stream;
+  if (o->T_f_w) CK(cudaMemcpyAsync(o->T_f_w, a.out_T, B * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->cov) CK(cudaMemcpyAsync(o->cov, a.out_cov, B * 36 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->estimated_scale) CK(cudaMemcpyAsync(o->estimated_scale, a.out_scale, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->error_init) CK(cudaMemcpyAsync(o->error_init, a.out_err_init, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->error_final) CK(cudaMemcpyAsync(o->error_final, a.out_err_final, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (o->num_obs_pt) CK(cudaMemcpyAsync(o->num_obs_pt, a.out_num_pt, B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (o->num_obs_ls) CK(cudaMemcpyAsync(o->num_obs_ls, a.out_num_ls, B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (o->pt_outlier && a.n_pts > 0) CK(cudaMemcpyAsync(o->pt_outlier, a.out_pt_outlier, B * a.n_pts, cudaMemcpyDeviceToHost, s));
+  if (o->seg_outlier && a.n_segs > 0)
+    CK(cudaMemcpyAsync(o->seg_outlier, a.out_seg_outlier, B * a.n_segs, cudaMemcpyDeviceToHost, s));
+  if (o->iters) CK(cudaMemcpyAsync(o->iters, a.out_iters, B * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (o->status) CK(cudaMemcpyAsync(o->status, a.out_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
+}
+
+int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* b, const plsvo_poseopt_params* p,
+                            const plsvo_poseopt_result* o) {
+  int rc = plsvo_poseopt_upload(ctx, b);
+  if (rc != PLSVO_OK) return rc;
+  rc = plsvo_poseopt_launch(ctx, p);
+  if (rc != PLSVO_OK) return rc;
+  return plsvo_poseopt_download(ctx, o);
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+"""Deterministic synthetic inputs for the PL-SVO hot path.
+
+The reference ships no dataset and no tests; these generators produce inputs with exact ground
+truth: an analytic textured surface rendered by per-pixel ray/surface intersection, truncating
+2x2 half-sample pyramids (vk::halfSample scalar path, called from src/frame.cpp:171-180),
+reference-frame point / segment features with their exact 3D positions, and pose-optimiser
+observation sets with noise and outliers.
+
+Everything here is *input generation* (torch is used only as an array library so the same code
+runs on the CPU for tests and on the GPU for the benchmark); nothing is on the product path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+# ------------------------------------------------------------------------------------------------
+# cameras
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass(frozen=True)
+class Camera:
+    width: int
+    height: int
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+
+
+VGA = Camera(640, 480, 420.0, 420.0, 319.5, 239.5)
+HD720 = Camera(1280, 720, 840.0, 840.0, 639.5, 359.5)
+QVGA = Camera(320, 240, 210.0, 210.0, 159.5, 119.5)  # small case for fast CPU tests
+
+
+# ------------------------------------------------------------------------------------------------
+# SE3 helpers (float64, batched).  Pose layout = [qx,qy,qz,qw,tx,ty,tz] as in include/plsvo_b200.h
+# ------------------------------------------------------------------------------------------------
+
+
+def _hat(w: torch.Tensor) -> torch.Tensor:
+    z = torch.zeros_like(w[..., 0])
+    return torch.stack(
+        [
+            torch.stack([z, -w[..., 2], w[..., 1]], -1),
+            torch.stack([w[..., 2], z, -w[..., 0]], -1),
+            torch.stack([-w[..., 1], w[..., 0], z], -1),
+        ],
+        -2,
+    )
+
+
+def se3_exp_Rt(xi: torch.Tensor):
+    """xi [...,6] = (upsilon, omega) -> R [...,3,3], t [...,3]  (closed form, float64)."""
+    ups, om = xi[..., :3], xi[..., 3:]
+    th = om.norm(dim=-1, keepdim=True).clamp_min(1e-300)
+    W = _hat(om)
+    W2 = W @ W
+    th2 = (th * th)[..., None]
+    th_ = th[..., None]
+    small = th_ < 1e-8
+    a = torch.where(small, 1.0 - th2 / 6, torch.sin(th_) / th_)
+    b = torch.where(small, 0.5 - th2 / 24, (1 - torch.cos(th_)) / th2)
+    c = torch.where(small, 1.0 / 6 - th2 / 120, (th_ - torch.sin(th_)) / (th2 * th_))
+    I = torch.eye(3, dtype=xi.dtype, device=xi.device).expand(W.shape)
+    R = I + a * W + b * W2
+    V = I + b * W + c * W2
+    t = (V @ ups[..., None])[..., 0]
+    return R, t
+
+
+def R_to_quat(R: torch.Tensor) -> torch.Tensor:
+    """Rotation matrices [...,3,3] -> unit quaternions [...,4] as (x,y,z,w), w >= 0 (small rotations)."""
+    m = R
+    w = 0.5 * torch.sqrt((1.0 + m[..., 0, 0] + m[..., 1, 1] + m[..., 2, 2]).clamp_min(1e-30))
+    x = (m[..., 2, 1] - m[..., 1, 2]) / (4 * w)
+    y = (m[..., 0, 2] - m[..., 2, 0]) / (4 * w)
+    z = (m[..., 1, 0] - m[..., 0, 1]) / (4 * w)
+    q = torch.stack([x, y, z, w], -1)
+    return q / q.norm(dim=-1, keepdim=True)
+
+
+def quat_to_R(q: torch.Tensor) -> torch.Tensor:
+    x, y, z, w = q.unbind(-1)
+    return torch.stack(
+        [
+            torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+            torch.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+            torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1),
+        ],
+        -2,
+    )
+
+
+def pose7_from_Rt(R: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    return torch.cat([R_to_quat(R), t], -1)
+
+
+def pose7_to_Rt(p: torch.Tensor):
+    return quat_to_R(p[..., :4]), p[..., 4:]
+
+
+def pose_error(p_a, p_b):
+    """Parity metric of SURVEY.md §8d: (rotation angle of R_a R_b^T in rad, ||t_a-t_b|| / max(||t_b||,1e-12))."""
+    p_a = torch.as_tensor(p_a, dtype=torch.float64)
+    p_b = torch.as_tensor(p_b, dtype=torch.float64)
+    Ra, ta = pose7_to_Rt(p_a)
+    Rb, tb = pose7_to_Rt(p_b)
+    dR = Ra @ Rb.transpose(-1, -2)
+    # angle from the skew part (accurate for tiny angles)
+    s = 0.5 * torch.stack([dR[..., 2, 1] - dR[..., 1, 2], dR[..., 0, 2] - dR[..., 2, 0], dR[..., 1, 0] - dR[..., 0, 1]], -1)
+    sn = s.norm(dim=-1)
+    cs = 0.5 * (dR[..., 0, 0] + dR[..., 1, 1] + dR[..., 2, 2] - 1.0)
+    ang = torch.atan2(sn, cs)
+    rel_t = (ta - tb).norm(dim=-1) / tb.norm(dim=-1).clamp_min(1e-12)
+    return ang.numpy(), rel_t.numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# scene: Z(X,Y) = 2.0 + 0.15 sin(1.3X+0.4) cos(0.9Y), texture = 127 + sum_k a_k sin(w_k.(X,Y) + phi_k)
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Scene:
+    seed: int = 1001
+    n_waves: int = 24
+    amp: np.ndarray = field(init=False)
+    wvec: np.ndarray = field(init=False)
+    phase: np.ndarray = field(init=False)
+
+    def __post_init__(self):
+        rng = np.random.Generator(np.random.PCG64(self.seed))
+        self.amp = rng.uniform(2.0, 10.0, self.n_waves)
+        mag = rng.uniform(4.0, 60.0, self.n_waves)
+        ang = rng.uniform(0.0, 2 * math.pi, self.n_waves)
+        self.wvec = np.stack([mag * np.cos(ang), mag * np.sin(ang)], -1)
+        self.phase = rng.uniform(0.0, 2 * math.pi, self.n_waves)
+
+    @staticmethod
+    def surface(X, Y):
+        return 2.0 + 0.15 * torch.sin(1.3 * X + 0.4) * torch.cos(0.9 * Y)
+
+    @staticmethod
+    def surface_grad(X, Y):
+        zx = 0.15 * 1.3 * torch.cos(1.3 * X + 0.4) * torch.cos(0.9 * Y)
+        zy = -0.15 * 0.9 * torch.sin(1.3 * X + 0.4) * torch.sin(0.9 * Y)
+        return zx, zy
+
+    def texture(self, X, Y):
+        I = torch.full_like(X, 127.0)
+        for k in range(self.n_waves):
+            I = I + float(self.amp[k]) * torch.sin(float(self.wvec[k, 0]) * X + float(self.wvec[k, 1]) * Y + float(self.phase[k]))
+        return I
+
+    def intersect(self, R_f_w, t_f_w, dirs_c):
+        """World points where camera rays hit the surface.
+        R_f_w [B,3,3], t_f_w [B,3], dirs_c [B,N,3] (camera-frame directions, z=1) -> P_w [B,N,3]."""
+        Rt = R_f_w.transpose(-1, -2)
+        C = -(Rt @ t_f_w[..., None])[..., 0]  # camera centre in world [B,3]
+        d = dirs_c @ R_f_w  # rows: (R^T d_c)^T = d_c^T R  -> [B,N,3]
+        lam = torch.full(d.shape[:-1], 2.0, dtype=d.dtype, device=d.device)
+        Cx, Cy, Cz = C[:, None, 0], C[:, None, 1], C[:, None, 2]
+        for _ in range(12):
+            X = Cx + lam * d[..., 0]
+            Y = Cy + lam * d[..., 1]
+            g = Cz + lam * d[..., 2] - self.surface(X, Y)
+            zx, zy = self.surface_grad(X, Y)
+            gp = d[..., 2] - (zx * d[..., 0] + zy * d[..., 1])
+            lam = lam - g / gp
+        return torch.stack([Cx + lam * d[..., 0], Cy + lam * d[..., 1], Cz + lam * d[..., 2]], -1)
+
+    def render(self, cam: Camera, pose7: torch.Tensor, chunk: int = 64) -> torch.Tensor:
+        """pose7 [B,7] (T_f_w) -> u8 images [B,H,W]."""
+        dev = pose7.device
+        B = pose7.shape[0]
+        u = torch.arange(cam.width, dtype=torch.float64, device=dev)
+        v = torch.arange(cam.height, dtype=torch.float64, device=dev)
+        vv, uu = torch.meshgrid(v, u, indexing="ij")
+        dirs = torch.stack([(uu - cam.cx) / cam.fx, (vv - cam.cy) / cam.fy, torch.ones_like(uu)], -1).reshape(1, -1, 3)
+        out = torch.empty(B, cam.height, cam.width, dtype=torch.uint8, device=dev)
+        for s in range(0, B, chunk):
+            R, t = pose7_to_Rt(pose7[s : s + chunk])
+            P = self.intersect(R, t, dirs.expand(R.shape[0], -1, -1))
+            I = self.texture(P[..., 0], P[..., 1])
+            out[s : s + chunk] = I.round().clamp(0, 255).to(torch.uint8).reshape(-1, cam.height, cam.width)
+        return out
+
+
+def half_sample(img: torch.Tensor) -> torch.Tensor:
+    """vk::halfSample, scalar path: truncating mean of each 2x2 block (u8 [B,H,W] -> [B,H/2,W/2])."""
+    B, H, W = img.shape
+    h, w = H // 2, W // 2
+    x = img[:, : 2 * h, : 2 * w].to(torch.int32)
+    s = x[:, 0::2, 0::2] + x[:, 0::2, 1::2] + x[:, 1::2, 0::2] + x[:, 1::2, 1::2]
+    return (s // 4).to(torch.uint8)
+
+
+def build_pyramid(img0: torch.Tensor, n_levels: int):
+    """frame_utils::createImgPyramid (src/frame.cpp:171-180)."""
+    pyr = [img0]
+    for _ in range(1, n_levels):
+        pyr.append(half_sample(pyr[-1]))
+    return pyr
+
+
+# ------------------------------------------------------------------------------------------------
+# alignment batches
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class AlignData:
+    """Host (numpy) arrays of one alignment batch, shaped as include/plsvo_b200.h describes."""
+
+    cam: Camera
+    max_level: int
+    min_level: int
+    ref_pyr: dict  # level -> u8 [B,h,w]
+    cur_pyr: dict
+    T_ref_w: np.ndarray  # [B,7]
+    T_cur_w: np.ndarray  # [B,7] initial guess (= T_ref_w, frame_handler_mono.cpp:266)
+    T_cur_w_gt: np.ndarray  # [B,7]
+    pt_px: np.ndarray
+    pt_f: np.ndarray
+    pt_pos: np.ndarray
+    seg_spx: np.ndarray
+    seg_epx: np.ndarray
+    seg_sf: np.ndarray
+    seg_ef: np.ndarray
+    seg_spos: np.ndarray
+    seg_epos: np.ndarray
+    seg_length: np.ndarray
+    pt_valid: np.ndarray | None = None
+    seg_valid: np.ndarray | None = None
+    pt_count: np.ndarray | None = None
+    seg_count: np.ndarray | None = None
+
+    @property
+    def batch(self):
+        return self.T_ref_w.shape[0]
+
+    @property
+    def n_pts(self):
+        return self.pt_px.shape[1]
+
+    @property
+    def n_segs(self):
+        return self.seg_spx.shape[1]
+
+
+def _bearing(cam: Camera, px: torch.Tensor) -> torch.Tensor:
+    """vk::PinholeCamera::cam2world: normalised ((u-cx)/fx, (v-cy)/fy, 1)."""
+    d = torch.stack([(px[..., 0] - cam.cx) / cam.fx, (px[..., 1] - cam.cy) / cam.fy, torch.ones_like(px[..., 0])], -1)
+    return d / d.norm(dim=-1, keepdim=True)
+
+
+def make_align_batch(
+    cam: Camera = VGA,
+    batch: int = 8,
+    n_pts: int = 300,
+    n_segs: int = 80,
+    max_level: int = 4,
+    min_level: int = 2,
+    n_pyr_levels: int | None = None,
+    seed: int = 3000,
+    device: str | torch.device = "cpu",
+    motion_t: float = 0.03,
+    motion_r: float = 0.01,
+    margin: int | None = None,
+    scene: Scene | None = None,
+    keep_levels_only: bool = True,
+) -> AlignData:
+    """SURVEY.md §8d config C2 generator: B independent frame pairs, each with its own reference view,
+    features and motion (seeds derived from `seed`)."""
+    dev = torch.device(device)
+    scene = scene or Scene()
+    n_pyr_levels = n_pyr_levels or (max_level + 1)
+    margin = margin if margin is not None else 4 * (1 << max_level)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    # reference views: small random pose around the origin so that every pair sees different pixels
+    xi_ref = np.concatenate([rng.uniform(-0.2, 0.2, (batch, 3)), rng.uniform(-0.03, 0.03, (batch, 3))], -1)
+    xi_mot = np.concatenate([rng.uniform(-motion_t, motion_t, (batch, 3)), rng.uniform(-motion_r, motion_r, (batch, 3))], -1)
+    R_ref, t_ref = se3_exp_Rt(torch.tensor(xi_ref, **f64))
+    R_m, t_m = se3_exp_Rt(torch.tensor(xi_mot, **f64))
+    R_cur = R_m @ R_ref  # T_cur_w = T_cur_from_ref * T_ref_w
+    t_cur = (R_m @ t_ref[..., None])[..., 0] + t_m
+    T_ref_w = pose7_from_Rt(R_ref, t_ref)
+    T_cur_w_gt = pose7_from_Rt(R_cur, t_cur)
+
+    ref0 = scene.render(cam, T_ref_w)
+    cur0 = scene.render(cam, T_cur_w_gt)
+    ref_pyr = build_pyramid(ref0, n_pyr_levels)
+    cur_pyr = build_pyramid(cur0, n_pyr_levels)
+    levels = range(min_level, max_level + 1) if keep_levels_only else range(n_pyr_levels)
+
+    lo_u, hi_u = margin, cam.width - margin
+    lo_v, hi_v = margin, cam.height - margin
+    pt_px = np.stack([rng.uniform(lo_u, hi_u, (batch, n_pts)), rng.uniform(lo_v, hi_v, (batch, n_pts))], -1)
+    # segments: start point uniform in the box, direction uniform, length U[60,240] clipped to the box
+    spx = np.stack([rng.uniform(lo_u, hi_u, (batch, n_segs)), rng.uniform(lo_v, hi_v, (batch, n_segs))], -1)
+    epx = np.empty_like(spx)
+    max_len = min(240.0, 0.5 * min(hi_u - lo_u, hi_v - lo_v))
+    min_len = min(60.0, 0.5 * max_len)
+    for b in range(batch):
+        for j in range(n_segs):
+            while True:
+                L = rng.uniform(min_len, max_len)
+                a = rng.uniform(0, 2 * math.pi)
+                e = spx[b, j] + L * np.array([math.cos(a), math.sin(a)])
+                if lo_u <= e[0] < hi_u and lo_v <= e[1] < hi_v:
+                    epx[b, j] = e
+                    break
+
+    def lift(px_np):
+        px = torch.tensor(px_np, **f64)
+        d = torch.stack([(px[..., 0] - cam.cx) / cam.fx, (px[..., 1] - cam.cy) / cam.fy, torch.ones_like(px[..., 0])], -1)
+        return _bearing(cam, px), scene.intersect(R_ref, t_ref, d)
+
+    pt_f, pt_pos = lift(pt_px)
+    seg_sf, seg_spos = lift(spx)
+    seg_ef, seg_epos = lift(epx)
+
+    npy = lambda t: np.ascontiguousarray(t.detach().cpu().numpy())
+    return AlignData(
+        cam=cam,
+        max_level=max_level,
+        min_level=min_level,
+        ref_pyr={l: npy(ref_pyr[l]) for l in levels},
+        cur_pyr={l: npy(cur_pyr[l]) for l in levels},
+        T_ref_w=npy(T_ref_w),
+        T_cur_w=npy(T_ref_w).copy(),
+        T_cur_w_gt=npy(T_cur_w_gt),
+        pt_px=np.ascontiguousarray(pt_px),
+        pt_f=npy(pt_f),
+        pt_pos=npy(pt_pos),
+        seg_spx=np.ascontiguousarray(spx),
+        seg_epx=np.ascontiguousarray(epx),
+        seg_sf=npy(seg_sf),
+        seg_ef=npy(seg_ef),
+        seg_spos=npy(seg_spos),
+        seg_epos=npy(seg_epos),
+        seg_length=np.ascontiguousarray(np.linalg.norm(epx - spx, axis=-1)),
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# pose-optimiser batches
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class PoseOptData:
+    fx: float
+    T_f_w: np.ndarray  # [B,7] initial (perturbed) pose
+    T_f_w_gt: np.ndarray
+    pt_f: np.ndarray
+    pt_pos: np.ndarray
+    pt_level: np.ndarray
+    seg_line: np.ndarray
+    seg_spos: np.ndarray
+    seg_epos: np.ndarray
+    seg_level: np.ndarray
+    pt_valid: np.ndarray | None = None
+    seg_valid: np.ndarray | None = None
+    pt_count: np.ndarray | None = None
+    seg_count: np.ndarray | None = None
+
+    @property
+    def batch(self):
+        return self.T_f_w.shape[0]
+
+    @property
+    def n_pts(self):
+        return self.pt_f.shape[1]
+
+    @property
+    def n_segs(self):
+        return self.seg_line.shape[1]
+
+
+def make_poseopt_batch(
+    cam: Camera = VGA,
+    batch: int = 8,
+    n_pts: int = 300,
+    n_segs: int = 80,
+    seed: int = 5000,
+    noise_px: float = 0.5,
+    outlier_frac: float = 0.10,
+    pert_t: float = 0.02,
+    pert_r: float = 0.01,
+    scene: Scene | None = None,
+) -> PoseOptData:
+    """B frames; observations = GT projection + N(0,(noise_px/fx)^2) on the unit plane, 10 % outliers
+    (U[5,30] px), level in {0,1,2}; initial pose = exp(delta) * T_gt."""
+    scene = scene or Scene()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f64 = dict(dtype=torch.float64)
+    xi_gt = np.concatenate([rng.uniform(-0.2, 0.2, (batch, 3)), rng.uniform(-0.03, 0.03, (batch, 3))], -1)
+    R_gt, t_gt = se3_exp_Rt(torch.tensor(xi_gt, **f64))
+    xi_d = np.concatenate([rng.uniform(-pert_t, pert_t, (batch, 3)), rng.uniform(-pert_r, pert_r, (batch, 3))], -1)
+    R_d, t_d = se3_exp_Rt(torch.tensor(xi_d, **f64))
+    R0 = R_d @ R_gt
+    t0 = (R_d @ t_gt[..., None])[..., 0] + t_d
+
+    def world_points(px_np):
+        px = torch.tensor(px_np, **f64)
+        d = torch.stack([(px[..., 0] - cam.cx) / cam.fx, (px[..., 1] - cam.cy) / cam.fy, torch.ones_like(px[..., 0])], -1)
+        return scene.intersect(R_gt, t_gt, d), d
+
+    def perturb(uv1, n):
+        """uv1 [B,n,3] unit-plane coords -> noisy, with outliers."""
+        uv = uv1[..., :2].clone()
+        uv += torch.tensor(rng.normal(0.0, noise_px / cam.fx, uv.shape), **f64)
+        out = rng.uniform(0, 1, (batch, n)) < outlier_frac
+        mag = rng.uniform(5.0, 30.0, (batch, n)) / cam.fx
+        ang = rng.uniform(0, 2 * math.pi, (batch, n))
+        off = torch.tensor(np.stack([mag * np.cos(ang), mag * np.sin(ang)], -1) * out[..., None], **f64)
+        return uv + off
+
+    m = 16
+    pt_px = np.stack([rng.uniform(m, cam.width - m, (batch, n_pts)), rng.uniform(m, cam.height - m, (batch, n_pts))], -1)
+    pt_pos, d = world_points(pt_px)
+    uv = perturb(d, n_pts)
+    f = torch.cat([uv, torch.ones_like(uv[..., :1])], -1)
+    pt_f = f / f.norm(dim=-1, keepdim=True)
+    pt_level = rng.integers(0, 3, (batch, n_pts)).astype(np.int32)
+
+    spx = np.stack([rng.uniform(m, cam.width - m, (batch, n_segs)), rng.uniform(m, cam.height - m, (batch, n_segs))], -1)
+    epx = np.stack([rng.uniform(m, cam.width - m, (batch, n_segs)), rng.uniform(m, cam.height - m, (batch, n_segs))], -1)
+    seg_spos, ds = world_points(spx)
+    seg_epos, de = world_points(epx)
+    s_uv = perturb(ds, n_segs)
+    e_uv = perturb(de, n_segs)
+    sf = torch.cat([s_uv, torch.ones_like(s_uv[..., :1])], -1)
+    ef = torch.cat([e_uv, torch.ones_like(e_uv[..., :1])], -1)
+    sf = sf / sf.norm(dim=-1, keepdim=True)
+    ef = ef / ef.norm(dim=-1, keepdim=True)
+    line = torch.linalg.cross(sf, ef)  # src/feature.cpp:93-107
+    line = line / torch.sqrt(line[..., 0:1] ** 2 + line[..., 1:2] ** 2)
+    seg_level = rng.integers(0, 3, (batch, n_segs)).astype(np.int32)
+
+    npy = lambda t: np.ascontiguousarray(t.detach().cpu().numpy())
+    return PoseOptData(
+        fx=cam.fx,
+        T_f_w=npy(pose7_from_Rt(R0, t0)),
+        T_f_w_gt=npy(pose7_from_Rt(R_gt, t_gt)),
+        pt_f=npy(pt_f),
+        pt_pos=npy(pt_pos),
+        pt_level=pt_level,
+        seg_line=npy(line),
+        seg_spos=npy(seg_spos),
+        seg_epos=npy(seg_epos),
+        seg_level=seg_level,
+    )
