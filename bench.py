@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--n-segs", type=int, default=80)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs per CPU-baseline pass (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident leg only, compact output (tuning)")
     return ap.parse_args()
 
 
@@ -212,7 +213,10 @@ def main():
                                                 "seg_ef", "seg_spos", "seg_epos", "seg_length"))
     h2d += sum(v.nbytes for v in data.ref_pyr.values()) + sum(v.nbytes for v in data.cur_pyr.values())
 
-    stream = torch.cuda.current_stream(dev)
+    # a non-default torch stream, handed to the C ABI so that torch.cuda.Event sees the kernels
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = plsvo_b200.Context(local_rank, stream.cuda_stream)
     al = plsvo_b200.SparseImgAlign(4, 2, 30, plsvo_b200.SparseImgAlign.GaussNewton, False, False, ctx=ctx)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -250,6 +254,16 @@ def main():
     torch.cuda.synchronize(dev)
     max_ms = float(t_total.item())
     value = n_gpus * B * args.steps / (max_ms * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": max_ms / args.steps,
+                              "kernel_ms": [round(x, 4) for x in kernel_ms],
+                              "lib": os.environ.get("PLSVO_LIB", "default"),
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("PLSVO_")}}))
+        if dist:
+            dist.destroy_process_group()
+        return 0
 
     # ---- end-to-end leg: host buffers -> C ABI -> host results, every step ----
     for _ in range(2):

@@ -209,6 +209,12 @@ int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* batch,
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 int64_t plsvo_launch_count(const plsvo_ctx* ctx);
 
+/* Device self-test of the fp32 weight kernel: evaluates w = 1/(1+a) with the product's fp32
+ * sequence and with the reference's double-then-narrow expression (sparse_img_align.cpp:479) for
+ * n pseudo-random a in [0,256) plus all n_exhaustive first float bit patterns of [0,256), and
+ * returns the number of bitwise mismatches. */
+int plsvo_selftest_weight(plsvo_ctx* ctx, uint32_t n, uint32_t seed, uint64_t* mismatches);
+
 /* library build info: "plsvo_b200 <version> sm_100a" */
 const char* plsvo_version(void);
 

@@ -638,7 +638,11 @@ struct SparseImgAlign {
   // vk::NLLSSolver<6,SE3>::optimizeGaussNewton + SparseImgAlign::solve/update (:697-710)
   void optimize(SE3& model) {
     if (use_weights_) {  // pre-pass: computeResiduals(model, false, true)
+      // (work executed by the reference but without observable effect beyond what iteration 0
+      // repeats at the same model; excluded from the patch_iters accounting, which counts GN passes)
+      const uint32_t saved = patch_iters;
       computeResiduals(model);
+      patch_iters = saved;
     }
     SE3 old_model = model;
     for (iter_ = 0; iter_ < n_iter_; ++iter_) {

@@ -297,6 +297,7 @@ ABI_SYMBOLS = [
     ("plsvo_poseopt_download", C.c_int, [C.c_void_p, _P(PoseOptResult)]),
     ("plsvo_poseopt_batch_run", C.c_int, [C.c_void_p, _P(PoseOptBatch), _P(PoseOptParams), _P(PoseOptResult)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
+    ("plsvo_selftest_weight", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
     ("plsvo_version", C.c_char_p, []),
 ]
 
@@ -308,7 +309,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("PLSVO_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: the CUDA extension has not been built (run `python __graft_entry__.py build`). "

@@ -71,7 +71,7 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_pat
   L.ctl = o;
   o = align_up(o + (uint32_t)sizeof(PairCtl), 16);
   L.red = o;
-  o += kAlignWarps * 32 * 8;
+  o += 8 * 32 * 8;  // cross-warp partials (up to 8 warps)
   L.tot = o;
   o += 32 * 8;
   L.seg_N = o;
@@ -94,7 +94,7 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_pat
   if (cache_in_smem) o += (uint32_t)kCacheRows * 16u * (uint32_t)max_patches;
   o = align_up(o, 128);
   L.img = o;
-  o += (uint32_t)img_bytes;
+  o += (uint32_t)img_bytes + 16u;  // slack: the 5-byte row reads fetch whole aligned words
   L.total = o;
   return L;
 }
@@ -169,22 +169,40 @@ __device__ __forceinline__ void rank2_update(double* acc, double X, double Y, do
 // One patch of the residual pass.  WEIGHTED = point patch (:450-500: w = 1/(1+|r|)), otherwise a
 // segment sample (:612-637: unweighted sums, |r| collected).  Returns false if the warped patch
 // is not fully inside the current image (isInFrame(halfsize)).
+// Per-pixel values (bilinear intensity, residual, weight, chi2 term) are bit-identical to the
+// reference's float arithmetic; the five in-patch sums run in fp32 FMAs over the 16 pixels and
+// are widened to double per patch (the reference accumulates every pixel in double: the
+// difference is ~1e-7 relative on one patch's contribution and does not move the fixed point).
 template <bool WEIGHTED>
 __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
                                            const float4* cache, int MP, int p, double u, double v,
-                                           double* S /*[5]*/, float& chi2_or_sumabs) {
+                                           double* S /*[6]*/, float& sumabs) {
   int ui, vi;
   float wTL, wTR, wBL, wBR;
   if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
-  const uint8_t* base = img + (size_t)(vi - 2) * pitch + (ui - 2);
+  // 5x5 footprint: per row two aligned 32-bit loads + funnel shift (rows are 16B-pitched)
+  const int c0 = ui - 2;
+  const int sh = (c0 & 3) * 8;
+  const uint8_t* base = img + (size_t)(vi - 2) * pitch + (c0 & ~3);
   float f[5][5];
 #pragma unroll
-  for (int r = 0; r < 5; ++r)
-#pragma unroll
-    for (int c = 0; c < 5; ++c) f[r][c] = u8f(base[r * pitch + c]);
+  for (int r = 0; r < 5; ++r) {
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base + r * pitch);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + r * pitch + 4);
+    const uint32_t lo = __funnelshift_r(w0, w1, sh);
+    const uint32_t hi = w1 >> sh;
+    f[r][0] = byte_to_float(lo, 0);
+    f[r][1] = byte_to_float(lo, 1);
+    f[r][2] = byte_to_float(lo, 2);
+    f[r][3] = byte_to_float(lo, 3);
+    f[r][4] = byte_to_float(hi, 0);
+  }
+#ifdef PLSVO_FP64_SUMS
   double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0;
+#else
+  float Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sxr = 0.f, Syr = 0.f;
+#endif
   float acc_f = 0.f;
-  double chi2 = 0.0;
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
     const float4 ref4 = cache[(0 + y) * MP + p];
@@ -197,29 +215,46 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
     for (int x = 0; x < 4; ++x) {
       const float cur = bilin(wTL, wTR, wBL, wBR, f[y][x], f[y][x + 1], f[y + 1][x], f[y + 1][x + 1]);
       const float res = __fsub_rn(cur, refv[x]);
-      const double dxd = (double)dxv[x], dyd = (double)dyv[x], rd = (double)res;
+      const float dx = dxv[x], dy = dyv[x];
       if (WEIGHTED) {
-        const float w = (float)(1.0 / (1.0 + (double)fabsf(res)));  // :479
-        chi2 += (double)__fmul_rn(__fmul_rn(res, res), w);          // :484 (terms in float, sum in double)
-        const double wdx = (double)w * dxd, wdy = (double)w * dyd;
-        Sxx += wdx * dxd;
-        Sxy += wdx * dyd;
-        Syy += wdy * dyd;
-        Sxr += wdx * rd;
-        Syr += wdy * rd;
+        const float w = weight_rcp(fabsf(res));                              // :479
+        acc_f = __fadd_rn(acc_f, __fmul_rn(__fmul_rn(res, res), w));         // :484
+#ifdef PLSVO_FP64_SUMS
+        const double wdx = (double)w * (double)dx, wdy = (double)w * (double)dy;
+        Sxx += wdx * (double)dx;
+        Sxy += wdx * (double)dy;
+        Syy += wdy * (double)dy;
+        Sxr += wdx * (double)res;
+        Syr += wdy * (double)res;
+#else
+        const float wdx = w * dx, wdy = w * dy;
+        Sxx = fmaf(wdx, dx, Sxx);
+        Sxy = fmaf(wdx, dy, Sxy);
+        Syy = fmaf(wdy, dy, Syy);
+        Sxr = fmaf(wdx, res, Sxr);
+        Syr = fmaf(wdy, res, Syr);
+#endif
       } else {
         acc_f = __fadd_rn(acc_f, fabsf(res));  // :643
-        Sxx += dxd * dxd;
-        Sxy += dxd * dyd;
-        Syy += dyd * dyd;
-        Sxr += dxd * rd;
-        Syr += dyd * rd;
+#ifdef PLSVO_FP64_SUMS
+        Sxx += (double)dx * (double)dx;
+        Sxy += (double)dx * (double)dy;
+        Syy += (double)dy * (double)dy;
+        Sxr += (double)dx * (double)res;
+        Syr += (double)dy * (double)res;
+#else
+        Sxx = fmaf(dx, dx, Sxx);
+        Sxy = fmaf(dx, dy, Sxy);
+        Syy = fmaf(dy, dy, Syy);
+        Sxr = fmaf(dx, res, Sxr);
+        Syr = fmaf(dy, res, Syr);
+#endif
       }
     }
   }
-  S[0] = Sxx, S[1] = Sxy, S[2] = Syy, S[3] = Sxr, S[4] = Syr;
-  chi2_or_sumabs = WEIGHTED ? (float)0 : acc_f;
-  if (WEIGHTED) S[5] = chi2;
+  S[0] = (double)Sxx, S[1] = (double)Sxy, S[2] = (double)Syy, S[3] = (double)Sxr, S[4] = (double)Syr;
+  if (WEIGHTED) S[5] = (double)acc_f;  // chi2 of this patch
+  sumabs = acc_f;
   return true;
 }
 
@@ -228,12 +263,24 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
 __device__ __forceinline__ void precompute_patch(const uint8_t* __restrict__ img, int pitch, int ui, int vi, float wTL,
                                                  float wTR, float wBL, float wBR, float4* __restrict__ cache, int MP,
                                                  int p) {
-  const uint8_t* base = img + (size_t)(vi - 3) * pitch + (ui - 3);
+  const int c0 = ui - 3;
+  const int sh = (c0 & 3) * 8;
+  const uint8_t* base = img + (size_t)(vi - 3) * pitch + (c0 & ~3);
   float g[7][7];
 #pragma unroll
-  for (int r = 0; r < 7; ++r)
-#pragma unroll
-    for (int c = 0; c < 7; ++c) g[r][c] = u8f(__ldg(base + r * pitch + c));
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(base + r * pitch);
+    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+    const uint32_t lo = __funnelshift_r(w0, w1, sh);
+    const uint32_t hi = __funnelshift_r(w1, w2, sh);
+    g[r][0] = byte_to_float(lo, 0);
+    g[r][1] = byte_to_float(lo, 1);
+    g[r][2] = byte_to_float(lo, 2);
+    g[r][3] = byte_to_float(lo, 3);
+    g[r][4] = byte_to_float(hi, 0);
+    g[r][5] = byte_to_float(hi, 1);
+    g[r][6] = byte_to_float(hi, 2);
+  }
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
     float refv[4], dxv[4], dyv[4];
@@ -278,7 +325,23 @@ __device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level,
   ctl->iters_level[level] += 1;
   // chi2/n_meas_ : float / size_t -> float (:192)
   const double new_chi2 = (double)((float)tot[27] / (float)(unsigned long long)n_meas);
-  ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
+  {
+    double Hu[21], gg[6], xx[6];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Hu[i] = tot[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gg[i] = tot[21 + i];
+#ifdef PLSVO_PIVOT_ALWAYS
+    if (false) {
+#else
+    if (ldlt6_reg(Hu, gg, xx)) {
+#endif
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ctl->x[i] = xx[i];
+    } else {
+      ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);  // pivoted Eigen-style path (degenerate systems)
+    }
+  }
   if (isnan(ctl->x[0])) ctl->stop = 1;
   const bool reject = (ctl->iter > 0 && new_chi2 > ctl->chi2_prev) || ctl->stop;
   int flag;
@@ -310,8 +373,10 @@ __device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level,
   ctl->flag = flag;
 }
 
-template <bool CACHE_SMEM>
-__global__ void __launch_bounds__(kAlignThreads) sparse_img_align_kernel(const AlignArgs a) {
+template <bool CACHE_SMEM, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const AlignArgs a) {
+  constexpr int kAlignThreads = NT;
+  constexpr int kAlignWarps = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int MP = a.max_patches;
@@ -663,30 +728,82 @@ __global__ void __launch_bounds__(kAlignThreads) sparse_img_align_kernel(const A
 
 }  // namespace
 
+namespace {
+__global__ void weight_selftest_kernel(uint32_t n, uint32_t seed, unsigned long long* mismatch) {
+  unsigned long long bad = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // half of the samples: random bit patterns in [0,256); other half: residual-like values k/2^m
+    uint32_t h = (i ^ seed) * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    float a;
+    if (i & 1) {
+      a = __uint_as_float(h % 0x43800000u);  // all floats in [0,256)
+    } else {
+      a = (float)(h & 0xffffff) * (1.0f / 65536.0f);  // multiples of 2^-16 below 256
+    }
+    const float fast = weight_rcp(a);
+    const float ref = (float)(1.0 / (1.0 + (double)a));
+    if (__float_as_uint(fast) != __float_as_uint(ref)) ++bad;
+  }
+  if (bad) atomicAdd(mismatch, bad);
+}
+}  // namespace
+
+cudaError_t weight_selftest_launch(uint32_t n, uint32_t seed, unsigned long long* d_mismatch, cudaStream_t s) {
+  weight_selftest_kernel<<<592, 256, 0, s>>>(n, seed, d_mismatch);
+  return cudaGetLastError();
+}
+
 size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_patches, int img_bytes,
                         bool cache_in_smem) {
   return make_layout(n_pts, n_segs, max_patches, max_seg_patches, img_bytes, cache_in_smem).total;
 }
 
-cudaError_t align_kernel_prepare(bool cache_in_smem, size_t smem_bytes, int* ctas_per_sm) {
-  cudaError_t e;
-  if (cache_in_smem) {
-    e = cudaFuncSetAttribute(sparse_img_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<true>, kAlignThreads,
-                                                         smem_bytes);
-  }
-  e = cudaFuncSetAttribute(sparse_img_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+namespace {
+template <bool CS, int NT>
+cudaError_t prepare_t(size_t smem_bytes, int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(sparse_img_align_kernel<CS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<false>, kAlignThreads,
-                                                       smem_bytes);
+  e = cudaFuncSetAttribute(sparse_img_align_kernel<CS, NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<CS, NT>, NT, smem_bytes);
+}
+}  // namespace
+
+cudaError_t align_kernel_prepare(bool cache_in_smem, int threads, size_t smem_bytes, int* ctas_per_sm) {
+  switch (threads) {
+    case 64:
+      return cache_in_smem ? prepare_t<true, 64>(smem_bytes, ctas_per_sm) : prepare_t<false, 64>(smem_bytes, ctas_per_sm);
+    case 128:
+      return cache_in_smem ? prepare_t<true, 128>(smem_bytes, ctas_per_sm) : prepare_t<false, 128>(smem_bytes, ctas_per_sm);
+    case 256:
+      return cache_in_smem ? prepare_t<true, 256>(smem_bytes, ctas_per_sm) : prepare_t<false, 256>(smem_bytes, ctas_per_sm);
+    default:
+      return cudaErrorInvalidValue;
+  }
 }
 
-cudaError_t align_kernel_launch(const AlignArgs& a, int grid, size_t smem_bytes, bool cache_in_smem, cudaStream_t s) {
-  if (cache_in_smem)
-    sparse_img_align_kernel<true><<<grid, kAlignThreads, smem_bytes, s>>>(a);
-  else
-    sparse_img_align_kernel<false><<<grid, kAlignThreads, smem_bytes, s>>>(a);
+cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, size_t smem_bytes, bool cache_in_smem,
+                                cudaStream_t s) {
+#define PLSVO_LAUNCH(CS, NT) sparse_img_align_kernel<CS, NT><<<grid, NT, smem_bytes, s>>>(a)
+  switch (threads) {
+    case 64:
+      if (cache_in_smem) PLSVO_LAUNCH(true, 64); else PLSVO_LAUNCH(false, 64);
+      break;
+    case 128:
+      if (cache_in_smem) PLSVO_LAUNCH(true, 128); else PLSVO_LAUNCH(false, 128);
+      break;
+    case 256:
+      if (cache_in_smem) PLSVO_LAUNCH(true, 256); else PLSVO_LAUNCH(false, 256);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef PLSVO_LAUNCH
   return cudaGetLastError();
 }
 

@@ -260,6 +260,82 @@ static __device__ __noinline__ void inverse6(const double* A, double* out, doubl
   }
 }
 
+
+// ---- register-resident, fully unrolled LDL^T solve of the symmetric 6x6 system (no pivoting).
+// H is a sum of weighted outer products (SPD unless degenerate); when a pivot is not safely
+// positive the caller falls back to the pivoted Eigen-style routine above, which also defines
+// the zero / NaN behaviour.  Hu = upper triangle, row-major (21 values).
+__device__ __forceinline__ bool ldlt6_reg(const double* Hu, const double* g, double* x) {
+  double A[6][6];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) A[j][i] = Hu[idx++];  // lower triangle
+  }
+  double dmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(A[i][i]));
+  const double tiny = 1e-13 * dmax;
+  double L[6][6], dinv[6], T[6][6];  // T[j][k] = L[j][k]*d[k]
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j][k] * T[j][k];
+
+    ok = ok && (s > tiny);
+    dinv[j] = 1.0 / s;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i][k] * T[j][k];
+      T[i][j] = t;
+      L[i][j] = t * dinv[j];
+    }
+  }
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= L[i][k] * z[k];
+    z[i] = t;
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double t = z[i] * dinv[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) t -= L[k][i] * x[k];
+    x[i] = t;
+  }
+  return ok;
+}
+
+// RN_float(1/(1+a)) for a >= 0 without leaving fp32: the reference evaluates
+// `1.0/(1.0+fabsf(res))` in double and narrows (sparse_img_align.cpp:479).  1+a is split exactly
+// into sh+sl (TwoSum), q0 = RN(1/sh), one Newton step with the exact residual.  Equal to the
+// double-then-narrow result except when the true quotient lies within ~2^-48 relative of a
+// rounding boundary (checked exhaustively by plsvo_selftest_weight).
+__device__ __forceinline__ float weight_rcp(float a) {
+  const float sh = __fadd_rn(1.0f, a);
+  const float bb = __fsub_rn(sh, 1.0f);
+  const float sl = __fadd_rn(__fsub_rn(1.0f, __fsub_rn(sh, bb)), __fsub_rn(a, bb));
+  float q0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(sh));  // MUFU.RCP; refined below
+  float e = __fmaf_rn(-sh, q0, 1.0f);
+  e = __fmaf_rn(-sl, q0, e);
+  return __fmaf_rn(e, q0, q0);
+}
+
+// byte k of w as float, via PRMT + FADD (keeps the XU conversion pipe free): 0x4B0000bb = 2^23 + bb
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k) {
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k)), 8388608.0f);
+}
+
 // Frame::jacobian_xyz2uv rows (include/plsvo/frame.h:138-160)
 __device__ __forceinline__ void jacobian_rows(double x, double y, double z, double* r0, double* r1) {
   const double z_inv = 1. / z;

@@ -7,8 +7,6 @@
 
 namespace plsvo {
 
-constexpr int kAlignThreads = 256;  // threads per CTA of the alignment kernel (8 warps)
-constexpr int kAlignWarps = kAlignThreads / 32;
 constexpr int kCacheRows = 12;  // float4 rows per patch: 4 ref + 4 dx + 4 dy
 
 // Device-layout description of one alignment batch (all pointers are device pointers).
@@ -67,8 +65,10 @@ struct AlignLaunchInfo {
 
 // shared memory the kernel needs for a configuration (host + device agree through this)
 size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_patches, int img_bytes, bool cache_in_smem);
-cudaError_t align_kernel_prepare(bool cache_in_smem, size_t smem_bytes, int* ctas_per_sm);
-cudaError_t align_kernel_launch(const AlignArgs& a, int grid, size_t smem_bytes, bool cache_in_smem, cudaStream_t s);
+cudaError_t align_kernel_prepare(bool cache_in_smem, int threads, size_t smem_bytes, int* ctas_per_sm);
+cudaError_t weight_selftest_launch(uint32_t n, uint32_t seed, unsigned long long* d_mismatch, cudaStream_t s);
+cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, size_t smem_bytes, bool cache_in_smem,
+                                cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 struct PoseOptArgs {

@@ -206,6 +206,22 @@ int64_t plsvo_launch_count(const plsvo_ctx* ctx) {
   return ctx ? reinterpret_cast<const plsvo_ctx_impl*>(ctx)->launches : 0;
 }
 
+int plsvo_selftest_weight(plsvo_ctx* ctx, uint32_t n, uint32_t seed, uint64_t* mismatches) {
+  if (!ctx || !mismatches) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  CK(cudaSetDevice(c->device));
+  CK(ensure(c->d_counter, 256));
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->d_counter.p) + 64);
+  CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
+  CK(weight_selftest_launch(n, seed, d, c->stream));
+  c->launches += 1;
+  unsigned long long h = 0;
+  CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *mismatches = h;
+  return PLSVO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // alignment
 // ------------------------------------------------------------------------------------------------
@@ -367,8 +383,15 @@ int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
     cache_in_smem = false;
     if (smem > (size_t)limit) return fail(c, PLSVO_ERR_INVALID, "feature counts exceed the shared-memory plan");
   }
+  // CTA size: small CTAs keep more independent frame pairs in flight per SM (each pair's serial
+  // solve / barriers then stall fewer warps) and let the hardware scheduler balance pairs of
+  // different iteration counts; big CTAs cut per-pair latency when the batch is small.
+  int threads = 128;
+  if (a.B <= c->num_sms) threads = 256;
+  const char* tenv = getenv("PLSVO_THREADS");
+  if (tenv && (atoi(tenv) == 64 || atoi(tenv) == 128 || atoi(tenv) == 256)) threads = atoi(tenv);
   int ctas_per_sm = 0;
-  CK(align_kernel_prepare(cache_in_smem, smem, &ctas_per_sm));
+  CK(align_kernel_prepare(cache_in_smem, threads, smem, &ctas_per_sm));
   if (ctas_per_sm < 1) return fail(c, PLSVO_ERR_INVALID, "kernel does not fit on an SM");
   const char* cap = getenv("PLSVO_CTAS_PER_SM");
   if (cap && atoi(cap) > 0) ctas_per_sm = std::min(ctas_per_sm, atoi(cap));
@@ -380,7 +403,7 @@ int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
   a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
   a.ws_xyz = static_cast<double*>(c->d_ws_xyz.p);
   CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), c->stream));
-  CK(align_kernel_launch(a, grid, smem, cache_in_smem, c->stream));
+  CK(align_kernel_launch(a, grid, threads, smem, cache_in_smem, c->stream));
   c->launches += 1;
   return PLSVO_OK;
 }
