@@ -28,12 +28,6 @@ namespace plsvo {
 
 namespace {
 
-struct SegStash {  // per segment-sample scratch: unweighted sums of one pass (or sample px during precompute)
-  double S[5];
-  float sumabs;
-  int ok;
-};
-
 struct PairCtl {
   double R[9];
   double t[3];
@@ -53,13 +47,14 @@ struct PairCtl {
   int stop;
   int iter;
   int n_seg_patches;
+  int seg_gshift;  // log2 of the lane-group size of a segment at the current level
   unsigned int patch_iters;
   unsigned int patch_levels;
   int iters_level[PLSVO_MAX_LEVELS];
 };
 
 struct Layout {
-  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, patch_seg, stash, pt_vis, xyz, cache, img, total;
+  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, seg_px, pt_vis, xyz, cache, img, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -78,17 +73,15 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_pat
   o += 4u * (uint32_t)n_segs;
   L.seg_off = o;
   o += 4u * (uint32_t)n_segs;
-  L.stash = align_up(o, 8);
-  o = L.stash + (uint32_t)sizeof(SegStash) * (uint32_t)max_seg_patches;
-  L.patch_seg = o;
-  o += 2u * (uint32_t)max_seg_patches;
+  L.seg_px = align_up(o, 16);
+  o = L.seg_px + 16u * (uint32_t)max_seg_patches;  // 2D centre of every segment sample (precompute only)
   L.seg_alive = o;
   o += (uint32_t)n_segs;
   L.pt_vis = o;
   o += (uint32_t)n_pts;
   o = align_up(o, 16);
   L.xyz = o;
-  if (cache_in_smem) o += 3u * 8u * (uint32_t)max_patches;
+  o += 4u * 8u * (uint32_t)max_patches;  // X, Y, Z, 1/Z of every patch's 3D point in the ref frame
   o = align_up(o, 16);
   L.cache = o;
   if (cache_in_smem) o += (uint32_t)kCacheRows * 16u * (uint32_t)max_patches;
@@ -147,10 +140,10 @@ __device__ __forceinline__ bool cam_in_frame(int ox, int oy, int boundary, int l
 
 // rank-2 update of the 21 (upper-triangular H) + 6 (Jres) accumulators of one thread:
 //   H += Sxx r0 r0^T + Sxy (r0 r1^T + r1 r0^T) + Syy r1 r1^T ,  Jres -= Sxr r0 + Syr r1
-__device__ __forceinline__ void rank2_update(double* acc, double X, double Y, double Z, double Sxx, double Sxy,
+__device__ __forceinline__ void rank2_update(double* acc, double X, double Y, double z_inv, double Sxx, double Sxy,
                                              double Syy, double Sxr, double Syr) {
   double r0[6], r1[6];
-  jacobian_rows(X, Y, Z, r0, r1);
+  jacobian_rows_zinv(X, Y, z_inv, r0, r1);
   double p[6], q[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -281,18 +274,24 @@ __device__ __forceinline__ void precompute_patch(const uint8_t* __restrict__ img
     g[r][5] = byte_to_float(hi, 1);
     g[r][6] = byte_to_float(hi, 2);
   }
+  // V[a][b] = interpolated intensity at integer offset (a-1, b-1) from the patch origin; the
+  // reference evaluates the same bilinear expression for ref / dx / dy of neighbouring pixels
+  // (:251-258), so each value is computed once here (corners are never used).
+  float V[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+      if (!((r == 0 || r == 5) && (c == 0 || c == 5)))
+        V[r][c] = bilin(wTL, wTR, wBL, wBR, g[r][c], g[r][c + 1], g[r + 1][c], g[r + 1][c + 1]);
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
     float refv[4], dxv[4], dyv[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-      const int r = y + 1, c = x + 1;
-#define PLSVO_IAT(dr, dc) \
-  bilin(wTL, wTR, wBL, wBR, g[r + (dr)][c + (dc)], g[r + (dr)][c + (dc) + 1], g[r + (dr) + 1][c + (dc)], g[r + (dr) + 1][c + (dc) + 1])
-      refv[x] = PLSVO_IAT(0, 0);
-      dxv[x] = __fmul_rn(0.5f, __fsub_rn(PLSVO_IAT(0, 1), PLSVO_IAT(0, -1)));
-      dyv[x] = __fmul_rn(0.5f, __fsub_rn(PLSVO_IAT(1, 0), PLSVO_IAT(-1, 0)));
-#undef PLSVO_IAT
+      refv[x] = V[y + 1][x + 1];
+      dxv[x] = __fmul_rn(0.5f, __fsub_rn(V[y + 1][x + 2], V[y + 1][x]));
+      dyv[x] = __fmul_rn(0.5f, __fsub_rn(V[y + 2][x + 1], V[y][x + 1]));
     }
     cache[(0 + y) * MP + p] = make_float4(refv[0], refv[1], refv[2], refv[3]);
     cache[(4 + y) * MP + p] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
@@ -387,18 +386,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
   uint8_t* seg_alive = smem + L.seg_alive;
   int* seg_N = reinterpret_cast<int*>(smem + L.seg_N);
   int* seg_off = reinterpret_cast<int*>(smem + L.seg_off);
-  uint16_t* patch_seg = reinterpret_cast<uint16_t*>(smem + L.patch_seg);
-  SegStash* stash = reinterpret_cast<SegStash*>(smem + L.stash);
+  double* seg_px = reinterpret_cast<double*>(smem + L.seg_px);
   uint8_t* pt_vis = smem + L.pt_vis;
   uint8_t* img_s = smem + L.img;
+  double* xyz = reinterpret_cast<double*>(smem + L.xyz);
   float4* cache;
-  double* xyz;
   if (CACHE_SMEM) {
     cache = reinterpret_cast<float4*>(smem + L.cache);
-    xyz = reinterpret_cast<double*>(smem + L.xyz);
   } else {
     cache = a.ws_cache + (size_t)blockIdx.x * kCacheRows * MP;
-    xyz = a.ws_xyz + (size_t)blockIdx.x * 3 * MP;
   }
   uint64_t* bar = reinterpret_cast<uint64_t*>(&ctl->mbar);
   if (tid == 0) {
@@ -462,9 +458,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       const double* f = a.pt_f + (po + i) * 3;
       const double dx = pos[0] - rpx, dy = pos[1] - rpy, dz = pos[2] - rpz;
       const double depth = sqrt(dx * dx + dy * dy + dz * dz);
+      const double Zr = f[2] * depth;
       xyz[0 * MP + i] = f[0] * depth;
       xyz[1 * MP + i] = f[1] * depth;
-      xyz[2 * MP + i] = f[2] * depth;
+      xyz[2 * MP + i] = Zr;
+      xyz[3 * MP + i] = 1. / Zr;  // z_inv of Frame::jacobian_xyz2uv (frame.h:144), constant per pair
     }
     for (int j = tid; j < ns; j += kAlignThreads) seg_alive[j] = a.seg_valid ? (a.seg_valid[so + j] ? 1 : 0) : 1;
     unsigned int my_patch_levels = 0;
@@ -478,7 +476,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       const uint8_t* cur_img_g = a.cur_img[level] + (size_t)b * a.stride[level];
       const bool stage = a.img_in_smem[level] != 0;
       const uint8_t* cur_img = stage ? img_s : cur_img_g;
-      __syncthreads();  // previous level's readers of img_s / stash are done
+      __syncthreads();  // previous level's readers of img_s are done
       if (tid == 0) {
         if (stage) {
           const uint32_t bytes = (uint32_t)rows * (uint32_t)pitch;
@@ -505,11 +503,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         seg_N[j] = N;
       }
       __syncthreads();
-      if (warp == 0) {  // exclusive scan of seg_N -> seg_off (cache offsets in patches, :282-292)
-        int carry = 0;
+      if (warp == 0) {  // exclusive scan of seg_N -> seg_off (cache offsets in patches, :282-292) + max N
+        int carry = 0, nmax = 1;
         for (int base = 0; base < ns; base += 32) {
           const int j = base + lane;
           const int v = (j < ns) ? seg_N[j] : 0;
+          nmax = max(nmax, v);
           int incl = v;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -519,11 +518,20 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
           if (j < ns) seg_off[j] = carry + incl - v;
           carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) ctl->n_seg_patches = carry;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+        if (lane == 0) {
+          ctl->n_seg_patches = carry;
+          int gs = 0;  // lane-group size per segment: smallest power of two >= max N, capped at a warp
+          while ((1 << gs) < nmax && gs < 5) ++gs;
+          ctl->seg_gshift = gs;
+        }
       }
       __syncthreads();
       const int n_sp = min(ctl->n_seg_patches, a.max_seg_patches);
       const int n_patches = np + n_sp;
+      const int gshift = ctl->seg_gshift;
+      const int G = 1 << gshift;
       // ---- expand segments into sample patches: 2D centre and 3D point by repeated addition (:323-335) ----
       for (int j = tid; j < ns; j += kAlignThreads) {
         const int N = seg_N[j];
@@ -551,12 +559,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         for (int n = 0; n < N; ++n) {
           const int sp_idx = off + n;
           if (sp_idx < n_sp) {
-            patch_seg[sp_idx] = (uint16_t)j;
-            stash[sp_idx].S[0] = px0;
-            stash[sp_idx].S[1] = px1;
+            seg_px[2 * sp_idx] = px0;
+            seg_px[2 * sp_idx + 1] = px1;
             xyz[0 * MP + np + sp_idx] = X;
             xyz[1 * MP + np + sp_idx] = Y;
             xyz[2 * MP + np + sp_idx] = Z;
+            xyz[3 * MP + np + sp_idx] = 1. / Z;
           }
           px0 += inc2d0, px1 += inc2d1;
           X += i0, Y += i1, Z += i2;
@@ -572,7 +580,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
           const double* px = a.pt_px + (po + p) * 2;
           u = px[0] * dscale, v = px[1] * dscale;
         } else {
-          u = stash[p - np].S[0], v = stash[p - np].S[1];
+          u = seg_px[2 * (p - np)], v = seg_px[2 * (p - np) + 1];
         }
         int ui, vi;
         float wTL, wTR, wBL, wBR;
@@ -596,6 +604,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       // ---- Gauss-Newton iterations at this level (vk::NLLSSolver::optimizeGaussNewton) ----
       const double cJ = fabs(a.fx) / (double)(1 << level);  // focal_length / 2^level (:262)
       const double cJ2 = cJ * cJ;
+      const int n_seg_slots = (ns << gshift);
       for (;;) {
         double acc[32];
 #pragma unroll
@@ -603,80 +612,100 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         const double R0 = ctl->R[0], R1 = ctl->R[1], R2 = ctl->R[2], R3 = ctl->R[3], R4 = ctl->R[4], R5 = ctl->R[5],
                      R6 = ctl->R[6], R7 = ctl->R[7], R8 = ctl->R[8];
         const double t0 = ctl->t[0], t1 = ctl->t[1], t2 = ctl->t[2];
-        for (int p = tid; p < n_patches; p += kAlignThreads) {
-          const bool is_pt = p < np;
-          if (is_pt && !pt_vis[p]) continue;
+        // ---- point patches (:380-502): thread per patch ----
+        for (int p = tid; p < np; p += kAlignThreads) {
+          if (!pt_vis[p]) continue;
           const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
           const double xc = R0 * X + R1 * Y + R2 * Z + t0;
           const double yc = R3 * X + R4 * Y + R5 * Z + t1;
           const double zc = R6 * X + R7 * Y + R8 * Z + t2;
-          const double u = (a.fx * (xc / zc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
-          const double v = (a.fy * (yc / zc) + a.cy) * dscale;
+          const double izc = 1.0 / zc;
+          const double u = (a.fx * (xc * izc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
+          const double v = (a.fy * (yc * izc) + a.cy) * dscale;
           double S[6];
           float aux;
-          if (is_pt) {
-            if (!eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) continue;
-            rank2_update(acc, X, Y, Z, S[0] * cJ2, S[1] * cJ2, S[2] * cJ2, S[3] * cJ, S[4] * cJ);
-            acc[27] += S[5];
-            acc[28] += 16.0;
-            acc[29] += 1.0;
-          } else {
-            SegStash& st = stash[p - np];
-            const bool ok = seg_alive[patch_seg[p - np]] &&
-                            eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux);
-            st.ok = ok ? 1 : 0;
-            if (ok) {
-              st.S[0] = S[0], st.S[1] = S[1], st.S[2] = S[2], st.S[3] = S[3], st.S[4] = S[4];
-              st.sumabs = aux;
-            }
-          }
+          if (!eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) continue;
+          rank2_update(acc, X, Y, xyz[3 * MP + p], S[0] * cJ2, S[1] * cJ2, S[2] * cJ2, S[3] * cJ, S[4] * cJ);
+          acc[27] += S[5];
+          acc[28] += 16.0;
+          acc[29] += 1.0;
         }
-        if (n_sp > 0) {
-          __syncthreads();
-          // ---- per-segment gate + weight (:640-688), applied by every sample thread of the segment ----
-          for (int sp_idx = tid; sp_idx < n_sp; sp_idx += kAlignThreads) {
-            const int j = patch_seg[sp_idx];
-            if (!seg_alive[j]) continue;
-            const int off = seg_off[j], N = seg_N[j];
-            float res_ = 0.f;
-            bool good = true;
-            int n_eval = 0;
-            for (int n = 0; n < N; ++n) {
-              const SegStash& s = stash[off + n];
-              if (!s.ok) {
-                good = false;
-                break;
-              }
-              res_ = __fadd_rn(res_, s.sumabs);
-              ++n_eval;
-            }
-            res_ = (float)((double)res_ / (double)(unsigned long long)N);  // :647
-            const bool first = (sp_idx == off);
-            if (good && (double)res_ < 200.0) {
-              const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
-              const SegStash& s = stash[sp_idx];
-              const double sH = (double)w / (double)res_ * cJ2;  // H += H_*weight/res_ (:681)
-              const double sJ = (double)w * cJ;                  // Jres += Jres_*weight (:682)
-              const int p = np + sp_idx;
-              rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], s.S[0] * sH, s.S[1] * sH,
-                           s.S[2] * sH, s.S[3] * sJ, s.S[4] * sJ);
-              if (first) {
-                acc[27] += (double)__fmul_rn(__fmul_rn(res_, res_), w);  // :683
-                acc[28] += 1.0;                                         // :684
-                acc[29] += (double)n_eval;
-              }
-            } else if (first) {
-              acc[29] += (double)n_eval;
-              patch_seg[sp_idx] |= 0x8000u;  // kill marker, applied after the barrier below
-            }
+        // ---- segment samples (:504-695): every segment owns a group of G = 2^gshift consecutive lanes
+        // of one warp (G >= its sample count, or the whole warp looping over samples), so the
+        // per-segment gate/weight (:640-688) is a few shuffles: no shared staging, no block barrier.
+        // Warps take segment rounds from the top so they interleave with the point rounds.
+        for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
+          const int q = base + lane;
+          const int j = q >> gshift;
+          const int n0 = q & (G - 1);
+          const bool seg_ok = (j < ns) && seg_alive[j];
+          const int N = seg_ok ? seg_N[j] : 0;
+          const int off = seg_ok ? seg_off[j] : 0;
+          double S[6] = {0, 0, 0, 0, 0, 0};
+          float my_abs = 0.f;
+          int first_bad = 0x7fffffff;
+          for (int n = n0; n < N; n += G) {  // one trip unless a segment has more samples than a warp
+            const int p = np + off + n;
+            const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
+            const double xc = R0 * X + R1 * Y + R2 * Z + t0;
+            const double yc = R3 * X + R4 * Y + R5 * Z + t1;
+            const double zc = R6 * X + R7 * Y + R8 * Z + t2;
+            const double izc = 1.0 / zc;
+            const double u = (a.fx * (xc * izc) + a.cx) * dscale;
+            const double v = (a.fy * (yc * izc) + a.cy) * dscale;
+            float aux;
+            if (eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux))
+              my_abs = __fadd_rn(my_abs, aux);
+            else
+              first_bad = min(first_bad, n);
           }
-          __syncthreads();
-          for (int sp_idx = tid; sp_idx < n_sp; sp_idx += kAlignThreads) {
-            const uint16_t v = patch_seg[sp_idx];
-            if (v & 0x8000u) {
-              patch_seg[sp_idx] = v & 0x7fffu;
-              seg_alive[v & 0x7fffu] = 0;  // it->feat3D = NULL (:688)
+          // group reductions: sum of |res| in sample order for small groups, first out-of-frame sample
+          float res_ = 0.f;
+          if (gshift <= 3) {
+            const int gbase = lane & ~(G - 1);
+            for (int n = 0; n < G; ++n) res_ = __fadd_rn(res_, __shfl_sync(0xffffffffu, my_abs, gbase + n));
+          } else {
+            res_ = my_abs;
+            for (int d = G >> 1; d >= 1; d >>= 1) res_ = __fadd_rn(res_, __shfl_xor_sync(0xffffffffu, res_, d));
+          }
+          for (int d = G >> 1; d >= 1; d >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, d));
+          if (N == 0) continue;
+          const bool good = first_bad >= N;
+          const int n_eval = good ? N : first_bad;       // samples evaluated before the loop stops (:588-594)
+          res_ = (float)((double)res_ / (double)(unsigned long long)N);  // :647
+          if (n0 == 0) acc[29] += (double)n_eval;
+          if (good && (double)res_ < 200.0) {
+            const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
+            const double sH = (double)w / (double)res_ * cJ2;     // H += H_*weight/res_ (:681)
+            const double sJ = (double)w * cJ;                     // Jres += Jres_*weight (:682)
+            if (N <= G) {
+              if (n0 < N) {
+                const int p = np + off + n0;
+                rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[3 * MP + p], S[0] * sH, S[1] * sH, S[2] * sH,
+                             S[3] * sJ, S[4] * sJ);
+              }
+            } else {
+              for (int n = n0; n < N; n += G) {  // long segment: re-evaluate this lane's samples
+                const int p = np + off + n;
+                const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
+                const double xc = R0 * X + R1 * Y + R2 * Z + t0;
+                const double yc = R3 * X + R4 * Y + R5 * Z + t1;
+                const double zc = R6 * X + R7 * Y + R8 * Z + t2;
+                const double izc = 1.0 / zc;
+                const double u = (a.fx * (xc * izc) + a.cx) * dscale;
+                const double v = (a.fy * (yc * izc) + a.cy) * dscale;
+                float aux;
+                double S2[6];
+                if (eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S2, aux))
+                  rank2_update(acc, X, Y, xyz[3 * MP + p], S2[0] * sH, S2[1] * sH, S2[2] * sH, S2[3] * sJ, S2[4] * sJ);
+              }
             }
+            if (n0 == 0) {
+              acc[27] += (double)__fmul_rn(__fmul_rn(res_, res_), w);  // :683
+              acc[28] += 1.0;                                         // :684
+            }
+          } else if (n0 == 0) {
+            seg_alive[j] = 0;  // it->feat3D = NULL (:688); the group's lanes have all read it already
           }
         }
         // ---- block reduction (deterministic order) ----

@@ -354,6 +354,22 @@ __device__ __forceinline__ void jacobian_rows(double x, double y, double z, doub
   r1[5] = -x * z_inv;
 }
 
+__device__ __forceinline__ void jacobian_rows_zinv(double x, double y, double z_inv, double* r0, double* r1) {
+  const double z_inv_2 = z_inv * z_inv;
+  r0[0] = -z_inv;
+  r0[1] = 0.0;
+  r0[2] = x * z_inv_2;
+  r0[3] = y * r0[2];
+  r0[4] = -(1.0 + x * r0[2]);
+  r0[5] = y * z_inv;
+  r1[0] = 0.0;
+  r1[1] = -z_inv;
+  r1[2] = y * z_inv_2;
+  r1[3] = 1.0 + y * r1[2];
+  r1[4] = -r0[3];
+  r1[5] = -x * z_inv;
+}
+
 // ---- shared-memory address + mbarrier + bulk async copy (TMA engine, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -398,7 +398,6 @@ int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
   const int grid = std::min(a.B, c->num_sms * ctas_per_sm);
   if (!cache_in_smem) {
     CK(ensure(c->d_ws_cache, (size_t)grid * kCacheRows * a.max_patches * sizeof(float4)));
-    CK(ensure(c->d_ws_xyz, (size_t)grid * 3 * a.max_patches * sizeof(double)));
   }
   a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
   a.ws_xyz = static_cast<double*>(c->d_ws_xyz.p);
