@@ -126,8 +126,17 @@ def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
         setattr(sub, name, np.ascontiguousarray(getattr(data, name)[sl]))
     sub.ref_pyr = {l: np.ascontiguousarray(v[sl]) for l, v in data.ref_pyr.items()}
     sub.cur_pyr = {l: np.ascontiguousarray(v[sl]) for l, v in data.cur_pyr.items()}
-    threads = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
-    oracle_lib.align(abi, sub, n_threads=threads)  # warm
+    hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+    # the box may expose more logical CPUs than it lets us run on: take the best of a few thread counts
+    best = None
+    for threads in sorted({hw, max(1, hw // 2), max(1, hw // 4), max(1, hw // 8)}, reverse=True):
+        oracle_lib.align(abi, sub, n_threads=threads)  # warm
+        t0 = time.perf_counter()
+        oracle_lib.align(abi, sub, n_threads=threads)
+        r = n_pairs / (time.perf_counter() - t0)
+        if best is None or r > best[0]:
+            best = (r, threads)
+    threads = best[1]
     t0 = time.perf_counter()
     reps = 0
     while True:
@@ -158,7 +167,16 @@ def main():
         n = args.cpu_sample or min(args.batch, 256)
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         data = synth.make_align_batch(batch=n, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=3000)
-        threads = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+        hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+        best = None  # logical CPUs may exceed what the box lets us run on: pick the fastest thread count
+        for th in sorted({hw, max(1, hw // 2), max(1, hw // 4), max(1, hw // 8)}, reverse=True):
+            oracle_lib.align(abi, data, n_threads=th)
+            t0 = time.perf_counter()
+            oracle_lib.align(abi, data, n_threads=th)
+            r = n / (time.perf_counter() - t0)
+            if best is None or r > best[0]:
+                best = (r, th)
+        threads = best[1]
         for _ in range(args.warmup):
             oracle_lib.align(abi, data, n_threads=threads)
         t0 = time.perf_counter()

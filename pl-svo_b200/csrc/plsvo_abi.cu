@@ -41,7 +41,7 @@ struct plsvo_ctx_impl {
   DevBuf d_ref_img, d_cur_img, d_T_ref, d_T_cur, d_pt_count, d_pt_px, d_pt_f, d_pt_pos, d_pt_valid, d_seg_count,
       d_seg_spx, d_seg_epx, d_seg_sf, d_seg_ef, d_seg_spos, d_seg_epos, d_seg_length, d_seg_valid;
   DevBuf d_out_T, d_out_ntr, d_out_H, d_out_killed, d_out_iters, d_out_status, d_out_pi, d_out_pl, d_counter,
-      d_ws_cache, d_ws_xyz;
+      d_ws_cache, d_ws_xyz, d_stage;
   size_t level_off[PLSVO_MAX_LEVELS];
 
   // ---- pose-opt state ----
@@ -163,7 +163,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
-                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->p_T,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -272,9 +272,21 @@ int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
     uint8_t* dc = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
     a.ref_img[l] = dr;
     a.cur_img[l] = dc;
-    if (h->img_stride[l] == (size_t)rows * h->img_pitch[l]) {  // uniformly pitched stack: one 2D copy
-      CK(cudaMemcpy2DAsync(dr, a.pitch[l], h->ref_img[l], h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpy2DAsync(dc, a.pitch[l], h->cur_img[l], h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyHostToDevice, s));
+    const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
+    if (uniform && h->img_pitch[l] == a.pitch[l]) {
+      // host stack already has the device layout: one linear copy per frame set
+      CK(cudaMemcpyAsync(dr, h->ref_img[l], a.stride[l] * B, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(dc, h->cur_img[l], a.stride[l] * B, cudaMemcpyHostToDevice, s));
+    } else if (uniform) {
+      // uniformly pitched stack with a different pitch: linear H2D into staging (PCIe-friendly), then a
+      // device-side 2D repack into the 16-byte-pitched layout (row-granular DMA over PCIe is slow)
+      const size_t bytes = h->img_stride[l] * B;
+      CK(ensure(c->d_stage, 2 * bytes));
+      uint8_t* st = static_cast<uint8_t*>(c->d_stage.p);
+      CK(cudaMemcpyAsync(st, h->ref_img[l], bytes, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(st + bytes, h->cur_img[l], bytes, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpy2DAsync(dr, a.pitch[l], st, h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpy2DAsync(dc, a.pitch[l], st + bytes, h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyDeviceToDevice, s));
     } else {
       for (size_t b = 0; b < B; ++b) {
         CK(cudaMemcpy2DAsync(dr + b * a.stride[l], a.pitch[l], h->ref_img[l] + b * h->img_stride[l], h->img_pitch[l], cols,
@@ -305,18 +317,15 @@ int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
   // per-level bound on segment samples per pair (sizes the sample slots; host arrays are still valid here)
   c->seg_patch_bound.assign(PLSVO_MAX_LEVELS, 0);
   if (h->n_segs > 0) {
-    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
-      int worst = 0;
-      for (size_t b = 0; b < B; ++b) {
-        const int ns = h->seg_count ? std::min(h->seg_count[b], h->n_segs) : h->n_segs;
-        int sum = 0;
-        for (int j = 0; j < ns; ++j) {
-          const size_t k = b * h->n_segs + j;
-          sum += host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], l);
-        }
-        worst = std::max(worst, sum);
+    for (size_t b = 0; b < B; ++b) {
+      const int ns = h->seg_count ? std::min(h->seg_count[b], h->n_segs) : h->n_segs;
+      int sum[PLSVO_MAX_LEVELS] = {0};
+      for (int j = 0; j < ns; ++j) {
+        const size_t k = b * h->n_segs + j;
+        const int n0 = host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], 0);
+        for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) sum[l] += 1 + ((n0 - 1) >> l);
       }
-      c->seg_patch_bound[l] = worst;
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], sum[l]);
     }
   }
 

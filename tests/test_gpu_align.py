@@ -129,3 +129,16 @@ def test_fp32_weight_matches_reference_expression(pkg):
     n = 1 << 26
     ctx.check(ctx.lib.plsvo_selftest_weight(ctx.handle, n, 12345, C.byref(bad)), "selftest")
     assert bad.value <= n * 1e-6, f"{bad.value} of {n} weights differ"
+
+
+def test_align_zero_residual_segment_raises_stop(pkg, abi, synth, oracle, gen_device):
+    """Identical images: a segment with zero mean residual makes the reference divide by zero
+    (sparse_img_align.cpp:681) -> NaN step -> stop_ (sticky) -> pose untouched.  Same on the GPU."""
+    data = synth.make_align_batch(cam=synth.QVGA, batch=4, n_pts=40, n_segs=8, max_level=3, min_level=1, seed=21,
+                                  margin=32, motion_t=0.0, motion_r=0.0, device=gen_device)
+    gpu, ref = _run_both(pkg, abi, synth, oracle, data, 3, 1)
+    np.testing.assert_array_equal(gpu.status, ref.status)
+    assert (gpu.status == 2).all()
+    np.testing.assert_array_equal(gpu.iters, ref.iters)
+    ang, rel = synth.pose_error(gpu.T_cur_w, ref.T_cur_w)
+    assert ang.max() < 1e-12
