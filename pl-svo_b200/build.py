@@ -34,3 +34,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
     return OUT
+
+
+HOST = os.path.join(_HERE, "host")
+SHIM_OUT = os.path.join(HOST, "libplsvo_shim.so")
+SHIM_SOURCES = ["plsvo_shim.cpp", "shim_harness.cpp"]
+
+
+def build_shim(force: bool = False) -> str:
+    """The signature-preserving C++ shim (host side above the C ABI) + its test harness, built against the
+    compat stand-in types (the reference's own headers are not available in this image)."""
+    deps = [os.path.join(HOST, f) for f in SHIM_SOURCES + ["plsvo_shim.h", "plsvo_compat.h"]] + [OUT]
+    if not force and os.path.exists(SHIM_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_OUT) for d in deps):
+        return SHIM_OUT
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", SHIM_OUT] + SHIM_SOURCES + [
+        "-L" + CSRC, "-lplsvo_b200", "-Wl,-rpath,$ORIGIN/../csrc"]
+    subprocess.check_call(cmd, cwd=HOST)
+    return SHIM_OUT

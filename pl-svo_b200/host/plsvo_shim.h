@@ -1,0 +1,60 @@
+// plsvo_shim.h — the reference's two entry points, source-compatible with their callers, over the
+// B200 C ABI (include/plsvo_b200.h).
+//
+//   plsvo::SparseImgAlign                     replaces include/plsvo/sparse_img_align.h:46-70
+//   plsvo::pose_optimizer::optimizeGaussNewton (x2) replaces include/plsvo/pose_optimizer.h:47-64
+//
+// src/frame_handler_mono.cpp:272-274, :327-329 and :418-420 compile against this header unchanged.
+// Build modes: with -DPLSVO_SHIM_WITH_REFERENCE_HEADERS the reference's own Frame / Feature /
+// Sophus / OpenCV types are used; otherwise the stand-ins of plsvo_compat.h.
+#pragma once
+#ifdef PLSVO_SHIM_WITH_REFERENCE_HEADERS
+#include <plsvo/feature.h>
+#include <plsvo/feature3D.h>
+#include <plsvo/frame.h>
+#include <plsvo/global.h>
+#include <vikit/pinhole_camera.h>
+#else
+#include "plsvo_compat.h"
+#endif
+#include <cstddef>
+
+namespace plsvo {
+
+/// Optimize the pose of the frame by minimizing the photometric error of feature patches.
+class SparseImgAlign {
+ public:
+  enum Method { GaussNewton, LevenbergMarquardt };  // vk::NLLSSolver::Method, named at the call site
+#ifdef PLSVO_SHIM_WITH_REFERENCE_HEADERS
+  cv::Mat resimg_;  // public member of the reference class (display only; never filled, display is false)
+#endif
+  SparseImgAlign(int max_level, int min_level, int n_iter, Method method, bool display, bool verbose);
+  /// returns n_meas_/16 (src/sparse_img_align.cpp:94); writes cur_frame->T_f_w_; nulls feat3D of
+  /// reference-frame segments the optimisation rejects (:687-688)
+  size_t run(FramePtr ref_frame, FramePtr cur_frame);
+  /// H_/(5e-4*255^2) (:97-102), 36 doubles row-major
+  void getFisherInformation(double out36[36]) const;
+#ifdef PLSVO_SHIM_WITH_REFERENCE_HEADERS
+  Eigen::Matrix<double, 6, 6> getFisherInformation();
+#endif
+
+ private:
+  int max_level_, min_level_, n_iter_;
+  double H_[36];
+};
+
+namespace pose_optimizer {
+void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter, const bool verbose, FramePtr& frame,
+                         double& estimated_scale, double& error_init, double& error_final, size_t& num_obs_pt,
+                         size_t& num_obs_ls);
+void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter, const size_t n_iter_ref, const bool verbose,
+                         FramePtr& frame, double& estimated_scale, double& error_init, double& error_final,
+                         size_t& num_obs_pt, size_t& num_obs_ls);
+}  // namespace pose_optimizer
+
+/// process-wide device context used by the shim (SparseImgAlign is stack-constructed per call at
+/// frame_handler_mono.cpp:272, so the device state cannot live in the object)
+int shim_set_device(int device);
+const char* shim_last_error();
+
+}  // namespace plsvo
