@@ -166,136 +166,150 @@ __device__ __forceinline__ void rank2_update(double* acc, double X, double Y, do
 // reference's float arithmetic; the five in-patch sums run in fp32 FMAs over the 16 pixels and
 // are widened to double per patch (the reference accumulates every pixel in double: the
 // difference is ~1e-7 relative on one patch's contribution and does not move the fixed point).
-template <bool WEIGHTED>
+// five consecutive image bytes starting at byte offset (sh/8) of the aligned word pair at `row`
+__device__ __forceinline__ void load_row5(const uint8_t* row, int sh, float* f) {
+  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row);
+  const uint32_t w1 = *reinterpret_cast<const uint32_t*>(row + 4);
+  const uint32_t lo = __funnelshift_r(w0, w1, sh);
+  const uint32_t hi = w1 >> sh;
+  f[0] = byte_to_float(lo, 0);
+  f[1] = byte_to_float(lo, 1);
+  f[2] = byte_to_float(lo, 2);
+  f[3] = byte_to_float(lo, 3);
+  f[4] = byte_to_float(hi, 0);
+}
+// seven consecutive bytes (reference image, global memory, read-only path)
+__device__ __forceinline__ void load_row7(const uint8_t* row, int sh, float* g) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(row);
+  const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+  const uint32_t lo = __funnelshift_r(w0, w1, sh);
+  const uint32_t hi = __funnelshift_r(w1, w2, sh);
+  g[0] = byte_to_float(lo, 0);
+  g[1] = byte_to_float(lo, 1);
+  g[2] = byte_to_float(lo, 2);
+  g[3] = byte_to_float(lo, 3);
+  g[4] = byte_to_float(hi, 0);
+  g[5] = byte_to_float(hi, 1);
+  g[6] = byte_to_float(hi, 2);
+}
+
+// One patch of the residual pass.  weighted = point patch (:450-500: w = 1/(1+|r|)); otherwise a segment
+// sample (:612-637: unweighted sums, |r| collected).  One body serves both (w = 1 is exact for the
+// unweighted sums) so that the hot loop stays small enough for the instruction cache.  Returns false
+// if the warped patch is not fully inside the current image (isInFrame(halfsize)).
+// Per-pixel values (bilinear intensity, residual, weight, chi2 term) are bit-identical to the
+// reference's float arithmetic; the five in-patch sums run in fp32 FMAs over the 16 pixels and are
+// widened to double per patch (the reference accumulates every pixel in double: the difference is
+// ~1e-7 relative on one patch's contribution and does not move the fixed point).
+template <bool weighted>
 __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
                                            const float4* cache, int MP, int p, double u, double v,
-                                           double* S /*[6]*/, float& sumabs) {
+                                           double* S /*[6]*/, float& acc_out) {
   int ui, vi;
   float wTL, wTR, wBL, wBR;
   if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
-  // 5x5 footprint: per row two aligned 32-bit loads + funnel shift (rows are 16B-pitched)
+  // 5x5 footprint, streamed row by row (two aligned 32-bit loads + funnel shift per row; rows are
+  // 16B-pitched).  The row loop is kept rolled.
   const int c0 = ui - 2;
   const int sh = (c0 & 3) * 8;
-  const uint8_t* base = img + (size_t)(vi - 2) * pitch + (c0 & ~3);
-  float f[5][5];
-#pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base + r * pitch);
-    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + r * pitch + 4);
-    const uint32_t lo = __funnelshift_r(w0, w1, sh);
-    const uint32_t hi = w1 >> sh;
-    f[r][0] = byte_to_float(lo, 0);
-    f[r][1] = byte_to_float(lo, 1);
-    f[r][2] = byte_to_float(lo, 2);
-    f[r][3] = byte_to_float(lo, 3);
-    f[r][4] = byte_to_float(hi, 0);
-  }
+  const uint8_t* rowp = img + (size_t)(vi - 2) * pitch + (c0 & ~3);
+  float ra[5], rb[5];
+  load_row5(rowp, sh, ra);
 #ifdef PLSVO_FP64_SUMS
   double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0;
 #else
   float Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sxr = 0.f, Syr = 0.f;
 #endif
   float acc_f = 0.f;
-#pragma unroll
+  const float4* cp = cache + p;
+#pragma unroll 1
   for (int y = 0; y < 4; ++y) {
-    const float4 ref4 = cache[(0 + y) * MP + p];
-    const float4 dx4 = cache[(4 + y) * MP + p];
-    const float4 dy4 = cache[(8 + y) * MP + p];
+    rowp += pitch;
+    load_row5(rowp, sh, rb);
+    const float4 ref4 = cp[0];
+    const float4 dx4 = cp[4 * MP];
+    const float4 dy4 = cp[8 * MP];
+    cp += MP;
     const float refv[4] = {ref4.x, ref4.y, ref4.z, ref4.w};
     const float dxv[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
     const float dyv[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-      const float cur = bilin(wTL, wTR, wBL, wBR, f[y][x], f[y][x + 1], f[y + 1][x], f[y + 1][x + 1]);
+      const float cur = bilin(wTL, wTR, wBL, wBR, ra[x], ra[x + 1], rb[x], rb[x + 1]);
       const float res = __fsub_rn(cur, refv[x]);
       const float dx = dxv[x], dy = dyv[x];
-      if (WEIGHTED) {
-        const float w = weight_rcp(fabsf(res));                              // :479
-        acc_f = __fadd_rn(acc_f, __fmul_rn(__fmul_rn(res, res), w));         // :484
+      const float ares = fabsf(res);
+      const float w = weighted ? weight_rcp(ares) : 1.0f;                        // :479
+      const float term = weighted ? __fmul_rn(__fmul_rn(res, res), w) : ares;   // :484 / :643
+      acc_f = __fadd_rn(acc_f, term);
 #ifdef PLSVO_FP64_SUMS
-        const double wdx = (double)w * (double)dx, wdy = (double)w * (double)dy;
-        Sxx += wdx * (double)dx;
-        Sxy += wdx * (double)dy;
-        Syy += wdy * (double)dy;
-        Sxr += wdx * (double)res;
-        Syr += wdy * (double)res;
+      const double wdx = (double)w * (double)dx, wdy = (double)w * (double)dy;
+      Sxx += wdx * (double)dx;
+      Sxy += wdx * (double)dy;
+      Syy += wdy * (double)dy;
+      Sxr += wdx * (double)res;
+      Syr += wdy * (double)res;
 #else
-        const float wdx = w * dx, wdy = w * dy;
-        Sxx = fmaf(wdx, dx, Sxx);
-        Sxy = fmaf(wdx, dy, Sxy);
-        Syy = fmaf(wdy, dy, Syy);
-        Sxr = fmaf(wdx, res, Sxr);
-        Syr = fmaf(wdy, res, Syr);
+      const float wdx = __fmul_rn(w, dx), wdy = __fmul_rn(w, dy);
+      Sxx = fmaf(wdx, dx, Sxx);
+      Sxy = fmaf(wdx, dy, Sxy);
+      Syy = fmaf(wdy, dy, Syy);
+      Sxr = fmaf(wdx, res, Sxr);
+      Syr = fmaf(wdy, res, Syr);
 #endif
-      } else {
-        acc_f = __fadd_rn(acc_f, fabsf(res));  // :643
-#ifdef PLSVO_FP64_SUMS
-        Sxx += (double)dx * (double)dx;
-        Sxy += (double)dx * (double)dy;
-        Syy += (double)dy * (double)dy;
-        Sxr += (double)dx * (double)res;
-        Syr += (double)dy * (double)res;
-#else
-        Sxx = fmaf(dx, dx, Sxx);
-        Sxy = fmaf(dx, dy, Sxy);
-        Syy = fmaf(dy, dy, Syy);
-        Sxr = fmaf(dx, res, Sxr);
-        Syr = fmaf(dy, res, Syr);
-#endif
-      }
     }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ra[c] = rb[c];
   }
   S[0] = (double)Sxx, S[1] = (double)Sxy, S[2] = (double)Syy, S[3] = (double)Sxr, S[4] = (double)Syr;
-  if (WEIGHTED) S[5] = (double)acc_f;  // chi2 of this patch
-  sumabs = acc_f;
+  if (weighted) S[5] = (double)acc_f;  // chi2 of this patch
+  acc_out = acc_f;                      // sum of |res| for a segment sample
   return true;
 }
 
 // Reference-patch precompute for one patch (:243-264 / :354-375): 16 interpolated intensities and
 // central-difference gradients of the interpolated image, written as 12 float4 rows.
+// V[a][b] = interpolated intensity at integer offset (a-1, b-1) from the patch origin; the reference
+// evaluates the same bilinear expression for ref / dx / dy of neighbouring pixels (:251-258), so each
+// value is computed once, in a rolled sliding window over the rows (V rows y, y+1, y+2 for pixel row y).
 __device__ __forceinline__ void precompute_patch(const uint8_t* __restrict__ img, int pitch, int ui, int vi, float wTL,
                                                  float wTR, float wBL, float wBR, float4* __restrict__ cache, int MP,
                                                  int p) {
   const int c0 = ui - 3;
   const int sh = (c0 & 3) * 8;
-  const uint8_t* base = img + (size_t)(vi - 3) * pitch + (c0 & ~3);
-  float g[7][7];
+  const uint8_t* rowp = img + (size_t)(vi - 3) * pitch + (c0 & ~3);
+  float g0[7], g1[7], Va[6], Vb[6], Vc[6];
+  load_row7(rowp, sh, g0);
+  load_row7(rowp + pitch, sh, g1);
 #pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(base + r * pitch);
-    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-    const uint32_t lo = __funnelshift_r(w0, w1, sh);
-    const uint32_t hi = __funnelshift_r(w1, w2, sh);
-    g[r][0] = byte_to_float(lo, 0);
-    g[r][1] = byte_to_float(lo, 1);
-    g[r][2] = byte_to_float(lo, 2);
-    g[r][3] = byte_to_float(lo, 3);
-    g[r][4] = byte_to_float(hi, 0);
-    g[r][5] = byte_to_float(hi, 1);
-    g[r][6] = byte_to_float(hi, 2);
-  }
-  // V[a][b] = interpolated intensity at integer offset (a-1, b-1) from the patch origin; the
-  // reference evaluates the same bilinear expression for ref / dx / dy of neighbouring pixels
-  // (:251-258), so each value is computed once here (corners are never used).
-  float V[6][6];
+  for (int c = 0; c < 6; ++c) Va[c] = bilin(wTL, wTR, wBL, wBR, g0[c], g0[c + 1], g1[c], g1[c + 1]);
+  rowp += 2 * pitch;
+  load_row7(rowp, sh, g0);
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c < 6; ++c)
-      if (!((r == 0 || r == 5) && (c == 0 || c == 5)))
-        V[r][c] = bilin(wTL, wTR, wBL, wBR, g[r][c], g[r][c + 1], g[r + 1][c], g[r + 1][c + 1]);
-#pragma unroll
+  for (int c = 0; c < 6; ++c) Vb[c] = bilin(wTL, wTR, wBL, wBR, g1[c], g1[c + 1], g0[c], g0[c + 1]);
+  // here g0 holds block row 2; loop invariant: g0 = block row y+2
+  float4* cp = cache + p;
+#pragma unroll 1
   for (int y = 0; y < 4; ++y) {
+    rowp += pitch;
+    load_row7(rowp, sh, g1);  // block row y+3
+#pragma unroll
+    for (int c = 0; c < 6; ++c) Vc[c] = bilin(wTL, wTR, wBL, wBR, g0[c], g0[c + 1], g1[c], g1[c + 1]);
     float refv[4], dxv[4], dyv[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-      refv[x] = V[y + 1][x + 1];
-      dxv[x] = __fmul_rn(0.5f, __fsub_rn(V[y + 1][x + 2], V[y + 1][x]));
-      dyv[x] = __fmul_rn(0.5f, __fsub_rn(V[y + 2][x + 1], V[y][x + 1]));
+      refv[x] = Vb[x + 1];
+      dxv[x] = __fmul_rn(0.5f, __fsub_rn(Vb[x + 2], Vb[x]));
+      dyv[x] = __fmul_rn(0.5f, __fsub_rn(Vc[x + 1], Va[x + 1]));
     }
-    cache[(0 + y) * MP + p] = make_float4(refv[0], refv[1], refv[2], refv[3]);
-    cache[(4 + y) * MP + p] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
-    cache[(8 + y) * MP + p] = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+    cp[0] = make_float4(refv[0], refv[1], refv[2], refv[3]);
+    cp[4 * MP] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
+    cp[8 * MP] = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+    cp += MP;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) Va[c] = Vb[c], Vb[c] = Vc[c];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) g0[c] = g1[c];
   }
 }
 

@@ -32,7 +32,8 @@ struct PoCtl {
   double scratch[36];
   double cov_in[36];
   double chi2;
-  double kth;
+  unsigned long long sel[2];
+  int hist[256];
   int flag;
   int iter;
   int count;
@@ -62,23 +63,57 @@ __device__ __forceinline__ void accumulate(double* acc, const double* J0, const 
   acc[27] += e_sq * w;                                                        // :128
 }
 
-// element of rank k (0-based) among keys[0..n) — vk::getMedian's nth_element at floor(n/2)
-__device__ __forceinline__ double block_kth(const double* keys, int n, int k, double* slot, int tid) {
-  for (int i = tid; i < n; i += kPoThreads) {
-    const double xi = keys[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const double xj = keys[j];
-      rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0;
-    }
-    if (rank == k) *slot = xi;
+// element of rank k (0-based) among the non-negative keys[0..n) — vk::getMedian's nth_element at
+// floor(n/2) — by MSB-first radix select on the IEEE bit patterns (monotone for keys >= 0, +inf last):
+// 8 bits per pass, shared-memory histogram, warp 0 locates the bin holding rank k.
+__device__ __forceinline__ double block_kth(const double* keys, int n, int k, int* hist, unsigned long long* sel,
+                                            int tid) {
+  const int lane = tid & 31;
+  if (tid == 0) {
+    sel[0] = 0ull;                    // bits decided so far
+    sel[1] = (unsigned long long)k;   // rank inside the surviving set
   }
-  __syncthreads();
-  const double r = *slot;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += kPoThreads) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = sel[0];
+    const unsigned long long hi_mask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+    for (int i = tid; i < n; i += kPoThreads) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(keys[i]);
+      if ((key & hi_mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j] = hist[lane * 8 + j];
+        sum += c[j];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int kk = (int)sel[1];
+      const int before = incl - sum;
+      if (kk >= before && kk < incl) {  // exactly one lane
+        int acc = before, bin = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kk >= acc && kk < acc + c[j]) bin = j, sel[1] = (unsigned long long)(kk - acc);
+          acc += c[j];
+        }
+        sel[0] = prefix | ((unsigned long long)(lane * 8 + bin) << shift);
+      }
+    }
+    __syncthreads();
+  }
+  const double r = __longlong_as_double((long long)sel[0]);
   __syncthreads();
   return r;
 }
-
 
 struct Feat {  // per-frame feature arrays
   const double *pt_f, *pt_pos, *seg_line, *seg_spos, *seg_epos;
@@ -316,10 +351,10 @@ __global__ void __launch_bounds__(kPoThreads) pose_optimizer_kernel(const PoseOp
       continue;
     }
     double estimated_scale_pt = 0.0;  // reference: getMedian on an empty vector is UB; defined as 0 here
-    if (n_pt > 0) estimated_scale_pt = (double)__fmul_rn(1.48f, (float)block_kth(keys, a.n_pts, n_pt / 2, &ctl->kth, tid));
+    if (n_pt > 0) estimated_scale_pt = (double)__fmul_rn(1.48f, (float)block_kth(keys, a.n_pts, n_pt / 2, ctl->hist, ctl->sel, tid));
     double estimated_scale_ls = 1.0;
     if (n_ls > 0)
-      estimated_scale_ls = (double)__fmul_rn(1.48f, (float)block_kth(keys + a.n_pts, a.n_segs, n_ls / 2, &ctl->kth, tid));
+      estimated_scale_ls = (double)__fmul_rn(1.48f, (float)block_kth(keys + a.n_pts, a.n_segs, n_ls / 2, ctl->hist, ctl->sel, tid));
     __syncthreads();
     for (int i = tid; i < n_tot; i += kPoThreads) keys_final[i] = CUDART_INF;
     __syncthreads();
@@ -393,8 +428,8 @@ __global__ void __launch_bounds__(kPoThreads) pose_optimizer_kernel(const PoseOp
 
     // ---- reporting medians (:244-251) ----
     const int n_final = n_pt + n_ls;
-    const double med_init = (n_init > 0) ? block_kth(keys_init, 2 * n_tot, n_init / 2, &ctl->kth, tid) : 0.0;
-    const double med_final = block_kth(keys_final, n_tot, n_final / 2, &ctl->kth, tid);
+    const double med_init = (n_init > 0) ? block_kth(keys_init, 2 * n_tot, n_init / 2, ctl->hist, ctl->sel, tid) : 0.0;
+    const double med_final = block_kth(keys_final, n_tot, n_final / 2, ctl->hist, ctl->sel, tid);
     if (tid == 0) {
       for (int i = 0; i < 7; ++i) a.out_T[(size_t)b * 7 + i] = ctl->T[i];
       a.out_scale[b] = estimated_scale_pt * fx;
