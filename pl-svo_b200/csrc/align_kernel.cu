@@ -53,8 +53,13 @@ struct PairCtl {
   int iters_level[PLSVO_MAX_LEVELS];
 };
 
+struct PatchSums {  // five fp32 in-patch sums of one pass + how to apply them (0 skip, 1 point, 2+j segment j)
+  float S[5];
+  int kind;
+};
+
 struct Layout {
-  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, seg_px, pt_vis, xyz, cache, img, total;
+  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, seg_px, seg_scale, prec, pt_vis, xyz, cache, img, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -75,6 +80,10 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_pat
   o += 4u * (uint32_t)n_segs;
   L.seg_px = align_up(o, 16);
   o = L.seg_px + 16u * (uint32_t)max_seg_patches;  // 2D centre of every segment sample (precompute only)
+  L.seg_scale = o;
+  o += 16u * (uint32_t)n_segs;  // per-segment (weight/res_, weight) of the current pass
+  L.prec = o;
+  o += (uint32_t)sizeof(PatchSums) * (uint32_t)max_patches;  // per-patch sums of the current pass
   L.seg_alive = o;
   o += (uint32_t)n_segs;
   L.pt_vis = o;
@@ -204,7 +213,7 @@ __device__ __forceinline__ void load_row7(const uint8_t* row, int sh, float* g) 
 template <bool weighted>
 __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
                                            const float4* cache, int MP, int p, double u, double v,
-                                           double* S /*[6]*/, float& acc_out) {
+                                           float* S /*[5]*/, float& acc_out) {
   int ui, vi;
   float wTL, wTR, wBL, wBR;
   if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
@@ -261,9 +270,8 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
 #pragma unroll
     for (int c = 0; c < 5; ++c) ra[c] = rb[c];
   }
-  S[0] = (double)Sxx, S[1] = (double)Sxy, S[2] = (double)Syy, S[3] = (double)Sxr, S[4] = (double)Syr;
-  if (weighted) S[5] = (double)acc_f;  // chi2 of this patch
-  acc_out = acc_f;                      // sum of |res| for a segment sample
+  S[0] = (float)Sxx, S[1] = (float)Sxy, S[2] = (float)Syy, S[3] = (float)Sxr, S[4] = (float)Syr;
+  acc_out = acc_f;  // chi2 of this patch (points) / sum of |res| (segment sample)
   return true;
 }
 
@@ -401,6 +409,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
   int* seg_N = reinterpret_cast<int*>(smem + L.seg_N);
   int* seg_off = reinterpret_cast<int*>(smem + L.seg_off);
   double* seg_px = reinterpret_cast<double*>(smem + L.seg_px);
+  double* seg_scale = reinterpret_cast<double*>(smem + L.seg_scale);
+  PatchSums* prec = reinterpret_cast<PatchSums*>(smem + L.prec);
   uint8_t* pt_vis = smem + L.pt_vis;
   uint8_t* img_s = smem + L.img;
   double* xyz = reinterpret_cast<double*>(smem + L.xyz);
@@ -620,33 +630,40 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       const double cJ2 = cJ * cJ;
       const int n_seg_slots = (ns << gshift);
       for (;;) {
-        double acc[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
         const double R0 = ctl->R[0], R1 = ctl->R[1], R2 = ctl->R[2], R3 = ctl->R[3], R4 = ctl->R[4], R5 = ctl->R[5],
                      R6 = ctl->R[6], R7 = ctl->R[7], R8 = ctl->R[8];
         const double t0 = ctl->t[0], t1 = ctl->t[1], t2 = ctl->t[2];
+        double chi2_acc = 0.0;
+        int n_meas_acc = 0, n_patch_acc = 0;
+        // ======== phase 1: residuals.  Each thread evaluates its patches and leaves five fp32 sums per
+        // patch in shared memory; the 27 double accumulators are not live here, which keeps the pixel
+        // loop free of register spills. ========
         // ---- point patches (:380-502): thread per patch ----
         for (int p = tid; p < np; p += kAlignThreads) {
-          if (!pt_vis[p]) continue;
-          const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
-          const double xc = R0 * X + R1 * Y + R2 * Z + t0;
-          const double yc = R3 * X + R4 * Y + R5 * Z + t1;
-          const double zc = R6 * X + R7 * Y + R8 * Z + t2;
-          const double izc = 1.0 / zc;
-          const double u = (a.fx * (xc * izc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
-          const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-          double S[6];
-          float aux;
-          if (!eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) continue;
-          rank2_update(acc, X, Y, xyz[3 * MP + p], S[0] * cJ2, S[1] * cJ2, S[2] * cJ2, S[3] * cJ, S[4] * cJ);
-          acc[27] += S[5];
-          acc[28] += 16.0;
-          acc[29] += 1.0;
+          int kind = 0;
+          if (pt_vis[p]) {
+            const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
+            const double xc = R0 * X + R1 * Y + R2 * Z + t0;
+            const double yc = R3 * X + R4 * Y + R5 * Z + t1;
+            const double zc = R6 * X + R7 * Y + R8 * Z + t2;
+            const double izc = 1.0 / zc;
+            const double u = (a.fx * (xc * izc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
+            const double v = (a.fy * (yc * izc) + a.cy) * dscale;
+            float S[5], aux;
+            if (eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) {
+              kind = 1;
+#pragma unroll
+              for (int k = 0; k < 5; ++k) prec[p].S[k] = S[k];
+              chi2_acc += (double)aux;
+              n_meas_acc += 16;
+              n_patch_acc += 1;
+            }
+          }
+          prec[p].kind = kind;
         }
         // ---- segment samples (:504-695): every segment owns a group of G = 2^gshift consecutive lanes
         // of one warp (G >= its sample count, or the whole warp looping over samples), so the
-        // per-segment gate/weight (:640-688) is a few shuffles: no shared staging, no block barrier.
+        // per-segment gate/weight (:640-688) is a few shuffles: no block barrier.
         // Warps take segment rounds from the top so they interleave with the point rounds.
         for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
           const int q = base + lane;
@@ -655,7 +672,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
           const bool seg_ok = (j < ns) && seg_alive[j];
           const int N = seg_ok ? seg_N[j] : 0;
           const int off = seg_ok ? seg_off[j] : 0;
-          double S[6] = {0, 0, 0, 0, 0, 0};
           float my_abs = 0.f;
           int first_bad = 0x7fffffff;
           for (int n = n0; n < N; n += G) {  // one trip unless a segment has more samples than a warp
@@ -667,11 +683,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
             const double izc = 1.0 / zc;
             const double u = (a.fx * (xc * izc) + a.cx) * dscale;
             const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-            float aux;
-            if (eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux))
+            float S[5], aux;
+            if (eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) {
               my_abs = __fadd_rn(my_abs, aux);
-            else
+#pragma unroll
+              for (int k = 0; k < 5; ++k) prec[p].S[k] = S[k];
+              prec[p].kind = 2 + j;
+            } else {
               first_bad = min(first_bad, n);
+              prec[p].kind = 0;
+            }
           }
           // group reductions: sum of |res| in sample order for small groups, first out-of-frame sample
           float res_ = 0.f;
@@ -683,45 +704,52 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
             for (int d = G >> 1; d >= 1; d >>= 1) res_ = __fadd_rn(res_, __shfl_xor_sync(0xffffffffu, res_, d));
           }
           for (int d = G >> 1; d >= 1; d >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, d));
-          if (N == 0) continue;
+          if (N == 0 || n0 != 0) continue;  // the group's first lane settles the segment
           const bool good = first_bad >= N;
-          const int n_eval = good ? N : first_bad;       // samples evaluated before the loop stops (:588-594)
+          n_patch_acc += good ? N : first_bad;  // samples evaluated before the loop stops (:588-594)
           res_ = (float)((double)res_ / (double)(unsigned long long)N);  // :647
-          if (n0 == 0) acc[29] += (double)n_eval;
           if (good && (double)res_ < 200.0) {
             const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
-            const double sH = (double)w / (double)res_ * cJ2;     // H += H_*weight/res_ (:681)
-            const double sJ = (double)w * cJ;                     // Jres += Jres_*weight (:682)
-            if (N <= G) {
-              if (n0 < N) {
-                const int p = np + off + n0;
-                rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[3 * MP + p], S[0] * sH, S[1] * sH, S[2] * sH,
-                             S[3] * sJ, S[4] * sJ);
-              }
-            } else {
-              for (int n = n0; n < N; n += G) {  // long segment: re-evaluate this lane's samples
-                const int p = np + off + n;
-                const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
-                const double xc = R0 * X + R1 * Y + R2 * Z + t0;
-                const double yc = R3 * X + R4 * Y + R5 * Z + t1;
-                const double zc = R6 * X + R7 * Y + R8 * Z + t2;
-                const double izc = 1.0 / zc;
-                const double u = (a.fx * (xc * izc) + a.cx) * dscale;
-                const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-                float aux;
-                double S2[6];
-                if (eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S2, aux))
-                  rank2_update(acc, X, Y, xyz[3 * MP + p], S2[0] * sH, S2[1] * sH, S2[2] * sH, S2[3] * sJ, S2[4] * sJ);
-              }
-            }
-            if (n0 == 0) {
-              acc[27] += (double)__fmul_rn(__fmul_rn(res_, res_), w);  // :683
-              acc[28] += 1.0;                                         // :684
-            }
-          } else if (n0 == 0) {
+            seg_scale[2 * j] = (double)w / (double)res_ * cJ2;    // H += H_*weight/res_ (:681)
+            seg_scale[2 * j + 1] = (double)w * cJ;                // Jres += Jres_*weight (:682)
+            chi2_acc += (double)__fmul_rn(__fmul_rn(res_, res_), w);  // :683
+            n_meas_acc += 1;                                         // :684
+          } else {
+            seg_scale[2 * j] = 0.0;  // rejected: its samples are skipped in phase 2
+            seg_scale[2 * j + 1] = 0.0;
             seg_alive[j] = 0;  // it->feat3D = NULL (:688); the group's lanes have all read it already
           }
         }
+        __syncwarp();  // phase 2 reads back what lanes of this warp wrote (records of own patches, seg_scale)
+        // ======== phase 2: normal equations.  Rank-2 update of this thread's 21+6 accumulators per patch. ========
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+        for (int p = tid; p < np; p += kAlignThreads) {
+          if (prec[p].kind != 1) continue;
+          const PatchSums ps = prec[p];
+          rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[3 * MP + p], (double)ps.S[0] * cJ2,
+                       (double)ps.S[1] * cJ2, (double)ps.S[2] * cJ2, (double)ps.S[3] * cJ, (double)ps.S[4] * cJ);
+        }
+        for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
+          const int q = base + lane;
+          const int j = q >> gshift;
+          const int n0 = q & (G - 1);
+          if (j >= ns) continue;
+          const int N = seg_N[j];
+          const double sH = seg_scale[2 * j], sJ = seg_scale[2 * j + 1];
+          if (sH == 0.0 && sJ == 0.0) continue;
+          for (int n = n0; n < N; n += G) {
+            const int p = np + seg_off[j] + n;
+            if (prec[p].kind != 2 + j) continue;
+            const PatchSums ps = prec[p];
+            rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[3 * MP + p], (double)ps.S[0] * sH, (double)ps.S[1] * sH,
+                         (double)ps.S[2] * sH, (double)ps.S[3] * sJ, (double)ps.S[4] * sJ);
+          }
+        }
+        acc[27] = chi2_acc;
+        acc[28] = (double)n_meas_acc;
+        acc[29] = (double)n_patch_acc;
         // ---- block reduction (deterministic order) ----
         const double mine = warp_reduce32(acc, lane);
         red[warp * 32 + lane] = mine;

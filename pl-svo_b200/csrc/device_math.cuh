@@ -84,6 +84,37 @@ __device__ __forceinline__ SE3q se3_inverse(const SE3q& a) {
 }
 __device__ __forceinline__ Vec3 se3_act(const SE3q& T, Vec3 p) { return vadd(qrot(T.q, p), T.t); }
 
+// sin/cos for the SE3 exponential.  Gauss-Newton steps are small rotations: |x| < 0.5 takes a short
+// Taylor evaluation (truncation < 1e-22, i.e. below double rounding) so that the hot kernels do not
+// drag libdevice's sincos with its argument-reduction slow path through the instruction cache; larger
+// arguments (degenerate systems only) use sincos().
+__device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
+  if (fabs(x) < 0.5) {
+    const double x2 = x * x;
+    double ps = -1.0 / 355687428096000.0;  // -x^17/17!
+    ps = ps * x2 + 1.0 / 1307674368000.0;
+    ps = ps * x2 - 1.0 / 6227020800.0;
+    ps = ps * x2 + 1.0 / 39916800.0;
+    ps = ps * x2 - 1.0 / 362880.0;
+    ps = ps * x2 + 1.0 / 5040.0;
+    ps = ps * x2 - 1.0 / 120.0;
+    ps = ps * x2 + 1.0 / 6.0;
+    *s = x - x * x2 * ps;
+    double pc = 1.0 / 6402373705728000.0;  // x^18/18!
+    pc = pc * x2 - 1.0 / 20922789888000.0;
+    pc = pc * x2 + 1.0 / 87178291200.0;
+    pc = pc * x2 - 1.0 / 479001600.0;
+    pc = pc * x2 + 1.0 / 3628800.0;
+    pc = pc * x2 - 1.0 / 40320.0;
+    pc = pc * x2 + 1.0 / 720.0;
+    pc = pc * x2 - 1.0 / 24.0;
+    pc = pc * x2 + 0.5;
+    *c = 1.0 - x2 * pc;
+  } else {
+    sincos(x, s, c);
+  }
+}
+
 // SE3::exp([upsilon, omega]) — Sophus (non-templated) se3.cpp / so3.cpp
 __device__ __forceinline__ SE3q se3_exp(const double* u) {
   const Vec3 upsilon = v3(u[0], u[1], u[2]);
@@ -92,7 +123,7 @@ __device__ __forceinline__ SE3q se3_exp(const double* u) {
   const double half_theta = 0.5 * theta;
   double imag_factor;
   double s_half, c_half;
-  sincos(half_theta, &s_half, &c_half);
+  sincos_small(half_theta, &s_half, &c_half);
   if (theta < 1e-10) {
     const double theta_sq = theta * theta;
     const double theta_po4 = theta_sq * theta_sq;
@@ -107,10 +138,11 @@ __device__ __forceinline__ SE3q se3_exp(const double* u) {
   if (theta < 1e-10) {
     r.t = qrot(r.q, upsilon);
   } else {
-    double s, c;
-    sincos(theta, &s, &c);
+    // sin(theta), 1 - cos(theta) from the half angle (no second evaluation, no cancellation)
+    const double s = 2.0 * s_half * c_half;
+    const double one_minus_c = 2.0 * s_half * s_half;
     const double theta_sq = theta * theta;
-    const double a = (1 - c) / theta_sq;
+    const double a = one_minus_c / theta_sq;
     const double b = (theta - s) / (theta_sq * theta);
     const Vec3 wu = vcross(omega, upsilon);
     const Vec3 wwu = vcross(omega, wu);
