@@ -27,6 +27,9 @@ struct plsvo_ctx_impl {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // second stream of the chunked host-buffer pipeline
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t start_ev = nullptr;
   int num_sms = 0;
   int smem_optin = 0;
   std::string err;
@@ -169,6 +172,11 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
                     &c->p_out_pto,   &c->p_out_sgo,  &c->p_out_iters, &c->p_out_status};
   for (DevBuf* b : bufs) release(*b);
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    for (int k = 0; k < 8; ++k) cudaEventDestroy(c->chunk_ev[k]);
+    cudaEventDestroy(c->start_ev);
+  }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -225,46 +233,72 @@ int plsvo_selftest_weight(plsvo_ctx* ctx, uint32_t n, uint32_t seed, uint64_t* m
 // ------------------------------------------------------------------------------------------------
 // alignment
 // ------------------------------------------------------------------------------------------------
-int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
-  if (!ctx || !h) return PLSVO_ERR_INVALID;
-  plsvo_ctx_impl* c = CTX(ctx);
-  c->align_ready = false;
-  if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0 || h->n_segs > 32767)
-    return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
-  if (!h->T_ref_w || !h->T_cur_w) return fail(c, PLSVO_ERR_INVALID, "T_ref_w/T_cur_w missing");
-  if (h->n_pts > 0 && (!h->pt_px || !h->pt_f || !h->pt_pos)) return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
-  if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || !h->seg_sf || !h->seg_ef || !h->seg_spos || !h->seg_epos ||
-                        !h->seg_length))
-    return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
-  if (h->cam.width <= 0 || h->cam.height <= 0) return fail(c, PLSVO_ERR_INVALID, "camera size");
-  CK(cudaSetDevice(c->device));
-  cudaStream_t s = c->stream;
+}  // extern "C" (helpers below use templates)
+
+namespace {
+
+// copy items [b0,b1) of a per-pair host array to its device buffer (device pointer NULL when the host one is)
+template <class T>
+cudaError_t up_range(DevBuf& buf, const T* host, size_t per_item, size_t B, size_t b0, size_t b1, cudaStream_t s,
+                     const T** dev, bool prepare) {
+  if (!host || per_item == 0) {
+    *dev = nullptr;
+    return cudaSuccess;
+  }
+  if (prepare) {
+    cudaError_t e = ensure(buf, B * per_item * sizeof(T));
+    if (e != cudaSuccess) return e;
+  }
+  *dev = static_cast<const T*>(buf.p);
+  return cudaMemcpyAsync(static_cast<T*>(buf.p) + b0 * per_item, host + b0 * per_item, (b1 - b0) * per_item * sizeof(T),
+                         cudaMemcpyHostToDevice, s);
+}
+
+// Host arrays -> device layout for pairs [b0,b1).  prepare = validate, size the buffers for the whole batch
+// and lay out the pyramid levels; later chunks of the same batch only copy.
+int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, size_t b1, cudaStream_t s, bool prepare) {
   AlignArgs& a = c->aa;
   const size_t B = (size_t)h->batch;
-  a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs;
-  a.width = h->cam.width, a.height = h->cam.height;
-  a.fx = h->cam.fx, a.fy = h->cam.fy, a.cx = h->cam.cx, a.cy = h->cam.cy;
-  c->cam = h->cam;
-
-  // images: every provided level is packed as [B][rows][pitch16]
-  size_t total = 0;
-  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
-    a.ref_img[l] = a.cur_img[l] = nullptr;
-    a.pitch[l] = 0, a.stride[l] = 0;
-    c->level_off[l] = 0;
-    if (!h->ref_img[l] || !h->cur_img[l]) continue;
-    const int cols = h->cam.width >> l, rows = h->cam.height >> l;
-    if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
-    if (h->img_pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "img_pitch smaller than the level width");
-    const uint32_t pitch = (uint32_t)((cols + 15) / 16 * 16);
-    a.pitch[l] = pitch;
-    a.stride[l] = (size_t)rows * pitch;
-    total = (total + 255) / 256 * 256;
-    c->level_off[l] = total;
-    total += a.stride[l] * B;
+  if (prepare) {
+    c->align_ready = false;
+    if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0 || h->n_segs > 32767)
+      return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
+    if (!h->T_ref_w || !h->T_cur_w) return fail(c, PLSVO_ERR_INVALID, "T_ref_w/T_cur_w missing");
+    if (h->n_pts > 0 && (!h->pt_px || !h->pt_f || !h->pt_pos)) return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
+    if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || !h->seg_sf || !h->seg_ef || !h->seg_spos || !h->seg_epos ||
+                          !h->seg_length))
+      return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
+    if (h->cam.width <= 0 || h->cam.height <= 0) return fail(c, PLSVO_ERR_INVALID, "camera size");
+    CK(cudaSetDevice(c->device));
+    a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs;
+    a.width = h->cam.width, a.height = h->cam.height;
+    a.fx = h->cam.fx, a.fy = h->cam.fy, a.cx = h->cam.cx, a.cy = h->cam.cy;
+    c->cam = h->cam;
+    // images: every provided level is packed as [B][rows][pitch16]
+    size_t total = 0;
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+      a.ref_img[l] = a.cur_img[l] = nullptr;
+      a.pitch[l] = 0, a.stride[l] = 0;
+      c->level_off[l] = 0;
+      if (!h->ref_img[l] || !h->cur_img[l]) continue;
+      const int cols = h->cam.width >> l, rows = h->cam.height >> l;
+      if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
+      if (h->img_pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "img_pitch smaller than the level width");
+      const uint32_t pitch = (uint32_t)((cols + 15) / 16 * 16);
+      a.pitch[l] = pitch;
+      a.stride[l] = (size_t)rows * pitch;
+      total = (total + 255) / 256 * 256;
+      c->level_off[l] = total;
+      total += a.stride[l] * B;
+    }
+    CK(ensure(c->d_ref_img, total + 256));
+    CK(ensure(c->d_cur_img, total + 256));
+    size_t stage = 0;
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
+      if (a.pitch[l] && h->img_pitch[l] != a.pitch[l]) stage = std::max(stage, 2 * h->img_stride[l] * B);
+    if (stage) CK(ensure(c->d_stage, stage));
   }
-  CK(ensure(c->d_ref_img, total + 256));
-  CK(ensure(c->d_cur_img, total + 256));
+  const size_t nb = b1 - b0;
   for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
     if (!a.pitch[l]) continue;
     const int cols = h->cam.width >> l, rows = h->cam.height >> l;
@@ -272,55 +306,59 @@ int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
     uint8_t* dc = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
     a.ref_img[l] = dr;
     a.cur_img[l] = dc;
+    const uint8_t* hr = h->ref_img[l] + b0 * h->img_stride[l];
+    const uint8_t* hc = h->cur_img[l] + b0 * h->img_stride[l];
+    dr += b0 * a.stride[l];
+    dc += b0 * a.stride[l];
     const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
     if (uniform && h->img_pitch[l] == a.pitch[l]) {
       // host stack already has the device layout: one linear copy per frame set
-      CK(cudaMemcpyAsync(dr, h->ref_img[l], a.stride[l] * B, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(dc, h->cur_img[l], a.stride[l] * B, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(dr, hr, a.stride[l] * nb, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(dc, hc, a.stride[l] * nb, cudaMemcpyHostToDevice, s));
     } else if (uniform) {
       // uniformly pitched stack with a different pitch: linear H2D into staging (PCIe-friendly), then a
       // device-side 2D repack into the 16-byte-pitched layout (row-granular DMA over PCIe is slow)
-      const size_t bytes = h->img_stride[l] * B;
-      CK(ensure(c->d_stage, 2 * bytes));
-      uint8_t* st = static_cast<uint8_t*>(c->d_stage.p);
-      CK(cudaMemcpyAsync(st, h->ref_img[l], bytes, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(st + bytes, h->cur_img[l], bytes, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpy2DAsync(dr, a.pitch[l], st, h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyDeviceToDevice, s));
-      CK(cudaMemcpy2DAsync(dc, a.pitch[l], st + bytes, h->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyDeviceToDevice, s));
+      const size_t off = 2 * h->img_stride[l] * b0, bytes = h->img_stride[l] * nb;
+      uint8_t* st = static_cast<uint8_t*>(c->d_stage.p) + off;
+      CK(cudaMemcpyAsync(st, hr, bytes, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(st + bytes, hc, bytes, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpy2DAsync(dr, a.pitch[l], st, h->img_pitch[l], cols, (size_t)rows * nb, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpy2DAsync(dc, a.pitch[l], st + bytes, h->img_pitch[l], cols, (size_t)rows * nb, cudaMemcpyDeviceToDevice, s));
     } else {
-      for (size_t b = 0; b < B; ++b) {
-        CK(cudaMemcpy2DAsync(dr + b * a.stride[l], a.pitch[l], h->ref_img[l] + b * h->img_stride[l], h->img_pitch[l], cols,
-                             rows, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpy2DAsync(dc + b * a.stride[l], a.pitch[l], h->cur_img[l] + b * h->img_stride[l], h->img_pitch[l], cols,
-                             rows, cudaMemcpyHostToDevice, s));
+      for (size_t b = 0; b < nb; ++b) {
+        CK(cudaMemcpy2DAsync(dr + b * a.stride[l], a.pitch[l], hr + b * h->img_stride[l], h->img_pitch[l], cols, rows,
+                             cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpy2DAsync(dc + b * a.stride[l], a.pitch[l], hc + b * h->img_stride[l], h->img_pitch[l], cols, rows,
+                             cudaMemcpyHostToDevice, s));
       }
     }
   }
-
-  CK(up(c->d_T_ref, h->T_ref_w, B * 7, s, &a.T_ref_w));
-  CK(up(c->d_T_cur, h->T_cur_w, B * 7, s, &a.T_cur_w));
-  CK(up(c->d_pt_count, h->pt_count, B, s, &a.pt_count));
-  CK(up(c->d_pt_px, h->pt_px, B * h->n_pts * 2, s, &a.pt_px));
-  CK(up(c->d_pt_f, h->pt_f, B * h->n_pts * 3, s, &a.pt_f));
-  CK(up(c->d_pt_pos, h->pt_pos, B * h->n_pts * 3, s, &a.pt_pos));
-  CK(up(c->d_pt_valid, h->pt_valid, B * h->n_pts, s, &a.pt_valid));
-  CK(up(c->d_seg_count, h->seg_count, B, s, &a.seg_count));
-  CK(up(c->d_seg_spx, h->seg_spx, B * h->n_segs * 2, s, &a.seg_spx));
-  CK(up(c->d_seg_epx, h->seg_epx, B * h->n_segs * 2, s, &a.seg_epx));
-  CK(up(c->d_seg_sf, h->seg_sf, B * h->n_segs * 3, s, &a.seg_sf));
-  CK(up(c->d_seg_ef, h->seg_ef, B * h->n_segs * 3, s, &a.seg_ef));
-  CK(up(c->d_seg_spos, h->seg_spos, B * h->n_segs * 3, s, &a.seg_spos));
-  CK(up(c->d_seg_epos, h->seg_epos, B * h->n_segs * 3, s, &a.seg_epos));
-  CK(up(c->d_seg_length, h->seg_length, B * h->n_segs, s, &a.seg_length));
-  CK(up(c->d_seg_valid, h->seg_valid, B * h->n_segs, s, &a.seg_valid));
+  const size_t np = (size_t)h->n_pts, ns = (size_t)h->n_segs;
+  CK(up_range(c->d_T_ref, h->T_ref_w, 7, B, b0, b1, s, &a.T_ref_w, prepare));
+  CK(up_range(c->d_T_cur, h->T_cur_w, 7, B, b0, b1, s, &a.T_cur_w, prepare));
+  CK(up_range(c->d_pt_count, h->pt_count, 1, B, b0, b1, s, &a.pt_count, prepare));
+  CK(up_range(c->d_pt_px, h->pt_px, np * 2, B, b0, b1, s, &a.pt_px, prepare));
+  CK(up_range(c->d_pt_f, h->pt_f, np * 3, B, b0, b1, s, &a.pt_f, prepare));
+  CK(up_range(c->d_pt_pos, h->pt_pos, np * 3, B, b0, b1, s, &a.pt_pos, prepare));
+  CK(up_range(c->d_pt_valid, h->pt_valid, np, B, b0, b1, s, &a.pt_valid, prepare));
+  CK(up_range(c->d_seg_count, h->seg_count, 1, B, b0, b1, s, &a.seg_count, prepare));
+  CK(up_range(c->d_seg_spx, h->seg_spx, ns * 2, B, b0, b1, s, &a.seg_spx, prepare));
+  CK(up_range(c->d_seg_epx, h->seg_epx, ns * 2, B, b0, b1, s, &a.seg_epx, prepare));
+  CK(up_range(c->d_seg_sf, h->seg_sf, ns * 3, B, b0, b1, s, &a.seg_sf, prepare));
+  CK(up_range(c->d_seg_ef, h->seg_ef, ns * 3, B, b0, b1, s, &a.seg_ef, prepare));
+  CK(up_range(c->d_seg_spos, h->seg_spos, ns * 3, B, b0, b1, s, &a.seg_spos, prepare));
+  CK(up_range(c->d_seg_epos, h->seg_epos, ns * 3, B, b0, b1, s, &a.seg_epos, prepare));
+  CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, s, &a.seg_length, prepare));
+  CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, s, &a.seg_valid, prepare));
+  if (!prepare) return PLSVO_OK;
 
   // per-level bound on segment samples per pair (sizes the sample slots; host arrays are still valid here)
   c->seg_patch_bound.assign(PLSVO_MAX_LEVELS, 0);
   if (h->n_segs > 0) {
     for (size_t b = 0; b < B; ++b) {
-      const int ns = h->seg_count ? std::min(h->seg_count[b], h->n_segs) : h->n_segs;
+      const int nsb = h->seg_count ? std::min(h->seg_count[b], h->n_segs) : h->n_segs;
       int sum[PLSVO_MAX_LEVELS] = {0};
-      for (int j = 0; j < ns; ++j) {
+      for (int j = 0; j < nsb; ++j) {
         const size_t k = b * h->n_segs + j;
         const int n0 = host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], 0);
         for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) sum[l] += 1 + ((n0 - 1) >> l);
@@ -328,7 +366,6 @@ int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], sum[l]);
     }
   }
-
   CK(ensure(c->d_out_T, B * 7 * sizeof(double)));
   CK(ensure(c->d_out_ntr, B * sizeof(long long)));
   CK(ensure(c->d_out_H, B * 36 * sizeof(double)));
@@ -351,9 +388,14 @@ int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
   return PLSVO_OK;
 }
 
-int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
-  if (!ctx || !p) return PLSVO_ERR_INVALID;
-  plsvo_ctx_impl* c = CTX(ctx);
+// launch plan of the alignment kernel for the uploaded batch (shared memory, CTA size, grid)
+struct AlignPlan {
+  bool cache_in_smem;
+  int threads, ctas_per_sm;
+  size_t smem;
+};
+
+int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, AlignPlan* plan) {
   if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_launch before plsvo_align_upload");
   if (p->min_level < 0 || p->max_level < p->min_level || p->max_level >= PLSVO_MAX_LEVELS || p->n_iter < 1)
     return fail(c, PLSVO_ERR_INVALID, "level range / n_iter");
@@ -381,7 +423,7 @@ int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
   a.smem_img_bytes = img_bytes;
   size_t smem_s = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, img_bytes, true);
   size_t smem_g = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, img_bytes, false);
-  bool cache_in_smem = smem_s <= (size_t)(limit / 2 - 1024);
+  bool cache_in_smem = smem_s <= (size_t)(limit / 4 - 1024);
   if (mode && !strcmp(mode, "smem")) cache_in_smem = smem_s <= (size_t)limit;
   if (mode && !strcmp(mode, "global")) cache_in_smem = false;
   size_t smem = cache_in_smem ? smem_s : smem_g;
@@ -396,7 +438,7 @@ int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
   // solve / barriers then stall fewer warps) and let the hardware scheduler balance pairs of
   // different iteration counts; big CTAs cut per-pair latency when the batch is small.
   int threads = 128;
-  if (a.B <= c->num_sms) threads = 256;
+  if (chunk_pairs <= c->num_sms) threads = 256;
   const char* tenv = getenv("PLSVO_THREADS");
   if (tenv && (atoi(tenv) == 64 || atoi(tenv) == 128 || atoi(tenv) == 256)) threads = atoi(tenv);
   int ctas_per_sm = 0;
@@ -404,16 +446,78 @@ int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
   if (ctas_per_sm < 1) return fail(c, PLSVO_ERR_INVALID, "kernel does not fit on an SM");
   const char* cap = getenv("PLSVO_CTAS_PER_SM");
   if (cap && atoi(cap) > 0) ctas_per_sm = std::min(ctas_per_sm, atoi(cap));
-  const int grid = std::min(a.B, c->num_sms * ctas_per_sm);
   if (!cache_in_smem) {
-    CK(ensure(c->d_ws_cache, (size_t)grid * kCacheRows * a.max_patches * sizeof(float4)));
+    const int grid_max = std::min(a.B, c->num_sms * ctas_per_sm);
+    CK(ensure(c->d_ws_cache, (size_t)grid_max * kCacheRows * a.max_patches * sizeof(float4)));
   }
   a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
-  a.ws_xyz = static_cast<double*>(c->d_ws_xyz.p);
-  CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), c->stream));
-  CK(align_kernel_launch(a, grid, threads, smem, cache_in_smem, c->stream));
+  a.ws_xyz = nullptr;
+  plan->cache_in_smem = cache_in_smem, plan->threads = threads, plan->ctas_per_sm = ctas_per_sm, plan->smem = smem;
+  return PLSVO_OK;
+}
+
+// one kernel over pairs [b0,b1) of the uploaded batch (pointers rebased to the chunk)
+int align_launch_range(plsvo_ctx_impl* c, const AlignPlan& plan, size_t b0, size_t b1, int counter_slot, cudaStream_t s) {
+  AlignArgs a = c->aa;
+  const size_t np = (size_t)a.n_pts, ns = (size_t)a.n_segs;
+  a.B = (int)(b1 - b0);
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    if (!a.pitch[l]) continue;
+    a.ref_img[l] += b0 * a.stride[l];
+    a.cur_img[l] += b0 * a.stride[l];
+  }
+#define REBASE(f, per) \
+  if (a.f) a.f += b0 * (per)
+  REBASE(T_ref_w, 7);
+  REBASE(T_cur_w, 7);
+  REBASE(pt_count, 1);
+  REBASE(pt_px, np * 2);
+  REBASE(pt_f, np * 3);
+  REBASE(pt_pos, np * 3);
+  REBASE(pt_valid, np);
+  REBASE(seg_count, 1);
+  REBASE(seg_spx, ns * 2);
+  REBASE(seg_epx, ns * 2);
+  REBASE(seg_sf, ns * 3);
+  REBASE(seg_ef, ns * 3);
+  REBASE(seg_spos, ns * 3);
+  REBASE(seg_epos, ns * 3);
+  REBASE(seg_length, ns);
+  REBASE(seg_valid, ns);
+  REBASE(out_T, 7);
+  REBASE(out_n_tracked, 1);
+  REBASE(out_H, 36);
+  REBASE(out_seg_killed, ns);
+  REBASE(out_iters, PLSVO_MAX_LEVELS);
+  REBASE(out_status, 1);
+  REBASE(out_patch_iters, 1);
+  REBASE(out_patch_levels, 1);
+#undef REBASE
+  a.work_counter = c->aa.work_counter + counter_slot;
+  const int grid = std::min(a.B, c->num_sms * plan.ctas_per_sm);
+  CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), s));
+  CK(align_kernel_launch(a, grid, plan.threads, plan.smem, plan.cache_in_smem, s));
   c->launches += 1;
   return PLSVO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
+  if (!ctx || !h) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  return align_upload_impl(c, h, 0, (size_t)std::max(h->batch, 0), c->stream, true);
+}
+
+int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
+  if (!ctx || !p) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  AlignPlan plan;
+  int rc = align_plan(c, p, c->aa.B, &plan);
+  if (rc != PLSVO_OK) return rc;
+  return align_launch_range(c, plan, 0, (size_t)c->aa.B, 0, c->stream);
 }
 
 int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* o) {
@@ -439,10 +543,48 @@ int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* o) {
 
 int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsvo_align_params* p,
                           const plsvo_align_result* o) {
-  int rc = plsvo_align_upload(ctx, b);
-  if (rc != PLSVO_OK) return rc;
-  rc = plsvo_align_launch(ctx, p);
-  if (rc != PLSVO_OK) return rc;
+  if (!ctx || !b || !p || !o) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  // Optional chunked pipeline (PLSVO_E2E_CHUNKS=k): the batch is cut into k chunks and a second stream copies
+  // chunk i+1 to the device while the kernel aligns chunk i.  Measured on B200/PCIe5 at B=1024 the single-shot
+  // path is faster (2.63 ms vs 3.11 ms with k=2: half-batches under-fill the 592 CTA slots and the H2D leg,
+  // 82 MB at ~48 GB/s, dominates either way), so the default is one chunk.
+  int chunks = 1;
+  const char* cenv = getenv("PLSVO_E2E_CHUNKS");
+  if (cenv && atoi(cenv) >= 1) chunks = std::min(atoi(cenv), 8);
+  if (chunks > b->batch) chunks = 1;
+  if (chunks == 1) {
+    int rc = plsvo_align_upload(ctx, b);
+    if (rc != PLSVO_OK) return rc;
+    rc = plsvo_align_launch(ctx, p);
+    if (rc != PLSVO_OK) return rc;
+    return plsvo_align_download(ctx, o);
+  }
+  CK(cudaSetDevice(c->device));
+  if (!c->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; ++k) CK(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming));
+  }
+  // the copy stream must not overtake work already queued on the main stream (previous batch's kernels
+  // still read the device buffers)
+  CK(cudaEventRecord(c->start_ev, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->start_ev, 0));
+  const size_t B = (size_t)b->batch;
+  AlignPlan plan;
+  for (int k = 0; k < chunks; ++k) {
+    const size_t b0 = B * k / chunks, b1 = B * (k + 1) / chunks;
+    int rc = align_upload_impl(c, b, b0, b1, c->copy_stream, k == 0);
+    if (rc != PLSVO_OK) return rc;
+    CK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
+    if (k == 0) {
+      rc = align_plan(c, p, (int)(b1 - b0), &plan);
+      if (rc != PLSVO_OK) return rc;
+    }
+    CK(cudaStreamWaitEvent(c->stream, c->chunk_ev[k], 0));
+    rc = align_launch_range(c, plan, b0, b1, k, c->stream);
+    if (rc != PLSVO_OK) return rc;
+  }
   return plsvo_align_download(ctx, o);
 }
 

@@ -232,7 +232,19 @@ __device__ __forceinline__ void gn_loop(const PoseOptArgs& a, const Feat& F, PoC
           }
         for (int i = 0; i < 6; ++i) ctl->b[i] = tot[21 + i];
         const double new_chi2 = tot[27];
-        ldlt6_solve(ctl->A, ctl->b, ctl->dT, ctl->scratch);  // :170
+        {  // :170 — register LDL^T; the pivoted Eigen-style routine handles degenerate systems
+          double Hu[21], gg[6], xx[6];
+#pragma unroll
+          for (int i = 0; i < 21; ++i) Hu[i] = tot[i];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) gg[i] = tot[21 + i];
+          if (ldlt6_reg(Hu, gg, xx)) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ctl->dT[i] = xx[i];
+          } else {
+            ldlt6_solve(ctl->A, ctl->b, ctl->dT, ctl->scratch);
+          }
+        }
         *iters_out += 1;
         int flag = 0;
         if ((ctl->iter > 0 && new_chi2 > ctl->chi2) || isnan(ctl->dT[0])) {  // :173-180

@@ -142,3 +142,16 @@ def test_align_zero_residual_segment_raises_stop(pkg, abi, synth, oracle, gen_de
     np.testing.assert_array_equal(gpu.iters, ref.iters)
     ang, rel = synth.pose_error(gpu.T_cur_w, ref.T_cur_w)
     assert ang.max() < 1e-12
+
+
+def test_align_chunked_host_pipeline_matches_single_shot(pkg, synth, gen_device, monkeypatch):
+    """plsvo_align_batch_run pipelines large host batches in chunks on two streams; results are identical."""
+    data = synth.make_align_batch(batch=24, n_pts=120, n_segs=24, device=gen_device, seed=3700)
+    monkeypatch.setenv("PLSVO_E2E_CHUNKS", "1")
+    one = pkg.SparseImgAlign(4, 2, 30).run(data)
+    monkeypatch.setenv("PLSVO_E2E_CHUNKS", "3")
+    three = pkg.SparseImgAlign(4, 2, 30).run(data)
+    np.testing.assert_array_equal(one.T_cur_w, three.T_cur_w)
+    np.testing.assert_array_equal(one.n_tracked, three.n_tracked)
+    np.testing.assert_array_equal(one.seg_killed, three.seg_killed)
+    np.testing.assert_array_equal(one.iters, three.iters)
