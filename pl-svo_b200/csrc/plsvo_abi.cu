@@ -413,7 +413,13 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
   // workspace (L2 resident) with coalesced 128-bit loads.
   const char* mode = getenv("PLSVO_CACHE_MODE");  // "smem" | "global" | unset (= auto)
   const int limit = c->smem_optin;                // 227 KB on sm_100a
-  const int img_budget = 64 * 1024;
+  // Staging budget: a level is staged only if the CTA still fits 4x (else 2x) per SM next to the
+  // per-pair state; bigger levels are read through L2 with the same aligned-word loads.
+  const int other = (int)align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, 0, false);
+  int img_budget = limit / 4 - other - 1024;
+  if (img_budget < 1024) img_budget = limit / 2 - other - 1024;
+  if (img_budget < 0) img_budget = 0;
+  img_budget = std::min(img_budget, 96 * 1024);
   int img_bytes = 0;
   for (int l = p->min_level; l <= p->max_level; ++l) {
     const size_t bytes = a.stride[l];

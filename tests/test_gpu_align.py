@@ -155,3 +155,40 @@ def test_align_chunked_host_pipeline_matches_single_shot(pkg, synth, gen_device,
     np.testing.assert_array_equal(one.n_tracked, three.n_tracked)
     np.testing.assert_array_equal(one.seg_killed, three.seg_killed)
     np.testing.assert_array_equal(one.iters, three.iters)
+
+
+def test_align_720p_combined_config(pkg, abi, synth, oracle, gen_device):
+    """BASELINE config 4 shape: 720p, 500 points + 150 segments (levels 4->2): larger per-pair state,
+    the finest level is no longer staged in shared memory."""
+    data = synth.make_align_batch(cam=synth.HD720, batch=6, n_pts=500, n_segs=150, device=gen_device, seed=3800)
+    gpu, ref = _run_both(pkg, abi, synth, oracle, data)
+    _check(synth, gpu, ref, exact_iters=False)
+
+
+def test_align_segments_longer_than_a_warp(pkg, abi, synth, oracle, gen_device):
+    """At level 0 a 700-px segment has more than 32 samples: the whole-warp loop (long-segment path)."""
+    data = synth.make_align_batch(cam=synth.HD720, batch=4, n_pts=200, n_segs=12, max_level=2, min_level=0,
+                                  device=gen_device, seed=3900, motion_t=0.004, motion_r=0.0012, margin=24)
+    rng = np.random.default_rng(3)
+    # stretch the segments: endpoints far apart inside the image
+    import torch
+
+    B, S = data.seg_spx.shape[:2]
+    spx = np.stack([rng.uniform(40, 300, (B, S)), rng.uniform(40, 680, (B, S))], -1)
+    epx = np.stack([rng.uniform(980, 1240, (B, S)), rng.uniform(40, 680, (B, S))], -1)
+    scene = synth.Scene()
+    R, t = synth.pose7_to_Rt(torch.tensor(data.T_ref_w))
+
+    def lift(px):
+        p = torch.tensor(px)
+        d = torch.stack([(p[..., 0] - data.cam.cx) / data.cam.fx, (p[..., 1] - data.cam.cy) / data.cam.fy, torch.ones_like(p[..., 0])], -1)
+        f = d / d.norm(dim=-1, keepdim=True)
+        return f.numpy(), scene.intersect(R, t, d).numpy()
+
+    data.seg_spx, data.seg_epx = np.ascontiguousarray(spx), np.ascontiguousarray(epx)
+    data.seg_sf, data.seg_spos = (np.ascontiguousarray(x) for x in lift(spx))
+    data.seg_ef, data.seg_epos = (np.ascontiguousarray(x) for x in lift(epx))
+    data.seg_length = np.ascontiguousarray(np.linalg.norm(epx - spx, axis=-1))
+    gpu, ref = _run_both(pkg, abi, synth, oracle, data, 2, 0)
+    assert (data.seg_length / 16 > 32).any()
+    _check(synth, gpu, ref, exact_iters=False)
