@@ -47,7 +47,7 @@ struct PairCtl {
   int stop;
   int iter;
   int n_seg_patches;
-  int seg_gshift;  // log2 of the lane-group size of a segment at the current level
+  int n_seg_slots;  // lane slots taken by the segment groups at the current level
   unsigned int patch_iters;
   unsigned int patch_levels;
   int iters_level[PLSVO_MAX_LEVELS];
@@ -59,7 +59,7 @@ struct PatchSums {  // five fp32 in-patch sums of one pass + how to apply them (
 };
 
 struct Layout {
-  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, seg_px, seg_scale, prec, pt_vis, xyz, cache, img, total;
+  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, seg_slot, slot_seg, seg_px, seg_scale, prec, pt_vis, xyz, cache, img, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -78,6 +78,10 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_pat
   o += 4u * (uint32_t)n_segs;
   L.seg_off = o;
   o += 4u * (uint32_t)n_segs;
+  L.seg_slot = o;
+  o += 4u * (uint32_t)n_segs;
+  L.slot_seg = o;
+  o += 2u * (2u * (uint32_t)max_seg_patches + 64u);  // lane slot -> segment (groups of 2^k lanes, k per segment)
   L.seg_px = align_up(o, 16);
   o = L.seg_px + 16u * (uint32_t)max_seg_patches;  // 2D centre of every segment sample (precompute only)
   L.seg_scale = o;
@@ -408,6 +412,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
   uint8_t* seg_alive = smem + L.seg_alive;
   int* seg_N = reinterpret_cast<int*>(smem + L.seg_N);
   int* seg_off = reinterpret_cast<int*>(smem + L.seg_off);
+  int* seg_slot = reinterpret_cast<int*>(smem + L.seg_slot);
+  uint16_t* slot_seg = reinterpret_cast<uint16_t*>(smem + L.slot_seg);
+  const int max_slots = 2 * a.max_seg_patches + 64;
   double* seg_px = reinterpret_cast<double*>(smem + L.seg_px);
   double* seg_scale = reinterpret_cast<double*>(smem + L.seg_scale);
   PatchSums* prec = reinterpret_cast<PatchSums*>(smem + L.prec);
@@ -526,13 +533,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         }
         seg_N[j] = N;
       }
+      for (int q = tid; q < max_slots; q += kAlignThreads) slot_seg[q] = 0xffffu;
       __syncthreads();
-      if (warp == 0) {  // exclusive scan of seg_N -> seg_off (cache offsets in patches, :282-292) + max N
-        int carry = 0, nmax = 1;
+      if (warp == 0) {  // exclusive scan of seg_N -> seg_off (cache offsets in patches, :282-292) + lane groups
+        int carry = 0;
         for (int base = 0; base < ns; base += 32) {
           const int j = base + lane;
           const int v = (j < ns) ? seg_N[j] : 0;
-          nmax = max(nmax, v);
           int incl = v;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -542,20 +549,35 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
           if (j < ns) seg_off[j] = carry + incl - v;
           carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+        // Lane groups: segment j gets 2^k consecutive lanes, 2^k = smallest power of two >= min(N_j, 32).
+        // Groups are laid out class by class, largest first, so every group is aligned to its own size
+        // and never straddles a warp.
+        int slot_base = 0;
+        for (int cls = 5; cls >= 0; --cls) {
+          int cnt = 0;
+          for (int base = 0; base < ns; base += 32) {
+            const int j = base + lane;
+            const int N = (j < ns) ? seg_N[j] : 0;
+            int k = -1;
+            if (N > 0) {
+              k = 0;
+              while ((1 << k) < N && k < 5) ++k;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, k == cls);
+            if (k == cls) seg_slot[j] = slot_base + ((cnt + __popc(m & ((1u << lane) - 1u))) << cls);
+            cnt += __popc(m);
+          }
+          slot_base += cnt << cls;
+        }
         if (lane == 0) {
           ctl->n_seg_patches = carry;
-          int gs = 0;  // lane-group size per segment: smallest power of two >= max N, capped at a warp
-          while ((1 << gs) < nmax && gs < 5) ++gs;
-          ctl->seg_gshift = gs;
+          ctl->n_seg_slots = slot_base;
         }
       }
       __syncthreads();
       const int n_sp = min(ctl->n_seg_patches, a.max_seg_patches);
       const int n_patches = np + n_sp;
-      const int gshift = ctl->seg_gshift;
-      const int G = 1 << gshift;
+      const int n_seg_slots = min((ctl->n_seg_slots + 31) & ~31, max_slots & ~31);
       // ---- expand segments into sample patches: 2D centre and 3D point by repeated addition (:323-335) ----
       for (int j = tid; j < ns; j += kAlignThreads) {
         const int N = seg_N[j];
@@ -580,6 +602,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         const double i0 = (Q0 - P0) / nm1, i1 = (Q1 - P1) / nm1, i2 = (Q2 - P2) / nm1;
         double X = P0, Y = P1, Z = P2;
         const int off = seg_off[j];
+        {
+          int g = 1;
+          while (g < N && g < 32) g <<= 1;
+          const int s0 = seg_slot[j];
+          for (int n = 0; n < g; ++n)
+            if (s0 + n < max_slots) slot_seg[s0 + n] = (uint16_t)j;
+        }
         for (int n = 0; n < N; ++n) {
           const int sp_idx = off + n;
           if (sp_idx < n_sp) {
@@ -628,7 +657,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       // ---- Gauss-Newton iterations at this level (vk::NLLSSolver::optimizeGaussNewton) ----
       const double cJ = fabs(a.fx) / (double)(1 << level);  // focal_length / 2^level (:262)
       const double cJ2 = cJ * cJ;
-      const int n_seg_slots = (ns << gshift);
       for (;;) {
         const double R0 = ctl->R[0], R1 = ctl->R[1], R2 = ctl->R[2], R3 = ctl->R[3], R4 = ctl->R[4], R5 = ctl->R[5],
                      R6 = ctl->R[6], R7 = ctl->R[7], R8 = ctl->R[8];
@@ -667,11 +695,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         // Warps take segment rounds from the top so they interleave with the point rounds.
         for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
           const int q = base + lane;
-          const int j = q >> gshift;
-          const int n0 = q & (G - 1);
+          const int j = slot_seg[q];
           const bool seg_ok = (j < ns) && seg_alive[j];
           const int N = seg_ok ? seg_N[j] : 0;
           const int off = seg_ok ? seg_off[j] : 0;
+          const int n0 = seg_ok ? q - seg_slot[j] : 0;
+          int G = 1;
+          while (G < N && G < 32) G <<= 1;
           float my_abs = 0.f;
           int first_bad = 0x7fffffff;
           for (int n = n0; n < N; n += G) {  // one trip unless a segment has more samples than a warp
@@ -694,16 +724,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
               prec[p].kind = 0;
             }
           }
-          // group reductions: sum of |res| in sample order for small groups, first out-of-frame sample
-          float res_ = 0.f;
-          if (gshift <= 3) {
-            const int gbase = lane & ~(G - 1);
-            for (int n = 0; n < G; ++n) res_ = __fadd_rn(res_, __shfl_sync(0xffffffffu, my_abs, gbase + n));
-          } else {
-            res_ = my_abs;
-            for (int d = G >> 1; d >= 1; d >>= 1) res_ = __fadd_rn(res_, __shfl_xor_sync(0xffffffffu, res_, d));
+          // group reductions (xor tree inside the group: partners at distance d < G stay in the group)
+          float res_ = my_abs;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, res_, d);
+            const int fb = __shfl_xor_sync(0xffffffffu, first_bad, d);
+            if (d < G) {
+              res_ = __fadd_rn(res_, o);
+              first_bad = min(first_bad, fb);
+            }
           }
-          for (int d = G >> 1; d >= 1; d >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, d));
           if (N == 0 || n0 != 0) continue;  // the group's first lane settles the segment
           const bool good = first_bad >= N;
           n_patch_acc += good ? N : first_bad;  // samples evaluated before the loop stops (:588-594)
@@ -733,13 +764,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         }
         for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
           const int q = base + lane;
-          const int j = q >> gshift;
-          const int n0 = q & (G - 1);
+          const int j = slot_seg[q];
           if (j >= ns) continue;
           const int N = seg_N[j];
           const double sH = seg_scale[2 * j], sJ = seg_scale[2 * j + 1];
           if (sH == 0.0 && sJ == 0.0) continue;
-          for (int n = n0; n < N; n += G) {
+          int G = 1;
+          while (G < N && G < 32) G <<= 1;
+          for (int n = q - seg_slot[j]; n < N; n += G) {
             const int p = np + seg_off[j] + n;
             if (prec[p].kind != 2 + j) continue;
             const PatchSums ps = prec[p];
