@@ -206,6 +206,25 @@ int plsvo_poseopt_download(plsvo_ctx* ctx, const plsvo_poseopt_result* out);
 int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* batch,
                             const plsvo_poseopt_params* params, const plsvo_poseopt_result* out);
 
+/* ------------------------------------------------------------------------------------------
+ * Image pyramid (SURVEY.md §8f "next", rank 2): frame_utils::createImgPyramid, src/frame.cpp:171-180,
+ * i.e. repeated vk::halfSample (truncating 2x2 mean), for B frames.  Host in, host out.
+ * level[0] of the result may be NULL (level 0 is the input); n_levels <= 7.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plsvo_pyramid_batch {
+  int32_t batch, width, height, n_levels;
+  const uint8_t* img0; /* [B] level-0 images: image b at img0 + b*stride0, rows pitch0 bytes */
+  size_t pitch0, stride0;
+} plsvo_pyramid_batch;
+
+typedef struct plsvo_pyramid_result {
+  uint8_t* level[PLSVO_MAX_LEVELS]; /* caller-allocated; level l holds (width>>l) x (height>>l) pixels */
+  size_t pitch[PLSVO_MAX_LEVELS];
+  size_t stride[PLSVO_MAX_LEVELS];
+} plsvo_pyramid_result;
+
+int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out);
+
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 int64_t plsvo_launch_count(const plsvo_ctx* ctx);
 

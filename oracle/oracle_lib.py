@@ -48,6 +48,8 @@ def load(abi):
         fn = getattr(lib, name)
         fn.restype = None
         fn.argtypes = [P(C.c_double)] * (n_in + 1)
+    lib.plsvo_oracle_half_sample.restype = None
+    lib.plsvo_oracle_half_sample.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8), C.c_size_t]
     lib.plsvo_oracle_hardware_threads.restype = C.c_int
     _lib = lib
     return lib
@@ -88,3 +90,19 @@ def poseopt(abi, data, params=None, n_threads: int = 1):
     if rc != 0:
         raise RuntimeError(f"oracle poseopt failed rc={rc}")
     return out
+
+
+def pyramid(abi, img0, n_levels: int):
+    """frame_utils::createImgPyramid restated: u8 [B,H,W] -> list of levels."""
+    lib = load(abi)
+    img0 = np.ascontiguousarray(img0, np.uint8)
+    levels = [img0]
+    u8p = C.POINTER(C.c_uint8)
+    for _ in range(1, n_levels):
+        prev = levels[-1]
+        B, H, W = prev.shape
+        out = np.empty((B, H // 2, W // 2), np.uint8)
+        for b in range(B):
+            lib.plsvo_oracle_half_sample(prev[b].ctypes.data_as(u8p), W, H, prev.strides[1], out[b].ctypes.data_as(u8p), out.strides[1])
+        levels.append(out)
+    return levels

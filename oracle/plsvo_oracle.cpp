@@ -1041,5 +1041,19 @@ void plsvo_oracle_se3_inverse(const double* a7, double* out7) { se3_to_pose7(se3
 void plsvo_oracle_solve6(const double* A36, const double* b6, double* x6) { solve6(A36, b6, x6); }
 void plsvo_oracle_inverse6(const double* A36, double* out36) { inverse6(A36, out36); }
 
+// vk::halfSample, scalar path (rpg_vikit vision.cpp): out(i,j) = (in(2i,2j)+in(2i,2j+1)+in(2i+1,2j)+in(2i+1,2j+1))/4,
+// integer division; called level by level from frame_utils::createImgPyramid (src/frame.cpp:171-180).
+// in: rows x cols with row pitch in_pitch; out: (rows/2) x (cols/2), pitch out_pitch.
+void plsvo_oracle_half_sample(const uint8_t* in, int cols, int rows, size_t in_pitch, uint8_t* out, size_t out_pitch) {
+  const int oc = cols / 2, orows = rows / 2;
+  for (int i = 0; i < orows; ++i) {
+    const uint8_t* top = in + (size_t)(2 * i) * in_pitch;
+    const uint8_t* bottom = top + in_pitch;
+    uint8_t* p = out + (size_t)i * out_pitch;
+    for (int j = 0; j < oc; ++j, top += 2, bottom += 2, ++p)
+      *p = static_cast<uint8_t>((top[0] + top[1] + bottom[0] + bottom[1]) / 4);
+  }
+}
+
 int plsvo_oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 }

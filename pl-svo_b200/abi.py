@@ -134,6 +134,15 @@ class PoseOptResult(C.Structure):
     ]
 
 
+class PyramidBatch(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("n_levels", C.c_int32),
+                ("img0", _u8p), ("pitch0", C.c_size_t), ("stride0", C.c_size_t)]
+
+
+class PyramidResult(C.Structure):
+    _fields_ = [("level", _u8p * MAX_LEVELS), ("pitch", C.c_size_t * MAX_LEVELS), ("stride", C.c_size_t * MAX_LEVELS)]
+
+
 # ------------------------------------------------------------------------------------------------
 # numpy <-> struct helpers
 # ------------------------------------------------------------------------------------------------
@@ -296,6 +305,7 @@ ABI_SYMBOLS = [
     ("plsvo_poseopt_launch", C.c_int, [C.c_void_p, _P(PoseOptParams)]),
     ("plsvo_poseopt_download", C.c_int, [C.c_void_p, _P(PoseOptResult)]),
     ("plsvo_poseopt_batch_run", C.c_int, [C.c_void_p, _P(PoseOptBatch), _P(PoseOptParams), _P(PoseOptResult)]),
+    ("plsvo_pyramid_batch_run", C.c_int, [C.c_void_p, _P(PyramidBatch), _P(PyramidResult)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
     ("plsvo_selftest_weight", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
     ("plsvo_version", C.c_char_p, []),

@@ -136,3 +136,24 @@ class pose_optimizer:
             "plsvo_poseopt_batch_run",
         )
         return out
+
+
+def createImgPyramid(img_level_0, n_levels: int, ctx: Context | None = None):
+    """Batched frame_utils::createImgPyramid (src/frame.cpp:171-180): u8 images [B,H,W] -> list of levels
+    (level 0 is the input array itself), each the truncating 2x2 half-sample of the previous one."""
+    import numpy as np
+
+    ctx = ctx or default_context()
+    img = np.ascontiguousarray(img_level_0, dtype=np.uint8)
+    B, H, W = img.shape
+    b = abi.PyramidBatch(B, W, H, n_levels, img.ctypes.data_as(C.POINTER(C.c_uint8)), img.strides[1], img.strides[0])
+    r = abi.PyramidResult()
+    levels = [img]
+    for l in range(1, n_levels):
+        out = np.empty((B, H >> l, W >> l), np.uint8)
+        levels.append(out)
+        r.level[l] = out.ctypes.data_as(C.POINTER(C.c_uint8))
+        r.pitch[l] = out.strides[1]
+        r.stride[l] = out.strides[0]
+    ctx.check(ctx.lib.plsvo_pyramid_batch_run(ctx.handle, C.byref(b), C.byref(r)), "plsvo_pyramid_batch_run")
+    return levels

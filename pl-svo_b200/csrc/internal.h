@@ -102,4 +102,14 @@ struct PoseOptArgs {
 size_t poseopt_smem_bytes(int n_pts, int n_segs);
 cudaError_t poseopt_kernel_launch(const PoseOptArgs& a, size_t smem_bytes, cudaStream_t s);
 
+
+// ---------------------------------------------------------------------------------------------
+struct PyramidArgs {
+  int B, width, height, n_levels;  // n_levels <= 7 (64x64 level-0 tiles)
+  uint8_t* level[PLSVO_MAX_LEVELS];  // device, [B][rows_l][pitch_l]; level[0] is the input
+  uint32_t pitch[PLSVO_MAX_LEVELS];
+  size_t stride[PLSVO_MAX_LEVELS];
+};
+cudaError_t pyramid_kernel_launch(const PyramidArgs& a, cudaStream_t s);
+
 }  // namespace plsvo

@@ -52,6 +52,7 @@ struct plsvo_ctx_impl {
   PoseOptArgs pa;
   DevBuf p_T, p_pt_count, p_pt_f, p_pt_pos, p_pt_level, p_pt_valid, p_seg_count, p_seg_line, p_seg_spos, p_seg_epos,
       p_seg_level, p_seg_valid;
+  DevBuf y_img;  // pyramid levels
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
 };
@@ -166,7 +167,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
-                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->p_T,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -706,3 +707,52 @@ int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* b, const 
 }
 
 }  // extern "C"
+
+extern "C" int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (in->batch <= 0 || in->width <= 0 || in->height <= 0 || in->n_levels < 1 || in->n_levels > 7 || !in->img0 ||
+      in->pitch0 < (size_t)in->width)
+    return fail(c, PLSVO_ERR_INVALID, "pyramid batch description");
+  CK(cudaSetDevice(c->device));
+  PyramidArgs a;
+  memset(&a, 0, sizeof a);
+  a.B = in->batch, a.width = in->width, a.height = in->height, a.n_levels = in->n_levels;
+  const size_t B = (size_t)in->batch;
+  size_t total = 0, off[PLSVO_MAX_LEVELS] = {0};
+  for (int l = 0; l < in->n_levels; ++l) {
+    const int cols = in->width >> l, rows = in->height >> l;
+    if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
+    if (l > 0 && !out->level[l]) return fail(c, PLSVO_ERR_INVALID, "output level missing");
+    a.pitch[l] = (uint32_t)((cols + 15) / 16 * 16);
+    a.stride[l] = (size_t)rows * a.pitch[l];
+    total = (total + 255) / 256 * 256;
+    off[l] = total;
+    total += a.stride[l] * B;
+  }
+  CK(ensure(c->y_img, total + 256));
+  for (int l = 0; l < in->n_levels; ++l) a.level[l] = static_cast<uint8_t*>(c->y_img.p) + off[l];
+  cudaStream_t s = c->stream;
+  if (in->stride0 == (size_t)in->height * in->pitch0) {
+    CK(cudaMemcpy2DAsync(a.level[0], a.pitch[0], in->img0, in->pitch0, in->width, (size_t)in->height * B, cudaMemcpyHostToDevice, s));
+  } else {
+    for (size_t b = 0; b < B; ++b)
+      CK(cudaMemcpy2DAsync(a.level[0] + b * a.stride[0], a.pitch[0], in->img0 + b * in->stride0, in->pitch0, in->width,
+                           in->height, cudaMemcpyHostToDevice, s));
+  }
+  CK(pyramid_kernel_launch(a, s));
+  c->launches += 1;
+  for (int l = 1; l < in->n_levels; ++l) {
+    const int cols = in->width >> l, rows = in->height >> l;
+    if (out->pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "output pitch smaller than the level width");
+    if (out->stride[l] == (size_t)rows * out->pitch[l]) {
+      CK(cudaMemcpy2DAsync(out->level[l], out->pitch[l], a.level[l], a.pitch[l], cols, (size_t)rows * B, cudaMemcpyDeviceToHost, s));
+    } else {
+      for (size_t b = 0; b < B; ++b)
+        CK(cudaMemcpy2DAsync(out->level[l] + b * out->stride[l], out->pitch[l], a.level[l] + b * a.stride[l], a.pitch[l], cols,
+                             rows, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
+}
