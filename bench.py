@@ -164,7 +164,7 @@ def main():
         import oracle_lib
         import torch
 
-        n = args.cpu_sample or min(args.batch, 256)
+        n = args.cpu_sample or args.batch
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         data = synth.make_align_batch(batch=n, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=3000)
         hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
@@ -313,6 +313,13 @@ def main():
     avg_kernel_s = (total_ms / args.steps) * 1e-3
     peak, peak_src = measured_hbm_peak()
     achieved = alg_bytes / avg_kernel_s / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of the same kernel/config, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["sparse_img_align_kernel"]
+        if args.batch == 1024 and args.n_pts == 300 and args.n_segs == 80:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
 
     # ---- secondary: pose optimiser (BASELINE config 3: 300 pts + 80 lines, 10 iters, B = 4096 frames) ----
     poseopt = None
@@ -372,7 +379,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "sparse_img_align_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "sparse_img_align_kernel",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_kernel_ms": total_ms / args.steps,
                          "mean_gn_passes_per_pair": float(out.iters.sum(axis=1).mean())},
             "cpu_baseline": cpu,
