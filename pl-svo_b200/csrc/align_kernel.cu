@@ -438,7 +438,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
 
   for (;;) {
     __syncthreads();  // everyone is done with ctl of the previous pair
-    if (tid == 0) ctl->pair = (int)atomicAdd(a.work_counter, 1u);
+    if (tid == 0) {
+      const int nb = (int)atomicAdd(a.work_counter, 1u);
+      if (a.gate_chunk > 0 && nb < a.B) {
+        // host-buffer pipeline: this pair's inputs are still in flight over PCIe until the copy stream
+        // has bumped the arrival counter past its chunk
+        const unsigned need = (unsigned)(nb / a.gate_chunk) + 1u;
+        while (*reinterpret_cast<const volatile unsigned int*>(a.arrived) < need) __nanosleep(1000);
+        __threadfence_system();
+      }
+      ctl->pair = nb;
+    }
     __syncthreads();
     const int b = ctl->pair;
     if (b >= a.B) break;

@@ -49,6 +49,10 @@ struct AlignArgs {
   uint32_t* out_patch_levels;
   // work distribution + per-CTA workspace
   unsigned int* work_counter;
+  // arrival gate of the host-buffer pipeline: pair b may be touched once *arrived > b / gate_chunk
+  // (a copy stream bumps it after each chunk of the batch has landed); gate_chunk == 0: no gate.
+  const unsigned int* arrived;
+  int gate_chunk;
   int max_patches;      // patch slots per pair: n_pts + max segment samples
   int max_seg_patches;  // segment sample slots per pair
   int smem_img_bytes;   // bytes of the image staging buffer

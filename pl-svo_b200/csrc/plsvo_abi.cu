@@ -30,6 +30,11 @@ struct plsvo_ctx_impl {
   cudaStream_t copy_stream = nullptr;  // second stream of the chunked host-buffer pipeline
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t start_ev = nullptr;
+  unsigned int* h_flags = nullptr;  // pinned arrival values of the gated pipeline
+  char* h_out = nullptr;            // pinned staging of the alignment outputs (one D2H per download)
+  size_t h_out_cap = 0, out_bytes = 0;
+  size_t oo_T = 0, oo_H = 0, oo_ntr = 0, oo_iters = 0, oo_status = 0, oo_pi = 0, oo_pl = 0, oo_killed = 0;
+  int h_flags_cap = 0;
   int num_sms = 0;
   int smem_optin = 0;
   std::string err;
@@ -173,6 +178,8 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
                     &c->p_out_pto,   &c->p_out_sgo,  &c->p_out_iters, &c->p_out_status};
   for (DevBuf* b : bufs) release(*b);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->h_out) cudaFreeHost(c->h_out);
   if (c->copy_stream) {
     cudaStreamDestroy(c->copy_stream);
     for (int k = 0; k < 8; ++k) cudaEventDestroy(c->chunk_ev[k]);
@@ -257,9 +264,13 @@ cudaError_t up_range(DevBuf& buf, const T* host, size_t per_item, size_t B, size
 
 // Host arrays -> device layout for pairs [b0,b1).  prepare = validate, size the buffers for the whole batch
 // and lay out the pyramid levels; later chunks of the same batch only copy.
-int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, size_t b1, cudaStream_t s, bool prepare) {
+int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, size_t b1, cudaStream_t s, int mode) {
+  // mode 0: copy [b0,b1) only; 1: validate + lay out + copy + host-side sizing; 2: validate + lay out + copy;
+  // 3: host-side sizing only
   AlignArgs& a = c->aa;
   const size_t B = (size_t)h->batch;
+  const bool prepare = (mode == 1 || mode == 2);
+  if (mode != 3) {
   if (prepare) {
     c->align_ready = false;
     if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0 || h->n_segs > 32767)
@@ -285,7 +296,13 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       const int cols = h->cam.width >> l, rows = h->cam.height >> l;
       if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
       if (h->img_pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "img_pitch smaller than the level width");
-      const uint32_t pitch = (uint32_t)((cols + 15) / 16 * 16);
+      // device pitch: the host layout is kept when rows are word aligned and images 16-byte aligned
+      // (what the aligned-word loads and the bulk copy need) — then a level moves with one linear copy;
+      // otherwise rows are padded to 16 bytes and repacked on the device.
+      uint32_t pitch = (uint32_t)((cols + 15) / 16 * 16);
+      const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
+      if (uniform && h->img_pitch[l] % 4 == 0 && h->img_stride[l] % 16 == 0 && h->img_pitch[l] < (1u << 20))
+        pitch = (uint32_t)h->img_pitch[l];
       a.pitch[l] = pitch;
       a.stride[l] = (size_t)rows * pitch;
       total = (total + 255) / 256 * 256;
@@ -351,7 +368,8 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   CK(up_range(c->d_seg_epos, h->seg_epos, ns * 3, B, b0, b1, s, &a.seg_epos, prepare));
   CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, s, &a.seg_length, prepare));
   CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, s, &a.seg_valid, prepare));
-  if (!prepare) return PLSVO_OK;
+  }  // mode != 3
+  if (mode == 0 || mode == 2) return PLSVO_OK;
 
   // per-level bound on segment samples per pair (sizes the sample slots; host arrays are still valid here)
   c->seg_patch_bound.assign(PLSVO_MAX_LEVELS, 0);
@@ -367,23 +385,38 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], sum[l]);
     }
   }
-  CK(ensure(c->d_out_T, B * 7 * sizeof(double)));
-  CK(ensure(c->d_out_ntr, B * sizeof(long long)));
-  CK(ensure(c->d_out_H, B * 36 * sizeof(double)));
-  CK(ensure(c->d_out_killed, B * std::max(1, h->n_segs)));
-  CK(ensure(c->d_out_iters, B * PLSVO_MAX_LEVELS * sizeof(int32_t)));
-  CK(ensure(c->d_out_status, B * sizeof(int32_t)));
-  CK(ensure(c->d_out_pi, B * sizeof(uint32_t)));
-  CK(ensure(c->d_out_pl, B * sizeof(uint32_t)));
+  // all outputs live in one device block so that the download is a single D2H into pinned staging
+  {
+    const size_t nsg = (size_t)std::max(1, h->n_segs);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 255) / 256 * 256; return at; };
+    c->oo_T = take(B * 7 * sizeof(double));
+    c->oo_H = take(B * 36 * sizeof(double));
+    c->oo_ntr = take(B * sizeof(long long));
+    c->oo_iters = take(B * PLSVO_MAX_LEVELS * sizeof(int32_t));
+    c->oo_status = take(B * sizeof(int32_t));
+    c->oo_pi = take(B * sizeof(uint32_t));
+    c->oo_pl = take(B * sizeof(uint32_t));
+    c->oo_killed = take(B * nsg);
+    c->out_bytes = o;
+    CK(ensure(c->d_out_T, o));
+    if (c->h_out_cap < o) {
+      if (c->h_out) cudaFreeHost(c->h_out);
+      c->h_out = nullptr, c->h_out_cap = 0;
+      CK(cudaHostAlloc((void**)&c->h_out, o, cudaHostAllocDefault));
+      c->h_out_cap = o;
+    }
+    char* base = static_cast<char*>(c->d_out_T.p);
+    a.out_T = reinterpret_cast<double*>(base + c->oo_T);
+    a.out_H = reinterpret_cast<double*>(base + c->oo_H);
+    a.out_n_tracked = reinterpret_cast<long long*>(base + c->oo_ntr);
+    a.out_iters = reinterpret_cast<int32_t*>(base + c->oo_iters);
+    a.out_status = reinterpret_cast<int32_t*>(base + c->oo_status);
+    a.out_patch_iters = reinterpret_cast<uint32_t*>(base + c->oo_pi);
+    a.out_patch_levels = reinterpret_cast<uint32_t*>(base + c->oo_pl);
+    a.out_seg_killed = reinterpret_cast<uint8_t*>(base + c->oo_killed);
+  }
   CK(ensure(c->d_counter, 256));
-  a.out_T = static_cast<double*>(c->d_out_T.p);
-  a.out_n_tracked = static_cast<long long*>(c->d_out_ntr.p);
-  a.out_H = static_cast<double*>(c->d_out_H.p);
-  a.out_seg_killed = static_cast<uint8_t*>(c->d_out_killed.p);
-  a.out_iters = static_cast<int32_t*>(c->d_out_iters.p);
-  a.out_status = static_cast<int32_t*>(c->d_out_status.p);
-  a.out_patch_iters = static_cast<uint32_t*>(c->d_out_pi.p);
-  a.out_patch_levels = static_cast<uint32_t*>(c->d_out_pl.p);
   a.work_counter = static_cast<unsigned int*>(c->d_counter.p);
   c->align_ready = true;
   return PLSVO_OK;
@@ -464,7 +497,8 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
 }
 
 // one kernel over pairs [b0,b1) of the uploaded batch (pointers rebased to the chunk)
-int align_launch_range(plsvo_ctx_impl* c, const AlignPlan& plan, size_t b0, size_t b1, int counter_slot, cudaStream_t s) {
+int align_launch_range(plsvo_ctx_impl* c, const AlignPlan& plan, size_t b0, size_t b1, int counter_slot, cudaStream_t s,
+                       int gate_chunk = 0) {
   AlignArgs a = c->aa;
   const size_t np = (size_t)a.n_pts, ns = (size_t)a.n_segs;
   a.B = (int)(b1 - b0);
@@ -501,6 +535,8 @@ int align_launch_range(plsvo_ctx_impl* c, const AlignPlan& plan, size_t b0, size
   REBASE(out_patch_levels, 1);
 #undef REBASE
   a.work_counter = c->aa.work_counter + counter_slot;
+  a.arrived = gate_chunk > 0 ? c->aa.work_counter + 32 : nullptr;
+  a.gate_chunk = gate_chunk;
   const int grid = std::min(a.B, c->num_sms * plan.ctas_per_sm);
   CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), s));
   CK(align_kernel_launch(a, grid, plan.threads, plan.smem, plan.cache_in_smem, s));
@@ -515,7 +551,7 @@ extern "C" {
 int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
   if (!ctx || !h) return PLSVO_ERR_INVALID;
   plsvo_ctx_impl* c = CTX(ctx);
-  return align_upload_impl(c, h, 0, (size_t)std::max(h->batch, 0), c->stream, true);
+  return align_upload_impl(c, h, 0, (size_t)std::max(h->batch, 0), c->stream, 1);
 }
 
 int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
@@ -535,16 +571,19 @@ int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* o) {
   const AlignArgs& a = c->aa;
   const size_t B = (size_t)a.B;
   cudaStream_t s = c->stream;
-  if (o->T_cur_w) CK(cudaMemcpyAsync(o->T_cur_w, a.out_T, B * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->n_tracked) CK(cudaMemcpyAsync(o->n_tracked, a.out_n_tracked, B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  if (o->H) CK(cudaMemcpyAsync(o->H, a.out_H, B * 36 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->seg_killed && a.n_segs > 0)
-    CK(cudaMemcpyAsync(o->seg_killed, a.out_seg_killed, B * a.n_segs, cudaMemcpyDeviceToHost, s));
-  if (o->iters) CK(cudaMemcpyAsync(o->iters, a.out_iters, B * PLSVO_MAX_LEVELS * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (o->status) CK(cudaMemcpyAsync(o->status, a.out_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (o->patch_iters) CK(cudaMemcpyAsync(o->patch_iters, a.out_patch_iters, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  if (o->patch_levels) CK(cudaMemcpyAsync(o->patch_levels, a.out_patch_levels, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  // one D2H of the whole output block into pinned staging, then plain copies into the caller's arrays
+  // (which are usually pageable: eight separate device->pageable copies cost several times more)
+  CK(cudaMemcpyAsync(c->h_out, c->d_out_T.p, c->out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  const char* hb = c->h_out;
+  if (o->T_cur_w) memcpy(o->T_cur_w, hb + c->oo_T, B * 7 * sizeof(double));
+  if (o->n_tracked) memcpy(o->n_tracked, hb + c->oo_ntr, B * sizeof(int64_t));
+  if (o->H) memcpy(o->H, hb + c->oo_H, B * 36 * sizeof(double));
+  if (o->seg_killed && a.n_segs > 0) memcpy(o->seg_killed, hb + c->oo_killed, B * a.n_segs);
+  if (o->iters) memcpy(o->iters, hb + c->oo_iters, B * PLSVO_MAX_LEVELS * sizeof(int32_t));
+  if (o->status) memcpy(o->status, hb + c->oo_status, B * sizeof(int32_t));
+  if (o->patch_iters) memcpy(o->patch_iters, hb + c->oo_pi, B * sizeof(uint32_t));
+  if (o->patch_levels) memcpy(o->patch_levels, hb + c->oo_pl, B * sizeof(uint32_t));
   return PLSVO_OK;
 }
 
@@ -552,13 +591,71 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
                           const plsvo_align_result* o) {
   if (!ctx || !b || !p || !o) return PLSVO_ERR_INVALID;
   plsvo_ctx_impl* c = CTX(ctx);
-  // Optional chunked pipeline (PLSVO_E2E_CHUNKS=k): the batch is cut into k chunks and a second stream copies
-  // chunk i+1 to the device while the kernel aligns chunk i.  Measured on B200/PCIe5 at B=1024 the single-shot
-  // path is faster (2.63 ms vs 3.11 ms with k=2: half-batches under-fill the 592 CTA slots and the H2D leg,
-  // 82 MB at ~48 GB/s, dominates either way), so the default is one chunk.
-  int chunks = 1;
+  // Host-buffer pipeline.  Default for large batches: ONE persistent kernel over the whole batch is
+  // launched immediately while a second stream copies the batch to the device in chunks of 128 pairs
+  // and bumps an arrival counter after each chunk; the kernel's work queue hands a pair out only once
+  // its chunk has landed (arrival gate), so the PCIe leg and the compute leg overlap without cutting
+  // the batch into under-filled kernels.  Chunks of 128 pairs keep every array's chunk boundary
+  // 128-byte aligned (no cache line shared between an arrived and an in-flight chunk).
+  // PLSVO_E2E_CHUNKS=k (k>=2) selects the older k-kernel pipeline, PLSVO_E2E_CHUNKS=1 the plain
+  // upload -> launch -> download sequence.
+  int chunks = 0;
   const char* cenv = getenv("PLSVO_E2E_CHUNKS");
   if (cenv && atoi(cenv) >= 1) chunks = std::min(atoi(cenv), 8);
+  bool gated = (chunks == 0) && b->batch >= 256;
+  if (gated) {
+    for (int l = p->min_level; l <= p->max_level && l < PLSVO_MAX_LEVELS && l >= 0; ++l) {
+      const int rows = b->cam.height >> l;
+      const bool direct = b->ref_img[l] && b->img_stride[l] == (size_t)rows * b->img_pitch[l] && b->img_pitch[l] % 4 == 0 &&
+                          b->img_stride[l] % 16 == 0;
+      if (!direct) gated = false;  // padded layouts need a device-side repack kernel: not under the gate
+    }
+  }
+  if (gated) {
+    CK(cudaSetDevice(c->device));
+    if (!c->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 8; ++k) CK(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming));
+    }
+    const size_t B = (size_t)b->batch;
+    int chunk = 512;  // multiple of 128 pairs: every array's chunk boundary stays 128-byte aligned
+    const char* genv = getenv("PLSVO_GATE_CHUNK");
+    if (genv && atoi(genv) >= 128) chunk = atoi(genv) / 128 * 128;
+    const int n_chunks = (int)((B + chunk - 1) / chunk);
+    if (!c->h_flags || c->h_flags_cap < n_chunks) {
+      if (c->h_flags) cudaFreeHost(c->h_flags);
+      c->h_flags = nullptr;
+      CK(cudaHostAlloc((void**)&c->h_flags, sizeof(unsigned int) * (size_t)n_chunks, cudaHostAllocDefault));
+      c->h_flags_cap = n_chunks;
+    }
+    for (int k = 0; k < n_chunks; ++k) c->h_flags[k] = (unsigned int)(k + 1);
+    // the copy stream must not overtake work already queued on the main stream; the arrival counter is
+    // cleared on the main stream before the copy stream may bump it
+    CK(ensure(c->d_counter, 256));
+    unsigned int* d_arrived = static_cast<unsigned int*>(c->d_counter.p) + 32;
+    CK(cudaMemsetAsync(d_arrived, 0, sizeof(unsigned int), c->stream));
+    CK(cudaEventRecord(c->start_ev, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->start_ev, 0));
+    // enqueue every chunk copy first (asynchronous from pinned memory): the host-side sizing below and
+    // the kernel launch then overlap with the DMA
+    int rc = PLSVO_OK;
+    for (int k = 0; k < n_chunks; ++k) {
+      rc = align_upload_impl(c, b, (size_t)k * chunk, std::min<size_t>((size_t)(k + 1) * chunk, B), c->copy_stream,
+                             k == 0 ? 2 : 0);
+      if (rc != PLSVO_OK) return rc;
+      CK(cudaMemcpyAsync(d_arrived, &c->h_flags[k], sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    rc = align_upload_impl(c, b, 0, 0, c->copy_stream, 3);  // host-side sizing (segment-sample bound, outputs)
+    if (rc != PLSVO_OK) return rc;
+    AlignPlan plan;
+    rc = align_plan(c, p, (int)B, &plan);
+    if (rc != PLSVO_OK) return rc;
+    rc = align_launch_range(c, plan, 0, B, 0, c->stream, chunk);  // gated on arrivals
+    if (rc != PLSVO_OK) return rc;
+    return plsvo_align_download(ctx, o);
+  }
+  if (chunks == 0) chunks = 1;
   if (chunks > b->batch) chunks = 1;
   if (chunks == 1) {
     int rc = plsvo_align_upload(ctx, b);
@@ -581,7 +678,7 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
   AlignPlan plan;
   for (int k = 0; k < chunks; ++k) {
     const size_t b0 = B * k / chunks, b1 = B * (k + 1) / chunks;
-    int rc = align_upload_impl(c, b, b0, b1, c->copy_stream, k == 0);
+    int rc = align_upload_impl(c, b, b0, b1, c->copy_stream, k == 0 ? 1 : 0);
     if (rc != PLSVO_OK) return rc;
     CK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
     if (k == 0) {

@@ -192,3 +192,18 @@ def test_align_segments_longer_than_a_warp(pkg, abi, synth, oracle, gen_device):
     gpu, ref = _run_both(pkg, abi, synth, oracle, data, 2, 0)
     assert (data.seg_length / 16 > 32).any()
     _check(synth, gpu, ref, exact_iters=False)
+
+
+def test_align_gated_host_pipeline_matches_single_shot(pkg, synth, gen_device, monkeypatch):
+    """Default host-buffer path for >= 256 pairs: one persistent kernel gated on chunk arrivals while a copy
+    stream streams the batch in.  Results must equal the plain upload -> launch -> download sequence."""
+    data = synth.make_align_batch(batch=300, n_pts=64, n_segs=12, device=gen_device, seed=3750)
+    monkeypatch.setenv("PLSVO_E2E_CHUNKS", "1")
+    plain = pkg.SparseImgAlign(4, 2, 30).run(data)
+    monkeypatch.delenv("PLSVO_E2E_CHUNKS")
+    for _ in range(3):
+        gated = pkg.SparseImgAlign(4, 2, 30).run(data)
+        np.testing.assert_array_equal(plain.T_cur_w, gated.T_cur_w)
+        np.testing.assert_array_equal(plain.n_tracked, gated.n_tracked)
+        np.testing.assert_array_equal(plain.iters, gated.iters)
+        np.testing.assert_array_equal(plain.H, gated.H)
