@@ -225,6 +225,32 @@ typedef struct plsvo_pyramid_result {
 
 int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out);
 
+/* ------------------------------------------------------------------------------------------
+ * Feature alignment (SURVEY.md §8f "next", rank 1): feature_alignment::align2D,
+ * include/plsvo/feature_alignment.h:49-55, src/feature_alignment.cpp:160-290 (scalar path) — the 8x8
+ * inverse-compositional refinement Matcher::findMatchDirect runs per feature (src/matcher.cpp:201).
+ * n features; feature i searches pyramid level level[i] of frame image_index[i].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct plsvo_align2d_batch {
+  int32_t n_features, n_images, width, height; /* width/height = level-0 size of the frames */
+  int32_t n_iter, reserved;
+  const uint8_t* img[PLSVO_MAX_LEVELS]; /* cur_img per level: frame b at img[l] + b*img_stride[l] */
+  size_t img_pitch[PLSVO_MAX_LEVELS];
+  size_t img_stride[PLSVO_MAX_LEVELS];
+  const int32_t* image_index;           /* [n] */
+  const int32_t* level;                 /* [n] */
+  const uint8_t* ref_patch_with_border; /* [n][10*10] */
+  const uint8_t* ref_patch;             /* [n][8*8]   */
+  const double* px;                     /* [n][2] cur_px_estimate on entry (pixels of the search level) */
+} plsvo_align2d_batch;
+
+typedef struct plsvo_align2d_result {
+  double* px;         /* [n][2] cur_px_estimate on return */
+  uint8_t* converged; /* [n]    return value of align2D */
+} plsvo_align2d_result;
+
+int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch* in, const plsvo_align2d_result* out);
+
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 int64_t plsvo_launch_count(const plsvo_ctx* ctx);
 

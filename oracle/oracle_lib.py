@@ -50,6 +50,8 @@ def load(abi):
         fn.argtypes = [P(C.c_double)] * (n_in + 1)
     lib.plsvo_oracle_half_sample.restype = None
     lib.plsvo_oracle_half_sample.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8), C.c_size_t]
+    lib.plsvo_oracle_align2d.restype = C.c_int
+    lib.plsvo_oracle_align2d.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_double)]
     lib.plsvo_oracle_hardware_threads.restype = C.c_int
     _lib = lib
     return lib
@@ -106,3 +108,21 @@ def pyramid(abi, img0, n_levels: int):
             lib.plsvo_oracle_half_sample(prev[b].ctypes.data_as(u8p), W, H, prev.strides[1], out[b].ctypes.data_as(u8p), out.strides[1])
         levels.append(out)
     return levels
+
+
+def align2d(abi, cur_pyr, image_index, level, border, ref, px, n_iter):
+    """feature_alignment::align2D restated, looped over features -> (converged [n] bool, px [n,2])."""
+    lib = load(abi)
+    u8p, dp = C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+    out = np.array(px, np.float64, copy=True)
+    conv = np.zeros(len(image_index), bool)
+    border = np.ascontiguousarray(border, np.uint8)
+    ref = np.ascontiguousarray(ref, np.uint8)
+    for i in range(len(image_index)):
+        im = np.ascontiguousarray(cur_pyr[int(level[i])][int(image_index[i])])
+        p = out[i].copy()
+        conv[i] = bool(lib.plsvo_oracle_align2d(im.ctypes.data_as(u8p), im.shape[1], im.shape[0], im.strides[0],
+                                                border[i].ctypes.data_as(u8p), ref[i].ctypes.data_as(u8p), n_iter,
+                                                p.ctypes.data_as(dp)))
+        out[i] = p
+    return conv, out

@@ -1055,5 +1055,83 @@ void plsvo_oracle_half_sample(const uint8_t* in, int cols, int rows, size_t in_p
   }
 }
 
+// feature_alignment::align2D, scalar path — src/feature_alignment.cpp:160-290.  cur_img: cols x rows, row step
+// cur_step; ref_patch_with_border 10x10, ref_patch 8x8; px = cur_px_estimate in/out.  Returns `converged`.
+// Hinv = H.inverse() follows Eigen's fixed-size 3x3 inverse (cofactors of column 0, determinant, 1/det).
+int plsvo_oracle_align2d(const uint8_t* cur_img, int cols, int rows, size_t cur_step_, const uint8_t* ref_patch_with_border,
+                         const uint8_t* ref_patch, int n_iter, double* px) {
+  const int patch_size_ = 8;
+  Image im{cur_img, cols, rows, (int)cur_step_};
+  bool converged = false;
+  float ref_patch_dx[64], ref_patch_dy[64];
+  float H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  const int ref_step = patch_size_ + 2;
+  float* it_dx = ref_patch_dx;
+  float* it_dy = ref_patch_dy;
+  for (int y = 0; y < patch_size_; ++y) {
+    const uint8_t* it = ref_patch_with_border + (y + 1) * ref_step + 1;
+    for (int x = 0; x < patch_size_; ++x, ++it, ++it_dx, ++it_dy) {
+      float J[3];
+      J[0] = 0.5 * (it[1] - it[-1]);
+      J[1] = 0.5 * (it[ref_step] - it[-ref_step]);
+      J[2] = 1;
+      *it_dx = J[0];
+      *it_dy = J[1];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) H[r][c] += J[r] * J[c];
+    }
+  }
+  float Hinv[3][3];
+  {
+    auto cof = [&](int i, int j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      return H[i1][j1] * H[i2][j2] - H[i1][j2] * H[i2][j1];
+    };
+    const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const float det = (c0 * H[0][0] + c1 * H[1][0]) + c2 * H[2][0];
+    const float invdet = 1.0f / det;
+    Hinv[0][0] = c0 * invdet, Hinv[0][1] = c1 * invdet, Hinv[0][2] = c2 * invdet;
+    Hinv[1][0] = cof(0, 1) * invdet, Hinv[1][1] = cof(1, 1) * invdet, Hinv[1][2] = cof(2, 1) * invdet;
+    Hinv[2][0] = cof(0, 2) * invdet, Hinv[2][1] = cof(1, 2) * invdet, Hinv[2][2] = cof(2, 2) * invdet;
+  }
+  float mean_diff = 0;
+  float u = (float)px[0];
+  float v = (float)px[1];
+  const float min_update_squared = 0.03 * 0.03;
+  const int cur_step = (int)cur_step_;
+  float update[3] = {0, 0, 0};
+  for (int iter = 0; iter < n_iter; ++iter) {
+    Patch patch(im);
+    patch.setPosition((double)u, (double)v);
+    if (!patch.isInFrame(4)) break;
+    patch.computeInterpWeights();
+    const uint8_t* roi = im.data + (size_t)(patch.v_ref_i - 4) * im.stride + (patch.u_ref_i - 4);
+    const uint8_t* it_ref = ref_patch;
+    float* it_ref_dx = ref_patch_dx;
+    float* it_ref_dy = ref_patch_dy;
+    float Jres[3] = {0, 0, 0};
+    for (int y = 0; y < 8; ++y) {
+      const uint8_t* ptr = roi + (size_t)y * im.stride;
+      for (int x = 0; x < 8; ++x, ++ptr, ++it_ref, ++it_ref_dx, ++it_ref_dy) {
+        float search_pixel = patch.wTL * ptr[0] + patch.wTR * ptr[1] + patch.wBL * ptr[cur_step] + patch.wBR * ptr[cur_step + 1];
+        float res = search_pixel - *it_ref + mean_diff;
+        Jres[0] -= res * (*it_ref_dx);
+        Jres[1] -= res * (*it_ref_dy);
+        Jres[2] -= res;
+      }
+    }
+    for (int r = 0; r < 3; ++r) update[r] = (Hinv[r][0] * Jres[0] + Hinv[r][1] * Jres[1]) + Hinv[r][2] * Jres[2];
+    u += update[0];
+    v += update[1];
+    mean_diff += update[2];
+    if (update[0] * update[0] + update[1] * update[1] < min_update_squared) {
+      converged = true;
+      break;
+    }
+  }
+  px[0] = u, px[1] = v;
+  return converged ? 1 : 0;
+}
+
 int plsvo_oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 }

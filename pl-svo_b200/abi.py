@@ -143,6 +143,17 @@ class PyramidResult(C.Structure):
     _fields_ = [("level", _u8p * MAX_LEVELS), ("pitch", C.c_size_t * MAX_LEVELS), ("stride", C.c_size_t * MAX_LEVELS)]
 
 
+class Align2DBatch(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("n_images", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("n_iter", C.c_int32), ("reserved", C.c_int32),
+                ("img", _u8p * MAX_LEVELS), ("img_pitch", C.c_size_t * MAX_LEVELS), ("img_stride", C.c_size_t * MAX_LEVELS),
+                ("image_index", _i32p), ("level", _i32p), ("ref_patch_with_border", _u8p), ("ref_patch", _u8p), ("px", _f64p)]
+
+
+class Align2DResult(C.Structure):
+    _fields_ = [("px", _f64p), ("converged", _u8p)]
+
+
 # ------------------------------------------------------------------------------------------------
 # numpy <-> struct helpers
 # ------------------------------------------------------------------------------------------------
@@ -306,6 +317,7 @@ ABI_SYMBOLS = [
     ("plsvo_poseopt_download", C.c_int, [C.c_void_p, _P(PoseOptResult)]),
     ("plsvo_poseopt_batch_run", C.c_int, [C.c_void_p, _P(PoseOptBatch), _P(PoseOptParams), _P(PoseOptResult)]),
     ("plsvo_pyramid_batch_run", C.c_int, [C.c_void_p, _P(PyramidBatch), _P(PyramidResult)]),
+    ("plsvo_align2d_batch_run", C.c_int, [C.c_void_p, _P(Align2DBatch), _P(Align2DResult)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
     ("plsvo_selftest_weight", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
     ("plsvo_version", C.c_char_p, []),
@@ -333,3 +345,23 @@ def load_library(path: str | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def make_align2d_batch(pyr, image_index, level, border, ref, px, n_iter, width, height):
+    """pyr: {level: u8 [n_images,h,w]}; border u8 [n,10,10]; ref u8 [n,8,8]; px f64 [n,2]."""
+    b = Align2DBatch()
+    keep = [pyr, image_index, level, border, ref, px]
+    b.n_features, b.n_iter = len(image_index), n_iter
+    b.width, b.height = width, height
+    for l, im in pyr.items():
+        assert im.dtype == np.uint8 and im.ndim == 3 and im.strides[2] == 1
+        b.n_images = im.shape[0]
+        b.img[l] = im.ctypes.data_as(_u8p)
+        b.img_pitch[l] = im.strides[1]
+        b.img_stride[l] = im.strides[0]
+    b.image_index = _ptr(image_index, np.int32)
+    b.level = _ptr(level, np.int32)
+    b.ref_patch_with_border = _ptr(border.reshape(len(image_index), -1), np.uint8)
+    b.ref_patch = _ptr(ref.reshape(len(image_index), -1), np.uint8)
+    b.px = _ptr(px, np.float64)
+    return b, keep

@@ -157,3 +157,26 @@ def createImgPyramid(img_level_0, n_levels: int, ctx: Context | None = None):
         r.stride[l] = out.strides[0]
     ctx.check(ctx.lib.plsvo_pyramid_batch_run(ctx.handle, C.byref(b), C.byref(r)), "plsvo_pyramid_batch_run")
     return levels
+
+
+class feature_alignment:
+    """Namespace mirror of plsvo::feature_alignment (include/plsvo/feature_alignment.h:49-55)."""
+
+    @staticmethod
+    def align2D(cur_pyr, image_index, level, ref_patch_with_border, ref_patch, n_iter, cur_px_estimate,
+                width: int, height: int, ctx: Context | None = None):
+        """Batched align2D (src/feature_alignment.cpp:160-290): returns (converged [n] bool, px [n,2])."""
+        import numpy as np
+
+        ctx = ctx or default_context()
+        image_index = np.ascontiguousarray(image_index, np.int32)
+        level = np.ascontiguousarray(level, np.int32)
+        border = np.ascontiguousarray(ref_patch_with_border, np.uint8)
+        ref = np.ascontiguousarray(ref_patch, np.uint8)
+        px = np.ascontiguousarray(cur_px_estimate, np.float64)
+        b, keep = abi.make_align2d_batch(cur_pyr, image_index, level, border, ref, px, n_iter, width, height)
+        out_px = np.zeros_like(px)
+        conv = np.zeros(len(image_index), np.uint8)
+        r = abi.Align2DResult(out_px.ctypes.data_as(C.POINTER(C.c_double)), conv.ctypes.data_as(C.POINTER(C.c_uint8)))
+        ctx.check(ctx.lib.plsvo_align2d_batch_run(ctx.handle, C.byref(b), C.byref(r)), "plsvo_align2d_batch_run")
+        return conv.astype(bool), out_px

@@ -1,0 +1,139 @@
+// align2d_kernel.cu — feature_alignment::align2D (src/feature_alignment.cpp:160-290): 8x8 inverse-
+// compositional Lucas-Kanade refinement of a feature position (2 DoF + mean intensity offset), the
+// per-feature kernel of Matcher::findMatchDirect (src/matcher.cpp:201,257,268).  SURVEY.md §8f rank 1
+// ("next"): the step between the two hot-path calls.
+//
+// One thread per feature keeps the reference's sequential fp32 accumulation order over the 64 pixels,
+// so positions and convergence flags are bit-identical to the scalar reference code (the SSE2/NEON
+// variants of the reference use fixed-point arithmetic and differ from its own scalar path).
+// The 10x10 reference patch with border and the 8x8 reference patch of a feature live in shared
+// memory; template gradients are recomputed from the border patch (two byte subtractions) instead
+// of being cached.  Image bytes come straight from global memory / L2 (9x9 footprint per iteration).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "internal.h"
+
+namespace plsvo {
+namespace {
+
+constexpr int kA2Threads = 128;
+
+__global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a) {
+  __shared__ uint8_t s_border[kA2Threads][104];  // 100 used (+4 pad keeps rows word aligned)
+  __shared__ uint8_t s_ref[kA2Threads][64];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kA2Threads + tid;
+  const bool active = i < a.n;
+  if (active) {
+    const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.ref_patch_with_border + (size_t)i * 100);
+    const uint32_t* gr = reinterpret_cast<const uint32_t*>(a.ref_patch + (size_t)i * 64);
+    uint32_t* sb = reinterpret_cast<uint32_t*>(s_border[tid]);
+    uint32_t* sr = reinterpret_cast<uint32_t*>(s_ref[tid]);
+#pragma unroll
+    for (int k = 0; k < 25; ++k) sb[k] = gb[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sr[k] = gr[k];
+  }
+  if (!active) return;
+  const uint8_t* border = s_border[tid];
+  const uint8_t* ref = s_ref[tid];
+  const int level = a.level[i];
+  const int cols = a.width >> level, rows = a.height >> level;
+  const int cur_step = (int)a.pitch[level];
+  const uint8_t* img = a.img[level] + (size_t)a.image_index[i] * a.stride[level];
+
+  // ---- template Hessian (:183-201): J = (0.5*dx, 0.5*dy, 1), H = sum J J^T (exact in fp32) ----
+  float H00 = 0, H01 = 0, H02 = 0, H11 = 0, H12 = 0, H22 = 0;
+  for (int y = 0; y < 8; ++y) {
+    const uint8_t* it = border + (y + 1) * 10 + 1;
+    for (int x = 0; x < 8; ++x, ++it) {
+      const float J0 = (float)(0.5 * (double)((int)it[1] - (int)it[-1]));
+      const float J1 = (float)(0.5 * (double)((int)it[10] - (int)it[-10]));
+      H00 = __fadd_rn(H00, __fmul_rn(J0, J0));
+      H01 = __fadd_rn(H01, __fmul_rn(J0, J1));
+      H02 = __fadd_rn(H02, J0);
+      H11 = __fadd_rn(H11, __fmul_rn(J1, J1));
+      H12 = __fadd_rn(H12, J1);
+      H22 = __fadd_rn(H22, 1.0f);
+    }
+  }
+  // ---- Hinv = H.inverse(): Eigen's fixed-size 3x3 path (cofactors of column 0, determinant, 1/det) ----
+  const float m00 = H00, m01 = H01, m02 = H02, m10 = H01, m11 = H11, m12 = H12, m20 = H02, m21 = H12, m22 = H22;
+#define COF(i1, j1, i2, j2, i3, j3, i4, j4) __fsub_rn(__fmul_rn(m##i1##j1, m##i2##j2), __fmul_rn(m##i3##j3, m##i4##j4))
+  const float c00 = COF(1, 1, 2, 2, 1, 2, 2, 1);  // cofactor<0,0>
+  const float c10 = COF(2, 1, 0, 2, 2, 2, 0, 1);  // cofactor<1,0>
+  const float c20 = COF(0, 1, 1, 2, 0, 2, 1, 1);  // cofactor<2,0>
+  const float det = __fadd_rn(__fadd_rn(__fmul_rn(c00, m00), __fmul_rn(c10, m10)), __fmul_rn(c20, m20));
+  const float invdet = __fdiv_rn(1.0f, det);
+  const float c01 = COF(1, 2, 2, 0, 1, 0, 2, 2);  // cofactor<0,1>
+  const float c11 = COF(2, 2, 0, 0, 2, 0, 0, 2);  // cofactor<1,1>
+  const float c21 = COF(0, 2, 1, 0, 0, 0, 1, 2);  // cofactor<2,1>
+  const float c02 = COF(1, 0, 2, 1, 1, 1, 2, 0);  // cofactor<0,2>
+  const float c12 = COF(2, 0, 0, 1, 2, 1, 0, 0);  // cofactor<1,2>
+  const float c22 = COF(0, 0, 1, 1, 0, 1, 1, 0);  // cofactor<2,2>
+#undef COF
+  // result.row(0) = cofactors_col0 * invdet ; result(1,0)=c01*invdet ; (1,1)=c11 ; (1,2)=c21 ; (2,0)=c02 ; (2,1)=c12 ; (2,2)=c22
+  const float I00 = __fmul_rn(c00, invdet), I01 = __fmul_rn(c10, invdet), I02 = __fmul_rn(c20, invdet);
+  const float I10 = __fmul_rn(c01, invdet), I11 = __fmul_rn(c11, invdet), I12 = __fmul_rn(c21, invdet);
+  const float I20 = __fmul_rn(c02, invdet), I21 = __fmul_rn(c12, invdet), I22 = __fmul_rn(c22, invdet);
+
+  float mean_diff = 0.f;
+  float u = (float)a.px[2 * (size_t)i], v = (float)a.px[2 * (size_t)i + 1];
+  const float min_update_squared = (float)(0.03 * 0.03);
+  bool converged = false;
+  for (int iter = 0; iter < a.n_iter; ++iter) {
+    // Patch::setPosition / isInFrame(halfsize=4) / computeInterpWeights (src/feature.cpp:189-208)
+    const float fu = floorf(u), fv = floorf(v);
+    const int ui = (int)fu, vi = (int)fv;
+    if (ui < 4 || vi < 4 || ui >= cols - 4 || vi >= rows - 4) break;
+    const float su = __fsub_rn(u, fu), sv = __fsub_rn(v, fv);
+    const float wTL = (float)((1.0 - (double)su) * (1.0 - (double)sv));
+    const float wTR = (float)((double)su * (1.0 - (double)sv));
+    const float wBL = (float)((1.0 - (double)su) * (double)sv);
+    const float wBR = __fmul_rn(su, sv);
+    float J0 = 0.f, J1 = 0.f, J2 = 0.f;
+    const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
+    const uint8_t* it_ref = ref;
+    for (int y = 0; y < 8; ++y, row += cur_step) {
+      const uint8_t* itb = border + (y + 1) * 10 + 1;
+#pragma unroll
+      for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
+        const float search_pixel =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, (float)row[x]), __fmul_rn(wTR, (float)row[x + 1])),
+                                __fmul_rn(wBL, (float)row[x + cur_step])),
+                      __fmul_rn(wBR, (float)row[x + cur_step + 1]));
+        const float res = __fadd_rn(__fsub_rn(search_pixel, (float)*it_ref), mean_diff);
+        const float dx = (float)(0.5 * (double)((int)itb[1] - (int)itb[-1]));
+        const float dy = (float)(0.5 * (double)((int)itb[10] - (int)itb[-10]));
+        J0 = __fsub_rn(J0, __fmul_rn(res, dx));
+        J1 = __fsub_rn(J1, __fmul_rn(res, dy));
+        J2 = __fsub_rn(J2, res);
+      }
+    }
+    // update = Hinv * Jres
+    const float up0 = __fadd_rn(__fadd_rn(__fmul_rn(I00, J0), __fmul_rn(I01, J1)), __fmul_rn(I02, J2));
+    const float up1 = __fadd_rn(__fadd_rn(__fmul_rn(I10, J0), __fmul_rn(I11, J1)), __fmul_rn(I12, J2));
+    const float up2 = __fadd_rn(__fadd_rn(__fmul_rn(I20, J0), __fmul_rn(I21, J1)), __fmul_rn(I22, J2));
+    u = __fadd_rn(u, up0);
+    v = __fadd_rn(v, up1);
+    mean_diff = __fadd_rn(mean_diff, up2);
+    if (__fadd_rn(__fmul_rn(up0, up0), __fmul_rn(up1, up1)) < min_update_squared) {
+      converged = true;
+      break;
+    }
+  }
+  a.out_px[2 * (size_t)i] = (double)u;
+  a.out_px[2 * (size_t)i + 1] = (double)v;
+  a.out_converged[i] = converged ? 1 : 0;
+}
+
+}  // namespace
+
+cudaError_t align2d_kernel_launch(const Align2DArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  align2d_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace plsvo

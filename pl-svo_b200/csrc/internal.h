@@ -116,4 +116,21 @@ struct PyramidArgs {
 };
 cudaError_t pyramid_kernel_launch(const PyramidArgs& a, cudaStream_t s);
 
+
+// ---------------------------------------------------------------------------------------------
+struct Align2DArgs {
+  int n, n_iter, width, height;
+  const uint8_t* img[PLSVO_MAX_LEVELS];  // device, [n_images][rows_l][pitch_l]
+  uint32_t pitch[PLSVO_MAX_LEVELS];
+  size_t stride[PLSVO_MAX_LEVELS];
+  const int32_t* image_index;
+  const int32_t* level;
+  const uint8_t* ref_patch_with_border;  // [n][100]
+  const uint8_t* ref_patch;              // [n][64]
+  const double* px;                      // [n][2]
+  double* out_px;
+  uint8_t* out_converged;
+};
+cudaError_t align2d_kernel_launch(const Align2DArgs& a, cudaStream_t s);
+
 }  // namespace plsvo

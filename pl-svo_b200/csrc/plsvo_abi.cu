@@ -58,6 +58,7 @@ struct plsvo_ctx_impl {
   DevBuf p_T, p_pt_count, p_pt_f, p_pt_pos, p_pt_level, p_pt_valid, p_seg_count, p_seg_line, p_seg_spos, p_seg_epos,
       p_seg_level, p_seg_valid;
   DevBuf y_img;  // pyramid levels
+  DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv;  // align2D
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
 };
@@ -172,7 +173,8 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
-                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->p_T,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
+                    &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -850,6 +852,67 @@ extern "C" int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch
                              rows, cudaMemcpyDeviceToHost, s));
     }
   }
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
+}
+
+extern "C" int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch* in, const plsvo_align2d_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (in->n_features < 0 || in->n_images <= 0 || in->width <= 0 || in->height <= 0 || in->n_iter < 0)
+    return fail(c, PLSVO_ERR_INVALID, "align2d batch description");
+  if (in->n_features == 0) return PLSVO_OK;
+  if (!in->image_index || !in->level || !in->ref_patch_with_border || !in->ref_patch || !in->px || !out->px || !out->converged)
+    return fail(c, PLSVO_ERR_INVALID, "align2d arrays missing");
+  const size_t n = (size_t)in->n_features, B = (size_t)in->n_images;
+  for (size_t i = 0; i < n; ++i) {
+    const int l = in->level[i];
+    if (l < 0 || l >= PLSVO_MAX_LEVELS || !in->img[l] || in->image_index[i] < 0 || in->image_index[i] >= in->n_images)
+      return fail(c, PLSVO_ERR_INVALID, "align2d feature refers to a missing level or frame");
+  }
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Align2DArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = in->n_features, a.n_iter = in->n_iter, a.width = in->width, a.height = in->height;
+  size_t total = 0, off[PLSVO_MAX_LEVELS] = {0};
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    if (!in->img[l]) continue;
+    const int cols = in->width >> l, rows = in->height >> l;
+    if (cols <= 0 || rows <= 0 || in->img_pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "align2d level geometry");
+    a.pitch[l] = (uint32_t)((cols + 15) / 16 * 16);
+    a.stride[l] = (size_t)rows * a.pitch[l];
+    total = (total + 255) / 256 * 256;
+    off[l] = total;
+    total += a.stride[l] * B;
+  }
+  CK(ensure(c->f_img, total + 256));
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    if (!in->img[l]) continue;
+    const int cols = in->width >> l, rows = in->height >> l;
+    uint8_t* d = static_cast<uint8_t*>(c->f_img.p) + off[l];
+    a.img[l] = d;
+    if (in->img_stride[l] == (size_t)rows * in->img_pitch[l]) {
+      CK(cudaMemcpy2DAsync(d, a.pitch[l], in->img[l], in->img_pitch[l], cols, (size_t)rows * B, cudaMemcpyHostToDevice, s));
+    } else {
+      for (size_t b = 0; b < B; ++b)
+        CK(cudaMemcpy2DAsync(d + b * a.stride[l], a.pitch[l], in->img[l] + b * in->img_stride[l], in->img_pitch[l], cols, rows,
+                             cudaMemcpyHostToDevice, s));
+    }
+  }
+  CK(up(c->f_idx, in->image_index, n, s, &a.image_index));
+  CK(up(c->f_lvl, in->level, n, s, &a.level));
+  CK(up(c->f_border, in->ref_patch_with_border, n * 100, s, &a.ref_patch_with_border));
+  CK(up(c->f_ref, in->ref_patch, n * 64, s, &a.ref_patch));
+  CK(up(c->f_px, in->px, n * 2, s, &a.px));
+  CK(ensure(c->f_opx, n * 2 * sizeof(double)));
+  CK(ensure(c->f_oconv, n));
+  a.out_px = static_cast<double*>(c->f_opx.p);
+  a.out_converged = static_cast<uint8_t*>(c->f_oconv.p);
+  CK(align2d_kernel_launch(a, s));
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out->px, a.out_px, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->converged, a.out_converged, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
 }
