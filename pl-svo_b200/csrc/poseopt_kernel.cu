@@ -97,6 +97,7 @@ __device__ __forceinline__ double block_kth(const double* keys, int n, int k, in
         if (lane >= d) incl += v;
       }
       const int kk = (int)sel[1];
+      __syncwarp();  // every lane has read the rank before the owning lane overwrites it
       const int before = incl - sum;
       if (kk >= before && kk < incl) {  // exactly one lane
         int acc = before, bin = 0;
