@@ -29,11 +29,11 @@ def test_state_and_argument_errors(pkg, abi, synth, gen_device):
     batch.batch = 0
     assert lib.plsvo_align_upload(ctx.handle, C.byref(batch)) == abi.ERR_INVALID
     batch.batch = 2
-    saved = batch.pt_px
+    saved = C.cast(batch.pt_px, C.c_void_p).value  # the field object aliases the struct: keep the address
     batch.pt_px = None
     assert lib.plsvo_align_upload(ctx.handle, C.byref(batch)) == abi.ERR_INVALID
     assert b"point arrays" in lib.plsvo_last_error(ctx.handle)
-    batch.pt_px = saved
+    batch.pt_px = C.cast(C.c_void_p(saved), C.POINTER(C.c_double))
     assert lib.plsvo_align_upload(ctx.handle, C.byref(batch)) == abi.OK
     # level range that was not uploaded / nonsense parameters
     bad = abi.align_params(5, 1, 30)
