@@ -335,15 +335,6 @@ __device__ __forceinline__ void zero_gradients(float4* cache, int MP, int p) {
 // solve()/update() (:697-710).  tot = block totals [0..20]=H upper, [21..26]=Jres, [27]=chi2,
 // [28]=n_meas, [29]=patches evaluated.
 __device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level, int n_iter, double eps) {
-  double* H = ctl->H_last;
-  int idx = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j) {
-      H[i * 6 + j] = tot[idx];
-      H[j * 6 + i] = tot[idx];
-      ++idx;
-    }
-  for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
   const long long n_meas = (long long)tot[28];
   ctl->n_meas_last = n_meas;
   ctl->patch_iters += (unsigned int)tot[29];
@@ -364,7 +355,17 @@ __device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level,
 #pragma unroll
       for (int i = 0; i < 6; ++i) ctl->x[i] = xx[i];
     } else {
-      ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);  // pivoted Eigen-style path (degenerate systems)
+      // degenerate system: pivoted Eigen-style routine on the full symmetric matrix
+      double* H = ctl->H_last;
+      int idx = 0;
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) {
+          H[i * 6 + j] = tot[idx];
+          H[j * 6 + i] = tot[idx];
+          ++idx;
+        }
+      for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
+      ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
     }
   }
   if (isnan(ctl->x[0])) ctl->stop = 1;
@@ -395,6 +396,15 @@ __device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level,
   q.x = ctl->model[0], q.y = ctl->model[1], q.z = ctl->model[2], q.w = ctl->model[3];
   quat_to_R(q, ctl->R);
   ctl->t[0] = ctl->model[4], ctl->t[1] = ctl->model[5], ctl->t[2] = ctl->model[6];
+  if (flag) {  // last evaluated pass of this level: keep H_ (getFisherInformation, :97-102)
+    int idx = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) {
+        ctl->H_last[i * 6 + j] = tot[idx];
+        ctl->H_last[j * 6 + i] = tot[idx];
+        ++idx;
+      }
+  }
   ctl->flag = flag;
 }
 
