@@ -89,70 +89,76 @@ __device__ __forceinline__ SE3q se3_inverse(const SE3q& a) {
 }
 __device__ __forceinline__ Vec3 se3_act(const SE3q& T, Vec3 p) { return vadd(qrot(T.q, p), T.t); }
 
-// sin/cos for the SE3 exponential.  Gauss-Newton steps are small rotations: |x| < 0.5 takes a short
-// Taylor evaluation (truncation < 1e-22, i.e. below double rounding) so that the hot kernels do not
-// drag libdevice's sincos with its argument-reduction slow path through the instruction cache; larger
-// arguments (degenerate systems only) use sincos().
-__device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
-  if (fabs(x) < 0.5) {
-    const double x2 = x * x;
-    double ps = -1.0 / 355687428096000.0;  // -x^17/17!
-    ps = ps * x2 + 1.0 / 1307674368000.0;
-    ps = ps * x2 - 1.0 / 6227020800.0;
-    ps = ps * x2 + 1.0 / 39916800.0;
-    ps = ps * x2 - 1.0 / 362880.0;
-    ps = ps * x2 + 1.0 / 5040.0;
-    ps = ps * x2 - 1.0 / 120.0;
-    ps = ps * x2 + 1.0 / 6.0;
-    *s = x - x * x2 * ps;
-    double pc = 1.0 / 6402373705728000.0;  // x^18/18!
-    pc = pc * x2 - 1.0 / 20922789888000.0;
-    pc = pc * x2 + 1.0 / 87178291200.0;
-    pc = pc * x2 - 1.0 / 479001600.0;
-    pc = pc * x2 + 1.0 / 3628800.0;
-    pc = pc * x2 - 1.0 / 40320.0;
-    pc = pc * x2 + 1.0 / 720.0;
-    pc = pc * x2 - 1.0 / 24.0;
-    pc = pc * x2 + 0.5;
-    *c = 1.0 - x2 * pc;
-  } else {
-    sincos(x, s, c);
-  }
-}
-
-// SE3::exp([upsilon, omega]) — Sophus (non-templated) se3.cpp / so3.cpp
+// SE3::exp([upsilon, omega]) — Sophus (non-templated) se3.cpp / so3.cpp.
+// For |omega|^2 < 0.25 (every Gauss-Newton step of a converging run) the four scalar functions of theta
+// that Sophus evaluates with sqrt, sin, cos and three divisions —
+//   sin(theta/2)/theta, cos(theta/2), (1-cos theta)/theta^2, (theta-sin theta)/theta^3 —
+// are even in theta and are evaluated as short polynomials in theta^2 (truncation < 1e-20): no square
+// root, no division, no cancellation on the serial solver path.  They agree with the closed forms to
+// double rounding (and are more accurate than `theta - sin(theta)` for small theta).  Larger rotations
+// take the closed forms.
 __device__ __forceinline__ SE3q se3_exp(const double* u) {
   const Vec3 upsilon = v3(u[0], u[1], u[2]);
   const Vec3 omega = v3(u[3], u[4], u[5]);
-  const double theta = vnorm(omega);
-  const double half_theta = 0.5 * theta;
-  double imag_factor;
-  double s_half, c_half;
-  sincos_small(half_theta, &s_half, &c_half);
-  if (theta < 1e-10) {
-    const double theta_sq = theta * theta;
-    const double theta_po4 = theta_sq * theta_sq;
-    imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
+  const double t2 = omega.x * omega.x + omega.y * omega.y + omega.z * omega.z;
+  double imag_factor, real_factor, a, b;
+  if (t2 < 0.25) {
+    const double h2 = 0.25 * t2;  // (theta/2)^2
+    double ps = 1.0 / 355687428096000.0;  // sin(h)/h = 1 - h2/3! + h2^2/5! - ...
+    ps = ps * h2 - 1.0 / 1307674368000.0;
+    ps = ps * h2 + 1.0 / 6227020800.0;
+    ps = ps * h2 - 1.0 / 39916800.0;
+    ps = ps * h2 + 1.0 / 362880.0;
+    ps = ps * h2 - 1.0 / 5040.0;
+    ps = ps * h2 + 1.0 / 120.0;
+    ps = ps * h2 - 1.0 / 6.0;
+    ps = ps * h2 + 1.0;
+    imag_factor = 0.5 * ps;  // sin(theta/2)/theta
+    double pc = 1.0 / 20922789888000.0;  // cos(h) = 1 - h2/2! + h2^2/4! - ...
+    pc = pc * h2 - 1.0 / 87178291200.0;
+    pc = pc * h2 + 1.0 / 479001600.0;
+    pc = pc * h2 - 1.0 / 3628800.0;
+    pc = pc * h2 + 1.0 / 40320.0;
+    pc = pc * h2 - 1.0 / 720.0;
+    pc = pc * h2 + 1.0 / 24.0;
+    pc = pc * h2 - 0.5;
+    real_factor = pc * h2 + 1.0;
+    double pa = 1.0 / 6402373705728000.0;  // (1-cos t)/t^2 = 1/2! - t2/4! + t2^2/6! - ...
+    pa = pa * t2 - 1.0 / 20922789888000.0;
+    pa = pa * t2 + 1.0 / 87178291200.0;
+    pa = pa * t2 - 1.0 / 479001600.0;
+    pa = pa * t2 + 1.0 / 3628800.0;
+    pa = pa * t2 - 1.0 / 40320.0;
+    pa = pa * t2 + 1.0 / 720.0;
+    pa = pa * t2 - 1.0 / 24.0;
+    a = pa * t2 + 0.5;
+    double pb = 1.0 / 121645100408832000.0;  // (t-sin t)/t^3 = 1/3! - t2/5! + t2^2/7! - ...
+    pb = pb * t2 - 1.0 / 355687428096000.0;
+    pb = pb * t2 + 1.0 / 1307674368000.0;
+    pb = pb * t2 - 1.0 / 6227020800.0;
+    pb = pb * t2 + 1.0 / 39916800.0;
+    pb = pb * t2 - 1.0 / 362880.0;
+    pb = pb * t2 + 1.0 / 5040.0;
+    pb = pb * t2 - 1.0 / 120.0;
+    b = pb * t2 + 1.0 / 6.0;
   } else {
+    const double theta = sqrt(t2);
+    double s_half, c_half, sn, cs;
+    sincos(0.5 * theta, &s_half, &c_half);
+    sincos(theta, &sn, &cs);
     imag_factor = s_half / theta;
+    real_factor = c_half;
+    a = (1 - cs) / t2;
+    b = (theta - sn) / (t2 * theta);
   }
   SE3q r;
   Quat q;
-  q.x = imag_factor * omega.x, q.y = imag_factor * omega.y, q.z = imag_factor * omega.z, q.w = c_half;
+  q.x = imag_factor * omega.x, q.y = imag_factor * omega.y, q.z = imag_factor * omega.z, q.w = real_factor;
   r.q = qnormalized(q);
-  if (theta < 1e-10) {
-    r.t = qrot(r.q, upsilon);
-  } else {
-    // sin(theta), 1 - cos(theta) from the half angle (no second evaluation, no cancellation)
-    const double s = 2.0 * s_half * c_half;
-    const double one_minus_c = 2.0 * s_half * s_half;
-    const double theta_sq = theta * theta;
-    const double a = one_minus_c / theta_sq;
-    const double b = (theta - s) / (theta_sq * theta);
-    const Vec3 wu = vcross(omega, upsilon);
-    const Vec3 wwu = vcross(omega, wu);
-    r.t = vadd(vadd(upsilon, vscale(wu, a)), vscale(wwu, b));
-  }
+  // t = V*upsilon, V = I + a*Omega + b*Omega^2 (for theta -> 0 this tends to upsilon, as Sophus' small-angle branch)
+  const Vec3 wu = vcross(omega, upsilon);
+  const Vec3 wwu = vcross(omega, wu);
+  r.t = vadd(vadd(upsilon, vscale(wu, a)), vscale(wwu, b));
   return r;
 }
 // rotation matrix of a unit quaternion (Eigen toRotationMatrix), row-major R[9]
@@ -324,7 +330,7 @@ __device__ __forceinline__ bool ldlt6_reg(const double* Hu, const double* g, dou
     for (int k = 0; k < j; ++k) s -= L[j][k] * T[j][k];
 
     ok = ok && (s > tiny);
-    dinv[j] = 1.0 / s;
+    dinv[j] = __drcp_rn(s);
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double t = A[i][j];
