@@ -126,3 +126,63 @@ def align2d(abi, cur_pyr, image_index, level, border, ref, px, n_iter):
                                                 p.ctypes.data_as(dp)))
         out[i] = p
     return conv, out
+
+
+# ---- oracle/_ref: the reference's own translation units (oracle/ref_harness.cpp, Makefile target `ref`) ----
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "libplsvo_ref.so")
+REFERENCE_ROOT = os.environ.get("PLSVO_REFERENCE_ROOT", "/root/reference")
+_ref_lib = None
+
+
+def build_ref(force: bool = False) -> str | None:
+    """Build oracle/_ref/libplsvo_ref.so when the reference sources are present (authoring container only).
+    Returns the path, or None when neither the sources nor a prebuilt library exist."""
+    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp")]
+    if all(os.path.exists(s) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "ref", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
+    return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_LIB_PATH)
+
+
+def load_ref(abi):
+    global _ref_lib
+    if _ref_lib is not None:
+        return _ref_lib
+    if not os.path.exists(REF_LIB_PATH):
+        raise FileNotFoundError(f"{REF_LIB_PATH} is not built (needs {REFERENCE_ROOT}; run `make -C oracle ref`)")
+    lib = C.CDLL(REF_LIB_PATH)
+    P = C.POINTER
+    lib.plsvo_ref_align_batch.restype = C.c_int
+    lib.plsvo_ref_align_batch.argtypes = [P(abi.AlignBatch), P(abi.AlignParams), P(abi.AlignResult), C.c_int]
+    lib.plsvo_ref_poseopt_batch.restype = C.c_int
+    lib.plsvo_ref_poseopt_batch.argtypes = [P(abi.PoseOptBatch), P(abi.PoseOptParams), P(abi.PoseOptResult), C.c_int]
+    lib.plsvo_ref_describe.restype = C.c_char_p
+    _ref_lib = lib
+    return lib
+
+
+def ref_align(abi, data, params=None, n_threads: int = 1):
+    """SparseImgAlign::run of the reference's own sparse_img_align.cpp on an AlignData batch -> abi.AlignOut."""
+    lib = load_ref(abi)
+    params = params or abi.align_params(data.max_level, data.min_level)
+    batch, keep = abi.make_align_batch(data)
+    out = abi.AlignOut(data.batch, data.n_segs)
+    rc = lib.plsvo_ref_align_batch(C.byref(batch), C.byref(params), C.byref(out.struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"reference align failed rc={rc}")
+    return out
+
+
+def ref_poseopt(abi, data, params=None, n_threads: int = 1):
+    """pose_optimizer::optimizeGaussNewton of the reference's own pose_optimizer.cpp -> abi.PoseOptOut."""
+    lib = load_ref(abi)
+    params = params or abi.poseopt_params()
+    batch, keep = abi.make_poseopt_batch(data)
+    out = abi.PoseOptOut(data.batch, data.n_pts, data.n_segs)
+    rc = lib.plsvo_ref_poseopt_batch(C.byref(batch), C.byref(params), C.byref(out.struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"reference poseopt failed rc={rc}")
+    return out

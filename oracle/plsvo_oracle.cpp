@@ -4,16 +4,23 @@
 // bench.py's cpu_baseline / --impl reference legs may load this library; the product
 // (pl-svo_b200/csrc) never links, loads or calls it.
 //
-// PARITY UNPINNED: the reference (rubengooj/pl-svo @ 5d4ca39) ships no tests, golden vectors or
-// fixtures for this path, and it cannot be compiled here (Eigen, Sophus, OpenCV C++, boost and
-// rpg_vikit are absent; no network).  This file is therefore a line-by-line restatement:
-//   * of the code that IS in /root/reference — each function cites the file:line it follows;
-//   * of the un-vendored third-party arithmetic the path calls (uzh-rpg/rpg_vikit vikit_common:
-//     NLLSSolver<6,SE3>, robust_cost, math_utils, PinholeCamera; strasdat/Sophus non-templated
-//     SE3/SO3; Eigen LDLT / inverse) restated from their published sources.  Neither is version
-//     pinned by the reference (CMakeLists.txt:40-41,57), see SURVEY.md §8c.
-// It is pinned instead by an independent NumPy restatement (oracle/np_oracle.py), analytic
-// properties (tests/test_oracle_*.py) and frozen traces under tests/golden/.
+// PARITY PINNED AGAINST THE REFERENCE RUN HERE.  The reference (rubengooj/pl-svo @ 5d4ca39) ships no
+// tests, golden vectors or fixtures for this path, and its own build cannot run in this image (cmake +
+// Eigen, Sophus, OpenCV C++, boost, rpg_vikit are absent; no network).  Its three translation units on the
+// path — src/sparse_img_align.cpp, src/pose_optimizer.cpp, src/feature.cpp — are however compiled
+// UNMODIFIED, where they lie under /root/reference, against the reference's own headers and small
+// stand-in headers for the absent third-party libraries (oracle/refdeps/, oracle/ref_harness.cpp,
+// `make -C oracle ref` -> oracle/_ref/libplsvo_ref.so).  tests/test_reference_tu_cpu.py requires this
+// file to reproduce that library BIT FOR BIT (poses, H, n_tracked, killed segments, iteration counts,
+// status; pose, covariance, scale, errors, counts, outlier flags) over the domain's edge cases, and
+// tests/golden/*.npz are outputs of that library (tests/golden/make_golden.py).
+// What remains a restatement on BOTH sides is the un-vendored third-party arithmetic the path calls
+// (uzh-rpg/rpg_vikit vikit_common: NLLSSolver<6,SE3>, robust_cost, math_utils, PinholeCamera;
+// strasdat/Sophus non-templated SE3/SO3; Eigen LDLT / inverse / quaternion), written from their
+// published sources; the reference pins no version of them (CMakeLists.txt:40-41,57).
+// Those pieces are additionally checked against closed forms, an independent NumPy restatement
+// (oracle/np_oracle.py) and analytic properties (tests/test_oracle_cpu.py).
+// This file is a line-by-line restatement: each function cites the reference file:line it follows.
 //
 // Arithmetic follows the source text as strict IEEE-754 without FMA contraction (build with
 // -ffp-contract=off): float where the reference uses float, double where it uses double.
@@ -71,6 +78,16 @@ inline Vec3 qrot(Quat q, Vec3 v) {  // Eigen QuaternionBase::_transformVector
   return v + uv * q.w + cross(qv, uv);
 }
 
+inline void quat_to_matrix(Quat q, double R[3][3]) {  // Eigen QuaternionBase::toRotationMatrix
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0][0] = 1 - (tyy + tzz), R[0][1] = txy - twz, R[0][2] = txz + twy;
+  R[1][0] = txy + twz, R[1][1] = 1 - (txx + tzz), R[1][2] = tyz - twx;
+  R[2][0] = txz - twy, R[2][1] = tyz + twx, R[2][2] = 1 - (txx + tyy);
+}
+
 struct SE3 {
   Quat q{0, 0, 0, 1};
   Vec3 t{0, 0, 0};
@@ -116,17 +133,25 @@ inline SE3 se3_exp(const double u[6]) {
   }
   SE3 r;
   r.q = qnormalized(Quat{imag_factor * omega.x, imag_factor * omega.y, imag_factor * omega.z, real_factor});
-  // V = I + (1-cos)/theta^2 * Omega + (theta - sin)/theta^3 * Omega^2 ;  t = V * upsilon
+  // V = I + (1-cos)/theta^2 * Omega + (theta - sin)/theta^3 * Omega^2 ;  t = V * upsilon, formed as 3x3
+  // matrices coefficient by coefficient exactly as Sophus writes it (se3.cpp, SE3::exp).
+  const double Om[3][3] = {{0, -omega.z, omega.y}, {omega.z, 0, -omega.x}, {-omega.y, omega.x, 0}};
+  double Om2[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Om2[i][j] = (Om[i][0] * Om[0][j] + Om[i][1] * Om[1][j]) + Om[i][2] * Om[2][j];
   if (theta < kSmallEps) {
-    r.t = qrot(r.q, upsilon);  // V = so3.matrix()
+    quat_to_matrix(r.q, V);  // V = so3.matrix()
   } else {
     const double theta_sq = theta * theta;
     const double a = (1 - std::cos(theta)) / theta_sq;
     const double b = (theta - std::sin(theta)) / (theta_sq * theta);
-    const Vec3 wu = cross(omega, upsilon);  // Omega * upsilon
-    const Vec3 wwu = cross(omega, wu);      // Omega^2 * upsilon
-    r.t = upsilon + wu * a + wwu * b;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) V[i][j] = ((i == j ? 1.0 : 0.0) + a * Om[i][j]) + b * Om2[i][j];
   }
+  const double u3[3] = {upsilon.x, upsilon.y, upsilon.z};
+  double t3[3];
+  for (int i = 0; i < 3; ++i) t3[i] = (V[i][0] * u3[0] + V[i][1] * u3[1]) + V[i][2] * u3[2];
+  r.t = {t3[0], t3[1], t3[2]};
   return r;
 }
 

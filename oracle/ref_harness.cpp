@@ -1,0 +1,291 @@
+// ref_harness.cpp — drives the reference's OWN translation units from flat batch arrays.
+//
+// TEST INFRASTRUCTURE, NOT THE PRODUCT (same rule as plsvo_oracle.cpp: only tests/, smoke() and
+// bench.py's CPU legs may load the library this builds).
+//
+// oracle/Makefile target `ref` compiles, unmodified and where they lie,
+//     /root/reference/src/sparse_img_align.cpp   /root/reference/src/pose_optimizer.cpp
+//     /root/reference/src/feature.cpp
+// against the reference's own headers (/root/reference/include/plsvo/*.h) and the stand-in
+// third-party headers in oracle/refdeps/ (Eigen, Sophus, rpg_vikit, OpenCV core, boost — absent
+// from the image and from /root/reference), links this file, and writes oracle/_ref/libplsvo_ref.so.
+// Nothing under /root/reference is copied into the repo; the .so is git-ignored and travels to
+// the GPU box like any other built artefact.
+//
+// This file only (1) defines the handful of out-of-line members of plsvo::Frame / Point /
+// LineSeg that live in reference sources we do not build (frame.cpp, feature3D.cpp: OpenCV image
+// processing and map bookkeeping, not on the path), (2) turns a plsvo_align_batch /
+// plsvo_poseopt_batch into Frame / PointFeat / LineFeat / Point / LineSeg objects, (3) makes the
+// two calls exactly as src/frame_handler_mono.cpp:272-274 and :327-329 make them, and (4) copies
+// the mutated state back out.  It is the checker for oracle/plsvo_oracle.cpp, which stays the
+// self-contained restatement.
+
+#include <plsvo/feature.h>
+#include <plsvo/feature3D.h>
+#include <plsvo/frame.h>
+#include <plsvo/pose_optimizer.h>
+#include <plsvo/sparse_img_align.h>
+#include <vikit/pinhole_camera.h>
+
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "../include/plsvo_b200.h"
+
+// ---- out-of-line members the unbuilt reference sources would provide --------------------------
+namespace plsvo {
+
+int Frame::frame_counter_ = 0;
+
+// src/frame.cpp:38-47 builds the pyramid with OpenCV; here the caller supplies the levels.
+Frame::Frame(vk::AbstractCamera* cam, const cv::Mat&, double timestamp)
+    : id_(0), timestamp_(timestamp), cam_(cam), key_pts_(5), is_keyframe_(false), v_kf_(NULL) {}
+
+// src/frame.cpp:49-53: a frame owns its features.
+Frame::~Frame() {
+  for (PointFeat* f : pt_fts_) delete f;
+  for (LineFeat* f : seg_fts_) delete f;
+}
+
+Point::Point(const Vector3d& pos) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {}
+bool Point::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
+void Point::optimize(const size_t) {}
+
+LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos)
+    : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {}
+bool LineSeg::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
+void LineSeg::optimize(const size_t) {}
+
+}  // namespace plsvo
+
+namespace {
+
+using plsvo::FramePtr;
+using Eigen::Quaterniond;
+using Eigen::Vector2d;
+using Eigen::Vector3d;
+using Sophus::SE3;
+
+SE3 pose_from7(const double* p) { return SE3(Quaterniond(p[3], p[0], p[1], p[2]), Vector3d(p[4], p[5], p[6])); }
+void pose_to7(const SE3& T, double* p) {
+  const Quaterniond& q = T.unit_quaternion();
+  p[0] = q.x(), p[1] = q.y(), p[2] = q.z(), p[3] = q.w();
+  p[4] = T.translation()[0], p[5] = T.translation()[1], p[6] = T.translation()[2];
+}
+Vector3d v3(const double* p) { return Vector3d(p[0], p[1], p[2]); }
+Vector2d v2(const double* p) { return Vector2d(p[0], p[1]); }
+
+// SparseImgAlign with its protected solver state readable and GN iterations counted per level.
+struct AlignProbe : plsvo::SparseImgAlign {
+  int iters[PLSVO_MAX_LEVELS] = {0};
+  AlignProbe(int max_level, int min_level, int n_iter)
+      : plsvo::SparseImgAlign(max_level, min_level, n_iter, plsvo::SparseImgAlign::GaussNewton, false, false) {}
+  void startIteration() override {
+    if (level_ >= 0 && level_ < PLSVO_MAX_LEVELS) ++iters[level_];
+  }
+  const Eigen::Matrix<double, 6, 6>& H() const { return H_; }
+};
+
+template <class F>
+void parallel_for(int n, int n_threads, F&& body) {
+  if (n_threads <= 1 || n <= 1) {
+    for (int i = 0; i < n; ++i) body(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < std::min(n_threads, n); ++t)
+    pool.emplace_back([&] {
+      for (int i = next++; i < n; i = next++) body(i);
+    });
+  for (auto& t : pool) t.join();
+}
+
+void align_one(const plsvo_align_batch* B, const plsvo_align_params* P, const plsvo_align_result* out, int b) {
+  const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
+  const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
+  const size_t po = (size_t)b * B->n_pts, so = (size_t)b * B->n_segs;
+
+  vk::PinholeCamera cam(B->cam.width, B->cam.height, B->cam.fx, B->cam.fy, B->cam.cx, B->cam.cy);
+  FramePtr ref(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+  FramePtr cur(new plsvo::Frame(&cam, cv::Mat(), 1.0));
+  ref->img_pyr_.resize(P->max_level + 1);
+  cur->img_pyr_.resize(P->max_level + 1);
+  for (int l = P->min_level; l <= P->max_level; ++l) {
+    const int cols = B->cam.width >> l, rows = B->cam.height >> l;
+    ref->img_pyr_[l] = cv::Mat(rows, cols, CV_8U, const_cast<uint8_t*>(B->ref_img[l] + (size_t)b * B->img_stride[l]), B->img_pitch[l]);
+    cur->img_pyr_[l] = cv::Mat(rows, cols, CV_8U, const_cast<uint8_t*>(B->cur_img[l] + (size_t)b * B->img_stride[l]), B->img_pitch[l]);
+  }
+  ref->T_f_w_ = pose_from7(B->T_ref_w + 7 * (size_t)b);
+  cur->T_f_w_ = pose_from7(B->T_cur_w + 7 * (size_t)b);
+
+  std::vector<std::unique_ptr<plsvo::Point>> points;
+  std::vector<std::unique_ptr<plsvo::LineSeg>> lines;
+  for (int i = 0; i < np; ++i) {
+    const bool valid = !B->pt_valid || B->pt_valid[po + i];
+    plsvo::Point* p3 = NULL;
+    if (valid) {
+      points.emplace_back(new plsvo::Point(v3(B->pt_pos + 3 * (po + i))));
+      p3 = points.back().get();
+    }
+    ref->pt_fts_.push_back(new plsvo::PointFeat(ref.get(), p3, v2(B->pt_px + 2 * (po + i)), v3(B->pt_f + 3 * (po + i)), 0));
+  }
+  std::vector<plsvo::LineFeat*> segs;
+  for (int j = 0; j < ns; ++j) {
+    const bool valid = !B->seg_valid || B->seg_valid[so + j];
+    plsvo::LineSeg* l3 = NULL;
+    if (valid) {
+      lines.emplace_back(new plsvo::LineSeg(v3(B->seg_spos + 3 * (so + j)), v3(B->seg_epos + 3 * (so + j))));
+      l3 = lines.back().get();
+    }
+    plsvo::LineFeat* f = new plsvo::LineFeat(ref.get(), l3, v2(B->seg_spx + 2 * (so + j)), v2(B->seg_epx + 2 * (so + j)),
+                                             v3(B->seg_sf + 3 * (so + j)), v3(B->seg_ef + 3 * (so + j)), 0);
+    f->length = B->seg_length[so + j];  // the ABI carries LineFeat::length explicitly
+    ref->seg_fts_.push_back(f);
+    segs.push_back(f);
+  }
+
+  // src/frame_handler_mono.cpp:272-274
+  AlignProbe img_align(P->max_level, P->min_level, P->n_iter);
+  img_align.eps_ = P->eps;  // the reference hard-codes 1e-6 (sparse_img_align.cpp:51); the ABI carries it
+  const bool empty = (np == 0 && ns == 0);
+  const size_t n_tracked = img_align.run(ref, cur);
+
+  if (out->T_cur_w) {
+    if (empty)
+      std::memcpy(out->T_cur_w + 7 * (size_t)b, B->T_cur_w + 7 * (size_t)b, 7 * sizeof(double));
+    else
+      pose_to7(cur->T_f_w_, out->T_cur_w + 7 * (size_t)b);
+  }
+  if (out->n_tracked) out->n_tracked[b] = (int64_t)n_tracked;
+  if (out->H)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) out->H[36 * (size_t)b + 6 * i + j] = empty ? 0.0 : img_align.H()(i, j);
+  if (out->seg_killed) {
+    for (int j = 0; j < B->n_segs; ++j) out->seg_killed[so + j] = 0;
+    for (int j = 0; j < ns; ++j) {
+      const bool valid = !B->seg_valid || B->seg_valid[so + j];
+      out->seg_killed[so + j] = (valid && segs[j]->feat3D == NULL) ? 1 : 0;
+    }
+  }
+  if (out->iters)
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) out->iters[(size_t)b * PLSVO_MAX_LEVELS + l] = img_align.iters[l];
+  if (out->status) out->status[b] = (empty ? 1 : 0) | (img_align.stop_ ? 2 : 0);
+  if (out->patch_iters) out->patch_iters[b] = 0;   // not observable from outside the reference class
+  if (out->patch_levels) out->patch_levels[b] = 0;
+}
+
+void poseopt_one(const plsvo_poseopt_batch* B, const plsvo_poseopt_params* P, const plsvo_poseopt_result* out, int b) {
+  const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
+  const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
+  const size_t po = (size_t)b * B->n_pts, so = (size_t)b * B->n_segs;
+
+  vk::PinholeCamera cam(640, 480, B->fx, B->fx, 320, 240);  // only errorMultiplier2() = |fx| is read
+  FramePtr frame(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+  frame->T_f_w_ = pose_from7(B->T_f_w + 7 * (size_t)b);
+  frame->Cov_.setZero();
+
+  std::vector<std::unique_ptr<plsvo::Point>> points;
+  std::vector<std::unique_ptr<plsvo::LineSeg>> lines;
+  std::vector<plsvo::PointFeat*> pts;
+  std::vector<plsvo::LineFeat*> segs;
+  int n_valid = 0;
+  for (int i = 0; i < np; ++i) {
+    const bool valid = !B->pt_valid || B->pt_valid[po + i];
+    plsvo::Point* p3 = NULL;
+    if (valid) {
+      points.emplace_back(new plsvo::Point(v3(B->pt_pos + 3 * (po + i))));
+      p3 = points.back().get();
+      ++n_valid;
+    }
+    plsvo::PointFeat* f = new plsvo::PointFeat(frame.get(), p3, Vector2d(0, 0), v3(B->pt_f + 3 * (po + i)), B->pt_level[po + i]);
+    frame->pt_fts_.push_back(f);
+    pts.push_back(f);
+  }
+  for (int j = 0; j < ns; ++j) {
+    const bool valid = !B->seg_valid || B->seg_valid[so + j];
+    plsvo::LineSeg* l3 = NULL;
+    if (valid) {
+      lines.emplace_back(new plsvo::LineSeg(v3(B->seg_spos + 3 * (so + j)), v3(B->seg_epos + 3 * (so + j))));
+      l3 = lines.back().get();
+      ++n_valid;
+    }
+    // bearing vectors are placeholders: the optimiser reads only LineFeat::line, set below
+    plsvo::LineFeat* f = new plsvo::LineFeat(frame.get(), l3, Vector2d(0, 0), Vector2d(1, 0), Vector3d(0, 0, 1), Vector3d(1, 0, 1),
+                                             B->seg_level[so + j]);
+    f->line = v3(B->seg_line + 3 * (so + j));
+    frame->seg_fts_.push_back(f);
+    segs.push_back(f);
+  }
+
+  double estimated_scale = 0, error_init = 0, error_final = 0;
+  size_t num_obs_pt = 0, num_obs_ls = 0;
+  // src/frame_handler_mono.cpp:327-329 (9-argument overload) / the exported 10-argument overload
+  if (P->n_iter_ref < 0)
+    plsvo::pose_optimizer::optimizeGaussNewton(P->reproj_thresh, (size_t)P->n_iter, false, frame, estimated_scale, error_init,
+                                               error_final, num_obs_pt, num_obs_ls);
+  else
+    plsvo::pose_optimizer::optimizeGaussNewton(P->reproj_thresh, (size_t)P->n_iter, (size_t)P->n_iter_ref, false, frame,
+                                               estimated_scale, error_init, error_final, num_obs_pt, num_obs_ls);
+
+  const bool no_obs = (n_valid == 0);
+  if (out->status) out->status[b] = no_obs ? 1 : 0;
+  if (out->T_f_w) {
+    if (no_obs)
+      std::memcpy(out->T_f_w + 7 * (size_t)b, B->T_f_w + 7 * (size_t)b, 7 * sizeof(double));
+    else
+      pose_to7(frame->T_f_w_, out->T_f_w + 7 * (size_t)b);
+  }
+  if (out->cov)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) out->cov[36 * (size_t)b + 6 * i + j] = frame->Cov_(i, j);
+  if (out->estimated_scale) out->estimated_scale[b] = estimated_scale;
+  if (out->error_init) out->error_init[b] = error_init;
+  if (out->error_final) out->error_final[b] = error_final;
+  if (out->num_obs_pt) out->num_obs_pt[b] = (int64_t)num_obs_pt;
+  if (out->num_obs_ls) out->num_obs_ls[b] = (int64_t)num_obs_ls;
+  if (out->pt_outlier) {
+    std::memset(out->pt_outlier + po, 0, B->n_pts);
+    for (int i = 0; i < np; ++i) {
+      const bool valid = !B->pt_valid || B->pt_valid[po + i];
+      out->pt_outlier[po + i] = (valid && pts[i]->feat3D == NULL) ? 1 : 0;
+    }
+  }
+  if (out->seg_outlier && B->n_segs) {
+    std::memset(out->seg_outlier + so, 0, B->n_segs);
+    for (int j = 0; j < ns; ++j) {
+      const bool valid = !B->seg_valid || B->seg_valid[so + j];
+      out->seg_outlier[so + j] = (valid && segs[j]->feat3D == NULL) ? 1 : 0;
+    }
+  }
+  if (out->iters) out->iters[2 * (size_t)b] = out->iters[2 * (size_t)b + 1] = -1;  // not observable from outside
+}
+
+}  // namespace
+
+extern "C" {
+
+int plsvo_ref_align_batch(const plsvo_align_batch* batch, const plsvo_align_params* params, const plsvo_align_result* out,
+                          int n_threads) {
+  if (!batch || !params || !out) return PLSVO_ERR_INVALID;
+  if (params->max_level < params->min_level || params->min_level < 0 || params->max_level >= PLSVO_MAX_LEVELS)
+    return PLSVO_ERR_INVALID;
+  parallel_for(batch->batch, n_threads, [&](int b) { align_one(batch, params, out, b); });
+  return PLSVO_OK;
+}
+
+int plsvo_ref_poseopt_batch(const plsvo_poseopt_batch* batch, const plsvo_poseopt_params* params,
+                            const plsvo_poseopt_result* out, int n_threads) {
+  if (!batch || !params || !out) return PLSVO_ERR_INVALID;
+  parallel_for(batch->batch, n_threads, [&](int b) { poseopt_one(batch, params, out, b); });
+  return PLSVO_OK;
+}
+
+const char* plsvo_ref_describe(void) {
+  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature}.cpp compiled unmodified against stand-in "
+         "Eigen/Sophus/vikit/OpenCV/boost headers (oracle/refdeps)";
+}
+}

@@ -1,6 +1,10 @@
-"""Generates tests/golden/*.npz: small frozen inputs + the CPU oracle's outputs and per-iteration
-traces.  The reference ships no golden vectors; these pin the oracle against drift
-and give the GPU tests an oracle-independent target.  Run from the repo root:
+"""Generates tests/golden/*.npz: small frozen inputs + the outputs of THE REFERENCE ITSELF run here
+(oracle/_ref: the reference's src/sparse_img_align.cpp, pose_optimizer.cpp and feature.cpp compiled
+unmodified against stand-in third-party headers — oracle/ref_harness.cpp), plus the oracle's
+per-iteration traces, which the reference class does not expose.  The reference ships no golden
+vectors of its own.  /root/reference cannot travel to the GPU box, so the vectors are
+committed; they pin the oracle restatement (bit-exact) and give the GPU tests a reference-derived
+target.  Needs /root/reference; run from the repo root:
     python tests/golden/make_golden.py
 """
 import os
@@ -24,7 +28,8 @@ def align_case():
     d = synth.make_align_batch(cam=synth.QVGA, batch=3, n_pts=64, n_segs=16, max_level=3, min_level=1, seed=9001,
                                margin=32, motion_t=0.02, motion_r=0.006)
     params = abi.align_params(3, 1, 30)
-    out = oracle_lib.align(abi, d, params)
+    out = oracle_lib.ref_align(abi, d, params)   # the reference's own translation units
+    port = oracle_lib.align(abi, d, params)      # oracle restatement: only for the roofline counters below
     traces = [oracle_lib.align_trace(abi, d, b, params) for b in range(d.batch)]
     save = {f: getattr(d, f) for f in ALIGN_FIELDS}
     for l, v in d.ref_pyr.items():
@@ -32,7 +37,8 @@ def align_case():
     for l, v in d.cur_pyr.items():
         save[f"cur_pyr_{l}"] = v
     save.update(out_T_cur_w=out.T_cur_w, out_n_tracked=out.n_tracked, out_H=out.H, out_seg_killed=out.seg_killed,
-                out_iters=out.iters, out_patch_iters=out.patch_iters, out_patch_levels=out.patch_levels)
+                out_iters=out.iters, out_status=out.status, out_patch_iters=port.patch_iters, out_patch_levels=port.patch_levels,
+                source=np.array(oracle_lib.load_ref(abi).plsvo_ref_describe().decode()))
     for b, t in enumerate(traces):
         save[f"trace_{b}"] = t
     np.savez_compressed(os.path.join(HERE, "align_qvga.npz"), **save)
@@ -42,15 +48,20 @@ def poseopt_case():
     d = synth.make_poseopt_batch(batch=6, n_pts=96, n_segs=24, seed=9002)
     save = {f: getattr(d, f) for f in PO_FIELDS}
     for tag, n_ref in (("9arg", -1), ("10arg", 3)):
-        out = oracle_lib.poseopt(abi, d, abi.poseopt_params(2.0, 10, n_ref))
+        out = oracle_lib.ref_poseopt(abi, d, abi.poseopt_params(2.0, 10, n_ref))  # the reference's own pose_optimizer.cpp
         for f in ("T_f_w", "cov", "estimated_scale", "error_init", "error_final", "num_obs_pt", "num_obs_ls", "pt_outlier",
-                  "seg_outlier", "iters"):
+                  "seg_outlier", "status"):
             save[f"out_{tag}_{f}"] = getattr(out, f)
+        # GN pass counts are not observable from outside the reference function: taken from the oracle restatement
+        save[f"out_{tag}_iters"] = oracle_lib.poseopt(abi, d, abi.poseopt_params(2.0, 10, n_ref)).iters
+    save["source"] = np.array(oracle_lib.load_ref(abi).plsvo_ref_describe().decode())
     np.savez_compressed(os.path.join(HERE, "poseopt.npz"), **save)
 
 
 if __name__ == "__main__":
     oracle_lib.build()
+    if not oracle_lib.build_ref():
+        raise SystemExit("oracle/_ref could not be built (needs /root/reference)")
     align_case()
     poseopt_case()
     print("golden fixtures written to", HERE)
