@@ -137,7 +137,7 @@ _ref_lib = None
 def build_ref(force: bool = False) -> str | None:
     """Build oracle/_ref/libplsvo_ref.so when the reference sources are present (authoring container only).
     Returns the path, or None when neither the sources nor a prebuilt library exist."""
-    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp")]
+    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp")]
     if all(os.path.exists(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "ref", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
     return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
@@ -160,6 +160,11 @@ def load_ref(abi):
     lib.plsvo_ref_poseopt_batch.restype = C.c_int
     lib.plsvo_ref_poseopt_batch.argtypes = [P(abi.PoseOptBatch), P(abi.PoseOptParams), P(abi.PoseOptResult), C.c_int]
     lib.plsvo_ref_describe.restype = C.c_char_p
+    u8p, dp = P(C.c_uint8), P(C.c_double)
+    lib.plsvo_ref_align2d.restype = C.c_int
+    lib.plsvo_ref_align2d.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, u8p, C.c_int, dp]
+    lib.plsvo_ref_align1d.restype = C.c_int
+    lib.plsvo_ref_align1d.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, P(C.c_float), u8p, u8p, C.c_int, dp, dp]
     _ref_lib = lib
     return lib
 
@@ -186,3 +191,21 @@ def ref_poseopt(abi, data, params=None, n_threads: int = 1):
     if rc != 0:
         raise RuntimeError(f"reference poseopt failed rc={rc}")
     return out
+
+
+def ref_align2d(abi, cur_pyr, image_index, level, border, ref, px, n_iter):
+    """feature_alignment::align2D of the reference's own feature_alignment.cpp, looped over features."""
+    lib = load_ref(abi)
+    u8p, dp = C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+    out = np.array(px, np.float64, copy=True)
+    conv = np.zeros(len(image_index), bool)
+    border = np.ascontiguousarray(border, np.uint8)
+    ref = np.ascontiguousarray(ref, np.uint8)
+    for i in range(len(image_index)):
+        im = np.ascontiguousarray(cur_pyr[int(level[i])][int(image_index[i])])
+        p = out[i].copy()
+        conv[i] = bool(lib.plsvo_ref_align2d(im.ctypes.data_as(u8p), im.shape[1], im.shape[0], im.strides[0],
+                                             border[i].ctypes.data_as(u8p), ref[i].ctypes.data_as(u8p), n_iter,
+                                             p.ctypes.data_as(dp)))
+        out[i] = p
+    return conv, out

@@ -5,7 +5,7 @@
 //
 // oracle/Makefile target `ref` compiles, unmodified and where they lie,
 //     /root/reference/src/sparse_img_align.cpp   /root/reference/src/pose_optimizer.cpp
-//     /root/reference/src/feature.cpp
+//     /root/reference/src/feature.cpp            /root/reference/src/feature_alignment.cpp
 // against the reference's own headers (/root/reference/include/plsvo/*.h) and the stand-in
 // third-party headers in oracle/refdeps/ (Eigen, Sophus, rpg_vikit, OpenCV core, boost — absent
 // from the image and from /root/reference), links this file, and writes oracle/_ref/libplsvo_ref.so.
@@ -21,6 +21,7 @@
 // self-contained restatement.
 
 #include <plsvo/feature.h>
+#include <plsvo/feature_alignment.h>
 #include <plsvo/feature3D.h>
 #include <plsvo/frame.h>
 #include <plsvo/pose_optimizer.h>
@@ -284,8 +285,29 @@ int plsvo_ref_poseopt_batch(const plsvo_poseopt_batch* batch, const plsvo_poseop
   return PLSVO_OK;
 }
 
+// feature_alignment::align2D / align1D (src/feature_alignment.cpp:160-290, :36-157) on one feature.
+int plsvo_ref_align2d(const uint8_t* cur_img, int cols, int rows, size_t cur_step, const uint8_t* ref_patch_with_border,
+                      const uint8_t* ref_patch, int n_iter, double* px) {
+  cv::Mat img(rows, cols, CV_8U, const_cast<uint8_t*>(cur_img), cur_step);
+  Vector2d est(px[0], px[1]);
+  const bool ok = plsvo::feature_alignment::align2D(img, const_cast<uint8_t*>(ref_patch_with_border),
+                                                    const_cast<uint8_t*>(ref_patch), n_iter, est);
+  px[0] = est[0], px[1] = est[1];
+  return ok ? 1 : 0;
+}
+int plsvo_ref_align1d(const uint8_t* cur_img, int cols, int rows, size_t cur_step, const float* dir,
+                      const uint8_t* ref_patch_with_border, const uint8_t* ref_patch, int n_iter, double* px, double* h_inv) {
+  cv::Mat img(rows, cols, CV_8U, const_cast<uint8_t*>(cur_img), cur_step);
+  Vector2d est(px[0], px[1]);
+  Eigen::Vector2f d(dir[0], dir[1]);
+  const bool ok = plsvo::feature_alignment::align1D(img, d, const_cast<uint8_t*>(ref_patch_with_border),
+                                                    const_cast<uint8_t*>(ref_patch), n_iter, est, *h_inv);
+  px[0] = est[0], px[1] = est[1];
+  return ok ? 1 : 0;
+}
+
 const char* plsvo_ref_describe(void) {
-  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature}.cpp compiled unmodified against stand-in "
+  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment}.cpp compiled unmodified against stand-in "
          "Eigen/Sophus/vikit/OpenCV/boost headers (oracle/refdeps)";
 }
 }

@@ -48,3 +48,16 @@ def test_gpu_align2d_is_bit_identical_to_the_oracle(pkg, oracle, abi, synth, gen
     finite = np.isfinite(px_ref).all(axis=1)
     np.testing.assert_array_equal(px[finite], px_ref[finite])
     assert (np.isnan(px[~finite]) == np.isnan(px_ref[~finite])).all()
+
+
+def test_oracle_align2d_is_bit_identical_to_the_reference_tu(oracle, abi, synth):
+    """oracle/_ref compiles the reference's own src/feature_alignment.cpp in place (oracle/ref_harness.cpp);
+    the restatement must reproduce align2D's converged flags and refined positions bit for bit."""
+    if not oracle.build_ref():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    for seed, n_iter in ((9, 10), (10, 3), (11, 30)):
+        cam, pyr, idx, lvl, border, ref, px0, truth = _case(synth, n=600, seed=seed)
+        conv_o, px_o = oracle.align2d(abi, pyr, idx, lvl, border, ref, px0, n_iter)
+        conv_r, px_r = oracle.ref_align2d(abi, pyr, idx, lvl, border, ref, px0, n_iter)
+        np.testing.assert_array_equal(conv_o, conv_r)
+        np.testing.assert_array_equal(px_o, px_r)  # NaN == NaN under assert_array_equal
