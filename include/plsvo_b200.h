@@ -251,6 +251,32 @@ typedef struct plsvo_align2d_result {
 
 int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch* in, const plsvo_align2d_result* out);
 
+/* ---- feature_alignment::align1D ("next") --------------------------------
+ * Replaces, for n features at once, include/plsvo/feature_alignment.h:39-46 /
+ * src/feature_alignment.cpp:40-157:
+ *     bool align1D(const cv::Mat& cur_img, const Vector2f& dir, uint8_t* ref_patch_with_border,
+ *                  uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate, double& h_inv);
+ * the 1-DoF variant Matcher::findMatchDirect / findEpipolarMatchDirect use for edgelets
+ * (src/matcher.cpp:195,331,400,497): the patch may only move along `dir`.  Same feature arrays as
+ * plsvo_align2d_batch plus one direction per feature. */
+typedef struct plsvo_align1d_batch {
+  plsvo_align2d_batch features; /* images, image_index, level, patches, px — as for align2D */
+  const float* dir;             /* [n][2] direction in which the patch is allowed to move */
+} plsvo_align1d_batch;
+
+typedef struct plsvo_align1d_result {
+  double* px;         /* [n][2] cur_px_estimate on return */
+  uint8_t* converged; /* [n]    return value of align1D */
+  double* h_inv;      /* [n]    h_inv on return (:75) */
+} plsvo_align1d_result;
+
+int plsvo_align1d_batch_run(plsvo_ctx* ctx, const plsvo_align1d_batch* in, const plsvo_align1d_result* out);
+
+/* device time (CUDA events on the context's stream) of the kernel launched by the last
+ * plsvo_pyramid_batch_run / plsvo_align2d_batch_run / plsvo_align1d_batch_run call: the kernel alone,
+ * without the host<->device copies those calls also make.  Measurement aid, no reference counterpart. */
+int plsvo_last_kernel_ms(plsvo_ctx* ctx, float* ms);
+
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 int64_t plsvo_launch_count(const plsvo_ctx* ctx);
 

@@ -52,6 +52,9 @@ def load(abi):
     lib.plsvo_oracle_half_sample.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8), C.c_size_t]
     lib.plsvo_oracle_align2d.restype = C.c_int
     lib.plsvo_oracle_align2d.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_double)]
+    lib.plsvo_oracle_align1d.restype = C.c_int
+    lib.plsvo_oracle_align1d.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_uint8),
+                                         C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.plsvo_oracle_hardware_threads.restype = C.c_int
     _lib = lib
     return lib
@@ -209,3 +212,32 @@ def ref_align2d(abi, cur_pyr, image_index, level, border, ref, px, n_iter):
                                              p.ctypes.data_as(dp)))
         out[i] = p
     return conv, out
+
+
+def _align1d_loop(fn, cur_pyr, image_index, level, dirs, border, ref, px, n_iter):
+    u8p, dp, fp = C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_float)
+    out = np.array(px, np.float64, copy=True)
+    conv = np.zeros(len(image_index), bool)
+    h_inv = np.zeros(len(image_index))
+    border = np.ascontiguousarray(border, np.uint8)
+    ref = np.ascontiguousarray(ref, np.uint8)
+    dirs = np.ascontiguousarray(dirs, np.float32)
+    for i in range(len(image_index)):
+        im = np.ascontiguousarray(cur_pyr[int(level[i])][int(image_index[i])])
+        p = out[i].copy()
+        h = C.c_double(0)
+        conv[i] = bool(fn(im.ctypes.data_as(u8p), im.shape[1], im.shape[0], im.strides[0], dirs[i].ctypes.data_as(fp),
+                          border[i].ctypes.data_as(u8p), ref[i].ctypes.data_as(u8p), n_iter, p.ctypes.data_as(dp), C.byref(h)))
+        out[i] = p
+        h_inv[i] = h.value
+    return conv, out, h_inv
+
+
+def align1d(abi, cur_pyr, image_index, level, dirs, border, ref, px, n_iter):
+    """feature_alignment::align1D restated -> (converged [n], px [n,2], h_inv [n])."""
+    return _align1d_loop(load(abi).plsvo_oracle_align1d, cur_pyr, image_index, level, dirs, border, ref, px, n_iter)
+
+
+def ref_align1d(abi, cur_pyr, image_index, level, dirs, border, ref, px, n_iter):
+    """feature_alignment::align1D of the reference's own feature_alignment.cpp."""
+    return _align1d_loop(load_ref(abi).plsvo_ref_align1d, cur_pyr, image_index, level, dirs, border, ref, px, n_iter)

@@ -1158,5 +1158,136 @@ int plsvo_oracle_align2d(const uint8_t* cur_img, int cols, int rows, size_t cur_
   return converged ? 1 : 0;
 }
 
+// feature_alignment::align1D — src/feature_alignment.cpp:40-157.  dir = direction the patch may move in;
+// returns `converged`, writes px (in/out) and h_inv.  Matrix2f::inverse() follows Eigen's 2x2 path
+// (determinant, 1/det, adjugate * invdet).
+int plsvo_oracle_align1d(const uint8_t* cur_img, int cols, int rows, size_t cur_step_, const float* dir,
+                         const uint8_t* ref_patch_with_border, const uint8_t* ref_patch, int n_iter, double* px, double* h_inv) {
+  const int halfpatch_size_ = 4, patch_size = 8;
+  bool converged = false;
+  float ref_patch_dv[64];
+  float H[2][2] = {{0, 0}, {0, 0}};
+  const int ref_step = patch_size + 2;
+  float* it_dv = ref_patch_dv;
+  for (int y = 0; y < patch_size; ++y) {
+    const uint8_t* it = ref_patch_with_border + (y + 1) * ref_step + 1;
+    for (int x = 0; x < patch_size; ++x, ++it, ++it_dv) {
+      float J[2];
+      J[0] = 0.5 * (dir[0] * (it[1] - it[-1]) + dir[1] * (it[ref_step] - it[-ref_step]));
+      J[1] = 1;
+      *it_dv = J[0];
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c) H[r][c] += J[r] * J[c];
+    }
+  }
+  *h_inv = 1.0 / H[0][0] * patch_size * patch_size;
+  float Hinv[2][2];
+  {
+    const float det = H[0][0] * H[1][1] - H[1][0] * H[0][1];
+    const float invdet = 1.0f / det;
+    Hinv[0][0] = H[1][1] * invdet;
+    Hinv[1][0] = -H[1][0] * invdet;
+    Hinv[0][1] = -H[0][1] * invdet;
+    Hinv[1][1] = H[0][0] * invdet;
+  }
+  float mean_diff = 0;
+  float u = (float)px[0];
+  float v = (float)px[1];
+  const float min_update_squared = 0.03 * 0.03;
+  const int cur_step = (int)cur_step_;
+  float chi2 = 0;
+  float update[2] = {0, 0};
+  for (int iter = 0; iter < n_iter; ++iter) {
+    // int u_r = floor(u): out-of-range / NaN conversions give INT_MIN on x86 and fail the bounds test,
+    // so the isnan() early return at :94-95 is never reached.
+    const double fu = std::floor((double)u), fv = std::floor((double)v);
+    const int u_r = (fu >= -2147483648.0 && fu < 2147483648.0) ? (int)fu : INT32_MIN;
+    const int v_r = (fv >= -2147483648.0 && fv < 2147483648.0) ? (int)fv : INT32_MIN;
+    if (u_r < halfpatch_size_ || v_r < halfpatch_size_ || u_r >= cols - halfpatch_size_ || v_r >= rows - halfpatch_size_) break;
+    const float subpix_x = u - u_r;
+    const float subpix_y = v - v_r;
+    const float wTL = (float)((1.0 - subpix_x) * (1.0 - subpix_y));
+    const float wTR = (float)(subpix_x * (1.0 - subpix_y));
+    const float wBL = (float)((1.0 - subpix_x) * subpix_y);
+    const float wBR = subpix_x * subpix_y;
+    const uint8_t* it_ref = ref_patch;
+    const float* it_ref_dv = ref_patch_dv;
+    float new_chi2 = 0.0;
+    float Jres[2] = {0, 0};
+    for (int y = 0; y < patch_size; ++y) {
+      const uint8_t* it = cur_img + (ptrdiff_t)(v_r + y - halfpatch_size_) * cur_step + u_r - halfpatch_size_;
+      for (int x = 0; x < patch_size; ++x, ++it, ++it_ref, ++it_ref_dv) {
+        const float search_pixel = wTL * it[0] + wTR * it[1] + wBL * it[cur_step] + wBR * it[cur_step + 1];
+        const float res = search_pixel - *it_ref + mean_diff;
+        Jres[0] -= res * (*it_ref_dv);
+        Jres[1] -= res;
+        new_chi2 += res * res;
+      }
+    }
+    if (iter > 0 && new_chi2 > chi2) {
+      u -= update[0];
+      v -= update[1];
+      break;
+    }
+    chi2 = new_chi2;
+    const float up0 = Hinv[0][0] * Jres[0] + Hinv[0][1] * Jres[1];
+    const float up1 = Hinv[1][0] * Jres[0] + Hinv[1][1] * Jres[1];
+    update[0] = up0, update[1] = up1;
+    u += update[0] * dir[0];
+    v += update[0] * dir[1];
+    mean_diff += update[1];
+    if (update[0] * update[0] + update[1] * update[1] < min_update_squared) {
+      converged = true;
+      break;
+    }
+  }
+  px[0] = u, px[1] = v;
+  return converged ? 1 : 0;
+}
+
+// Batch drivers over the ABI structs (CPU baseline of tools/bench_next.py): one call per feature, threads over features.
+int plsvo_oracle_align2d_batch(const plsvo_align2d_batch* in, const plsvo_align2d_result* out, int n_threads) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  parallel_for(in->n_features, n_threads, [&](int i) {
+    const int l = in->level[i];
+    const uint8_t* img = in->img[l] + (size_t)in->image_index[i] * in->img_stride[l];
+    double px[2] = {in->px[2 * (size_t)i], in->px[2 * (size_t)i + 1]};
+    out->converged[i] = (uint8_t)plsvo_oracle_align2d(img, in->width >> l, in->height >> l, in->img_pitch[l],
+                                                      in->ref_patch_with_border + 100 * (size_t)i, in->ref_patch + 64 * (size_t)i,
+                                                      in->n_iter, px);
+    out->px[2 * (size_t)i] = px[0], out->px[2 * (size_t)i + 1] = px[1];
+  });
+  return PLSVO_OK;
+}
+int plsvo_oracle_align1d_batch(const plsvo_align1d_batch* in1, const plsvo_align1d_result* out, int n_threads) {
+  if (!in1 || !out) return PLSVO_ERR_INVALID;
+  const plsvo_align2d_batch* in = &in1->features;
+  parallel_for(in->n_features, n_threads, [&](int i) {
+    const int l = in->level[i];
+    const uint8_t* img = in->img[l] + (size_t)in->image_index[i] * in->img_stride[l];
+    double px[2] = {in->px[2 * (size_t)i], in->px[2 * (size_t)i + 1]};
+    double h_inv = 0;
+    out->converged[i] = (uint8_t)plsvo_oracle_align1d(img, in->width >> l, in->height >> l, in->img_pitch[l], in1->dir + 2 * (size_t)i,
+                                                      in->ref_patch_with_border + 100 * (size_t)i, in->ref_patch + 64 * (size_t)i,
+                                                      in->n_iter, px, &h_inv);
+    out->px[2 * (size_t)i] = px[0], out->px[2 * (size_t)i + 1] = px[1];
+    if (out->h_inv) out->h_inv[i] = h_inv;
+  });
+  return PLSVO_OK;
+}
+int plsvo_oracle_pyramid_batch(const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out, int n_threads) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  parallel_for(in->batch, n_threads, [&](int b) {
+    const uint8_t* prev = in->img0 + (size_t)b * in->stride0;
+    size_t prev_pitch = in->pitch0;
+    for (int l = 1; l < in->n_levels; ++l) {
+      uint8_t* dst = out->level[l] + (size_t)b * out->stride[l];
+      plsvo_oracle_half_sample(prev, in->width >> (l - 1), in->height >> (l - 1), prev_pitch, dst, out->pitch[l]);
+      prev = dst, prev_pitch = out->pitch[l];
+    }
+  });
+  return PLSVO_OK;
+}
+
 int plsvo_oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 }

@@ -154,6 +154,14 @@ class Align2DResult(C.Structure):
     _fields_ = [("px", _f64p), ("converged", _u8p)]
 
 
+class Align1DBatch(C.Structure):
+    _fields_ = [("features", Align2DBatch), ("dir", C.POINTER(C.c_float))]
+
+
+class Align1DResult(C.Structure):
+    _fields_ = [("px", _f64p), ("converged", _u8p), ("h_inv", _f64p)]
+
+
 # ------------------------------------------------------------------------------------------------
 # numpy <-> struct helpers
 # ------------------------------------------------------------------------------------------------
@@ -318,6 +326,8 @@ ABI_SYMBOLS = [
     ("plsvo_poseopt_batch_run", C.c_int, [C.c_void_p, _P(PoseOptBatch), _P(PoseOptParams), _P(PoseOptResult)]),
     ("plsvo_pyramid_batch_run", C.c_int, [C.c_void_p, _P(PyramidBatch), _P(PyramidResult)]),
     ("plsvo_align2d_batch_run", C.c_int, [C.c_void_p, _P(Align2DBatch), _P(Align2DResult)]),
+    ("plsvo_align1d_batch_run", C.c_int, [C.c_void_p, _P(Align1DBatch), _P(Align1DResult)]),
+    ("plsvo_last_kernel_ms", C.c_int, [C.c_void_p, _P(C.c_float)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
     ("plsvo_selftest_weight", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
     ("plsvo_version", C.c_char_p, []),

@@ -47,6 +47,12 @@ class Context:
     def sync(self):
         self.check(self.lib.plsvo_sync(self.handle), "plsvo_sync")
 
+    def last_kernel_ms(self) -> float:
+        """Device time of the kernel of the last pyramid / align2D / align1D call (plsvo_last_kernel_ms)."""
+        ms = C.c_float(0)
+        self.check(self.lib.plsvo_last_kernel_ms(self.handle, C.byref(ms)), "plsvo_last_kernel_ms")
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(self.lib.plsvo_launch_count(self.handle))
 
@@ -180,3 +186,26 @@ class feature_alignment:
         r = abi.Align2DResult(out_px.ctypes.data_as(C.POINTER(C.c_double)), conv.ctypes.data_as(C.POINTER(C.c_uint8)))
         ctx.check(ctx.lib.plsvo_align2d_batch_run(ctx.handle, C.byref(b), C.byref(r)), "plsvo_align2d_batch_run")
         return conv.astype(bool), out_px
+
+    @staticmethod
+    def align1D(cur_pyr, image_index, level, dir, ref_patch_with_border, ref_patch, n_iter, cur_px_estimate,
+                width: int, height: int, ctx: Context | None = None):
+        """Batched align1D (src/feature_alignment.cpp:40-157): returns (converged [n] bool, px [n,2], h_inv [n])."""
+        import numpy as np
+
+        ctx = ctx or default_context()
+        image_index = np.ascontiguousarray(image_index, np.int32)
+        level = np.ascontiguousarray(level, np.int32)
+        border = np.ascontiguousarray(ref_patch_with_border, np.uint8)
+        ref = np.ascontiguousarray(ref_patch, np.uint8)
+        px = np.ascontiguousarray(cur_px_estimate, np.float64)
+        d = np.ascontiguousarray(dir, np.float32)
+        feats, keep = abi.make_align2d_batch(cur_pyr, image_index, level, border, ref, px, n_iter, width, height)
+        b = abi.Align1DBatch(feats, d.ctypes.data_as(C.POINTER(C.c_float)))
+        out_px = np.zeros_like(px)
+        conv = np.zeros(len(image_index), np.uint8)
+        h_inv = np.zeros(len(image_index), np.float64)
+        r = abi.Align1DResult(out_px.ctypes.data_as(C.POINTER(C.c_double)), conv.ctypes.data_as(C.POINTER(C.c_uint8)),
+                              h_inv.ctypes.data_as(C.POINTER(C.c_double)))
+        ctx.check(ctx.lib.plsvo_align1d_batch_run(ctx.handle, C.byref(b), C.byref(r)), "plsvo_align1d_batch_run")
+        return conv.astype(bool), out_px, h_inv

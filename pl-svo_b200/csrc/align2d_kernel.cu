@@ -128,7 +128,116 @@ __global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a
   a.out_converged[i] = converged ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// feature_alignment::align1D (src/feature_alignment.cpp:40-157): the patch moves along `dir` only
+// (edgelets), 1 DoF + mean intensity offset, with the reference's chi2 back-off.  Same layout and
+// the same bit-exact fp32 sequencing as align2d_kernel.
+__global__ void __launch_bounds__(kA2Threads) align1d_kernel(const Align2DArgs a) {
+  __shared__ uint8_t s_border[kA2Threads][104];
+  __shared__ uint8_t s_ref[kA2Threads][64];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kA2Threads + tid;
+  if (i >= a.n) return;
+  {
+    const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.ref_patch_with_border + (size_t)i * 100);
+    const uint32_t* gr = reinterpret_cast<const uint32_t*>(a.ref_patch + (size_t)i * 64);
+    uint32_t* sb = reinterpret_cast<uint32_t*>(s_border[tid]);
+    uint32_t* sr = reinterpret_cast<uint32_t*>(s_ref[tid]);
+#pragma unroll
+    for (int k = 0; k < 25; ++k) sb[k] = gb[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sr[k] = gr[k];
+  }
+  const uint8_t* border = s_border[tid];
+  const uint8_t* ref = s_ref[tid];
+  const int level = a.level[i];
+  const int cols = a.width >> level, rows = a.height >> level;
+  const int cur_step = (int)a.pitch[level];
+  const uint8_t* img = a.img[level] + (size_t)a.image_index[i] * a.stride[level];
+  const float d0 = a.dir[2 * (size_t)i], d1 = a.dir[2 * (size_t)i + 1];
+
+  // directional template derivative (:63-66): J0 = 0.5*(dir0*(I[x+1]-I[x-1]) + dir1*(I[y+1]-I[y-1])) in float, J1 = 1
+  auto dv_at = [&](const uint8_t* it) {
+    const float gx = __fmul_rn(d0, (float)((int)it[1] - (int)it[-1]));
+    const float gy = __fmul_rn(d1, (float)((int)it[10] - (int)it[-10]));
+    return (float)(0.5 * (double)__fadd_rn(gx, gy));
+  };
+  float H00 = 0, H01 = 0, H11 = 0;
+  for (int y = 0; y < 8; ++y) {
+    const uint8_t* it = border + (y + 1) * 10 + 1;
+    for (int x = 0; x < 8; ++x, ++it) {
+      const float J0 = dv_at(it);
+      H00 = __fadd_rn(H00, __fmul_rn(J0, J0));
+      H01 = __fadd_rn(H01, J0);
+      H11 = __fadd_rn(H11, 1.0f);
+    }
+  }
+  a.out_h_inv[i] = 1.0 / (double)H00 * 8 * 8;  // :75
+  // Matrix2f::inverse(): 1/det, (d, -c; -b, a) * invdet
+  const float det = __fsub_rn(__fmul_rn(H00, H11), __fmul_rn(H01, H01));
+  const float invdet = __fdiv_rn(1.0f, det);
+  const float I00 = __fmul_rn(H11, invdet), I10 = __fmul_rn(-H01, invdet);
+  const float I01 = __fmul_rn(-H01, invdet), I11 = __fmul_rn(H00, invdet);
+
+  float mean_diff = 0.f;
+  float u = (float)a.px[2 * (size_t)i], v = (float)a.px[2 * (size_t)i + 1];
+  const float min_update_squared = (float)(0.03 * 0.03);
+  float chi2 = 0.f, up0 = 0.f, up1 = 0.f;
+  bool converged = false;
+  for (int iter = 0; iter < a.n_iter; ++iter) {
+    const float fu = floorf(u), fv = floorf(v);
+    const int ui = (int)fu, vi = (int)fv;
+    if (ui < 4 || vi < 4 || ui >= cols - 4 || vi >= rows - 4) break;  // NaN never passes this test (:87-92)
+    const float su = __fsub_rn(u, fu), sv = __fsub_rn(v, fv);
+    const float wTL = (float)((1.0 - (double)su) * (1.0 - (double)sv));
+    const float wTR = (float)((double)su * (1.0 - (double)sv));
+    const float wBL = (float)((1.0 - (double)su) * (double)sv);
+    const float wBR = __fmul_rn(su, sv);
+    float J0 = 0.f, J1 = 0.f, new_chi2 = 0.f;
+    const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
+    const uint8_t* it_ref = ref;
+    for (int y = 0; y < 8; ++y, row += cur_step) {
+      const uint8_t* itb = border + (y + 1) * 10 + 1;
+#pragma unroll
+      for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
+        const float search_pixel =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, (float)row[x]), __fmul_rn(wTR, (float)row[x + 1])),
+                                __fmul_rn(wBL, (float)row[x + cur_step])),
+                      __fmul_rn(wBR, (float)row[x + cur_step + 1]));
+        const float res = __fadd_rn(__fsub_rn(search_pixel, (float)*it_ref), mean_diff);
+        J0 = __fsub_rn(J0, __fmul_rn(res, dv_at(itb)));
+        J1 = __fsub_rn(J1, res);
+        new_chi2 = __fadd_rn(new_chi2, __fmul_rn(res, res));
+      }
+    }
+    if (iter > 0 && new_chi2 > chi2) {  // :124-132 (the back-off subtracts the raw update, as the reference does)
+      u = __fsub_rn(u, up0);
+      v = __fsub_rn(v, up1);
+      break;
+    }
+    chi2 = new_chi2;
+    up0 = __fadd_rn(__fmul_rn(I00, J0), __fmul_rn(I01, J1));
+    up1 = __fadd_rn(__fmul_rn(I10, J0), __fmul_rn(I11, J1));
+    u = __fadd_rn(u, __fmul_rn(up0, d0));
+    v = __fadd_rn(v, __fmul_rn(up0, d1));
+    mean_diff = __fadd_rn(mean_diff, up1);
+    if (__fadd_rn(__fmul_rn(up0, up0), __fmul_rn(up1, up1)) < min_update_squared) {
+      converged = true;
+      break;
+    }
+  }
+  a.out_px[2 * (size_t)i] = (double)u;
+  a.out_px[2 * (size_t)i + 1] = (double)v;
+  a.out_converged[i] = converged ? 1 : 0;
+}
+
 }  // namespace
+
+cudaError_t align1d_kernel_launch(const Align2DArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  align1d_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t align2d_kernel_launch(const Align2DArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;

@@ -130,7 +130,10 @@ struct Align2DArgs {
   const double* px;                      // [n][2]
   double* out_px;
   uint8_t* out_converged;
+  const float* dir;   // align1D only: [n][2]
+  double* out_h_inv;  // align1D only: [n]
 };
 cudaError_t align2d_kernel_launch(const Align2DArgs& a, cudaStream_t s);
+cudaError_t align1d_kernel_launch(const Align2DArgs& a, cudaStream_t s);
 
 }  // namespace plsvo

@@ -30,6 +30,7 @@ struct plsvo_ctx_impl {
   cudaStream_t copy_stream = nullptr;  // second stream of the chunked host-buffer pipeline
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t start_ev = nullptr;
+  cudaEvent_t k_ev[2] = {nullptr, nullptr};  // around the kernel of the last pyramid / align2D / align1D call
   unsigned int* h_flags = nullptr;  // pinned arrival values of the gated pipeline
   char* h_out = nullptr;            // pinned staging of the alignment outputs (one D2H per download)
   size_t h_out_cap = 0, out_bytes = 0;
@@ -58,7 +59,7 @@ struct plsvo_ctx_impl {
   DevBuf p_T, p_pt_count, p_pt_f, p_pt_pos, p_pt_level, p_pt_valid, p_seg_count, p_seg_line, p_seg_spos, p_seg_epos,
       p_seg_level, p_seg_valid;
   DevBuf y_img;  // pyramid levels
-  DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv;  // align2D
+  DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv, f_dir, f_ohinv;  // align2D / align1D
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
 };
@@ -83,6 +84,15 @@ int fail(plsvo_ctx_impl* c, int code, const char* what, cudaError_t e = cudaSucc
     cudaError_t e_ = (call);                                            \
     if (e_ != cudaSuccess) return fail(c, PLSVO_ERR_CUDA, #call, e_);   \
   } while (0)
+
+// Records one of the two timing events around the kernel of a host-in/host-out entry point.
+cudaError_t kernel_timer(plsvo_ctx_impl* c, int which, cudaStream_t s) {
+  if (!c->k_ev[which]) {
+    cudaError_t e = cudaEventCreate(&c->k_ev[which]);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaEventRecord(c->k_ev[which], s);
+}
 
 cudaError_t ensure(DevBuf& b, size_t bytes) {
   if (bytes <= b.cap && b.p) return cudaSuccess;
@@ -174,7 +184,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
                     &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
-                    &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->p_T,
+                    &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -186,6 +196,8 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
     cudaStreamDestroy(c->copy_stream);
     for (int k = 0; k < 8; ++k) cudaEventDestroy(c->chunk_ev[k]);
     cudaEventDestroy(c->start_ev);
+    for (auto& e : c->k_ev)
+      if (e) cudaEventDestroy(e);
   }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -218,6 +230,15 @@ int plsvo_host_alloc(void** ptr, size_t bytes) {
 int plsvo_host_free(void* ptr) {
   if (!ptr) return PLSVO_OK;
   return cudaFreeHost(ptr) == cudaSuccess ? PLSVO_OK : PLSVO_ERR_CUDA;
+}
+
+int plsvo_last_kernel_ms(plsvo_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (!c->k_ev[0] || !c->k_ev[1]) return fail(c, PLSVO_ERR_STATE, "no timed kernel has run on this context");
+  CK(cudaEventSynchronize(c->k_ev[1]));
+  CK(cudaEventElapsedTime(ms, c->k_ev[0], c->k_ev[1]));
+  return PLSVO_OK;
 }
 
 int64_t plsvo_launch_count(const plsvo_ctx* ctx) {
@@ -839,7 +860,9 @@ extern "C" int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch
       CK(cudaMemcpy2DAsync(a.level[0] + b * a.stride[0], a.pitch[0], in->img0 + b * in->stride0, in->pitch0, in->width,
                            in->height, cudaMemcpyHostToDevice, s));
   }
+  CK(kernel_timer(c, 0, s));
   CK(pyramid_kernel_launch(a, s));
+  CK(kernel_timer(c, 1, s));
   c->launches += 1;
   for (int l = 1; l < in->n_levels; ++l) {
     const int cols = in->width >> l, rows = in->height >> l;
@@ -856,13 +879,14 @@ extern "C" int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch
   return PLSVO_OK;
 }
 
-extern "C" int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch* in, const plsvo_align2d_result* out) {
-  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
-  plsvo_ctx_impl* c = CTX(ctx);
+namespace {
+// align2D (dir == nullptr) and align1D (dir != nullptr) share staging and launch.
+int feature_align_run(plsvo_ctx_impl* c, const plsvo_align2d_batch* in, const float* dir, double* o_px, uint8_t* o_conv,
+                      double* o_hinv) {
   if (in->n_features < 0 || in->n_images <= 0 || in->width <= 0 || in->height <= 0 || in->n_iter < 0)
     return fail(c, PLSVO_ERR_INVALID, "align2d batch description");
   if (in->n_features == 0) return PLSVO_OK;
-  if (!in->image_index || !in->level || !in->ref_patch_with_border || !in->ref_patch || !in->px || !out->px || !out->converged)
+  if (!in->image_index || !in->level || !in->ref_patch_with_border || !in->ref_patch || !in->px || !o_px || !o_conv)
     return fail(c, PLSVO_ERR_INVALID, "align2d arrays missing");
   const size_t n = (size_t)in->n_features, B = (size_t)in->n_images;
   for (size_t i = 0; i < n; ++i) {
@@ -909,10 +933,30 @@ extern "C" int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch
   CK(ensure(c->f_oconv, n));
   a.out_px = static_cast<double*>(c->f_opx.p);
   a.out_converged = static_cast<uint8_t*>(c->f_oconv.p);
-  CK(align2d_kernel_launch(a, s));
+  if (dir) {
+    CK(up(c->f_dir, dir, n * 2, s, &a.dir));
+    CK(ensure(c->f_ohinv, n * sizeof(double)));
+    a.out_h_inv = static_cast<double*>(c->f_ohinv.p);
+  }
+  CK(kernel_timer(c, 0, s));
+  CK(dir ? align1d_kernel_launch(a, s) : align2d_kernel_launch(a, s));
+  CK(kernel_timer(c, 1, s));
   c->launches += 1;
-  CK(cudaMemcpyAsync(out->px, a.out_px, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(out->converged, a.out_converged, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(o_px, a.out_px, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(o_conv, a.out_converged, n, cudaMemcpyDeviceToHost, s));
+  if (dir && o_hinv) CK(cudaMemcpyAsync(o_hinv, a.out_h_inv, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
+}
+}  // namespace
+
+extern "C" int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch* in, const plsvo_align2d_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  return feature_align_run(CTX(ctx), in, nullptr, out->px, out->converged, nullptr);
+}
+
+extern "C" int plsvo_align1d_batch_run(plsvo_ctx* ctx, const plsvo_align1d_batch* in, const plsvo_align1d_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  if (in->features.n_features > 0 && !in->dir) return fail(CTX(ctx), PLSVO_ERR_INVALID, "align1d directions missing");
+  return feature_align_run(CTX(ctx), &in->features, in->dir, out->px, out->converged, out->h_inv);
 }

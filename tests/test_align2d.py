@@ -61,3 +61,39 @@ def test_oracle_align2d_is_bit_identical_to_the_reference_tu(oracle, abi, synth)
         conv_r, px_r = oracle.ref_align2d(abi, pyr, idx, lvl, border, ref, px0, n_iter)
         np.testing.assert_array_equal(conv_o, conv_r)
         np.testing.assert_array_equal(px_o, px_r)  # NaN == NaN under assert_array_equal
+
+
+# ---- align1D (src/feature_alignment.cpp:40-157): 1 DoF along a direction -----------------------------
+def _dirs(n, seed):
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    d = np.stack([np.cos(ang), np.sin(ang)], -1).astype(np.float32)
+    d[:3] = [[1, 0], [0, 1], [0.6, 0.8]]
+    return d
+
+
+def test_oracle_align1d_is_bit_identical_to_the_reference_tu(oracle, abi, synth):
+    if not oracle.build_ref():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    for seed, n_iter in ((19, 10), (20, 3), (21, 30)):
+        cam, pyr, idx, lvl, border, ref, px0, truth = _case(synth, n=600, seed=seed)
+        d = _dirs(600, seed)
+        conv_o, px_o, h_o = oracle.align1d(abi, pyr, idx, lvl, d, border, ref, px0, n_iter)
+        conv_r, px_r, h_r = oracle.ref_align1d(abi, pyr, idx, lvl, d, border, ref, px0, n_iter)
+        np.testing.assert_array_equal(conv_o, conv_r)
+        np.testing.assert_array_equal(px_o, px_r)
+        np.testing.assert_array_equal(h_o, h_r)
+        assert conv_o[5:].mean() > 0.3  # 1-DoF search converges when the offset has a component along dir
+
+
+@pytest.mark.gpu
+def test_gpu_align1d_is_bit_identical_to_the_oracle(pkg, oracle, abi, synth, gen_device):
+    cam, pyr, idx, lvl, border, ref, px0, truth = _case(synth, n=2000, seed=22, device=gen_device)
+    d = _dirs(2000, 22)
+    conv_ref, px_ref, h_ref = oracle.align1d(abi, pyr, idx, lvl, d, border, ref, px0, 10)
+    conv, px, h = pkg.feature_alignment.align1D(pyr, idx, lvl, d, border, ref, 10, px0, cam.width, cam.height)
+    np.testing.assert_array_equal(conv, conv_ref)
+    np.testing.assert_array_equal(h, h_ref)
+    finite = np.isfinite(px_ref).all(axis=1)
+    np.testing.assert_array_equal(px[finite], px_ref[finite])
+    assert (np.isnan(px[~finite]) == np.isnan(px_ref[~finite])).all()
