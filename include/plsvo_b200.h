@@ -272,6 +272,53 @@ typedef struct plsvo_align1d_result {
 
 int plsvo_align1d_batch_run(plsvo_ctx* ctx, const plsvo_align1d_batch* in, const plsvo_align1d_result* out);
 
+/* ---- Matcher::findMatchDirect ("next") ----------------------------------
+ * Replaces, for n (3D feature, current frame) candidates at once, include/plsvo/matcher.h:104-107 /
+ * src/matcher.cpp:159-211:
+ *     bool Matcher::findMatchDirect(const Point& pt, const Frame& cur_frame, Vector2d& px_cur);
+ * i.e. everything after pt.getCloseViewObs() has picked the reference observation ref_ftr_ (list
+ * logic, stays on the host): the in-frame test of the reference patch (:169-171), the affine warp
+ * matrix (warp::getWarpMatrixAffine, :42-71), the search level (warp::getBestSearchLevel, :73-87), the
+ * warped 10x10 reference patch (warp::warpAffine, :89-133, bilinear vk::interpolateMat_8u), the 8x8
+ * patch cut out of it (:148-157) and the align2D / align1D refinement at the search level (:189-208).
+ * The line-segment overload (:241-275) is the same computation on the two end points
+ * (precomputeRefPatch, :213-232, + align2D): pass each end point as one feature and AND the flags.
+ * Both frames use the same undistorted pinhole camera (app/run_pipeline.cpp:786-795). */
+typedef struct plsvo_match_batch {
+  int32_t n_features;
+  int32_t n_ref_images;   /* keyframes holding the reference observations */
+  int32_t n_cur_images;   /* current frames */
+  int32_t n_pyr_levels;   /* Config::nPyrLevels(): the search level is < n_pyr_levels (:180) */
+  int32_t n_iter;         /* Matcher::Options::align_max_iter (10, matcher.h:85) */
+  int32_t reserved;
+  plsvo_camera cam;
+  const uint8_t* ref_img[PLSVO_MAX_LEVELS]; /* ref_ftr_->frame->img_pyr_[l]: frame r at ref_img[l] + r*ref_stride[l] */
+  size_t ref_pitch[PLSVO_MAX_LEVELS];
+  size_t ref_stride[PLSVO_MAX_LEVELS];
+  const uint8_t* cur_img[PLSVO_MAX_LEVELS]; /* cur_frame.img_pyr_[l] */
+  size_t cur_pitch[PLSVO_MAX_LEVELS];
+  size_t cur_stride[PLSVO_MAX_LEVELS];
+  const double* T_ref_w;      /* [n_ref_images][7] ref_ftr_->frame->T_f_w_ */
+  const double* T_cur_w;      /* [n_cur_images][7] cur_frame.T_f_w_ */
+  const int32_t* ref_index;   /* [n] keyframe of the reference observation */
+  const int32_t* cur_index;   /* [n] current frame */
+  const double* ref_px;       /* [n][2] ref_ftr_->px (level-0 pixels) */
+  const double* ref_f;        /* [n][3] ref_ftr_->f */
+  const int32_t* ref_level;   /* [n]    ref_ftr_->level */
+  const uint8_t* is_edgelet;  /* [n] or NULL: PointFeat::type == EDGELET -> align1D along A_cur_ref*grad */
+  const double* ref_grad;     /* [n][2] or NULL: PointFeat::grad */
+  const double* pos;          /* [n][3] pt.pos_ (world) */
+  const double* px_cur;       /* [n][2] px_cur on entry: the projection estimate (level-0 pixels) */
+} plsvo_match_batch;
+
+typedef struct plsvo_match_result {
+  double* px_cur;        /* [n][2] px_cur on return (untouched where the in-frame test fails) */
+  uint8_t* success;      /* [n]    return value of findMatchDirect */
+  int32_t* search_level; /* [n]    Matcher::search_level_ (-1 where the in-frame test fails) */
+} plsvo_match_result;
+
+int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out);
+
 /* device time (CUDA events on the context's stream) of the kernel launched by the last
  * plsvo_pyramid_batch_run / plsvo_align2d_batch_run / plsvo_align1d_batch_run call: the kernel alone,
  * without the host<->device copies those calls also make.  Measurement aid, no reference counterpart. */

@@ -140,7 +140,7 @@ _ref_lib = None
 def build_ref(force: bool = False) -> str | None:
     """Build oracle/_ref/libplsvo_ref.so when the reference sources are present (authoring container only).
     Returns the path, or None when neither the sources nor a prebuilt library exist."""
-    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp")]
+    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp")]
     if all(os.path.exists(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "ref", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
     return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
@@ -241,3 +241,29 @@ def align1d(abi, cur_pyr, image_index, level, dirs, border, ref, px, n_iter):
 def ref_align1d(abi, cur_pyr, image_index, level, dirs, border, ref, px, n_iter):
     """feature_alignment::align1D of the reference's own feature_alignment.cpp."""
     return _align1d_loop(load_ref(abi).plsvo_ref_align1d, cur_pyr, image_index, level, dirs, border, ref, px, n_iter)
+
+
+def match_direct(abi, data, n_threads: int = 1):
+    """Matcher::findMatchDirect restated, over a synth.MatchData batch -> abi.MatchOut."""
+    lib = load(abi)
+    lib.plsvo_oracle_match_direct_batch.restype = C.c_int
+    lib.plsvo_oracle_match_direct_batch.argtypes = [C.POINTER(abi.MatchBatch), C.POINTER(abi.MatchResult), C.c_int]
+    b, keep = abi.make_match_batch(data)
+    out = abi.MatchOut(data.n)
+    rc = lib.plsvo_oracle_match_direct_batch(C.byref(b), C.byref(out.struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle match_direct failed rc={rc}")
+    return out
+
+
+def ref_match_direct(abi, data):
+    """Matcher::findMatchDirect of the reference's own matcher.cpp -> abi.MatchOut."""
+    lib = load_ref(abi)
+    lib.plsvo_ref_match_direct_batch.restype = C.c_int
+    lib.plsvo_ref_match_direct_batch.argtypes = [C.POINTER(abi.MatchBatch), C.POINTER(abi.MatchResult)]
+    b, keep = abi.make_match_batch(data)
+    out = abi.MatchOut(data.n)
+    rc = lib.plsvo_ref_match_direct_batch(C.byref(b), C.byref(out.struct))
+    if rc != 0:
+        raise RuntimeError(f"reference match_direct failed rc={rc}")
+    return out

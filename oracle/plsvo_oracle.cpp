@@ -1245,6 +1245,142 @@ int plsvo_oracle_align1d(const uint8_t* cur_img, int cols, int rows, size_t cur_
   return converged ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Matcher::findMatchDirect(const Point&, const Frame&, Vector2d&) — src/matcher.cpp:159-211, with
+// warp::getWarpMatrixAffine (:42-71), getBestSearchLevel (:73-87), warpAffine (:89-133),
+// createPatchFromPatchWithBorder (:148-157) and vk::interpolateMat_8u (rpg_vikit vision.h).
+// ------------------------------------------------------------------------------------------------
+static Vec3 pinhole_cam2world(const plsvo_camera& c, double u, double v) {  // PinholeCamera::cam2world, undistorted
+  const Vec3 xyz{(u - c.cx) / c.fx, (v - c.cy) / c.fy, 1.0};
+  const double n = std::sqrt((xyz.x * xyz.x + xyz.y * xyz.y) + xyz.z * xyz.z);
+  return {xyz.x / n, xyz.y / n, xyz.z / n};
+}
+static void pinhole_world2cam(const plsvo_camera& c, Vec3 p, double px[2]) {  // world2cam(project2d(xyz))
+  const double u = p.x / p.z, v = p.y / p.z;
+  px[0] = c.fx * u + c.cx;
+  px[1] = c.fy * v + c.cy;
+}
+static float interpolate_mat_8u(const uint8_t* data, int stride, float u, float v) {
+  const int x = (int)std::floor(u);
+  const int y = (int)std::floor(v);
+  const float subpix_x = u - x;
+  const float subpix_y = v - y;
+  const float w00 = (1.0f - subpix_x) * (1.0f - subpix_y);
+  const float w01 = (1.0f - subpix_x) * subpix_y;
+  const float w10 = subpix_x * (1.0f - subpix_y);
+  const float w11 = 1.0f - w00 - w01 - w10;
+  const uint8_t* ptr = data + (ptrdiff_t)y * stride + x;
+  return w00 * ptr[0] + w01 * ptr[stride] + w10 * ptr[1] + w11 * ptr[stride + 1];
+}
+
+static void match_direct_one(const plsvo_match_batch* in, const plsvo_match_result* out, int i) {
+  const plsvo_camera& cam = in->cam;
+  const int halfpatch_size_ = 4;
+  const size_t I = (size_t)i;
+  const double* px_ref = in->ref_px + 2 * I;
+  const int level_ref = in->ref_level[i];
+  out->px_cur[2 * I] = in->px_cur[2 * I], out->px_cur[2 * I + 1] = in->px_cur[2 * I + 1];
+  out->success[i] = 0;
+  if (out->search_level) out->search_level[i] = -1;
+  // :169-171  isInFrame(px.cast<int>()/(1<<level), halfpatch_size_+2, level)
+  {
+    const int ox = (int)px_ref[0] / (1 << level_ref), oy = (int)px_ref[1] / (1 << level_ref);
+    if (!cam_is_in_frame(cam, ox, oy, halfpatch_size_ + 2, level_ref)) return;
+  }
+  const SE3 T_ref_w = se3_from_pose7(in->T_ref_w + 7 * (size_t)in->ref_index[i]);
+  const SE3 T_cur_w = se3_from_pose7(in->T_cur_w + 7 * (size_t)in->cur_index[i]);
+  const SE3 T_w_ref = se3_inverse(T_ref_w);
+  const SE3 T_cur_ref = se3_mul(T_cur_w, T_w_ref);
+  const Vec3 pos{in->pos[3 * I], in->pos[3 * I + 1], in->pos[3 * I + 2]};
+  const Vec3 f_ref{in->ref_f[3 * I], in->ref_f[3 * I + 1], in->ref_f[3 * I + 2]};
+  const double depth_ref = norm(T_w_ref.t - pos);  // (ref_ftr_->frame->pos() - pt.pos_).norm()
+  // ---- getWarpMatrixAffine ----
+  double A[2][2];
+  {
+    const int halfpatch_size = 5;
+    const Vec3 xyz_ref = f_ref * depth_ref;
+    const double step = (double)halfpatch_size * (double)(1 << level_ref);
+    Vec3 xyz_du_ref = pinhole_cam2world(cam, px_ref[0] + step, px_ref[1] + 0.0 * (double)(1 << level_ref));
+    Vec3 xyz_dv_ref = pinhole_cam2world(cam, px_ref[0] + 0.0 * (double)(1 << level_ref), px_ref[1] + step);
+    xyz_du_ref = xyz_du_ref * (xyz_ref.z / xyz_du_ref.z);
+    xyz_dv_ref = xyz_dv_ref * (xyz_ref.z / xyz_dv_ref.z);
+    double px_cur[2], px_du[2], px_dv[2];
+    pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_ref), px_cur);
+    pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_du_ref), px_du);
+    pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_dv_ref), px_dv);
+    A[0][0] = (px_du[0] - px_cur[0]) / halfpatch_size;
+    A[1][0] = (px_du[1] - px_cur[1]) / halfpatch_size;
+    A[0][1] = (px_dv[0] - px_cur[0]) / halfpatch_size;
+    A[1][1] = (px_dv[1] - px_cur[1]) / halfpatch_size;
+  }
+  // ---- getBestSearchLevel ----
+  int search_level = 0;
+  {
+    double D = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+    const int max_level = in->n_pyr_levels - 1;
+    while (D > 3.0 && search_level < max_level) {
+      search_level += 1;
+      D *= 0.25;
+    }
+  }
+  if (out->search_level) out->search_level[i] = search_level;
+  // ---- warpAffine on the (halfpatch_size_+1) = 5 border patch ----
+  uint8_t patch_with_border[100] = {0};
+  uint8_t patch[64];
+  {
+    const int halfpatch_size = halfpatch_size_ + 1, patch_size = 2 * halfpatch_size;
+    const double det = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+    const double invdet = 1.0 / det;
+    const float R00 = (float)(A[1][1] * invdet), R10 = (float)(-A[1][0] * invdet);
+    const float R01 = (float)(-A[0][1] * invdet), R11 = (float)(A[0][0] * invdet);
+    if (!std::isnan(R00)) {
+      const int cols = cam.width >> level_ref, rows = cam.height >> level_ref;
+      const uint8_t* img = in->ref_img[level_ref] + (size_t)in->ref_index[i] * in->ref_stride[level_ref];
+      const int stride = (int)in->ref_pitch[level_ref];
+      const float pr0 = (float)px_ref[0] / (1 << level_ref), pr1 = (float)px_ref[1] / (1 << level_ref);
+      uint8_t* patch_ptr = patch_with_border;
+      for (int y = 0; y < patch_size; ++y)
+        for (int x = 0; x < patch_size; ++x, ++patch_ptr) {
+          float p0 = (float)(x - halfpatch_size), p1 = (float)(y - halfpatch_size);
+          p0 *= (1 << search_level), p1 *= (1 << search_level);
+          const float q0 = (R00 * p0 + R01 * p1) + pr0;
+          const float q1 = (R10 * p0 + R11 * p1) + pr1;
+          if (q0 < 0 || q1 < 0 || q0 >= cols - 1 || q1 >= rows - 1)
+            *patch_ptr = 0;
+          else
+            *patch_ptr = (uint8_t)interpolate_mat_8u(img, stride, q0, q1);
+        }
+    }
+  }
+  for (int y = 1; y < 9; ++y)
+    for (int x = 0; x < 8; ++x) patch[(y - 1) * 8 + x] = patch_with_border[y * 10 + 1 + x];
+  // ---- align at the search level ----
+  const double scale = (double)(1 << search_level);
+  double px_scaled[2] = {in->px_cur[2 * I] / scale, in->px_cur[2 * I + 1] / scale};
+  const uint8_t* cur = in->cur_img[search_level] + (size_t)in->cur_index[i] * in->cur_stride[search_level];
+  const int ccols = cam.width >> search_level, crows = cam.height >> search_level;
+  int ok;
+  if (in->is_edgelet && in->is_edgelet[i]) {
+    const double g0 = in->ref_grad[2 * I], g1 = in->ref_grad[2 * I + 1];
+    double d0 = A[0][0] * g0 + A[0][1] * g1, d1 = A[1][0] * g0 + A[1][1] * g1;
+    const double n = std::sqrt(d0 * d0 + d1 * d1);
+    d0 /= n, d1 /= n;
+    const float dir[2] = {(float)d0, (float)d1};
+    double h_inv;
+    ok = plsvo_oracle_align1d(cur, ccols, crows, in->cur_pitch[search_level], dir, patch_with_border, patch, in->n_iter, px_scaled, &h_inv);
+  } else {
+    ok = plsvo_oracle_align2d(cur, ccols, crows, in->cur_pitch[search_level], patch_with_border, patch, in->n_iter, px_scaled);
+  }
+  out->px_cur[2 * I] = px_scaled[0] * scale, out->px_cur[2 * I + 1] = px_scaled[1] * scale;
+  out->success[i] = (uint8_t)ok;
+}
+
+int plsvo_oracle_match_direct_batch(const plsvo_match_batch* in, const plsvo_match_result* out, int n_threads) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  parallel_for(in->n_features, n_threads, [&](int i) { match_direct_one(in, out, i); });
+  return PLSVO_OK;
+}
+
 // Batch drivers over the ABI structs (CPU baseline of tools/bench_next.py): one call per feature, threads over features.
 int plsvo_oracle_align2d_batch(const plsvo_align2d_batch* in, const plsvo_align2d_result* out, int n_threads) {
   if (!in || !out) return PLSVO_ERR_INVALID;

@@ -6,6 +6,7 @@
 // oracle/Makefile target `ref` compiles, unmodified and where they lie,
 //     /root/reference/src/sparse_img_align.cpp   /root/reference/src/pose_optimizer.cpp
 //     /root/reference/src/feature.cpp            /root/reference/src/feature_alignment.cpp
+//     /root/reference/src/matcher.cpp            /root/reference/src/config.cpp            
 // against the reference's own headers (/root/reference/include/plsvo/*.h) and the stand-in
 // third-party headers in oracle/refdeps/ (Eigen, Sophus, rpg_vikit, OpenCV core, boost — absent
 // from the image and from /root/reference), links this file, and writes oracle/_ref/libplsvo_ref.so.
@@ -24,6 +25,8 @@
 #include <plsvo/feature_alignment.h>
 #include <plsvo/feature3D.h>
 #include <plsvo/frame.h>
+#include <plsvo/matcher.h>
+#include <plsvo/config.h>
 #include <plsvo/pose_optimizer.h>
 #include <plsvo/sparse_img_align.h>
 #include <vikit/pinhole_camera.h>
@@ -52,7 +55,13 @@ Frame::~Frame() {
 }
 
 Point::Point(const Vector3d& pos) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {}
-bool Point::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
+// src/feature3D_impl.cpp picks, among obs_, the observation with the closest viewing direction (list logic that
+// stays on the host side of the ABI); the harness hands over exactly one observation per point.
+bool Point::getCloseViewObs(const Vector3d&, Feature*& obs) const {
+  if (obs_.empty()) return false;
+  obs = obs_.front();
+  return true;
+}
 void Point::optimize(const size_t) {}
 
 LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos)
@@ -306,8 +315,49 @@ int plsvo_ref_align1d(const uint8_t* cur_img, int cols, int rows, size_t cur_ste
   return ok ? 1 : 0;
 }
 
+// Matcher::findMatchDirect(const Point&, const Frame&, Vector2d&) (src/matcher.cpp:159-211) per feature.
+int plsvo_ref_match_direct_batch(const plsvo_match_batch* in, const plsvo_match_result* out) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  plsvo::Config::nPyrLevels() = (size_t)in->n_pyr_levels;
+  vk::PinholeCamera cam(in->cam.width, in->cam.height, in->cam.fx, in->cam.fy, in->cam.cx, in->cam.cy);
+  auto make_frames = [&](int n, const uint8_t* const* img, const size_t* pitch, const size_t* stride, const double* T) {
+    std::vector<FramePtr> frames;
+    for (int r = 0; r < n; ++r) {
+      FramePtr f(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+      f->img_pyr_.resize(PLSVO_MAX_LEVELS);
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
+        if (img[l])
+          f->img_pyr_[l] = cv::Mat(in->cam.height >> l, in->cam.width >> l, CV_8U, const_cast<uint8_t*>(img[l] + (size_t)r * stride[l]), pitch[l]);
+      f->T_f_w_ = pose_from7(T + 7 * (size_t)r);
+      frames.push_back(f);
+    }
+    return frames;
+  };
+  std::vector<FramePtr> refs = make_frames(in->n_ref_images, in->ref_img, in->ref_pitch, in->ref_stride, in->T_ref_w);
+  std::vector<FramePtr> curs = make_frames(in->n_cur_images, in->cur_img, in->cur_pitch, in->cur_stride, in->T_cur_w);
+  for (int i = 0; i < in->n_features; ++i) {
+    plsvo::Frame* rf = refs[in->ref_index[i]].get();
+    plsvo::Point pt(v3(in->pos + 3 * (size_t)i));
+    plsvo::PointFeat ftr(rf, &pt, v2(in->ref_px + 2 * (size_t)i), v3(in->ref_f + 3 * (size_t)i), in->ref_level[i]);
+    if (in->is_edgelet && in->is_edgelet[i]) {
+      ftr.type = plsvo::PointFeat::EDGELET;
+      ftr.grad = v2(in->ref_grad + 2 * (size_t)i);
+    }
+    pt.addFrameRef(&ftr);
+    plsvo::Matcher matcher{};  // value-initialised: the patch buffers start zeroed (warpAffine may leave them untouched)
+    matcher.search_level_ = -1;
+    matcher.options_.align_max_iter = in->n_iter;
+    Vector2d px(in->px_cur[2 * (size_t)i], in->px_cur[2 * (size_t)i + 1]);
+    const bool ok = matcher.findMatchDirect(pt, *curs[in->cur_index[i]], px);
+    out->px_cur[2 * (size_t)i] = px[0], out->px_cur[2 * (size_t)i + 1] = px[1];
+    out->success[i] = ok ? 1 : 0;
+    if (out->search_level) out->search_level[i] = matcher.search_level_;
+  }
+  return PLSVO_OK;
+}
+
 const char* plsvo_ref_describe(void) {
-  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment}.cpp compiled unmodified against stand-in "
+  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment,matcher,config}.cpp compiled unmodified against stand-in "
          "Eigen/Sophus/vikit/OpenCV/boost headers (oracle/refdeps)";
 }
 }

@@ -162,6 +162,20 @@ class Align1DResult(C.Structure):
     _fields_ = [("px", _f64p), ("converged", _u8p), ("h_inv", _f64p)]
 
 
+class MatchBatch(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("n_ref_images", C.c_int32), ("n_cur_images", C.c_int32), ("n_pyr_levels", C.c_int32),
+                ("n_iter", C.c_int32), ("reserved", C.c_int32), ("cam", Camera),
+                ("ref_img", _u8p * MAX_LEVELS), ("ref_pitch", C.c_size_t * MAX_LEVELS), ("ref_stride", C.c_size_t * MAX_LEVELS),
+                ("cur_img", _u8p * MAX_LEVELS), ("cur_pitch", C.c_size_t * MAX_LEVELS), ("cur_stride", C.c_size_t * MAX_LEVELS),
+                ("T_ref_w", _f64p), ("T_cur_w", _f64p), ("ref_index", _i32p), ("cur_index", _i32p), ("ref_px", _f64p),
+                ("ref_f", _f64p), ("ref_level", _i32p), ("is_edgelet", _u8p), ("ref_grad", _f64p), ("pos", _f64p),
+                ("px_cur", _f64p)]
+
+
+class MatchResult(C.Structure):
+    _fields_ = [("px_cur", _f64p), ("success", _u8p), ("search_level", _i32p)]
+
+
 # ------------------------------------------------------------------------------------------------
 # numpy <-> struct helpers
 # ------------------------------------------------------------------------------------------------
@@ -327,6 +341,7 @@ ABI_SYMBOLS = [
     ("plsvo_pyramid_batch_run", C.c_int, [C.c_void_p, _P(PyramidBatch), _P(PyramidResult)]),
     ("plsvo_align2d_batch_run", C.c_int, [C.c_void_p, _P(Align2DBatch), _P(Align2DResult)]),
     ("plsvo_align1d_batch_run", C.c_int, [C.c_void_p, _P(Align1DBatch), _P(Align1DResult)]),
+    ("plsvo_match_direct_batch_run", C.c_int, [C.c_void_p, _P(MatchBatch), _P(MatchResult)]),
     ("plsvo_last_kernel_ms", C.c_int, [C.c_void_p, _P(C.c_float)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
     ("plsvo_selftest_weight", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
@@ -375,3 +390,33 @@ def make_align2d_batch(pyr, image_index, level, border, ref, px, n_iter, width, 
     b.ref_patch = _ptr(ref.reshape(len(image_index), -1), np.uint8)
     b.px = _ptr(px, np.float64)
     return b, keep
+
+
+def make_match_batch(d):
+    """Build a plsvo_match_batch from a synth.MatchData-like object.  Returns (struct, keepalive)."""
+    b = MatchBatch()
+    b.n_features, b.n_ref_images, b.n_cur_images = d.n, d.T_ref_w.shape[0], d.T_cur_w.shape[0]
+    b.n_pyr_levels, b.n_iter = d.n_pyr_levels, d.n_iter
+    b.cam = Camera(d.cam.width, d.cam.height, 0, 0, d.cam.fx, d.cam.fy, d.cam.cx, d.cam.cy)
+    for l, im in d.ref_pyr.items():
+        b.ref_img[l] = _ptr(im, np.uint8)
+        b.ref_pitch[l], b.ref_stride[l] = im.strides[1], im.strides[0]
+    for l, im in d.cur_pyr.items():
+        b.cur_img[l] = _ptr(im, np.uint8)
+        b.cur_pitch[l], b.cur_stride[l] = im.strides[1], im.strides[0]
+    b.T_ref_w, b.T_cur_w = _ptr(d.T_ref_w, np.float64), _ptr(d.T_cur_w, np.float64)
+    b.ref_index, b.cur_index = _ptr(d.ref_index, np.int32), _ptr(d.cur_index, np.int32)
+    b.ref_px, b.ref_f, b.ref_level = _ptr(d.ref_px, np.float64), _ptr(d.ref_f, np.float64), _ptr(d.ref_level, np.int32)
+    b.is_edgelet, b.ref_grad = _ptr(d.is_edgelet, np.uint8), _ptr(d.ref_grad, np.float64)
+    b.pos, b.px_cur = _ptr(d.pos, np.float64), _ptr(d.px_cur, np.float64)
+    return b, [d]
+
+
+class MatchOut:
+    """Owns the output arrays of one findMatchDirect batch and the plsvo_match_result pointing at them."""
+
+    def __init__(self, n: int):
+        self.px_cur = np.zeros((n, 2))
+        self.success = np.zeros(n, np.uint8)
+        self.search_level = np.zeros(n, np.int32)
+        self.struct = MatchResult(_ptr(self.px_cur, np.float64), _ptr(self.success, np.uint8), _ptr(self.search_level, np.int32))

@@ -459,3 +459,75 @@ def make_poseopt_batch(
         seg_epos=npy(seg_epos),
         seg_level=seg_level,
     )
+
+
+# ---- Matcher::findMatchDirect candidates -----------------------------------------
+@dataclass
+class MatchData:
+    """Host arrays of one findMatchDirect batch, shaped as plsvo_match_batch describes."""
+
+    cam: Camera
+    n_pyr_levels: int
+    ref_pyr: dict  # level -> u8 [n_ref,h,w]
+    cur_pyr: dict  # level -> u8 [n_cur,h,w]
+    T_ref_w: np.ndarray
+    T_cur_w: np.ndarray
+    ref_index: np.ndarray
+    cur_index: np.ndarray
+    ref_px: np.ndarray
+    ref_f: np.ndarray
+    ref_level: np.ndarray
+    is_edgelet: np.ndarray
+    ref_grad: np.ndarray
+    pos: np.ndarray
+    px_cur: np.ndarray
+    px_cur_gt: np.ndarray
+    n_iter: int = 10
+
+    @property
+    def n(self):
+        return self.ref_index.shape[0]
+
+
+def make_match_batch(cam: Camera = VGA, n: int = 2000, n_ref: int = 3, n_cur: int = 3, n_pyr_levels: int = 3, seed: int = 7000,
+                     device: str | torch.device = "cpu", motion_t: float = 0.08, motion_r: float = 0.04,
+                     edgelet_frac: float = 0.25, noise_px: float = 1.5, scene: Scene | None = None) -> MatchData:
+    """n reprojection candidates: a reference observation (keyframe r, pixel, bearing, level), its 3D point on the
+    synthetic surface, and the projection into current frame c perturbed by up to `noise_px` (what the reprojector
+    hands to findMatchDirect).  A few candidates sit at the image border / far outside to exercise the early-outs."""
+    dev = torch.device(device)
+    scene = scene or Scene()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f64 = dict(dtype=torch.float64, device=dev)
+    xi_ref = np.concatenate([rng.uniform(-0.2, 0.2, (n_ref, 3)), rng.uniform(-0.03, 0.03, (n_ref, 3))], -1)
+    xi_cur = np.concatenate([rng.uniform(-0.2 - motion_t, 0.2 + motion_t, (n_cur, 3)), rng.uniform(-motion_r, motion_r, (n_cur, 3))], -1)
+    xi_cur[:, 2] = rng.uniform(-0.05, 0.45, n_cur)  # some frames closer to the scene: search levels above 0
+    R_ref, t_ref = se3_exp_Rt(torch.tensor(xi_ref, **f64))
+    R_cur, t_cur = se3_exp_Rt(torch.tensor(xi_cur, **f64))
+    T_ref_w, T_cur_w = pose7_from_Rt(R_ref, t_ref), pose7_from_Rt(R_cur, t_cur)
+    ref_pyr = {l: np.ascontiguousarray(p.cpu().numpy()) for l, p in enumerate(build_pyramid(scene.render(cam, T_ref_w), n_pyr_levels))}
+    cur_pyr = {l: np.ascontiguousarray(p.cpu().numpy()) for l, p in enumerate(build_pyramid(scene.render(cam, T_cur_w), n_pyr_levels))}
+    ref_index = rng.integers(0, n_ref, n).astype(np.int32)
+    cur_index = rng.integers(0, n_cur, n).astype(np.int32)
+    ref_level = rng.integers(0, n_pyr_levels, n).astype(np.int32)
+    ref_px = np.stack([rng.uniform(20, cam.width - 20, n), rng.uniform(20, cam.height - 20, n)], -1)
+    k = min(8, n)
+    ref_px[:k] = [[3.0, 50.0], [cam.width - 4.0, 50.0], [100.0, 2.0], [100.0, cam.height - 3.0], [6.0 * 4, 6.0 * 4],
+                  [cam.width / 2, cam.height / 2], [7.9, 200.0], [cam.width - 7.0, cam.height - 7.0]][:k]
+    px_t = torch.tensor(ref_px, **f64)
+    d = torch.stack([(px_t[:, 0] - cam.cx) / cam.fx, (px_t[:, 1] - cam.cy) / cam.fy, torch.ones_like(px_t[:, 0])], -1)
+    ref_f = d / d.norm(dim=-1, keepdim=True)
+    ridx = torch.tensor(ref_index, device=dev, dtype=torch.long)
+    cidx = torch.tensor(cur_index, device=dev, dtype=torch.long)
+    pos = scene.intersect(R_ref[ridx], t_ref[ridx], d[:, None, :])[:, 0, :]
+    p_cur = (R_cur[cidx] @ pos[..., None])[..., 0] + t_cur[cidx]
+    px_gt = torch.stack([cam.fx * p_cur[:, 0] / p_cur[:, 2] + cam.cx, cam.fy * p_cur[:, 1] / p_cur[:, 2] + cam.cy], -1).cpu().numpy()
+    px_cur = px_gt + rng.uniform(-noise_px, noise_px, (n, 2))
+    is_edgelet = (rng.uniform(size=n) < edgelet_frac).astype(np.uint8)
+    ang = rng.uniform(0, 2 * math.pi, n)
+    ref_grad = np.stack([np.cos(ang), np.sin(ang)], -1)
+    c = lambda a, t: np.ascontiguousarray(a.cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=t)  # noqa: E731
+    return MatchData(cam=cam, n_pyr_levels=n_pyr_levels, ref_pyr=ref_pyr, cur_pyr=cur_pyr, T_ref_w=c(T_ref_w, np.float64),
+                     T_cur_w=c(T_cur_w, np.float64), ref_index=ref_index, cur_index=cur_index, ref_px=c(ref_px, np.float64),
+                     ref_f=c(ref_f, np.float64), ref_level=ref_level, is_edgelet=is_edgelet, ref_grad=c(ref_grad, np.float64),
+                     pos=c(pos, np.float64), px_cur=c(px_cur, np.float64), px_cur_gt=c(px_gt, np.float64))
