@@ -209,3 +209,21 @@ class feature_alignment:
                               h_inv.ctypes.data_as(C.POINTER(C.c_double)))
         ctx.check(ctx.lib.plsvo_align1d_batch_run(ctx.handle, C.byref(b), C.byref(r)), "plsvo_align1d_batch_run")
         return conv.astype(bool), out_px, h_inv
+
+
+class Matcher:
+    """Batched counterpart of plsvo::Matcher::findMatchDirect (include/plsvo/matcher.h:104-107, src/matcher.cpp:159-211)
+    for candidates whose reference observation has already been chosen (getCloseViewObs stays host-side list logic)."""
+
+    def __init__(self, align_max_iter: int = 10, ctx: Context | None = None):
+        self.align_max_iter = align_max_iter  # Matcher::Options::align_max_iter
+        self.ctx = ctx or default_context()
+
+    def findMatchDirect(self, data) -> abi.MatchOut:
+        """data: synth.MatchData-like batch -> px_cur (refined, level-0 pixels), success flags, search levels."""
+        data.n_iter = self.align_max_iter
+        b, keep = abi.make_match_batch(data)
+        out = abi.MatchOut(data.n)
+        self.ctx.check(self.ctx.lib.plsvo_match_direct_batch_run(self.ctx.handle, C.byref(b), C.byref(out.struct)),
+                       "plsvo_match_direct_batch_run")
+        return out

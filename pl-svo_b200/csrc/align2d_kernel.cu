@@ -19,30 +19,11 @@ namespace {
 
 constexpr int kA2Threads = 128;
 
-__global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a) {
-  __shared__ uint8_t s_border[kA2Threads][104];  // 100 used (+4 pad keeps rows word aligned)
-  __shared__ uint8_t s_ref[kA2Threads][64];
-  const int tid = threadIdx.x;
-  const int i = blockIdx.x * kA2Threads + tid;
-  const bool active = i < a.n;
-  if (active) {
-    const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.ref_patch_with_border + (size_t)i * 100);
-    const uint32_t* gr = reinterpret_cast<const uint32_t*>(a.ref_patch + (size_t)i * 64);
-    uint32_t* sb = reinterpret_cast<uint32_t*>(s_border[tid]);
-    uint32_t* sr = reinterpret_cast<uint32_t*>(s_ref[tid]);
-#pragma unroll
-    for (int k = 0; k < 25; ++k) sb[k] = gb[k];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) sr[k] = gr[k];
-  }
-  if (!active) return;
-  const uint8_t* border = s_border[tid];
-  const uint8_t* ref = s_ref[tid];
-  const int level = a.level[i];
-  const int cols = a.width >> level, rows = a.height >> level;
-  const int cur_step = (int)a.pitch[level];
-  const uint8_t* img = a.img[level] + (size_t)a.image_index[i] * a.stride[level];
-
+// align2D on one feature.  border = 10x10 reference patch with border, ref = 8x8 reference patch with row step
+// ref_step (8 for a packed patch, 10 when it is the interior of `border`).  u,v in/out; returns `converged`.
+__device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_t* ref, const int ref_step, const uint8_t* img,
+                                             const int cur_step, const int cols, const int rows, const int n_iter, float& u,
+                                             float& v) {
   // ---- template Hessian (:183-201): J = (0.5*dx, 0.5*dy, 1), H = sum J J^T (exact in fp32) ----
   float H00 = 0, H01 = 0, H02 = 0, H11 = 0, H12 = 0, H22 = 0;
   for (int y = 0; y < 8; ++y) {
@@ -79,10 +60,9 @@ __global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a
   const float I20 = __fmul_rn(c02, invdet), I21 = __fmul_rn(c12, invdet), I22 = __fmul_rn(c22, invdet);
 
   float mean_diff = 0.f;
-  float u = (float)a.px[2 * (size_t)i], v = (float)a.px[2 * (size_t)i + 1];
   const float min_update_squared = (float)(0.03 * 0.03);
   bool converged = false;
-  for (int iter = 0; iter < a.n_iter; ++iter) {
+  for (int iter = 0; iter < n_iter; ++iter) {
     // Patch::setPosition / isInFrame(halfsize=4) / computeInterpWeights (src/feature.cpp:189-208)
     const float fu = floorf(u), fv = floorf(v);
     const int ui = (int)fu, vi = (int)fv;
@@ -94,9 +74,10 @@ __global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a
     const float wBR = __fmul_rn(su, sv);
     float J0 = 0.f, J1 = 0.f, J2 = 0.f;
     const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
-    const uint8_t* it_ref = ref;
-    for (int y = 0; y < 8; ++y, row += cur_step) {
+    const uint8_t* ref_row = ref;
+    for (int y = 0; y < 8; ++y, row += cur_step, ref_row += ref_step) {
       const uint8_t* itb = border + (y + 1) * 10 + 1;
+      const uint8_t* it_ref = ref_row;
 #pragma unroll
       for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
         const float search_pixel =
@@ -123,6 +104,112 @@ __global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a
       break;
     }
   }
+  return converged;
+}
+
+// align1D on one feature (same conventions as align2d_core); d0,d1 = direction, h_inv out.
+__device__ __forceinline__ bool align1d_core(const uint8_t* border, const uint8_t* ref, const int ref_step, const uint8_t* img,
+                                             const int cur_step, const int cols, const int rows, const int n_iter, const float d0,
+                                             const float d1, float& u, float& v, double& h_inv) {
+  // directional template derivative (:63-66): J0 = 0.5*(dir0*(I[x+1]-I[x-1]) + dir1*(I[y+1]-I[y-1])) in float, J1 = 1
+  auto dv_at = [&](const uint8_t* it) {
+    const float gx = __fmul_rn(d0, (float)((int)it[1] - (int)it[-1]));
+    const float gy = __fmul_rn(d1, (float)((int)it[10] - (int)it[-10]));
+    return (float)(0.5 * (double)__fadd_rn(gx, gy));
+  };
+  float H00 = 0, H01 = 0, H11 = 0;
+  for (int y = 0; y < 8; ++y) {
+    const uint8_t* it = border + (y + 1) * 10 + 1;
+    for (int x = 0; x < 8; ++x, ++it) {
+      const float J0 = dv_at(it);
+      H00 = __fadd_rn(H00, __fmul_rn(J0, J0));
+      H01 = __fadd_rn(H01, J0);
+      H11 = __fadd_rn(H11, 1.0f);
+    }
+  }
+  h_inv = 1.0 / (double)H00 * 8 * 8;  // :75
+  // Matrix2f::inverse(): 1/det, (d, -c; -b, a) * invdet
+  const float det = __fsub_rn(__fmul_rn(H00, H11), __fmul_rn(H01, H01));
+  const float invdet = __fdiv_rn(1.0f, det);
+  const float I00 = __fmul_rn(H11, invdet), I10 = __fmul_rn(-H01, invdet);
+  const float I01 = __fmul_rn(-H01, invdet), I11 = __fmul_rn(H00, invdet);
+
+  float mean_diff = 0.f;
+  const float min_update_squared = (float)(0.03 * 0.03);
+  float chi2 = 0.f, up0 = 0.f, up1 = 0.f;
+  bool converged = false;
+  for (int iter = 0; iter < n_iter; ++iter) {
+    const float fu = floorf(u), fv = floorf(v);
+    const int ui = (int)fu, vi = (int)fv;
+    if (ui < 4 || vi < 4 || ui >= cols - 4 || vi >= rows - 4) break;  // NaN never passes this test (:87-92)
+    const float su = __fsub_rn(u, fu), sv = __fsub_rn(v, fv);
+    const float wTL = (float)((1.0 - (double)su) * (1.0 - (double)sv));
+    const float wTR = (float)((double)su * (1.0 - (double)sv));
+    const float wBL = (float)((1.0 - (double)su) * (double)sv);
+    const float wBR = __fmul_rn(su, sv);
+    float J0 = 0.f, J1 = 0.f, new_chi2 = 0.f;
+    const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
+    const uint8_t* ref_row = ref;
+    for (int y = 0; y < 8; ++y, row += cur_step, ref_row += ref_step) {
+      const uint8_t* itb = border + (y + 1) * 10 + 1;
+      const uint8_t* it_ref = ref_row;
+#pragma unroll
+      for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
+        const float search_pixel =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, (float)row[x]), __fmul_rn(wTR, (float)row[x + 1])),
+                                __fmul_rn(wBL, (float)row[x + cur_step])),
+                      __fmul_rn(wBR, (float)row[x + cur_step + 1]));
+        const float res = __fadd_rn(__fsub_rn(search_pixel, (float)*it_ref), mean_diff);
+        J0 = __fsub_rn(J0, __fmul_rn(res, dv_at(itb)));
+        J1 = __fsub_rn(J1, res);
+        new_chi2 = __fadd_rn(new_chi2, __fmul_rn(res, res));
+      }
+    }
+    if (iter > 0 && new_chi2 > chi2) {  // :124-132 (the back-off subtracts the raw update, as the reference does)
+      u = __fsub_rn(u, up0);
+      v = __fsub_rn(v, up1);
+      break;
+    }
+    chi2 = new_chi2;
+    up0 = __fadd_rn(__fmul_rn(I00, J0), __fmul_rn(I01, J1));
+    up1 = __fadd_rn(__fmul_rn(I10, J0), __fmul_rn(I11, J1));
+    u = __fadd_rn(u, __fmul_rn(up0, d0));
+    v = __fadd_rn(v, __fmul_rn(up0, d1));
+    mean_diff = __fadd_rn(mean_diff, up1);
+    if (__fadd_rn(__fmul_rn(up0, up0), __fmul_rn(up1, up1)) < min_update_squared) {
+      converged = true;
+      break;
+    }
+  }
+  return converged;
+}
+
+__global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a) {
+  __shared__ uint8_t s_border[kA2Threads][104];  // 100 used (+4 pad keeps rows word aligned)
+  __shared__ uint8_t s_ref[kA2Threads][64];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kA2Threads + tid;
+  const bool active = i < a.n;
+  if (active) {
+    const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.ref_patch_with_border + (size_t)i * 100);
+    const uint32_t* gr = reinterpret_cast<const uint32_t*>(a.ref_patch + (size_t)i * 64);
+    uint32_t* sb = reinterpret_cast<uint32_t*>(s_border[tid]);
+    uint32_t* sr = reinterpret_cast<uint32_t*>(s_ref[tid]);
+#pragma unroll
+    for (int k = 0; k < 25; ++k) sb[k] = gb[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sr[k] = gr[k];
+  }
+  if (!active) return;
+  const uint8_t* border = s_border[tid];
+  const uint8_t* ref = s_ref[tid];
+  const int level = a.level[i];
+  const int cols = a.width >> level, rows = a.height >> level;
+  const int cur_step = (int)a.pitch[level];
+  const uint8_t* img = a.img[level] + (size_t)a.image_index[i] * a.stride[level];
+
+  float u = (float)a.px[2 * (size_t)i], v = (float)a.px[2 * (size_t)i + 1];
+  const bool converged = align2d_core(border, ref, 8, img, cur_step, cols, rows, a.n_iter, u, v);
   a.out_px[2 * (size_t)i] = (double)u;
   a.out_px[2 * (size_t)i + 1] = (double)v;
   a.out_converged[i] = converged ? 1 : 0;
@@ -156,82 +243,214 @@ __global__ void __launch_bounds__(kA2Threads) align1d_kernel(const Align2DArgs a
   const uint8_t* img = a.img[level] + (size_t)a.image_index[i] * a.stride[level];
   const float d0 = a.dir[2 * (size_t)i], d1 = a.dir[2 * (size_t)i + 1];
 
-  // directional template derivative (:63-66): J0 = 0.5*(dir0*(I[x+1]-I[x-1]) + dir1*(I[y+1]-I[y-1])) in float, J1 = 1
-  auto dv_at = [&](const uint8_t* it) {
-    const float gx = __fmul_rn(d0, (float)((int)it[1] - (int)it[-1]));
-    const float gy = __fmul_rn(d1, (float)((int)it[10] - (int)it[-10]));
-    return (float)(0.5 * (double)__fadd_rn(gx, gy));
-  };
-  float H00 = 0, H01 = 0, H11 = 0;
-  for (int y = 0; y < 8; ++y) {
-    const uint8_t* it = border + (y + 1) * 10 + 1;
-    for (int x = 0; x < 8; ++x, ++it) {
-      const float J0 = dv_at(it);
-      H00 = __fadd_rn(H00, __fmul_rn(J0, J0));
-      H01 = __fadd_rn(H01, J0);
-      H11 = __fadd_rn(H11, 1.0f);
-    }
-  }
-  a.out_h_inv[i] = 1.0 / (double)H00 * 8 * 8;  // :75
-  // Matrix2f::inverse(): 1/det, (d, -c; -b, a) * invdet
-  const float det = __fsub_rn(__fmul_rn(H00, H11), __fmul_rn(H01, H01));
-  const float invdet = __fdiv_rn(1.0f, det);
-  const float I00 = __fmul_rn(H11, invdet), I10 = __fmul_rn(-H01, invdet);
-  const float I01 = __fmul_rn(-H01, invdet), I11 = __fmul_rn(H00, invdet);
-
-  float mean_diff = 0.f;
   float u = (float)a.px[2 * (size_t)i], v = (float)a.px[2 * (size_t)i + 1];
-  const float min_update_squared = (float)(0.03 * 0.03);
-  float chi2 = 0.f, up0 = 0.f, up1 = 0.f;
-  bool converged = false;
-  for (int iter = 0; iter < a.n_iter; ++iter) {
-    const float fu = floorf(u), fv = floorf(v);
-    const int ui = (int)fu, vi = (int)fv;
-    if (ui < 4 || vi < 4 || ui >= cols - 4 || vi >= rows - 4) break;  // NaN never passes this test (:87-92)
-    const float su = __fsub_rn(u, fu), sv = __fsub_rn(v, fv);
-    const float wTL = (float)((1.0 - (double)su) * (1.0 - (double)sv));
-    const float wTR = (float)((double)su * (1.0 - (double)sv));
-    const float wBL = (float)((1.0 - (double)su) * (double)sv);
-    const float wBR = __fmul_rn(su, sv);
-    float J0 = 0.f, J1 = 0.f, new_chi2 = 0.f;
-    const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
-    const uint8_t* it_ref = ref;
-    for (int y = 0; y < 8; ++y, row += cur_step) {
-      const uint8_t* itb = border + (y + 1) * 10 + 1;
-#pragma unroll
-      for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
-        const float search_pixel =
-            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, (float)row[x]), __fmul_rn(wTR, (float)row[x + 1])),
-                                __fmul_rn(wBL, (float)row[x + cur_step])),
-                      __fmul_rn(wBR, (float)row[x + cur_step + 1]));
-        const float res = __fadd_rn(__fsub_rn(search_pixel, (float)*it_ref), mean_diff);
-        J0 = __fsub_rn(J0, __fmul_rn(res, dv_at(itb)));
-        J1 = __fsub_rn(J1, res);
-        new_chi2 = __fadd_rn(new_chi2, __fmul_rn(res, res));
-      }
-    }
-    if (iter > 0 && new_chi2 > chi2) {  // :124-132 (the back-off subtracts the raw update, as the reference does)
-      u = __fsub_rn(u, up0);
-      v = __fsub_rn(v, up1);
-      break;
-    }
-    chi2 = new_chi2;
-    up0 = __fadd_rn(__fmul_rn(I00, J0), __fmul_rn(I01, J1));
-    up1 = __fadd_rn(__fmul_rn(I10, J0), __fmul_rn(I11, J1));
-    u = __fadd_rn(u, __fmul_rn(up0, d0));
-    v = __fadd_rn(v, __fmul_rn(up0, d1));
-    mean_diff = __fadd_rn(mean_diff, up1);
-    if (__fadd_rn(__fmul_rn(up0, up0), __fmul_rn(up1, up1)) < min_update_squared) {
-      converged = true;
-      break;
-    }
-  }
+  double h_inv;
+  const bool converged = align1d_core(border, ref, 8, img, cur_step, cols, rows, a.n_iter, d0, d1, u, v, h_inv);
+  a.out_h_inv[i] = h_inv;
   a.out_px[2 * (size_t)i] = (double)u;
   a.out_px[2 * (size_t)i + 1] = (double)v;
   a.out_converged[i] = converged ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Matcher::findMatchDirect(const Point&, const Frame&, Vector2d&) after getCloseViewObs (src/matcher.cpp:159-211):
+// in-frame test, warp::getWarpMatrixAffine (:42-71), getBestSearchLevel (:73-87), warp::warpAffine (:89-133,
+// vk::interpolateMat_8u), createPatchFromPatchWithBorder (:148-157), align2D / align1D at the search level.
+// One thread per candidate.  The double-precision geometry is written with explicit round-to-nearest intrinsics
+// so that the compiler cannot contract a*b+c into an FMA: A_cur_ref, the search level, every byte of the warped
+// patch and therefore the refined position are bit-identical to the reference's scalar code.
+struct V3 {
+  double x, y, z;
+};
+struct Q4 {
+  double x, y, z, w;
+};
+struct Pose {
+  Q4 q;
+  V3 t;
+};
+#define DM(a, b) __dmul_rn((a), (b))
+#define DA(a, b) __dadd_rn((a), (b))
+#define DS(a, b) __dsub_rn((a), (b))
+#define DD(a, b) __ddiv_rn((a), (b))
+__device__ __forceinline__ V3 v_add(V3 a, V3 b) { return {DA(a.x, b.x), DA(a.y, b.y), DA(a.z, b.z)}; }
+__device__ __forceinline__ V3 v_sub(V3 a, V3 b) { return {DS(a.x, b.x), DS(a.y, b.y), DS(a.z, b.z)}; }
+__device__ __forceinline__ V3 v_scale(V3 a, double s) { return {DM(a.x, s), DM(a.y, s), DM(a.z, s)}; }
+__device__ __forceinline__ V3 v_cross(V3 a, V3 b) {
+  return {DS(DM(a.y, b.z), DM(a.z, b.y)), DS(DM(a.z, b.x), DM(a.x, b.z)), DS(DM(a.x, b.y), DM(a.y, b.x))};
+}
+__device__ __forceinline__ double v_norm(V3 a) { return __dsqrt_rn(DA(DA(DM(a.x, a.x), DM(a.y, a.y)), DM(a.z, a.z))); }
+__device__ __forceinline__ Q4 q_normalized(Q4 q) {  // Eigen: coeffs() /= coeffs().norm()
+  const double n = __dsqrt_rn(DA(DA(DA(DM(q.x, q.x), DM(q.y, q.y)), DM(q.z, q.z)), DM(q.w, q.w)));
+  return {DD(q.x, n), DD(q.y, n), DD(q.z, n), DD(q.w, n)};
+}
+__device__ __forceinline__ Q4 q_mul(Q4 a, Q4 b) {
+  return {DS(DA(DA(DM(a.w, b.x), DM(a.x, b.w)), DM(a.y, b.z)), DM(a.z, b.y)),
+          DS(DA(DA(DM(a.w, b.y), DM(a.y, b.w)), DM(a.z, b.x)), DM(a.x, b.z)),
+          DS(DA(DA(DM(a.w, b.z), DM(a.z, b.w)), DM(a.x, b.y)), DM(a.y, b.x)),
+          DS(DS(DS(DM(a.w, b.w), DM(a.x, b.x)), DM(a.y, b.y)), DM(a.z, b.z))};
+}
+__device__ __forceinline__ V3 q_rot(Q4 q, V3 v) {  // Eigen QuaternionBase::_transformVector
+  const V3 qv{q.x, q.y, q.z};
+  V3 uv = v_cross(qv, v);
+  uv = v_add(uv, uv);
+  return v_add(v_add(v, v_scale(uv, q.w)), v_cross(qv, uv));
+}
+__device__ __forceinline__ Pose pose_load(const double* p) {  // SO3(const Quaterniond&) normalises
+  return {q_normalized(Q4{p[0], p[1], p[2], p[3]}), V3{p[4], p[5], p[6]}};
+}
+__device__ __forceinline__ Pose pose_inverse(Pose a) {  // Sophus SE3::inverse
+  Pose r;
+  r.q = q_normalized(Q4{-a.q.x, -a.q.y, -a.q.z, a.q.w});
+  r.t = q_rot(r.q, v_scale(a.t, -1.0));
+  return r;
+}
+__device__ __forceinline__ Pose pose_mul(Pose a, Pose b) {  // SE3::operator*=
+  Pose r;
+  r.t = v_add(a.t, q_rot(a.q, b.t));
+  r.q = q_normalized(q_mul(a.q, b.q));
+  return r;
+}
+__device__ __forceinline__ V3 pose_act(Pose T, V3 p) { return v_add(q_rot(T.q, p), T.t); }
+
+__global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArgs a) {
+  __shared__ uint8_t s_border[kA2Threads][104];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kA2Threads + tid;
+  if (i >= a.n) return;
+  const size_t I = (size_t)i;
+  const double px_ref0 = a.ref_px[2 * I], px_ref1 = a.ref_px[2 * I + 1];
+  const int level_ref = a.ref_level[i];
+  const int r = a.ref_index[i], c = a.cur_index[i];
+  a.out_px[2 * I] = a.px_cur[2 * I];
+  a.out_px[2 * I + 1] = a.px_cur[2 * I + 1];
+  a.out_success[i] = 0;
+  a.out_level[i] = -1;
+  // :169-171  cam.isInFrame(px.cast<int>() / (1 << level), halfpatch_size_ + 2, level)
+  {
+    const int ox = (int)px_ref0 / (1 << level_ref), oy = (int)px_ref1 / (1 << level_ref);
+    const int b = 6;
+    if (!(ox >= b && ox < a.width / (1 << level_ref) - b && oy >= b && oy < a.height / (1 << level_ref) - b)) return;
+  }
+  const Pose T_w_ref = pose_inverse(pose_load(a.T_ref_w + 7 * (size_t)r));
+  const Pose T_cur_ref = pose_mul(pose_load(a.T_cur_w + 7 * (size_t)c), T_w_ref);
+  const V3 pos{a.pos[3 * I], a.pos[3 * I + 1], a.pos[3 * I + 2]};
+  const V3 f_ref{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
+  const double depth_ref = v_norm(v_sub(T_w_ref.t, pos));
+  auto cam2world = [&](double u, double v) {  // PinholeCamera::cam2world, undistorted, then normalized()
+    const V3 xyz{DD(DS(u, a.cx), a.fx), DD(DS(v, a.cy), a.fy), 1.0};
+    const double n = v_norm(xyz);
+    return V3{DD(xyz.x, n), DD(xyz.y, n), DD(xyz.z, n)};
+  };
+  auto world2cam = [&](V3 p, double& u, double& v) {  // world2cam(project2d(xyz))
+    u = DA(DM(a.fx, DD(p.x, p.z)), a.cx);
+    v = DA(DM(a.fy, DD(p.y, p.z)), a.cy);
+  };
+  // ---- warp::getWarpMatrixAffine ----
+  double A00, A01, A10, A11;
+  {
+    const V3 xyz_ref = v_scale(f_ref, depth_ref);
+    const double scale_ref = (double)(1 << level_ref);
+    const double step = DM(5.0, scale_ref), zero = DM(0.0, scale_ref);
+    V3 xyz_du = cam2world(DA(px_ref0, step), DA(px_ref1, zero));
+    V3 xyz_dv = cam2world(DA(px_ref0, zero), DA(px_ref1, step));
+    xyz_du = v_scale(xyz_du, DD(xyz_ref.z, xyz_du.z));
+    xyz_dv = v_scale(xyz_dv, DD(xyz_ref.z, xyz_dv.z));
+    double pc0, pc1, pu0, pu1, pv0, pv1;
+    world2cam(pose_act(T_cur_ref, xyz_ref), pc0, pc1);
+    world2cam(pose_act(T_cur_ref, xyz_du), pu0, pu1);
+    world2cam(pose_act(T_cur_ref, xyz_dv), pv0, pv1);
+    A00 = DD(DS(pu0, pc0), 5.0), A10 = DD(DS(pu1, pc1), 5.0);
+    A01 = DD(DS(pv0, pc0), 5.0), A11 = DD(DS(pv1, pc1), 5.0);
+  }
+  // ---- warp::getBestSearchLevel ----
+  const double det = DS(DM(A00, A11), DM(A10, A01));
+  int search_level = 0;
+  {
+    double D = det;
+    const int max_level = a.n_pyr_levels - 1;
+    while (D > 3.0 && search_level < max_level) {
+      search_level += 1;
+      D = DM(D, 0.25);
+    }
+  }
+  a.out_level[i] = search_level;
+  // ---- warp::warpAffine into the 10x10 patch with border ----
+  uint8_t* border = s_border[tid];
+  {
+    const double invdet = DD(1.0, det);
+    const float R00 = (float)DM(A11, invdet), R10 = (float)DM(-A10, invdet);
+    const float R01 = (float)DM(-A01, invdet), R11 = (float)DM(A00, invdet);
+    const bool bad = isnan(R00);  // "Affine warp is NaN": the reference leaves the (zeroed) patch untouched
+    const int cols = a.width >> level_ref, rows = a.height >> level_ref;
+    const uint8_t* img = a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref];
+    const int stride = (int)a.ref_pitch[level_ref];
+    const float fs = (float)(1 << level_ref);
+    const float pr0 = __fdiv_rn((float)px_ref0, fs), pr1 = __fdiv_rn((float)px_ref1, fs);
+    const float ss = (float)(1 << search_level);
+    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
+    for (int y = 0; y < 10; ++y) {
+      const float p1 = __fmul_rn((float)(y - 5), ss);
+      for (int x = 0; x < 10; ++x) {
+        uint8_t val = 0;
+        if (!bad) {
+          const float p0 = __fmul_rn((float)(x - 5), ss);
+          const float q0 = __fadd_rn(__fadd_rn(__fmul_rn(R00, p0), __fmul_rn(R01, p1)), pr0);
+          const float q1 = __fadd_rn(__fadd_rn(__fmul_rn(R10, p0), __fmul_rn(R11, p1)), pr1);
+          if (!(q0 < 0 || q1 < 0 || q0 >= xmax || q1 >= ymax)) {
+            // vk::interpolateMat_8u
+            const float fx = floorf(q0), fy = floorf(q1);
+            const int ix = (int)fx, iy = (int)fy;
+            const float sx = __fsub_rn(q0, fx), sy = __fsub_rn(q1, fy);
+            const float w00 = __fmul_rn(__fsub_rn(1.0f, sx), __fsub_rn(1.0f, sy));
+            const float w01 = __fmul_rn(__fsub_rn(1.0f, sx), sy);
+            const float w10 = __fmul_rn(sx, __fsub_rn(1.0f, sy));
+            const float w11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, w00), w01), w10);
+            const uint8_t* ptr = img + (size_t)iy * stride + ix;
+            const float I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, (float)ptr[0]), __fmul_rn(w01, (float)ptr[stride])),
+                                                __fmul_rn(w10, (float)ptr[1])),
+                                      __fmul_rn(w11, (float)ptr[stride + 1]));
+            val = (uint8_t)I;
+          }
+        }
+        border[y * 10 + x] = val;
+      }
+    }
+  }
+  // ---- align at the search level; the 8x8 reference patch is the interior of the border patch ----
+  const double scale = (double)(1 << search_level);
+  float u = (float)DD(a.px_cur[2 * I], scale), v = (float)DD(a.px_cur[2 * I + 1], scale);
+  const uint8_t* cur = a.cur_img[search_level] + (size_t)c * a.cur_stride[search_level];
+  const int ccols = a.width >> search_level, crows = a.height >> search_level;
+  const int cur_step = (int)a.cur_pitch[search_level];
+  const uint8_t* ref = border + 11;
+  bool ok;
+  if (a.is_edgelet && a.is_edgelet[i]) {
+    const double g0 = a.ref_grad[2 * I], g1 = a.ref_grad[2 * I + 1];
+    double d0 = DA(DM(A00, g0), DM(A01, g1)), d1 = DA(DM(A10, g0), DM(A11, g1));
+    const double n = __dsqrt_rn(DA(DM(d0, d0), DM(d1, d1)));
+    d0 = DD(d0, n), d1 = DD(d1, n);
+    double h_inv;
+    ok = align1d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, (float)d0, (float)d1, u, v, h_inv);
+  } else {
+    ok = align2d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, u, v);
+  }
+  a.out_px[2 * I] = DM((double)u, scale);
+  a.out_px[2 * I + 1] = DM((double)v, scale);
+  a.out_success[i] = ok ? 1 : 0;
+}
+#undef DM
+#undef DA
+#undef DS
+#undef DD
+
 }  // namespace
+
+cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  match_direct_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t align1d_kernel_launch(const Align2DArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;

@@ -136,4 +136,31 @@ struct Align2DArgs {
 cudaError_t align2d_kernel_launch(const Align2DArgs& a, cudaStream_t s);
 cudaError_t align1d_kernel_launch(const Align2DArgs& a, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+struct MatchArgs {
+  int n, n_iter, n_pyr_levels, width, height;
+  double fx, fy, cx, cy;
+  const uint8_t* ref_img[PLSVO_MAX_LEVELS];  // device, [n_ref][rows_l][pitch_l]
+  uint32_t ref_pitch[PLSVO_MAX_LEVELS];
+  size_t ref_stride[PLSVO_MAX_LEVELS];
+  const uint8_t* cur_img[PLSVO_MAX_LEVELS];
+  uint32_t cur_pitch[PLSVO_MAX_LEVELS];
+  size_t cur_stride[PLSVO_MAX_LEVELS];
+  const double* T_ref_w;  // [n_ref][7]
+  const double* T_cur_w;  // [n_cur][7]
+  const int32_t* ref_index;
+  const int32_t* cur_index;
+  const double* ref_px;
+  const double* ref_f;
+  const int32_t* ref_level;
+  const uint8_t* is_edgelet;  // may be null
+  const double* ref_grad;     // may be null
+  const double* pos;
+  const double* px_cur;
+  double* out_px;
+  uint8_t* out_success;
+  int32_t* out_level;
+};
+cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s);
+
 }  // namespace plsvo

@@ -60,6 +60,8 @@ struct plsvo_ctx_impl {
       p_seg_level, p_seg_valid;
   DevBuf y_img;  // pyramid levels
   DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv, f_dir, f_ohinv;  // align2D / align1D
+  DevBuf m_ref_img, m_cur_img, m_T_ref, m_T_cur, m_ridx, m_cidx, m_px, m_f, m_lvl, m_edge, m_grad, m_pos, m_pxc, m_opx, m_osucc,
+      m_olvl;  // findMatchDirect
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
 };
@@ -184,7 +186,9 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
                     &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
-                    &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->p_T,
+                    &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->m_ref_img,   &c->m_cur_img,   &c->m_T_ref,     &c->m_T_cur,
+                    &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
+                    &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -959,4 +963,99 @@ extern "C" int plsvo_align1d_batch_run(plsvo_ctx* ctx, const plsvo_align1d_batch
   if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
   if (in->features.n_features > 0 && !in->dir) return fail(CTX(ctx), PLSVO_ERR_INVALID, "align1d directions missing");
   return feature_align_run(CTX(ctx), &in->features, in->dir, out->px, out->converged, out->h_inv);
+}
+
+namespace {
+// Copies the given pyramid levels of n_images frames to the device with 16-byte row pitch.
+int stage_pyramid(plsvo_ctx_impl* c, DevBuf& buf, const uint8_t* const* img, const size_t* pitch, const size_t* stride, int n_images,
+                  int width, int height, cudaStream_t s, const uint8_t** d_img, uint32_t* d_pitch, size_t* d_stride) {
+  size_t total = 0, off[PLSVO_MAX_LEVELS] = {0};
+  const size_t B = (size_t)n_images;
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    d_img[l] = nullptr, d_pitch[l] = 0, d_stride[l] = 0;
+    if (!img[l]) continue;
+    const int cols = width >> l, rows = height >> l;
+    if (cols <= 0 || rows <= 0 || pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "pyramid level geometry");
+    d_pitch[l] = (uint32_t)((cols + 15) / 16 * 16);
+    d_stride[l] = (size_t)rows * d_pitch[l];
+    total = (total + 255) / 256 * 256;
+    off[l] = total;
+    total += d_stride[l] * B;
+  }
+  CK(ensure(buf, total + 256));
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    if (!img[l]) continue;
+    const int cols = width >> l, rows = height >> l;
+    uint8_t* d = static_cast<uint8_t*>(buf.p) + off[l];
+    d_img[l] = d;
+    if (stride[l] == (size_t)rows * pitch[l]) {
+      CK(cudaMemcpy2DAsync(d, d_pitch[l], img[l], pitch[l], cols, (size_t)rows * B, cudaMemcpyHostToDevice, s));
+    } else {
+      for (size_t b = 0; b < B; ++b)
+        CK(cudaMemcpy2DAsync(d + b * d_stride[l], d_pitch[l], img[l] + b * stride[l], pitch[l], cols, rows, cudaMemcpyHostToDevice, s));
+    }
+  }
+  return PLSVO_OK;
+}
+}  // namespace
+
+extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (in->n_features < 0 || in->n_ref_images <= 0 || in->n_cur_images <= 0 || in->cam.width <= 0 || in->cam.height <= 0 ||
+      in->n_iter < 0 || in->n_pyr_levels < 1 || in->n_pyr_levels > PLSVO_MAX_LEVELS)
+    return fail(c, PLSVO_ERR_INVALID, "match batch description");
+  if (in->n_features == 0) return PLSVO_OK;
+  if (!in->T_ref_w || !in->T_cur_w || !in->ref_index || !in->cur_index || !in->ref_px || !in->ref_f || !in->ref_level || !in->pos ||
+      !in->px_cur || !out->px_cur || !out->success)
+    return fail(c, PLSVO_ERR_INVALID, "match arrays missing");
+  if (in->is_edgelet && !in->ref_grad) return fail(c, PLSVO_ERR_INVALID, "edgelets need ref_grad");
+  const size_t n = (size_t)in->n_features;
+  for (int l = 0; l < in->n_pyr_levels; ++l)
+    if (!in->cur_img[l]) return fail(c, PLSVO_ERR_INVALID, "current pyramid level missing below n_pyr_levels");
+  for (size_t i = 0; i < n; ++i) {
+    const int l = in->ref_level[i];
+    if (l < 0 || l >= PLSVO_MAX_LEVELS || !in->ref_img[l] || in->ref_index[i] < 0 || in->ref_index[i] >= in->n_ref_images ||
+        in->cur_index[i] < 0 || in->cur_index[i] >= in->n_cur_images)
+      return fail(c, PLSVO_ERR_INVALID, "match candidate refers to a missing level or frame");
+  }
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  MatchArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = in->n_features, a.n_iter = in->n_iter, a.n_pyr_levels = in->n_pyr_levels;
+  a.width = in->cam.width, a.height = in->cam.height;
+  a.fx = in->cam.fx, a.fy = in->cam.fy, a.cx = in->cam.cx, a.cy = in->cam.cy;
+  int rc = stage_pyramid(c, c->m_ref_img, in->ref_img, in->ref_pitch, in->ref_stride, in->n_ref_images, a.width, a.height, s, a.ref_img,
+                         a.ref_pitch, a.ref_stride);
+  if (rc != PLSVO_OK) return rc;
+  rc = stage_pyramid(c, c->m_cur_img, in->cur_img, in->cur_pitch, in->cur_stride, in->n_cur_images, a.width, a.height, s, a.cur_img,
+                     a.cur_pitch, a.cur_stride);
+  if (rc != PLSVO_OK) return rc;
+  CK(up(c->m_T_ref, in->T_ref_w, (size_t)in->n_ref_images * 7, s, &a.T_ref_w));
+  CK(up(c->m_T_cur, in->T_cur_w, (size_t)in->n_cur_images * 7, s, &a.T_cur_w));
+  CK(up(c->m_ridx, in->ref_index, n, s, &a.ref_index));
+  CK(up(c->m_cidx, in->cur_index, n, s, &a.cur_index));
+  CK(up(c->m_px, in->ref_px, n * 2, s, &a.ref_px));
+  CK(up(c->m_f, in->ref_f, n * 3, s, &a.ref_f));
+  CK(up(c->m_lvl, in->ref_level, n, s, &a.ref_level));
+  CK(up(c->m_edge, in->is_edgelet, n, s, &a.is_edgelet));
+  CK(up(c->m_grad, in->is_edgelet ? in->ref_grad : nullptr, n * 2, s, &a.ref_grad));
+  CK(up(c->m_pos, in->pos, n * 3, s, &a.pos));
+  CK(up(c->m_pxc, in->px_cur, n * 2, s, &a.px_cur));
+  CK(ensure(c->m_opx, n * 2 * sizeof(double)));
+  CK(ensure(c->m_osucc, n));
+  CK(ensure(c->m_olvl, n * sizeof(int32_t)));
+  a.out_px = static_cast<double*>(c->m_opx.p);
+  a.out_success = static_cast<uint8_t*>(c->m_osucc.p);
+  a.out_level = static_cast<int32_t*>(c->m_olvl.p);
+  CK(kernel_timer(c, 0, s));
+  CK(match_direct_kernel_launch(a, s));
+  CK(kernel_timer(c, 1, s));
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out->px_cur, a.out_px, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->success, a.out_success, n, cudaMemcpyDeviceToHost, s));
+  if (out->search_level) CK(cudaMemcpyAsync(out->search_level, a.out_level, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
 }

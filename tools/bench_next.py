@@ -172,6 +172,32 @@ def main():
             "algorithmic_bytes_upper_bound": alg, "achieved_gbs_upper_bound": alg / (k_ms * 1e-3) / 1e9,
             "roofline_frac_upper_bound": alg / (k_ms * 1e-3) / 1e9 / peak, "bit_exact_vs_oracle": bool(exact),
             "converged_frac": float(got[0].mean()), "cpu_oracle_features_per_s": rate, "cpu_threads": th}
+    # ---- Matcher::findMatchDirect (affine warp + patch + align) --------------------------------------------
+    m = args.features // 2
+    md = synth.make_match_batch(n=m, n_ref=8, n_cur=8, n_pyr_levels=3, seed=3, device=dev)
+    matcher = api.Matcher(10, ctx)
+    mo = {}
+
+    def run_m():
+        mo["gpu"] = matcher.findMatchDirect(md)
+
+    k_ms, e_ms = timed(ctx, run_m, args.reps)
+    olib.plsvo_oracle_match_direct_batch.restype = C.c_int
+    mb, keep_m = abi.make_match_batch(md)
+    cpu_out = abi.MatchOut(m)
+    rate, th = best_threads(lambda t: olib.plsvo_oracle_match_direct_batch(C.byref(mb), C.byref(cpu_out.struct), t), m)
+    fin = np.isfinite(cpu_out.px_cur).all(axis=1)
+    exact = (np.array_equal(mo["gpu"].success, cpu_out.success) and np.array_equal(mo["gpu"].search_level, cpu_out.search_level)
+             and np.array_equal(mo["gpu"].px_cur[fin], cpu_out.px_cur[fin]))
+    # per candidate: inputs 2 idx + level + flag (13) + px,f,grad,pos,px_cur (96) + outputs (21) = 130 B; the warp reads
+    # 100 x 4 reference bytes (bilinear taps, upper bound), align reads 81 B x iterations (upper bound n_iter)
+    alg = m * (130 + 400 + 81 * 10)
+    res["find_match_direct"] = {
+        "workload": f"{m} candidates, 8 keyframes -> 8 current VGA frames, 3 pyramid levels, 25 % edgelets (Matcher::findMatchDirect)",
+        "kernel_ms": k_ms, "e2e_ms": e_ms, "candidates_per_s_kernel": m / (k_ms * 1e-3), "candidates_per_s_e2e": m / (e_ms * 1e-3),
+        "algorithmic_bytes_upper_bound": alg, "achieved_gbs_upper_bound": alg / (k_ms * 1e-3) / 1e9,
+        "roofline_frac_upper_bound": alg / (k_ms * 1e-3) / 1e9 / peak, "bit_exact_vs_oracle": bool(exact),
+        "success_frac": float(cpu_out.success.mean()), "cpu_oracle_candidates_per_s": rate, "cpu_threads": th}
     print(json.dumps(res, indent=1))
 
 
