@@ -319,8 +319,43 @@ typedef struct plsvo_match_result {
 
 int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out);
 
+/* ---- Structure optimisation: Point::optimize / LineSeg::optimize ("next") ---
+ * Replaces, for a batch of 3D features, include/plsvo/feature3D.h:120,157 / src/feature3D_impl.cpp:36-95,
+ * 97-174 as driven by FrameHandlerBase::optimizeStructure (src/frame_handler_base.cpp:202-237):
+ *     void Point::optimize(const size_t n_iter);     void LineSeg::optimize(const size_t n_iter);
+ * 3x3 Gauss-Newton on the reprojection error (unit plane) of a 3D point over its observations obs_
+ * (a LineSeg optimises its two end points with a coupled accept/roll-back/convergence test).
+ * Observations are given in CSR form, in obs_ list order (the summation order of the reference). */
+typedef struct plsvo_structopt_batch {
+  int32_t n_points, n_segs, n_frames;
+  int32_t n_iter_pts;  /* Config::structureOptimNumIter() */
+  int32_t n_iter_segs; /* Config::structureOptimNumIterSegs() */
+  int32_t reserved;
+  const double* T_f_w;           /* [n_frames][7] (*it)->frame->T_f_w_ of the observing keyframes */
+  const int32_t* pt_obs_begin;   /* [n_points+1] offsets into pt_obs_* */
+  const int32_t* pt_obs_frame;   /* [n_pt_obs]   index into T_f_w */
+  const double* pt_obs_f;        /* [n_pt_obs][3] PointFeat::f */
+  const double* pt_pos;          /* [n_points][3] Point::pos_ on entry */
+  const int32_t* seg_obs_begin;  /* [n_segs+1] */
+  const int32_t* seg_obs_frame;  /* [n_seg_obs] */
+  const double* seg_obs_sf;      /* [n_seg_obs][3] LineFeat::sf */
+  const double* seg_obs_ef;      /* [n_seg_obs][3] LineFeat::ef */
+  const double* seg_spos;        /* [n_segs][3] LineSeg::spos_ on entry */
+  const double* seg_epos;        /* [n_segs][3] LineSeg::epos_ on entry */
+} plsvo_structopt_batch;
+
+typedef struct plsvo_structopt_result {
+  double* pt_pos;   /* [n_points][3] Point::pos_ on return */
+  double* seg_spos; /* [n_segs][3] */
+  double* seg_epos; /* [n_segs][3] */
+  int32_t* pt_iters;  /* [n_points] or NULL: GN iterations executed (diagnostic) */
+  int32_t* seg_iters; /* [n_segs] or NULL */
+} plsvo_structopt_result;
+
+int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_batch* in, const plsvo_structopt_result* out);
+
 /* device time (CUDA events on the context's stream) of the kernel launched by the last
- * plsvo_pyramid_batch_run / plsvo_align2d_batch_run / plsvo_align1d_batch_run call: the kernel alone,
+ * plsvo_pyramid / align2d / align1d / match_direct / structopt _batch_run call: the kernel alone,
  * without the host<->device copies those calls also make.  Measurement aid, no reference counterpart. */
 int plsvo_last_kernel_ms(plsvo_ctx* ctx, float* ms);
 

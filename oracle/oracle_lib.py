@@ -140,7 +140,7 @@ _ref_lib = None
 def build_ref(force: bool = False) -> str | None:
     """Build oracle/_ref/libplsvo_ref.so when the reference sources are present (authoring container only).
     Returns the path, or None when neither the sources nor a prebuilt library exist."""
-    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp")]
+    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp", "feature3D_impl.cpp")]
     if all(os.path.exists(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "ref", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
     return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
@@ -266,4 +266,30 @@ def ref_match_direct(abi, data):
     rc = lib.plsvo_ref_match_direct_batch(C.byref(b), C.byref(out.struct))
     if rc != 0:
         raise RuntimeError(f"reference match_direct failed rc={rc}")
+    return out
+
+
+def structopt(abi, data, n_threads: int = 1):
+    """Point::optimize / LineSeg::optimize restated -> abi.StructOptOut."""
+    lib = load(abi)
+    lib.plsvo_oracle_structopt_batch.restype = C.c_int
+    lib.plsvo_oracle_structopt_batch.argtypes = [C.POINTER(abi.StructOptBatch), C.POINTER(abi.StructOptResult), C.c_int]
+    b, keep = abi.make_structopt_batch(data)
+    out = abi.StructOptOut(b.n_points, b.n_segs)
+    rc = lib.plsvo_oracle_structopt_batch(C.byref(b), C.byref(out.struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle structopt failed rc={rc}")
+    return out
+
+
+def ref_structopt(abi, data):
+    """Point::optimize / LineSeg::optimize of the reference's own feature3D_impl.cpp -> abi.StructOptOut (iters not observable)."""
+    lib = load_ref(abi)
+    lib.plsvo_ref_structopt_batch.restype = C.c_int
+    lib.plsvo_ref_structopt_batch.argtypes = [C.POINTER(abi.StructOptBatch), C.POINTER(abi.StructOptResult)]
+    b, keep = abi.make_structopt_batch(data)
+    out = abi.StructOptOut(b.n_points, b.n_segs)
+    rc = lib.plsvo_ref_structopt_batch(C.byref(b), C.byref(out.struct))
+    if rc != 0:
+        raise RuntimeError(f"reference structopt failed rc={rc}")
     return out

@@ -1381,6 +1381,168 @@ int plsvo_oracle_match_direct_batch(const plsvo_match_batch* in, const plsvo_mat
   return PLSVO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Structure optimisation — Point::optimize (src/feature3D_impl.cpp:36-95), LineSeg::optimize (:97-174),
+// Point::jacobian_xyz2uv (include/plsvo/feature3D.h:126-140), Eigen 3x3 LDLT (same unblocked pivoted
+// algorithm as the 6x6 one above).
+// ------------------------------------------------------------------------------------------------
+struct Ldlt3 {
+  double m[3][3];
+  int tr[3];
+};
+static void ldlt3_compute(const double A[3][3], Ldlt3& f) {
+  const int n = 3;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) f.m[i][j] = A[i][j];
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double big = std::fabs(f.m[k][k]);
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(f.m[i][i]) > big) big = std::fabs(f.m[i][i]), piv = i;
+    f.tr[k] = piv;
+    if (piv != k) {
+      for (int j = 0; j < k; ++j) std::swap(f.m[k][j], f.m[piv][j]);
+      for (int i = piv + 1; i < n; ++i) std::swap(f.m[i][k], f.m[i][piv]);
+      std::swap(f.m[k][k], f.m[piv][piv]);
+      for (int i = k + 1; i < piv; ++i) std::swap(f.m[i][k], f.m[piv][i]);
+    }
+    if (k > 0) {
+      double temp[3];
+      for (int j = 0; j < k; ++j) temp[j] = f.m[j][j] * f.m[k][j];
+      double s = 0;
+      for (int j = 0; j < k; ++j) s += f.m[k][j] * temp[j];
+      f.m[k][k] -= s;
+      for (int i = k + 1; i < n; ++i) {
+        double s2 = 0;
+        for (int j = 0; j < k; ++j) s2 += f.m[i][j] * temp[j];
+        f.m[i][k] -= s2;
+      }
+    }
+    const double akk = f.m[k][k];
+    const bool pivot_is_valid = std::fabs(akk) > 0.0;
+    if (k == 0 && !pivot_is_valid) {
+      for (int j = 0; j < n; ++j) f.tr[j] = j;
+      return;
+    }
+    if (pivot_is_valid)
+      for (int i = k + 1; i < n; ++i) f.m[i][k] /= akk;
+  }
+}
+static void ldlt3_solve(const Ldlt3& f, const double b[3], double x[3]) {
+  const int n = 3;
+  for (int i = 0; i < n; ++i) x[i] = b[i];
+  for (int k = 0; k < n; ++k) std::swap(x[k], x[f.tr[k]]);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) x[i] -= f.m[i][j] * x[j];
+  const double tol = 1.0 / std::numeric_limits<double>::max();
+  for (int i = 0; i < n; ++i) {
+    if (std::fabs(f.m[i][i]) > tol)
+      x[i] /= f.m[i][i];
+    else
+      x[i] = 0.0;
+  }
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = i + 1; j < n; ++j) x[i] -= f.m[j][i] * x[j];
+  for (int k = n - 1; k >= 0; --k) std::swap(x[k], x[f.tr[k]]);
+}
+// one observation's contribution: A += J^T J, b -= J^T e, chi2 += |e|^2   (feature3D_impl.cpp:49-59)
+static void structopt_accumulate(const SE3& T, const double R[3][3], Vec3 pos, Vec3 f, double A[3][3], double b[3], double& chi2) {
+  const Vec3 p = se3_act(T, pos);
+  const double z_inv = 1.0 / p.z;
+  const double z_inv_sq = z_inv * z_inv;
+  // point_jac = -[[z_inv, 0, -x z_inv^2], [0, z_inv, -y z_inv^2]] * R_f_w
+  const double P[2][3] = {{-(z_inv), -(0.0), -(-p.x * z_inv_sq)}, {-(0.0), -(z_inv), -(-p.y * z_inv_sq)}};
+  double J[2][3];
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 3; ++c) J[r][c] = (P[r][0] * R[0][c] + P[r][1] * R[1][c]) + P[r][2] * R[2][c];
+  const double e0 = f.x / f.z - p.x / p.z, e1 = f.y / f.z - p.y / p.z;
+  chi2 += e0 * e0 + e1 * e1;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) A[r][c] += J[0][r] * J[0][c] + J[1][r] * J[1][c];
+  for (int r = 0; r < 3; ++r) b[r] -= J[0][r] * e0 + J[1][r] * e1;
+}
+static double norm_max3(const double x[3]) { return std::max(std::max(std::fabs(x[0]), std::fabs(x[1])), std::fabs(x[2])); }
+
+int plsvo_oracle_structopt_batch(const plsvo_structopt_batch* in, const plsvo_structopt_result* out, int n_threads) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  std::vector<SE3> T(in->n_frames);
+  std::vector<double> R((size_t)in->n_frames * 9);
+  for (int k = 0; k < in->n_frames; ++k) {
+    T[k] = se3_from_pose7(in->T_f_w + 7 * (size_t)k);
+    quat_to_matrix(T[k].q, reinterpret_cast<double(*)[3]>(R.data() + 9 * (size_t)k));
+  }
+  auto Rk = [&](int k) { return reinterpret_cast<const double(*)[3]>(R.data() + 9 * (size_t)k); };
+  const double kEps = 0.0000000001;  // plsvo::EPS, global.h:92
+  parallel_for(in->n_points, n_threads, [&](int i) {
+    Vec3 pos{in->pt_pos[3 * (size_t)i], in->pt_pos[3 * (size_t)i + 1], in->pt_pos[3 * (size_t)i + 2]};
+    Vec3 old_point = pos;
+    double chi2 = 0.0;
+    int iters = 0;
+    for (int it = 0; it < in->n_iter_pts; ++it) {
+      double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, b[3] = {0, 0, 0}, new_chi2 = 0.0;
+      for (int o = in->pt_obs_begin[i]; o < in->pt_obs_begin[i + 1]; ++o) {
+        const int k = in->pt_obs_frame[o];
+        structopt_accumulate(T[k], Rk(k), pos, Vec3{in->pt_obs_f[3 * (size_t)o], in->pt_obs_f[3 * (size_t)o + 1], in->pt_obs_f[3 * (size_t)o + 2]},
+                             A, b, new_chi2);
+      }
+      Ldlt3 f;
+      ldlt3_compute(A, f);
+      double dp[3];
+      ldlt3_solve(f, b, dp);
+      ++iters;
+      if ((it > 0 && new_chi2 > chi2) || std::isnan(dp[0])) {
+        pos = old_point;
+        break;
+      }
+      const Vec3 new_point{pos.x + dp[0], pos.y + dp[1], pos.z + dp[2]};
+      old_point = pos;
+      pos = new_point;
+      chi2 = new_chi2;
+      if (norm_max3(dp) <= kEps) break;
+    }
+    out->pt_pos[3 * (size_t)i] = pos.x, out->pt_pos[3 * (size_t)i + 1] = pos.y, out->pt_pos[3 * (size_t)i + 2] = pos.z;
+    if (out->pt_iters) out->pt_iters[i] = iters;
+  });
+  parallel_for(in->n_segs, n_threads, [&](int i) {
+    const size_t I = (size_t)i;
+    Vec3 sp{in->seg_spos[3 * I], in->seg_spos[3 * I + 1], in->seg_spos[3 * I + 2]};
+    Vec3 ep{in->seg_epos[3 * I], in->seg_epos[3 * I + 1], in->seg_epos[3 * I + 2]};
+    Vec3 old_s = sp, old_e = ep;
+    double chi2s = 0.0, chi2e = 0.0;
+    int iters = 0;
+    for (int it = 0; it < in->n_iter_segs; ++it) {
+      double As[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Ae[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      double bs[3] = {0, 0, 0}, be[3] = {0, 0, 0}, ns = 0.0, ne = 0.0;
+      for (int o = in->seg_obs_begin[i]; o < in->seg_obs_begin[i + 1]; ++o) {
+        const int k = in->seg_obs_frame[o];
+        const size_t O = (size_t)o;
+        structopt_accumulate(T[k], Rk(k), sp, Vec3{in->seg_obs_sf[3 * O], in->seg_obs_sf[3 * O + 1], in->seg_obs_sf[3 * O + 2]}, As, bs, ns);
+        structopt_accumulate(T[k], Rk(k), ep, Vec3{in->seg_obs_ef[3 * O], in->seg_obs_ef[3 * O + 1], in->seg_obs_ef[3 * O + 2]}, Ae, be, ne);
+      }
+      Ldlt3 fs, fe;
+      ldlt3_compute(As, fs);
+      ldlt3_compute(Ae, fe);
+      double dps[3], dpe[3];
+      ldlt3_solve(fs, bs, dps);
+      ldlt3_solve(fe, be, dpe);
+      ++iters;
+      if ((it > 0 && ns > chi2s) || std::isnan(dps[0]) || (it > 0 && ne > chi2e) || std::isnan(dpe[0])) {
+        sp = old_s, ep = old_e;
+        break;
+      }
+      const Vec3 new_s{sp.x + dps[0], sp.y + dps[1], sp.z + dps[2]};
+      old_s = sp, sp = new_s, chi2s = ns;
+      const Vec3 new_e{ep.x + dpe[0], ep.y + dpe[1], ep.z + dpe[2]};
+      old_e = ep, ep = new_e, chi2e = ne;
+      if (norm_max3(dps) <= kEps || norm_max3(dpe) <= kEps) break;
+    }
+    out->seg_spos[3 * I] = sp.x, out->seg_spos[3 * I + 1] = sp.y, out->seg_spos[3 * I + 2] = sp.z;
+    out->seg_epos[3 * I] = ep.x, out->seg_epos[3 * I + 1] = ep.y, out->seg_epos[3 * I + 2] = ep.z;
+    if (out->seg_iters) out->seg_iters[i] = iters;
+  });
+  return PLSVO_OK;
+}
+
 // Batch drivers over the ABI structs (CPU baseline of tools/bench_next.py): one call per feature, threads over features.
 int plsvo_oracle_align2d_batch(const plsvo_align2d_batch* in, const plsvo_align2d_result* out, int n_threads) {
   if (!in || !out) return PLSVO_ERR_INVALID;

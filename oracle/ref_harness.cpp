@@ -7,6 +7,7 @@
 //     /root/reference/src/sparse_img_align.cpp   /root/reference/src/pose_optimizer.cpp
 //     /root/reference/src/feature.cpp            /root/reference/src/feature_alignment.cpp
 //     /root/reference/src/matcher.cpp            /root/reference/src/config.cpp            
+//     /root/reference/src/feature3D_impl.cpp     (Point::optimize / LineSeg::optimize)
 // against the reference's own headers (/root/reference/include/plsvo/*.h) and the stand-in
 // third-party headers in oracle/refdeps/ (Eigen, Sophus, rpg_vikit, OpenCV core, boost — absent
 // from the image and from /root/reference), links this file, and writes oracle/_ref/libplsvo_ref.so.
@@ -62,12 +63,10 @@ bool Point::getCloseViewObs(const Vector3d&, Feature*& obs) const {
   obs = obs_.front();
   return true;
 }
-void Point::optimize(const size_t) {}
 
 LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos)
     : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {}
 bool LineSeg::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
-void LineSeg::optimize(const size_t) {}
 
 }  // namespace plsvo
 
@@ -356,8 +355,42 @@ int plsvo_ref_match_direct_batch(const plsvo_match_batch* in, const plsvo_match_
   return PLSVO_OK;
 }
 
+// Point::optimize / LineSeg::optimize (src/feature3D_impl.cpp:36-174) over CSR observation lists.
+int plsvo_ref_structopt_batch(const plsvo_structopt_batch* in, const plsvo_structopt_result* out) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  vk::PinholeCamera cam(640, 480, 300, 300, 320, 240);  // not read by optimize()
+  std::vector<FramePtr> frames;
+  for (int k = 0; k < in->n_frames; ++k) {
+    FramePtr f(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+    f->T_f_w_ = pose_from7(in->T_f_w + 7 * (size_t)k);
+    frames.push_back(f);
+  }
+  for (int i = 0; i < in->n_points; ++i) {
+    plsvo::Point pt(v3(in->pt_pos + 3 * (size_t)i));
+    std::vector<std::unique_ptr<plsvo::PointFeat>> obs;
+    for (int o = in->pt_obs_begin[i + 1] - 1; o >= in->pt_obs_begin[i]; --o) {  // addFrameRef pushes to the front
+      obs.emplace_back(new plsvo::PointFeat(frames[in->pt_obs_frame[o]].get(), &pt, Vector2d(0, 0), v3(in->pt_obs_f + 3 * (size_t)o), 0));
+      pt.addFrameRef(obs.back().get());
+    }
+    pt.optimize((size_t)in->n_iter_pts);
+    for (int k = 0; k < 3; ++k) out->pt_pos[3 * (size_t)i + k] = pt.pos_[k];
+  }
+  for (int i = 0; i < in->n_segs; ++i) {
+    plsvo::LineSeg ls(v3(in->seg_spos + 3 * (size_t)i), v3(in->seg_epos + 3 * (size_t)i));
+    std::vector<std::unique_ptr<plsvo::LineFeat>> obs;
+    for (int o = in->seg_obs_begin[i + 1] - 1; o >= in->seg_obs_begin[i]; --o) {
+      obs.emplace_back(new plsvo::LineFeat(frames[in->seg_obs_frame[o]].get(), &ls, Vector2d(0, 0), Vector2d(1, 0),
+                                           v3(in->seg_obs_sf + 3 * (size_t)o), v3(in->seg_obs_ef + 3 * (size_t)o), 0));
+      ls.addFrameRef(obs.back().get());
+    }
+    ls.optimize((size_t)in->n_iter_segs);
+    for (int k = 0; k < 3; ++k) out->seg_spos[3 * (size_t)i + k] = ls.spos_[k], out->seg_epos[3 * (size_t)i + k] = ls.epos_[k];
+  }
+  return PLSVO_OK;
+}
+
 const char* plsvo_ref_describe(void) {
-  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment,matcher,config}.cpp compiled unmodified against stand-in "
+  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment,matcher,config,feature3D_impl}.cpp compiled unmodified against stand-in "
          "Eigen/Sophus/vikit/OpenCV/boost headers (oracle/refdeps)";
 }
 }

@@ -172,6 +172,18 @@ class MatchBatch(C.Structure):
                 ("px_cur", _f64p)]
 
 
+class StructOptBatch(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("n_segs", C.c_int32), ("n_frames", C.c_int32), ("n_iter_pts", C.c_int32),
+                ("n_iter_segs", C.c_int32), ("reserved", C.c_int32), ("T_f_w", _f64p),
+                ("pt_obs_begin", _i32p), ("pt_obs_frame", _i32p), ("pt_obs_f", _f64p), ("pt_pos", _f64p),
+                ("seg_obs_begin", _i32p), ("seg_obs_frame", _i32p), ("seg_obs_sf", _f64p), ("seg_obs_ef", _f64p),
+                ("seg_spos", _f64p), ("seg_epos", _f64p)]
+
+
+class StructOptResult(C.Structure):
+    _fields_ = [("pt_pos", _f64p), ("seg_spos", _f64p), ("seg_epos", _f64p), ("pt_iters", _i32p), ("seg_iters", _i32p)]
+
+
 class MatchResult(C.Structure):
     _fields_ = [("px_cur", _f64p), ("success", _u8p), ("search_level", _i32p)]
 
@@ -342,6 +354,7 @@ ABI_SYMBOLS = [
     ("plsvo_align2d_batch_run", C.c_int, [C.c_void_p, _P(Align2DBatch), _P(Align2DResult)]),
     ("plsvo_align1d_batch_run", C.c_int, [C.c_void_p, _P(Align1DBatch), _P(Align1DResult)]),
     ("plsvo_match_direct_batch_run", C.c_int, [C.c_void_p, _P(MatchBatch), _P(MatchResult)]),
+    ("plsvo_structopt_batch_run", C.c_int, [C.c_void_p, _P(StructOptBatch), _P(StructOptResult)]),
     ("plsvo_last_kernel_ms", C.c_int, [C.c_void_p, _P(C.c_float)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
     ("plsvo_selftest_weight", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
@@ -420,3 +433,28 @@ class MatchOut:
         self.success = np.zeros(n, np.uint8)
         self.search_level = np.zeros(n, np.int32)
         self.struct = MatchResult(_ptr(self.px_cur, np.float64), _ptr(self.success, np.uint8), _ptr(self.search_level, np.int32))
+
+
+def make_structopt_batch(d):
+    """Build a plsvo_structopt_batch from a synth.StructOptData-like object.  Returns (struct, keepalive)."""
+    b = StructOptBatch()
+    b.n_points, b.n_segs, b.n_frames = d.pt_pos.shape[0], d.seg_spos.shape[0], d.T_f_w.shape[0]
+    b.n_iter_pts, b.n_iter_segs = d.n_iter_pts, d.n_iter_segs
+    b.T_f_w = _ptr(d.T_f_w, np.float64)
+    b.pt_obs_begin, b.pt_obs_frame = _ptr(d.pt_obs_begin, np.int32), _ptr(d.pt_obs_frame, np.int32)
+    b.pt_obs_f, b.pt_pos = _ptr(d.pt_obs_f, np.float64), _ptr(d.pt_pos, np.float64)
+    b.seg_obs_begin, b.seg_obs_frame = _ptr(d.seg_obs_begin, np.int32), _ptr(d.seg_obs_frame, np.int32)
+    b.seg_obs_sf, b.seg_obs_ef = _ptr(d.seg_obs_sf, np.float64), _ptr(d.seg_obs_ef, np.float64)
+    b.seg_spos, b.seg_epos = _ptr(d.seg_spos, np.float64), _ptr(d.seg_epos, np.float64)
+    return b, [d]
+
+
+class StructOptOut:
+    def __init__(self, n_points: int, n_segs: int):
+        self.pt_pos = np.zeros((n_points, 3))
+        self.seg_spos = np.zeros((n_segs, 3))
+        self.seg_epos = np.zeros((n_segs, 3))
+        self.pt_iters = np.zeros(n_points, np.int32)
+        self.seg_iters = np.zeros(n_segs, np.int32)
+        self.struct = StructOptResult(_ptr(self.pt_pos, np.float64), _ptr(self.seg_spos, np.float64), _ptr(self.seg_epos, np.float64),
+                                      _ptr(self.pt_iters, np.int32), _ptr(self.seg_iters, np.int32))

@@ -227,3 +227,13 @@ class Matcher:
         self.ctx.check(self.ctx.lib.plsvo_match_direct_batch_run(self.ctx.handle, C.byref(b), C.byref(out.struct)),
                        "plsvo_match_direct_batch_run")
         return out
+
+
+def optimizeStructure(data, ctx: Context | None = None) -> abi.StructOptOut:
+    """Batched Point::optimize / LineSeg::optimize (src/feature3D_impl.cpp:36-174) as FrameHandlerBase::optimizeStructure
+    (src/frame_handler_base.cpp:202-237) applies them: data = synth.StructOptData-like CSR observation lists."""
+    ctx = ctx or default_context()
+    b, keep = abi.make_structopt_batch(data)
+    out = abi.StructOptOut(b.n_points, b.n_segs)
+    ctx.check(ctx.lib.plsvo_structopt_batch_run(ctx.handle, C.byref(b), C.byref(out.struct)), "plsvo_structopt_batch_run")
+    return out

@@ -7,8 +7,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["align_kernel.cu", "poseopt_kernel.cu", "pyramid_kernel.cu", "align2d_kernel.cu", "plsvo_abi.cu"]
-HEADERS = ["device_math.cuh", "internal.h", os.path.join("..", "..", "include", "plsvo_b200.h")]
+SOURCES = ["align_kernel.cu", "poseopt_kernel.cu", "pyramid_kernel.cu", "align2d_kernel.cu", "structopt_kernel.cu", "plsvo_abi.cu"]
+HEADERS = ["device_math.cuh", "exact_math.cuh", "internal.h", os.path.join("..", "..", "include", "plsvo_b200.h")]
 OUT = os.path.join(CSRC, "libplsvo_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "exact_math.cuh"
 #include "internal.h"
 
 namespace plsvo {
@@ -259,60 +260,6 @@ __global__ void __launch_bounds__(kA2Threads) align1d_kernel(const Align2DArgs a
 // One thread per candidate.  The double-precision geometry is written with explicit round-to-nearest intrinsics
 // so that the compiler cannot contract a*b+c into an FMA: A_cur_ref, the search level, every byte of the warped
 // patch and therefore the refined position are bit-identical to the reference's scalar code.
-struct V3 {
-  double x, y, z;
-};
-struct Q4 {
-  double x, y, z, w;
-};
-struct Pose {
-  Q4 q;
-  V3 t;
-};
-#define DM(a, b) __dmul_rn((a), (b))
-#define DA(a, b) __dadd_rn((a), (b))
-#define DS(a, b) __dsub_rn((a), (b))
-#define DD(a, b) __ddiv_rn((a), (b))
-__device__ __forceinline__ V3 v_add(V3 a, V3 b) { return {DA(a.x, b.x), DA(a.y, b.y), DA(a.z, b.z)}; }
-__device__ __forceinline__ V3 v_sub(V3 a, V3 b) { return {DS(a.x, b.x), DS(a.y, b.y), DS(a.z, b.z)}; }
-__device__ __forceinline__ V3 v_scale(V3 a, double s) { return {DM(a.x, s), DM(a.y, s), DM(a.z, s)}; }
-__device__ __forceinline__ V3 v_cross(V3 a, V3 b) {
-  return {DS(DM(a.y, b.z), DM(a.z, b.y)), DS(DM(a.z, b.x), DM(a.x, b.z)), DS(DM(a.x, b.y), DM(a.y, b.x))};
-}
-__device__ __forceinline__ double v_norm(V3 a) { return __dsqrt_rn(DA(DA(DM(a.x, a.x), DM(a.y, a.y)), DM(a.z, a.z))); }
-__device__ __forceinline__ Q4 q_normalized(Q4 q) {  // Eigen: coeffs() /= coeffs().norm()
-  const double n = __dsqrt_rn(DA(DA(DA(DM(q.x, q.x), DM(q.y, q.y)), DM(q.z, q.z)), DM(q.w, q.w)));
-  return {DD(q.x, n), DD(q.y, n), DD(q.z, n), DD(q.w, n)};
-}
-__device__ __forceinline__ Q4 q_mul(Q4 a, Q4 b) {
-  return {DS(DA(DA(DM(a.w, b.x), DM(a.x, b.w)), DM(a.y, b.z)), DM(a.z, b.y)),
-          DS(DA(DA(DM(a.w, b.y), DM(a.y, b.w)), DM(a.z, b.x)), DM(a.x, b.z)),
-          DS(DA(DA(DM(a.w, b.z), DM(a.z, b.w)), DM(a.x, b.y)), DM(a.y, b.x)),
-          DS(DS(DS(DM(a.w, b.w), DM(a.x, b.x)), DM(a.y, b.y)), DM(a.z, b.z))};
-}
-__device__ __forceinline__ V3 q_rot(Q4 q, V3 v) {  // Eigen QuaternionBase::_transformVector
-  const V3 qv{q.x, q.y, q.z};
-  V3 uv = v_cross(qv, v);
-  uv = v_add(uv, uv);
-  return v_add(v_add(v, v_scale(uv, q.w)), v_cross(qv, uv));
-}
-__device__ __forceinline__ Pose pose_load(const double* p) {  // SO3(const Quaterniond&) normalises
-  return {q_normalized(Q4{p[0], p[1], p[2], p[3]}), V3{p[4], p[5], p[6]}};
-}
-__device__ __forceinline__ Pose pose_inverse(Pose a) {  // Sophus SE3::inverse
-  Pose r;
-  r.q = q_normalized(Q4{-a.q.x, -a.q.y, -a.q.z, a.q.w});
-  r.t = q_rot(r.q, v_scale(a.t, -1.0));
-  return r;
-}
-__device__ __forceinline__ Pose pose_mul(Pose a, Pose b) {  // SE3::operator*=
-  Pose r;
-  r.t = v_add(a.t, q_rot(a.q, b.t));
-  r.q = q_normalized(q_mul(a.q, b.q));
-  return r;
-}
-__device__ __forceinline__ V3 pose_act(Pose T, V3 p) { return v_add(q_rot(T.q, p), T.t); }
-
 __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArgs a) {
   __shared__ uint8_t s_border[kA2Threads][104];
   const int tid = threadIdx.x;
@@ -439,10 +386,6 @@ __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArg
   a.out_px[2 * I + 1] = DM((double)v, scale);
   a.out_success[i] = ok ? 1 : 0;
 }
-#undef DM
-#undef DA
-#undef DS
-#undef DD
 
 }  // namespace
 

@@ -163,4 +163,26 @@ struct MatchArgs {
 };
 cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+struct StructOptArgs {
+  int n_points, n_segs, n_iter_pts, n_iter_segs;
+  const double* T_f_w;
+  const int32_t* pt_obs_begin;
+  const int32_t* pt_obs_frame;
+  const double* pt_obs_f;
+  const double* pt_pos;
+  const int32_t* seg_obs_begin;
+  const int32_t* seg_obs_frame;
+  const double* seg_obs_sf;
+  const double* seg_obs_ef;
+  const double* seg_spos;
+  const double* seg_epos;
+  double* out_pt_pos;
+  double* out_seg_spos;
+  double* out_seg_epos;
+  int32_t* out_pt_iters;
+  int32_t* out_seg_iters;
+};
+cudaError_t structopt_kernel_launch(const StructOptArgs& a, cudaStream_t s);
+
 }  // namespace plsvo

@@ -62,6 +62,7 @@ struct plsvo_ctx_impl {
   DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv, f_dir, f_ohinv;  // align2D / align1D
   DevBuf m_ref_img, m_cur_img, m_T_ref, m_T_cur, m_ridx, m_cidx, m_px, m_f, m_lvl, m_edge, m_grad, m_pos, m_pxc, m_opx, m_osucc,
       m_olvl;  // findMatchDirect
+  DevBuf s_T, s_pb, s_pf, s_pof, s_pp, s_sb, s_sf, s_ssf, s_sef, s_sp, s_ep, s_out;  // structure optimisation
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
 };
@@ -188,7 +189,9 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
                     &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->m_ref_img,   &c->m_cur_img,   &c->m_T_ref,     &c->m_T_cur,
                     &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
-                    &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->p_T,
+                    &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
+                    &c->s_pp,        &c->s_sb,       &c->s_sf,        &c->s_ssf,        &c->s_sef,       &c->s_sp,
+                    &c->s_ep,        &c->s_out,      &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -1056,6 +1059,65 @@ extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_ba
   CK(cudaMemcpyAsync(out->px_cur, a.out_px, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(out->success, a.out_success, n, cudaMemcpyDeviceToHost, s));
   if (out->search_level) CK(cudaMemcpyAsync(out->search_level, a.out_level, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
+}
+
+extern "C" int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_batch* in, const plsvo_structopt_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (in->n_points < 0 || in->n_segs < 0 || in->n_frames <= 0 || in->n_iter_pts < 0 || in->n_iter_segs < 0 || !in->T_f_w)
+    return fail(c, PLSVO_ERR_INVALID, "structopt batch description");
+  if (in->n_points + in->n_segs == 0) return PLSVO_OK;
+  if (in->n_points > 0 && (!in->pt_obs_begin || !in->pt_pos || !out->pt_pos)) return fail(c, PLSVO_ERR_INVALID, "structopt point arrays missing");
+  if (in->n_segs > 0 && (!in->seg_obs_begin || !in->seg_spos || !in->seg_epos || !out->seg_spos || !out->seg_epos))
+    return fail(c, PLSVO_ERR_INVALID, "structopt segment arrays missing");
+  const size_t np = (size_t)in->n_points, ns = (size_t)in->n_segs;
+  const size_t npo = np ? (size_t)in->pt_obs_begin[np] : 0, nso = ns ? (size_t)in->seg_obs_begin[ns] : 0;
+  // observation lists: monotone offsets, frame indices in range
+  for (size_t i = 0; i < np; ++i)
+    if (in->pt_obs_begin[i] > in->pt_obs_begin[i + 1] || in->pt_obs_begin[i] < 0) return fail(c, PLSVO_ERR_INVALID, "pt_obs_begin not monotone");
+  for (size_t i = 0; i < ns; ++i)
+    if (in->seg_obs_begin[i] > in->seg_obs_begin[i + 1] || in->seg_obs_begin[i] < 0) return fail(c, PLSVO_ERR_INVALID, "seg_obs_begin not monotone");
+  if ((npo && (!in->pt_obs_frame || !in->pt_obs_f)) || (nso && (!in->seg_obs_frame || !in->seg_obs_sf || !in->seg_obs_ef)))
+    return fail(c, PLSVO_ERR_INVALID, "structopt observation arrays missing");
+  for (size_t o = 0; o < npo; ++o)
+    if (in->pt_obs_frame[o] < 0 || in->pt_obs_frame[o] >= in->n_frames) return fail(c, PLSVO_ERR_INVALID, "observation refers to a missing frame");
+  for (size_t o = 0; o < nso; ++o)
+    if (in->seg_obs_frame[o] < 0 || in->seg_obs_frame[o] >= in->n_frames) return fail(c, PLSVO_ERR_INVALID, "observation refers to a missing frame");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  StructOptArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_points = in->n_points, a.n_segs = in->n_segs, a.n_iter_pts = in->n_iter_pts, a.n_iter_segs = in->n_iter_segs;
+  CK(up(c->s_T, in->T_f_w, (size_t)in->n_frames * 7, s, &a.T_f_w));
+  CK(up(c->s_pb, in->pt_obs_begin, np ? np + 1 : 0, s, &a.pt_obs_begin));
+  CK(up(c->s_pf, in->pt_obs_frame, npo, s, &a.pt_obs_frame));
+  CK(up(c->s_pof, in->pt_obs_f, npo * 3, s, &a.pt_obs_f));
+  CK(up(c->s_pp, in->pt_pos, np * 3, s, &a.pt_pos));
+  CK(up(c->s_sb, in->seg_obs_begin, ns ? ns + 1 : 0, s, &a.seg_obs_begin));
+  CK(up(c->s_sf, in->seg_obs_frame, nso, s, &a.seg_obs_frame));
+  CK(up(c->s_ssf, in->seg_obs_sf, nso * 3, s, &a.seg_obs_sf));
+  CK(up(c->s_sef, in->seg_obs_ef, nso * 3, s, &a.seg_obs_ef));
+  CK(up(c->s_sp, in->seg_spos, ns * 3, s, &a.seg_spos));
+  CK(up(c->s_ep, in->seg_epos, ns * 3, s, &a.seg_epos));
+  CK(ensure(c->s_out, (np * 3 + ns * 6) * sizeof(double) + (np + ns) * sizeof(int32_t) + 64));
+  a.out_pt_pos = static_cast<double*>(c->s_out.p);
+  a.out_seg_spos = a.out_pt_pos + np * 3;
+  a.out_seg_epos = a.out_seg_spos + ns * 3;
+  a.out_pt_iters = reinterpret_cast<int32_t*>(a.out_seg_epos + ns * 3);
+  a.out_seg_iters = a.out_pt_iters + np;
+  CK(kernel_timer(c, 0, s));
+  CK(structopt_kernel_launch(a, s));
+  CK(kernel_timer(c, 1, s));
+  c->launches += 1;
+  if (np) CK(cudaMemcpyAsync(out->pt_pos, a.out_pt_pos, np * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (ns) {
+    CK(cudaMemcpyAsync(out->seg_spos, a.out_seg_spos, ns * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->seg_epos, a.out_seg_epos, ns * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  if (np && out->pt_iters) CK(cudaMemcpyAsync(out->pt_iters, a.out_pt_iters, np * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (ns && out->seg_iters) CK(cudaMemcpyAsync(out->seg_iters, a.out_seg_iters, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
 }

@@ -531,3 +531,73 @@ def make_match_batch(cam: Camera = VGA, n: int = 2000, n_ref: int = 3, n_cur: in
                      T_cur_w=c(T_cur_w, np.float64), ref_index=ref_index, cur_index=cur_index, ref_px=c(ref_px, np.float64),
                      ref_f=c(ref_f, np.float64), ref_level=ref_level, is_edgelet=is_edgelet, ref_grad=c(ref_grad, np.float64),
                      pos=c(pos, np.float64), px_cur=c(px_cur, np.float64), px_cur_gt=c(px_gt, np.float64))
+
+
+# ---- structure optimisation: Point::optimize / LineSeg::optimize -------------------
+@dataclass
+class StructOptData:
+    """Host arrays of one structure-optimisation batch, shaped as plsvo_structopt_batch describes."""
+
+    T_f_w: np.ndarray
+    pt_obs_begin: np.ndarray
+    pt_obs_frame: np.ndarray
+    pt_obs_f: np.ndarray
+    pt_pos: np.ndarray
+    pt_pos_gt: np.ndarray
+    seg_obs_begin: np.ndarray
+    seg_obs_frame: np.ndarray
+    seg_obs_sf: np.ndarray
+    seg_obs_ef: np.ndarray
+    seg_spos: np.ndarray
+    seg_epos: np.ndarray
+    seg_spos_gt: np.ndarray
+    seg_epos_gt: np.ndarray
+    n_iter_pts: int = 5
+    n_iter_segs: int = 5
+
+
+def make_structopt_batch(n_points: int = 2000, n_segs: int = 500, n_frames: int = 12, max_obs: int = 10, seed: int = 8000,
+                         noise: float = 1e-3, pert: float = 0.05, cam: Camera = VGA) -> StructOptData:
+    """3D points / segments around z ~ 2 observed from n_frames keyframes on a small baseline; observations are unit
+    bearing vectors of the true position with unit-plane noise `noise`; the entry position is perturbed by `pert`.
+    A few features get a single observation (rank-deficient normal equations) or coincident views."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xi = np.concatenate([rng.uniform(-0.4, 0.4, (n_frames, 3)) * [1, 1, 0.2], rng.uniform(-0.05, 0.05, (n_frames, 3))], -1)
+    R, t = se3_exp_Rt(torch.tensor(xi, dtype=torch.float64))
+    T = pose7_from_Rt(R, t).numpy()
+    R, t = R.numpy(), t.numpy()
+
+    def observe(P, frames):  # P [3], frames [k] -> unit bearings [k,3]
+        pc = (R[frames] @ P) + t[frames]
+        uv = pc[:, :2] / pc[:, 2:3] + rng.normal(0, noise, (len(frames), 2))
+        d = np.concatenate([uv, np.ones((len(frames), 1))], -1)
+        return d / np.linalg.norm(d, axis=-1, keepdims=True)
+
+    def world_points(n):
+        return np.stack([rng.uniform(-1.2, 1.2, n), rng.uniform(-0.9, 0.9, n), rng.uniform(1.5, 3.0, n)], -1)
+
+    def csr(n, gt_list):
+        begin, frame, obs = [0], [], [[] for _ in gt_list]
+        for i in range(n):
+            k = int(rng.integers(2, max_obs + 1))
+            if i % 97 == 5:
+                k = 1  # single observation: singular A, the pivoted LDLT still returns a step
+            fr = rng.choice(n_frames, size=min(k, n_frames), replace=False)
+            if i % 97 == 11:
+                fr = np.repeat(fr[:1], 3)  # the same view three times
+            frame.extend(fr.tolist())
+            for g, o in zip(gt_list, obs):
+                o.append(observe(g[i], fr))
+            begin.append(len(frame))
+        return (np.asarray(begin, np.int32), np.asarray(frame, np.int32), [np.ascontiguousarray(np.concatenate(o, 0)) for o in obs])
+
+    P = world_points(n_points)
+    pb, pf, (pobs,) = csr(n_points, [P])
+    S, E = world_points(n_segs), None
+    E = S + rng.uniform(-0.3, 0.3, (n_segs, 3)) * [1, 1, 0.3]
+    sb, sf_, (sobs, eobs) = csr(n_segs, [S, E])
+    c = np.ascontiguousarray
+    return StructOptData(T_f_w=c(T), pt_obs_begin=pb, pt_obs_frame=pf, pt_obs_f=pobs, pt_pos=c(P + rng.normal(0, pert, P.shape)),
+                         pt_pos_gt=c(P), seg_obs_begin=sb, seg_obs_frame=sf_, seg_obs_sf=sobs, seg_obs_ef=eobs,
+                         seg_spos=c(S + rng.normal(0, pert, S.shape)), seg_epos=c(E + rng.normal(0, pert, E.shape)),
+                         seg_spos_gt=c(S), seg_epos_gt=c(E))

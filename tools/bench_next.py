@@ -198,6 +198,32 @@ def main():
         "algorithmic_bytes_upper_bound": alg, "achieved_gbs_upper_bound": alg / (k_ms * 1e-3) / 1e9,
         "roofline_frac_upper_bound": alg / (k_ms * 1e-3) / 1e9 / peak, "bit_exact_vs_oracle": bool(exact),
         "success_frac": float(cpu_out.success.mean()), "cpu_oracle_candidates_per_s": rate, "cpu_threads": th}
+    # ---- structure optimisation (Point::optimize / LineSeg::optimize) ------------------------------------
+    sd = synth.make_structopt_batch(n_points=200000, n_segs=50000, n_frames=32, seed=4)
+    so = {}
+
+    def run_s():
+        so["gpu"] = api.optimizeStructure(sd, ctx)
+
+    k_ms, e_ms = timed(ctx, run_s, args.reps)
+    olib.plsvo_oracle_structopt_batch.restype = C.c_int
+    sb, keep_s = abi.make_structopt_batch(sd)
+    cpu_s = abi.StructOptOut(sb.n_points, sb.n_segs)
+    nfeat = sb.n_points + sb.n_segs
+    rate, th = best_threads(lambda t: olib.plsvo_oracle_structopt_batch(C.byref(sb), C.byref(cpu_s.struct), t), nfeat)
+    exact = (np.array_equal(so["gpu"].pt_pos, cpu_s.pt_pos) and np.array_equal(so["gpu"].seg_spos, cpu_s.seg_spos)
+             and np.array_equal(so["gpu"].seg_epos, cpu_s.seg_epos) and np.array_equal(so["gpu"].pt_iters, cpu_s.pt_iters))
+    n_pt_obs, n_seg_obs = int(sd.pt_obs_begin[-1]), int(sd.seg_obs_begin[-1])
+    # per executed iteration an observation costs its frame index + bearing(s) + the 56-byte pose (re-read, L2-resident)
+    passes_pt = float(cpu_s.pt_iters.mean()), float(cpu_s.seg_iters.mean())
+    alg = (n_pt_obs * (4 + 24 + 56) * passes_pt[0] + n_seg_obs * (4 + 48 + 56) * passes_pt[1]
+           + sb.n_points * (24 + 24 + 8) + sb.n_segs * (48 + 48 + 8))
+    res["structure_optimisation"] = {
+        "workload": f"{sb.n_points} points ({n_pt_obs} observations) + {sb.n_segs} segments ({n_seg_obs} observations), 32 keyframes, "
+                    "5 GN iterations (Point::optimize / LineSeg::optimize)",
+        "kernel_ms": k_ms, "e2e_ms": e_ms, "features_per_s_kernel": nfeat / (k_ms * 1e-3), "features_per_s_e2e": nfeat / (e_ms * 1e-3),
+        "algorithmic_bytes": alg, "achieved_gbs": alg / (k_ms * 1e-3) / 1e9, "roofline_frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+        "bit_exact_vs_oracle": bool(exact), "mean_iterations": passes_pt, "cpu_oracle_features_per_s": rate, "cpu_threads": th}
     print(json.dumps(res, indent=1))
 
 
