@@ -589,7 +589,8 @@ def make_structopt_batch(n_points: int = 2000, n_segs: int = 500, n_frames: int 
             for g, o in zip(gt_list, obs):
                 o.append(observe(g[i], fr))
             begin.append(len(frame))
-        return (np.asarray(begin, np.int32), np.asarray(frame, np.int32), [np.ascontiguousarray(np.concatenate(o, 0)) for o in obs])
+        cat = lambda o: np.ascontiguousarray(np.concatenate(o, 0)) if o else np.zeros((0, 3))  # noqa: E731
+        return (np.asarray(begin, np.int32), np.asarray(frame, np.int32), [cat(o) for o in obs])
 
     P = world_points(n_points)
     pb, pf, (pobs,) = csr(n_points, [P])
