@@ -20,6 +20,14 @@ namespace {
 
 constexpr int kA2Threads = 128;
 
+// Exact u8 -> f32 and (u8 - u8) -> f32 without the conversion unit: 0x4B000000 | v is the float 2^23 + v, so one
+// FADD gives v exactly; differences of two such values (|d| <= 255) and their halves are exact as well, i.e. the
+// same numbers as the reference's int -> float / double conversions, produced on the FMA pipe instead of XU.
+__device__ __forceinline__ float u8f(uint8_t v) { return __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)v), 8388608.0f); }
+__device__ __forceinline__ float u8diff(uint8_t a, uint8_t b) {
+  return __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)a), __uint_as_float(0x4B000000u | (uint32_t)b));
+}
+
 // align2D on one feature.  border = 10x10 reference patch with border, ref = 8x8 reference patch with row step
 // ref_step (8 for a packed patch, 10 when it is the interior of `border`).  u,v in/out; returns `converged`.
 __device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_t* ref, const int ref_step, const uint8_t* img,
@@ -30,8 +38,8 @@ __device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_
   for (int y = 0; y < 8; ++y) {
     const uint8_t* it = border + (y + 1) * 10 + 1;
     for (int x = 0; x < 8; ++x, ++it) {
-      const float J0 = (float)(0.5 * (double)((int)it[1] - (int)it[-1]));
-      const float J1 = (float)(0.5 * (double)((int)it[10] - (int)it[-10]));
+      const float J0 = __fmul_rn(0.5f, u8diff(it[1], it[-1]));
+      const float J1 = __fmul_rn(0.5f, u8diff(it[10], it[-10]));
       H00 = __fadd_rn(H00, __fmul_rn(J0, J0));
       H01 = __fadd_rn(H01, __fmul_rn(J0, J1));
       H02 = __fadd_rn(H02, J0);
@@ -82,12 +90,12 @@ __device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_
 #pragma unroll
       for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
         const float search_pixel =
-            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, (float)row[x]), __fmul_rn(wTR, (float)row[x + 1])),
-                                __fmul_rn(wBL, (float)row[x + cur_step])),
-                      __fmul_rn(wBR, (float)row[x + cur_step + 1]));
-        const float res = __fadd_rn(__fsub_rn(search_pixel, (float)*it_ref), mean_diff);
-        const float dx = (float)(0.5 * (double)((int)itb[1] - (int)itb[-1]));
-        const float dy = (float)(0.5 * (double)((int)itb[10] - (int)itb[-10]));
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, u8f(row[x])), __fmul_rn(wTR, u8f(row[x + 1]))),
+                                __fmul_rn(wBL, u8f(row[x + cur_step]))),
+                      __fmul_rn(wBR, u8f(row[x + cur_step + 1])));
+        const float res = __fadd_rn(__fsub_rn(search_pixel, u8f(*it_ref)), mean_diff);
+        const float dx = __fmul_rn(0.5f, u8diff(itb[1], itb[-1]));
+        const float dy = __fmul_rn(0.5f, u8diff(itb[10], itb[-10]));
         J0 = __fsub_rn(J0, __fmul_rn(res, dx));
         J1 = __fsub_rn(J1, __fmul_rn(res, dy));
         J2 = __fsub_rn(J2, res);
@@ -114,9 +122,9 @@ __device__ __forceinline__ bool align1d_core(const uint8_t* border, const uint8_
                                              const float d1, float& u, float& v, double& h_inv) {
   // directional template derivative (:63-66): J0 = 0.5*(dir0*(I[x+1]-I[x-1]) + dir1*(I[y+1]-I[y-1])) in float, J1 = 1
   auto dv_at = [&](const uint8_t* it) {
-    const float gx = __fmul_rn(d0, (float)((int)it[1] - (int)it[-1]));
-    const float gy = __fmul_rn(d1, (float)((int)it[10] - (int)it[-10]));
-    return (float)(0.5 * (double)__fadd_rn(gx, gy));
+    const float gx = __fmul_rn(d0, u8diff(it[1], it[-1]));
+    const float gy = __fmul_rn(d1, u8diff(it[10], it[-10]));
+    return __fmul_rn(0.5f, __fadd_rn(gx, gy));
   };
   float H00 = 0, H01 = 0, H11 = 0;
   for (int y = 0; y < 8; ++y) {
@@ -157,10 +165,10 @@ __device__ __forceinline__ bool align1d_core(const uint8_t* border, const uint8_
 #pragma unroll
       for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
         const float search_pixel =
-            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, (float)row[x]), __fmul_rn(wTR, (float)row[x + 1])),
-                                __fmul_rn(wBL, (float)row[x + cur_step])),
-                      __fmul_rn(wBR, (float)row[x + cur_step + 1]));
-        const float res = __fadd_rn(__fsub_rn(search_pixel, (float)*it_ref), mean_diff);
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, u8f(row[x])), __fmul_rn(wTR, u8f(row[x + 1]))),
+                                __fmul_rn(wBL, u8f(row[x + cur_step]))),
+                      __fmul_rn(wBR, u8f(row[x + cur_step + 1])));
+        const float res = __fadd_rn(__fsub_rn(search_pixel, u8f(*it_ref)), mean_diff);
         J0 = __fsub_rn(J0, __fmul_rn(res, dv_at(itb)));
         J1 = __fsub_rn(J1, res);
         new_chi2 = __fadd_rn(new_chi2, __fmul_rn(res, res));
@@ -186,8 +194,8 @@ __device__ __forceinline__ bool align1d_core(const uint8_t* border, const uint8_
 }
 
 __global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a) {
-  __shared__ uint8_t s_border[kA2Threads][104];  // 100 used (+4 pad keeps rows word aligned)
-  __shared__ uint8_t s_ref[kA2Threads][64];
+  __shared__ __align__(4) uint8_t s_border[kA2Threads][108];  // 100 used; 27-word pitch (odd) keeps the threads of a warp on distinct banks
+  __shared__ __align__(4) uint8_t s_ref[kA2Threads][68];  // 64 used; 17-word pitch (odd): no bank conflicts
   const int tid = threadIdx.x;
   const int i = blockIdx.x * kA2Threads + tid;
   const bool active = i < a.n;
@@ -221,8 +229,8 @@ __global__ void __launch_bounds__(kA2Threads) align2d_kernel(const Align2DArgs a
 // (edgelets), 1 DoF + mean intensity offset, with the reference's chi2 back-off.  Same layout and
 // the same bit-exact fp32 sequencing as align2d_kernel.
 __global__ void __launch_bounds__(kA2Threads) align1d_kernel(const Align2DArgs a) {
-  __shared__ uint8_t s_border[kA2Threads][104];
-  __shared__ uint8_t s_ref[kA2Threads][64];
+  __shared__ __align__(4) uint8_t s_border[kA2Threads][108];  // 100 used; 27-word pitch (odd) keeps the threads of a warp on distinct banks
+  __shared__ __align__(4) uint8_t s_ref[kA2Threads][68];  // 64 used; 17-word pitch (odd): no bank conflicts
   const int tid = threadIdx.x;
   const int i = blockIdx.x * kA2Threads + tid;
   if (i >= a.n) return;
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(kA2Threads) align1d_kernel(const Align2DArgs a
 // so that the compiler cannot contract a*b+c into an FMA: A_cur_ref, the search level, every byte of the warped
 // patch and therefore the refined position are bit-identical to the reference's scalar code.
 __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArgs a) {
-  __shared__ uint8_t s_border[kA2Threads][104];
+  __shared__ __align__(4) uint8_t s_border[kA2Threads][108];  // 100 used; 27-word pitch (odd) keeps the threads of a warp on distinct banks
   const int tid = threadIdx.x;
   const int i = blockIdx.x * kA2Threads + tid;
   if (i >= a.n) return;
@@ -354,9 +362,9 @@ __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArg
             const float w10 = __fmul_rn(sx, __fsub_rn(1.0f, sy));
             const float w11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, w00), w01), w10);
             const uint8_t* ptr = img + (size_t)iy * stride + ix;
-            const float I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, (float)ptr[0]), __fmul_rn(w01, (float)ptr[stride])),
-                                                __fmul_rn(w10, (float)ptr[1])),
-                                      __fmul_rn(w11, (float)ptr[stride + 1]));
+            const float I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, u8f(ptr[0])), __fmul_rn(w01, u8f(ptr[stride]))),
+                                                __fmul_rn(w10, u8f(ptr[1]))),
+                                      __fmul_rn(w11, u8f(ptr[stride + 1])));
             val = (uint8_t)I;
           }
         }

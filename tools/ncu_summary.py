@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Text summary of one .ncu-rep capture (raw page): duration, DRAM traffic, issue/occupancy, pipes, stall mix.
-Usage: python tools/ncu_summary.py <file.ncu-rep> [title]"""
+Usage: python tools/ncu_summary.py <file.ncu-rep> [title] [kernel-name substring: the LAST matching launch is summarised]"""
 import csv
 import subprocess
 import sys
@@ -10,6 +10,12 @@ title = sys.argv[2] if len(sys.argv) > 2 else rep
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
+if len(sys.argv) > 3:
+    ki = hdr.index("Kernel Name")
+    match = [r for r in rows[2:] if len(r) > ki and sys.argv[3] in r[ki]]
+    if not match:
+        sys.exit(f"no launch of a kernel matching {sys.argv[3]!r} in {rep}")
+    vals = match[-1]
 d = dict(zip(hdr, vals))
 u = dict(zip(hdr, units))
 
