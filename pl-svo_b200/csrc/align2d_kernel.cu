@@ -28,6 +28,23 @@ __device__ __forceinline__ float u8diff(uint8_t a, uint8_t b) {
   return __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)a), __uint_as_float(0x4B000000u | (uint32_t)b));
 }
 
+// Nine consecutive image bytes starting at an arbitrary address, as exact floats: three aligned 32-bit loads and
+// two funnel shifts instead of nine byte loads (the image buffers are 256-byte aligned with 256 bytes of slack, so
+// the aligned window never leaves the allocation).  Byte -> float through PRMT + FADD (see u8f).
+__device__ __forceinline__ float bytef(uint32_t w, int k) {
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | k)), 8388608.0f);
+}
+__device__ __forceinline__ void load_row9(const uint8_t* p, float f[9]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  const uint32_t lo = __funnelshift_r(w0, w1, sh), mid = __funnelshift_r(w1, w2, sh), hi = w2 >> sh;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) f[k] = bytef(lo, k), f[4 + k] = bytef(mid, k);
+  f[8] = bytef(hi, 0);
+}
+
 // align2D on one feature.  border = 10x10 reference patch with border, ref = 8x8 reference patch with row step
 // ref_step (8 for a packed patch, 10 when it is the interior of `border`).  u,v in/out; returns `converged`.
 __device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_t* ref, const int ref_step, const uint8_t* img,
@@ -84,15 +101,19 @@ __device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_
     float J0 = 0.f, J1 = 0.f, J2 = 0.f;
     const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
     const uint8_t* ref_row = ref;
-    for (int y = 0; y < 8; ++y, row += cur_step, ref_row += ref_step) {
+    float top[9], bot[9];
+    load_row9(row, top);
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y, ref_row += ref_step) {
+      row += cur_step;
+      load_row9(row, bot);
       const uint8_t* itb = border + (y + 1) * 10 + 1;
       const uint8_t* it_ref = ref_row;
 #pragma unroll
       for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
         const float search_pixel =
-            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, u8f(row[x])), __fmul_rn(wTR, u8f(row[x + 1]))),
-                                __fmul_rn(wBL, u8f(row[x + cur_step]))),
-                      __fmul_rn(wBR, u8f(row[x + cur_step + 1])));
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, top[x]), __fmul_rn(wTR, top[x + 1])), __fmul_rn(wBL, bot[x])),
+                      __fmul_rn(wBR, bot[x + 1]));
         const float res = __fadd_rn(__fsub_rn(search_pixel, u8f(*it_ref)), mean_diff);
         const float dx = __fmul_rn(0.5f, u8diff(itb[1], itb[-1]));
         const float dy = __fmul_rn(0.5f, u8diff(itb[10], itb[-10]));
@@ -100,6 +121,8 @@ __device__ __forceinline__ bool align2d_core(const uint8_t* border, const uint8_
         J1 = __fsub_rn(J1, __fmul_rn(res, dy));
         J2 = __fsub_rn(J2, res);
       }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) top[k] = bot[k];
     }
     // update = Hinv * Jres
     const float up0 = __fadd_rn(__fadd_rn(__fmul_rn(I00, J0), __fmul_rn(I01, J1)), __fmul_rn(I02, J2));
@@ -159,20 +182,26 @@ __device__ __forceinline__ bool align1d_core(const uint8_t* border, const uint8_
     float J0 = 0.f, J1 = 0.f, new_chi2 = 0.f;
     const uint8_t* row = img + (size_t)(vi - 4) * cur_step + (ui - 4);
     const uint8_t* ref_row = ref;
-    for (int y = 0; y < 8; ++y, row += cur_step, ref_row += ref_step) {
+    float top[9], bot[9];
+    load_row9(row, top);
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y, ref_row += ref_step) {
+      row += cur_step;
+      load_row9(row, bot);
       const uint8_t* itb = border + (y + 1) * 10 + 1;
       const uint8_t* it_ref = ref_row;
 #pragma unroll
       for (int x = 0; x < 8; ++x, ++it_ref, ++itb) {
         const float search_pixel =
-            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, u8f(row[x])), __fmul_rn(wTR, u8f(row[x + 1]))),
-                                __fmul_rn(wBL, u8f(row[x + cur_step]))),
-                      __fmul_rn(wBR, u8f(row[x + cur_step + 1])));
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, top[x]), __fmul_rn(wTR, top[x + 1])), __fmul_rn(wBL, bot[x])),
+                      __fmul_rn(wBR, bot[x + 1]));
         const float res = __fadd_rn(__fsub_rn(search_pixel, u8f(*it_ref)), mean_diff);
         J0 = __fsub_rn(J0, __fmul_rn(res, dv_at(itb)));
         J1 = __fsub_rn(J1, res);
         new_chi2 = __fadd_rn(new_chi2, __fmul_rn(res, res));
       }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) top[k] = bot[k];
     }
     if (iter > 0 && new_chi2 > chi2) {  // :124-132 (the back-off subtracts the raw update, as the reference does)
       u = __fsub_rn(u, up0);
