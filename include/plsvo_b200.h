@@ -354,8 +354,72 @@ typedef struct plsvo_structopt_result {
 
 int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_batch* in, const plsvo_structopt_result* out);
 
+/* ---- Depth-filter point-seed update ("next") ------------------------------
+ * Replaces, for n point seeds at once, the body of DepthFilter::updatePointSeeds (src/depth_filter.cpp:270-365):
+ * visibility test of the seed in the current frame (:291-304), inverse-depth search range (:307-308),
+ *     bool Matcher::findEpipolarMatchDirect(ref_frame, cur_frame, ref_ftr, d_estimate, d_min, d_max, depth)
+ * (include/plsvo/matcher.h, src/matcher.cpp:277-420: epipolar segment, affine warp, edgelet pre-selection, ZMSSD
+ * search along the epipolar line or direct alignment when it is shorter than 2 px, sub-pixel align2D/align1D,
+ * depthFromTriangulation :135-146), DepthFilter::computeTau (:568-584) and the Gaussian x Beta update
+ * DepthFilter::updatePointSeed (:489-512, Vogiatzis & Hernandez 2011).  The list logic around it (seed ageing,
+ * creating a Point from a converged seed, the detector's occupancy grid) stays on the host; `converged` reports
+ * the reference's test sqrt(sigma2) < z_range / seed_convergence_sigma2_thresh (:334).
+ * Images must be dense (pitch == width of the level): the reference indexes the ZMSSD patch with Mat::cols (:380-382). */
+typedef struct plsvo_seed_batch {
+  int32_t n_seeds;
+  int32_t n_ref_images;
+  int32_t n_cur_images;
+  int32_t n_pyr_levels;          /* Config::nPyrLevels() */
+  int32_t n_iter;                /* Matcher::Options::align_max_iter (10) */
+  int32_t max_epi_search_steps;  /* Matcher::Options::max_epi_search_steps (1000) */
+  uint8_t align_1d;              /* Matcher::Options::align_1d (false) */
+  uint8_t subpix_refinement;     /* Matcher::Options::subpix_refinement (true) */
+  uint8_t epi_search_edgelet_filtering; /* (true) */
+  uint8_t reserved0[5];
+  double epi_search_edgelet_max_angle;   /* (0.7) */
+  double seed_convergence_sigma2_thresh; /* DepthFilter::Options (200.0) */
+  plsvo_camera cam;
+  const uint8_t* ref_img[PLSVO_MAX_LEVELS];
+  size_t ref_pitch[PLSVO_MAX_LEVELS];
+  size_t ref_stride[PLSVO_MAX_LEVELS];
+  const uint8_t* cur_img[PLSVO_MAX_LEVELS];
+  size_t cur_pitch[PLSVO_MAX_LEVELS];
+  size_t cur_stride[PLSVO_MAX_LEVELS];
+  const double* T_ref_w;     /* [n_ref_images][7] it->ftr->frame->T_f_w_ */
+  const double* T_cur_w;     /* [n_cur_images][7] frame->T_f_w_ */
+  const int32_t* ref_index;  /* [n] */
+  const int32_t* cur_index;  /* [n] */
+  const double* ref_px;      /* [n][2] it->ftr->px */
+  const double* ref_f;       /* [n][3] it->ftr->f */
+  const int32_t* ref_level;  /* [n]    it->ftr->level */
+  const uint8_t* is_edgelet; /* [n] or NULL */
+  const double* ref_grad;    /* [n][2] or NULL */
+  const float* a;            /* [n] PointSeed::a on entry */
+  const float* b;            /* [n] */
+  const float* mu;           /* [n] inverse depth mean */
+  const float* z_range;      /* [n] */
+  const float* sigma2;       /* [n] */
+} plsvo_seed_batch;
+
+#define PLSVO_SEED_NOT_VISIBLE 0 /* behind the camera / outside the image: seed untouched (:296-304) */
+#define PLSVO_SEED_NO_MATCH 1    /* findEpipolarMatchDirect failed: b += 1 (:312-317) */
+#define PLSVO_SEED_UPDATED 2     /* Bayesian update applied (:320-325) */
+
+typedef struct plsvo_seed_result {
+  float* a;           /* [n] PointSeed state on return */
+  float* b;
+  float* mu;
+  float* sigma2;
+  int32_t* status;    /* [n] PLSVO_SEED_* */
+  uint8_t* converged; /* [n] */
+  double* depth;      /* [n] z of findEpipolarMatchDirect (NaN unless status == UPDATED) */
+  double* px_cur;     /* [n][2] Matcher::px_cur_ (diagnostic; NaN where no position was computed) */
+} plsvo_seed_result;
+
+int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batch* in, const plsvo_seed_result* out);
+
 /* device time (CUDA events on the context's stream) of the kernel launched by the last
- * plsvo_pyramid / align2d / align1d / match_direct / structopt _batch_run call: the kernel alone,
+ * plsvo_pyramid / align2d / align1d / match_direct / seed_update / structopt _batch_run call: the kernel alone,
  * without the host<->device copies those calls also make.  Measurement aid, no reference counterpart. */
 int plsvo_last_kernel_ms(plsvo_ctx* ctx, float* ms);
 

@@ -140,7 +140,7 @@ _ref_lib = None
 def build_ref(force: bool = False) -> str | None:
     """Build oracle/_ref/libplsvo_ref.so when the reference sources are present (authoring container only).
     Returns the path, or None when neither the sources nor a prebuilt library exist."""
-    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp", "feature3D_impl.cpp")]
+    srcs = [os.path.join(REFERENCE_ROOT, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp", "feature3D_impl.cpp", "depth_filter.cpp")]
     if all(os.path.exists(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "ref", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
     return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
@@ -292,4 +292,31 @@ def ref_structopt(abi, data):
     rc = lib.plsvo_ref_structopt_batch(C.byref(b), C.byref(out.struct))
     if rc != 0:
         raise RuntimeError(f"reference structopt failed rc={rc}")
+    return out
+
+
+def seed_update(abi, data, n_threads: int = 1):
+    """DepthFilter::updatePointSeeds body restated, over a synth.SeedData batch -> abi.SeedOut."""
+    lib = load(abi)
+    lib.plsvo_oracle_seed_update_batch.restype = C.c_int
+    lib.plsvo_oracle_seed_update_batch.argtypes = [C.POINTER(abi.SeedBatch), C.POINTER(abi.SeedResult), C.c_int]
+    b, keep = abi.make_seed_batch(data)
+    out = abi.SeedOut(data.n)
+    rc = lib.plsvo_oracle_seed_update_batch(C.byref(b), C.byref(out.struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle seed_update failed rc={rc}")
+    return out
+
+
+def ref_seed_update(abi, data):
+    """DepthFilter::updatePointSeeds of the reference's own depth_filter.cpp + matcher.cpp -> abi.SeedOut
+    (a, b, mu, sigma2 only; status is -1 where the reference erased the seed, 0 otherwise)."""
+    lib = load_ref(abi)
+    lib.plsvo_ref_seed_update_batch.restype = C.c_int
+    lib.plsvo_ref_seed_update_batch.argtypes = [C.POINTER(abi.SeedBatch), C.POINTER(abi.SeedResult)]
+    b, keep = abi.make_seed_batch(data)
+    out = abi.SeedOut(data.n)
+    rc = lib.plsvo_ref_seed_update_batch(C.byref(b), C.byref(out.struct))
+    if rc != 0:
+        raise RuntimeError(f"reference seed_update failed rc={rc}")
     return out

@@ -1273,6 +1273,63 @@ static float interpolate_mat_8u(const uint8_t* data, int stride, float u, float 
   return w00 * ptr[0] + w01 * ptr[stride] + w10 * ptr[1] + w11 * ptr[stride + 1];
 }
 
+// warp::getWarpMatrixAffine — src/matcher.cpp:42-71 (same undistorted pinhole for both frames)
+static void warp_matrix_affine(const plsvo_camera& cam, const double* px_ref, Vec3 f_ref, double depth_ref, const SE3& T_cur_ref,
+                               int level_ref, double A[2][2]) {
+  const int halfpatch_size = 5;
+  const Vec3 xyz_ref = f_ref * depth_ref;
+  const double step = (double)halfpatch_size * (double)(1 << level_ref);
+  Vec3 xyz_du_ref = pinhole_cam2world(cam, px_ref[0] + step, px_ref[1] + 0.0 * (double)(1 << level_ref));
+  Vec3 xyz_dv_ref = pinhole_cam2world(cam, px_ref[0] + 0.0 * (double)(1 << level_ref), px_ref[1] + step);
+  xyz_du_ref = xyz_du_ref * (xyz_ref.z / xyz_du_ref.z);
+  xyz_dv_ref = xyz_dv_ref * (xyz_ref.z / xyz_dv_ref.z);
+  double px_cur[2], px_du[2], px_dv[2];
+  pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_ref), px_cur);
+  pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_du_ref), px_du);
+  pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_dv_ref), px_dv);
+  A[0][0] = (px_du[0] - px_cur[0]) / halfpatch_size;
+  A[1][0] = (px_du[1] - px_cur[1]) / halfpatch_size;
+  A[0][1] = (px_dv[0] - px_cur[0]) / halfpatch_size;
+  A[1][1] = (px_dv[1] - px_cur[1]) / halfpatch_size;
+}
+// warp::getBestSearchLevel — :73-87
+static int best_search_level(const double A[2][2], int max_level) {
+  int search_level = 0;
+  double D = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+  while (D > 3.0 && search_level < max_level) {
+    search_level += 1;
+    D *= 0.25;
+  }
+  return search_level;
+}
+// warp::warpAffine with halfpatch_size = 5 (:89-133) + createPatchFromPatchWithBorder (:148-157).
+// patch_with_border must be zero-initialised by the caller (a NaN warp leaves it untouched).
+static void warp_affine_patches(const double A[2][2], const uint8_t* img, int stride, int cols, int rows, const double* px_ref,
+                                int level_ref, int search_level, uint8_t patch_with_border[100], uint8_t patch[64]) {
+  const int halfpatch_size = 5, patch_size = 10;
+  const double det = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+  const double invdet = 1.0 / det;
+  const float R00 = (float)(A[1][1] * invdet), R10 = (float)(-A[1][0] * invdet);
+  const float R01 = (float)(-A[0][1] * invdet), R11 = (float)(A[0][0] * invdet);
+  if (!std::isnan(R00)) {
+    const float pr0 = (float)px_ref[0] / (1 << level_ref), pr1 = (float)px_ref[1] / (1 << level_ref);
+    uint8_t* patch_ptr = patch_with_border;
+    for (int y = 0; y < patch_size; ++y)
+      for (int x = 0; x < patch_size; ++x, ++patch_ptr) {
+        float p0 = (float)(x - halfpatch_size), p1 = (float)(y - halfpatch_size);
+        p0 *= (1 << search_level), p1 *= (1 << search_level);
+        const float q0 = (R00 * p0 + R01 * p1) + pr0;
+        const float q1 = (R10 * p0 + R11 * p1) + pr1;
+        if (q0 < 0 || q1 < 0 || q0 >= cols - 1 || q1 >= rows - 1)
+          *patch_ptr = 0;
+        else
+          *patch_ptr = (uint8_t)interpolate_mat_8u(img, stride, q0, q1);
+      }
+  }
+  for (int y = 1; y < 9; ++y)
+    for (int x = 0; x < 8; ++x) patch[(y - 1) * 8 + x] = patch_with_border[y * 10 + 1 + x];
+}
+
 static void match_direct_one(const plsvo_match_batch* in, const plsvo_match_result* out, int i) {
   const plsvo_camera& cam = in->cam;
   const int halfpatch_size_ = 4;
@@ -1294,66 +1351,14 @@ static void match_direct_one(const plsvo_match_batch* in, const plsvo_match_resu
   const Vec3 pos{in->pos[3 * I], in->pos[3 * I + 1], in->pos[3 * I + 2]};
   const Vec3 f_ref{in->ref_f[3 * I], in->ref_f[3 * I + 1], in->ref_f[3 * I + 2]};
   const double depth_ref = norm(T_w_ref.t - pos);  // (ref_ftr_->frame->pos() - pt.pos_).norm()
-  // ---- getWarpMatrixAffine ----
   double A[2][2];
-  {
-    const int halfpatch_size = 5;
-    const Vec3 xyz_ref = f_ref * depth_ref;
-    const double step = (double)halfpatch_size * (double)(1 << level_ref);
-    Vec3 xyz_du_ref = pinhole_cam2world(cam, px_ref[0] + step, px_ref[1] + 0.0 * (double)(1 << level_ref));
-    Vec3 xyz_dv_ref = pinhole_cam2world(cam, px_ref[0] + 0.0 * (double)(1 << level_ref), px_ref[1] + step);
-    xyz_du_ref = xyz_du_ref * (xyz_ref.z / xyz_du_ref.z);
-    xyz_dv_ref = xyz_dv_ref * (xyz_ref.z / xyz_dv_ref.z);
-    double px_cur[2], px_du[2], px_dv[2];
-    pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_ref), px_cur);
-    pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_du_ref), px_du);
-    pinhole_world2cam(cam, se3_act(T_cur_ref, xyz_dv_ref), px_dv);
-    A[0][0] = (px_du[0] - px_cur[0]) / halfpatch_size;
-    A[1][0] = (px_du[1] - px_cur[1]) / halfpatch_size;
-    A[0][1] = (px_dv[0] - px_cur[0]) / halfpatch_size;
-    A[1][1] = (px_dv[1] - px_cur[1]) / halfpatch_size;
-  }
-  // ---- getBestSearchLevel ----
-  int search_level = 0;
-  {
-    double D = A[0][0] * A[1][1] - A[1][0] * A[0][1];
-    const int max_level = in->n_pyr_levels - 1;
-    while (D > 3.0 && search_level < max_level) {
-      search_level += 1;
-      D *= 0.25;
-    }
-  }
+  warp_matrix_affine(cam, px_ref, f_ref, depth_ref, T_cur_ref, level_ref, A);
+  const int search_level = best_search_level(A, in->n_pyr_levels - 1);
   if (out->search_level) out->search_level[i] = search_level;
-  // ---- warpAffine on the (halfpatch_size_+1) = 5 border patch ----
   uint8_t patch_with_border[100] = {0};
   uint8_t patch[64];
-  {
-    const int halfpatch_size = halfpatch_size_ + 1, patch_size = 2 * halfpatch_size;
-    const double det = A[0][0] * A[1][1] - A[1][0] * A[0][1];
-    const double invdet = 1.0 / det;
-    const float R00 = (float)(A[1][1] * invdet), R10 = (float)(-A[1][0] * invdet);
-    const float R01 = (float)(-A[0][1] * invdet), R11 = (float)(A[0][0] * invdet);
-    if (!std::isnan(R00)) {
-      const int cols = cam.width >> level_ref, rows = cam.height >> level_ref;
-      const uint8_t* img = in->ref_img[level_ref] + (size_t)in->ref_index[i] * in->ref_stride[level_ref];
-      const int stride = (int)in->ref_pitch[level_ref];
-      const float pr0 = (float)px_ref[0] / (1 << level_ref), pr1 = (float)px_ref[1] / (1 << level_ref);
-      uint8_t* patch_ptr = patch_with_border;
-      for (int y = 0; y < patch_size; ++y)
-        for (int x = 0; x < patch_size; ++x, ++patch_ptr) {
-          float p0 = (float)(x - halfpatch_size), p1 = (float)(y - halfpatch_size);
-          p0 *= (1 << search_level), p1 *= (1 << search_level);
-          const float q0 = (R00 * p0 + R01 * p1) + pr0;
-          const float q1 = (R10 * p0 + R11 * p1) + pr1;
-          if (q0 < 0 || q1 < 0 || q0 >= cols - 1 || q1 >= rows - 1)
-            *patch_ptr = 0;
-          else
-            *patch_ptr = (uint8_t)interpolate_mat_8u(img, stride, q0, q1);
-        }
-    }
-  }
-  for (int y = 1; y < 9; ++y)
-    for (int x = 0; x < 8; ++x) patch[(y - 1) * 8 + x] = patch_with_border[y * 10 + 1 + x];
+  warp_affine_patches(A, in->ref_img[level_ref] + (size_t)in->ref_index[i] * in->ref_stride[level_ref], (int)in->ref_pitch[level_ref],
+                      cam.width >> level_ref, cam.height >> level_ref, px_ref, level_ref, search_level, patch_with_border, patch);
   // ---- align at the search level ----
   const double scale = (double)(1 << search_level);
   double px_scaled[2] = {in->px_cur[2 * I] / scale, in->px_cur[2 * I + 1] / scale};
@@ -1540,6 +1545,250 @@ int plsvo_oracle_structopt_batch(const plsvo_structopt_batch* in, const plsvo_st
     out->seg_epos[3 * I] = ep.x, out->seg_epos[3 * I + 1] = ep.y, out->seg_epos[3 * I + 2] = ep.z;
     if (out->seg_iters) out->seg_iters[i] = iters;
   });
+  return PLSVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depth-filter point-seed update: DepthFilter::updatePointSeeds body (src/depth_filter.cpp:270-365),
+// Matcher::findEpipolarMatchDirect (src/matcher.cpp:277-420), depthFromTriangulation (:135-146),
+// vk::patch_score::ZMSSD<4> (rpg_vikit patch_score.h), DepthFilter::computeTau (:568-584),
+// DepthFilter::updatePointSeed (:489-512), boost::math::pdf(normal_distribution<float>).
+// ------------------------------------------------------------------------------------------------
+static bool depth_from_triangulation(const SE3& T_search_ref, Vec3 f_ref, Vec3 f_cur, double& depth) {
+  double R[3][3];
+  quat_to_matrix(T_search_ref.q, R);
+  const double fr[3] = {f_ref.x, f_ref.y, f_ref.z};
+  double A[3][2];
+  for (int i = 0; i < 3; ++i) A[i][0] = (R[i][0] * fr[0] + R[i][1] * fr[1]) + R[i][2] * fr[2];
+  A[0][1] = f_cur.x, A[1][1] = f_cur.y, A[2][1] = f_cur.z;
+  double AtA[2][2];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) AtA[i][j] = (A[0][i] * A[0][j] + A[1][i] * A[1][j]) + A[2][i] * A[2][j];
+  const double det = AtA[0][0] * AtA[1][1] - AtA[1][0] * AtA[0][1];
+  if (det < 0.000001) return false;
+  const double invdet = 1.0 / det;
+  // M = -(AtA.inverse())
+  const double M[2][2] = {{-(AtA[1][1] * invdet), -(-AtA[0][1] * invdet)}, {-(-AtA[1][0] * invdet), -(AtA[0][0] * invdet)}};
+  // N = M * A^T (2x3), depth2 = N * t
+  const double t[3] = {T_search_ref.t.x, T_search_ref.t.y, T_search_ref.t.z};
+  double N0[3];
+  for (int j = 0; j < 3; ++j) N0[j] = M[0][0] * A[j][0] + M[0][1] * A[j][1];
+  const double d0 = (N0[0] * t[0] + N0[1] * t[1]) + N0[2] * t[2];
+  depth = std::fabs(d0);
+  return true;
+}
+
+struct EpiResult {
+  int search_level = -1;
+  double px_cur[2] = {std::numeric_limits<double>::quiet_NaN(), std::numeric_limits<double>::quiet_NaN()};
+};
+static bool find_epipolar_match_direct(const plsvo_seed_batch* in, int i, double d_estimate, double d_min, double d_max, double& depth,
+                                       EpiResult& er) {
+  const plsvo_camera& cam = in->cam;
+  const size_t I = (size_t)i;
+  const int halfpatch_size_ = 4, patch_size_ = 8;
+  const SE3 T_ref_w = se3_from_pose7(in->T_ref_w + 7 * (size_t)in->ref_index[i]);
+  const SE3 T_cur_w = se3_from_pose7(in->T_cur_w + 7 * (size_t)in->cur_index[i]);
+  const SE3 T_cur_ref = se3_mul(T_cur_w, se3_inverse(T_ref_w));
+  const Vec3 f{in->ref_f[3 * I], in->ref_f[3 * I + 1], in->ref_f[3 * I + 2]};
+  const double* px_ref = in->ref_px + 2 * I;
+  const int level_ref = in->ref_level[i];
+  int zmssd_best = 2000 * 64;  // PatchScore::threshold()
+  double uv_best[2] = {0, 0};
+  // start and end of the epipolar segment on the unit plane (:291-293)
+  double A2[2], B2[2];
+  project2d(se3_act(T_cur_ref, f * d_min), A2);
+  project2d(se3_act(T_cur_ref, f * d_max), B2);
+  const double epi_dir[2] = {A2[0] - B2[0], A2[1] - B2[1]};
+  double A[2][2];
+  warp_matrix_affine(cam, px_ref, f, d_estimate, T_cur_ref, level_ref, A);
+  // feature pre-selection (:300-310)
+  if (in->is_edgelet && in->is_edgelet[i] && in->epi_search_edgelet_filtering) {
+    const double g0 = in->ref_grad[2 * I], g1 = in->ref_grad[2 * I + 1];
+    double c0 = A[0][0] * g0 + A[0][1] * g1, c1 = A[1][0] * g0 + A[1][1] * g1;
+    const double nc = std::sqrt(c0 * c0 + c1 * c1);
+    c0 /= nc, c1 /= nc;
+    const double ne = std::sqrt(epi_dir[0] * epi_dir[0] + epi_dir[1] * epi_dir[1]);
+    const double e0 = epi_dir[0] / ne, e1 = epi_dir[1] / ne;
+    const double cosangle = std::fabs(c0 * e0 + c1 * e1);
+    if (cosangle < in->epi_search_edgelet_max_angle) return false;  // reject_
+  }
+  const int search_level = best_search_level(A, in->n_pyr_levels - 1);
+  er.search_level = search_level;
+  // length of the search range (:315-317); world2cam(Vector2d uv) = (fx*u+cx, fy*v+cy)
+  const double px_A[2] = {cam.fx * A2[0] + cam.cx, cam.fy * A2[1] + cam.cy};
+  const double px_B[2] = {cam.fx * B2[0] + cam.cx, cam.fy * B2[1] + cam.cy};
+  const double dAB[2] = {px_A[0] - px_B[0], px_A[1] - px_B[1]};
+  const double epi_length = std::sqrt(dAB[0] * dAB[0] + dAB[1] * dAB[1]) / (1 << search_level);
+  uint8_t patch_with_border[100] = {0};
+  uint8_t patch[64];
+  warp_affine_patches(A, in->ref_img[level_ref] + (size_t)in->ref_index[i] * in->ref_stride[level_ref], (int)in->ref_pitch[level_ref],
+                      cam.width >> level_ref, cam.height >> level_ref, px_ref, level_ref, search_level, patch_with_border, patch);
+  const uint8_t* cur = in->cur_img[search_level] + (size_t)in->cur_index[i] * in->cur_stride[search_level];
+  const int ccols = cam.width >> search_level, crows = cam.height >> search_level;
+  const size_t cpitch = in->cur_pitch[search_level];
+  const double scale = (double)(1 << search_level);
+  float dir1d[2];
+  {  // (px_A-px_B).cast<float>().normalized()
+    const float fx_ = (float)dAB[0], fy_ = (float)dAB[1];
+    const float n = std::sqrt(fx_ * fx_ + fy_ * fy_);
+    dir1d[0] = fx_ / n, dir1d[1] = fy_ / n;
+  }
+  auto refine_and_triangulate = [&](const double px_start[2]) -> bool {
+    double px_scaled[2] = {px_start[0] / scale, px_start[1] / scale};
+    int res;
+    double h_inv;
+    if (in->align_1d)
+      res = plsvo_oracle_align1d(cur, ccols, crows, cpitch, dir1d, patch_with_border, patch, in->n_iter, px_scaled, &h_inv);
+    else
+      res = plsvo_oracle_align2d(cur, ccols, crows, cpitch, patch_with_border, patch, in->n_iter, px_scaled);
+    if (res) {
+      er.px_cur[0] = px_scaled[0] * scale, er.px_cur[1] = px_scaled[1] * scale;
+      if (depth_from_triangulation(T_cur_ref, f, pinhole_cam2world(cam, er.px_cur[0], er.px_cur[1]), depth)) return true;
+    }
+    return false;
+  };
+  if (epi_length < 2.0 && !std::isnan(fabsf((float)epi_length)) && !std::isinf(fabsf((float)epi_length))) {  // :324-343
+    er.px_cur[0] = (px_A[0] + px_B[0]) / 2.0, er.px_cur[1] = (px_A[1] + px_B[1]) / 2.0;
+    const double start[2] = {er.px_cur[0], er.px_cur[1]};
+    return refine_and_triangulate(start);
+  }
+  size_t n_steps = (size_t)(epi_length / 0.7);  // one step per pixel (:345)
+  const double step[2] = {epi_dir[0] / (double)n_steps, epi_dir[1] / (double)n_steps};
+  if (n_steps > (size_t)in->max_epi_search_steps) return false;
+  // ZMSSD of the warped reference patch (:354-356)
+  int sumA = 0, sumAA = 0;
+  for (int r = 0; r < 64; ++r) sumA += patch[r], sumAA += patch[r] * patch[r];
+  double uv[2] = {B2[0] - step[0], B2[1] - step[1]};
+  int last_checked[2] = {0, 0};
+  ++n_steps;
+  for (size_t k = 0; k < n_steps; ++k, uv[0] += step[0], uv[1] += step[1]) {
+    const double px[2] = {cam.fx * uv[0] + cam.cx, cam.fy * uv[1] + cam.cy};
+    const double qx = px[0] / (1 << search_level) + 0.5, qy = px[1] / (1 << search_level) + 0.5;
+    // Vector2i(double, double): conversion toward zero (x86 gives INT_MIN outside the int range / for NaN)
+    const int pxi0 = (qx >= -2147483648.0 && qx < 2147483648.0) ? (int)qx : INT32_MIN;
+    const int pxi1 = (qy >= -2147483648.0 && qy < 2147483648.0) ? (int)qy : INT32_MIN;
+    if (pxi0 == last_checked[0] && pxi1 == last_checked[1]) continue;
+    last_checked[0] = pxi0, last_checked[1] = pxi1;
+    if (!cam_is_in_frame(cam, pxi0, pxi1, patch_size_, search_level)) continue;
+    // the reference strides the patch with Mat::cols (:380-382); images are dense (checked by the caller)
+    const uint8_t* cur_patch_ptr = cur + (ptrdiff_t)(pxi1 - halfpatch_size_) * ccols + (pxi0 - halfpatch_size_);
+    int sumB = 0, sumBB = 0, sumAB = 0;
+    for (int y = 0, r = 0; y < patch_size_; ++y) {
+      const uint8_t* p = cur_patch_ptr + (ptrdiff_t)y * ccols;
+      for (int x = 0; x < patch_size_; ++x, ++r) {
+        const int cur_px = p[x];
+        sumB += cur_px, sumBB += cur_px * cur_px, sumAB += cur_px * patch[r];
+      }
+    }
+    const int zmssd = sumAA - 2 * sumAB + sumBB - (sumA * sumA - 2 * sumA * sumB + sumB * sumB) / 64;
+    if (zmssd < zmssd_best) zmssd_best = zmssd, uv_best[0] = uv[0], uv_best[1] = uv[1];
+  }
+  if (zmssd_best < 2000 * 64) {
+    er.px_cur[0] = cam.fx * uv_best[0] + cam.cx, er.px_cur[1] = cam.fy * uv_best[1] + cam.cy;
+    if (in->subpix_refinement) {
+      const double start[2] = {er.px_cur[0], er.px_cur[1]};
+      return refine_and_triangulate(start);
+    }
+    const Vec3 u3{uv_best[0], uv_best[1], 1.0};  // vk::unproject2d(uv_best).normalized()
+    const double n = std::sqrt((u3.x * u3.x + u3.y * u3.y) + u3.z * u3.z);
+    if (depth_from_triangulation(T_cur_ref, f, Vec3{u3.x / n, u3.y / n, u3.z / n}, depth)) return true;
+  }
+  return false;
+}
+
+static double compute_tau(const SE3& T_ref_cur, Vec3 f, double z, double px_error_angle) {  // depth_filter.cpp:568-584
+  const Vec3 t = T_ref_cur.t;
+  const Vec3 a = f * z - t;
+  const double t_norm = norm(t), a_norm = norm(a);
+  const double alpha = std::acos(((f.x * t.x + f.y * t.y) + f.z * t.z) / t_norm);
+  const Vec3 mt{-t.x, -t.y, -t.z};
+  const double beta = std::acos(((a.x * mt.x + a.y * mt.y) + a.z * mt.z) / (t_norm * a_norm));
+  const double beta_plus = beta + px_error_angle;
+  const double gamma_plus = 3.14159265 - alpha - beta_plus;  // plsvo::PI (global.h:93)
+  const double z_plus = t_norm * std::sin(beta_plus) / std::sin(gamma_plus);
+  return z_plus - z;
+}
+struct SeedState {
+  float a, b, mu, z_range, sigma2;
+};
+static void update_point_seed(const float x, const float tau2, SeedState* seed) {  // depth_filter.cpp:489-512
+  const float norm_scale = std::sqrt(seed->sigma2 + tau2);
+  if (std::isnan(norm_scale)) return;
+  float pdf;
+  {  // boost::math::pdf(normal_distribution<float>(mu, norm_scale), x)
+    float exponent = x - seed->mu;
+    exponent *= -exponent;
+    exponent /= 2 * norm_scale * norm_scale;
+    pdf = std::exp(exponent);
+    pdf /= norm_scale * std::sqrt(2 * static_cast<float>(3.141592653589793238462643383279502884L));
+    if (std::isinf(x)) pdf = 0;
+  }
+  const float s2 = 1. / (1. / seed->sigma2 + 1. / tau2);
+  const float m = s2 * (seed->mu / seed->sigma2 + x / tau2);
+  float C1 = seed->a / (seed->a + seed->b) * pdf;
+  float C2 = seed->b / (seed->a + seed->b) * 1. / seed->z_range;
+  const float normalization_constant = C1 + C2;
+  C1 /= normalization_constant;
+  C2 /= normalization_constant;
+  const float f = C1 * (seed->a + 1.) / (seed->a + seed->b + 1.) + C2 * seed->a / (seed->a + seed->b + 1.);
+  const float e = C1 * (seed->a + 1.) * (seed->a + 2.) / ((seed->a + seed->b + 1.) * (seed->a + seed->b + 2.)) +
+                  C2 * seed->a * (seed->a + 1.0f) / ((seed->a + seed->b + 1.0f) * (seed->a + seed->b + 2.0f));
+  const float mu_new = C1 * m + C2 * seed->mu;
+  seed->sigma2 = C1 * (s2 + m * m) + C2 * (seed->sigma2 + seed->mu * seed->mu) - mu_new * mu_new;
+  seed->mu = mu_new;
+  seed->a = (e - f) / (f - e / f);
+  seed->b = seed->a * (1.0f - f) / f;
+}
+
+static void seed_update_one(const plsvo_seed_batch* in, const plsvo_seed_result* out, int i) {
+  const plsvo_camera& cam = in->cam;
+  const size_t I = (size_t)i;
+  SeedState sd{in->a[i], in->b[i], in->mu[i], in->z_range[i], in->sigma2[i]};
+  int status = PLSVO_SEED_NOT_VISIBLE;
+  double z = std::numeric_limits<double>::quiet_NaN();
+  EpiResult er;
+  const SE3 T_ref_w = se3_from_pose7(in->T_ref_w + 7 * (size_t)in->ref_index[i]);
+  const SE3 T_cur_w = se3_from_pose7(in->T_cur_w + 7 * (size_t)in->cur_index[i]);
+  const Vec3 f{in->ref_f[3 * I], in->ref_f[3 * I + 1], in->ref_f[3 * I + 2]};
+  const double focal_length = std::fabs(cam.fx);  // errorMultiplier2()
+  const double px_noise = 1.0;
+  const double px_error_angle = std::atan(px_noise / (2.0 * focal_length)) * 2.0;  // law of chord (:279-280)
+  do {
+    const SE3 T_ref_cur = se3_mul(T_ref_w, se3_inverse(T_cur_w));  // :291
+    const Vec3 xyz_f = se3_act(se3_inverse(T_ref_cur), f * (1.0 / sd.mu));
+    if (xyz_f.z < 0.0) break;  // behind the camera
+    double pxc[2];
+    pinhole_world2cam(cam, xyz_f, pxc);
+    {
+      const int ox = (pxc[0] >= -2147483648.0 && pxc[0] < 2147483648.0) ? (int)pxc[0] : INT32_MIN;
+      const int oy = (pxc[1] >= -2147483648.0 && pxc[1] < 2147483648.0) ? (int)pxc[1] : INT32_MIN;
+      if (!(ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height)) break;  // isInFrame(obs, 0)
+    }
+    const float z_inv_min = sd.mu + std::sqrt(sd.sigma2);
+    const float z_inv_max = std::max(sd.mu - std::sqrt(sd.sigma2), 0.00000001f);
+    if (!find_epipolar_match_direct(in, i, 1.0 / sd.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, z, er)) {
+      sd.b++;  // :314
+      status = PLSVO_SEED_NO_MATCH;
+      z = std::numeric_limits<double>::quiet_NaN();
+      break;
+    }
+    const double tau = compute_tau(T_ref_cur, f, z, px_error_angle);
+    const double tau_inverse = 0.5 * (1.0 / std::max(0.0000001, z - tau) - 1.0 / (z + tau));
+    update_point_seed((float)(1. / z), (float)(tau_inverse * tau_inverse), &sd);
+    status = PLSVO_SEED_UPDATED;
+  } while (false);
+  out->a[i] = sd.a, out->b[i] = sd.b, out->mu[i] = sd.mu, out->sigma2[i] = sd.sigma2;
+  out->status[i] = status;
+  if (out->converged)
+    out->converged[i] = (status == PLSVO_SEED_UPDATED && std::sqrt(sd.sigma2) < sd.z_range / in->seed_convergence_sigma2_thresh) ? 1 : 0;
+  if (out->depth) out->depth[i] = z;
+  if (out->px_cur) out->px_cur[2 * I] = er.px_cur[0], out->px_cur[2 * I + 1] = er.px_cur[1];
+}
+
+int plsvo_oracle_seed_update_batch(const plsvo_seed_batch* in, const plsvo_seed_result* out, int n_threads) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  parallel_for(in->n_seeds, n_threads, [&](int i) { seed_update_one(in, out, i); });
   return PLSVO_OK;
 }
 

@@ -8,6 +8,7 @@
 //     /root/reference/src/feature.cpp            /root/reference/src/feature_alignment.cpp
 //     /root/reference/src/matcher.cpp            /root/reference/src/config.cpp            
 //     /root/reference/src/feature3D_impl.cpp     (Point::optimize / LineSeg::optimize)
+//     /root/reference/src/depth_filter.cpp       (DepthFilter::updatePointSeeds)
 // against the reference's own headers (/root/reference/include/plsvo/*.h) and the stand-in
 // third-party headers in oracle/refdeps/ (Eigen, Sophus, rpg_vikit, OpenCV core, boost — absent
 // from the image and from /root/reference), links this file, and writes oracle/_ref/libplsvo_ref.so.
@@ -25,6 +26,7 @@
 #include <plsvo/feature.h>
 #include <plsvo/feature_alignment.h>
 #include <plsvo/feature3D.h>
+#include <plsvo/depth_filter.h>
 #include <plsvo/frame.h>
 #include <plsvo/matcher.h>
 #include <plsvo/config.h>
@@ -56,6 +58,10 @@ Frame::~Frame() {
 }
 
 Point::Point(const Vector3d& pos) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {}
+Point::Point(const Vector3d& pos, PointFeat* ftr) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {
+  obs_.push_front(ftr);
+  ++n_obs_;
+}
 // src/feature3D_impl.cpp picks, among obs_, the observation with the closest viewing direction (list logic that
 // stays on the host side of the ABI); the harness hands over exactly one observation per point.
 bool Point::getCloseViewObs(const Vector3d&, Feature*& obs) const {
@@ -66,6 +72,11 @@ bool Point::getCloseViewObs(const Vector3d&, Feature*& obs) const {
 
 LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos)
     : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {}
+LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos, LineFeat* ftr)
+    : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {
+  obs_.push_front(ftr);
+  ++n_obs_;
+}
 bool LineSeg::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
 
 }  // namespace plsvo
@@ -389,8 +400,81 @@ int plsvo_ref_structopt_batch(const plsvo_structopt_batch* in, const plsvo_struc
   return PLSVO_OK;
 }
 
+// DepthFilter::updatePointSeeds (src/depth_filter.cpp:270-365) driven through the reference class itself: the seeds
+// of one current frame are put into pt_seeds_, the protected update is called, and the mutated seeds are read back.
+// Seed ageing and convergence never erase a seed here (same batch id; convergence threshold disabled) so that every
+// seed's state can be read; the convergence flag is recomputed from the returned state by the caller.
+namespace {
+struct DepthFilterProbe : plsvo::DepthFilter {
+  DepthFilterProbe(plsvo::feature_detection::DetectorPtr<plsvo::PointFeat> pd, plsvo::feature_detection::DetectorPtr<plsvo::LineFeat> ld)
+      : plsvo::DepthFilter(pd, ld, [](plsvo::Point* p, double) { delete p; }, [](plsvo::LineSeg* l, double, double) { delete l; }) {}
+  using plsvo::DepthFilter::pt_seeds_;
+  using plsvo::DepthFilter::matcher_;
+  void update(FramePtr f) { updatePointSeeds(f); }
+};
+}  // namespace
+
+int plsvo_ref_seed_update_batch(const plsvo_seed_batch* in, const plsvo_seed_result* out) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  plsvo::Config::nPyrLevels() = (size_t)in->n_pyr_levels;
+  vk::PinholeCamera cam(in->cam.width, in->cam.height, in->cam.fx, in->cam.fy, in->cam.cx, in->cam.cy);
+  auto make_frames = [&](int n, const uint8_t* const* img, const size_t* pitch, const size_t* stride, const double* T) {
+    std::vector<FramePtr> frames;
+    for (int r = 0; r < n; ++r) {
+      FramePtr f(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+      f->img_pyr_.resize(PLSVO_MAX_LEVELS);
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
+        if (img[l])
+          f->img_pyr_[l] = cv::Mat(in->cam.height >> l, in->cam.width >> l, CV_8U, const_cast<uint8_t*>(img[l] + (size_t)r * stride[l]), pitch[l]);
+      f->T_f_w_ = pose_from7(T + 7 * (size_t)r);
+      frames.push_back(f);
+    }
+    return frames;
+  };
+  std::vector<FramePtr> refs = make_frames(in->n_ref_images, in->ref_img, in->ref_pitch, in->ref_stride, in->T_ref_w);
+  std::vector<FramePtr> curs = make_frames(in->n_cur_images, in->cur_img, in->cur_pitch, in->cur_stride, in->T_cur_w);
+  typedef plsvo::feature_detection::AbstractDetector<plsvo::PointFeat> VoidPt;
+  typedef plsvo::feature_detection::AbstractDetector<plsvo::LineFeat> VoidLs;
+  plsvo::feature_detection::DetectorPtr<plsvo::PointFeat> pd(new VoidPt(in->cam.width, in->cam.height, 25, in->n_pyr_levels));
+  plsvo::feature_detection::DetectorPtr<plsvo::LineFeat> ld(new VoidLs(in->cam.width, in->cam.height, 25, in->n_pyr_levels));
+  for (int c = 0; c < in->n_cur_images; ++c) {
+    DepthFilterProbe df(pd, ld);
+    df.options_.seed_convergence_sigma2_thresh = 1e300;  // never erase: every seed's state is read back below
+    df.matcher_.options_.align_max_iter = in->n_iter;
+    df.matcher_.options_.max_epi_search_steps = (size_t)in->max_epi_search_steps;
+    df.matcher_.options_.align_1d = in->align_1d != 0;
+    df.matcher_.options_.subpix_refinement = in->subpix_refinement != 0;
+    df.matcher_.options_.epi_search_edgelet_filtering = in->epi_search_edgelet_filtering != 0;
+    df.matcher_.options_.epi_search_edgelet_max_angle = in->epi_search_edgelet_max_angle;
+    std::vector<std::unique_ptr<plsvo::PointFeat>> ftrs;
+    std::vector<int> ids;
+    for (int i = 0; i < in->n_seeds; ++i) {
+      if (in->cur_index[i] != c) continue;
+      ftrs.emplace_back(new plsvo::PointFeat(refs[in->ref_index[i]].get(), v2(in->ref_px + 2 * (size_t)i), v3(in->ref_f + 3 * (size_t)i),
+                                             in->ref_level[i]));
+      if (in->is_edgelet && in->is_edgelet[i]) {
+        ftrs.back()->type = plsvo::PointFeat::EDGELET;
+        ftrs.back()->grad = v2(in->ref_grad + 2 * (size_t)i);
+      }
+      plsvo::PointSeed seed(ftrs.back().get(), 1.0f, 1.0f);
+      seed.batch_id = plsvo::Seed::batch_counter;
+      seed.id = i;
+      seed.a = in->a[i], seed.b = in->b[i], seed.mu = in->mu[i], seed.z_range = in->z_range[i], seed.sigma2 = in->sigma2[i];
+      df.pt_seeds_.push_back(seed);
+      out->status[i] = -1;  // stays -1 if the reference erased the seed (NaN search range, :355-359)
+    }
+    df.update(curs[c]);
+    for (const plsvo::PointSeed& sd : df.pt_seeds_) {
+      const int i = sd.id;
+      out->a[i] = sd.a, out->b[i] = sd.b, out->mu[i] = sd.mu, out->sigma2[i] = sd.sigma2;
+      out->status[i] = 0;  // state only: the reference does not report which branch a seed took
+    }
+  }
+  return PLSVO_OK;
+}
+
 const char* plsvo_ref_describe(void) {
-  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment,matcher,config,feature3D_impl}.cpp compiled unmodified against stand-in "
+  return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment,matcher,config,feature3D_impl,depth_filter}.cpp compiled unmodified against stand-in "
          "Eigen/Sophus/vikit/OpenCV/boost headers (oracle/refdeps)";
 }
 }

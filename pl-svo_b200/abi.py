@@ -184,6 +184,29 @@ class StructOptResult(C.Structure):
     _fields_ = [("pt_pos", _f64p), ("seg_spos", _f64p), ("seg_epos", _f64p), ("pt_iters", _i32p), ("seg_iters", _i32p)]
 
 
+_f32p = C.POINTER(C.c_float)
+
+
+class SeedBatch(C.Structure):
+    _fields_ = [("n_seeds", C.c_int32), ("n_ref_images", C.c_int32), ("n_cur_images", C.c_int32), ("n_pyr_levels", C.c_int32),
+                ("n_iter", C.c_int32), ("max_epi_search_steps", C.c_int32), ("align_1d", C.c_uint8), ("subpix_refinement", C.c_uint8),
+                ("epi_search_edgelet_filtering", C.c_uint8), ("reserved0", C.c_uint8 * 5),
+                ("epi_search_edgelet_max_angle", C.c_double), ("seed_convergence_sigma2_thresh", C.c_double), ("cam", Camera),
+                ("ref_img", _u8p * MAX_LEVELS), ("ref_pitch", C.c_size_t * MAX_LEVELS), ("ref_stride", C.c_size_t * MAX_LEVELS),
+                ("cur_img", _u8p * MAX_LEVELS), ("cur_pitch", C.c_size_t * MAX_LEVELS), ("cur_stride", C.c_size_t * MAX_LEVELS),
+                ("T_ref_w", _f64p), ("T_cur_w", _f64p), ("ref_index", _i32p), ("cur_index", _i32p), ("ref_px", _f64p),
+                ("ref_f", _f64p), ("ref_level", _i32p), ("is_edgelet", _u8p), ("ref_grad", _f64p),
+                ("a", _f32p), ("b", _f32p), ("mu", _f32p), ("z_range", _f32p), ("sigma2", _f32p)]
+
+
+class SeedResult(C.Structure):
+    _fields_ = [("a", _f32p), ("b", _f32p), ("mu", _f32p), ("sigma2", _f32p), ("status", _i32p), ("converged", _u8p),
+                ("depth", _f64p), ("px_cur", _f64p)]
+
+
+SEED_NOT_VISIBLE, SEED_NO_MATCH, SEED_UPDATED = 0, 1, 2
+
+
 class MatchResult(C.Structure):
     _fields_ = [("px_cur", _f64p), ("success", _u8p), ("search_level", _i32p)]
 
@@ -192,7 +215,7 @@ class MatchResult(C.Structure):
 # numpy <-> struct helpers
 # ------------------------------------------------------------------------------------------------
 
-_CT = {np.dtype(np.uint8): _u8p, np.dtype(np.float64): _f64p, np.dtype(np.int32): _i32p,
+_CT = {np.dtype(np.float32): C.POINTER(C.c_float), np.dtype(np.uint8): _u8p, np.dtype(np.float64): _f64p, np.dtype(np.int32): _i32p,
        np.dtype(np.int64): _i64p, np.dtype(np.uint32): _u32p}
 
 
@@ -354,6 +377,7 @@ ABI_SYMBOLS = [
     ("plsvo_align2d_batch_run", C.c_int, [C.c_void_p, _P(Align2DBatch), _P(Align2DResult)]),
     ("plsvo_align1d_batch_run", C.c_int, [C.c_void_p, _P(Align1DBatch), _P(Align1DResult)]),
     ("plsvo_match_direct_batch_run", C.c_int, [C.c_void_p, _P(MatchBatch), _P(MatchResult)]),
+    ("plsvo_seed_update_batch_run", C.c_int, [C.c_void_p, _P(SeedBatch), _P(SeedResult)]),
     ("plsvo_structopt_batch_run", C.c_int, [C.c_void_p, _P(StructOptBatch), _P(StructOptResult)]),
     ("plsvo_last_kernel_ms", C.c_int, [C.c_void_p, _P(C.c_float)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
@@ -458,3 +482,41 @@ class StructOptOut:
         self.seg_iters = np.zeros(n_segs, np.int32)
         self.struct = StructOptResult(_ptr(self.pt_pos, np.float64), _ptr(self.seg_spos, np.float64), _ptr(self.seg_epos, np.float64),
                                       _ptr(self.pt_iters, np.int32), _ptr(self.seg_iters, np.int32))
+
+
+def make_seed_batch(d):
+    """Build a plsvo_seed_batch from a synth.SeedData-like object.  Returns (struct, keepalive)."""
+    b = SeedBatch()
+    b.n_seeds, b.n_ref_images, b.n_cur_images = d.n, d.T_ref_w.shape[0], d.T_cur_w.shape[0]
+    b.n_pyr_levels, b.n_iter, b.max_epi_search_steps = d.n_pyr_levels, d.n_iter, d.max_epi_search_steps
+    b.align_1d, b.subpix_refinement, b.epi_search_edgelet_filtering = int(d.align_1d), int(d.subpix_refinement), int(d.edgelet_filtering)
+    b.epi_search_edgelet_max_angle, b.seed_convergence_sigma2_thresh = d.edgelet_max_angle, d.convergence_thresh
+    b.cam = Camera(d.cam.width, d.cam.height, 0, 0, d.cam.fx, d.cam.fy, d.cam.cx, d.cam.cy)
+    for l, im in d.ref_pyr.items():
+        b.ref_img[l] = _ptr(im, np.uint8)
+        b.ref_pitch[l], b.ref_stride[l] = im.strides[1], im.strides[0]
+    for l, im in d.cur_pyr.items():
+        b.cur_img[l] = _ptr(im, np.uint8)
+        b.cur_pitch[l], b.cur_stride[l] = im.strides[1], im.strides[0]
+    b.T_ref_w, b.T_cur_w = _ptr(d.T_ref_w, np.float64), _ptr(d.T_cur_w, np.float64)
+    b.ref_index, b.cur_index = _ptr(d.ref_index, np.int32), _ptr(d.cur_index, np.int32)
+    b.ref_px, b.ref_f, b.ref_level = _ptr(d.ref_px, np.float64), _ptr(d.ref_f, np.float64), _ptr(d.ref_level, np.int32)
+    b.is_edgelet, b.ref_grad = _ptr(d.is_edgelet, np.uint8), _ptr(d.ref_grad, np.float64)
+    b.a, b.b, b.mu = _ptr(d.a, np.float32), _ptr(d.b, np.float32), _ptr(d.mu, np.float32)
+    b.z_range, b.sigma2 = _ptr(d.z_range, np.float32), _ptr(d.sigma2, np.float32)
+    return b, [d]
+
+
+class SeedOut:
+    """Owns the output arrays of one seed-update batch and the plsvo_seed_result pointing at them."""
+
+    def __init__(self, n: int):
+        self.a, self.b = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.mu, self.sigma2 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.status = np.zeros(n, np.int32)
+        self.converged = np.zeros(n, np.uint8)
+        self.depth = np.zeros(n)
+        self.px_cur = np.zeros((n, 2))
+        self.struct = SeedResult(_ptr(self.a, np.float32), _ptr(self.b, np.float32), _ptr(self.mu, np.float32), _ptr(self.sigma2, np.float32),
+                                 _ptr(self.status, np.int32), _ptr(self.converged, np.uint8), _ptr(self.depth, np.float64),
+                                 _ptr(self.px_cur, np.float64))

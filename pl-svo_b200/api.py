@@ -237,3 +237,19 @@ def optimizeStructure(data, ctx: Context | None = None) -> abi.StructOptOut:
     out = abi.StructOptOut(b.n_points, b.n_segs)
     ctx.check(ctx.lib.plsvo_structopt_batch_run(ctx.handle, C.byref(b), C.byref(out.struct)), "plsvo_structopt_batch_run")
     return out
+
+
+class DepthFilter:
+    """Batched counterpart of plsvo::DepthFilter::updatePointSeeds (src/depth_filter.cpp:270-365): visibility test,
+    Matcher::findEpipolarMatchDirect, computeTau and the Gaussian x Beta update of every seed; seed ageing, point creation
+    and the detector's occupancy grid stay on the host."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+
+    def updatePointSeeds(self, data) -> abi.SeedOut:
+        b, keep = abi.make_seed_batch(data)
+        out = abi.SeedOut(data.n)
+        self.ctx.check(self.ctx.lib.plsvo_seed_update_batch_run(self.ctx.handle, C.byref(b), C.byref(out.struct)),
+                       "plsvo_seed_update_batch_run")
+        return out

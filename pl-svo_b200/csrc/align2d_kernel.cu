@@ -291,18 +291,107 @@ __global__ void __launch_bounds__(kA2Threads) align1d_kernel(const Align2DArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared pieces of Matcher::findMatchDirect and Matcher::findEpipolarMatchDirect.  The double-precision geometry
+// is written with explicit round-to-nearest intrinsics (exact_math.cuh) so that the compiler cannot contract a*b+c
+// into an FMA: A_cur_ref, the search level and every byte of the warped patch are bit-identical to the scalar code.
+struct CamP {
+  double fx, fy, cx, cy;
+  int width, height;
+};
+__device__ __forceinline__ V3 cam2world(const CamP& c, double u, double v) {  // PinholeCamera::cam2world, undistorted, normalized()
+  const V3 xyz{DD(DS(u, c.cx), c.fx), DD(DS(v, c.cy), c.fy), 1.0};
+  const double n = v_norm(xyz);
+  return V3{DD(xyz.x, n), DD(xyz.y, n), DD(xyz.z, n)};
+}
+__device__ __forceinline__ void world2cam(const CamP& c, V3 p, double& u, double& v) {  // world2cam(project2d(xyz))
+  u = DA(DM(c.fx, DD(p.x, p.z)), c.cx);
+  v = DA(DM(c.fy, DD(p.y, p.z)), c.cy);
+}
+__device__ __forceinline__ bool cam_in_frame(const CamP& c, int ox, int oy, int b, int level) {  // AbstractCamera::isInFrame(obs, b, level)
+  return ox >= b && ox < c.width / (1 << level) - b && oy >= b && oy < c.height / (1 << level) - b;
+}
+// double -> int as the x86 cvttsd2si the reference compiles to: out-of-range and NaN give INT_MIN
+__device__ __forceinline__ int d2i_x86(double q) { return (q >= -2147483648.0 && q < 2147483648.0) ? (int)q : (-2147483647 - 1); }
+
+// warp::getWarpMatrixAffine (src/matcher.cpp:42-71)
+__device__ __forceinline__ void warp_matrix_affine(const CamP& cam, double px_ref0, double px_ref1, V3 f_ref, double depth_ref,
+                                                   const Pose& T_cur_ref, int level_ref, double& A00, double& A01, double& A10,
+                                                   double& A11) {
+  const V3 xyz_ref = v_scale(f_ref, depth_ref);
+  const double scale_ref = (double)(1 << level_ref);
+  const double step = DM(5.0, scale_ref), zero = DM(0.0, scale_ref);
+  V3 xyz_du = cam2world(cam, DA(px_ref0, step), DA(px_ref1, zero));
+  V3 xyz_dv = cam2world(cam, DA(px_ref0, zero), DA(px_ref1, step));
+  xyz_du = v_scale(xyz_du, DD(xyz_ref.z, xyz_du.z));
+  xyz_dv = v_scale(xyz_dv, DD(xyz_ref.z, xyz_dv.z));
+  double pc0, pc1, pu0, pu1, pv0, pv1;
+  world2cam(cam, pose_act(T_cur_ref, xyz_ref), pc0, pc1);
+  world2cam(cam, pose_act(T_cur_ref, xyz_du), pu0, pu1);
+  world2cam(cam, pose_act(T_cur_ref, xyz_dv), pv0, pv1);
+  A00 = DD(DS(pu0, pc0), 5.0), A10 = DD(DS(pu1, pc1), 5.0);
+  A01 = DD(DS(pv0, pc0), 5.0), A11 = DD(DS(pv1, pc1), 5.0);
+}
+// warp::getBestSearchLevel (:73-87)
+__device__ __forceinline__ int best_search_level(double det, int max_level) {
+  int search_level = 0;
+  double D = det;
+  while (D > 3.0 && search_level < max_level) {
+    search_level += 1;
+    D = DM(D, 0.25);
+  }
+  return search_level;
+}
+// warp::warpAffine with halfpatch_size 5 (:89-133, vk::interpolateMat_8u) into a 10x10 patch with border
+__device__ __forceinline__ void warp_affine_patch(double A00, double A01, double A10, double A11, double det, const uint8_t* img,
+                                                  int stride, int cols, int rows, double px_ref0, double px_ref1, int level_ref,
+                                                  int search_level, uint8_t* border) {
+  const double invdet = DD(1.0, det);
+  const float R00 = (float)DM(A11, invdet), R10 = (float)DM(-A10, invdet);
+  const float R01 = (float)DM(-A01, invdet), R11 = (float)DM(A00, invdet);
+  const bool bad = isnan(R00);  // "Affine warp is NaN": the reference leaves the (zeroed) patch untouched
+  const float fs = (float)(1 << level_ref);
+  const float pr0 = __fdiv_rn((float)px_ref0, fs), pr1 = __fdiv_rn((float)px_ref1, fs);
+  const float ss = (float)(1 << search_level);
+  const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
+  for (int y = 0; y < 10; ++y) {
+    const float p1 = __fmul_rn((float)(y - 5), ss);
+    for (int x = 0; x < 10; ++x) {
+      uint8_t val = 0;
+      if (!bad) {
+        const float p0 = __fmul_rn((float)(x - 5), ss);
+        const float q0 = __fadd_rn(__fadd_rn(__fmul_rn(R00, p0), __fmul_rn(R01, p1)), pr0);
+        const float q1 = __fadd_rn(__fadd_rn(__fmul_rn(R10, p0), __fmul_rn(R11, p1)), pr1);
+        if (!(q0 < 0 || q1 < 0 || q0 >= xmax || q1 >= ymax)) {
+          const float fx = floorf(q0), fy = floorf(q1);
+          const int ix = (int)fx, iy = (int)fy;
+          const float sx = __fsub_rn(q0, fx), sy = __fsub_rn(q1, fy);
+          const float w00 = __fmul_rn(__fsub_rn(1.0f, sx), __fsub_rn(1.0f, sy));
+          const float w01 = __fmul_rn(__fsub_rn(1.0f, sx), sy);
+          const float w10 = __fmul_rn(sx, __fsub_rn(1.0f, sy));
+          const float w11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, w00), w01), w10);
+          const uint8_t* ptr = img + (size_t)iy * stride + ix;
+          const float I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, u8f(ptr[0])), __fmul_rn(w01, u8f(ptr[stride]))),
+                                              __fmul_rn(w10, u8f(ptr[1]))),
+                                    __fmul_rn(w11, u8f(ptr[stride + 1])));
+          val = (uint8_t)I;
+        }
+      }
+      border[y * 10 + x] = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Matcher::findMatchDirect(const Point&, const Frame&, Vector2d&) after getCloseViewObs (src/matcher.cpp:159-211):
-// in-frame test, warp::getWarpMatrixAffine (:42-71), getBestSearchLevel (:73-87), warp::warpAffine (:89-133,
-// vk::interpolateMat_8u), createPatchFromPatchWithBorder (:148-157), align2D / align1D at the search level.
-// One thread per candidate.  The double-precision geometry is written with explicit round-to-nearest intrinsics
-// so that the compiler cannot contract a*b+c into an FMA: A_cur_ref, the search level, every byte of the warped
-// patch and therefore the refined position are bit-identical to the reference's scalar code.
+// in-frame test, affine warp, search level, warped patch, align2D / align1D at the search level.  One thread per
+// candidate; the refined position is bit-identical to the reference's scalar code.
 __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArgs a) {
   __shared__ __align__(4) uint8_t s_border[kA2Threads][108];  // 100 used; 27-word pitch (odd) keeps the threads of a warp on distinct banks
   const int tid = threadIdx.x;
   const int i = blockIdx.x * kA2Threads + tid;
   if (i >= a.n) return;
   const size_t I = (size_t)i;
+  const CamP cam{a.fx, a.fy, a.cx, a.cy, a.width, a.height};
   const double px_ref0 = a.ref_px[2 * I], px_ref1 = a.ref_px[2 * I + 1];
   const int level_ref = a.ref_level[i];
   const int r = a.ref_index[i], c = a.cur_index[i];
@@ -311,96 +400,20 @@ __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArg
   a.out_success[i] = 0;
   a.out_level[i] = -1;
   // :169-171  cam.isInFrame(px.cast<int>() / (1 << level), halfpatch_size_ + 2, level)
-  {
-    const int ox = (int)px_ref0 / (1 << level_ref), oy = (int)px_ref1 / (1 << level_ref);
-    const int b = 6;
-    if (!(ox >= b && ox < a.width / (1 << level_ref) - b && oy >= b && oy < a.height / (1 << level_ref) - b)) return;
-  }
+  if (!cam_in_frame(cam, (int)px_ref0 / (1 << level_ref), (int)px_ref1 / (1 << level_ref), 6, level_ref)) return;
   const Pose T_w_ref = pose_inverse(pose_load(a.T_ref_w + 7 * (size_t)r));
   const Pose T_cur_ref = pose_mul(pose_load(a.T_cur_w + 7 * (size_t)c), T_w_ref);
   const V3 pos{a.pos[3 * I], a.pos[3 * I + 1], a.pos[3 * I + 2]};
   const V3 f_ref{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
   const double depth_ref = v_norm(v_sub(T_w_ref.t, pos));
-  auto cam2world = [&](double u, double v) {  // PinholeCamera::cam2world, undistorted, then normalized()
-    const V3 xyz{DD(DS(u, a.cx), a.fx), DD(DS(v, a.cy), a.fy), 1.0};
-    const double n = v_norm(xyz);
-    return V3{DD(xyz.x, n), DD(xyz.y, n), DD(xyz.z, n)};
-  };
-  auto world2cam = [&](V3 p, double& u, double& v) {  // world2cam(project2d(xyz))
-    u = DA(DM(a.fx, DD(p.x, p.z)), a.cx);
-    v = DA(DM(a.fy, DD(p.y, p.z)), a.cy);
-  };
-  // ---- warp::getWarpMatrixAffine ----
   double A00, A01, A10, A11;
-  {
-    const V3 xyz_ref = v_scale(f_ref, depth_ref);
-    const double scale_ref = (double)(1 << level_ref);
-    const double step = DM(5.0, scale_ref), zero = DM(0.0, scale_ref);
-    V3 xyz_du = cam2world(DA(px_ref0, step), DA(px_ref1, zero));
-    V3 xyz_dv = cam2world(DA(px_ref0, zero), DA(px_ref1, step));
-    xyz_du = v_scale(xyz_du, DD(xyz_ref.z, xyz_du.z));
-    xyz_dv = v_scale(xyz_dv, DD(xyz_ref.z, xyz_dv.z));
-    double pc0, pc1, pu0, pu1, pv0, pv1;
-    world2cam(pose_act(T_cur_ref, xyz_ref), pc0, pc1);
-    world2cam(pose_act(T_cur_ref, xyz_du), pu0, pu1);
-    world2cam(pose_act(T_cur_ref, xyz_dv), pv0, pv1);
-    A00 = DD(DS(pu0, pc0), 5.0), A10 = DD(DS(pu1, pc1), 5.0);
-    A01 = DD(DS(pv0, pc0), 5.0), A11 = DD(DS(pv1, pc1), 5.0);
-  }
-  // ---- warp::getBestSearchLevel ----
+  warp_matrix_affine(cam, px_ref0, px_ref1, f_ref, depth_ref, T_cur_ref, level_ref, A00, A01, A10, A11);
   const double det = DS(DM(A00, A11), DM(A10, A01));
-  int search_level = 0;
-  {
-    double D = det;
-    const int max_level = a.n_pyr_levels - 1;
-    while (D > 3.0 && search_level < max_level) {
-      search_level += 1;
-      D = DM(D, 0.25);
-    }
-  }
+  const int search_level = best_search_level(det, a.n_pyr_levels - 1);
   a.out_level[i] = search_level;
-  // ---- warp::warpAffine into the 10x10 patch with border ----
   uint8_t* border = s_border[tid];
-  {
-    const double invdet = DD(1.0, det);
-    const float R00 = (float)DM(A11, invdet), R10 = (float)DM(-A10, invdet);
-    const float R01 = (float)DM(-A01, invdet), R11 = (float)DM(A00, invdet);
-    const bool bad = isnan(R00);  // "Affine warp is NaN": the reference leaves the (zeroed) patch untouched
-    const int cols = a.width >> level_ref, rows = a.height >> level_ref;
-    const uint8_t* img = a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref];
-    const int stride = (int)a.ref_pitch[level_ref];
-    const float fs = (float)(1 << level_ref);
-    const float pr0 = __fdiv_rn((float)px_ref0, fs), pr1 = __fdiv_rn((float)px_ref1, fs);
-    const float ss = (float)(1 << search_level);
-    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
-    for (int y = 0; y < 10; ++y) {
-      const float p1 = __fmul_rn((float)(y - 5), ss);
-      for (int x = 0; x < 10; ++x) {
-        uint8_t val = 0;
-        if (!bad) {
-          const float p0 = __fmul_rn((float)(x - 5), ss);
-          const float q0 = __fadd_rn(__fadd_rn(__fmul_rn(R00, p0), __fmul_rn(R01, p1)), pr0);
-          const float q1 = __fadd_rn(__fadd_rn(__fmul_rn(R10, p0), __fmul_rn(R11, p1)), pr1);
-          if (!(q0 < 0 || q1 < 0 || q0 >= xmax || q1 >= ymax)) {
-            // vk::interpolateMat_8u
-            const float fx = floorf(q0), fy = floorf(q1);
-            const int ix = (int)fx, iy = (int)fy;
-            const float sx = __fsub_rn(q0, fx), sy = __fsub_rn(q1, fy);
-            const float w00 = __fmul_rn(__fsub_rn(1.0f, sx), __fsub_rn(1.0f, sy));
-            const float w01 = __fmul_rn(__fsub_rn(1.0f, sx), sy);
-            const float w10 = __fmul_rn(sx, __fsub_rn(1.0f, sy));
-            const float w11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, w00), w01), w10);
-            const uint8_t* ptr = img + (size_t)iy * stride + ix;
-            const float I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, u8f(ptr[0])), __fmul_rn(w01, u8f(ptr[stride]))),
-                                                __fmul_rn(w10, u8f(ptr[1]))),
-                                      __fmul_rn(w11, u8f(ptr[stride + 1])));
-            val = (uint8_t)I;
-          }
-        }
-        border[y * 10 + x] = val;
-      }
-    }
-  }
+  warp_affine_patch(A00, A01, A10, A11, det, a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref], (int)a.ref_pitch[level_ref],
+                    a.width >> level_ref, a.height >> level_ref, px_ref0, px_ref1, level_ref, search_level, border);
   // ---- align at the search level; the 8x8 reference patch is the interior of the border patch ----
   const double scale = (double)(1 << search_level);
   float u = (float)DD(a.px_cur[2 * I], scale), v = (float)DD(a.px_cur[2 * I + 1], scale);
@@ -424,11 +437,246 @@ __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArg
   a.out_success[i] = ok ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Depth-filter point-seed update: the body of DepthFilter::updatePointSeeds (src/depth_filter.cpp:270-365) with
+// Matcher::findEpipolarMatchDirect (src/matcher.cpp:277-420), depthFromTriangulation (:135-146), the ZMSSD patch score
+// (rpg_vikit patch_score.h; packed-byte dot products, exact integer arithmetic), DepthFilter::computeTau (:568-584)
+// and DepthFilter::updatePointSeed (:489-512).  One thread per seed.  Everything up to and including the
+// triangulated depth z is bit-identical to the scalar code; computeTau and the Gaussian pdf go through
+// acos/sin/atan/expf, whose last bit differs between libm implementations, so the updated seed agrees to float
+// round-off (tests/test_depth_filter.py states the tolerance).
+__device__ __forceinline__ bool depth_from_triangulation(const Pose& T, V3 f_ref, V3 f_cur, double& depth) {
+  double R[3][3];
+  q_to_matrix(T.q, R);
+  double A0[3], A1[3] = {f_cur.x, f_cur.y, f_cur.z};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) A0[i] = DA(DA(DM(R[i][0], f_ref.x), DM(R[i][1], f_ref.y)), DM(R[i][2], f_ref.z));
+  const double a00 = DA(DA(DM(A0[0], A0[0]), DM(A0[1], A0[1])), DM(A0[2], A0[2]));
+  const double a01 = DA(DA(DM(A0[0], A1[0]), DM(A0[1], A1[1])), DM(A0[2], A1[2]));
+  const double a10 = DA(DA(DM(A1[0], A0[0]), DM(A1[1], A0[1])), DM(A1[2], A0[2]));
+  const double a11 = DA(DA(DM(A1[0], A1[0]), DM(A1[1], A1[1])), DM(A1[2], A1[2]));
+  const double det = DS(DM(a00, a11), DM(a10, a01));
+  if (det < 0.000001) return false;
+  const double invdet = DD(1.0, det);
+  const double M00 = -DM(a11, invdet), M01 = -DM(-a01, invdet);  // -(AtA.inverse()), first row
+  const double N0 = DA(DM(M00, A0[0]), DM(M01, A1[0])), N1 = DA(DM(M00, A0[1]), DM(M01, A1[1])), N2 = DA(DM(M00, A0[2]), DM(M01, A1[2]));
+  depth = fabs(DA(DA(DM(N0, T.t.x), DM(N1, T.t.y)), DM(N2, T.t.z)));
+  return true;
+}
+
+__global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs a) {
+  __shared__ __align__(4) uint8_t s_border[kA2Threads][108];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kA2Threads + tid;
+  if (i >= a.n) return;
+  const size_t I = (size_t)i;
+  const CamP cam{a.fx, a.fy, a.cx, a.cy, a.width, a.height};
+  float sa = a.a[i], sb = a.b[i], smu = a.mu[i], ssig = a.sigma2[i];
+  const float z_range = a.z_range[i];
+  int status = 0;
+  const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+  double z = kNaN, pxc0 = kNaN, pxc1 = kNaN;
+  const int r = a.ref_index[i], c = a.cur_index[i];
+  const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
+  const V3 f{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
+  const double px_ref0 = a.ref_px[2 * I], px_ref1 = a.ref_px[2 * I + 1];
+  const int level_ref = a.ref_level[i];
+  uint8_t* border = s_border[tid];
+  do {
+    // ---- visibility of the seed in the current frame (depth_filter.cpp:291-304) ----
+    const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));
+    const V3 xyz_f = pose_act(pose_inverse(T_ref_cur), v_scale(f, DD(1.0, (double)smu)));
+    if (xyz_f.z < 0.0) break;
+    {
+      double u, v;
+      world2cam(cam, xyz_f, u, v);
+      const int ox = d2i_x86(u), oy = d2i_x86(v);
+      if (!(ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height)) break;
+    }
+    const float sq = __fsqrt_rn(ssig);
+    const float z_inv_min = __fadd_rn(smu, sq);
+    const float dmin = __fsub_rn(smu, sq);
+    const float z_inv_max = (dmin < 0.00000001f) ? 0.00000001f : dmin;  // std::max(dmin, 1e-8f)
+    const double d_estimate = DD(1.0, (double)smu), d_min = DD(1.0, (double)z_inv_min), d_max = DD(1.0, (double)z_inv_max);
+    status = 1;  // no match unless the search below succeeds; b is incremented at the end (:314)
+    // ---- Matcher::findEpipolarMatchDirect ----
+    const Pose T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
+    const V3 pa = pose_act(T_cur_ref, v_scale(f, d_min)), pb = pose_act(T_cur_ref, v_scale(f, d_max));
+    const double Au = DD(pa.x, pa.z), Av = DD(pa.y, pa.z), Bu = DD(pb.x, pb.z), Bv = DD(pb.y, pb.z);
+    const double epi0 = DS(Au, Bu), epi1 = DS(Av, Bv);
+    double A00, A01, A10, A11;
+    warp_matrix_affine(cam, px_ref0, px_ref1, f, d_estimate, T_cur_ref, level_ref, A00, A01, A10, A11);
+    if (a.is_edgelet && a.is_edgelet[i] && a.edgelet_filtering) {  // :300-310
+      const double g0 = a.ref_grad[2 * I], g1 = a.ref_grad[2 * I + 1];
+      double c0 = DA(DM(A00, g0), DM(A01, g1)), c1 = DA(DM(A10, g0), DM(A11, g1));
+      const double nc = __dsqrt_rn(DA(DM(c0, c0), DM(c1, c1)));
+      c0 = DD(c0, nc), c1 = DD(c1, nc);
+      const double ne = __dsqrt_rn(DA(DM(epi0, epi0), DM(epi1, epi1)));
+      const double cosangle = fabs(DA(DM(c0, DD(epi0, ne)), DM(c1, DD(epi1, ne))));
+      if (cosangle < a.edgelet_max_angle) break;
+    }
+    const double det = DS(DM(A00, A11), DM(A10, A01));
+    const int search_level = best_search_level(det, a.n_pyr_levels - 1);
+    const double pxA0 = DA(DM(cam.fx, Au), cam.cx), pxA1 = DA(DM(cam.fy, Av), cam.cy);
+    const double pxB0 = DA(DM(cam.fx, Bu), cam.cx), pxB1 = DA(DM(cam.fy, Bv), cam.cy);
+    const double dAB0 = DS(pxA0, pxB0), dAB1 = DS(pxA1, pxB1);
+    const double scale = (double)(1 << search_level);
+    const double epi_length = DD(__dsqrt_rn(DA(DM(dAB0, dAB0), DM(dAB1, dAB1))), scale);
+    warp_affine_patch(A00, A01, A10, A11, det, a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref], (int)a.ref_pitch[level_ref],
+                      a.width >> level_ref, a.height >> level_ref, px_ref0, px_ref1, level_ref, search_level, border);
+    const uint8_t* cur = a.cur_img[search_level] + (size_t)c * a.cur_stride[search_level];
+    const int ccols = a.width >> search_level, crows = a.height >> search_level;
+    const int cur_step = (int)a.cur_pitch[search_level];
+    const uint8_t* ref = border + 11;
+    float dir0, dir1;
+    {  // (px_A - px_B).cast<float>().normalized()
+      const float fx_ = (float)dAB0, fy_ = (float)dAB1;
+      const float n = __fsqrt_rn(__fadd_rn(__fmul_rn(fx_, fx_), __fmul_rn(fy_, fy_)));
+      dir0 = __fdiv_rn(fx_, n), dir1 = __fdiv_rn(fy_, n);
+    }
+    // sub-pixel refinement at the search level followed by triangulation (:326-342, :396-413)
+    auto refine_and_triangulate = [&](double start0, double start1) -> bool {
+      float u = (float)DD(start0, scale), v = (float)DD(start1, scale);
+      bool res;
+      if (a.align_1d) {
+        double h_inv;
+        res = align1d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, dir0, dir1, u, v, h_inv);
+      } else {
+        res = align2d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, u, v);
+      }
+      if (!res) return false;
+      pxc0 = DM((double)u, scale), pxc1 = DM((double)v, scale);
+      return depth_from_triangulation(T_cur_ref, f, cam2world(cam, pxc0, pxc1), z);
+    };
+    const float elf = fabsf((float)epi_length);
+    if (epi_length < 2.0 && !isnan(elf) && !isinf(elf)) {
+      pxc0 = DD(DA(pxA0, pxB0), 2.0), pxc1 = DD(DA(pxA1, pxB1), 2.0);
+      if (refine_and_triangulate(pxc0, pxc1)) status = 2;
+      break;
+    }
+    const double qsteps = DD(epi_length, 0.7);
+    if (!(qsteps < 9.0e18)) break;  // NaN / beyond size_t: the x86 conversion yields 2^63, i.e. "too many steps"
+    unsigned long long n_steps = (unsigned long long)qsteps;
+    if (n_steps > (unsigned long long)a.max_epi_search_steps) break;
+    const double step0 = DD(epi0, (double)n_steps), step1 = DD(epi1, (double)n_steps);
+    // ZMSSD of the warped 8x8 patch against the integer-pixel patches along the epipolar line (:354-391)
+    uint32_t refw[16];
+    uint32_t sumA = 0, sumAA = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const uint8_t* p = ref + y * 10;
+      const uint32_t w0 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+      const uint32_t w1 = p[4] | (p[5] << 8) | (p[6] << 16) | ((uint32_t)p[7] << 24);
+      refw[2 * y] = w0, refw[2 * y + 1] = w1;
+      sumA = __dp4a(w0, 0x01010101u, sumA), sumA = __dp4a(w1, 0x01010101u, sumA);
+      sumAA = __dp4a(w0, w0, sumAA), sumAA = __dp4a(w1, w1, sumAA);
+    }
+    int zmssd_best = 2000 * 64;
+    double uvb0 = 0.0, uvb1 = 0.0;
+    double uv0 = DS(Bu, step0), uv1 = DS(Bv, step1);
+    int last0 = 0, last1 = 0;
+    ++n_steps;
+    for (unsigned long long k = 0; k < n_steps; ++k, uv0 = DA(uv0, step0), uv1 = DA(uv1, step1)) {
+      const double px0 = DA(DM(cam.fx, uv0), cam.cx), px1 = DA(DM(cam.fy, uv1), cam.cy);
+      const int pxi0 = d2i_x86(DA(DD(px0, scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, scale), 0.5));
+      if (pxi0 == last0 && pxi1 == last1) continue;
+      last0 = pxi0, last1 = pxi1;
+      if (!cam_in_frame(cam, pxi0, pxi1, 8, search_level)) continue;
+      const uint8_t* p = cur + (size_t)(pxi1 - 4) * cur_step + (pxi0 - 4);
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+      const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+      uint32_t sumB = 0, sumBB = 0, sumAB = 0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        const uint32_t* wr = w + (size_t)y * (cur_step >> 2);
+        const uint32_t x0 = __ldg(wr), x1 = __ldg(wr + 1), x2 = __ldg(wr + 2);
+        const uint32_t c0 = __funnelshift_r(x0, x1, sh), c1 = __funnelshift_r(x1, x2, sh);
+        sumB = __dp4a(c0, 0x01010101u, sumB), sumB = __dp4a(c1, 0x01010101u, sumB);
+        sumBB = __dp4a(c0, c0, sumBB), sumBB = __dp4a(c1, c1, sumBB);
+        sumAB = __dp4a(c0, refw[2 * y], sumAB), sumAB = __dp4a(c1, refw[2 * y + 1], sumAB);
+      }
+      const int iA = (int)sumA, iAA = (int)sumAA, iB = (int)sumB, iBB = (int)sumBB, iAB = (int)sumAB;
+      const int zmssd = iAA - 2 * iAB + iBB - (iA * iA - 2 * iA * iB + iB * iB) / 64;
+      if (zmssd < zmssd_best) zmssd_best = zmssd, uvb0 = uv0, uvb1 = uv1;
+    }
+    if (zmssd_best < 2000 * 64) {
+      pxc0 = DA(DM(cam.fx, uvb0), cam.cx), pxc1 = DA(DM(cam.fy, uvb1), cam.cy);
+      if (a.subpix_refinement) {
+        if (refine_and_triangulate(pxc0, pxc1)) status = 2;
+      } else {
+        const V3 u3{uvb0, uvb1, 1.0};
+        const double n = v_norm(u3);
+        if (depth_from_triangulation(T_cur_ref, f, V3{DD(u3.x, n), DD(u3.y, n), DD(u3.z, n)}, z)) status = 2;
+      }
+    }
+    if (status == 2) {
+      // ---- computeTau (:568-584) and updatePointSeed (:489-512) ----
+      const double px_error_angle = atan(1.0 / (2.0 * fabs(cam.fx))) * 2.0;
+      const V3 t = T_ref_cur.t;
+      const V3 av = v_sub(v_scale(f, z), t);
+      const double t_norm = v_norm(t), a_norm = v_norm(av);
+      const double alpha = acos(DD(DA(DA(DM(f.x, t.x), DM(f.y, t.y)), DM(f.z, t.z)), t_norm));
+      const double beta = acos(DD(DA(DA(DM(av.x, -t.x), DM(av.y, -t.y)), DM(av.z, -t.z)), DM(t_norm, a_norm)));
+      const double beta_plus = DA(beta, px_error_angle);
+      const double gamma_plus = DS(DS(3.14159265, alpha), beta_plus);  // plsvo::PI
+      const double z_plus = DD(DM(t_norm, sin(beta_plus)), sin(gamma_plus));
+      const double tau = DS(z_plus, z);
+      const double zmt = DS(z, tau);
+      const double lo = (0.0000001 < zmt) ? zmt : 0.0000001;  // std::max(0.0000001, z - tau)
+      const double tau_inverse = DM(0.5, DS(DD(1.0, lo), DD(1.0, DA(z, tau))));
+      const float x = (float)DD(1.0, z), tau2 = (float)DM(tau_inverse, tau_inverse);
+      const float norm_scale = __fsqrt_rn(__fadd_rn(ssig, tau2));
+      if (!isnan(norm_scale)) {
+        float ex = __fsub_rn(x, smu);
+        ex = __fmul_rn(ex, -ex);
+        ex = __fdiv_rn(ex, __fmul_rn(__fmul_rn(2.0f, norm_scale), norm_scale));
+        float pdf = expf(ex);
+        pdf = __fdiv_rn(pdf, __fmul_rn(norm_scale, __fsqrt_rn(__fmul_rn(2.0f, 3.14159274101257324f))));
+        if (isinf(x)) pdf = 0.0f;
+        const float s2 = (float)DD(1.0, DA(DD(1.0, (double)ssig), DD(1.0, (double)tau2)));
+        const float m = __fmul_rn(s2, __fadd_rn(__fdiv_rn(smu, ssig), __fdiv_rn(x, tau2)));
+        const float ab = __fadd_rn(sa, sb);
+        float C1 = __fmul_rn(__fdiv_rn(sa, ab), pdf);
+        float C2 = (float)DD(DM((double)__fdiv_rn(sb, ab), 1.0), (double)z_range);
+        const float nc = __fadd_rn(C1, C2);
+        C1 = __fdiv_rn(C1, nc), C2 = __fdiv_rn(C2, nc);
+        const double ab1 = DA((double)ab, 1.0), ab2 = DA((double)ab, 2.0);
+        const float fq = (float)DA(DD(DM((double)C1, DA((double)sa, 1.0)), ab1), DD((double)__fmul_rn(C2, sa), ab1));
+        const float abf1 = __fadd_rn(ab, 1.0f), abf2 = __fadd_rn(ab, 2.0f);
+        const float eq = (float)DA(DD(DM(DM((double)C1, DA((double)sa, 1.0)), DA((double)sa, 2.0)), DM(ab1, ab2)),
+                                   (double)__fdiv_rn(__fmul_rn(__fmul_rn(C2, sa), __fadd_rn(sa, 1.0f)), __fmul_rn(abf1, abf2)));
+        const float mu_new = __fadd_rn(__fmul_rn(C1, m), __fmul_rn(C2, smu));
+        ssig = __fsub_rn(__fadd_rn(__fmul_rn(C1, __fadd_rn(s2, __fmul_rn(m, m))), __fmul_rn(C2, __fadd_rn(ssig, __fmul_rn(smu, smu)))),
+                         __fmul_rn(mu_new, mu_new));
+        smu = mu_new;
+        sa = __fdiv_rn(__fsub_rn(eq, fq), __fsub_rn(fq, __fdiv_rn(eq, fq)));
+        sb = __fdiv_rn(__fmul_rn(sa, __fsub_rn(1.0f, fq)), fq);
+      }
+    }
+  } while (false);
+  if (status == 1) {
+    sb = __fadd_rn(sb, 1.0f);
+    z = kNaN;
+  }
+  a.out_a[i] = sa, a.out_b[i] = sb, a.out_mu[i] = smu, a.out_sigma2[i] = ssig;
+  a.out_status[i] = status;
+  a.out_converged[i] = (status == 2 && (double)__fsqrt_rn(ssig) < DD((double)z_range, a.convergence_thresh)) ? 1 : 0;
+  a.out_depth[i] = z;
+  a.out_px_cur[2 * I] = pxc0, a.out_px_cur[2 * I + 1] = pxc1;
+}
+
 }  // namespace
 
 cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;
   match_direct_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  seed_update_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -164,6 +164,43 @@ struct MatchArgs {
 cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
+struct SeedArgs {
+  int n, n_iter, n_pyr_levels, width, height, max_epi_search_steps;
+  int align_1d, subpix_refinement, edgelet_filtering;
+  double edgelet_max_angle, convergence_thresh;
+  double fx, fy, cx, cy;
+  const uint8_t* ref_img[PLSVO_MAX_LEVELS];
+  uint32_t ref_pitch[PLSVO_MAX_LEVELS];
+  size_t ref_stride[PLSVO_MAX_LEVELS];
+  const uint8_t* cur_img[PLSVO_MAX_LEVELS];
+  uint32_t cur_pitch[PLSVO_MAX_LEVELS];
+  size_t cur_stride[PLSVO_MAX_LEVELS];
+  const double* T_ref_w;
+  const double* T_cur_w;
+  const int32_t* ref_index;
+  const int32_t* cur_index;
+  const double* ref_px;
+  const double* ref_f;
+  const int32_t* ref_level;
+  const uint8_t* is_edgelet;  // may be null
+  const double* ref_grad;     // may be null
+  const float* a;
+  const float* b;
+  const float* mu;
+  const float* z_range;
+  const float* sigma2;
+  float* out_a;
+  float* out_b;
+  float* out_mu;
+  float* out_sigma2;
+  int32_t* out_status;
+  uint8_t* out_converged;
+  double* out_depth;
+  double* out_px_cur;
+};
+cudaError_t seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
 struct StructOptArgs {
   int n_points, n_segs, n_iter_pts, n_iter_segs;
   const double* T_f_w;

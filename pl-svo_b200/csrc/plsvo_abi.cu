@@ -62,6 +62,7 @@ struct plsvo_ctx_impl {
   DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv, f_dir, f_ohinv;  // align2D / align1D
   DevBuf m_ref_img, m_cur_img, m_T_ref, m_T_cur, m_ridx, m_cidx, m_px, m_f, m_lvl, m_edge, m_grad, m_pos, m_pxc, m_opx, m_osucc,
       m_olvl;  // findMatchDirect
+  DevBuf d_sa, d_sb, d_smu, d_szr, d_ssig, d_sout;  // depth-filter seeds
   DevBuf s_T, s_pb, s_pf, s_pof, s_pp, s_sb, s_sf, s_ssf, s_sef, s_sp, s_ep, s_out;  // structure optimisation
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
@@ -191,7 +192,8 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
                     &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
                     &c->s_pp,        &c->s_sb,       &c->s_sf,        &c->s_ssf,        &c->s_sef,       &c->s_sp,
-                    &c->s_ep,        &c->s_out,      &c->p_T,
+                    &c->s_ep,        &c->s_out,      &c->d_sa,        &c->d_sb,         &c->d_smu,       &c->d_szr,
+                    &c->d_ssig,      &c->d_sout,     &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -1118,6 +1120,82 @@ extern "C" int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_b
   }
   if (np && out->pt_iters) CK(cudaMemcpyAsync(out->pt_iters, a.out_pt_iters, np * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   if (ns && out->seg_iters) CK(cudaMemcpyAsync(out->seg_iters, a.out_seg_iters, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return PLSVO_OK;
+}
+
+extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batch* in, const plsvo_seed_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (in->n_seeds < 0 || in->n_ref_images <= 0 || in->n_cur_images <= 0 || in->cam.width <= 0 || in->cam.height <= 0 ||
+      in->n_iter < 0 || in->n_pyr_levels < 1 || in->n_pyr_levels > PLSVO_MAX_LEVELS || in->max_epi_search_steps < 0)
+    return fail(c, PLSVO_ERR_INVALID, "seed batch description");
+  if (in->n_seeds == 0) return PLSVO_OK;
+  if (!in->T_ref_w || !in->T_cur_w || !in->ref_index || !in->cur_index || !in->ref_px || !in->ref_f || !in->ref_level || !in->a ||
+      !in->b || !in->mu || !in->z_range || !in->sigma2 || !out->a || !out->b || !out->mu || !out->sigma2 || !out->status)
+    return fail(c, PLSVO_ERR_INVALID, "seed arrays missing");
+  if (in->is_edgelet && !in->ref_grad) return fail(c, PLSVO_ERR_INVALID, "edgelets need ref_grad");
+  const size_t n = (size_t)in->n_seeds;
+  for (int l = 0; l < in->n_pyr_levels; ++l) {
+    if (!in->cur_img[l]) return fail(c, PLSVO_ERR_INVALID, "current pyramid level missing below n_pyr_levels");
+    // the reference strides the ZMSSD patch with Mat::cols (matcher.cpp:380-382): only dense images mean the same thing
+    if (in->cur_pitch[l] != (size_t)(in->cam.width >> l)) return fail(c, PLSVO_ERR_INVALID, "current images must be dense (pitch == level width)");
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const int l = in->ref_level[i];
+    if (l < 0 || l >= PLSVO_MAX_LEVELS || !in->ref_img[l] || in->ref_index[i] < 0 || in->ref_index[i] >= in->n_ref_images ||
+        in->cur_index[i] < 0 || in->cur_index[i] >= in->n_cur_images)
+      return fail(c, PLSVO_ERR_INVALID, "seed refers to a missing level or frame");
+  }
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  SeedArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = in->n_seeds, a.n_iter = in->n_iter, a.n_pyr_levels = in->n_pyr_levels, a.max_epi_search_steps = in->max_epi_search_steps;
+  a.align_1d = in->align_1d, a.subpix_refinement = in->subpix_refinement, a.edgelet_filtering = in->epi_search_edgelet_filtering;
+  a.edgelet_max_angle = in->epi_search_edgelet_max_angle, a.convergence_thresh = in->seed_convergence_sigma2_thresh;
+  a.width = in->cam.width, a.height = in->cam.height;
+  a.fx = in->cam.fx, a.fy = in->cam.fy, a.cx = in->cam.cx, a.cy = in->cam.cy;
+  int rc = stage_pyramid(c, c->m_ref_img, in->ref_img, in->ref_pitch, in->ref_stride, in->n_ref_images, a.width, a.height, s, a.ref_img,
+                         a.ref_pitch, a.ref_stride);
+  if (rc != PLSVO_OK) return rc;
+  rc = stage_pyramid(c, c->m_cur_img, in->cur_img, in->cur_pitch, in->cur_stride, in->n_cur_images, a.width, a.height, s, a.cur_img,
+                     a.cur_pitch, a.cur_stride);
+  if (rc != PLSVO_OK) return rc;
+  CK(up(c->m_T_ref, in->T_ref_w, (size_t)in->n_ref_images * 7, s, &a.T_ref_w));
+  CK(up(c->m_T_cur, in->T_cur_w, (size_t)in->n_cur_images * 7, s, &a.T_cur_w));
+  CK(up(c->m_ridx, in->ref_index, n, s, &a.ref_index));
+  CK(up(c->m_cidx, in->cur_index, n, s, &a.cur_index));
+  CK(up(c->m_px, in->ref_px, n * 2, s, &a.ref_px));
+  CK(up(c->m_f, in->ref_f, n * 3, s, &a.ref_f));
+  CK(up(c->m_lvl, in->ref_level, n, s, &a.ref_level));
+  CK(up(c->m_edge, in->is_edgelet, n, s, &a.is_edgelet));
+  CK(up(c->m_grad, in->is_edgelet ? in->ref_grad : nullptr, n * 2, s, &a.ref_grad));
+  CK(up(c->d_sa, in->a, n, s, &a.a));
+  CK(up(c->d_sb, in->b, n, s, &a.b));
+  CK(up(c->d_smu, in->mu, n, s, &a.mu));
+  CK(up(c->d_szr, in->z_range, n, s, &a.z_range));
+  CK(up(c->d_ssig, in->sigma2, n, s, &a.sigma2));
+  // outputs: [px_cur 2n f64][depth n f64][a b mu sigma2 n f32 each][status n i32][converged n u8]
+  CK(ensure(c->d_sout, n * (16 + 8 + 16 + 4 + 1) + 64));
+  a.out_px_cur = static_cast<double*>(c->d_sout.p);
+  a.out_depth = a.out_px_cur + 2 * n;
+  a.out_a = reinterpret_cast<float*>(a.out_depth + n);
+  a.out_b = a.out_a + n, a.out_mu = a.out_b + n, a.out_sigma2 = a.out_mu + n;
+  a.out_status = reinterpret_cast<int32_t*>(a.out_sigma2 + n);
+  a.out_converged = reinterpret_cast<uint8_t*>(a.out_status + n);
+  CK(kernel_timer(c, 0, s));
+  CK(seed_update_kernel_launch(a, s));
+  CK(kernel_timer(c, 1, s));
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out->a, a.out_a, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->b, a.out_b, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->mu, a.out_mu, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->sigma2, a.out_sigma2, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->status, a.out_status, n * 4, cudaMemcpyDeviceToHost, s));
+  if (out->converged) CK(cudaMemcpyAsync(out->converged, a.out_converged, n, cudaMemcpyDeviceToHost, s));
+  if (out->depth) CK(cudaMemcpyAsync(out->depth, a.out_depth, n * 8, cudaMemcpyDeviceToHost, s));
+  if (out->px_cur) CK(cudaMemcpyAsync(out->px_cur, a.out_px_cur, n * 16, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
 }

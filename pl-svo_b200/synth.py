@@ -602,3 +602,89 @@ def make_structopt_batch(n_points: int = 2000, n_segs: int = 500, n_frames: int 
                          pt_pos_gt=c(P), seg_obs_begin=sb, seg_obs_frame=sf_, seg_obs_sf=sobs, seg_obs_ef=eobs,
                          seg_spos=c(S + rng.normal(0, pert, S.shape)), seg_epos=c(E + rng.normal(0, pert, E.shape)),
                          seg_spos_gt=c(S), seg_epos_gt=c(E))
+
+
+# ---- depth-filter point seeds ---------------------------------------------------------
+@dataclass
+class SeedData:
+    """Host arrays of one depth-filter seed batch, shaped as plsvo_seed_batch describes."""
+
+    cam: Camera
+    n_pyr_levels: int
+    ref_pyr: dict
+    cur_pyr: dict
+    T_ref_w: np.ndarray
+    T_cur_w: np.ndarray
+    ref_index: np.ndarray
+    cur_index: np.ndarray
+    ref_px: np.ndarray
+    ref_f: np.ndarray
+    ref_level: np.ndarray
+    is_edgelet: np.ndarray
+    ref_grad: np.ndarray
+    a: np.ndarray
+    b: np.ndarray
+    mu: np.ndarray
+    z_range: np.ndarray
+    sigma2: np.ndarray
+    depth_gt: np.ndarray
+    n_iter: int = 10
+    max_epi_search_steps: int = 1000
+    align_1d: bool = False
+    subpix_refinement: bool = True
+    edgelet_filtering: bool = True
+    edgelet_max_angle: float = 0.7
+    convergence_thresh: float = 200.0
+
+    @property
+    def n(self):
+        return self.ref_index.shape[0]
+
+
+def make_seed_batch(cam: Camera = VGA, n: int = 2000, n_ref: int = 3, n_cur: int = 3, n_pyr_levels: int = 3, seed: int = 9000,
+                    device: str | torch.device = "cpu", baseline: float = 0.12, edgelet_frac: float = 0.2,
+                    scene: Scene | None = None) -> SeedData:
+    """n depth-filter seeds: a feature in keyframe r (pixel, bearing, level), a Gaussian x Beta prior on its inverse
+    depth at various stages of convergence (so that epipolar segments range from sub-pixel to hundreds of pixels),
+    and a current frame c a small baseline away.  A few seeds are invisible in c, far outside or nearly converged."""
+    dev = torch.device(device)
+    scene = scene or Scene()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f64 = dict(dtype=torch.float64, device=dev)
+    xi_ref = np.concatenate([rng.uniform(-0.15, 0.15, (n_ref, 3)), rng.uniform(-0.03, 0.03, (n_ref, 3))], -1)
+    xi_cur = np.concatenate([rng.uniform(-0.15 - baseline, 0.15 + baseline, (n_cur, 3)), rng.uniform(-0.04, 0.04, (n_cur, 3))], -1)
+    xi_cur[:, 2] = rng.uniform(-0.05, 0.15, n_cur)
+    R_ref, t_ref = se3_exp_Rt(torch.tensor(xi_ref, **f64))
+    R_cur, t_cur = se3_exp_Rt(torch.tensor(xi_cur, **f64))
+    T_ref_w, T_cur_w = pose7_from_Rt(R_ref, t_ref), pose7_from_Rt(R_cur, t_cur)
+    ref_pyr = {l: np.ascontiguousarray(p.cpu().numpy()) for l, p in enumerate(build_pyramid(scene.render(cam, T_ref_w), n_pyr_levels))}
+    cur_pyr = {l: np.ascontiguousarray(p.cpu().numpy()) for l, p in enumerate(build_pyramid(scene.render(cam, T_cur_w), n_pyr_levels))}
+    ref_index = rng.integers(0, n_ref, n).astype(np.int32)
+    cur_index = rng.integers(0, n_cur, n).astype(np.int32)
+    ref_level = rng.integers(0, n_pyr_levels, n).astype(np.int32)
+    ref_px = np.stack([rng.uniform(24, cam.width - 24, n), rng.uniform(24, cam.height - 24, n)], -1)
+    px_t = torch.tensor(ref_px, **f64)
+    d = torch.stack([(px_t[:, 0] - cam.cx) / cam.fx, (px_t[:, 1] - cam.cy) / cam.fy, torch.ones_like(px_t[:, 0])], -1)
+    ref_f = d / d.norm(dim=-1, keepdim=True)
+    ridx = torch.tensor(ref_index, device=dev, dtype=torch.long)
+    pos = scene.intersect(R_ref[ridx], t_ref[ridx], d[:, None, :])[:, 0, :]
+    p_ref = (R_ref[ridx] @ pos[..., None])[..., 0] + t_ref[ridx]
+    depth = p_ref.norm(dim=-1).cpu().numpy()  # distance along the unit bearing
+    z_range = np.full(n, 1.0 / 1.2, np.float32)  # 1 / depth_min of the scene
+    stage = rng.uniform(0.0, 3.0, n)  # decades of variance reduction already achieved
+    sigma2 = (z_range.astype(np.float64) ** 2 / 36.0 * 10.0 ** (-stage)).astype(np.float32)
+    mu = (1.0 / depth + rng.normal(0, 1, n) * np.sqrt(sigma2) * 0.5).astype(np.float32)
+    mu = np.maximum(mu, 0.05).astype(np.float32)
+    a = (10.0 + rng.uniform(0, 20, n)).astype(np.float32)
+    b = (10.0 + rng.uniform(0, 5, n)).astype(np.float32)
+    k = min(6, n)
+    mu[:k] = [1e-3, 5.0, 0.4, 0.5, 0.45, 0.6][:k]        # far beyond the scene / in front of it / plausible
+    sigma2[:k] = [1e-8, 1e-4, 1e-9, 2e-2, 1e-12, 4e-2][:k]  # already converged ... very uncertain (long epipolar segments)
+    is_edgelet = (rng.uniform(size=n) < edgelet_frac).astype(np.uint8)
+    ang = rng.uniform(0, 2 * math.pi, n)
+    ref_grad = np.stack([np.cos(ang), np.sin(ang)], -1)
+    c = lambda x, t: np.ascontiguousarray(x.cpu().numpy() if isinstance(x, torch.Tensor) else x, dtype=t)  # noqa: E731
+    return SeedData(cam=cam, n_pyr_levels=n_pyr_levels, ref_pyr=ref_pyr, cur_pyr=cur_pyr, T_ref_w=c(T_ref_w, np.float64),
+                    T_cur_w=c(T_cur_w, np.float64), ref_index=ref_index, cur_index=cur_index, ref_px=c(ref_px, np.float64),
+                    ref_f=c(ref_f, np.float64), ref_level=ref_level, is_edgelet=is_edgelet, ref_grad=c(ref_grad, np.float64),
+                    a=a, b=b, mu=mu, z_range=z_range, sigma2=sigma2, depth_gt=c(depth, np.float64))

@@ -224,6 +224,31 @@ def main():
         "kernel_ms": k_ms, "e2e_ms": e_ms, "features_per_s_kernel": nfeat / (k_ms * 1e-3), "features_per_s_e2e": nfeat / (e_ms * 1e-3),
         "algorithmic_bytes": alg, "achieved_gbs": alg / (k_ms * 1e-3) / 1e9, "roofline_frac": alg / (k_ms * 1e-3) / 1e9 / peak,
         "bit_exact_vs_oracle": bool(exact), "mean_iterations": passes_pt, "cpu_oracle_features_per_s": rate, "cpu_threads": th}
+    # ---- depth-filter point-seed update (epipolar ZMSSD search + Bayesian update) ------------------------------
+    ns = args.features // 4
+    sdd = synth.make_seed_batch(n=ns, n_ref=8, n_cur=8, n_pyr_levels=3, seed=5, device=dev)
+    dfilt = api.DepthFilter(ctx)
+    dfo = {}
+
+    def run_df():
+        dfo["gpu"] = dfilt.updatePointSeeds(sdd)
+
+    k_ms, e_ms = timed(ctx, run_df, args.reps)
+    olib.plsvo_oracle_seed_update_batch.restype = C.c_int
+    sbb, keep_sd = abi.make_seed_batch(sdd)
+    cpu_sd = abi.SeedOut(ns)
+    rate, th = best_threads(lambda t: olib.plsvo_oracle_seed_update_batch(C.byref(sbb), C.byref(cpu_sd.struct), t), ns)
+    up = cpu_sd.status == abi.SEED_UPDATED
+    exact = bool(np.array_equal(dfo["gpu"].status, cpu_sd.status) and np.array_equal(dfo["gpu"].depth[up], cpu_sd.depth[up]))
+    okm = up & np.isfinite(cpu_sd.sigma2)
+    res["depth_filter_seed_update"] = {
+        "workload": f"{ns} point seeds, 8 keyframes -> 8 current VGA frames, 3 pyramid levels, 20 % edgelets "
+                    "(DepthFilter::updatePointSeeds body: visibility, findEpipolarMatchDirect, computeTau, updatePointSeed)",
+        "kernel_ms": k_ms, "e2e_ms": e_ms, "seeds_per_s_kernel": ns / (k_ms * 1e-3), "seeds_per_s_e2e": ns / (e_ms * 1e-3),
+        "status_and_depth_bit_exact_vs_oracle": exact,
+        "max_rel_diff_mu": float(np.max(np.abs(dfo["gpu"].mu[okm] - cpu_sd.mu[okm]) / np.abs(cpu_sd.mu[okm]))) if okm.any() else None,
+        "status_hist_not_visible_no_match_updated": np.bincount(cpu_sd.status, minlength=3).tolist(),
+        "cpu_oracle_seeds_per_s": rate, "cpu_threads": th}
     print(json.dumps(res, indent=1))
 
 

@@ -35,7 +35,7 @@ def main():
     n_batches = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     if not oracle_lib.build_ref():
         raise SystemExit("needs /root/reference")
-    srcs = [os.path.join(REF, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp", "feature3D_impl.cpp")]
+    srcs = [os.path.join(REF, "src", f) for f in ("sparse_img_align.cpp", "pose_optimizer.cpp", "feature.cpp", "feature_alignment.cpp", "matcher.cpp", "config.cpp", "feature3D_impl.cpp", "depth_filter.cpp")]
     subprocess.check_call(["g++", *FLAGS.split(), "-I" + os.path.join(ROOT, "oracle", "refdeps"), "-I" + os.path.join(REF, "include"),
                            "-shared", "-o", NATIVE, *srcs, os.path.join(ROOT, "oracle", "ref_harness.cpp"), "-lpthread"])
     nat = C.CDLL(NATIVE)
