@@ -482,9 +482,9 @@ __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs 
   const double px_ref0 = a.ref_px[2 * I], px_ref1 = a.ref_px[2 * I + 1];
   const int level_ref = a.ref_level[i];
   uint8_t* border = s_border[tid];
+  const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // depth_filter.cpp:291
   do {
     // ---- visibility of the seed in the current frame (depth_filter.cpp:291-304) ----
-    const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));
     const V3 xyz_f = pose_act(pose_inverse(T_ref_cur), v_scale(f, DD(1.0, (double)smu)));
     if (xyz_f.z < 0.0) break;
     {
@@ -610,51 +610,51 @@ __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs 
         if (depth_from_triangulation(T_cur_ref, f, V3{DD(u3.x, n), DD(u3.y, n), DD(u3.z, n)}, z)) status = 2;
       }
     }
-    if (status == 2) {
-      // ---- computeTau (:568-584) and updatePointSeed (:489-512) ----
-      const double px_error_angle = atan(1.0 / (2.0 * fabs(cam.fx))) * 2.0;
-      const V3 t = T_ref_cur.t;
-      const V3 av = v_sub(v_scale(f, z), t);
-      const double t_norm = v_norm(t), a_norm = v_norm(av);
-      const double alpha = acos(DD(DA(DA(DM(f.x, t.x), DM(f.y, t.y)), DM(f.z, t.z)), t_norm));
-      const double beta = acos(DD(DA(DA(DM(av.x, -t.x), DM(av.y, -t.y)), DM(av.z, -t.z)), DM(t_norm, a_norm)));
-      const double beta_plus = DA(beta, px_error_angle);
-      const double gamma_plus = DS(DS(3.14159265, alpha), beta_plus);  // plsvo::PI
-      const double z_plus = DD(DM(t_norm, sin(beta_plus)), sin(gamma_plus));
-      const double tau = DS(z_plus, z);
-      const double zmt = DS(z, tau);
-      const double lo = (0.0000001 < zmt) ? zmt : 0.0000001;  // std::max(0.0000001, z - tau)
-      const double tau_inverse = DM(0.5, DS(DD(1.0, lo), DD(1.0, DA(z, tau))));
-      const float x = (float)DD(1.0, z), tau2 = (float)DM(tau_inverse, tau_inverse);
-      const float norm_scale = __fsqrt_rn(__fadd_rn(ssig, tau2));
-      if (!isnan(norm_scale)) {
-        float ex = __fsub_rn(x, smu);
-        ex = __fmul_rn(ex, -ex);
-        ex = __fdiv_rn(ex, __fmul_rn(__fmul_rn(2.0f, norm_scale), norm_scale));
-        float pdf = expf(ex);
-        pdf = __fdiv_rn(pdf, __fmul_rn(norm_scale, __fsqrt_rn(__fmul_rn(2.0f, 3.14159274101257324f))));
-        if (isinf(x)) pdf = 0.0f;
-        const float s2 = (float)DD(1.0, DA(DD(1.0, (double)ssig), DD(1.0, (double)tau2)));
-        const float m = __fmul_rn(s2, __fadd_rn(__fdiv_rn(smu, ssig), __fdiv_rn(x, tau2)));
-        const float ab = __fadd_rn(sa, sb);
-        float C1 = __fmul_rn(__fdiv_rn(sa, ab), pdf);
-        float C2 = (float)DD(DM((double)__fdiv_rn(sb, ab), 1.0), (double)z_range);
-        const float nc = __fadd_rn(C1, C2);
-        C1 = __fdiv_rn(C1, nc), C2 = __fdiv_rn(C2, nc);
-        const double ab1 = DA((double)ab, 1.0), ab2 = DA((double)ab, 2.0);
-        const float fq = (float)DA(DD(DM((double)C1, DA((double)sa, 1.0)), ab1), DD((double)__fmul_rn(C2, sa), ab1));
-        const float abf1 = __fadd_rn(ab, 1.0f), abf2 = __fadd_rn(ab, 2.0f);
-        const float eq = (float)DA(DD(DM(DM((double)C1, DA((double)sa, 1.0)), DA((double)sa, 2.0)), DM(ab1, ab2)),
-                                   (double)__fdiv_rn(__fmul_rn(__fmul_rn(C2, sa), __fadd_rn(sa, 1.0f)), __fmul_rn(abf1, abf2)));
-        const float mu_new = __fadd_rn(__fmul_rn(C1, m), __fmul_rn(C2, smu));
-        ssig = __fsub_rn(__fadd_rn(__fmul_rn(C1, __fadd_rn(s2, __fmul_rn(m, m))), __fmul_rn(C2, __fadd_rn(ssig, __fmul_rn(smu, smu)))),
-                         __fmul_rn(mu_new, mu_new));
-        smu = mu_new;
-        sa = __fdiv_rn(__fsub_rn(eq, fq), __fsub_rn(fq, __fdiv_rn(eq, fq)));
-        sb = __fdiv_rn(__fmul_rn(sa, __fsub_rn(1.0f, fq)), fq);
-      }
-    }
   } while (false);
+  if (status == 2) {
+    // ---- computeTau (:568-584) and updatePointSeed (:489-512) ----
+    const double px_error_angle = atan(1.0 / (2.0 * fabs(cam.fx))) * 2.0;
+    const V3 t = T_ref_cur.t;
+    const V3 av = v_sub(v_scale(f, z), t);
+    const double t_norm = v_norm(t), a_norm = v_norm(av);
+    const double alpha = acos(DD(DA(DA(DM(f.x, t.x), DM(f.y, t.y)), DM(f.z, t.z)), t_norm));
+    const double beta = acos(DD(DA(DA(DM(av.x, -t.x), DM(av.y, -t.y)), DM(av.z, -t.z)), DM(t_norm, a_norm)));
+    const double beta_plus = DA(beta, px_error_angle);
+    const double gamma_plus = DS(DS(3.14159265, alpha), beta_plus);  // plsvo::PI
+    const double z_plus = DD(DM(t_norm, sin(beta_plus)), sin(gamma_plus));
+    const double tau = DS(z_plus, z);
+    const double zmt = DS(z, tau);
+    const double lo = (0.0000001 < zmt) ? zmt : 0.0000001;  // std::max(0.0000001, z - tau)
+    const double tau_inverse = DM(0.5, DS(DD(1.0, lo), DD(1.0, DA(z, tau))));
+    const float x = (float)DD(1.0, z), tau2 = (float)DM(tau_inverse, tau_inverse);
+    const float norm_scale = __fsqrt_rn(__fadd_rn(ssig, tau2));
+    if (!isnan(norm_scale)) {
+      float ex = __fsub_rn(x, smu);
+      ex = __fmul_rn(ex, -ex);
+      ex = __fdiv_rn(ex, __fmul_rn(__fmul_rn(2.0f, norm_scale), norm_scale));
+      float pdf = expf(ex);
+      pdf = __fdiv_rn(pdf, __fmul_rn(norm_scale, __fsqrt_rn(__fmul_rn(2.0f, 3.14159274101257324f))));
+      if (isinf(x)) pdf = 0.0f;
+      const float s2 = (float)DD(1.0, DA(DD(1.0, (double)ssig), DD(1.0, (double)tau2)));
+      const float m = __fmul_rn(s2, __fadd_rn(__fdiv_rn(smu, ssig), __fdiv_rn(x, tau2)));
+      const float ab = __fadd_rn(sa, sb);
+      float C1 = __fmul_rn(__fdiv_rn(sa, ab), pdf);
+      float C2 = (float)DD(DM((double)__fdiv_rn(sb, ab), 1.0), (double)z_range);
+      const float nc = __fadd_rn(C1, C2);
+      C1 = __fdiv_rn(C1, nc), C2 = __fdiv_rn(C2, nc);
+      const double ab1 = DA((double)ab, 1.0), ab2 = DA((double)ab, 2.0);
+      const float fq = (float)DA(DD(DM((double)C1, DA((double)sa, 1.0)), ab1), DD((double)__fmul_rn(C2, sa), ab1));
+      const float abf1 = __fadd_rn(ab, 1.0f), abf2 = __fadd_rn(ab, 2.0f);
+      const float eq = (float)DA(DD(DM(DM((double)C1, DA((double)sa, 1.0)), DA((double)sa, 2.0)), DM(ab1, ab2)),
+                                 (double)__fdiv_rn(__fmul_rn(__fmul_rn(C2, sa), __fadd_rn(sa, 1.0f)), __fmul_rn(abf1, abf2)));
+      const float mu_new = __fadd_rn(__fmul_rn(C1, m), __fmul_rn(C2, smu));
+      ssig = __fsub_rn(__fadd_rn(__fmul_rn(C1, __fadd_rn(s2, __fmul_rn(m, m))), __fmul_rn(C2, __fadd_rn(ssig, __fmul_rn(smu, smu)))),
+                       __fmul_rn(mu_new, mu_new));
+      smu = mu_new;
+      sa = __fdiv_rn(__fsub_rn(eq, fq), __fsub_rn(fq, __fdiv_rn(eq, fq)));
+      sb = __fdiv_rn(__fmul_rn(sa, __fsub_rn(1.0f, fq)), fq);
+    }
+  }
   if (status == 1) {
     sb = __fadd_rn(sb, 1.0f);
     z = kNaN;
