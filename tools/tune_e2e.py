@@ -17,7 +17,7 @@ for pyr in (data.ref_pyr, data.cur_pyr):
     for l in list(pyr): pyr[l] = pin(pyr[l])
 ctx = plsvo_b200.Context(0)
 al = plsvo_b200.SparseImgAlign(4, 2, 30, ctx=ctx)
-for chunks, gate in ((0, 128), (0, 256), (0, 512), (1, 0)):
+for chunks, gate in ((0, 128), (0, 192), (0, 256), (0, 384), (0, 512), (0, 1024), (1, 0)):
     os.environ['PLSVO_GATE_CHUNK'] = str(gate)
     os.environ["PLSVO_E2E_CHUNKS"] = str(chunks) if chunks else ""
     if not chunks: os.environ.pop("PLSVO_E2E_CHUNKS")
