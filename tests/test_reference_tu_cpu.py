@@ -53,6 +53,7 @@ def assert_poseopt_identical(ref, abi, data, params, rows=None):
     dict(cam="VGA", batch=6, n_pts=200, n_segs=60, seed=105, margin=6),             # features at the image border
     dict(cam="VGA", batch=6, n_pts=200, n_segs=60, seed=106, motion_t=0.15, motion_r=0.05),  # large motion: rollbacks
     dict(cam="HD720", batch=3, n_pts=300, n_segs=80, seed=107),
+    dict(cam="HD720", batch=2, n_pts=500, n_segs=150, seed=109),                    # BASELINE config 4 shape
     dict(cam="QVGA", batch=6, n_pts=64, n_segs=16, seed=108, max_level=3, min_level=0),       # down to level 0
 ])
 def test_align_restatement_is_bit_identical_to_reference_tus(ref, abi, synth, cfg):
