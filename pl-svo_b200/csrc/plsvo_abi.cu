@@ -28,6 +28,9 @@ struct plsvo_ctx_impl {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;  // second stream of the chunked host-buffer pipeline
+  cudaStream_t rr_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // extra copy streams: the arrays of a chunk go round-robin
+  cudaEvent_t rr_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int rr_n = 0, rr_i = 0;  // rr_n > 0 only while the gated pipeline enqueues its copies
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t start_ev = nullptr;
   cudaEvent_t k_ev[2] = {nullptr, nullptr};  // around the kernel of the last pyramid / align2D / align1D call
@@ -201,6 +204,10 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
   for (DevBuf* b : bufs) release(*b);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_out) cudaFreeHost(c->h_out);
+  for (int k = 0; k < 4; ++k) {
+    if (c->rr_stream[k]) cudaStreamDestroy(c->rr_stream[k]);
+    if (c->rr_ev[k]) cudaEventDestroy(c->rr_ev[k]);
+  }
   if (c->copy_stream) {
     cudaStreamDestroy(c->copy_stream);
     for (int k = 0; k < 8; ++k) cudaEventDestroy(c->chunk_ev[k]);
@@ -296,6 +303,13 @@ cudaError_t up_range(DevBuf& buf, const T* host, size_t per_item, size_t B, size
 
 // Host arrays -> device layout for pairs [b0,b1).  prepare = validate, size the buffers for the whole batch
 // and lay out the pyramid levels; later chunks of the same batch only copy.
+// Stream for the next host->device array copy: the caller's stream, or — while the gated pipeline is enqueuing a chunk —
+// one of the extra copy streams in turn, so that the per-copy start-up latency of one array overlaps the transfer of another.
+static inline cudaStream_t pick_copy_stream(plsvo_ctx_impl* c, cudaStream_t s) {
+  if (c->rr_n <= 0 || s != c->copy_stream) return s;
+  return c->rr_stream[c->rr_i++ % c->rr_n];
+}
+
 int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, size_t b1, cudaStream_t s, int mode) {
   // mode 0: copy [b0,b1) only; 1: validate + lay out + copy + host-side sizing; 2: validate + lay out + copy;
   // 3: host-side sizing only
@@ -363,8 +377,8 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
     if (uniform && h->img_pitch[l] == a.pitch[l]) {
       // host stack already has the device layout: one linear copy per frame set
-      CK(cudaMemcpyAsync(dr, hr, a.stride[l] * nb, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(dc, hc, a.stride[l] * nb, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(dr, hr, a.stride[l] * nb, cudaMemcpyHostToDevice, pick_copy_stream(c, s)));
+      CK(cudaMemcpyAsync(dc, hc, a.stride[l] * nb, cudaMemcpyHostToDevice, pick_copy_stream(c, s)));
     } else if (uniform) {
       // uniformly pitched stack with a different pitch: linear H2D into staging (PCIe-friendly), then a
       // device-side 2D repack into the 16-byte-pitched layout (row-granular DMA over PCIe is slow)
@@ -384,22 +398,22 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     }
   }
   const size_t np = (size_t)h->n_pts, ns = (size_t)h->n_segs;
-  CK(up_range(c->d_T_ref, h->T_ref_w, 7, B, b0, b1, s, &a.T_ref_w, prepare));
-  CK(up_range(c->d_T_cur, h->T_cur_w, 7, B, b0, b1, s, &a.T_cur_w, prepare));
-  CK(up_range(c->d_pt_count, h->pt_count, 1, B, b0, b1, s, &a.pt_count, prepare));
-  CK(up_range(c->d_pt_px, h->pt_px, np * 2, B, b0, b1, s, &a.pt_px, prepare));
-  CK(up_range(c->d_pt_f, h->pt_f, np * 3, B, b0, b1, s, &a.pt_f, prepare));
-  CK(up_range(c->d_pt_pos, h->pt_pos, np * 3, B, b0, b1, s, &a.pt_pos, prepare));
-  CK(up_range(c->d_pt_valid, h->pt_valid, np, B, b0, b1, s, &a.pt_valid, prepare));
-  CK(up_range(c->d_seg_count, h->seg_count, 1, B, b0, b1, s, &a.seg_count, prepare));
-  CK(up_range(c->d_seg_spx, h->seg_spx, ns * 2, B, b0, b1, s, &a.seg_spx, prepare));
-  CK(up_range(c->d_seg_epx, h->seg_epx, ns * 2, B, b0, b1, s, &a.seg_epx, prepare));
-  CK(up_range(c->d_seg_sf, h->seg_sf, ns * 3, B, b0, b1, s, &a.seg_sf, prepare));
-  CK(up_range(c->d_seg_ef, h->seg_ef, ns * 3, B, b0, b1, s, &a.seg_ef, prepare));
-  CK(up_range(c->d_seg_spos, h->seg_spos, ns * 3, B, b0, b1, s, &a.seg_spos, prepare));
-  CK(up_range(c->d_seg_epos, h->seg_epos, ns * 3, B, b0, b1, s, &a.seg_epos, prepare));
-  CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, s, &a.seg_length, prepare));
-  CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, s, &a.seg_valid, prepare));
+  CK(up_range(c->d_T_ref, h->T_ref_w, 7, B, b0, b1, pick_copy_stream(c, s), &a.T_ref_w, prepare));
+  CK(up_range(c->d_T_cur, h->T_cur_w, 7, B, b0, b1, pick_copy_stream(c, s), &a.T_cur_w, prepare));
+  CK(up_range(c->d_pt_count, h->pt_count, 1, B, b0, b1, pick_copy_stream(c, s), &a.pt_count, prepare));
+  CK(up_range(c->d_pt_px, h->pt_px, np * 2, B, b0, b1, pick_copy_stream(c, s), &a.pt_px, prepare));
+  CK(up_range(c->d_pt_f, h->pt_f, np * 3, B, b0, b1, pick_copy_stream(c, s), &a.pt_f, prepare));
+  CK(up_range(c->d_pt_pos, h->pt_pos, np * 3, B, b0, b1, pick_copy_stream(c, s), &a.pt_pos, prepare));
+  CK(up_range(c->d_pt_valid, h->pt_valid, np, B, b0, b1, pick_copy_stream(c, s), &a.pt_valid, prepare));
+  CK(up_range(c->d_seg_count, h->seg_count, 1, B, b0, b1, pick_copy_stream(c, s), &a.seg_count, prepare));
+  CK(up_range(c->d_seg_spx, h->seg_spx, ns * 2, B, b0, b1, pick_copy_stream(c, s), &a.seg_spx, prepare));
+  CK(up_range(c->d_seg_epx, h->seg_epx, ns * 2, B, b0, b1, pick_copy_stream(c, s), &a.seg_epx, prepare));
+  CK(up_range(c->d_seg_sf, h->seg_sf, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_sf, prepare));
+  CK(up_range(c->d_seg_ef, h->seg_ef, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_ef, prepare));
+  CK(up_range(c->d_seg_spos, h->seg_spos, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_spos, prepare));
+  CK(up_range(c->d_seg_epos, h->seg_epos, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_epos, prepare));
+  CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_length, prepare));
+  CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_valid, prepare));
   }  // mode != 3
   if (mode == 0 || mode == 2) return PLSVO_OK;
 
@@ -669,13 +683,33 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
     CK(cudaMemsetAsync(d_arrived, 0, sizeof(unsigned int), c->stream));
     CK(cudaEventRecord(c->start_ev, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->start_ev, 0));
+    // extra copy streams (PLSVO_COPY_STREAMS, default 1 = the copy stream alone): a chunk's ~24 array copies go
+    // round-robin over them and the arrival flag waits for all of them
+    int n_rr = 1;
+    const char* renv = getenv("PLSVO_COPY_STREAMS");
+    if (renv && atoi(renv) >= 1) n_rr = std::min(atoi(renv), 4);
+    if (n_rr > 1) {
+      for (int k = 0; k < n_rr; ++k) {
+        if (!c->rr_stream[k]) {
+          CK(cudaStreamCreateWithFlags(&c->rr_stream[k], cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&c->rr_ev[k], cudaEventDisableTiming));
+        }
+        CK(cudaStreamWaitEvent(c->rr_stream[k], c->start_ev, 0));
+      }
+    }
     // enqueue every chunk copy first (asynchronous from pinned memory): the host-side sizing below and
     // the kernel launch then overlap with the DMA
     int rc = PLSVO_OK;
     for (int k = 0; k < n_chunks; ++k) {
+      c->rr_n = n_rr > 1 ? n_rr : 0, c->rr_i = 0;
       rc = align_upload_impl(c, b, (size_t)k * chunk, std::min<size_t>((size_t)(k + 1) * chunk, B), c->copy_stream,
                              k == 0 ? 2 : 0);
+      c->rr_n = 0;
       if (rc != PLSVO_OK) return rc;
+      for (int j = 0; j < (n_rr > 1 ? n_rr : 0); ++j) {
+        CK(cudaEventRecord(c->rr_ev[j], c->rr_stream[j]));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->rr_ev[j], 0));
+      }
       CK(cudaMemcpyAsync(d_arrived, &c->h_flags[k], sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream));
     }
     rc = align_upload_impl(c, b, 0, 0, c->copy_stream, 3);  // host-side sizing (segment-sample bound, outputs)

@@ -17,8 +17,10 @@ for pyr in (data.ref_pyr, data.cur_pyr):
     for l in list(pyr): pyr[l] = pin(pyr[l])
 ctx = plsvo_b200.Context(0)
 al = plsvo_b200.SparseImgAlign(4, 2, 30, ctx=ctx)
-for chunks, gate in ((0, 128), (0, 192), (0, 256), (0, 384), (0, 512), (0, 1024), (1, 0)):
+for chunks, gate, rr in ((0, 512, 1), (0, 512, 2), (0, 512, 3), (0, 512, 4), (0, 256, 1), (0, 256, 2), (0, 256, 3), (0, 256, 4),
+                         (0, 128, 4), (0, 384, 3), (1, 0, 1)):
     os.environ['PLSVO_GATE_CHUNK'] = str(gate)
+    os.environ['PLSVO_COPY_STREAMS'] = str(rr)
     os.environ["PLSVO_E2E_CHUNKS"] = str(chunks) if chunks else ""
     if not chunks: os.environ.pop("PLSVO_E2E_CHUNKS")
     for _ in range(3): al.run(data)
@@ -26,7 +28,7 @@ for chunks, gate in ((0, 128), (0, 192), (0, 256), (0, 384), (0, 512), (0, 1024)
     n = 10
     for _ in range(n): al.run(data)
     dt = (time.perf_counter() - t0) / n
-    print(json.dumps({"chunks": chunks, "gate": gate, "ms": round(dt * 1e3, 3), "pairs_per_s": round(B / dt)}), flush=True)
+    print(json.dumps({"chunks": chunks, "gate": gate, "copy_streams": rr, "ms": round(dt * 1e3, 3), "pairs_per_s": round(B / dt)}), flush=True)
 # breakdown of the single-shot path
 os.environ["PLSVO_E2E_CHUNKS"] = "1"
 t0 = time.perf_counter(); al.upload(data); ctx.sync(); t1 = time.perf_counter(); al.launch(); ctx.sync(); t2 = time.perf_counter(); al.download(); t3 = time.perf_counter()
