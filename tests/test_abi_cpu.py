@@ -35,13 +35,26 @@ def test_struct_layout_matches_header(abi, tmp_path):
         " sizeof(plsvo_align_result), sizeof(plsvo_poseopt_params), sizeof(plsvo_poseopt_batch), sizeof(plsvo_poseopt_result));\n"
         'printf("%zu %zu %zu %zu\\n", offsetof(plsvo_align_batch, T_ref_w), offsetof(plsvo_align_batch, seg_valid),'
         " offsetof(plsvo_poseopt_batch, seg_valid), offsetof(plsvo_align_batch, img_stride));\n"
+        'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(plsvo_pyramid_batch), sizeof(plsvo_pyramid_result),'
+        " sizeof(plsvo_align2d_batch), sizeof(plsvo_align2d_result), sizeof(plsvo_align1d_batch), sizeof(plsvo_align1d_result),"
+        " sizeof(plsvo_match_batch), sizeof(plsvo_match_result), sizeof(plsvo_structopt_batch), sizeof(plsvo_structopt_result),"
+        " sizeof(plsvo_seed_batch), sizeof(plsvo_seed_result));\n"
+        'printf("%zu %zu %zu %zu\\n", offsetof(plsvo_match_batch, px_cur), offsetof(plsvo_seed_batch, cam),'
+        " offsetof(plsvo_seed_batch, sigma2), offsetof(plsvo_structopt_batch, seg_epos));\n"
         "return 0;}\n"
     )
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).decode().split()
     sizes = [int(x) for x in out[:7]]
-    offs = [int(x) for x in out[7:]]
+    offs = [int(x) for x in out[7:11]]
+    next_sizes = [int(x) for x in out[11:23]]
+    next_offs = [int(x) for x in out[23:]]
+    assert next_sizes == [C.sizeof(t) for t in (abi.PyramidBatch, abi.PyramidResult, abi.Align2DBatch, abi.Align2DResult,
+                                                 abi.Align1DBatch, abi.Align1DResult, abi.MatchBatch, abi.MatchResult,
+                                                 abi.StructOptBatch, abi.StructOptResult, abi.SeedBatch, abi.SeedResult)]
+    assert next_offs == [abi.MatchBatch.px_cur.offset, abi.SeedBatch.cam.offset, abi.SeedBatch.sigma2.offset,
+                         abi.StructOptBatch.seg_epos.offset]
     assert sizes == [C.sizeof(t) for t in (abi.Camera, abi.AlignParams, abi.AlignBatch, abi.AlignResult,
                                             abi.PoseOptParams, abi.PoseOptBatch, abi.PoseOptResult)]
     assert offs == [abi.AlignBatch.T_ref_w.offset, abi.AlignBatch.seg_valid.offset,
