@@ -418,6 +418,32 @@ typedef struct plsvo_seed_result {
 
 int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batch* in, const plsvo_seed_result* out);
 
+/* Line-seed variant: the body of DepthFilter::updateLineSeeds (src/depth_filter.cpp:367-471).  A LineSeed carries one
+ * inverse-depth Gaussian per end point and a shared Beta (a, b).  Both end points are searched with
+ * Matcher::findEpipolarMatchDirectSegmentEndpoint (src/matcher.cpp:420-588) — which, as in the reference, warps and
+ * searches around the segment feature's own px / f (its mid point, base Feature fields) for BOTH depth hypotheses and
+ * has no edgelet pre-selection — then computeTau uses the end-point bearings sf / ef (:415-418) and
+ * DepthFilter::updateLineSeed (:514-565) updates both Gaussians and takes a = max(a_s, a_e), b = min(b_s, b_e).
+ * `seeds` describes the start point: ref_px / ref_f = LineFeat::px / f, mu / z_range / sigma2 = mu_s / z_range_s / sigma2_s;
+ * is_edgelet / ref_grad are ignored. */
+typedef struct plsvo_line_seed_batch {
+  plsvo_seed_batch seeds;
+  const double* ref_sf;    /* [n][3] LineFeat::sf */
+  const double* ref_ef;    /* [n][3] LineFeat::ef */
+  const float* mu_e;       /* [n] */
+  const float* z_range_e;  /* [n] */
+  const float* sigma2_e;   /* [n] */
+} plsvo_line_seed_batch;
+
+typedef struct plsvo_line_seed_result {
+  plsvo_seed_result seeds; /* a, b, mu_s, sigma2_s, status, converged (both end points), depth = z_s, px_cur of the start search */
+  float* mu_e;             /* [n] */
+  float* sigma2_e;         /* [n] */
+  double* depth_e;         /* [n] z_e (NaN unless status == UPDATED) */
+} plsvo_line_seed_result;
+
+int plsvo_line_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_line_seed_batch* in, const plsvo_line_seed_result* out);
+
 /* device time (CUDA events on the context's stream) of the kernel launched by the last
  * plsvo_pyramid / align2d / align1d / match_direct / seed_update / structopt _batch_run call: the kernel alone,
  * without the host<->device copies those calls also make.  Measurement aid, no reference counterpart. */

@@ -320,3 +320,29 @@ def ref_seed_update(abi, data):
     if rc != 0:
         raise RuntimeError(f"reference seed_update failed rc={rc}")
     return out
+
+
+def line_seed_update(abi, data, n_threads: int = 1):
+    """DepthFilter::updateLineSeeds body restated -> abi.LineSeedOut."""
+    lib = load(abi)
+    lib.plsvo_oracle_line_seed_update_batch.restype = C.c_int
+    lib.plsvo_oracle_line_seed_update_batch.argtypes = [C.POINTER(abi.LineSeedBatch), C.POINTER(abi.LineSeedResult), C.c_int]
+    b, keep = abi.make_line_seed_batch(data)
+    out = abi.LineSeedOut(data.n)
+    rc = lib.plsvo_oracle_line_seed_update_batch(C.byref(b), C.byref(out.line_struct), n_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle line_seed_update failed rc={rc}")
+    return out
+
+
+def ref_line_seed_update(abi, data):
+    """DepthFilter::updateLineSeeds of the reference's own depth_filter.cpp + matcher.cpp -> abi.LineSeedOut (state only)."""
+    lib = load_ref(abi)
+    lib.plsvo_ref_line_seed_update_batch.restype = C.c_int
+    lib.plsvo_ref_line_seed_update_batch.argtypes = [C.POINTER(abi.LineSeedBatch), C.POINTER(abi.LineSeedResult)]
+    b, keep = abi.make_line_seed_batch(data)
+    out = abi.LineSeedOut(data.n)
+    rc = lib.plsvo_ref_line_seed_update_batch(C.byref(b), C.byref(out.line_struct))
+    if rc != 0:
+        raise RuntimeError(f"reference line_seed_update failed rc={rc}")
+    return out

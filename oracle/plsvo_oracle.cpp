@@ -1582,8 +1582,10 @@ struct EpiResult {
   int search_level = -1;
   double px_cur[2] = {std::numeric_limits<double>::quiet_NaN(), std::numeric_limits<double>::quiet_NaN()};
 };
+// segment_endpoint = true restates Matcher::findEpipolarMatchDirectSegmentEndpoint (src/matcher.cpp:420-588): NaN depth
+// range and NaN/inf epipolar length are rejected up front, no edgelet pre-selection, otherwise the same search.
 static bool find_epipolar_match_direct(const plsvo_seed_batch* in, int i, double d_estimate, double d_min, double d_max, double& depth,
-                                       EpiResult& er) {
+                                       EpiResult& er, bool segment_endpoint = false) {
   const plsvo_camera& cam = in->cam;
   const size_t I = (size_t)i;
   const int halfpatch_size_ = 4, patch_size_ = 8;
@@ -1595,6 +1597,7 @@ static bool find_epipolar_match_direct(const plsvo_seed_batch* in, int i, double
   const int level_ref = in->ref_level[i];
   int zmssd_best = 2000 * 64;  // PatchScore::threshold()
   double uv_best[2] = {0, 0};
+  if (segment_endpoint && (std::isnan(d_min) || std::isnan(d_max))) return false;  // :434-438
   // start and end of the epipolar segment on the unit plane (:291-293)
   double A2[2], B2[2];
   project2d(se3_act(T_cur_ref, f * d_min), A2);
@@ -1603,7 +1606,7 @@ static bool find_epipolar_match_direct(const plsvo_seed_batch* in, int i, double
   double A[2][2];
   warp_matrix_affine(cam, px_ref, f, d_estimate, T_cur_ref, level_ref, A);
   // feature pre-selection (:300-310)
-  if (in->is_edgelet && in->is_edgelet[i] && in->epi_search_edgelet_filtering) {
+  if (!segment_endpoint && in->is_edgelet && in->is_edgelet[i] && in->epi_search_edgelet_filtering) {
     const double g0 = in->ref_grad[2 * I], g1 = in->ref_grad[2 * I + 1];
     double c0 = A[0][0] * g0 + A[0][1] * g1, c1 = A[1][0] * g0 + A[1][1] * g1;
     const double nc = std::sqrt(c0 * c0 + c1 * c1);
@@ -1620,6 +1623,7 @@ static bool find_epipolar_match_direct(const plsvo_seed_batch* in, int i, double
   const double px_B[2] = {cam.fx * B2[0] + cam.cx, cam.fy * B2[1] + cam.cy};
   const double dAB[2] = {px_A[0] - px_B[0], px_A[1] - px_B[1]};
   const double epi_length = std::sqrt(dAB[0] * dAB[0] + dAB[1] * dAB[1]) / (1 << search_level);
+  if (segment_endpoint && (std::isnan(epi_length) || std::isinf(epi_length))) return false;  // :481-485
   uint8_t patch_with_border[100] = {0};
   uint8_t patch[64];
   warp_affine_patches(A, in->ref_img[level_ref] + (size_t)in->ref_index[i] * in->ref_stride[level_ref], (int)in->ref_pitch[level_ref],
@@ -1648,7 +1652,7 @@ static bool find_epipolar_match_direct(const plsvo_seed_batch* in, int i, double
     }
     return false;
   };
-  if (epi_length < 2.0 && !std::isnan(fabsf((float)epi_length)) && !std::isinf(fabsf((float)epi_length))) {  // :324-343
+  if (epi_length < 2.0 && (segment_endpoint || (!std::isnan(fabsf((float)epi_length)) && !std::isinf(fabsf((float)epi_length))))) {  // :324-343
     er.px_cur[0] = (px_A[0] + px_B[0]) / 2.0, er.px_cur[1] = (px_A[1] + px_B[1]) / 2.0;
     const double start[2] = {er.px_cur[0], er.px_cur[1]};
     return refine_and_triangulate(start);
@@ -1789,6 +1793,108 @@ static void seed_update_one(const plsvo_seed_batch* in, const plsvo_seed_result*
 int plsvo_oracle_seed_update_batch(const plsvo_seed_batch* in, const plsvo_seed_result* out, int n_threads) {
   if (!in || !out) return PLSVO_ERR_INVALID;
   parallel_for(in->n_seeds, n_threads, [&](int i) { seed_update_one(in, out, i); });
+  return PLSVO_OK;
+}
+
+// One end point's share of DepthFilter::updateLineSeed (depth_filter.cpp:524-539 / :541-556): new mean and variance of the
+// end point's Gaussian and the moments f, e of the Beta update — the same arithmetic as update_point_seed.
+static void line_endpoint_update(float x, float tau2, float norm_scale, float a, float b, float z_range, float& mu, float& sigma2,
+                                 float& f_out, float& e_out) {
+  float pdf;
+  {
+    float exponent = x - mu;
+    exponent *= -exponent;
+    exponent /= 2 * norm_scale * norm_scale;
+    pdf = std::exp(exponent);
+    pdf /= norm_scale * std::sqrt(2 * static_cast<float>(3.141592653589793238462643383279502884L));
+    if (std::isinf(x)) pdf = 0;
+  }
+  const float s2 = 1. / (1. / sigma2 + 1. / tau2);
+  const float m = s2 * (mu / sigma2 + x / tau2);
+  float C1 = a / (a + b) * pdf;
+  float C2 = b / (a + b) * 1. / z_range;
+  const float normalization_constant = C1 + C2;
+  C1 /= normalization_constant;
+  C2 /= normalization_constant;
+  f_out = C1 * (a + 1.) / (a + b + 1.) + C2 * a / (a + b + 1.);
+  e_out = C1 * (a + 1.) * (a + 2.) / ((a + b + 1.) * (a + b + 2.)) + C2 * a * (a + 1.0f) / ((a + b + 1.0f) * (a + b + 2.0f));
+  const float mu_new = C1 * m + C2 * mu;
+  sigma2 = C1 * (s2 + m * m) + C2 * (sigma2 + mu * mu) - mu_new * mu_new;
+  mu = mu_new;
+}
+
+static void line_seed_update_one(const plsvo_line_seed_batch* inl, const plsvo_line_seed_result* outl, int i) {
+  const plsvo_seed_batch* in = &inl->seeds;
+  const plsvo_seed_result* out = &outl->seeds;
+  const plsvo_camera& cam = in->cam;
+  const size_t I = (size_t)i;
+  float a = in->a[i], b = in->b[i];
+  float mu_s = in->mu[i], sig_s = in->sigma2[i], mu_e = inl->mu_e[i], sig_e = inl->sigma2_e[i];
+  const float zr_s = in->z_range[i], zr_e = inl->z_range_e[i];
+  int status = PLSVO_SEED_NOT_VISIBLE;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  double z_s = nan, z_e = nan;
+  EpiResult er_s, er_e;
+  const SE3 T_ref_w = se3_from_pose7(in->T_ref_w + 7 * (size_t)in->ref_index[i]);
+  const SE3 T_cur_w = se3_from_pose7(in->T_cur_w + 7 * (size_t)in->cur_index[i]);
+  const Vec3 sf{inl->ref_sf[3 * I], inl->ref_sf[3 * I + 1], inl->ref_sf[3 * I + 2]};
+  const Vec3 ef{inl->ref_ef[3 * I], inl->ref_ef[3 * I + 1], inl->ref_ef[3 * I + 2]};
+  const double px_error_angle = std::atan(1.0 / (2.0 * std::fabs(cam.fx))) * 2.0;
+  auto in_image = [&](Vec3 p) {
+    double px[2];
+    pinhole_world2cam(cam, p, px);
+    const int ox = (px[0] >= -2147483648.0 && px[0] < 2147483648.0) ? (int)px[0] : INT32_MIN;
+    const int oy = (px[1] >= -2147483648.0 && px[1] < 2147483648.0) ? (int)px[1] : INT32_MIN;
+    return ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+  };
+  do {
+    const SE3 T_ref_cur = se3_mul(T_ref_w, se3_inverse(T_cur_w));  // :388
+    const SE3 T_cur_ref_vis = se3_inverse(T_ref_cur);
+    const Vec3 xyz_f_s = se3_act(T_cur_ref_vis, sf * (1.0 / mu_s));
+    const Vec3 xyz_f_e = se3_act(T_cur_ref_vis, ef * (1.0 / mu_e));
+    if (xyz_f_s.z < 0.0 || xyz_f_e.z < 0.0) break;
+    if (!in_image(xyz_f_s) || !in_image(xyz_f_e)) break;
+    const float z_inv_min_s = mu_s + std::sqrt(sig_s), z_inv_max_s = std::max(mu_s - std::sqrt(sig_s), 0.00000001f);
+    const float z_inv_min_e = mu_e + std::sqrt(sig_e), z_inv_max_e = std::max(mu_e - std::sqrt(sig_e), 0.00000001f);
+    if (!find_epipolar_match_direct(in, i, 1.0 / mu_s, 1.0 / z_inv_min_s, 1.0 / z_inv_max_s, z_s, er_s, true) ||
+        !find_epipolar_match_direct(in, i, 1.0 / mu_e, 1.0 / z_inv_min_e, 1.0 / z_inv_max_e, z_e, er_e, true)) {
+      b++;
+      status = PLSVO_SEED_NO_MATCH;
+      z_s = z_e = nan;
+      break;
+    }
+    const double tau_s = compute_tau(T_ref_cur, sf, z_s, px_error_angle);
+    const double tau_inverse_s = 0.5 * (1.0 / std::max(0.0000001, z_s - tau_s) - 1.0 / (z_s + tau_s));
+    const double tau_e = compute_tau(T_ref_cur, ef, z_e, px_error_angle);
+    const double tau_inverse_e = 0.5 * (1.0 / std::max(0.0000001, z_e - tau_e) - 1.0 / (z_e + tau_e));
+    status = PLSVO_SEED_UPDATED;
+    // updateLineSeed (:514-565)
+    const float x_s = (float)(1. / z_s), tau2_s = (float)(tau_inverse_s * tau_inverse_s);
+    const float x_e = (float)(1. / z_e), tau2_e = (float)(tau_inverse_e * tau_inverse_e);
+    const float norm_scale_s = std::sqrt(sig_s + tau2_s), norm_scale_e = std::sqrt(sig_e + tau2_e);
+    if (std::isnan(norm_scale_s) || std::isnan(norm_scale_e)) break;
+    float f_s, e_s, f_e, e_e;
+    line_endpoint_update(x_s, tau2_s, norm_scale_s, a, b, zr_s, mu_s, sig_s, f_s, e_s);
+    line_endpoint_update(x_e, tau2_e, norm_scale_e, a, b, zr_e, mu_e, sig_e, f_e, e_e);
+    const float a_s = (e_s - f_s) / (f_s - e_s / f_s), a_e = (e_e - f_e) / (f_e - e_e / f_e);
+    const float b_s = a_s * (1.f - f_s) / f_s, b_e = a_e * (1.f - f_e) / f_e;
+    a = std::max(a_s, a_e);
+    b = std::min(b_s, b_e);
+  } while (false);
+  out->a[i] = a, out->b[i] = b, out->mu[i] = mu_s, out->sigma2[i] = sig_s;
+  outl->mu_e[i] = mu_e, outl->sigma2_e[i] = sig_e;
+  out->status[i] = status;
+  if (out->converged)
+    out->converged[i] = (status == PLSVO_SEED_UPDATED && std::sqrt(sig_s) < zr_s / in->seed_convergence_sigma2_thresh &&
+                         std::sqrt(sig_e) < zr_e / in->seed_convergence_sigma2_thresh) ? 1 : 0;
+  if (out->depth) out->depth[i] = z_s;
+  if (outl->depth_e) outl->depth_e[i] = z_e;
+  if (out->px_cur) out->px_cur[2 * I] = er_s.px_cur[0], out->px_cur[2 * I + 1] = er_s.px_cur[1];
+}
+
+int plsvo_oracle_line_seed_update_batch(const plsvo_line_seed_batch* in, const plsvo_line_seed_result* out, int n_threads) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  parallel_for(in->seeds.n_seeds, n_threads, [&](int i) { line_seed_update_one(in, out, i); });
   return PLSVO_OK;
 }
 

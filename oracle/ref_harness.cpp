@@ -409,8 +409,11 @@ struct DepthFilterProbe : plsvo::DepthFilter {
   DepthFilterProbe(plsvo::feature_detection::DetectorPtr<plsvo::PointFeat> pd, plsvo::feature_detection::DetectorPtr<plsvo::LineFeat> ld)
       : plsvo::DepthFilter(pd, ld, [](plsvo::Point* p, double) { delete p; }, [](plsvo::LineSeg* l, double, double) { delete l; }) {}
   using plsvo::DepthFilter::pt_seeds_;
+  using plsvo::DepthFilter::seg_seeds_;
   using plsvo::DepthFilter::matcher_;
+  using plsvo::DepthFilter::matcherls_;
   void update(FramePtr f) { updatePointSeeds(f); }
+  void update_lines(FramePtr f) { updateLineSeeds(f); }
 };
 }  // namespace
 
@@ -468,6 +471,67 @@ int plsvo_ref_seed_update_batch(const plsvo_seed_batch* in, const plsvo_seed_res
       const int i = sd.id;
       out->a[i] = sd.a, out->b[i] = sd.b, out->mu[i] = sd.mu, out->sigma2[i] = sd.sigma2;
       out->status[i] = 0;  // state only: the reference does not report which branch a seed took
+    }
+  }
+  return PLSVO_OK;
+}
+
+// DepthFilter::updateLineSeeds (src/depth_filter.cpp:367-471) through the reference class, as for the point seeds above.
+int plsvo_ref_line_seed_update_batch(const plsvo_line_seed_batch* inl, const plsvo_line_seed_result* outl) {
+  if (!inl || !outl) return PLSVO_ERR_INVALID;
+  const plsvo_seed_batch* in = &inl->seeds;
+  const plsvo_seed_result* out = &outl->seeds;
+  plsvo::Config::nPyrLevels() = (size_t)in->n_pyr_levels;
+  vk::PinholeCamera cam(in->cam.width, in->cam.height, in->cam.fx, in->cam.fy, in->cam.cx, in->cam.cy);
+  auto make_frames = [&](int n, const uint8_t* const* img, const size_t* pitch, const size_t* stride, const double* T) {
+    std::vector<FramePtr> frames;
+    for (int r = 0; r < n; ++r) {
+      FramePtr f(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+      f->img_pyr_.resize(PLSVO_MAX_LEVELS);
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
+        if (img[l])
+          f->img_pyr_[l] = cv::Mat(in->cam.height >> l, in->cam.width >> l, CV_8U, const_cast<uint8_t*>(img[l] + (size_t)r * stride[l]), pitch[l]);
+      f->T_f_w_ = pose_from7(T + 7 * (size_t)r);
+      frames.push_back(f);
+    }
+    return frames;
+  };
+  std::vector<FramePtr> refs = make_frames(in->n_ref_images, in->ref_img, in->ref_pitch, in->ref_stride, in->T_ref_w);
+  std::vector<FramePtr> curs = make_frames(in->n_cur_images, in->cur_img, in->cur_pitch, in->cur_stride, in->T_cur_w);
+  typedef plsvo::feature_detection::AbstractDetector<plsvo::PointFeat> VoidPt;
+  typedef plsvo::feature_detection::AbstractDetector<plsvo::LineFeat> VoidLs;
+  plsvo::feature_detection::DetectorPtr<plsvo::PointFeat> pd(new VoidPt(in->cam.width, in->cam.height, 25, in->n_pyr_levels));
+  plsvo::feature_detection::DetectorPtr<plsvo::LineFeat> ld(new VoidLs(in->cam.width, in->cam.height, 25, in->n_pyr_levels));
+  for (int c = 0; c < in->n_cur_images; ++c) {
+    DepthFilterProbe df(pd, ld);
+    df.options_.seed_convergence_sigma2_thresh = 1e300;
+    df.matcherls_.options_.align_max_iter = in->n_iter;
+    df.matcherls_.options_.max_epi_search_steps = (size_t)in->max_epi_search_steps;
+    df.matcherls_.options_.align_1d = in->align_1d != 0;
+    df.matcherls_.options_.subpix_refinement = in->subpix_refinement != 0;
+    std::vector<std::unique_ptr<plsvo::LineFeat>> ftrs;
+    for (int i = 0; i < in->n_seeds; ++i) {
+      if (in->cur_index[i] != c) continue;
+      const Vector2d px = v2(in->ref_px + 2 * (size_t)i);
+      ftrs.emplace_back(new plsvo::LineFeat(refs[in->ref_index[i]].get(), px, px, v3(inl->ref_sf + 3 * (size_t)i),
+                                            v3(inl->ref_ef + 3 * (size_t)i), in->ref_level[i]));
+      ftrs.back()->px = px;                                 // base Feature fields the end-point search reads (matcher.cpp:440-447)
+      ftrs.back()->f = v3(in->ref_f + 3 * (size_t)i);
+      plsvo::LineSeed seed(ftrs.back().get(), 1.0f, 1.0f);
+      seed.batch_id = plsvo::Seed::batch_counter;
+      seed.id = i;
+      seed.a = in->a[i], seed.b = in->b[i];
+      seed.mu_s = in->mu[i], seed.z_range_s = in->z_range[i], seed.sigma2_s = in->sigma2[i];
+      seed.mu_e = inl->mu_e[i], seed.z_range_e = inl->z_range_e[i], seed.sigma2_e = inl->sigma2_e[i];
+      df.seg_seeds_.push_back(seed);
+      out->status[i] = -1;
+    }
+    df.update_lines(curs[c]);
+    for (const plsvo::LineSeed& sd : df.seg_seeds_) {
+      const int i = sd.id;
+      out->a[i] = sd.a, out->b[i] = sd.b, out->mu[i] = sd.mu_s, out->sigma2[i] = sd.sigma2_s;
+      outl->mu_e[i] = sd.mu_e, outl->sigma2_e[i] = sd.sigma2_e;
+      out->status[i] = 0;
     }
   }
   return PLSVO_OK;

@@ -204,6 +204,14 @@ class SeedResult(C.Structure):
                 ("depth", _f64p), ("px_cur", _f64p)]
 
 
+class LineSeedBatch(C.Structure):
+    _fields_ = [("seeds", SeedBatch), ("ref_sf", _f64p), ("ref_ef", _f64p), ("mu_e", _f32p), ("z_range_e", _f32p), ("sigma2_e", _f32p)]
+
+
+class LineSeedResult(C.Structure):
+    _fields_ = [("seeds", SeedResult), ("mu_e", _f32p), ("sigma2_e", _f32p), ("depth_e", _f64p)]
+
+
 SEED_NOT_VISIBLE, SEED_NO_MATCH, SEED_UPDATED = 0, 1, 2
 
 
@@ -378,6 +386,7 @@ ABI_SYMBOLS = [
     ("plsvo_align1d_batch_run", C.c_int, [C.c_void_p, _P(Align1DBatch), _P(Align1DResult)]),
     ("plsvo_match_direct_batch_run", C.c_int, [C.c_void_p, _P(MatchBatch), _P(MatchResult)]),
     ("plsvo_seed_update_batch_run", C.c_int, [C.c_void_p, _P(SeedBatch), _P(SeedResult)]),
+    ("plsvo_line_seed_update_batch_run", C.c_int, [C.c_void_p, _P(LineSeedBatch), _P(LineSeedResult)]),
     ("plsvo_structopt_batch_run", C.c_int, [C.c_void_p, _P(StructOptBatch), _P(StructOptResult)]),
     ("plsvo_last_kernel_ms", C.c_int, [C.c_void_p, _P(C.c_float)]),
     ("plsvo_launch_count", C.c_int64, [C.c_void_p]),
@@ -520,3 +529,23 @@ class SeedOut:
         self.struct = SeedResult(_ptr(self.a, np.float32), _ptr(self.b, np.float32), _ptr(self.mu, np.float32), _ptr(self.sigma2, np.float32),
                                  _ptr(self.status, np.int32), _ptr(self.converged, np.uint8), _ptr(self.depth, np.float64),
                                  _ptr(self.px_cur, np.float64))
+
+
+def make_line_seed_batch(d):
+    """Build a plsvo_line_seed_batch from a synth.LineSeedData-like object (a SeedData for the start point plus the
+    end-point fields).  Returns (struct, keepalive)."""
+    base, keep = make_seed_batch(d)
+    b = LineSeedBatch()
+    b.seeds = base
+    b.ref_sf, b.ref_ef = _ptr(d.ref_sf, np.float64), _ptr(d.ref_ef, np.float64)
+    b.mu_e, b.z_range_e, b.sigma2_e = _ptr(d.mu_e, np.float32), _ptr(d.z_range_e, np.float32), _ptr(d.sigma2_e, np.float32)
+    return b, keep
+
+
+class LineSeedOut(SeedOut):
+    def __init__(self, n: int):
+        super().__init__(n)
+        self.mu_e, self.sigma2_e = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.depth_e = np.zeros(n)
+        self.line_struct = LineSeedResult(self.struct, _ptr(self.mu_e, np.float32), _ptr(self.sigma2_e, np.float32),
+                                          _ptr(self.depth_e, np.float64))

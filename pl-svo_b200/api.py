@@ -247,6 +247,14 @@ class DepthFilter:
     def __init__(self, ctx: Context | None = None):
         self.ctx = ctx or default_context()
 
+    def updateLineSeeds(self, data) -> abi.LineSeedOut:
+        """Batched body of DepthFilter::updateLineSeeds (src/depth_filter.cpp:367-471): data = synth.LineSeedData-like."""
+        b, keep = abi.make_line_seed_batch(data)
+        out = abi.LineSeedOut(data.n)
+        self.ctx.check(self.ctx.lib.plsvo_line_seed_update_batch_run(self.ctx.handle, C.byref(b), C.byref(out.line_struct)),
+                       "plsvo_line_seed_update_batch_run")
+        return out
+
     def updatePointSeeds(self, data) -> abi.SeedOut:
         b, keep = abi.make_seed_batch(data)
         out = abi.SeedOut(data.n)

@@ -464,6 +464,192 @@ __device__ __forceinline__ bool depth_from_triangulation(const Pose& T, V3 f_ref
   return true;
 }
 
+// Matcher::findEpipolarMatchDirect (src/matcher.cpp:277-420) for one seed; segment_endpoint = true gives
+// Matcher::findEpipolarMatchDirectSegmentEndpoint (:420-588): NaN depth ranges and NaN / infinite epipolar lengths are
+// rejected up front and there is no edgelet pre-selection.  Returns false where the reference returns false; on success z is
+// the triangulated depth and (pxc0, pxc1) the matched position (also set, as Matcher::px_cur_, on some failure paths).
+__device__ __forceinline__ bool epipolar_match(const SeedArgs& a, const CamP& cam, const int i, const int r, const int c, const Pose& T_cur_ref,
+                                            const double px_ref0, const double px_ref1, const V3 f, const int level_ref,
+                                            const double d_estimate, const double d_min, const double d_max, const bool segment_endpoint,
+                                            uint8_t* border, double& z, double& pxc0, double& pxc1) {
+  const size_t I = (size_t)i;
+  if (segment_endpoint && (isnan(d_min) || isnan(d_max))) return false;  // matcher.cpp:434-438
+  const V3 pa = pose_act(T_cur_ref, v_scale(f, d_min)), pb = pose_act(T_cur_ref, v_scale(f, d_max));
+  const double Au = DD(pa.x, pa.z), Av = DD(pa.y, pa.z), Bu = DD(pb.x, pb.z), Bv = DD(pb.y, pb.z);
+  const double epi0 = DS(Au, Bu), epi1 = DS(Av, Bv);
+  double A00, A01, A10, A11;
+  warp_matrix_affine(cam, px_ref0, px_ref1, f, d_estimate, T_cur_ref, level_ref, A00, A01, A10, A11);
+  if (!segment_endpoint && a.is_edgelet && a.is_edgelet[i] && a.edgelet_filtering) {  // :300-310
+    const double g0 = a.ref_grad[2 * I], g1 = a.ref_grad[2 * I + 1];
+    double c0 = DA(DM(A00, g0), DM(A01, g1)), c1 = DA(DM(A10, g0), DM(A11, g1));
+    const double nc = __dsqrt_rn(DA(DM(c0, c0), DM(c1, c1)));
+    c0 = DD(c0, nc), c1 = DD(c1, nc);
+    const double ne = __dsqrt_rn(DA(DM(epi0, epi0), DM(epi1, epi1)));
+    const double cosangle = fabs(DA(DM(c0, DD(epi0, ne)), DM(c1, DD(epi1, ne))));
+    if (cosangle < a.edgelet_max_angle) return false;
+  }
+  const double det = DS(DM(A00, A11), DM(A10, A01));
+  const int search_level = best_search_level(det, a.n_pyr_levels - 1);
+  const double pxA0 = DA(DM(cam.fx, Au), cam.cx), pxA1 = DA(DM(cam.fy, Av), cam.cy);
+  const double pxB0 = DA(DM(cam.fx, Bu), cam.cx), pxB1 = DA(DM(cam.fy, Bv), cam.cy);
+  const double dAB0 = DS(pxA0, pxB0), dAB1 = DS(pxA1, pxB1);
+  const double scale = (double)(1 << search_level);
+  const double epi_length = DD(__dsqrt_rn(DA(DM(dAB0, dAB0), DM(dAB1, dAB1))), scale);
+  if (segment_endpoint && (isnan(epi_length) || isinf(epi_length))) return false;  // matcher.cpp:481-485
+  warp_affine_patch(A00, A01, A10, A11, det, a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref], (int)a.ref_pitch[level_ref],
+                    a.width >> level_ref, a.height >> level_ref, px_ref0, px_ref1, level_ref, search_level, border);
+  const uint8_t* cur = a.cur_img[search_level] + (size_t)c * a.cur_stride[search_level];
+  const int ccols = a.width >> search_level, crows = a.height >> search_level;
+  const int cur_step = (int)a.cur_pitch[search_level];
+  const uint8_t* ref = border + 11;
+  float dir0, dir1;
+  {  // (px_A - px_B).cast<float>().normalized()
+    const float fx_ = (float)dAB0, fy_ = (float)dAB1;
+    const float n = __fsqrt_rn(__fadd_rn(__fmul_rn(fx_, fx_), __fmul_rn(fy_, fy_)));
+    dir0 = __fdiv_rn(fx_, n), dir1 = __fdiv_rn(fy_, n);
+  }
+  // sub-pixel refinement at the search level followed by triangulation (:326-342, :396-413)
+  auto refine_and_triangulate = [&](double start0, double start1) -> bool {
+    float u = (float)DD(start0, scale), v = (float)DD(start1, scale);
+    bool res;
+    if (a.align_1d) {
+      double h_inv;
+      res = align1d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, dir0, dir1, u, v, h_inv);
+    } else {
+      res = align2d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, u, v);
+    }
+    if (!res) return false;
+    pxc0 = DM((double)u, scale), pxc1 = DM((double)v, scale);
+    return depth_from_triangulation(T_cur_ref, f, cam2world(cam, pxc0, pxc1), z);
+  };
+  const float elf = fabsf((float)epi_length);
+  if (epi_length < 2.0 && (segment_endpoint || (!isnan(elf) && !isinf(elf)))) {
+    pxc0 = DD(DA(pxA0, pxB0), 2.0), pxc1 = DD(DA(pxA1, pxB1), 2.0);
+    return refine_and_triangulate(pxc0, pxc1);
+  }
+  const double qsteps = DD(epi_length, 0.7);
+  if (!(qsteps < 9.0e18)) return false;  // NaN / beyond size_t: the x86 conversion yields 2^63, i.e. "too many steps"
+  unsigned long long n_steps = (unsigned long long)qsteps;
+  if (n_steps > (unsigned long long)a.max_epi_search_steps) return false;
+  const double step0 = DD(epi0, (double)n_steps), step1 = DD(epi1, (double)n_steps);
+  // ZMSSD of the warped 8x8 patch against the integer-pixel patches along the epipolar line (:354-391)
+  uint32_t refw[16];
+  uint32_t sumA = 0, sumAA = 0;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    const uint8_t* p = ref + y * 10;
+    const uint32_t w0 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+    const uint32_t w1 = p[4] | (p[5] << 8) | (p[6] << 16) | ((uint32_t)p[7] << 24);
+    refw[2 * y] = w0, refw[2 * y + 1] = w1;
+    sumA = __dp4a(w0, 0x01010101u, sumA), sumA = __dp4a(w1, 0x01010101u, sumA);
+    sumAA = __dp4a(w0, w0, sumAA), sumAA = __dp4a(w1, w1, sumAA);
+  }
+  int zmssd_best = 2000 * 64;
+  double uvb0 = 0.0, uvb1 = 0.0;
+  double uv0 = DS(Bu, step0), uv1 = DS(Bv, step1);
+  int last0 = 0, last1 = 0;
+  ++n_steps;
+  for (unsigned long long k = 0; k < n_steps; ++k, uv0 = DA(uv0, step0), uv1 = DA(uv1, step1)) {
+    const double px0 = DA(DM(cam.fx, uv0), cam.cx), px1 = DA(DM(cam.fy, uv1), cam.cy);
+    const int pxi0 = d2i_x86(DA(DD(px0, scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, scale), 0.5));
+    if (pxi0 == last0 && pxi1 == last1) continue;
+    last0 = pxi0, last1 = pxi1;
+    if (!cam_in_frame(cam, pxi0, pxi1, 8, search_level)) continue;
+    const uint8_t* p = cur + (size_t)(pxi1 - 4) * cur_step + (pxi0 - 4);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+    uint32_t sumB = 0, sumBB = 0, sumAB = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const uint32_t* wr = w + (size_t)y * (cur_step >> 2);
+      const uint32_t x0 = __ldg(wr), x1 = __ldg(wr + 1), x2 = __ldg(wr + 2);
+      const uint32_t c0 = __funnelshift_r(x0, x1, sh), c1 = __funnelshift_r(x1, x2, sh);
+      sumB = __dp4a(c0, 0x01010101u, sumB), sumB = __dp4a(c1, 0x01010101u, sumB);
+      sumBB = __dp4a(c0, c0, sumBB), sumBB = __dp4a(c1, c1, sumBB);
+      sumAB = __dp4a(c0, refw[2 * y], sumAB), sumAB = __dp4a(c1, refw[2 * y + 1], sumAB);
+    }
+    const int iA = (int)sumA, iAA = (int)sumAA, iB = (int)sumB, iBB = (int)sumBB, iAB = (int)sumAB;
+    const int zmssd = iAA - 2 * iAB + iBB - (iA * iA - 2 * iA * iB + iB * iB) / 64;
+    if (zmssd < zmssd_best) zmssd_best = zmssd, uvb0 = uv0, uvb1 = uv1;
+  }
+  if (zmssd_best < 2000 * 64) {
+    pxc0 = DA(DM(cam.fx, uvb0), cam.cx), pxc1 = DA(DM(cam.fy, uvb1), cam.cy);
+    if (a.subpix_refinement) {
+      return refine_and_triangulate(pxc0, pxc1);
+    } else {
+      const V3 u3{uvb0, uvb1, 1.0};
+      const double n = v_norm(u3);
+      return depth_from_triangulation(T_cur_ref, f, V3{DD(u3.x, n), DD(u3.y, n), DD(u3.z, n)}, z);
+    }
+  }
+  return false;
+}
+
+// computeTau (src/depth_filter.cpp:568-584) and the measurement (x = 1/z, tau2) handed to the Bayesian update (:319-323).
+// acos / sin / atan are libm calls: the result agrees with the scalar code to double round-off, not bit for bit.
+__device__ __forceinline__ void seed_measurement(const CamP& cam, const Pose& T_ref_cur, const V3 f, const double z, float& x, float& tau2) {
+  const double px_error_angle = atan(1.0 / (2.0 * fabs(cam.fx))) * 2.0;
+  const V3 t = T_ref_cur.t;
+  const V3 av = v_sub(v_scale(f, z), t);
+  const double t_norm = v_norm(t), a_norm = v_norm(av);
+  const double alpha = acos(DD(DA(DA(DM(f.x, t.x), DM(f.y, t.y)), DM(f.z, t.z)), t_norm));
+  const double beta = acos(DD(DA(DA(DM(av.x, -t.x), DM(av.y, -t.y)), DM(av.z, -t.z)), DM(t_norm, a_norm)));
+  const double beta_plus = DA(beta, px_error_angle);
+  const double gamma_plus = DS(DS(3.14159265, alpha), beta_plus);  // plsvo::PI
+  const double z_plus = DD(DM(t_norm, sin(beta_plus)), sin(gamma_plus));
+  const double tau = DS(z_plus, z);
+  const double zmt = DS(z, tau);
+  const double lo = (0.0000001 < zmt) ? zmt : 0.0000001;  // std::max(0.0000001, z - tau)
+  const double tau_inverse = DM(0.5, DS(DD(1.0, lo), DD(1.0, DA(z, tau))));
+  x = (float)DD(1.0, z);
+  tau2 = (float)DM(tau_inverse, tau_inverse);
+}
+// One inverse-depth Gaussian's share of DepthFilter::updatePointSeed / updateLineSeed (src/depth_filter.cpp:489-512,
+// :524-556): the new mean and variance and the moments f, e of the Beta update, with the reference's float / double mixing.
+__device__ __forceinline__ void gaussian_beta_update(const float x, const float tau2, const float norm_scale, const float sa, const float sb,
+                                                     const float z_range, float& smu, float& ssig, float& fq, float& eq) {
+  float ex = __fsub_rn(x, smu);
+  ex = __fmul_rn(ex, -ex);
+  ex = __fdiv_rn(ex, __fmul_rn(__fmul_rn(2.0f, norm_scale), norm_scale));
+  float pdf = expf(ex);
+  pdf = __fdiv_rn(pdf, __fmul_rn(norm_scale, __fsqrt_rn(__fmul_rn(2.0f, 3.14159274101257324f))));
+  if (isinf(x)) pdf = 0.0f;
+  const float s2 = (float)DD(1.0, DA(DD(1.0, (double)ssig), DD(1.0, (double)tau2)));
+  const float m = __fmul_rn(s2, __fadd_rn(__fdiv_rn(smu, ssig), __fdiv_rn(x, tau2)));
+  const float ab = __fadd_rn(sa, sb);
+  float C1 = __fmul_rn(__fdiv_rn(sa, ab), pdf);
+  float C2 = (float)DD(DM((double)__fdiv_rn(sb, ab), 1.0), (double)z_range);
+  const float nc = __fadd_rn(C1, C2);
+  C1 = __fdiv_rn(C1, nc), C2 = __fdiv_rn(C2, nc);
+  const double ab1 = DA((double)ab, 1.0), ab2 = DA((double)ab, 2.0);
+  fq = (float)DA(DD(DM((double)C1, DA((double)sa, 1.0)), ab1), DD((double)__fmul_rn(C2, sa), ab1));
+  const float abf1 = __fadd_rn(ab, 1.0f), abf2 = __fadd_rn(ab, 2.0f);
+  eq = (float)DA(DD(DM(DM((double)C1, DA((double)sa, 1.0)), DA((double)sa, 2.0)), DM(ab1, ab2)),
+                 (double)__fdiv_rn(__fmul_rn(__fmul_rn(C2, sa), __fadd_rn(sa, 1.0f)), __fmul_rn(abf1, abf2)));
+  const float mu_new = __fadd_rn(__fmul_rn(C1, m), __fmul_rn(C2, smu));
+  ssig = __fsub_rn(__fadd_rn(__fmul_rn(C1, __fadd_rn(s2, __fmul_rn(m, m))), __fmul_rn(C2, __fadd_rn(ssig, __fmul_rn(smu, smu)))),
+                   __fmul_rn(mu_new, mu_new));
+  smu = mu_new;
+}
+// visibility of a seed hypothesis in the current frame (depth_filter.cpp:291-304)
+__device__ __forceinline__ bool seed_visible(const CamP& cam, const Pose& T_cur_ref_vis, const V3 f, const float mu) {
+  const V3 xyz_f = pose_act(T_cur_ref_vis, v_scale(f, DD(1.0, (double)mu)));
+  if (xyz_f.z < 0.0) return false;
+  double u, v;
+  world2cam(cam, xyz_f, u, v);
+  const int ox = d2i_x86(u), oy = d2i_x86(v);
+  return ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+}
+// inverse-depth search range of a Gaussian (depth_filter.cpp:307-311)
+__device__ __forceinline__ void depth_range(const float mu, const float sigma2, double& d_estimate, double& d_min, double& d_max) {
+  const float sq = __fsqrt_rn(sigma2);
+  const float z_inv_min = __fadd_rn(mu, sq);
+  const float dmin = __fsub_rn(mu, sq);
+  const float z_inv_max = (dmin < 0.00000001f) ? 0.00000001f : dmin;  // std::max(dmin, 1e-8f)
+  d_estimate = DD(1.0, (double)mu), d_min = DD(1.0, (double)z_inv_min), d_max = DD(1.0, (double)z_inv_max);
+}
+
 __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs a) {
   __shared__ __align__(4) uint8_t s_border[kA2Threads][108];
   const int tid = threadIdx.x;
@@ -479,184 +665,28 @@ __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs 
   const int r = a.ref_index[i], c = a.cur_index[i];
   const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
   const V3 f{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
-  const double px_ref0 = a.ref_px[2 * I], px_ref1 = a.ref_px[2 * I + 1];
-  const int level_ref = a.ref_level[i];
-  uint8_t* border = s_border[tid];
   const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // depth_filter.cpp:291
-  do {
-    // ---- visibility of the seed in the current frame (depth_filter.cpp:291-304) ----
-    const V3 xyz_f = pose_act(pose_inverse(T_ref_cur), v_scale(f, DD(1.0, (double)smu)));
-    if (xyz_f.z < 0.0) break;
-    {
-      double u, v;
-      world2cam(cam, xyz_f, u, v);
-      const int ox = d2i_x86(u), oy = d2i_x86(v);
-      if (!(ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height)) break;
-    }
-    const float sq = __fsqrt_rn(ssig);
-    const float z_inv_min = __fadd_rn(smu, sq);
-    const float dmin = __fsub_rn(smu, sq);
-    const float z_inv_max = (dmin < 0.00000001f) ? 0.00000001f : dmin;  // std::max(dmin, 1e-8f)
-    const double d_estimate = DD(1.0, (double)smu), d_min = DD(1.0, (double)z_inv_min), d_max = DD(1.0, (double)z_inv_max);
-    status = 1;  // no match unless the search below succeeds; b is incremented at the end (:314)
-    // ---- Matcher::findEpipolarMatchDirect ----
+  if (seed_visible(cam, pose_inverse(T_ref_cur), f, smu)) {
+    double d_estimate, d_min, d_max;
+    depth_range(smu, ssig, d_estimate, d_min, d_max);
     const Pose T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
-    const V3 pa = pose_act(T_cur_ref, v_scale(f, d_min)), pb = pose_act(T_cur_ref, v_scale(f, d_max));
-    const double Au = DD(pa.x, pa.z), Av = DD(pa.y, pa.z), Bu = DD(pb.x, pb.z), Bv = DD(pb.y, pb.z);
-    const double epi0 = DS(Au, Bu), epi1 = DS(Av, Bv);
-    double A00, A01, A10, A11;
-    warp_matrix_affine(cam, px_ref0, px_ref1, f, d_estimate, T_cur_ref, level_ref, A00, A01, A10, A11);
-    if (a.is_edgelet && a.is_edgelet[i] && a.edgelet_filtering) {  // :300-310
-      const double g0 = a.ref_grad[2 * I], g1 = a.ref_grad[2 * I + 1];
-      double c0 = DA(DM(A00, g0), DM(A01, g1)), c1 = DA(DM(A10, g0), DM(A11, g1));
-      const double nc = __dsqrt_rn(DA(DM(c0, c0), DM(c1, c1)));
-      c0 = DD(c0, nc), c1 = DD(c1, nc);
-      const double ne = __dsqrt_rn(DA(DM(epi0, epi0), DM(epi1, epi1)));
-      const double cosangle = fabs(DA(DM(c0, DD(epi0, ne)), DM(c1, DD(epi1, ne))));
-      if (cosangle < a.edgelet_max_angle) break;
-    }
-    const double det = DS(DM(A00, A11), DM(A10, A01));
-    const int search_level = best_search_level(det, a.n_pyr_levels - 1);
-    const double pxA0 = DA(DM(cam.fx, Au), cam.cx), pxA1 = DA(DM(cam.fy, Av), cam.cy);
-    const double pxB0 = DA(DM(cam.fx, Bu), cam.cx), pxB1 = DA(DM(cam.fy, Bv), cam.cy);
-    const double dAB0 = DS(pxA0, pxB0), dAB1 = DS(pxA1, pxB1);
-    const double scale = (double)(1 << search_level);
-    const double epi_length = DD(__dsqrt_rn(DA(DM(dAB0, dAB0), DM(dAB1, dAB1))), scale);
-    warp_affine_patch(A00, A01, A10, A11, det, a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref], (int)a.ref_pitch[level_ref],
-                      a.width >> level_ref, a.height >> level_ref, px_ref0, px_ref1, level_ref, search_level, border);
-    const uint8_t* cur = a.cur_img[search_level] + (size_t)c * a.cur_stride[search_level];
-    const int ccols = a.width >> search_level, crows = a.height >> search_level;
-    const int cur_step = (int)a.cur_pitch[search_level];
-    const uint8_t* ref = border + 11;
-    float dir0, dir1;
-    {  // (px_A - px_B).cast<float>().normalized()
-      const float fx_ = (float)dAB0, fy_ = (float)dAB1;
-      const float n = __fsqrt_rn(__fadd_rn(__fmul_rn(fx_, fx_), __fmul_rn(fy_, fy_)));
-      dir0 = __fdiv_rn(fx_, n), dir1 = __fdiv_rn(fy_, n);
-    }
-    // sub-pixel refinement at the search level followed by triangulation (:326-342, :396-413)
-    auto refine_and_triangulate = [&](double start0, double start1) -> bool {
-      float u = (float)DD(start0, scale), v = (float)DD(start1, scale);
-      bool res;
-      if (a.align_1d) {
-        double h_inv;
-        res = align1d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, dir0, dir1, u, v, h_inv);
-      } else {
-        res = align2d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, u, v);
-      }
-      if (!res) return false;
-      pxc0 = DM((double)u, scale), pxc1 = DM((double)v, scale);
-      return depth_from_triangulation(T_cur_ref, f, cam2world(cam, pxc0, pxc1), z);
-    };
-    const float elf = fabsf((float)epi_length);
-    if (epi_length < 2.0 && !isnan(elf) && !isinf(elf)) {
-      pxc0 = DD(DA(pxA0, pxB0), 2.0), pxc1 = DD(DA(pxA1, pxB1), 2.0);
-      if (refine_and_triangulate(pxc0, pxc1)) status = 2;
-      break;
-    }
-    const double qsteps = DD(epi_length, 0.7);
-    if (!(qsteps < 9.0e18)) break;  // NaN / beyond size_t: the x86 conversion yields 2^63, i.e. "too many steps"
-    unsigned long long n_steps = (unsigned long long)qsteps;
-    if (n_steps > (unsigned long long)a.max_epi_search_steps) break;
-    const double step0 = DD(epi0, (double)n_steps), step1 = DD(epi1, (double)n_steps);
-    // ZMSSD of the warped 8x8 patch against the integer-pixel patches along the epipolar line (:354-391)
-    uint32_t refw[16];
-    uint32_t sumA = 0, sumAA = 0;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      const uint8_t* p = ref + y * 10;
-      const uint32_t w0 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
-      const uint32_t w1 = p[4] | (p[5] << 8) | (p[6] << 16) | ((uint32_t)p[7] << 24);
-      refw[2 * y] = w0, refw[2 * y + 1] = w1;
-      sumA = __dp4a(w0, 0x01010101u, sumA), sumA = __dp4a(w1, 0x01010101u, sumA);
-      sumAA = __dp4a(w0, w0, sumAA), sumAA = __dp4a(w1, w1, sumAA);
-    }
-    int zmssd_best = 2000 * 64;
-    double uvb0 = 0.0, uvb1 = 0.0;
-    double uv0 = DS(Bu, step0), uv1 = DS(Bv, step1);
-    int last0 = 0, last1 = 0;
-    ++n_steps;
-    for (unsigned long long k = 0; k < n_steps; ++k, uv0 = DA(uv0, step0), uv1 = DA(uv1, step1)) {
-      const double px0 = DA(DM(cam.fx, uv0), cam.cx), px1 = DA(DM(cam.fy, uv1), cam.cy);
-      const int pxi0 = d2i_x86(DA(DD(px0, scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, scale), 0.5));
-      if (pxi0 == last0 && pxi1 == last1) continue;
-      last0 = pxi0, last1 = pxi1;
-      if (!cam_in_frame(cam, pxi0, pxi1, 8, search_level)) continue;
-      const uint8_t* p = cur + (size_t)(pxi1 - 4) * cur_step + (pxi0 - 4);
-      const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-      const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
-      uint32_t sumB = 0, sumBB = 0, sumAB = 0;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) {
-        const uint32_t* wr = w + (size_t)y * (cur_step >> 2);
-        const uint32_t x0 = __ldg(wr), x1 = __ldg(wr + 1), x2 = __ldg(wr + 2);
-        const uint32_t c0 = __funnelshift_r(x0, x1, sh), c1 = __funnelshift_r(x1, x2, sh);
-        sumB = __dp4a(c0, 0x01010101u, sumB), sumB = __dp4a(c1, 0x01010101u, sumB);
-        sumBB = __dp4a(c0, c0, sumBB), sumBB = __dp4a(c1, c1, sumBB);
-        sumAB = __dp4a(c0, refw[2 * y], sumAB), sumAB = __dp4a(c1, refw[2 * y + 1], sumAB);
-      }
-      const int iA = (int)sumA, iAA = (int)sumAA, iB = (int)sumB, iBB = (int)sumBB, iAB = (int)sumAB;
-      const int zmssd = iAA - 2 * iAB + iBB - (iA * iA - 2 * iA * iB + iB * iB) / 64;
-      if (zmssd < zmssd_best) zmssd_best = zmssd, uvb0 = uv0, uvb1 = uv1;
-    }
-    if (zmssd_best < 2000 * 64) {
-      pxc0 = DA(DM(cam.fx, uvb0), cam.cx), pxc1 = DA(DM(cam.fy, uvb1), cam.cy);
-      if (a.subpix_refinement) {
-        if (refine_and_triangulate(pxc0, pxc1)) status = 2;
-      } else {
-        const V3 u3{uvb0, uvb1, 1.0};
-        const double n = v_norm(u3);
-        if (depth_from_triangulation(T_cur_ref, f, V3{DD(u3.x, n), DD(u3.y, n), DD(u3.z, n)}, z)) status = 2;
-      }
-    }
-  } while (false);
-  if (status == 2) {
-    // ---- computeTau (:568-584) and updatePointSeed (:489-512) ----
-    const double px_error_angle = atan(1.0 / (2.0 * fabs(cam.fx))) * 2.0;
-    const V3 t = T_ref_cur.t;
-    const V3 av = v_sub(v_scale(f, z), t);
-    const double t_norm = v_norm(t), a_norm = v_norm(av);
-    const double alpha = acos(DD(DA(DA(DM(f.x, t.x), DM(f.y, t.y)), DM(f.z, t.z)), t_norm));
-    const double beta = acos(DD(DA(DA(DM(av.x, -t.x), DM(av.y, -t.y)), DM(av.z, -t.z)), DM(t_norm, a_norm)));
-    const double beta_plus = DA(beta, px_error_angle);
-    const double gamma_plus = DS(DS(3.14159265, alpha), beta_plus);  // plsvo::PI
-    const double z_plus = DD(DM(t_norm, sin(beta_plus)), sin(gamma_plus));
-    const double tau = DS(z_plus, z);
-    const double zmt = DS(z, tau);
-    const double lo = (0.0000001 < zmt) ? zmt : 0.0000001;  // std::max(0.0000001, z - tau)
-    const double tau_inverse = DM(0.5, DS(DD(1.0, lo), DD(1.0, DA(z, tau))));
-    const float x = (float)DD(1.0, z), tau2 = (float)DM(tau_inverse, tau_inverse);
+    status = epipolar_match(a, cam, i, r, c, T_cur_ref, a.ref_px[2 * I], a.ref_px[2 * I + 1], f, a.ref_level[i], d_estimate, d_min, d_max,
+                            false, s_border[tid], z, pxc0, pxc1)
+                 ? 2
+                 : 1;
+  }
+  if (status == 2) {  // computeTau (:568-584) and updatePointSeed (:489-512)
+    float x, tau2, fq, eq;
+    seed_measurement(cam, T_ref_cur, f, z, x, tau2);
     const float norm_scale = __fsqrt_rn(__fadd_rn(ssig, tau2));
     if (!isnan(norm_scale)) {
-      float ex = __fsub_rn(x, smu);
-      ex = __fmul_rn(ex, -ex);
-      ex = __fdiv_rn(ex, __fmul_rn(__fmul_rn(2.0f, norm_scale), norm_scale));
-      float pdf = expf(ex);
-      pdf = __fdiv_rn(pdf, __fmul_rn(norm_scale, __fsqrt_rn(__fmul_rn(2.0f, 3.14159274101257324f))));
-      if (isinf(x)) pdf = 0.0f;
-      const float s2 = (float)DD(1.0, DA(DD(1.0, (double)ssig), DD(1.0, (double)tau2)));
-      const float m = __fmul_rn(s2, __fadd_rn(__fdiv_rn(smu, ssig), __fdiv_rn(x, tau2)));
-      const float ab = __fadd_rn(sa, sb);
-      float C1 = __fmul_rn(__fdiv_rn(sa, ab), pdf);
-      float C2 = (float)DD(DM((double)__fdiv_rn(sb, ab), 1.0), (double)z_range);
-      const float nc = __fadd_rn(C1, C2);
-      C1 = __fdiv_rn(C1, nc), C2 = __fdiv_rn(C2, nc);
-      const double ab1 = DA((double)ab, 1.0), ab2 = DA((double)ab, 2.0);
-      const float fq = (float)DA(DD(DM((double)C1, DA((double)sa, 1.0)), ab1), DD((double)__fmul_rn(C2, sa), ab1));
-      const float abf1 = __fadd_rn(ab, 1.0f), abf2 = __fadd_rn(ab, 2.0f);
-      const float eq = (float)DA(DD(DM(DM((double)C1, DA((double)sa, 1.0)), DA((double)sa, 2.0)), DM(ab1, ab2)),
-                                 (double)__fdiv_rn(__fmul_rn(__fmul_rn(C2, sa), __fadd_rn(sa, 1.0f)), __fmul_rn(abf1, abf2)));
-      const float mu_new = __fadd_rn(__fmul_rn(C1, m), __fmul_rn(C2, smu));
-      ssig = __fsub_rn(__fadd_rn(__fmul_rn(C1, __fadd_rn(s2, __fmul_rn(m, m))), __fmul_rn(C2, __fadd_rn(ssig, __fmul_rn(smu, smu)))),
-                       __fmul_rn(mu_new, mu_new));
-      smu = mu_new;
+      gaussian_beta_update(x, tau2, norm_scale, sa, sb, z_range, smu, ssig, fq, eq);
       sa = __fdiv_rn(__fsub_rn(eq, fq), __fsub_rn(fq, __fdiv_rn(eq, fq)));
       sb = __fdiv_rn(__fmul_rn(sa, __fsub_rn(1.0f, fq)), fq);
     }
   }
   if (status == 1) {
-    sb = __fadd_rn(sb, 1.0f);
+    sb = __fadd_rn(sb, 1.0f);  // :314
     z = kNaN;
   }
   a.out_a[i] = sa, a.out_b[i] = sb, a.out_mu[i] = smu, a.out_sigma2[i] = ssig;
@@ -666,11 +696,104 @@ __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs 
   a.out_px_cur[2 * I] = pxc0, a.out_px_cur[2 * I + 1] = pxc1;
 }
 
+// Line seeds: the body of DepthFilter::updateLineSeeds (src/depth_filter.cpp:367-471).  Both end points are searched around
+// the segment feature's own px / f (as the reference does) with their own depth hypotheses; computeTau uses sf / ef; the
+// shared Beta takes a = max(a_s, a_e), b = min(b_s, b_e) (updateLineSeed, :514-565).
+__global__ void __launch_bounds__(kA2Threads) line_seed_update_kernel(const SeedArgs a) {
+  __shared__ __align__(4) uint8_t s_border[kA2Threads][108];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kA2Threads + tid;
+  if (i >= a.n) return;
+  const size_t I = (size_t)i;
+  const CamP cam{a.fx, a.fy, a.cx, a.cy, a.width, a.height};
+  float sa = a.a[i], sb = a.b[i];
+  float mu_s = a.mu[i], sig_s = a.sigma2[i], mu_e = a.mu_e[i], sig_e = a.sigma2_e[i];
+  const float zr_s = a.z_range[i], zr_e = a.z_range_e[i];
+  int status = 0;
+  const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+  double z_s = kNaN, z_e = kNaN, pxc0 = kNaN, pxc1 = kNaN;
+  const int r = a.ref_index[i], c = a.cur_index[i];
+  const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
+  const V3 f{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
+  const V3 sf{a.ref_sf[3 * I], a.ref_sf[3 * I + 1], a.ref_sf[3 * I + 2]}, ef{a.ref_ef[3 * I], a.ref_ef[3 * I + 1], a.ref_ef[3 * I + 2]};
+  const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // :388
+  const Pose T_vis = pose_inverse(T_ref_cur);
+  // :389-400: both hypotheses in front of the camera, then both inside the image
+  bool visible;
+  {
+    const V3 ps = pose_act(T_vis, v_scale(sf, DD(1.0, (double)mu_s))), pe = pose_act(T_vis, v_scale(ef, DD(1.0, (double)mu_e)));
+    visible = !(ps.z < 0.0 || pe.z < 0.0);
+    if (visible) {
+      double u, v;
+      world2cam(cam, ps, u, v);
+      int ox = d2i_x86(u), oy = d2i_x86(v);
+      visible = ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+      if (visible) {
+        world2cam(cam, pe, u, v);
+        ox = d2i_x86(u), oy = d2i_x86(v);
+        visible = ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+      }
+    }
+  }
+  if (visible) {
+    const Pose T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
+    const double px0 = a.ref_px[2 * I], px1 = a.ref_px[2 * I + 1];
+    const int level_ref = a.ref_level[i];
+    bool ok = true;
+#pragma unroll 1
+    for (int e = 0; e < 2 && ok; ++e) {  // start point, then (only if it matched) end point: one inlined copy of the search
+      double de, dmin, dmax, zz = kNaN, q0 = kNaN, q1 = kNaN;
+      depth_range(e ? mu_e : mu_s, e ? sig_e : sig_s, de, dmin, dmax);
+      ok = epipolar_match(a, cam, i, r, c, T_cur_ref, px0, px1, f, level_ref, de, dmin, dmax, true, s_border[tid], zz, q0, q1);
+      if (e == 0)
+        z_s = zz, pxc0 = q0, pxc1 = q1;
+      else
+        z_e = zz;
+    }
+    status = ok ? 2 : 1;
+  }
+  if (status == 2) {
+    float x_s, tau2_s, x_e, tau2_e;
+    seed_measurement(cam, T_ref_cur, sf, z_s, x_s, tau2_s);
+    seed_measurement(cam, T_ref_cur, ef, z_e, x_e, tau2_e);
+    const float ns_s = __fsqrt_rn(__fadd_rn(sig_s, tau2_s)), ns_e = __fsqrt_rn(__fadd_rn(sig_e, tau2_e));
+    if (!(isnan(ns_s) || isnan(ns_e))) {
+      float f_s, e_s, f_e, e_e;
+      gaussian_beta_update(x_s, tau2_s, ns_s, sa, sb, zr_s, mu_s, sig_s, f_s, e_s);
+      gaussian_beta_update(x_e, tau2_e, ns_e, sa, sb, zr_e, mu_e, sig_e, f_e, e_e);
+      const float a_s = __fdiv_rn(__fsub_rn(e_s, f_s), __fsub_rn(f_s, __fdiv_rn(e_s, f_s)));
+      const float a_e = __fdiv_rn(__fsub_rn(e_e, f_e), __fsub_rn(f_e, __fdiv_rn(e_e, f_e)));
+      const float b_s = __fdiv_rn(__fmul_rn(a_s, __fsub_rn(1.0f, f_s)), f_s), b_e = __fdiv_rn(__fmul_rn(a_e, __fsub_rn(1.0f, f_e)), f_e);
+      sa = (a_s < a_e) ? a_e : a_s;  // std::max(a_s, a_e)
+      sb = (b_e < b_s) ? b_e : b_s;  // std::min(b_s, b_e)
+    }
+  }
+  if (status == 1) {
+    sb = __fadd_rn(sb, 1.0f);  // :410
+    z_s = z_e = kNaN;
+  }
+  a.out_a[i] = sa, a.out_b[i] = sb, a.out_mu[i] = mu_s, a.out_sigma2[i] = sig_s;
+  a.out_mu_e[i] = mu_e, a.out_sigma2_e[i] = sig_e;
+  a.out_status[i] = status;
+  a.out_converged[i] = (status == 2 && (double)__fsqrt_rn(sig_s) < DD((double)zr_s, a.convergence_thresh) &&
+                        (double)__fsqrt_rn(sig_e) < DD((double)zr_e, a.convergence_thresh))
+                           ? 1
+                           : 0;
+  a.out_depth[i] = z_s, a.out_depth_e[i] = z_e;
+  a.out_px_cur[2 * I] = pxc0, a.out_px_cur[2 * I + 1] = pxc1;
+}
+
 }  // namespace
 
 cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;
   match_direct_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t line_seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  line_seed_update_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -189,6 +189,15 @@ struct SeedArgs {
   const float* mu;
   const float* z_range;
   const float* sigma2;
+  // line seeds only
+  const double* ref_sf;
+  const double* ref_ef;
+  const float* mu_e;
+  const float* z_range_e;
+  const float* sigma2_e;
+  float* out_mu_e;
+  float* out_sigma2_e;
+  double* out_depth_e;
   float* out_a;
   float* out_b;
   float* out_mu;
@@ -199,6 +208,7 @@ struct SeedArgs {
   double* out_px_cur;
 };
 cudaError_t seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s);
+cudaError_t line_seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 struct StructOptArgs {

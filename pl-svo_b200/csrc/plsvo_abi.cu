@@ -65,7 +65,7 @@ struct plsvo_ctx_impl {
   DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv, f_dir, f_ohinv;  // align2D / align1D
   DevBuf m_ref_img, m_cur_img, m_T_ref, m_T_cur, m_ridx, m_cidx, m_px, m_f, m_lvl, m_edge, m_grad, m_pos, m_pxc, m_opx, m_osucc,
       m_olvl;  // findMatchDirect
-  DevBuf d_sa, d_sb, d_smu, d_szr, d_ssig, d_sout;  // depth-filter seeds
+  DevBuf d_sa, d_sb, d_smu, d_szr, d_ssig, d_smu_e, d_szr_e, d_ssig_e, d_sout;  // depth-filter seeds
   DevBuf s_T, s_pb, s_pf, s_pof, s_pp, s_sb, s_sf, s_ssf, s_sef, s_sp, s_ep, s_out;  // structure optimisation
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
       p_out_status;
@@ -196,7 +196,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
                     &c->s_pp,        &c->s_sb,       &c->s_sf,        &c->s_ssf,        &c->s_sef,       &c->s_sp,
                     &c->s_ep,        &c->s_out,      &c->d_sa,        &c->d_sb,         &c->d_smu,       &c->d_szr,
-                    &c->d_ssig,      &c->d_sout,     &c->p_T,
+                    &c->d_ssig,      &c->d_smu_e,    &c->d_szr_e,     &c->d_ssig_e,     &c->d_sout,      &c->p_T,
                     &c->p_pt_count,  &c->p_pt_f,     &c->p_pt_pos,    &c->p_pt_level,   &c->p_pt_valid,  &c->p_seg_count,
                     &c->p_seg_line,  &c->p_seg_spos, &c->p_seg_epos,  &c->p_seg_level,  &c->p_seg_valid, &c->p_out_T,
                     &c->p_out_cov,   &c->p_out_scale, &c->p_out_ei,   &c->p_out_ef,     &c->p_out_npt,   &c->p_out_nls,
@@ -1158,9 +1158,10 @@ extern "C" int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_b
   return PLSVO_OK;
 }
 
-extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batch* in, const plsvo_seed_result* out) {
-  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
-  plsvo_ctx_impl* c = CTX(ctx);
+namespace {
+// point seeds (lin == nullptr) and line seeds share staging; the line variant adds the end-point arrays
+int seed_update_run(plsvo_ctx_impl* c, const plsvo_seed_batch* in, const plsvo_seed_result* out, const plsvo_line_seed_batch* lin,
+                    const plsvo_line_seed_result* lout) {
   if (in->n_seeds < 0 || in->n_ref_images <= 0 || in->n_cur_images <= 0 || in->cam.width <= 0 || in->cam.height <= 0 ||
       in->n_iter < 0 || in->n_pyr_levels < 1 || in->n_pyr_levels > PLSVO_MAX_LEVELS || in->max_epi_search_steps < 0)
     return fail(c, PLSVO_ERR_INVALID, "seed batch description");
@@ -1168,7 +1169,9 @@ extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batc
   if (!in->T_ref_w || !in->T_cur_w || !in->ref_index || !in->cur_index || !in->ref_px || !in->ref_f || !in->ref_level || !in->a ||
       !in->b || !in->mu || !in->z_range || !in->sigma2 || !out->a || !out->b || !out->mu || !out->sigma2 || !out->status)
     return fail(c, PLSVO_ERR_INVALID, "seed arrays missing");
-  if (in->is_edgelet && !in->ref_grad) return fail(c, PLSVO_ERR_INVALID, "edgelets need ref_grad");
+  if (!lin && in->is_edgelet && !in->ref_grad) return fail(c, PLSVO_ERR_INVALID, "edgelets need ref_grad");
+  if (lin && (!lin->ref_sf || !lin->ref_ef || !lin->mu_e || !lin->z_range_e || !lin->sigma2_e || !lout->mu_e || !lout->sigma2_e))
+    return fail(c, PLSVO_ERR_INVALID, "line-seed end-point arrays missing");
   const size_t n = (size_t)in->n_seeds;
   for (int l = 0; l < in->n_pyr_levels; ++l) {
     if (!in->cur_img[l]) return fail(c, PLSVO_ERR_INVALID, "current pyramid level missing below n_pyr_levels");
@@ -1203,23 +1206,32 @@ extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batc
   CK(up(c->m_px, in->ref_px, n * 2, s, &a.ref_px));
   CK(up(c->m_f, in->ref_f, n * 3, s, &a.ref_f));
   CK(up(c->m_lvl, in->ref_level, n, s, &a.ref_level));
-  CK(up(c->m_edge, in->is_edgelet, n, s, &a.is_edgelet));
-  CK(up(c->m_grad, in->is_edgelet ? in->ref_grad : nullptr, n * 2, s, &a.ref_grad));
+  CK(up(c->m_edge, lin ? nullptr : in->is_edgelet, n, s, &a.is_edgelet));
+  CK(up(c->m_grad, (!lin && in->is_edgelet) ? in->ref_grad : nullptr, n * 2, s, &a.ref_grad));
+  if (lin) {
+    CK(up(c->m_pos, lin->ref_sf, n * 3, s, &a.ref_sf));
+    CK(up(c->m_pxc, lin->ref_ef, n * 3, s, &a.ref_ef));
+    CK(up(c->d_smu_e, lin->mu_e, n, s, &a.mu_e));
+    CK(up(c->d_szr_e, lin->z_range_e, n, s, &a.z_range_e));
+    CK(up(c->d_ssig_e, lin->sigma2_e, n, s, &a.sigma2_e));
+  }
   CK(up(c->d_sa, in->a, n, s, &a.a));
   CK(up(c->d_sb, in->b, n, s, &a.b));
   CK(up(c->d_smu, in->mu, n, s, &a.mu));
   CK(up(c->d_szr, in->z_range, n, s, &a.z_range));
   CK(up(c->d_ssig, in->sigma2, n, s, &a.sigma2));
-  // outputs: [px_cur 2n f64][depth n f64][a b mu sigma2 n f32 each][status n i32][converged n u8]
-  CK(ensure(c->d_sout, n * (16 + 8 + 16 + 4 + 1) + 64));
+  // outputs: [px_cur 2n f64][depth n f64][depth_e n f64][a b mu sigma2 mu_e sigma2_e n f32 each][status n i32][converged n u8]
+  CK(ensure(c->d_sout, n * (16 + 8 + 8 + 24 + 4 + 1) + 64));
   a.out_px_cur = static_cast<double*>(c->d_sout.p);
   a.out_depth = a.out_px_cur + 2 * n;
-  a.out_a = reinterpret_cast<float*>(a.out_depth + n);
+  a.out_depth_e = a.out_depth + n;
+  a.out_a = reinterpret_cast<float*>(a.out_depth_e + n);
   a.out_b = a.out_a + n, a.out_mu = a.out_b + n, a.out_sigma2 = a.out_mu + n;
-  a.out_status = reinterpret_cast<int32_t*>(a.out_sigma2 + n);
+  a.out_mu_e = a.out_sigma2 + n, a.out_sigma2_e = a.out_mu_e + n;
+  a.out_status = reinterpret_cast<int32_t*>(a.out_sigma2_e + n);
   a.out_converged = reinterpret_cast<uint8_t*>(a.out_status + n);
   CK(kernel_timer(c, 0, s));
-  CK(seed_update_kernel_launch(a, s));
+  CK(lin ? line_seed_update_kernel_launch(a, s) : seed_update_kernel_launch(a, s));
   CK(kernel_timer(c, 1, s));
   c->launches += 1;
   CK(cudaMemcpyAsync(out->a, a.out_a, n * 4, cudaMemcpyDeviceToHost, s));
@@ -1230,6 +1242,22 @@ extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batc
   if (out->converged) CK(cudaMemcpyAsync(out->converged, a.out_converged, n, cudaMemcpyDeviceToHost, s));
   if (out->depth) CK(cudaMemcpyAsync(out->depth, a.out_depth, n * 8, cudaMemcpyDeviceToHost, s));
   if (out->px_cur) CK(cudaMemcpyAsync(out->px_cur, a.out_px_cur, n * 16, cudaMemcpyDeviceToHost, s));
+  if (lin) {
+    CK(cudaMemcpyAsync(lout->mu_e, a.out_mu_e, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(lout->sigma2_e, a.out_sigma2_e, n * 4, cudaMemcpyDeviceToHost, s));
+    if (lout->depth_e) CK(cudaMemcpyAsync(lout->depth_e, a.out_depth_e, n * 8, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
+}
+}  // namespace
+
+extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batch* in, const plsvo_seed_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  return seed_update_run(CTX(ctx), in, out, nullptr, nullptr);
+}
+
+extern "C" int plsvo_line_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_line_seed_batch* in, const plsvo_line_seed_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  return seed_update_run(CTX(ctx), &in->seeds, &out->seeds, in, out);
 }

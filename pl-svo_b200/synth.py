@@ -688,3 +688,38 @@ def make_seed_batch(cam: Camera = VGA, n: int = 2000, n_ref: int = 3, n_cur: int
                     T_cur_w=c(T_cur_w, np.float64), ref_index=ref_index, cur_index=cur_index, ref_px=c(ref_px, np.float64),
                     ref_f=c(ref_f, np.float64), ref_level=ref_level, is_edgelet=is_edgelet, ref_grad=c(ref_grad, np.float64),
                     a=a, b=b, mu=mu, z_range=z_range, sigma2=sigma2, depth_gt=c(depth, np.float64))
+
+
+@dataclass
+class LineSeedData(SeedData):
+    """SeedData for the segment's mid-point feature and start-point Gaussian + the end-point fields (plsvo_line_seed_batch)."""
+
+    ref_sf: np.ndarray = None
+    ref_ef: np.ndarray = None
+    mu_e: np.ndarray = None
+    z_range_e: np.ndarray = None
+    sigma2_e: np.ndarray = None
+    depth_e_gt: np.ndarray = None
+
+
+def make_line_seed_batch(cam: Camera = VGA, n: int = 1500, seed: int = 9500, half_len_px: float = 18.0, device: str | torch.device = "cpu",
+                         **kw) -> LineSeedData:
+    """Line seeds: a point-seed batch for the segment mid points (px, f) plus end-point bearings sf / ef a few pixels either
+    side of the mid point and an independent inverse-depth Gaussian for the end point."""
+    base = make_seed_batch(cam=cam, n=n, seed=seed, device=device, edgelet_frac=0.0, **kw)
+    rng = np.random.Generator(np.random.PCG64(seed + 17))
+    ang = rng.uniform(0, 2 * math.pi, n)
+    off = np.stack([np.cos(ang), np.sin(ang)], -1) * rng.uniform(0.4, 1.0, (n, 1)) * half_len_px
+    spx, epx = base.ref_px - off, base.ref_px + off
+
+    def bearing(px):
+        d = np.stack([(px[:, 0] - cam.cx) / cam.fx, (px[:, 1] - cam.cy) / cam.fy, np.ones(n)], -1)
+        return np.ascontiguousarray(d / np.linalg.norm(d, axis=-1, keepdims=True))
+
+    stage = rng.uniform(0.0, 3.0, n)
+    z_range_e = base.z_range.copy()
+    sigma2_e = (z_range_e.astype(np.float64) ** 2 / 36.0 * 10.0 ** (-stage)).astype(np.float32)
+    mu_e = np.maximum(1.0 / base.depth_gt + rng.normal(0, 1, n) * np.sqrt(sigma2_e) * 0.5, 0.05).astype(np.float32)
+    fields = {f: getattr(base, f) for f in base.__dataclass_fields__}
+    return LineSeedData(**fields, ref_sf=bearing(spx), ref_ef=bearing(epx), mu_e=mu_e, z_range_e=z_range_e, sigma2_e=sigma2_e,
+                        depth_e_gt=base.depth_gt.copy())

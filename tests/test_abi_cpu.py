@@ -39,6 +39,8 @@ def test_struct_layout_matches_header(abi, tmp_path):
         " sizeof(plsvo_align2d_batch), sizeof(plsvo_align2d_result), sizeof(plsvo_align1d_batch), sizeof(plsvo_align1d_result),"
         " sizeof(plsvo_match_batch), sizeof(plsvo_match_result), sizeof(plsvo_structopt_batch), sizeof(plsvo_structopt_result),"
         " sizeof(plsvo_seed_batch), sizeof(plsvo_seed_result));\n"
+        'printf("%zu %zu %zu %zu\\n", sizeof(plsvo_line_seed_batch), sizeof(plsvo_line_seed_result), offsetof(plsvo_line_seed_batch, ref_sf),'
+        " offsetof(plsvo_line_seed_result, mu_e));\n"
         'printf("%zu %zu %zu %zu\\n", offsetof(plsvo_match_batch, px_cur), offsetof(plsvo_seed_batch, cam),'
         " offsetof(plsvo_seed_batch, sigma2), offsetof(plsvo_structopt_batch, seg_epos));\n"
         "return 0;}\n"
@@ -49,7 +51,9 @@ def test_struct_layout_matches_header(abi, tmp_path):
     sizes = [int(x) for x in out[:7]]
     offs = [int(x) for x in out[7:11]]
     next_sizes = [int(x) for x in out[11:23]]
-    next_offs = [int(x) for x in out[23:]]
+    line = [int(x) for x in out[23:27]]
+    assert line == [C.sizeof(abi.LineSeedBatch), C.sizeof(abi.LineSeedResult), abi.LineSeedBatch.ref_sf.offset, abi.LineSeedResult.mu_e.offset]
+    next_offs = [int(x) for x in out[27:]]
     assert next_sizes == [C.sizeof(t) for t in (abi.PyramidBatch, abi.PyramidResult, abi.Align2DBatch, abi.Align2DResult,
                                                  abi.Align1DBatch, abi.Align1DResult, abi.MatchBatch, abi.MatchResult,
                                                  abi.StructOptBatch, abi.StructOptResult, abi.SeedBatch, abi.SeedResult)]

@@ -104,3 +104,55 @@ def test_gpu_seed_update_options_and_bad_input(pkg, oracle, abi, synth, gen_devi
     b.cur_pitch[1] = b.cur_pitch[1] + 16  # not dense
     out = abi.SeedOut(d.n)
     assert ctx.lib.plsvo_seed_update_batch_run(ctx.handle, C.byref(b), C.byref(out.struct)) == abi.ERR_INVALID
+
+
+# ---- line seeds: DepthFilter::updateLineSeeds (src/depth_filter.cpp:367-471) -------------------------------------
+LINE_FIELDS = ("a", "b", "mu", "sigma2", "mu_e", "sigma2_e")
+
+
+@pytest.mark.parametrize("seed,kw", [(9500, {}), (9501, dict(n_pyr_levels=5)), (9502, dict(baseline=0.3)), (9503, dict(cam="QVGA"))])
+def test_oracle_line_seed_update_is_bit_identical_to_the_reference_tus(oracle, abi, synth, seed, kw):
+    if not oracle.build_ref():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    kw = dict(kw)
+    if "cam" in kw:
+        kw["cam"] = getattr(synth, kw["cam"])
+    d = synth.make_line_seed_batch(n=1000, seed=seed, **kw)
+    o = oracle.line_seed_update(abi, d, 4)
+    r = oracle.ref_line_seed_update(abi, d)
+    alive = r.status == 0
+    assert alive.mean() > 0.99
+    for f in LINE_FIELDS:
+        np.testing.assert_array_equal(getattr(o, f)[alive], getattr(r, f)[alive], err_msg=f)
+    assert set(np.unique(o.status)) == {0, 1, 2}
+    for opts in (dict(align_1d=True), dict(subpix_refinement=False), dict(max_epi_search_steps=30)):
+        for k, v in opts.items():
+            setattr(d, k, v)
+        o = oracle.line_seed_update(abi, d, 4)
+        r = oracle.ref_line_seed_update(abi, d)
+        alive = r.status == 0
+        for f in LINE_FIELDS:
+            np.testing.assert_array_equal(getattr(o, f)[alive], getattr(r, f)[alive], err_msg=f"{opts} {f}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,kw", [(9600, {}), (9601, dict(n_pyr_levels=5, baseline=0.25))])
+def test_gpu_line_seed_update_matches_the_oracle(pkg, oracle, abi, synth, gen_device, seed, kw):
+    d = synth.make_line_seed_batch(n=5000, seed=seed, device=gen_device, **kw)
+    ref = oracle.line_seed_update(abi, d, 8)
+    out = pkg.DepthFilter().updateLineSeeds(d)
+    np.testing.assert_array_equal(out.status, ref.status)
+    up = ref.status == abi.SEED_UPDATED
+    np.testing.assert_array_equal(out.depth[up], ref.depth[up])      # z_s: exact
+    np.testing.assert_array_equal(out.depth_e[up], ref.depth_e[up])  # z_e: exact
+    assert np.isnan(out.depth[~up]).all() and np.isnan(out.depth_e[~up]).all()
+    for f in LINE_FIELDS:
+        np.testing.assert_array_equal(getattr(out, f)[~up], getattr(ref, f)[~up], err_msg=f)
+    ok = up & np.isfinite(ref.a) & np.isfinite(ref.sigma2) & np.isfinite(ref.sigma2_e)
+    for f in ("mu", "mu_e"):
+        np.testing.assert_allclose(getattr(out, f)[ok], getattr(ref, f)[ok], rtol=2e-6, atol=0, err_msg=f)
+    for f in ("sigma2", "sigma2_e"):
+        np.testing.assert_allclose(getattr(out, f)[ok], getattr(ref, f)[ok], rtol=2e-4, atol=5e-7, err_msg=f)
+    np.testing.assert_allclose(out.a[ok], ref.a[ok], rtol=5e-2)
+    np.testing.assert_allclose(out.b[ok], ref.b[ok], rtol=5e-2, atol=1e-3)
+    assert (out.converged == ref.converged).mean() > 0.999

@@ -249,6 +249,27 @@ def main():
         "max_rel_diff_mu": float(np.max(np.abs(dfo["gpu"].mu[okm] - cpu_sd.mu[okm]) / np.abs(cpu_sd.mu[okm]))) if okm.any() else None,
         "status_hist_not_visible_no_match_updated": np.bincount(cpu_sd.status, minlength=3).tolist(),
         "cpu_oracle_seeds_per_s": rate, "cpu_threads": th}
+    # ---- line seeds -------------------------------------------------------------------------------------------
+    ls = synth.make_line_seed_batch(n=ns // 2, n_ref=8, n_cur=8, n_pyr_levels=3, seed=6, device=dev)
+    lo = {}
+
+    def run_ls():
+        lo["gpu"] = dfilt.updateLineSeeds(ls)
+
+    k_ms, e_ms = timed(ctx, run_ls, args.reps)
+    olib.plsvo_oracle_line_seed_update_batch.restype = C.c_int
+    lbb, keep_ls = abi.make_line_seed_batch(ls)
+    cpu_ls = abi.LineSeedOut(ls.n)
+    rate, th = best_threads(lambda t: olib.plsvo_oracle_line_seed_update_batch(C.byref(lbb), C.byref(cpu_ls.line_struct), t), ls.n)
+    upl = cpu_ls.status == abi.SEED_UPDATED
+    exact = bool(np.array_equal(lo["gpu"].status, cpu_ls.status) and np.array_equal(lo["gpu"].depth[upl], cpu_ls.depth[upl])
+                 and np.array_equal(lo["gpu"].depth_e[upl], cpu_ls.depth_e[upl]))
+    res["depth_filter_line_seed_update"] = {
+        "workload": f"{ls.n} line seeds (two end-point searches each), 8 keyframes -> 8 current VGA frames (DepthFilter::updateLineSeeds body)",
+        "kernel_ms": k_ms, "e2e_ms": e_ms, "seeds_per_s_kernel": ls.n / (k_ms * 1e-3), "seeds_per_s_e2e": ls.n / (e_ms * 1e-3),
+        "status_and_depths_bit_exact_vs_oracle": exact,
+        "status_hist_not_visible_no_match_updated": np.bincount(cpu_ls.status, minlength=3).tolist(),
+        "cpu_oracle_seeds_per_s": rate, "cpu_threads": th}
     print(json.dumps(res, indent=1))
 
 
