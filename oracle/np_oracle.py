@@ -5,7 +5,7 @@ numpy.linalg instead of a hand LDLT, vectorised patches instead of pointer walks
 
 TEST INFRASTRUCTURE ONLY.  Its job is to pin the C++ oracle: two independent transcriptions of
 the same source must produce the same per-iteration H, Jres, chi2, n_meas and step
-(tests/test_oracle_cross.py).  Float32 steps that the reference does in float are done with
+(tests/test_oracle_cpu.py::test_cpp_and_numpy_restatements_agree_*).  Float32 steps that the reference does in float are done with
 numpy float32 scalars/arrays (IEEE, no FMA); sums over pixels run in float64 in a different
 order than the reference, so agreement is to ~1e-6 relative on chi2 and ~1e-9 on H.
 
