@@ -26,6 +26,8 @@ struct Point_ {
   T x, y;
   Point_() : x(0), y(0) {}
   Point_(T xx, T yy) : x(xx), y(yy) {}
+  template <class U>
+  Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
 };
 typedef Point_<int> Point;
 typedef Point_<int> Point2i;
@@ -173,12 +175,22 @@ class Mat {
   MatIterator_<T> begin() {
     return MatIterator_<T>(data, step.p[0], cols);
   }
+  void copyTo(Mat& dst) const { dst = clone(); }
   Mat clone() const {
     Mat m(rows, cols, type_);
     for (int i = 0; i < rows; ++i) std::memcpy(m.ptr(i), ptr(i), (size_t)cols * step.p[1]);
     return m;
   }
 };
+
+// drawing / colour conversion named by the reference's display code (frame_handler_mono.cpp:280-300): declared so that
+// the callers compile; nothing on the measured path calls them
+enum { COLOR_GRAY2BGR = 8 };
+inline void cvtColor(const Mat& src, Mat& dst, int) { dst = src.clone(); }
+inline void rectangle(Mat&, Point, Point, const Scalar&, int = 1) {}
+inline void rectangle(Mat&, Rect, const Scalar&, int = 1) {}
+inline void line(Mat&, Point, Point, const Scalar&, int = 1) {}
+inline void circle(Mat&, Point, int, const Scalar&, int = 1) {}
 
 }  // namespace cv
 #endif

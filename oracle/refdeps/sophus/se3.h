@@ -51,6 +51,36 @@ class SE3 {
     return SE3(so3, V * upsilon);
   }
 
+  // SE3::log (sophus/se3.cpp): [upsilon, omega] with omega = SO3::log and upsilon = V^-1 t
+  static Vector6d log(const SE3& se3) {
+    Vector6d upsilon_omega;
+    const Quaterniond& q = se3.so3_.unit_quaternion();
+    const double n = q.vec().norm(), w = q.w(), squared_w = w * w;
+    double two_atan_nbyw_by_n;
+    if (n < SMALL_EPS) {
+      two_atan_nbyw_by_n = 2. / w - 2. * (n * n) / (w * squared_w);
+    } else if (std::abs(w) < SMALL_EPS) {
+      two_atan_nbyw_by_n = (w > 0 ? M_PI : -M_PI) / n;
+    } else {
+      two_atan_nbyw_by_n = 2 * std::atan(n / w) / n;
+    }
+    const double theta = two_atan_nbyw_by_n * n;
+    const Vector3d omega = two_atan_nbyw_by_n * q.vec();
+    Vector3d upsilon;
+    if (theta < SMALL_EPS) {
+      const Matrix3d Omega = SO3::hat(omega);
+      const Matrix3d V_inv = Matrix3d::Identity() - 0.5 * Omega + (1. / 12.) * (Omega * Omega);
+      upsilon = V_inv * se3.translation_;
+    } else {
+      const Matrix3d Omega = SO3::hat(omega);
+      const Matrix3d V_inv = (Matrix3d::Identity() - 0.5 * Omega +
+                              (1 - theta / (2 * std::tan(theta / 2))) / (theta * theta) * (Omega * Omega));
+      upsilon = V_inv * se3.translation_;
+    }
+    for (int k = 0; k < 3; ++k) upsilon_omega[k] = upsilon[k], upsilon_omega[3 + k] = omega[k];
+    return upsilon_omega;
+  }
+  Vector6d log() const { return log(*this); }
   Matrix3d rotation_matrix() const { return so3_.matrix(); }
   const Vector3d& translation() const { return translation_; }
   Vector3d& translation() { return translation_; }
