@@ -146,6 +146,56 @@ def build_ref(force: bool = False) -> str | None:
     return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
 
 
+SHIMREF_LIB_PATH = os.path.join(_HERE, "_ref", "libplsvo_shimref.so")
+_shimref_lib = None
+
+
+def build_shimref(force: bool = False) -> str | None:
+    """oracle/_ref/libplsvo_shimref.so: reference-typed Frame / Feature objects driven through the B200 shim compiled in
+    reference-headers mode (oracle/shimref_harness.cpp).  Needs /root/reference and the built CUDA library to build."""
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "feature.cpp")) and os.path.exists(
+            os.path.join(_HERE, "..", "pl-svo_b200", "csrc", "libplsvo_b200.so")):
+        subprocess.check_call(["make", "-C", _HERE, "shimref", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
+    return SHIMREF_LIB_PATH if os.path.exists(SHIMREF_LIB_PATH) else None
+
+
+def load_shimref(abi):
+    global _shimref_lib
+    if _shimref_lib is None:
+        lib = C.CDLL(SHIMREF_LIB_PATH)
+        P = C.POINTER
+        lib.plsvo_shimref_align_batch.restype = C.c_int
+        lib.plsvo_shimref_align_batch.argtypes = [P(abi.AlignBatch), P(abi.AlignParams), P(abi.AlignResult)]
+        lib.plsvo_shimref_poseopt_batch.restype = C.c_int
+        lib.plsvo_shimref_poseopt_batch.argtypes = [P(abi.PoseOptBatch), P(abi.PoseOptParams), P(abi.PoseOptResult)]
+        _shimref_lib = lib
+    return _shimref_lib
+
+
+def shimref_align(abi, data, params=None):
+    """plsvo::SparseImgAlign(...).run(ref, cur) of the B200 shim on reference-typed frames -> abi.AlignOut
+    (T_cur_w, n_tracked, seg_killed; H holds getFisherInformation() = H / (5e-4 * 255^2))."""
+    lib = load_shimref(abi)
+    params = params or abi.align_params(data.max_level, data.min_level)
+    batch, keep = abi.make_align_batch(data)
+    out = abi.AlignOut(data.batch, data.n_segs)
+    rc = lib.plsvo_shimref_align_batch(C.byref(batch), C.byref(params), C.byref(out.struct))
+    if rc != 0:
+        raise RuntimeError(f"shimref align failed rc={rc}")
+    return out
+
+
+def shimref_poseopt(abi, data, params=None):
+    lib = load_shimref(abi)
+    params = params or abi.poseopt_params()
+    batch, keep = abi.make_poseopt_batch(data)
+    out = abi.PoseOptOut(data.batch, data.n_pts, data.n_segs)
+    rc = lib.plsvo_shimref_poseopt_batch(C.byref(batch), C.byref(params), C.byref(out.struct))
+    if rc != 0:
+        raise RuntimeError(f"shimref poseopt failed rc={rc}")
+    return out
+
+
 def ref_available() -> bool:
     return os.path.exists(REF_LIB_PATH)
 

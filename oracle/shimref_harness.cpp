@@ -1,0 +1,181 @@
+// shimref_harness.cpp — the reference's OWN object model driven through the B200 shim.
+//
+// TEST INFRASTRUCTURE (same rule as the other files in oracle/).  `make -C oracle shimref` compiles, where they lie,
+//     /root/reference/src/feature.cpp                 (PointFeat / LineFeat constructors of the reference)
+// together with pl-svo_b200/host/plsvo_shim.cpp in -DPLSVO_SHIM_WITH_REFERENCE_HEADERS mode — i.e. against the reference's
+// real plsvo::Frame / PointFeat / LineFeat / Point / LineSeg / Sophus::SE3 definitions, with plsvo/sparse_img_align.h and
+// plsvo/pose_optimizer.h resolved to the shim through pl-svo_b200/host/overlay/ — and links the CUDA C-ABI library.
+// This file builds reference-typed frames from a flat batch (exactly as oracle/ref_harness.cpp does for the CPU
+// reference) and makes the two calls of src/frame_handler_mono.cpp:272-274 and :327-329; what answers them here is the
+// GPU.  tests/test_gpu_shim.py compares the poses / killed segments / outliers / covariance that come back in the
+// reference's own objects with the C ABI called directly and with the oracle.
+#include <plsvo/feature.h>
+#include <plsvo/feature3D.h>
+#include <plsvo/frame.h>
+#include <plsvo/pose_optimizer.h>    // -> plsvo_shim.h through the overlay
+#include <plsvo/sparse_img_align.h>  // -> plsvo_shim.h through the overlay
+#include <vikit/pinhole_camera.h>
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../include/plsvo_b200.h"
+
+namespace plsvo {
+int Frame::frame_counter_ = 0;
+Frame::Frame(vk::AbstractCamera* cam, const cv::Mat&, double timestamp)
+    : id_(0), timestamp_(timestamp), cam_(cam), key_pts_(5), is_keyframe_(false), v_kf_(NULL) {}
+Frame::~Frame() {
+  for (PointFeat* f : pt_fts_) delete f;
+  for (LineFeat* f : seg_fts_) delete f;
+}
+Point::Point(const Vector3d& pos) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {}
+bool Point::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
+void Point::optimize(const size_t) {}
+LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos) : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {}
+bool LineSeg::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
+void LineSeg::optimize(const size_t) {}
+}  // namespace plsvo
+
+namespace {
+using Eigen::Quaterniond;
+using Eigen::Vector2d;
+using Eigen::Vector3d;
+using plsvo::FramePtr;
+using Sophus::SE3;
+SE3 pose_from7(const double* p) { return SE3(Quaterniond(p[3], p[0], p[1], p[2]), Vector3d(p[4], p[5], p[6])); }
+void pose_to7(const SE3& T, double* p) {
+  const Quaterniond& q = T.unit_quaternion();
+  p[0] = q.x(), p[1] = q.y(), p[2] = q.z(), p[3] = q.w();
+  p[4] = T.translation()[0], p[5] = T.translation()[1], p[6] = T.translation()[2];
+}
+Vector3d v3(const double* p) { return Vector3d(p[0], p[1], p[2]); }
+Vector2d v2(const double* p) { return Vector2d(p[0], p[1]); }
+}  // namespace
+
+extern "C" {
+
+int plsvo_shimref_set_device(int device) { return plsvo::shim_set_device(device); }
+
+// SparseImgAlign(max, min, n_iter, GaussNewton, false, false).run(ref, cur) on reference-typed frames, pair by pair
+int plsvo_shimref_align_batch(const plsvo_align_batch* B, const plsvo_align_params* P, const plsvo_align_result* out) {
+  if (!B || !P || !out) return PLSVO_ERR_INVALID;
+  for (int b = 0; b < B->batch; ++b) {
+    const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
+    const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
+    const size_t po = (size_t)b * B->n_pts, so = (size_t)b * B->n_segs;
+    vk::PinholeCamera cam(B->cam.width, B->cam.height, B->cam.fx, B->cam.fy, B->cam.cx, B->cam.cy);
+    FramePtr ref(new plsvo::Frame(&cam, cv::Mat(), 0.0)), cur(new plsvo::Frame(&cam, cv::Mat(), 1.0));
+    ref->img_pyr_.resize(P->max_level + 1);
+    cur->img_pyr_.resize(P->max_level + 1);
+    for (int l = P->min_level; l <= P->max_level; ++l) {
+      const int cols = B->cam.width >> l, rows = B->cam.height >> l;
+      ref->img_pyr_[l] = cv::Mat(rows, cols, CV_8U, const_cast<uint8_t*>(B->ref_img[l] + (size_t)b * B->img_stride[l]), B->img_pitch[l]);
+      cur->img_pyr_[l] = cv::Mat(rows, cols, CV_8U, const_cast<uint8_t*>(B->cur_img[l] + (size_t)b * B->img_stride[l]), B->img_pitch[l]);
+    }
+    ref->T_f_w_ = pose_from7(B->T_ref_w + 7 * (size_t)b);
+    cur->T_f_w_ = pose_from7(B->T_cur_w + 7 * (size_t)b);
+    std::vector<std::unique_ptr<plsvo::Point>> points;
+    std::vector<std::unique_ptr<plsvo::LineSeg>> lines;
+    std::vector<plsvo::LineFeat*> segs;
+    for (int i = 0; i < np; ++i) {
+      plsvo::Point* p3 = NULL;
+      if (!B->pt_valid || B->pt_valid[po + i]) {
+        points.emplace_back(new plsvo::Point(v3(B->pt_pos + 3 * (po + i))));
+        p3 = points.back().get();
+      }
+      ref->pt_fts_.push_back(new plsvo::PointFeat(ref.get(), p3, v2(B->pt_px + 2 * (po + i)), v3(B->pt_f + 3 * (po + i)), 0));
+    }
+    for (int j = 0; j < ns; ++j) {
+      plsvo::LineSeg* l3 = NULL;
+      if (!B->seg_valid || B->seg_valid[so + j]) {
+        lines.emplace_back(new plsvo::LineSeg(v3(B->seg_spos + 3 * (so + j)), v3(B->seg_epos + 3 * (so + j))));
+        l3 = lines.back().get();
+      }
+      plsvo::LineFeat* f = new plsvo::LineFeat(ref.get(), l3, v2(B->seg_spx + 2 * (so + j)), v2(B->seg_epx + 2 * (so + j)),
+                                               v3(B->seg_sf + 3 * (so + j)), v3(B->seg_ef + 3 * (so + j)), 0);
+      f->length = B->seg_length[so + j];
+      ref->seg_fts_.push_back(f);
+      segs.push_back(f);
+    }
+    // src/frame_handler_mono.cpp:272-274, verbatim but for the Config:: constants
+    plsvo::SparseImgAlign img_align(P->max_level, P->min_level, P->n_iter, plsvo::SparseImgAlign::GaussNewton, false, false);
+    const size_t img_align_n_tracked = img_align.run(ref, cur);
+    pose_to7(cur->T_f_w_, out->T_cur_w + 7 * (size_t)b);
+    out->n_tracked[b] = (int64_t)img_align_n_tracked;
+    if (out->H) img_align.getFisherInformation(out->H + 36 * (size_t)b);  // H / (5e-4 * 255^2)
+    if (out->seg_killed) {
+      for (int j = 0; j < B->n_segs; ++j) out->seg_killed[so + j] = 0;
+      for (int j = 0; j < ns; ++j)
+        out->seg_killed[so + j] = ((!B->seg_valid || B->seg_valid[so + j]) && segs[j]->feat3D == NULL) ? 1 : 0;
+    }
+  }
+  return PLSVO_OK;
+}
+
+// pose_optimizer::optimizeGaussNewton(thresh, n_iter[, n_iter_ref], false, frame, ...) on reference-typed frames
+int plsvo_shimref_poseopt_batch(const plsvo_poseopt_batch* B, const plsvo_poseopt_params* P, const plsvo_poseopt_result* out) {
+  if (!B || !P || !out) return PLSVO_ERR_INVALID;
+  for (int b = 0; b < B->batch; ++b) {
+    const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
+    const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
+    const size_t po = (size_t)b * B->n_pts, so = (size_t)b * B->n_segs;
+    vk::PinholeCamera cam(640, 480, B->fx, B->fx, 320, 240);
+    FramePtr frame(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+    frame->T_f_w_ = pose_from7(B->T_f_w + 7 * (size_t)b);
+    frame->Cov_.setZero();
+    std::vector<std::unique_ptr<plsvo::Point>> points;
+    std::vector<std::unique_ptr<plsvo::LineSeg>> lines;
+    std::vector<plsvo::PointFeat*> pts;
+    std::vector<plsvo::LineFeat*> segs;
+    for (int i = 0; i < np; ++i) {
+      plsvo::Point* p3 = NULL;
+      if (!B->pt_valid || B->pt_valid[po + i]) {
+        points.emplace_back(new plsvo::Point(v3(B->pt_pos + 3 * (po + i))));
+        p3 = points.back().get();
+      }
+      pts.push_back(new plsvo::PointFeat(frame.get(), p3, Vector2d(0, 0), v3(B->pt_f + 3 * (po + i)), B->pt_level[po + i]));
+      frame->pt_fts_.push_back(pts.back());
+    }
+    for (int j = 0; j < ns; ++j) {
+      plsvo::LineSeg* l3 = NULL;
+      if (!B->seg_valid || B->seg_valid[so + j]) {
+        lines.emplace_back(new plsvo::LineSeg(v3(B->seg_spos + 3 * (so + j)), v3(B->seg_epos + 3 * (so + j))));
+        l3 = lines.back().get();
+      }
+      plsvo::LineFeat* f = new plsvo::LineFeat(frame.get(), l3, Vector2d(0, 0), Vector2d(1, 0), Vector3d(0, 0, 1), Vector3d(1, 0, 1),
+                                               B->seg_level[so + j]);
+      f->line = v3(B->seg_line + 3 * (so + j));
+      frame->seg_fts_.push_back(f);
+      segs.push_back(f);
+    }
+    double estimated_scale = 0, error_init = 0, error_final = 0;
+    size_t num_obs_pt = 0, num_obs_ls = 0;
+    if (P->n_iter_ref < 0)  // src/frame_handler_mono.cpp:327-329
+      plsvo::pose_optimizer::optimizeGaussNewton(P->reproj_thresh, (size_t)P->n_iter, false, frame, estimated_scale, error_init,
+                                                 error_final, num_obs_pt, num_obs_ls);
+    else
+      plsvo::pose_optimizer::optimizeGaussNewton(P->reproj_thresh, (size_t)P->n_iter, (size_t)P->n_iter_ref, false, frame,
+                                                 estimated_scale, error_init, error_final, num_obs_pt, num_obs_ls);
+    pose_to7(frame->T_f_w_, out->T_f_w + 7 * (size_t)b);
+    if (out->cov)
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) out->cov[36 * (size_t)b + 6 * i + j] = frame->Cov_(i, j);
+    if (out->estimated_scale) out->estimated_scale[b] = estimated_scale;
+    if (out->error_init) out->error_init[b] = error_init;
+    if (out->error_final) out->error_final[b] = error_final;
+    if (out->num_obs_pt) out->num_obs_pt[b] = (int64_t)num_obs_pt;
+    if (out->num_obs_ls) out->num_obs_ls[b] = (int64_t)num_obs_ls;
+    if (out->pt_outlier) {
+      std::memset(out->pt_outlier + po, 0, B->n_pts);
+      for (int i = 0; i < np; ++i) out->pt_outlier[po + i] = ((!B->pt_valid || B->pt_valid[po + i]) && pts[i]->feat3D == NULL) ? 1 : 0;
+    }
+    if (out->seg_outlier && B->n_segs) {
+      std::memset(out->seg_outlier + so, 0, B->n_segs);
+      for (int j = 0; j < ns; ++j) out->seg_outlier[so + j] = ((!B->seg_valid || B->seg_valid[so + j]) && segs[j]->feat3D == NULL) ? 1 : 0;
+    }
+  }
+  return PLSVO_OK;
+}
+}

@@ -74,3 +74,50 @@ def test_shim_pose_optimizer(shim, abi, synth, oracle, n_ref):
         np.testing.assert_allclose(sc[2], ref.error_final[b], rtol=1e-6)
         assert int(sc[3]) == ref.num_obs_pt[b] and int(sc[4]) == ref.num_obs_ls[b]
         np.testing.assert_allclose(cov, ref.cov[b], rtol=1e-5, atol=1e-9 * np.abs(ref.cov[b]).max())
+
+
+# ---- the reference's OWN Frame / Feature / SE3 types through the shim (oracle/shimref_harness.cpp) ------------------
+@pytest.fixture(scope="module")
+def shimref(oracle, abi):
+    """oracle/_ref/libplsvo_shimref.so: plsvo_shim.cpp compiled in -DPLSVO_SHIM_WITH_REFERENCE_HEADERS mode against the
+    reference's real class definitions (built where /root/reference exists, travels prebuilt to the GPU box)."""
+    if not oracle.build_shimref():
+        pytest.skip("oracle/_ref/libplsvo_shimref.so is not built and /root/reference is absent")
+    oracle.load_shimref(abi)
+    return oracle
+
+
+def test_reference_typed_frames_through_the_shim_align(shimref, pkg, abi, synth, gen_device):
+    d = synth.make_align_batch(batch=6, n_pts=200, n_segs=60, device=gen_device, seed=8300)
+    d.seg_valid = np.ones((6, 60), np.uint8)
+    d.seg_valid[:, ::7] = 0
+    d.pt_valid = np.ones((6, 200), np.uint8)
+    d.pt_valid[:, ::11] = 0
+    got = shimref.shimref_align(abi, d)                 # reference objects -> shim -> C ABI (B = 1 per pair) -> CUDA
+    direct = pkg.SparseImgAlign(4, 2, 30).run(d)        # the C ABI called directly on the whole batch
+    cpu = shimref.align(abi, d, n_threads=4)            # the oracle
+    np.testing.assert_array_equal(got.n_tracked, direct.n_tracked)
+    np.testing.assert_array_equal(got.seg_killed, direct.seg_killed)
+    # same kernel, same arrays — except that the poses make a trip through the reference's SE3 (the quaternion is
+    # re-normalised: last-bit input differences), so agreement is to round-off, not bit for bit
+    ang, rel = synth.pose_error(got.T_cur_w, direct.T_cur_w)
+    assert ang.max() <= 1e-5 and rel.max() <= 1e-4 and np.median(ang) < 1e-9
+    np.testing.assert_allclose(got.H * (5e-4 * 255 * 255), direct.H, rtol=1e-5, atol=1e-6 * np.abs(direct.H).max())
+    ang, rel = synth.pose_error(got.T_cur_w, cpu.T_cur_w)
+    assert ang.max() <= 1e-5 and rel.max() <= 1e-4
+    np.testing.assert_array_equal(got.n_tracked, cpu.n_tracked)
+    np.testing.assert_array_equal(got.seg_killed, cpu.seg_killed)
+
+
+@pytest.mark.parametrize("n_ref", [-1, 3])
+def test_reference_typed_frames_through_the_shim_poseopt(shimref, pkg, abi, synth, n_ref):
+    d = synth.make_poseopt_batch(batch=6, n_pts=200, n_segs=60, seed=8400)
+    p = abi.poseopt_params(2.0, 10, n_ref)
+    got = shimref.shimref_poseopt(abi, d, p)
+    direct = pkg.pose_optimizer.optimizeGaussNewton(2.0, 10, False, d, n_iter_ref=None if n_ref < 0 else n_ref)
+    for f in ("num_obs_pt", "num_obs_ls", "pt_outlier", "seg_outlier"):
+        np.testing.assert_array_equal(getattr(got, f), getattr(direct, f), err_msg=f)
+    np.testing.assert_allclose(got.T_f_w, direct.T_f_w, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got.cov, direct.cov, rtol=1e-6, atol=1e-12)
+    for f in ("estimated_scale", "error_init", "error_final"):
+        np.testing.assert_allclose(getattr(got, f), getattr(direct, f), rtol=1e-9, err_msg=f)
