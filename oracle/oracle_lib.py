@@ -159,8 +159,30 @@ def build_shimref(force: bool = False) -> str | None:
     return SHIMREF_LIB_PATH if os.path.exists(SHIMREF_LIB_PATH) else None
 
 
-def load_shimref(abi):
-    global _shimref_lib
+SHIMREF_CPU_LIB_PATH = os.path.join(_HERE, "_ref", "libplsvo_shimref_cpu.so")
+_shimref_cpu_lib = None
+
+
+def build_shimref_cpu(force: bool = False) -> str | None:
+    """oracle/_ref/libplsvo_shimref_cpu.so: the same harness + shim with the C ABI answered by the CPU oracle
+    (oracle/abi_on_oracle.cpp) — checks the shim's packing of reference objects without a GPU."""
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "feature.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "shimref-cpu", f"REFERENCE={REFERENCE_ROOT}"] + (["-B"] if force else ["-s"]))
+    return SHIMREF_CPU_LIB_PATH if os.path.exists(SHIMREF_CPU_LIB_PATH) else None
+
+
+def load_shimref(abi, cpu: bool = False):
+    global _shimref_lib, _shimref_cpu_lib
+    if cpu:
+        if _shimref_cpu_lib is None:
+            lib = C.CDLL(SHIMREF_CPU_LIB_PATH)
+            P = C.POINTER
+            lib.plsvo_shimref_align_batch.restype = C.c_int
+            lib.plsvo_shimref_align_batch.argtypes = [P(abi.AlignBatch), P(abi.AlignParams), P(abi.AlignResult)]
+            lib.plsvo_shimref_poseopt_batch.restype = C.c_int
+            lib.plsvo_shimref_poseopt_batch.argtypes = [P(abi.PoseOptBatch), P(abi.PoseOptParams), P(abi.PoseOptResult)]
+            _shimref_cpu_lib = lib
+        return _shimref_cpu_lib
     if _shimref_lib is None:
         lib = C.CDLL(SHIMREF_LIB_PATH)
         P = C.POINTER
@@ -172,10 +194,10 @@ def load_shimref(abi):
     return _shimref_lib
 
 
-def shimref_align(abi, data, params=None):
+def shimref_align(abi, data, params=None, cpu: bool = False):
     """plsvo::SparseImgAlign(...).run(ref, cur) of the B200 shim on reference-typed frames -> abi.AlignOut
     (T_cur_w, n_tracked, seg_killed; H holds getFisherInformation() = H / (5e-4 * 255^2))."""
-    lib = load_shimref(abi)
+    lib = load_shimref(abi, cpu)
     params = params or abi.align_params(data.max_level, data.min_level)
     batch, keep = abi.make_align_batch(data)
     out = abi.AlignOut(data.batch, data.n_segs)
@@ -185,8 +207,8 @@ def shimref_align(abi, data, params=None):
     return out
 
 
-def shimref_poseopt(abi, data, params=None):
-    lib = load_shimref(abi)
+def shimref_poseopt(abi, data, params=None, cpu: bool = False):
+    lib = load_shimref(abi, cpu)
     params = params or abi.poseopt_params()
     batch, keep = abi.make_poseopt_batch(data)
     out = abi.PoseOptOut(data.batch, data.n_pts, data.n_segs)

@@ -164,3 +164,34 @@ def test_golden_fixtures_are_reference_outputs(ref, abi, synth):
         for f in ("T_f_w", "cov", "estimated_scale", "error_init", "error_final", "num_obs_pt", "num_obs_ls", "pt_outlier",
                   "seg_outlier"):
             np.testing.assert_array_equal(getattr(r, f), z[f"out_{tag}_{f}"], err_msg=f"{tag} {f}")
+
+
+def test_shim_packs_reference_objects_like_the_reference_reads_them(ref, abi, synth):
+    """pl-svo_b200/host/plsvo_shim.cpp compiled in -DPLSVO_SHIM_WITH_REFERENCE_HEADERS mode, fed with the reference's own
+    Frame / PointFeat / LineFeat / Point / LineSeg objects, with the C ABI answered by the CPU oracle (oracle/abi_on_oracle.cpp,
+    test infrastructure): what comes back in those objects must be what the reference's own sparse_img_align.cpp /
+    pose_optimizer.cpp leave in them.  (The GPU run of the same harness is tests/test_gpu_shim.py.)"""
+    if not ref.build_shimref_cpu():
+        pytest.skip("needs /root/reference")
+    d = synth.make_align_batch(cam=synth.QVGA, batch=8, n_pts=120, n_segs=30, seed=120)
+    d.seg_valid = np.ones((8, 30), np.uint8)
+    d.seg_valid[:, ::5] = 0
+    d.pt_valid = np.ones((8, 120), np.uint8)
+    d.pt_valid[:, ::9] = 0
+    got = ref.shimref_align(abi, d, cpu=True)
+    want = ref.ref_align(abi, d)
+    np.testing.assert_array_equal(got.n_tracked, want.n_tracked)
+    np.testing.assert_array_equal(got.seg_killed, want.seg_killed)
+    # poses make one extra trip through SE3's quaternion normalisation on the way in and out: last-bit differences only
+    np.testing.assert_allclose(got.T_cur_w, want.T_cur_w, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(got.H * (5e-4 * 255 * 255), want.H, rtol=1e-9, atol=1e-9 * np.abs(want.H).max())
+    pd = synth.make_poseopt_batch(batch=8, n_pts=100, n_segs=30, seed=121)
+    for n_ref in (-1, 3):
+        p = abi.poseopt_params(2.0, 10, n_ref)
+        got, want = ref.shimref_poseopt(abi, pd, p, cpu=True), ref.ref_poseopt(abi, pd, p)
+        for f in ("num_obs_pt", "num_obs_ls", "pt_outlier", "seg_outlier"):
+            np.testing.assert_array_equal(getattr(got, f), getattr(want, f), err_msg=f)
+        np.testing.assert_allclose(got.T_f_w, want.T_f_w, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(got.cov, want.cov, rtol=1e-9, atol=1e-15)
+        for f in ("estimated_scale", "error_init", "error_final"):
+            np.testing.assert_allclose(getattr(got, f), getattr(want, f), rtol=1e-12, err_msg=f)
