@@ -369,6 +369,11 @@ constexpr int kTraceStride = 64;  // doubles per trace record
 
 struct AlignOptions {
   bool chi2_double = false;  // experiment switch: accumulate chi2 in double (NOT the reference behaviour)
+  // experiment switch (NOT the reference behaviour): form the point-patch normal equations the way the CUDA
+  // kernel does — five in-patch sums (1 = fp32 FMA chain, 2 = double) followed by a rank-2 update with the two
+  // projection-Jacobian rows — while chi2 keeps the reference's sequential float order.  Used by
+  // tools/emulate_kernel_sums.py to measure how often the accept/rollback decision can flip for that reason alone.
+  int h_mode = 0;
 };
 
 struct SparseImgAlign {
@@ -398,6 +403,8 @@ struct SparseImgAlign {
     std::vector<float> ref_patch;
     std::vector<double> jacobian;  // 6 x (N*16), column major
     std::vector<uint8_t> visible;
+    std::vector<float> gdx, gdy;  // experiment (h_mode): float gradients per pixel
+    std::vector<double> xyz;      // experiment (h_mode): X, Y, 1/Z per patch
   } pt_cache_, seg_cache_;
   std::vector<size_t> patch_offset;
 
@@ -438,13 +445,18 @@ struct SparseImgAlign {
       const Vec3 xyz_ref = Vec3{pt_f[3 * i], pt_f[3 * i + 1], pt_f[3 * i + 2]} * depth;
       double frame_jac[2][6];
       jacobian_xyz2uv(xyz_ref, frame_jac);
+      if (opt.h_mode) {
+        pt_cache_.gdx.resize((size_t)n_pts * 16), pt_cache_.gdy.resize((size_t)n_pts * 16), pt_cache_.xyz.resize((size_t)n_pts * 3);
+        pt_cache_.xyz[3 * i] = xyz_ref.x, pt_cache_.xyz[3 * i + 1] = xyz_ref.y, pt_cache_.xyz[3 * i + 2] = 1. / xyz_ref.z;
+      }
       fill_patch(patch, &pt_cache_.ref_patch[(size_t)16 * i], &pt_cache_.jacobian[(size_t)6 * 16 * i], frame_jac,
-                 focal_length);
+                 focal_length, opt.h_mode ? &pt_cache_.gdx[(size_t)16 * i] : nullptr,
+                 opt.h_mode ? &pt_cache_.gdy[(size_t)16 * i] : nullptr);
     }
   }
   // the 16-pixel body shared by :243-264 and :354-375
   void fill_patch(const Patch& patch, float* cache_ptr, double* jac_cols, const double frame_jac[2][6],
-                  double focal_length) const {
+                  double focal_length, float* gdx = nullptr, float* gdy = nullptr) const {
     const int stride = patch.img.stride;
     const double jscale = focal_length / (1 << level_);
     for (int y = 0; y < 4; ++y) {
@@ -461,6 +473,7 @@ struct SparseImgAlign {
                            (patch.wTL * img_ptr[-stride] + patch.wTR * img_ptr[1 - stride] + patch.wBL * img_ptr[0] +
                             patch.wBR * img_ptr[1]));
         for (int k = 0; k < 6; ++k) jac_cols[k] = (dx * frame_jac[0][k] + dy * frame_jac[1][k]) * jscale;
+        if (gdx) *gdx++ = dx, *gdy++ = dy;
       }
     }
   }
@@ -544,6 +557,43 @@ struct SparseImgAlign {
       const float* cache_ptr = &pt_cache_.ref_patch[(size_t)16 * i];
       const double* Jc = &pt_cache_.jacobian[(size_t)6 * 16 * i];
       const int stride = patch.img.stride;
+      if (opt.h_mode) {  // experiment: kernel-style normal equations, reference-order chi2
+        float Sf[5] = {0, 0, 0, 0, 0};
+        double Sd[5] = {0, 0, 0, 0, 0};
+        const float* gx = &pt_cache_.gdx[(size_t)16 * i];
+        const float* gy = &pt_cache_.gdy[(size_t)16 * i];
+        for (int y = 0; y < 4; ++y) {
+          const uint8_t* img_ptr = patch.roi + (size_t)y * stride;
+          for (int x = 0; x < 4; ++x, ++img_ptr, ++cache_ptr, ++gx, ++gy) {
+            const float intensity_cur = patch.wTL * img_ptr[0] + patch.wTR * img_ptr[1] + patch.wBL * img_ptr[stride] +
+                                        patch.wBR * img_ptr[stride + 1];
+            const float res = intensity_cur - (*cache_ptr);
+            const float weight = 1.0 / (1.0 + fabsf(res));
+            chi2 += res * res * weight;
+            chi2d += (double)(res * res * weight);
+            n_meas_++;
+            const float wdx = weight * *gx, wdy = weight * *gy;
+            Sf[0] = fmaf(wdx, *gx, Sf[0]), Sf[1] = fmaf(wdx, *gy, Sf[1]), Sf[2] = fmaf(wdy, *gy, Sf[2]);
+            Sf[3] = fmaf(wdx, res, Sf[3]), Sf[4] = fmaf(wdy, res, Sf[4]);
+            const double dwdx = (double)weight * (double)*gx, dwdy = (double)weight * (double)*gy;
+            Sd[0] += dwdx * (double)*gx, Sd[1] += dwdx * (double)*gy, Sd[2] += dwdy * (double)*gy;
+            Sd[3] += dwdx * (double)res, Sd[4] += dwdy * (double)res;
+          }
+        }
+        const double cJ = std::fabs(B->cam.fx) / (1 << level_), cJ2 = cJ * cJ;
+        double S[5];
+        for (int k = 0; k < 5; ++k) S[k] = (opt.h_mode == 1) ? (double)Sf[k] : Sd[k];
+        double fj[2][6];
+        const double X = pt_cache_.xyz[3 * i], Y = pt_cache_.xyz[3 * i + 1], zi = pt_cache_.xyz[3 * i + 2];
+        jacobian_xyz2uv(Vec3{X, Y, 1.0 / zi}, fj);
+        const double Sxx = S[0] * cJ2, Sxy = S[1] * cJ2, Syy = S[2] * cJ2, Sxr = S[3] * cJ, Syr = S[4] * cJ;
+        for (int r = 0; r < 6; ++r) {
+          const double pr = Sxx * fj[0][r] + Sxy * fj[1][r], qr = Sxy * fj[0][r] + Syy * fj[1][r];
+          for (int c = 0; c < 6; ++c) H[r * 6 + c] += pr * fj[0][c] + qr * fj[1][c];
+          Jres[r] -= Sxr * fj[0][r] + Syr * fj[1][r];
+        }
+        continue;
+      }
       for (int y = 0; y < 4; ++y) {
         const uint8_t* img_ptr = patch.roi + (size_t)y * stride;
         for (int x = 0; x < 4; ++x, ++img_ptr, ++cache_ptr, Jc += 6) {
@@ -1026,7 +1076,7 @@ void parallel_for(int n, int n_threads, F f) {
 
 extern "C" {
 
-// flags: bit0 = accumulate chi2 in double (experiment; NOT the reference behaviour)
+// flags: bit0 = accumulate chi2 in double; bits 1-2 = AlignOptions::h_mode (experiments; NOT the reference behaviour)
 int plsvo_oracle_align_batch(const plsvo_align_batch* batch, const plsvo_align_params* params,
                              const plsvo_align_result* out, int n_threads, int flags) {
   if (!batch || !params || !out) return PLSVO_ERR_INVALID;
@@ -1034,6 +1084,7 @@ int plsvo_oracle_align_batch(const plsvo_align_batch* batch, const plsvo_align_p
     return PLSVO_ERR_INVALID;
   AlignOptions opt;
   opt.chi2_double = (flags & 1) != 0;
+  opt.h_mode = (flags >> 1) & 3;  // bits 1-2: kernel-style normal equations (experiment, see AlignOptions)
   parallel_for(batch->batch, n_threads, [&](int b) { align_one(batch, params, out, b, opt, nullptr, 0, nullptr); });
   return PLSVO_OK;
 }

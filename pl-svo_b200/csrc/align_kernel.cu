@@ -2,22 +2,34 @@
 // as ONE persistent sm_100a kernel: a CTA owns a frame pair for its whole coarse-to-fine
 // Gauss-Newton optimisation, so a pair costs no host round trips and no re-launches.
 //
-// Mapping (DESIGN.md §kernels):
+// Mapping (DESIGN.md §4.1):
 //   * work queue: CTAs pull pair indices from an atomic counter (iteration counts vary per pair).
 //   * per level: one thread issues a bulk async copy (TMA engine, cp.async.bulk -> UBLKCP) of the
 //     current image level into shared memory while all threads precompute the reference-patch
 //     cache (4x4 bilinear intensities + central-difference gradients: sparse_img_align.cpp:195-378)
-//     from the reference image in global memory.
-//   * per GN iteration: thread-per-patch residual pass (:380-502 points, :504-695 segment samples):
-//     warp the patch centre with T_cur_from_ref (double), bilinear 4x4 residuals in float with the
-//     reference's exact operation order, five per-patch sums (w*dx*dx, w*dx*dy, w*dy*dy, w*dx*r,
-//     w*dy*r) in double, then a rank-2 update of the thread's 21+6 accumulators using the two
-//     projection-Jacobian rows of the patch (J_px = (dx*row0 + dy*row1)*fx/2^l, :261-262) — this
-//     factorisation replaces the reference's 6x(N*16) double Jacobian cache (768 B/patch) by
-//     128 B/patch of float gradients.  Accumulators are reduced with a register-halving warp
-//     shuffle tree, then across warps through shared memory in fixed order (deterministic).
-//   * thread 0 solves the 6x6 system (pivoted LDLT), applies T <- T*exp(-x) and the vikit
-//     NLLSSolver accept / rollback / convergence logic on chip.
+//     from the reference image in global memory into a per-CTA, L2-resident workspace.
+//   * per GN pass, phase 1 (residuals): thread per patch.  The patch centre is warped in double, the
+//     4x4 residuals, robust weights and chi2 terms are evaluated in float with the reference's exact
+//     operation order (:450-500 points, :612-637 segment samples), and the five in-patch sums
+//     (w*dx*dx, w*dx*dy, w*dy*dy, w*dx*r, w*dy*r) are accumulated per pixel in DOUBLE, as the
+//     reference accumulates every pixel's J*J^T*w in double (:487-492).
+//   * chi2 is reproduced BIT-EXACTLY in the reference's order (float accumulator, points in list
+//     order, pixels row-major, :484; then one term per segment, :683; pt_chi2 + seg_chi2, :171),
+//     because the accept/rollback decision of vk::NLLSSolver (`new_chi2 > chi2_`) compares two such
+//     sums that often agree to ~1e-6.  A sequential float sum is evaluated in parallel as follows:
+//     while the running sum s stays inside one binade, s -> fl(s + t) only depends on the parity of
+//     s's mantissa, so a patch's 16 additions collapse to "add A[parity] ulps"; these maps compose
+//     associatively (segmented warp scan).  Each patch classifies itself from the exact prefix sum of
+//     the patch totals (one block barrier per round of NT patches) with a rigorous error margin:
+//     patches that may cross a power of two keep their 16 terms ("opaque", ~10 per pass) and are
+//     chained serially by one warp together with the composed maps.
+//   * phase 2 (normal equations): J_px = (dx*row0 + dy*row1)*fx/2^l (:261-262) factorises, so
+//     H += [r0 r1] S [r0 r1]^T per patch — a rank-2 update of the thread's 21+6 double accumulators,
+//     replacing the reference's 6x(N*16) double Jacobian cache (768 B/patch) by 128 B/patch of float
+//     gradients.  Reduced with a register-halving warp shuffle tree, then across warps through shared
+//     memory in fixed order (bitwise reproducible run to run).
+//   * thread 0 solves the 6x6 system (LDLT), applies T <- T*exp(-x) and the vikit NLLSSolver
+//     accept / rollback / convergence logic on chip while a second warp chains the chi2 items.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,6 +39,8 @@
 namespace plsvo {
 
 namespace {
+
+constexpr int kOpqCap = 48;  // opaque patches (16 float terms each) per pass; one per binade crossing + margin
 
 struct PairCtl {
   double R[9];
@@ -51,29 +65,38 @@ struct PairCtl {
   unsigned int patch_iters;
   unsigned int patch_levels;
   int iters_level[PLSVO_MAX_LEVELS];
-};
-
-struct PatchSums {  // five fp32 in-patch sums of one pass + how to apply them (0 skip, 1 point, 2+j segment j)
-  float S[5];
-  int kind;
+  float chi2f;     // chi2 of the current pass, summed in the reference's order (walker warp -> thread 0)
+  int n_opq;       // opaque patches of the current pass
+  int chi2_flags;  // sticky per pair: 1 = opaque buffer overflowed (order approximated), 2 = binade check failed
 };
 
 struct Layout {
-  uint32_t ctl, red, tot, seg_alive, seg_N, seg_off, seg_slot, slot_seg, seg_px, seg_scale, prec, pt_vis, xyz, cache, img, total;
+  uint32_t ctl, red, tot, chunk_tot, items, cnt, opq, seg_N, seg_off, seg_slot, slot_seg, seg_scale, seg_term, seg_alive,
+      pt_vis, img, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_patches, int max_seg_patches,
-                                              int img_bytes, bool cache_in_smem) {
+__host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_seg_slots, int img_bytes, int nt) {
   Layout L;
+  const uint32_t nw = (uint32_t)nt / 32u;
+  const uint32_t rounds = ((uint32_t)n_pts + (uint32_t)nt - 1u) / (uint32_t)nt;
+  const uint32_t n_chunks = ((uint32_t)n_pts + 31u) / 32u;
   uint32_t o = 0;
   L.ctl = o;
   o = align_up(o + (uint32_t)sizeof(PairCtl), 16);
   L.red = o;
-  o += 8 * 32 * 8;  // cross-warp partials (up to 8 warps)
+  o += nw * 32u * 8u;  // cross-warp partials
   L.tot = o;
-  o += 32 * 8;
+  o += 32u * 8u;
+  L.chunk_tot = o;
+  o += 8u * (rounds * nw + 1u);  // per 32-patch chunk: float-chi2 total (estimate) of the pass
+  L.items = o;
+  o += 8u * 32u * (n_chunks + 1u);  // composed chi2 maps / opaque references, <= 32 per chunk
+  L.cnt = o;
+  o += 4u * (n_chunks + 1u);
+  L.opq = align_up(o, 16);
+  o = L.opq + 64u * (uint32_t)kOpqCap;
   L.seg_N = o;
   o += 4u * (uint32_t)n_segs;
   L.seg_off = o;
@@ -81,31 +104,21 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_pat
   L.seg_slot = o;
   o += 4u * (uint32_t)n_segs;
   L.slot_seg = o;
-  o += 2u * (2u * (uint32_t)max_seg_patches + 64u);  // lane slot -> segment (groups of 2^k lanes, k per segment)
-  L.seg_px = align_up(o, 16);
-  o = L.seg_px + 16u * (uint32_t)max_seg_patches;  // 2D centre of every segment sample (precompute only)
-  L.seg_scale = o;
-  o += 16u * (uint32_t)n_segs;  // per-segment (weight/res_, weight) of the current pass
-  L.prec = o;
-  o += (uint32_t)sizeof(PatchSums) * (uint32_t)max_patches;  // per-patch sums of the current pass
+  o += 2u * (uint32_t)max_seg_slots;  // lane slot -> segment (groups of 2^k lanes, k per segment)
+  L.seg_scale = align_up(o, 8);
+  o = L.seg_scale + 16u * (uint32_t)n_segs;  // per-segment (weight/res_, weight) of the current pass
+  L.seg_term = o;
+  o += 4u * (uint32_t)n_segs;  // per-segment chi2 term of the current pass (-1: none)
   L.seg_alive = o;
   o += (uint32_t)n_segs;
   L.pt_vis = o;
   o += (uint32_t)n_pts;
-  o = align_up(o, 16);
-  L.xyz = o;
-  o += 4u * 8u * (uint32_t)max_patches;  // X, Y, Z, 1/Z of every patch's 3D point in the ref frame
-  o = align_up(o, 16);
-  L.cache = o;
-  if (cache_in_smem) o += (uint32_t)kCacheRows * 16u * (uint32_t)max_patches;
   o = align_up(o, 128);
   L.img = o;
   o += (uint32_t)img_bytes + 16u;  // slack: the 5-byte row reads fetch whole aligned words
   L.total = o;
   return L;
 }
-
-__device__ __forceinline__ float u8f(uint8_t v) { return (float)v; }
 
 // bilinear sample with the reference's operation order: ((wTL*a + wTR*b) + wBL*c) + wBR*d,
 // every product and sum rounded separately (no FMA contraction) — sparse_img_align.cpp:458
@@ -132,16 +145,22 @@ __device__ __forceinline__ bool patch_setup(double u, double v, int cols, int ro
   return true;
 }
 
-// LineFeat::setupSampling (src/feature.cpp:160-173) followed by the per-level decimation (:320)
+// LineFeat::setupSampling (src/feature.cpp:160-173) followed by the per-level decimation (:320).
+// The sample count is clamped to 2^20 like the host-side sizing (plsvo_abi.cu:host_seg_samples), so a
+// non-finite or absurd length cannot overflow the int conversion.
 __device__ __forceinline__ int seg_num_samples(const double* spx, const double* epx, double length, int level,
                                                double* dif) {
   dif[0] = epx[0] - spx[0];
   dif[1] = epx[1] - spx[1];
   const double a0 = fabs(dif[0]), a1 = fabs(dif[1]);
-  const double tan_dir = fmin(a0, a1) / fmax(a0, a1);
-  const double sin_dir = tan_dir / sqrt(1.0 + tan_dir * tan_dir);
-  const double correction = 2.0 * sqrt(1.0 + sin_dir * sin_dir);
-  const double nd = fmax(1.0, length / (2.0 * 4 * correction));
+  // explicit round-to-nearest operations: the sample count is structural and must equal the reference's
+  // (and the host-side sizing's) value, so nothing here may be contracted into an FMA
+  const double tan_dir = __ddiv_rn(fmin(a0, a1), fmax(a0, a1));
+  const double sin_dir = __ddiv_rn(tan_dir, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(tan_dir, tan_dir))));
+  const double correction = __dmul_rn(2.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(sin_dir, sin_dir))));
+  double nd = __ddiv_rn(length, __dmul_rn(8.0, correction));
+  if (!(nd >= 1.0)) nd = 1.0;  // fmax(1, x) of the reference; also catches NaN
+  if (nd > 1048576.0) nd = 1048576.0;
   const unsigned long long n0 = (unsigned long long)nd;
   return (int)(1 + (n0 - 1) / (unsigned long long)(1 << level));
 }
@@ -151,12 +170,16 @@ __device__ __forceinline__ bool cam_in_frame(int ox, int oy, int boundary, int l
          oy < height / (1 << level) - boundary;
 }
 
-// rank-2 update of the 21 (upper-triangular H) + 6 (Jres) accumulators of one thread:
+// Rank-2 update of the 21 (upper-triangular H) + 6 (Jres) accumulators of one thread for a patch whose 3-D
+// point has normalised coordinates (xn, yn) = (X/Z, Y/Z) and inverse depth zi = 1/Z:
 //   H += Sxx r0 r0^T + Sxy (r0 r1^T + r1 r0^T) + Syy r1 r1^T ,  Jres -= Sxr r0 + Syr r1
-__device__ __forceinline__ void rank2_update(double* acc, double X, double Y, double z_inv, double Sxx, double Sxy,
+// with the rows of Frame::jacobian_xyz2uv (include/plsvo/frame.h:138-160) written in (xn, yn, zi).
+__device__ __forceinline__ void rank2_update(double* acc, double xn, double yn, double zi, double Sxx, double Sxy,
                                              double Syy, double Sxr, double Syr) {
   double r0[6], r1[6];
-  jacobian_rows_zinv(X, Y, z_inv, r0, r1);
+  const double xy = xn * yn;
+  r0[0] = -zi, r0[1] = 0.0, r0[2] = xn * zi, r0[3] = xy, r0[4] = -(1.0 + xn * xn), r0[5] = yn;
+  r1[0] = 0.0, r1[1] = -zi, r1[2] = yn * zi, r1[3] = 1.0 + yn * yn, r1[4] = -xy, r1[5] = -xn;
   double p[6], q[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -172,13 +195,6 @@ __device__ __forceinline__ void rank2_update(double* acc, double X, double Y, do
   for (int i = 0; i < 6; ++i) acc[21 + i] -= Sxr * r0[i] + Syr * r1[i];
 }
 
-// One patch of the residual pass.  WEIGHTED = point patch (:450-500: w = 1/(1+|r|)), otherwise a
-// segment sample (:612-637: unweighted sums, |r| collected).  Returns false if the warped patch
-// is not fully inside the current image (isInFrame(halfsize)).
-// Per-pixel values (bilinear intensity, residual, weight, chi2 term) are bit-identical to the
-// reference's float arithmetic; the five in-patch sums run in fp32 FMAs over the 16 pixels and
-// are widened to double per patch (the reference accumulates every pixel in double: the
-// difference is ~1e-7 relative on one patch's contribution and does not move the fixed point).
 // five consecutive image bytes starting at byte offset (sh/8) of the aligned word pair at `row`
 __device__ __forceinline__ void load_row5(const uint8_t* row, int sh, float* f) {
   const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row);
@@ -206,36 +222,34 @@ __device__ __forceinline__ void load_row7(const uint8_t* row, int sh, float* g) 
   g[6] = byte_to_float(hi, 2);
 }
 
-// One patch of the residual pass.  weighted = point patch (:450-500: w = 1/(1+|r|)); otherwise a segment
-// sample (:612-637: unweighted sums, |r| collected).  One body serves both (w = 1 is exact for the
-// unweighted sums) so that the hot loop stays small enough for the instruction cache.  Returns false
-// if the warped patch is not fully inside the current image (isInFrame(halfsize)).
-// Per-pixel values (bilinear intensity, residual, weight, chi2 term) are bit-identical to the
-// reference's float arithmetic; the five in-patch sums run in fp32 FMAs over the 16 pixels and are
-// widened to double per patch (the reference accumulates every pixel in double: the difference is
-// ~1e-7 relative on one patch's contribution and does not move the fixed point).
+// One patch of the residual pass.  weighted = point patch (:450-500: w = 1/(1+|r|), term = r*r*w); otherwise a
+// segment sample (:612-637: unweighted sums, term = |r|).  Returns false if the warped patch is not fully
+// inside the current image (isInFrame(halfsize)).
+// Per-pixel values (bilinear intensity, residual, weight, chi2 term) are bit-identical to the reference's
+// float arithmetic and are returned in t[16] (row-major, the reference's summation order); the five in-patch
+// sums are accumulated per pixel in double from the exactly widened float operands, as the reference does
+// for every pixel's J*J^T*w (:487-492).  PLSVO_FP32_SUMS builds the fp32-FMA variant for the A/B in
+// profiles/ (0.4 % of pairs then terminate differently from the reference; tools/emulate_kernel_sums.py).
 template <bool weighted>
 __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
-                                           const float4* cache, int MP, int p, double u, double v,
-                                           float* S /*[5]*/, float& acc_out) {
+                                           const float4* __restrict__ cache, int MP, int p, double u, double v,
+                                           double* S /*[5]*/, float* t /*[16]*/) {
   int ui, vi;
   float wTL, wTR, wBL, wBR;
   if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
-  // 5x5 footprint, streamed row by row (two aligned 32-bit loads + funnel shift per row; rows are
-  // 16B-pitched).  The row loop is kept rolled.
+  // 5x5 footprint, row by row (two aligned 32-bit loads + funnel shift per row; rows are 4B-pitched).
   const int c0 = ui - 2;
   const int sh = (c0 & 3) * 8;
   const uint8_t* rowp = img + (size_t)(vi - 2) * pitch + (c0 & ~3);
   float ra[5], rb[5];
   load_row5(rowp, sh, ra);
-#ifdef PLSVO_FP64_SUMS
-  double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0;
-#else
+#ifdef PLSVO_FP32_SUMS
   float Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sxr = 0.f, Syr = 0.f;
+#else
+  double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0;
 #endif
-  float acc_f = 0.f;
   const float4* cp = cache + p;
-#pragma unroll 1
+#pragma unroll
   for (int y = 0; y < 4; ++y) {
     rowp += pitch;
     load_row5(rowp, sh, rb);
@@ -252,31 +266,38 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
       const float res = __fsub_rn(cur, refv[x]);
       const float dx = dxv[x], dy = dyv[x];
       const float ares = fabsf(res);
-      const float w = weighted ? weight_rcp(ares) : 1.0f;                        // :479
-      const float term = weighted ? __fmul_rn(__fmul_rn(res, res), w) : ares;   // :484 / :643
-      acc_f = __fadd_rn(acc_f, term);
-#ifdef PLSVO_FP64_SUMS
-      const double wdx = (double)w * (double)dx, wdy = (double)w * (double)dy;
-      Sxx += wdx * (double)dx;
-      Sxy += wdx * (double)dy;
-      Syy += wdy * (double)dy;
-      Sxr += wdx * (double)res;
-      Syr += wdy * (double)res;
-#else
+      const float w = weighted ? weight_rcp(ares) : 1.0f;                          // :479
+      t[y * 4 + x] = weighted ? __fmul_rn(__fmul_rn(res, res), w) : ares;          // :484 / :643
+#ifdef PLSVO_FP32_SUMS
       const float wdx = __fmul_rn(w, dx), wdy = __fmul_rn(w, dy);
       Sxx = fmaf(wdx, dx, Sxx);
       Sxy = fmaf(wdx, dy, Sxy);
       Syy = fmaf(wdy, dy, Syy);
       Sxr = fmaf(wdx, res, Sxr);
       Syr = fmaf(wdy, res, Syr);
+#else
+      const double dxd = (double)dx, dyd = (double)dy, rd = (double)res;
+      const double wdx = weighted ? (double)w * dxd : dxd;  // exact products (24+24 bits)
+      const double wdy = weighted ? (double)w * dyd : dyd;
+      Sxx = fma(wdx, dxd, Sxx);
+      Sxy = fma(wdx, dyd, Sxy);
+      Syy = fma(wdy, dyd, Syy);
+      Sxr = fma(wdx, rd, Sxr);
+      Syr = fma(wdy, rd, Syr);
 #endif
     }
 #pragma unroll
     for (int c = 0; c < 5; ++c) ra[c] = rb[c];
   }
-  S[0] = (float)Sxx, S[1] = (float)Sxy, S[2] = (float)Syy, S[3] = (float)Sxr, S[4] = (float)Syr;
-  acc_out = acc_f;  // chi2 of this patch (points) / sum of |res| (segment sample)
+  S[0] = (double)Sxx, S[1] = (double)Sxy, S[2] = (double)Syy, S[3] = (double)Sxr, S[4] = (double)Syr;
   return true;
+}
+
+// s <- fl(...fl(fl(s + t0) + t1)... + t15): the reference's float accumulator walking one patch
+__device__ __forceinline__ float chain16(float s, const float* t) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s = __fadd_rn(s, t[k]);
+  return s;
 }
 
 // Reference-patch precompute for one patch (:243-264 / :354-375): 16 interpolated intensities and
@@ -331,44 +352,41 @@ __device__ __forceinline__ void zero_gradients(float4* cache, int MP, int p) {
   for (int y = 0; y < 8; ++y) cache[(4 + y) * MP + p] = z;
 }
 
-// Thread 0: one Gauss-Newton step of vk::NLLSSolver::optimizeGaussNewton with SparseImgAlign's
-// solve()/update() (:697-710).  tot = block totals [0..20]=H upper, [21..26]=Jres, [27]=chi2,
-// [28]=n_meas, [29]=patches evaluated.
-__device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level, int n_iter, double eps) {
-  const long long n_meas = (long long)tot[28];
-  ctl->n_meas_last = n_meas;
+// Thread 0, first half of one Gauss-Newton step: solve() of SparseImgAlign (:697-704) on the block totals.
+// tot = [0..20]=H upper, [21..26]=Jres, [28]=n_meas, [29]=patches evaluated.
+__device__ __noinline__ void gn_solve(PairCtl* ctl, const double* tot, int level) {
+  ctl->n_meas_last = (long long)tot[28];
   ctl->patch_iters += (unsigned int)tot[29];
   ctl->iters_level[level] += 1;
-  // chi2/n_meas_ : float / size_t -> float (:192)
-  const double new_chi2 = (double)((float)tot[27] / (float)(unsigned long long)n_meas);
-  {
-    double Hu[21], gg[6], xx[6];
+  double Hu[21], gg[6], xx[6];
 #pragma unroll
-    for (int i = 0; i < 21; ++i) Hu[i] = tot[i];
+  for (int i = 0; i < 21; ++i) Hu[i] = tot[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) gg[i] = tot[21 + i];
-#ifdef PLSVO_PIVOT_ALWAYS
-    if (false) {
-#else
-    if (ldlt6_reg(Hu, gg, xx)) {
-#endif
+  for (int i = 0; i < 6; ++i) gg[i] = tot[21 + i];
+  if (ldlt6_reg(Hu, gg, xx)) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) ctl->x[i] = xx[i];
-    } else {
-      // degenerate system: pivoted Eigen-style routine on the full symmetric matrix
-      double* H = ctl->H_last;
-      int idx = 0;
-      for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) {
-          H[i * 6 + j] = tot[idx];
-          H[j * 6 + i] = tot[idx];
-          ++idx;
-        }
-      for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
-      ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
-    }
+    for (int i = 0; i < 6; ++i) ctl->x[i] = xx[i];
+  } else {
+    // degenerate system: pivoted Eigen-style routine on the full symmetric matrix
+    double* H = ctl->H_last;
+    int idx = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) {
+        H[i * 6 + j] = tot[idx];
+        H[j * 6 + i] = tot[idx];
+        ++idx;
+      }
+    for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
+    ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
   }
   if (isnan(ctl->x[0])) ctl->stop = 1;
+}
+
+// Thread 0, second half: vk::NLLSSolver::optimizeGaussNewton's accept / rollback / convergence logic with
+// SparseImgAlign::update (:706-710).  chi2f is the pass's chi2 in the reference's summation order.
+__device__ __noinline__ void gn_decide(PairCtl* ctl, const double* tot, float chi2f, int n_iter, double eps) {
+  // chi2/n_meas_ : float / size_t -> float (:192)
+  const double new_chi2 = (double)(chi2f / (float)(unsigned long long)ctl->n_meas_last);
   const bool reject = (ctl->iter > 0 && new_chi2 > ctl->chi2_prev) || ctl->stop;
   int flag;
   if (reject) {
@@ -408,35 +426,50 @@ __device__ __noinline__ void gn_step(PairCtl* ctl, const double* tot, int level,
   ctl->flag = flag;
 }
 
-template <bool CACHE_SMEM, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const AlignArgs a) {
-  constexpr int kAlignThreads = NT;
-  constexpr int kAlignWarps = NT / 32;
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- chi2 items (shared memory, 8 bytes): x = A_even (ulps added when the running sum's mantissa is even),
+// y = [15:0] A_odd - A_even (signed) | [23:16] biased float exponent of the binade | [24] opaque | [31:25] opaque slot
+__device__ __forceinline__ uint2 make_item(uint32_t Ae, uint32_t Ao, uint32_t ef, uint32_t opaque, uint32_t slot) {
+  uint2 it;
+  it.x = Ae;
+  it.y = ((Ao - Ae) & 0xffffu) | (ef << 16) | (opaque << 24) | (slot << 25);
+  return it;
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignArgs a) {
+  constexpr int NW = NT / 32;
+  constexpr int WALK = NW > 1 ? 1 : 0;  // warp that chains the chi2 items while thread 0 solves
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int MP = a.max_patches;
-  const Layout L = make_layout(a.n_pts, a.n_segs, MP, a.max_seg_patches, a.smem_img_bytes, CACHE_SMEM);
+  const Layout L = make_layout(a.n_pts, a.n_segs, a.max_seg_slots, a.smem_img_bytes, NT);
   PairCtl* ctl = reinterpret_cast<PairCtl*>(smem + L.ctl);
   double* red = reinterpret_cast<double*>(smem + L.red);
   double* tot = reinterpret_cast<double*>(smem + L.tot);
+  double* chunk_tot = reinterpret_cast<double*>(smem + L.chunk_tot);
+  uint2* items = reinterpret_cast<uint2*>(smem + L.items);
+  int* item_cnt = reinterpret_cast<int*>(smem + L.cnt);
+  float* opq = reinterpret_cast<float*>(smem + L.opq);
   uint8_t* seg_alive = smem + L.seg_alive;
   int* seg_N = reinterpret_cast<int*>(smem + L.seg_N);
   int* seg_off = reinterpret_cast<int*>(smem + L.seg_off);
   int* seg_slot = reinterpret_cast<int*>(smem + L.seg_slot);
   uint16_t* slot_seg = reinterpret_cast<uint16_t*>(smem + L.slot_seg);
-  const int max_slots = 2 * a.max_seg_patches + 64;
-  double* seg_px = reinterpret_cast<double*>(smem + L.seg_px);
+  const int max_slots = a.max_seg_slots;  // multiple of 32
   double* seg_scale = reinterpret_cast<double*>(smem + L.seg_scale);
-  PatchSums* prec = reinterpret_cast<PatchSums*>(smem + L.prec);
+  float* seg_term = reinterpret_cast<float*>(smem + L.seg_term);
   uint8_t* pt_vis = smem + L.pt_vis;
   uint8_t* img_s = smem + L.img;
-  double* xyz = reinterpret_cast<double*>(smem + L.xyz);
-  float4* cache;
-  if (CACHE_SMEM) {
-    cache = reinterpret_cast<float4*>(smem + L.cache);
-  } else {
-    cache = a.ws_cache + (size_t)blockIdx.x * kCacheRows * MP;
-  }
+  // per-CTA workspaces in global memory (L2 resident)
+  float4* cache = a.ws_cache + (size_t)blockIdx.x * kCacheRows * MP;
+  double* xyz = a.ws_xyz + (size_t)blockIdx.x * 3 * MP;              // xn, yn, 1/Z of every patch's 3-D point
+  double* seg_px = a.ws_segpx + (size_t)blockIdx.x * 2 * a.max_seg_patches;  // 2-D centre of every segment sample
+  const int RS = a.rec_cap * NT;                                     // record slots per component
+  double* rec = a.ws_rec + (size_t)blockIdx.x * 5 * RS;               // five in-patch sums of this pass, per thread slot
   uint64_t* bar = reinterpret_cast<uint64_t*>(&ctl->mbar);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -463,8 +496,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
     const int b = ctl->pair;
     if (b >= a.B) break;
 
-    const int np = a.pt_count ? a.pt_count[b] : a.n_pts;
-    const int ns = a.seg_count ? a.seg_count[b] : a.n_segs;
+    // feature counts are validated on upload; the clamp keeps a corrupted count from indexing out of bounds
+    const int np = min(max(a.pt_count ? a.pt_count[b] : a.n_pts, 0), a.n_pts);
+    const int ns = min(max(a.seg_count ? a.seg_count[b] : a.n_segs, 0), a.n_segs);
     const size_t po = (size_t)b * a.n_pts, so = (size_t)b * a.n_segs;
 
     if (np == 0 && ns == 0) {  // :58-62 early-out: return 0, cur pose untouched
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         a.out_patch_iters[b] = 0;
         a.out_patch_levels[b] = 0;
       }
-      for (int j = tid; j < a.n_segs; j += kAlignThreads) a.out_seg_killed[so + j] = 0;
+      for (int j = tid; j < a.n_segs; j += NT) a.out_seg_killed[so + j] = 0;
       continue;
     }
 
@@ -496,27 +530,30 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       ctl->n_meas_last = 0;
       ctl->patch_iters = 0;
       ctl->patch_levels = 0;
+      ctl->chi2_flags = 0;
+      ctl->n_opq = 0;
       for (int i = 0; i < 36; ++i) ctl->H_last[i] = 0.0;
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) ctl->iters_level[l] = 0;
     }
     __syncthreads();
     const double rpx = ctl->ref_pos[0], rpy = ctl->ref_pos[1], rpz = ctl->ref_pos[2];
 
-    // per-pair point setup: xyz_ref = f * |pos - ref_pos|  (:229-230), visibility cleared
-    for (int i = tid; i < np; i += kAlignThreads) {
+    // per-pair point setup: xyz_ref = f * |pos - ref_pos| (:229-230), kept as (X/Z, Y/Z, 1/Z); visibility cleared
+    for (int i = tid; i < np; i += NT) {
       pt_vis[i] = 0;
       const double* pos = a.pt_pos + (po + i) * 3;
       const double* f = a.pt_f + (po + i) * 3;
       const double dx = pos[0] - rpx, dy = pos[1] - rpy, dz = pos[2] - rpz;
       const double depth = sqrt(dx * dx + dy * dy + dz * dz);
-      const double Zr = f[2] * depth;
-      xyz[0 * MP + i] = f[0] * depth;
-      xyz[1 * MP + i] = f[1] * depth;
-      xyz[2 * MP + i] = Zr;
-      xyz[3 * MP + i] = 1. / Zr;  // z_inv of Frame::jacobian_xyz2uv (frame.h:144), constant per pair
+      const double zi = 1.0 / (f[2] * depth);  // z_inv of Frame::jacobian_xyz2uv (frame.h:144), constant per pair
+      xyz[0 * MP + i] = (f[0] * depth) * zi;
+      xyz[1 * MP + i] = (f[1] * depth) * zi;
+      xyz[2 * MP + i] = zi;
     }
-    for (int j = tid; j < ns; j += kAlignThreads) seg_alive[j] = a.seg_valid ? (a.seg_valid[so + j] ? 1 : 0) : 1;
+    for (int j = tid; j < ns; j += NT) seg_alive[j] = a.seg_valid ? (a.seg_valid[so + j] ? 1 : 0) : 1;
     unsigned int my_patch_levels = 0;
+    const int n_chunks = (np + 31) >> 5;       // 32-patch chunks of the point list
+    const int rounds = (np + NT - 1) / NT;     // rounds of NT point patches per pass
 
     for (int level = a.max_level; level >= a.min_level; --level) {
       const int cols = a.width >> level, rows = a.height >> level;
@@ -539,7 +576,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         for (int i = 0; i < 7; ++i) ctl->old_model[i] = ctl->model[i];
       }
       // ---- segment sampling at this level (:285-332) ----
-      for (int j = tid; j < ns; j += kAlignThreads) {
+      for (int j = tid; j < ns; j += NT) {
         int N = 0;
         if (seg_alive[j]) {
           const double* spx = a.seg_spx + (so + j) * 2;
@@ -552,8 +589,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
           }
         }
         seg_N[j] = N;
+        seg_term[j] = -1.f;
       }
-      for (int q = tid; q < max_slots; q += kAlignThreads) slot_seg[q] = 0xffffu;
+      for (int q = tid; q < max_slots; q += NT) slot_seg[q] = 0xffffu;
       __syncthreads();
       if (warp == 0) {  // exclusive scan of seg_N -> seg_off (cache offsets in patches, :282-292) + lane groups
         int carry = 0;
@@ -597,9 +635,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       __syncthreads();
       const int n_sp = min(ctl->n_seg_patches, a.max_seg_patches);
       const int n_patches = np + n_sp;
-      const int n_seg_slots = min((ctl->n_seg_slots + 31) & ~31, max_slots & ~31);
+      const int n_seg_slots = min((ctl->n_seg_slots + 31) & ~31, max_slots);
       // ---- expand segments into sample patches: 2D centre and 3D point by repeated addition (:323-335) ----
-      for (int j = tid; j < ns; j += kAlignThreads) {
+      for (int j = tid; j < ns; j += NT) {
         const int N = seg_N[j];
         if (N == 0) continue;
         const double* spx = a.seg_spx + (so + j) * 2;
@@ -634,10 +672,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
           if (sp_idx < n_sp) {
             seg_px[2 * sp_idx] = px0;
             seg_px[2 * sp_idx + 1] = px1;
-            xyz[0 * MP + np + sp_idx] = X;
-            xyz[1 * MP + np + sp_idx] = Y;
-            xyz[2 * MP + np + sp_idx] = Z;
-            xyz[3 * MP + np + sp_idx] = 1. / Z;
+            const double zi = 1.0 / Z;
+            xyz[0 * MP + np + sp_idx] = X * zi;
+            xyz[1 * MP + np + sp_idx] = Y * zi;
+            xyz[2 * MP + np + sp_idx] = zi;
           }
           px0 += inc2d0, px1 += inc2d1;
           X += i0, Y += i1, Z += i2;
@@ -645,7 +683,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       }
       __syncthreads();
       // ---- reference patch cache (:195-378) ----
-      for (int p = tid; p < n_patches; p += kAlignThreads) {
+      for (int p = tid; p < n_patches; p += NT) {
         double u, v;
         const bool is_pt = p < np;
         if (is_pt) {
@@ -681,79 +719,190 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         const double R0 = ctl->R[0], R1 = ctl->R[1], R2 = ctl->R[2], R3 = ctl->R[3], R4 = ctl->R[4], R5 = ctl->R[5],
                      R6 = ctl->R[6], R7 = ctl->R[7], R8 = ctl->R[8];
         const double t0 = ctl->t[0], t1 = ctl->t[1], t2 = ctl->t[2];
-        double chi2_acc = 0.0;
         int n_meas_acc = 0, n_patch_acc = 0;
-        // ======== phase 1: residuals.  Each thread evaluates its patches and leaves five fp32 sums per
-        // patch in shared memory; the 27 double accumulators are not live here, which keeps the pixel
-        // loop free of register spills. ========
-        // ---- point patches (:380-502): thread per patch ----
-        for (int p = tid; p < np; p += kAlignThreads) {
-          int kind = 0;
-          if (pt_vis[p]) {
-            const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
-            const double xc = R0 * X + R1 * Y + R2 * Z + t0;
-            const double yc = R3 * X + R4 * Y + R5 * Z + t1;
-            const double zc = R6 * X + R7 * Y + R8 * Z + t2;
+#ifdef PLSVO_TREE_CHI2
+        double chi2_tree = 0.0;
+#endif
+        unsigned long long rec_ok = 0ull;  // bit k: this thread's k-th record of the pass holds sums
+        int n_rec = 0;
+        double prefix_rounds = 0.0;        // estimate of the float chi2 accumulator after all earlier rounds
+        // ======== phase 1a: point patches (:380-502), one round of NT consecutive patches at a time ========
+        for (int r = 0; r < rounds; ++r) {
+          const int c = r * NW + warp;  // 32-patch chunk of this warp: patches [32c, 32c+32) in list order
+          const int p = c * 32 + lane;
+          float t[16];
+          bool ok = false;
+          if (p < np && pt_vis[p]) {
+            const double xn = xyz[0 * MP + p], yn = xyz[1 * MP + p], zi = xyz[2 * MP + p];
+            const double xc = R0 * xn + R1 * yn + (R2 + t0 * zi);  // (R*xyz_ref + t) / Z_ref
+            const double yc = R3 * xn + R4 * yn + (R5 + t1 * zi);
+            const double zc = R6 * xn + R7 * yn + (R8 + t2 * zi);
             const double izc = 1.0 / zc;
             const double u = (a.fx * (xc * izc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
             const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-            float S[5], aux;
-            if (eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) {
-              kind = 1;
+            double S[5];
+            ok = eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, t);
+            if (ok && n_rec >= a.rec_cap) ok = false, atomicOr(&ctl->chi2_flags, 4);  // host plan violated (never)
+            if (ok) {
+              double* rp = rec + n_rec * NT + tid;
 #pragma unroll
-              for (int k = 0; k < 5; ++k) prec[p].S[k] = S[k];
-              chi2_acc += (double)aux;
+              for (int k = 0; k < 5; ++k) rp[k * RS] = S[k];
+              rec_ok |= 1ull << n_rec;
               n_meas_acc += 16;
               n_patch_acc += 1;
             }
           }
-          prec[p].kind = kind;
+          ++n_rec;
+          if (!ok) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) t[k] = 0.f;
+          }
+#ifdef PLSVO_TREE_CHI2
+          chi2_tree += (double)chain16(0.f, t);
+#else
+          // -- estimate of the accumulator before this patch: exact prefix sum of the patch totals --
+          const float Tf = chain16(0.f, t);
+          double incl = (double)Tf;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const double n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          if (lane == 31) chunk_tot[c] = incl;
+          __syncthreads();
+          double P = prefix_rounds;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            const double tw = chunk_tot[r * NW + w];
+            if (w < warp) P += tw;
+            prefix_rounds += tw;
+          }
+          P += incl - (double)Tf;
+          if (c < n_chunks) {
+            // -- classify: the float accumulator s_in before this patch satisfies |s_in - P| <= delta*P and the one
+            // after it |s_out - (P+T)| <= delta*(P+T), delta = (#terms so far)*2^-24 (+ the estimate's own error) --
+            const double delta = (double)(16 * (p + 2)) * 6.0e-8 + 2.0e-6;
+            const double lo = P * (1.0 - delta), hi = (P + (double)Tf) * (1.0 + delta);
+            const int e_lo = (__double2hiint(lo) >> 20) - 1023, e_hi = (__double2hiint(hi) >> 20) - 1023;
+            uint32_t ef = 0, opaque = 0, Ae = 0, Ao = 0, slot = 0;
+            if (P == 0.0) {
+              opaque = (Tf != 0.f) ? 1u : 0u;  // leading zeros leave the accumulator at 0
+            } else if (e_lo != e_hi || e_lo < -100 || e_lo > 100) {
+              opaque = 1u;
+            } else {
+              // inside binade e: the 16 additions add A[parity of s_in's mantissa] ulps
+              ef = (uint32_t)(e_lo + 127);
+              const uint32_t b0 = ef << 23;
+              const float s0 = chain16(__uint_as_float(b0), t), s1 = chain16(__uint_as_float(b0 | 1u), t);
+              Ae = __float_as_uint(s0) - b0;
+              Ao = __float_as_uint(s1) - (b0 | 1u);
+            }
+            if (opaque) {
+              const int idx = atomicAdd(&ctl->n_opq, 1);
+              if (idx < kOpqCap) {
+                slot = (uint32_t)idx;
+                float4* o4 = reinterpret_cast<float4*>(opq + idx * 16);
+                o4[0] = make_float4(t[0], t[1], t[2], t[3]);
+                o4[1] = make_float4(t[4], t[5], t[6], t[7]);
+                o4[2] = make_float4(t[8], t[9], t[10], t[11]);
+                o4[3] = make_float4(t[12], t[13], t[14], t[15]);
+              } else {
+                atomicOr(&ctl->chi2_flags, 1);
+                opaque = 0u;  // dropped from the exact chain; the walker falls back to the estimate
+              }
+            }
+            // -- compose the maps of consecutive patches of the same binade (segmented inclusive scan) --
+            const uint32_t ef_prev = __shfl_up_sync(0xffffffffu, ef, 1);
+            const uint32_t op_prev = __shfl_up_sync(0xffffffffu, opaque, 1);
+            uint32_t head = (lane == 0 || opaque || op_prev || ef != ef_prev) ? 1u : 0u;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const uint32_t pAe = __shfl_up_sync(0xffffffffu, Ae, d);
+              const uint32_t pAo = __shfl_up_sync(0xffffffffu, Ao, d);
+              const uint32_t phead = __shfl_up_sync(0xffffffffu, head, d);
+              if (lane >= d && !head) {
+                // earlier map first: parity p -> p ^ (A_prev[p] & 1), then this lane's map
+                const uint32_t nAe = pAe + ((pAe & 1u) ? Ao : Ae);
+                const uint32_t nAo = pAo + ((pAo & 1u) ? Ae : Ao);
+                Ae = nAe, Ao = nAo;
+                head = phead;
+              }
+            }
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            const uint32_t tails = __ballot_sync(0xffffffffu, tail);
+            if (tail) items[c * 32 + __popc(tails & ((1u << lane) - 1u))] = make_item(Ae, Ao, ef, opaque, slot);
+            if (lane == 0) item_cnt[c] = __popc(tails);
+          }
+#endif
         }
-        // ---- segment samples (:504-695): every segment owns a group of G = 2^gshift consecutive lanes
-        // of one warp (G >= its sample count, or the whole warp looping over samples), so the
-        // per-segment gate/weight (:640-688) is a few shuffles: no block barrier.
-        // Warps take segment rounds from the top so they interleave with the point rounds.
-        for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
+        // ======== phase 1b: segment samples (:504-695).  Every segment owns a group of G = 2^k consecutive lanes
+        // of one warp (G >= its sample count, or the whole warp looping over samples), so the per-segment
+        // gate / weight (:640-688) is a few shuffles: no block barrier.  Warps take segment rounds from the top
+        // so they interleave with the point rounds. ========
+        for (int base = (NW - 1 - warp) * 32; base < n_seg_slots; base += NT) {
           const int q = base + lane;
           const int j = slot_seg[q];
-          const bool seg_ok = (j < ns) && seg_alive[j];
-          const int N = seg_ok ? seg_N[j] : 0;
-          const int off = seg_ok ? seg_off[j] : 0;
-          const int n0 = seg_ok ? q - seg_slot[j] : 0;
+          const bool has = j < ns;
+          const bool seg_ok = has && seg_alive[j];
+          const int Ns = has ? seg_N[j] : 0;  // lane-group structure of the level (fixed for all its passes)
+          const int N = seg_ok ? Ns : 0;      // samples to evaluate in this pass
+          const int off = has ? seg_off[j] : 0;
+          const int n0 = has ? q - seg_slot[j] : 0;
           int G = 1;
-          while (G < N && G < 32) G <<= 1;
-          float my_abs = 0.f;
-          int first_bad = 0x7fffffff;
-          for (int n = n0; n < N; n += G) {  // one trip unless a segment has more samples than a warp
-            const int p = np + off + n;
-            const double X = xyz[0 * MP + p], Y = xyz[1 * MP + p], Z = xyz[2 * MP + p];
-            const double xc = R0 * X + R1 * Y + R2 * Z + t0;
-            const double yc = R3 * X + R4 * Y + R5 * Z + t1;
-            const double zc = R6 * X + R7 * Y + R8 * Z + t2;
-            const double izc = 1.0 / zc;
-            const double u = (a.fx * (xc * izc) + a.cx) * dscale;
-            const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-            float S[5], aux;
-            if (eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, aux)) {
-              my_abs = __fadd_rn(my_abs, aux);
-#pragma unroll
-              for (int k = 0; k < 5; ++k) prec[p].S[k] = S[k];
-              prec[p].kind = 2 + j;
-            } else {
-              first_bad = min(first_bad, n);
-              prec[p].kind = 0;
-            }
-          }
-          // group reductions (xor tree inside the group: partners at distance d < G stay in the group)
-          float res_ = my_abs;
+          while (G < Ns && G < 32) G <<= 1;
+          const int gbase = lane - n0;  // first lane of this lane's group
+          int trips = (Ns + G - 1) / G, gmax = seg_ok ? G : 0;
 #pragma unroll
           for (int d = 16; d >= 1; d >>= 1) {
-            const float o = __shfl_xor_sync(0xffffffffu, res_, d);
-            const int fb = __shfl_xor_sync(0xffffffffu, first_bad, d);
-            if (d < G) {
-              res_ = __fadd_rn(res_, o);
-              first_bad = min(first_bad, fb);
+            trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, d));
+            gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, d));
+          }
+          float s_tok = 0.f;  // the reference's res_ accumulator (:643-646) handed from sample to sample
+          int first_bad = 0x7fffffff;
+          for (int trip = 0; trip < trips; ++trip) {
+            const int n = n0 + trip * G;
+            const bool active = n < N;
+            float t[16];
+            bool ok = false;
+            if (active) {
+              const int p = np + off + n;
+              const double xn = xyz[0 * MP + p], yn = xyz[1 * MP + p], zi = xyz[2 * MP + p];
+              const double xc = R0 * xn + R1 * yn + (R2 + t0 * zi);
+              const double yc = R3 * xn + R4 * yn + (R5 + t1 * zi);
+              const double zc = R6 * xn + R7 * yn + (R8 + t2 * zi);
+              const double izc = 1.0 / zc;
+              const double u = (a.fx * (xc * izc) + a.cx) * dscale;
+              const double v = (a.fy * (yc * izc) + a.cy) * dscale;
+              double S[5];
+              ok = eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, t);
+              if (ok && n_rec >= a.rec_cap) ok = false, atomicOr(&ctl->chi2_flags, 4);
+              if (ok) {
+                double* rp = rec + n_rec * NT + tid;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) rp[k * RS] = S[k];
+                rec_ok |= 1ull << n_rec;
+              } else {
+                first_bad = min(first_bad, n);
+              }
             }
+            ++n_rec;
+            // res_ += fabsf(res) over the samples in order, 16 pixels each (:643-646): the accumulator walks the
+            // group's lanes; a lane without an evaluated sample hands it on unchanged
+            for (int g = 0; g < gmax; ++g) {
+              const float prev = __shfl_sync(0xffffffffu, s_tok, gbase + ((n0 - 1) & (G - 1)));
+              if (n0 == g) {
+                const float s_in = (g == 0 && trip == 0) ? 0.f : prev;
+                s_tok = (active && ok) ? chain16(s_in, t) : s_in;
+              }
+            }
+          }
+          // group results: the accumulator sits on the group's last lane; first failing sample by xor tree
+          float res_ = __shfl_sync(0xffffffffu, s_tok, gbase + G - 1);
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) {
+            const int fb = __shfl_xor_sync(0xffffffffu, first_bad, d);
+            if (d < G) first_bad = min(first_bad, fb);
           }
           if (N == 0 || n0 != 0) continue;  // the group's first lane settles the segment
           const bool good = first_bad >= N;
@@ -763,45 +912,56 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
             const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
             seg_scale[2 * j] = (double)w / (double)res_ * cJ2;    // H += H_*weight/res_ (:681)
             seg_scale[2 * j + 1] = (double)w * cJ;                // Jres += Jres_*weight (:682)
-            chi2_acc += (double)__fmul_rn(__fmul_rn(res_, res_), w);  // :683
-            n_meas_acc += 1;                                         // :684
+            seg_term[j] = __fmul_rn(__fmul_rn(res_, res_), w);    // chi2 += res_*res_*weight (:683)
+#ifdef PLSVO_TREE_CHI2
+            chi2_tree += (double)seg_term[j];
+#endif
+            n_meas_acc += 1;                                      // :684
           } else {
             seg_scale[2 * j] = 0.0;  // rejected: its samples are skipped in phase 2
             seg_scale[2 * j + 1] = 0.0;
+            seg_term[j] = -1.f;
             seg_alive[j] = 0;  // it->feat3D = NULL (:688); the group's lanes have all read it already
           }
         }
-        __syncwarp();  // phase 2 reads back what lanes of this warp wrote (records of own patches, seg_scale)
-        // ======== phase 2: normal equations.  Rank-2 update of this thread's 21+6 accumulators per patch. ========
+        __syncwarp();  // phase 2 reads back what lanes of this warp wrote (seg_scale)
+        // ======== phase 2: normal equations.  Rank-2 update of this thread's 21+6 accumulators per record. ========
         double acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-        for (int p = tid; p < np; p += kAlignThreads) {
-          if (prec[p].kind != 1) continue;
-          const PatchSums ps = prec[p];
-          rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[3 * MP + p], (double)ps.S[0] * cJ2,
-                       (double)ps.S[1] * cJ2, (double)ps.S[2] * cJ2, (double)ps.S[3] * cJ, (double)ps.S[4] * cJ);
+        n_rec = 0;
+        for (int r = 0; r < rounds; ++r, ++n_rec) {
+          if (!((rec_ok >> n_rec) & 1ull)) continue;
+          const int p = (r * NW + warp) * 32 + lane;
+          const double* rp = rec + n_rec * NT + tid;
+          rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], rp[0] * cJ2, rp[RS] * cJ2, rp[2 * RS] * cJ2,
+                       rp[3 * RS] * cJ, rp[4 * RS] * cJ);
         }
-        for (int base = (kAlignWarps - 1 - warp) * 32; base < n_seg_slots; base += kAlignThreads) {
+        for (int base = (NW - 1 - warp) * 32; base < n_seg_slots; base += NT) {
           const int q = base + lane;
           const int j = slot_seg[q];
-          if (j >= ns) continue;
-          const int N = seg_N[j];
-          const double sH = seg_scale[2 * j], sJ = seg_scale[2 * j + 1];
-          if (sH == 0.0 && sJ == 0.0) continue;
+          const bool has = j < ns;
+          const int N = has ? seg_N[j] : 0;
           int G = 1;
           while (G < N && G < 32) G <<= 1;
-          for (int n = q - seg_slot[j]; n < N; n += G) {
-            const int p = np + seg_off[j] + n;
-            if (prec[p].kind != 2 + j) continue;
-            const PatchSums ps = prec[p];
-            rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[3 * MP + p], (double)ps.S[0] * sH, (double)ps.S[1] * sH,
-                         (double)ps.S[2] * sH, (double)ps.S[3] * sJ, (double)ps.S[4] * sJ);
+          int trips = (N + G - 1) / G;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, d));
+          const double sH = has ? seg_scale[2 * j] : 0.0, sJ = has ? seg_scale[2 * j + 1] : 0.0;
+          const int n0 = has ? q - seg_slot[j] : 0;
+          for (int trip = 0; trip < trips; ++trip, ++n_rec) {
+            if (!((rec_ok >> n_rec) & 1ull) || (sH == 0.0 && sJ == 0.0)) continue;
+            const int p = np + seg_off[j] + n0 + trip * G;
+            const double* rp = rec + n_rec * NT + tid;
+            rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], rp[0] * sH, rp[RS] * sH, rp[2 * RS] * sH,
+                         rp[3 * RS] * sJ, rp[4 * RS] * sJ);
           }
         }
-        acc[27] = chi2_acc;
         acc[28] = (double)n_meas_acc;
         acc[29] = (double)n_patch_acc;
+#ifdef PLSVO_TREE_CHI2
+        acc[27] = chi2_tree;  // (variant for the A/B only) chi2 by tree sum, not in the reference's order
+#endif
         // ---- block reduction (deterministic order) ----
         const double mine = warp_reduce32(acc, lane);
         red[warp * 32 + lane] = mine;
@@ -809,11 +969,70 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
         if (warp == 0) {
           double s = 0.0;
 #pragma unroll
-          for (int w = 0; w < kAlignWarps; ++w) s += red[w * 32 + lane];
+          for (int w = 0; w < NW; ++w) s += red[w * 32 + lane];
           tot[lane] = s;
           __syncwarp();
-          if (lane == 0) gn_step(ctl, tot, level, a.n_iter, a.eps);
+          if (lane == 0) gn_solve(ctl, tot, level);
         }
+#ifdef PLSVO_TREE_CHI2
+        if (warp == WALK && lane == 0) ctl->chi2f = 0.f;
+        if (false) {
+#else
+        if (warp == WALK) {
+#endif
+          // ---- chi2 in the reference's order: chain the composed maps and the opaque patches ----
+          float s = 0.f;
+          uint32_t bad = 0;
+          for (int c = 0; c < n_chunks; ++c) {
+            const int cnt = item_cnt[c];
+            uint2 it = make_uint2(0u, 0u);
+            if (lane < cnt) it = items[c * 32 + lane];
+            for (int k = 0; k < cnt; ++k) {
+              const uint32_t ix = __shfl_sync(0xffffffffu, it.x, k), iy = __shfl_sync(0xffffffffu, it.y, k);
+              if ((iy >> 24) & 1u) {
+                const float tv = (lane < 16) ? opq[(iy >> 25) * 16 + lane] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s = __fadd_rn(s, __shfl_sync(0xffffffffu, tv, i));
+              } else {
+                uint32_t bits = __float_as_uint(s);
+                const uint32_t ef = (iy >> 16) & 0xffu;
+                const uint32_t Ao = ix + (uint32_t)(int)(short)(iy & 0xffffu);
+                bad |= (bits >> 23) ^ ef;
+                bits += (bits & 1u) ? Ao : ix;
+                bad |= (bits >> 23) ^ ef;
+                s = __uint_as_float(bits);
+              }
+            }
+          }
+          float s2 = 0.f;  // seg_chi2 (:683): one term per accepted segment, in list order
+          for (int base = 0; base < ns; base += 32) {
+            const float tv = (base + lane < ns && seg_N[base + lane] > 0) ? seg_term[base + lane] : -1.f;
+            const int m = min(32, ns - base);
+            for (int i = 0; i < m; ++i) {
+              const float x = __shfl_sync(0xffffffffu, tv, i);
+              if (x >= 0.f) s2 = __fadd_rn(s2, x);
+            }
+          }
+          if (lane == 0) {
+            if (ctl->n_opq > kOpqCap) {
+              // opaque buffer overflowed (flag 1): fall back to the estimate of the point sum for this pass
+              double e = 0.0;
+              for (int c = 0; c < rounds * NW; ++c) e += chunk_tot[c];
+              s = (float)e;
+            }
+            if (bad) atomicOr(&ctl->chi2_flags, 2);
+            ctl->chi2f = __fadd_rn(s, s2);  // float chi2 = pt_chi2 + seg_chi2 (:171)
+            ctl->n_opq = 0;
+          }
+        }
+        if (NW > 1) {
+          if (warp <= 1) named_barrier_sync(1, 64);  // chi2 (warp 1) -> decision (warp 0)
+        }
+#ifdef PLSVO_TREE_CHI2
+        if (tid == 0) gn_decide(ctl, tot, (float)tot[27], a.n_iter, a.eps);
+#else
+        if (tid == 0) gn_decide(ctl, tot, ctl->chi2f, a.n_iter, a.eps);
+#endif
         __syncthreads();
         if (ctl->flag) break;
       }
@@ -826,7 +1045,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
       if (lane == 0 && v) atomicAdd(&ctl->patch_levels, v);
     }
-    for (int j = tid; j < a.n_segs; j += kAlignThreads) {
+    for (int j = tid; j < a.n_segs; j += NT) {
       const bool valid0 = (j < ns) && (a.seg_valid ? a.seg_valid[so + j] != 0 : true);
       a.out_seg_killed[so + j] = (valid0 && !seg_alive[j]) ? 1 : 0;
     }
@@ -842,7 +1061,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sparse_img_align_kernel(const Al
       a.out_n_tracked[b] = ctl->n_meas_last / 16;  // :94
       for (int i = 0; i < 36; ++i) a.out_H[(size_t)b * 36 + i] = ctl->H_last[i];
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.out_iters[(size_t)b * PLSVO_MAX_LEVELS + l] = ctl->iters_level[l];
-      a.out_status[b] = ctl->stop ? 2 : 0;
+      // status: bit 1 = solver stopped (NaN step); bits 2,3 = chi2 order could not be reproduced exactly (never
+      // seen in practice; kept loud instead of silent)
+      a.out_status[b] = (ctl->stop ? 2 : 0) | (ctl->chi2_flags << 2);
       a.out_patch_iters[b] = ctl->patch_iters;
       a.out_patch_levels[b] = ctl->patch_levels;
     }
@@ -879,55 +1100,46 @@ cudaError_t weight_selftest_launch(uint32_t n, uint32_t seed, unsigned long long
   return cudaGetLastError();
 }
 
-size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_patches, int img_bytes,
-                        bool cache_in_smem) {
-  return make_layout(n_pts, n_segs, max_patches, max_seg_patches, img_bytes, cache_in_smem).total;
+size_t align_smem_bytes(int n_pts, int n_segs, int max_seg_slots, int img_bytes, int threads) {
+  return make_layout(n_pts, n_segs, max_seg_slots, img_bytes, threads).total;
 }
 
+// Kernel variants: CTA size x resident CTAs per SM the register budget is compiled for.  Small CTAs with many
+// resident pairs hide each pair's serial solve and barriers behind the other pairs and let a batch of ~7 pairs per
+// SM run in a single wave; big CTAs cut the latency of a pair when the batch is small.
+#define PLSVO_ALIGN_VARIANTS(X) X(64, 8) X(96, 7) X(96, 5) X(128, 5) X(128, 4) X(256, 2)
+
 namespace {
-template <bool CS, int NT>
+template <int NT, int MINB>
 cudaError_t prepare_t(size_t smem_bytes, int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(sparse_img_align_kernel<CS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(sparse_img_align_kernel<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(sparse_img_align_kernel<CS, NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  e = cudaFuncSetAttribute(sparse_img_align_kernel<NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<CS, NT>, NT, smem_bytes);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sparse_img_align_kernel<NT, MINB>, NT, smem_bytes);
 }
 }  // namespace
 
-cudaError_t align_kernel_prepare(bool cache_in_smem, int threads, size_t smem_bytes, int* ctas_per_sm) {
-  switch (threads) {
-    case 64:
-      return cache_in_smem ? prepare_t<true, 64>(smem_bytes, ctas_per_sm) : prepare_t<false, 64>(smem_bytes, ctas_per_sm);
-    case 128:
-      return cache_in_smem ? prepare_t<true, 128>(smem_bytes, ctas_per_sm) : prepare_t<false, 128>(smem_bytes, ctas_per_sm);
-    case 256:
-      return cache_in_smem ? prepare_t<true, 256>(smem_bytes, ctas_per_sm) : prepare_t<false, 256>(smem_bytes, ctas_per_sm);
-    default:
-      return cudaErrorInvalidValue;
-  }
+cudaError_t align_kernel_prepare(int threads, int min_blocks, size_t smem_bytes, int* ctas_per_sm) {
+#define X(NT, MB) \
+  if (threads == NT && min_blocks == MB) return prepare_t<NT, MB>(smem_bytes, ctas_per_sm);
+  PLSVO_ALIGN_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
-cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, size_t smem_bytes, bool cache_in_smem,
+cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, int min_blocks, size_t smem_bytes,
                                 cudaStream_t s) {
-#define PLSVO_LAUNCH(CS, NT) sparse_img_align_kernel<CS, NT><<<grid, NT, smem_bytes, s>>>(a)
-  switch (threads) {
-    case 64:
-      if (cache_in_smem) PLSVO_LAUNCH(true, 64); else PLSVO_LAUNCH(false, 64);
-      break;
-    case 128:
-      if (cache_in_smem) PLSVO_LAUNCH(true, 128); else PLSVO_LAUNCH(false, 128);
-      break;
-    case 256:
-      if (cache_in_smem) PLSVO_LAUNCH(true, 256); else PLSVO_LAUNCH(false, 256);
-      break;
-    default:
-      return cudaErrorInvalidValue;
+#define X(NT, MB)                                                            \
+  if (threads == NT && min_blocks == MB) {                                   \
+    sparse_img_align_kernel<NT, MB><<<grid, NT, smem_bytes, s>>>(a);         \
+    return cudaGetLastError();                                               \
   }
-#undef PLSVO_LAUNCH
-  return cudaGetLastError();
+  PLSVO_ALIGN_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace plsvo

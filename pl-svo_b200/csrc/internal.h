@@ -55,23 +55,22 @@ struct AlignArgs {
   int gate_chunk;
   int max_patches;      // patch slots per pair: n_pts + max segment samples
   int max_seg_patches;  // segment sample slots per pair
+  int max_seg_slots;    // lane slots of the segment groups per pair (multiple of 32)
   int smem_img_bytes;   // bytes of the image staging buffer
-  float4* ws_cache;     // [grid][kCacheRows][max_patches] when the patch cache lives in global memory
-  double* ws_xyz;       // [grid][3][max_patches]
-};
-
-struct AlignLaunchInfo {
-  int grid;
-  int ctas_per_sm;
-  size_t smem_bytes;
-  bool cache_in_smem;
+  float4* ws_cache;     // [grid][kCacheRows][max_patches] reference-patch cache (ref, dx, dy rows), L2 resident
+  double* ws_xyz;       // [grid][3][max_patches] X/Z, Y/Z, 1/Z of every patch's 3-D point in the reference frame
+  double* ws_segpx;     // [grid][2][max_seg_patches] 2-D centre of every segment sample (precompute only)
+  double* ws_rec;       // [grid][5][rec_cap*threads] in-patch sums of the current pass, one slot per thread and record
+  int rec_cap;          // records per thread and pass (point rounds + segment trips), <= 64
 };
 
 // shared memory the kernel needs for a configuration (host + device agree through this)
-size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_patches, int img_bytes, bool cache_in_smem);
-cudaError_t align_kernel_prepare(bool cache_in_smem, int threads, size_t smem_bytes, int* ctas_per_sm);
+size_t align_smem_bytes(int n_pts, int n_segs, int max_seg_slots, int img_bytes, int threads);
+// kernel variants are compiled per (threads per CTA, resident CTAs per SM the register budget allows):
+// (64,8) (96,7) (96,5) (128,5) (128,4) (256,2)
+cudaError_t align_kernel_prepare(int threads, int min_blocks, size_t smem_bytes, int* ctas_per_sm);
 cudaError_t weight_selftest_launch(uint32_t n, uint32_t seed, unsigned long long* d_mismatch, cudaStream_t s);
-cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, size_t smem_bytes, bool cache_in_smem,
+cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, int min_blocks, size_t smem_bytes,
                                 cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------

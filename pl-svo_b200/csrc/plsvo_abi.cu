@@ -50,10 +50,12 @@ struct plsvo_ctx_impl {
   plsvo_camera cam;
   int a_max_seg_patches_l0 = 0;  // bound at level 0 (levels >= 0 never need more)
   std::vector<int> seg_patch_bound;  // per level: max over pairs of the number of segment samples
+  std::vector<int> seg_slot_bound;   // per level: max over pairs of the lane slots of the segment groups
+  std::vector<int> seg_maxN;         // per level: most samples of any one segment
   DevBuf d_ref_img, d_cur_img, d_T_ref, d_T_cur, d_pt_count, d_pt_px, d_pt_f, d_pt_pos, d_pt_valid, d_seg_count,
       d_seg_spx, d_seg_epx, d_seg_sf, d_seg_ef, d_seg_spos, d_seg_epos, d_seg_length, d_seg_valid;
   DevBuf d_out_T, d_out_ntr, d_out_H, d_out_killed, d_out_iters, d_out_status, d_out_pi, d_out_pl, d_counter,
-      d_ws_cache, d_ws_xyz, d_stage;
+      d_ws_cache, d_ws_xyz, d_ws_segpx, d_ws_rec, d_stage;
   size_t level_off[PLSVO_MAX_LEVELS];
 
   // ---- pose-opt state ----
@@ -190,7 +192,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
-                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_ws_segpx,  &c->d_ws_rec,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
                     &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->m_ref_img,   &c->m_cur_img,   &c->m_T_ref,     &c->m_T_cur,
                     &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
                     &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
@@ -208,13 +210,12 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
     if (c->rr_stream[k]) cudaStreamDestroy(c->rr_stream[k]);
     if (c->rr_ev[k]) cudaEventDestroy(c->rr_ev[k]);
   }
-  if (c->copy_stream) {
-    cudaStreamDestroy(c->copy_stream);
-    for (int k = 0; k < 8; ++k) cudaEventDestroy(c->chunk_ev[k]);
-    cudaEventDestroy(c->start_ev);
-    for (auto& e : c->k_ev)
-      if (e) cudaEventDestroy(e);
-  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int k = 0; k < 8; ++k)
+    if (c->chunk_ev[k]) cudaEventDestroy(c->chunk_ev[k]);
+  if (c->start_ev) cudaEventDestroy(c->start_ev);
+  for (auto& e : c->k_ev)
+    if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -417,18 +418,39 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   }  // mode != 3
   if (mode == 0 || mode == 2) return PLSVO_OK;
 
-  // per-level bound on segment samples per pair (sizes the sample slots; host arrays are still valid here)
+  // per-pair feature counts index shared memory and the feature arrays in the kernels: reject anything outside
+  // [0, n_pts] / [0, n_segs] here (every other index array of the ABI is range-checked on the host as well)
+  for (size_t b = 0; b < B; ++b) {
+    if (h->pt_count && (h->pt_count[b] < 0 || h->pt_count[b] > h->n_pts))
+      return fail(c, PLSVO_ERR_INVALID, "pt_count[b] outside [0, n_pts]");
+    if (h->seg_count && (h->seg_count[b] < 0 || h->seg_count[b] > h->n_segs))
+      return fail(c, PLSVO_ERR_INVALID, "seg_count[b] outside [0, n_segs]");
+  }
+  // per-level bounds on the segment samples of a pair: sample slots, lane slots of the segment groups (a segment
+  // with N samples owns 2^k >= min(N,32) lanes) and the longest segment (host arrays are still valid here)
   c->seg_patch_bound.assign(PLSVO_MAX_LEVELS, 0);
+  c->seg_slot_bound.assign(PLSVO_MAX_LEVELS, 0);
+  c->seg_maxN.assign(PLSVO_MAX_LEVELS, 0);
   if (h->n_segs > 0) {
     for (size_t b = 0; b < B; ++b) {
-      const int nsb = h->seg_count ? std::min(h->seg_count[b], h->n_segs) : h->n_segs;
-      int sum[PLSVO_MAX_LEVELS] = {0};
+      const int nsb = h->seg_count ? h->seg_count[b] : h->n_segs;
+      int sum[PLSVO_MAX_LEVELS] = {0}, slots[PLSVO_MAX_LEVELS] = {0};
       for (int j = 0; j < nsb; ++j) {
         const size_t k = b * h->n_segs + j;
         const int n0 = host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], 0);
-        for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) sum[l] += 1 + ((n0 - 1) >> l);
+        for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+          const int N = 1 + ((n0 - 1) >> l);
+          int g = 1;
+          while (g < N && g < 32) g <<= 1;
+          sum[l] += N;
+          slots[l] += g;
+          c->seg_maxN[l] = std::max(c->seg_maxN[l], N);
+        }
       }
-      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], sum[l]);
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+        c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], sum[l]);
+        c->seg_slot_bound[l] = std::max(c->seg_slot_bound[l], slots[l]);
+      }
     }
   }
   // all outputs live in one device block so that the download is a single D2H into pinned staging
@@ -470,10 +492,12 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
 
 // launch plan of the alignment kernel for the uploaded batch (shared memory, CTA size, grid)
 struct AlignPlan {
-  bool cache_in_smem;
-  int threads, ctas_per_sm;
+  int threads, min_blocks, ctas_per_sm;
   size_t smem;
 };
+
+// kernel variants (threads per CTA, resident CTAs per SM the register budget is compiled for), see align_kernel.cu
+static const int kAlignVariants[][2] = {{128, 4}, {128, 5}, {96, 5}, {96, 7}, {64, 8}, {256, 2}};
 
 int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, AlignPlan* plan) {
   if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_launch before plsvo_align_upload");
@@ -484,62 +508,89 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
     if (!a.pitch[l]) return fail(c, PLSVO_ERR_INVALID, "a pyramid level in [min_level,max_level] was not uploaded");
   CK(cudaSetDevice(c->device));
   a.max_level = p->max_level, a.min_level = p->min_level, a.n_iter = p->n_iter, a.eps = p->eps;
-  a.max_seg_patches = c->seg_patch_bound[p->min_level];
+  a.max_seg_patches = std::max(c->seg_patch_bound[p->min_level], 1);
+  a.max_seg_slots = (c->seg_slot_bound[p->min_level] + 31) / 32 * 32 + 32;
+  if (a.max_seg_slots > 65504) return fail(c, PLSVO_ERR_INVALID, "segment samples exceed the lane-slot plan");
   a.max_patches = (a.n_pts + a.max_seg_patches + 3) / 4 * 4;
   if (a.max_patches == 0) a.max_patches = 4;
+  const int maxN = std::max(c->seg_maxN[p->min_level], 1);
 
-  // shared-memory plan: stage the current image level when it fits; keep the patch cache on chip
-  // when that still leaves room for >= 2 CTAs per SM, otherwise stream it from a per-CTA global
-  // workspace (L2 resident) with coalesced 128-bit loads.
-  const char* mode = getenv("PLSVO_CACHE_MODE");  // "smem" | "global" | unset (= auto)
-  const int limit = c->smem_optin;                // 227 KB on sm_100a
-  // Staging budget: a level is staged only if the CTA still fits 4x (else 2x) per SM next to the
-  // per-pair state; bigger levels are read through L2 with the same aligned-word loads.
-  const int other = (int)align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, 0, false);
-  int img_budget = limit / 4 - other - 1024;
-  if (img_budget < 1024) img_budget = limit / 2 - other - 1024;
-  if (img_budget < 0) img_budget = 0;
-  img_budget = std::min(img_budget, 96 * 1024);
-  int img_bytes = 0;
-  for (int l = p->min_level; l <= p->max_level; ++l) {
-    const size_t bytes = a.stride[l];
-    a.img_in_smem[l] = (bytes <= (size_t)img_budget && bytes < (1u << 20)) ? 1 : 0;
-    if (a.img_in_smem[l]) img_bytes = std::max(img_bytes, (int)bytes);
+  // Kernel variant.  Default: 128-thread CTAs with the register budget of four resident pairs per SM; small
+  // batches (at most one pair per SM) take 256-thread CTAs to cut the latency of a pair.
+  // PLSVO_VARIANT="threads,ctas" selects another compiled variant (tuning / the A-B runs in profiles/).
+  int want_t = 128, want_b = 4;
+  if (chunk_pairs <= c->num_sms) want_t = 256, want_b = 2;
+  if (const char* v = getenv("PLSVO_VARIANT")) {
+    int t = 0, mb = 0;
+    if (sscanf(v, "%d,%d", &t, &mb) == 2) {
+      bool known = false;
+      for (auto& kv : kAlignVariants) known |= (kv[0] == t && kv[1] == mb);
+      if (!known) return fail(c, PLSVO_ERR_INVALID, "PLSVO_VARIANT names a variant that is not compiled");
+      want_t = t, want_b = mb;
+    }
   }
-  a.smem_img_bytes = img_bytes;
-  size_t smem_s = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, img_bytes, true);
-  size_t smem_g = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, img_bytes, false);
-  bool cache_in_smem = smem_s <= (size_t)(limit / 4 - 1024);
-  if (mode && !strcmp(mode, "smem")) cache_in_smem = smem_s <= (size_t)limit;
-  if (mode && !strcmp(mode, "global")) cache_in_smem = false;
-  size_t smem = cache_in_smem ? smem_s : smem_g;
-  if (smem > (size_t)limit) {  // drop image staging as a last resort
+  const int limit = c->smem_optin;  // 227 KB on sm_100a
+  // try the wanted variant first, then bigger CTAs (more patches per round, fewer records per thread)
+  const int order[][2] = {{want_t, want_b}, {128, 4}, {256, 2}};
+  int rc_last = PLSVO_ERR_INVALID;
+  for (auto& v : order) {
+    const int threads = v[0], min_blocks = v[1];
+    // records per thread and pass: point rounds + segment rounds x trips of the longest segment
+    const int rounds = (a.n_pts + threads - 1) / threads;
+    const int seg_rounds = (a.max_seg_slots + threads - 1) / threads;
+    const int rec_cap = std::max(1, rounds + seg_rounds * ((maxN + 31) / 32));
+    if (rec_cap > 64) {
+      rc_last = fail(c, PLSVO_ERR_INVALID, "feature counts exceed the per-thread record plan");
+      continue;
+    }
+    // shared-memory plan: stage the current image level when the CTA still fits min_blocks times per SM next to
+    // the per-pair state; bigger levels are read through L2 with the same aligned-word loads.
+    const int other = (int)align_smem_bytes(a.n_pts, a.n_segs, a.max_seg_slots, 0, threads);
+    int img_budget = (limit + 1024) / min_blocks - 1024 - other;
+    if (img_budget < 0) img_budget = 0;
+    img_budget = std::min(img_budget, 96 * 1024);
+    if (const char* e = getenv("PLSVO_IMG_SMEM")) img_budget = atoi(e) ? 96 * 1024 : 0;
+    int img_bytes = 0;
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.img_in_smem[l] = 0;
-    a.smem_img_bytes = 0;
-    smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_patches, 0, false);
-    cache_in_smem = false;
-    if (smem > (size_t)limit) return fail(c, PLSVO_ERR_INVALID, "feature counts exceed the shared-memory plan");
+    for (int l = p->min_level; l <= p->max_level; ++l) {
+      const size_t bytes = a.stride[l];
+      a.img_in_smem[l] = (bytes <= (size_t)img_budget && bytes < (1u << 20) && bytes % 16 == 0) ? 1 : 0;
+      if (a.img_in_smem[l]) img_bytes = std::max(img_bytes, (int)bytes);
+    }
+    size_t smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_seg_slots, img_bytes, threads);
+    if (smem > (size_t)limit) {  // drop image staging as a last resort
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.img_in_smem[l] = 0;
+      img_bytes = 0;
+      smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_seg_slots, 0, threads);
+      if (smem > (size_t)limit) {
+        rc_last = fail(c, PLSVO_ERR_INVALID, "feature counts exceed the shared-memory plan");
+        continue;
+      }
+    }
+    a.smem_img_bytes = img_bytes;
+    a.rec_cap = rec_cap;
+    int ctas_per_sm = 0;
+    CK(align_kernel_prepare(threads, min_blocks, smem, &ctas_per_sm));
+    if (ctas_per_sm < 1) {
+      rc_last = fail(c, PLSVO_ERR_INVALID, "kernel does not fit on an SM");
+      continue;
+    }
+    const char* cap = getenv("PLSVO_CTAS_PER_SM");
+    if (cap && atoi(cap) > 0) ctas_per_sm = std::min(ctas_per_sm, atoi(cap));
+    // per-CTA workspaces (L2 resident): reference-patch cache, patch geometry, segment sample centres, pass records
+    const size_t grid_max = (size_t)std::min(a.B, c->num_sms * ctas_per_sm);
+    CK(ensure(c->d_ws_cache, grid_max * kCacheRows * a.max_patches * sizeof(float4)));
+    CK(ensure(c->d_ws_xyz, grid_max * 3 * a.max_patches * sizeof(double)));
+    CK(ensure(c->d_ws_segpx, grid_max * 2 * a.max_seg_patches * sizeof(double)));
+    CK(ensure(c->d_ws_rec, grid_max * 5 * (size_t)rec_cap * threads * sizeof(double)));
+    a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
+    a.ws_xyz = static_cast<double*>(c->d_ws_xyz.p);
+    a.ws_segpx = static_cast<double*>(c->d_ws_segpx.p);
+    a.ws_rec = static_cast<double*>(c->d_ws_rec.p);
+    plan->threads = threads, plan->min_blocks = min_blocks, plan->ctas_per_sm = ctas_per_sm, plan->smem = smem;
+    return PLSVO_OK;
   }
-  // CTA size: small CTAs keep more independent frame pairs in flight per SM (each pair's serial
-  // solve / barriers then stall fewer warps) and let the hardware scheduler balance pairs of
-  // different iteration counts; big CTAs cut per-pair latency when the batch is small.
-  int threads = 128;
-  if (chunk_pairs <= c->num_sms) threads = 256;
-  const char* tenv = getenv("PLSVO_THREADS");
-  if (tenv && (atoi(tenv) == 64 || atoi(tenv) == 128 || atoi(tenv) == 256)) threads = atoi(tenv);
-  int ctas_per_sm = 0;
-  CK(align_kernel_prepare(cache_in_smem, threads, smem, &ctas_per_sm));
-  if (ctas_per_sm < 1) return fail(c, PLSVO_ERR_INVALID, "kernel does not fit on an SM");
-  const char* cap = getenv("PLSVO_CTAS_PER_SM");
-  if (cap && atoi(cap) > 0) ctas_per_sm = std::min(ctas_per_sm, atoi(cap));
-  if (!cache_in_smem) {
-    const int grid_max = std::min(a.B, c->num_sms * ctas_per_sm);
-    CK(ensure(c->d_ws_cache, (size_t)grid_max * kCacheRows * a.max_patches * sizeof(float4)));
-  }
-  a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
-  a.ws_xyz = nullptr;
-  plan->cache_in_smem = cache_in_smem, plan->threads = threads, plan->ctas_per_sm = ctas_per_sm, plan->smem = smem;
-  return PLSVO_OK;
+  return rc_last;
 }
 
 // one kernel over pairs [b0,b1) of the uploaded batch (pointers rebased to the chunk)
@@ -585,7 +636,7 @@ int align_launch_range(plsvo_ctx_impl* c, const AlignPlan& plan, size_t b0, size
   a.gate_chunk = gate_chunk;
   const int grid = std::min(a.B, c->num_sms * plan.ctas_per_sm);
   CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), s));
-  CK(align_kernel_launch(a, grid, plan.threads, plan.smem, plan.cache_in_smem, s));
+  CK(align_kernel_launch(a, grid, plan.threads, plan.min_blocks, plan.smem, s));
   c->launches += 1;
   return PLSVO_OK;
 }

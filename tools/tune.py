@@ -1,5 +1,5 @@
-"""One-process tuning sweep over launch configurations (env knobs read at launch time)."""
-import itertools, json, os, sys, time
+"""One-process tuning sweep over the alignment kernel's compiled variants (env knobs read at launch time)."""
+import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np, torch
@@ -14,12 +14,12 @@ ctx = plsvo_b200.Context(0, stream.cuda_stream)
 al = plsvo_b200.SparseImgAlign(4, 2, 30, ctx=ctx)
 al.upload(data)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+KEYS = ("PLSVO_VARIANT", "PLSVO_CTAS_PER_SM", "PLSVO_IMG_SMEM")
 configs = json.loads(os.environ.get("TUNE_CONFIGS", "[]")) or [
-    {"PLSVO_THREADS": t, "PLSVO_CTAS_PER_SM": c, "PLSVO_CACHE_MODE": m}
-    for t in ("64", "128", "256") for c in ("0",) for m in ("global",)]
+    {"PLSVO_VARIANT": v} for v in ("128,4", "128,5", "96,5", "96,7", "64,8", "256,2")]
 base = None
 for cfg in configs:
-    for k in ("PLSVO_THREADS", "PLSVO_CTAS_PER_SM", "PLSVO_CACHE_MODE"):
+    for k in KEYS:
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in cfg.items()})
     try:
@@ -38,6 +38,7 @@ for cfg in configs:
             base = out
         ang, rel = synth.pose_error(out.T_cur_w, base.T_cur_w)
         print(json.dumps({"cfg": cfg, "ms": round(float(np.median(ts)), 4), "pairs_per_s": round(B / (np.median(ts) * 1e-3)),
-                          "vs_first_max_rot": float(ang.max()), "same_iters": float((out.iters == base.iters).all(axis=1).mean())}), flush=True)
+                          "vs_first_max_rot": float(ang.max()), "same_iters": float((out.iters == base.iters).all(axis=1).mean()),
+                          "flags": int((out.status >> 2).astype(bool).sum())}), flush=True)
     except Exception as ex:
         print(json.dumps({"cfg": cfg, "error": str(ex)}), flush=True)
