@@ -36,6 +36,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_variant(tag: str, defines: list[str], verbose: bool = False) -> str:
+    """A/B builds of the library with preprocessor switches (e.g. PLSVO_FP32_SUMS, PLSVO_TREE_CHI2), loaded through
+    PLSVO_LIB; used by the measurements in profiles/, never by the product path."""
+    out = os.path.join(CSRC, f"libplsvo_b200_{tag}.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return out
+
+
 HOST = os.path.join(_HERE, "host")
 SHIM_OUT = os.path.join(HOST, "libplsvo_shim.so")
 SHIM_SOURCES = ["plsvo_shim.cpp", "shim_harness.cpp"]

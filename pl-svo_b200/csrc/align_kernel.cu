@@ -65,19 +65,23 @@ struct PairCtl {
   unsigned int patch_iters;
   unsigned int patch_levels;
   int iters_level[PLSVO_MAX_LEVELS];
+  double cand[7];  // candidate model T*exp(-x) of the current pass and its rotation matrix / step norm
+  double candR[9];
+  double cand_nm;
   float chi2f;     // chi2 of the current pass, summed in the reference's order (walker warp -> thread 0)
   int n_opq;       // opaque patches of the current pass
   int chi2_flags;  // sticky per pair: 1 = opaque buffer overflowed (order approximated), 2 = binade check failed
 };
 
 struct Layout {
-  uint32_t ctl, red, tot, chunk_tot, items, cnt, opq, seg_N, seg_off, seg_slot, slot_seg, seg_scale, seg_term, seg_alive,
-      pt_vis, img, total;
+  uint32_t ctl, red, tot, chunk_tot, items, cnt, flat, opq, seg_N0, seg_N, seg_off, seg_slot, slot_seg, seg_term,
+      seg_alive, pt_vis, xyz, tsc, img, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_seg_slots, int img_bytes, int nt) {
+__host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_patches, int max_seg_slots, int img_bytes,
+                                              int nt) {
   Layout L;
   const uint32_t nw = (uint32_t)nt / 32u;
   const uint32_t rounds = ((uint32_t)n_pts + (uint32_t)nt - 1u) / (uint32_t)nt;
@@ -95,8 +99,12 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_seg
   o += 8u * 32u * (n_chunks + 1u);  // composed chi2 maps / opaque references, <= 32 per chunk
   L.cnt = o;
   o += 4u * (n_chunks + 1u);
+  L.flat = align_up(o, 8);
+  o = L.flat + 8u * 64u;  // the walker's current batch of items, in list order
   L.opq = align_up(o, 16);
   o = L.opq + 64u * (uint32_t)kOpqCap;
+  L.seg_N0 = o;
+  o += 4u * (uint32_t)n_segs;  // samples of every segment at level 0 (setupSampling), once per pair
   L.seg_N = o;
   o += 4u * (uint32_t)n_segs;
   L.seg_off = o;
@@ -105,14 +113,17 @@ __host__ __device__ inline Layout make_layout(int n_pts, int n_segs, int max_seg
   o += 4u * (uint32_t)n_segs;
   L.slot_seg = o;
   o += 2u * (uint32_t)max_seg_slots;  // lane slot -> segment (groups of 2^k lanes, k per segment)
-  L.seg_scale = align_up(o, 8);
-  o = L.seg_scale + 16u * (uint32_t)n_segs;  // per-segment (weight/res_, weight) of the current pass
-  L.seg_term = o;
+  L.seg_term = align_up(o, 4);
+  o = L.seg_term;
   o += 4u * (uint32_t)n_segs;  // per-segment chi2 term of the current pass (-1: none)
   L.seg_alive = o;
   o += (uint32_t)n_segs;
   L.pt_vis = o;
   o += (uint32_t)n_pts;
+  L.xyz = align_up(o, 16);
+  o = L.xyz + 3u * 8u * (uint32_t)max_patches;  // X/Z, Y/Z, 1/Z of every patch's 3-D point in the ref frame
+  L.tsc = o;
+  o += 16u * 4u * (uint32_t)nt;  // the 16 chi2 terms of each thread's current patch ([k][tid]: conflict-free)
   o = align_up(o, 128);
   L.img = o;
   o += (uint32_t)img_bytes + 16u;  // slack: the 5-byte row reads fetch whole aligned words
@@ -148,11 +159,8 @@ __device__ __forceinline__ bool patch_setup(double u, double v, int cols, int ro
 // LineFeat::setupSampling (src/feature.cpp:160-173) followed by the per-level decimation (:320).
 // The sample count is clamped to 2^20 like the host-side sizing (plsvo_abi.cu:host_seg_samples), so a
 // non-finite or absurd length cannot overflow the int conversion.
-__device__ __forceinline__ int seg_num_samples(const double* spx, const double* epx, double length, int level,
-                                               double* dif) {
-  dif[0] = epx[0] - spx[0];
-  dif[1] = epx[1] - spx[1];
-  const double a0 = fabs(dif[0]), a1 = fabs(dif[1]);
+__device__ __noinline__ int seg_num_samples0(const double* spx, const double* epx, double length) {
+  const double a0 = fabs(epx[0] - spx[0]), a1 = fabs(epx[1] - spx[1]);
   // explicit round-to-nearest operations: the sample count is structural and must equal the reference's
   // (and the host-side sizing's) value, so nothing here may be contracted into an FMA
   const double tan_dir = __ddiv_rn(fmin(a0, a1), fmax(a0, a1));
@@ -161,8 +169,7 @@ __device__ __forceinline__ int seg_num_samples(const double* spx, const double* 
   double nd = __ddiv_rn(length, __dmul_rn(8.0, correction));
   if (!(nd >= 1.0)) nd = 1.0;  // fmax(1, x) of the reference; also catches NaN
   if (nd > 1048576.0) nd = 1048576.0;
-  const unsigned long long n0 = (unsigned long long)nd;
-  return (int)(1 + (n0 - 1) / (unsigned long long)(1 << level));
+  return (int)(unsigned long long)nd;  // N_samples at level 0; level l uses 1 + (N0 - 1) / 2^l (:320)
 }
 
 __device__ __forceinline__ bool cam_in_frame(int ox, int oy, int boundary, int level, int width, int height) {
@@ -230,14 +237,15 @@ __device__ __forceinline__ void load_row7(const uint8_t* row, int sh, float* g) 
 // sums are accumulated per pixel in double from the exactly widened float operands, as the reference does
 // for every pixel's J*J^T*w (:487-492).  PLSVO_FP32_SUMS builds the fp32-FMA variant for the A/B in
 // profiles/ (0.4 % of pairs then terminate differently from the reference; tools/emulate_kernel_sums.py).
-template <bool weighted>
+template <bool weighted, int NT>
 __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
                                            const float4* __restrict__ cache, int MP, int p, double u, double v,
-                                           double* S /*[5]*/, float* t /*[16]*/) {
+                                           double* S /*[5]*/, float* __restrict__ tsc, float& tsum) {
   int ui, vi;
   float wTL, wTR, wBL, wBR;
   if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
-  // 5x5 footprint, row by row (two aligned 32-bit loads + funnel shift per row; rows are 4B-pitched).
+  // 5x5 footprint, streamed row by row (two aligned 32-bit loads + funnel shift per row; rows are 4B-pitched).
+  // The row loop is kept rolled: the pass loop must fit the 32 KB instruction cache.
   const int c0 = ui - 2;
   const int sh = (c0 & 3) * 8;
   const uint8_t* rowp = img + (size_t)(vi - 2) * pitch + (c0 & ~3);
@@ -248,8 +256,9 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
 #else
   double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0;
 #endif
+  float acc_f = 0.f;
   const float4* cp = cache + p;
-#pragma unroll
+#pragma unroll 1
   for (int y = 0; y < 4; ++y) {
     rowp += pitch;
     load_row5(rowp, sh, rb);
@@ -267,7 +276,9 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
       const float dx = dxv[x], dy = dyv[x];
       const float ares = fabsf(res);
       const float w = weighted ? weight_rcp(ares) : 1.0f;                          // :479
-      t[y * 4 + x] = weighted ? __fmul_rn(__fmul_rn(res, res), w) : ares;          // :484 / :643
+      const float term = weighted ? __fmul_rn(__fmul_rn(res, res), w) : ares;      // :484 / :643
+      tsc[(y * 4 + x) * NT] = term;
+      acc_f = __fadd_rn(acc_f, term);
 #ifdef PLSVO_FP32_SUMS
       const float wdx = __fmul_rn(w, dx), wdy = __fmul_rn(w, dy);
       Sxx = fmaf(wdx, dx, Sxx);
@@ -290,14 +301,27 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
     for (int c = 0; c < 5; ++c) ra[c] = rb[c];
   }
   S[0] = (double)Sxx, S[1] = (double)Sxy, S[2] = (double)Syy, S[3] = (double)Sxr, S[4] = (double)Syr;
+  tsum = acc_f;  // fl-sum of the 16 terms started from zero: the estimate of this patch's contribution
   return true;
 }
 
-// s <- fl(...fl(fl(s + t0) + t1)... + t15): the reference's float accumulator walking one patch
-__device__ __forceinline__ float chain16(float s, const float* t) {
+// s <- fl(...fl(fl(s + t0) + t1)... + t15): the reference's float accumulator walking one patch whose terms sit
+// in the thread's shared-memory scratch
+template <int NT>
+__device__ __forceinline__ float chain16(float s, const float* tsc) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) s = __fadd_rn(s, t[k]);
+  for (int k = 0; k < 16; ++k) s = __fadd_rn(s, tsc[k * NT]);
   return s;
+}
+// the same walk from two starting values at once (even / odd mantissa at the bottom of a binade)
+template <int NT>
+__device__ __forceinline__ void chain16x2(float& s0, float& s1, const float* tsc) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float t = tsc[k * NT];
+    s0 = __fadd_rn(s0, t);
+    s1 = __fadd_rn(s1, t);
+  }
 }
 
 // Reference-patch precompute for one patch (:243-264 / :354-375): 16 interpolated intensities and
@@ -352,38 +376,55 @@ __device__ __forceinline__ void zero_gradients(float4* cache, int MP, int p) {
   for (int y = 0; y < 8; ++y) cache[(4 + y) * MP + p] = z;
 }
 
-// Thread 0, first half of one Gauss-Newton step: solve() of SparseImgAlign (:697-704) on the block totals.
-// tot = [0..20]=H upper, [21..26]=Jres, [28]=n_meas, [29]=patches evaluated.
+// Thread 0, first half of one Gauss-Newton step of vk::NLLSSolver::optimizeGaussNewton: SparseImgAlign::solve()
+// (:697-704) on the block totals and the candidate update T*exp(-x) (:709), formed while the walker warp is still
+// chaining the chi2 items.  tot = [0..20]=H upper, [21..26]=Jres, [28]=n_meas, [29]=patches evaluated.
 __device__ __noinline__ void gn_solve(PairCtl* ctl, const double* tot, int level) {
   ctl->n_meas_last = (long long)tot[28];
   ctl->patch_iters += (unsigned int)tot[29];
   ctl->iters_level[level] += 1;
-  double Hu[21], gg[6], xx[6];
+  double xx[6];
+  {
+    double Hu[21], gg[6];
 #pragma unroll
-  for (int i = 0; i < 21; ++i) Hu[i] = tot[i];
+    for (int i = 0; i < 21; ++i) Hu[i] = tot[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) gg[i] = tot[21 + i];
-  if (ldlt6_reg(Hu, gg, xx)) {
+    for (int i = 0; i < 6; ++i) gg[i] = tot[21 + i];
+    if (!ldlt6_reg(Hu, gg, xx)) {
+      // degenerate system: pivoted Eigen-style routine on the full symmetric matrix
+      double* H = ctl->H_last;
+      int idx = 0;
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) {
+          H[i * 6 + j] = tot[idx];
+          H[j * 6 + i] = tot[idx];
+          ++idx;
+        }
+      for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
+      ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) ctl->x[i] = xx[i];
-  } else {
-    // degenerate system: pivoted Eigen-style routine on the full symmetric matrix
-    double* H = ctl->H_last;
-    int idx = 0;
-    for (int i = 0; i < 6; ++i)
-      for (int j = i; j < 6; ++j) {
-        H[i * 6 + j] = tot[idx];
-        H[j * 6 + i] = tot[idx];
-        ++idx;
-      }
-    for (int i = 0; i < 6; ++i) ctl->g[i] = tot[21 + i];
-    ldlt6_solve(H, ctl->g, ctl->x, ctl->scratch);
+      for (int i = 0; i < 6; ++i) xx[i] = ctl->x[i];
+    }
   }
-  if (isnan(ctl->x[0])) ctl->stop = 1;
+  if (isnan(xx[0])) ctl->stop = 1;
+  double mx[6];
+  double nm = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    mx[i] = -xx[i];
+    nm = fmax(nm, fabs(xx[i]));
+  }
+  SE3q model;
+  model.q.x = ctl->model[0], model.q.y = ctl->model[1], model.q.z = ctl->model[2], model.q.w = ctl->model[3];
+  model.t = v3(ctl->model[4], ctl->model[5], ctl->model[6]);
+  const SE3q cand = se3_mul(model, se3_exp(mx));
+  se3_store(cand, ctl->cand);
+  quat_to_R(cand.q, ctl->candR);
+  ctl->cand_nm = nm;
 }
 
-// Thread 0, second half: vk::NLLSSolver::optimizeGaussNewton's accept / rollback / convergence logic with
-// SparseImgAlign::update (:706-710).  chi2f is the pass's chi2 in the reference's summation order.
+// Thread 0, second half: the accept / rollback / convergence logic of vk::NLLSSolver::optimizeGaussNewton.
+// chi2f is the pass's chi2 in the reference's summation order.
 __device__ __noinline__ void gn_decide(PairCtl* ctl, const double* tot, float chi2f, int n_iter, double eps) {
   // chi2/n_meas_ : float / size_t -> float (:192)
   const double new_chi2 = (double)(chi2f / (float)(unsigned long long)ctl->n_meas_last);
@@ -391,29 +432,19 @@ __device__ __noinline__ void gn_decide(PairCtl* ctl, const double* tot, float ch
   int flag;
   if (reject) {
     for (int i = 0; i < 7; ++i) ctl->model[i] = ctl->old_model[i];
+    Quat q;
+    q.x = ctl->model[0], q.y = ctl->model[1], q.z = ctl->model[2], q.w = ctl->model[3];
+    quat_to_R(q, ctl->R);
     flag = 1;
   } else {
-    double mx[6];
-    double nm = 0.0;
-    for (int i = 0; i < 6; ++i) {
-      mx[i] = -ctl->x[i];
-      nm = fmax(nm, fabs(ctl->x[i]));
-    }
-    SE3q model;
-    model.q.x = ctl->model[0], model.q.y = ctl->model[1], model.q.z = ctl->model[2], model.q.w = ctl->model[3];
-    model.t = v3(ctl->model[4], ctl->model[5], ctl->model[6]);
-    const SE3q nm_model = se3_mul(model, se3_exp(mx));
-    for (int i = 0; i < 7; ++i) ctl->old_model[i] = ctl->model[i];
-    se3_store(nm_model, ctl->model);
+    for (int i = 0; i < 7; ++i) ctl->old_model[i] = ctl->model[i], ctl->model[i] = ctl->cand[i];
+    for (int i = 0; i < 9; ++i) ctl->R[i] = ctl->candR[i];
     ctl->chi2_prev = new_chi2;
-    flag = (nm <= eps) ? 1 : 0;
+    flag = (ctl->cand_nm <= eps) ? 1 : 0;
   }
+  ctl->t[0] = ctl->model[4], ctl->t[1] = ctl->model[5], ctl->t[2] = ctl->model[6];
   ctl->iter += 1;
   if (ctl->iter >= n_iter) flag = 1;
-  Quat q;
-  q.x = ctl->model[0], q.y = ctl->model[1], q.z = ctl->model[2], q.w = ctl->model[3];
-  quat_to_R(q, ctl->R);
-  ctl->t[0] = ctl->model[4], ctl->t[1] = ctl->model[5], ctl->t[2] = ctl->model[6];
   if (flag) {  // last evaluated pass of this level: keep H_ (getFisherInformation, :97-102)
     int idx = 0;
     for (int i = 0; i < 6; ++i)
@@ -446,7 +477,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int MP = a.max_patches;
-  const Layout L = make_layout(a.n_pts, a.n_segs, a.max_seg_slots, a.smem_img_bytes, NT);
+  const Layout L = make_layout(a.n_pts, a.n_segs, MP, a.max_seg_slots, a.smem_img_bytes, NT);
   PairCtl* ctl = reinterpret_cast<PairCtl*>(smem + L.ctl);
   double* red = reinterpret_cast<double*>(smem + L.red);
   double* tot = reinterpret_cast<double*>(smem + L.tot);
@@ -455,18 +486,20 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
   int* item_cnt = reinterpret_cast<int*>(smem + L.cnt);
   float* opq = reinterpret_cast<float*>(smem + L.opq);
   uint8_t* seg_alive = smem + L.seg_alive;
+  int* seg_N0 = reinterpret_cast<int*>(smem + L.seg_N0);
   int* seg_N = reinterpret_cast<int*>(smem + L.seg_N);
   int* seg_off = reinterpret_cast<int*>(smem + L.seg_off);
   int* seg_slot = reinterpret_cast<int*>(smem + L.seg_slot);
   uint16_t* slot_seg = reinterpret_cast<uint16_t*>(smem + L.slot_seg);
   const int max_slots = a.max_seg_slots;  // multiple of 32
-  double* seg_scale = reinterpret_cast<double*>(smem + L.seg_scale);
   float* seg_term = reinterpret_cast<float*>(smem + L.seg_term);
   uint8_t* pt_vis = smem + L.pt_vis;
   uint8_t* img_s = smem + L.img;
   // per-CTA workspaces in global memory (L2 resident)
   float4* cache = a.ws_cache + (size_t)blockIdx.x * kCacheRows * MP;
-  double* xyz = a.ws_xyz + (size_t)blockIdx.x * 3 * MP;              // xn, yn, 1/Z of every patch's 3-D point
+  double* xyz = reinterpret_cast<double*>(smem + L.xyz);
+  float* tsc = reinterpret_cast<float*>(smem + L.tsc) + tid;  // this thread's term k at tsc[k * NT]
+  uint2* flat = reinterpret_cast<uint2*>(smem + L.flat);
   double* seg_px = a.ws_segpx + (size_t)blockIdx.x * 2 * a.max_seg_patches;  // 2-D centre of every segment sample
   const int RS = a.rec_cap * NT;                                     // record slots per component
   double* rec = a.ws_rec + (size_t)blockIdx.x * 5 * RS;               // five in-patch sums of this pass, per thread slot
@@ -550,7 +583,10 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
       xyz[1 * MP + i] = (f[1] * depth) * zi;
       xyz[2 * MP + i] = zi;
     }
-    for (int j = tid; j < ns; j += NT) seg_alive[j] = a.seg_valid ? (a.seg_valid[so + j] ? 1 : 0) : 1;
+    for (int j = tid; j < ns; j += NT) {
+      seg_alive[j] = a.seg_valid ? (a.seg_valid[so + j] ? 1 : 0) : 1;
+      seg_N0[j] = seg_num_samples0(a.seg_spx + (so + j) * 2, a.seg_epx + (so + j) * 2, a.seg_length[so + j]);
+    }
     unsigned int my_patch_levels = 0;
     const int n_chunks = (np + 31) >> 5;       // 32-patch chunks of the point list
     const int rounds = (np + NT - 1) / NT;     // rounds of NT point patches per pass
@@ -583,13 +619,11 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
           const double* epx = a.seg_epx + (so + j) * 2;
           const int sx = (int)(spx[0] * dscale), sy = (int)(spx[1] * dscale);
           const int ex = (int)(epx[0] * dscale), ey = (int)(epx[1] * dscale);
-          if (cam_in_frame(sx, sy, 3, level, a.width, a.height) && cam_in_frame(ex, ey, 3, level, a.width, a.height)) {
-            double dif[2];
-            N = seg_num_samples(spx, epx, a.seg_length[so + j], level, dif);
-          }
+          if (cam_in_frame(sx, sy, 3, level, a.width, a.height) && cam_in_frame(ex, ey, 3, level, a.width, a.height))
+            N = 1 + ((seg_N0[j] - 1) >> level);
         }
         seg_N[j] = N;
-        seg_term[j] = -1.f;
+        seg_term[j] = 0.f;
       }
       for (int q = tid; q < max_slots; q += NT) slot_seg[q] = 0xffffu;
       __syncthreads();
@@ -642,8 +676,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
         if (N == 0) continue;
         const double* spx = a.seg_spx + (so + j) * 2;
         const double* epx = a.seg_epx + (so + j) * 2;
-        double dif[2];
-        seg_num_samples(spx, epx, a.seg_length[so + j], level, dif);
+        const double dif[2] = {epx[0] - spx[0], epx[1] - spx[1]};
         const double nm1 = (double)(unsigned long long)(N - 1);
         const double inc2d0 = dif[0] * dscale / nm1, inc2d1 = dif[1] * dscale / nm1;
         double px0 = spx[0] * dscale, px1 = spx[1] * dscale;
@@ -723,45 +756,39 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
 #ifdef PLSVO_TREE_CHI2
         double chi2_tree = 0.0;
 #endif
-        unsigned long long rec_ok = 0ull;  // bit k: this thread's k-th record of the pass holds sums
-        int n_rec = 0;
-        double prefix_rounds = 0.0;        // estimate of the float chi2 accumulator after all earlier rounds
-        // ======== phase 1a: point patches (:380-502), one round of NT consecutive patches at a time ========
+        // this thread's 21 (upper-triangular H) + 6 (Jres) accumulators of the pass
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+        double prefix_rounds = 0.0;  // estimate of the float chi2 accumulator after all earlier rounds
+        // ======== point patches (:380-502), one round of NT consecutive patches at a time ========
         for (int r = 0; r < rounds; ++r) {
           const int c = r * NW + warp;  // 32-patch chunk of this warp: patches [32c, 32c+32) in list order
           const int p = c * 32 + lane;
-          float t[16];
+          float Tf = 0.f;
           bool ok = false;
           if (p < np && pt_vis[p]) {
             const double xn = xyz[0 * MP + p], yn = xyz[1 * MP + p], zi = xyz[2 * MP + p];
             const double xc = R0 * xn + R1 * yn + (R2 + t0 * zi);  // (R*xyz_ref + t) / Z_ref
             const double yc = R3 * xn + R4 * yn + (R5 + t1 * zi);
             const double zc = R6 * xn + R7 * yn + (R8 + t2 * zi);
-            const double izc = 1.0 / zc;
+            const double izc = __drcp_rn(zc);
             const double u = (a.fx * (xc * izc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
             const double v = (a.fy * (yc * izc) + a.cy) * dscale;
             double S[5];
-            ok = eval_patch<true>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, t);
-            if (ok && n_rec >= a.rec_cap) ok = false, atomicOr(&ctl->chi2_flags, 4);  // host plan violated (never)
+            ok = eval_patch<true, NT>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, tsc, Tf);
             if (ok) {
-              double* rp = rec + n_rec * NT + tid;
-#pragma unroll
-              for (int k = 0; k < 5; ++k) rp[k * RS] = S[k];
-              rec_ok |= 1ull << n_rec;
+              // normal equations: rank-2 update with the two projection-Jacobian rows of the patch
+              rank2_update(acc, xn, yn, zi, S[0] * cJ2, S[1] * cJ2, S[2] * cJ2, S[3] * cJ, S[4] * cJ);
               n_meas_acc += 16;
               n_patch_acc += 1;
             }
           }
-          ++n_rec;
-          if (!ok) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) t[k] = 0.f;
-          }
+          if (!ok) Tf = 0.f;  // not evaluated: contributes nothing (its scratch terms are stale and never read)
 #ifdef PLSVO_TREE_CHI2
-          chi2_tree += (double)chain16(0.f, t);
+          chi2_tree += (double)Tf;
 #else
           // -- estimate of the accumulator before this patch: exact prefix sum of the patch totals --
-          const float Tf = chain16(0.f, t);
           double incl = (double)Tf;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -785,7 +812,12 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             const double lo = P * (1.0 - delta), hi = (P + (double)Tf) * (1.0 + delta);
             const int e_lo = (__double2hiint(lo) >> 20) - 1023, e_hi = (__double2hiint(hi) >> 20) - 1023;
             uint32_t ef = 0, opaque = 0, Ae = 0, Ao = 0, slot = 0;
-            if (P == 0.0) {
+            if (!ok) {
+              // no terms: identity map.  It joins the binade of the estimate so that it merges with its neighbours
+              // (P == 0: still in front of the first non-zero term).
+              if (P != 0.0 && e_lo == e_hi && e_lo >= -100 && e_lo <= 100) ef = (uint32_t)(e_lo + 127);
+              else if (P != 0.0) ef = 255u;  // next to a power of two: a group of its own, still the identity
+            } else if (P == 0.0) {
               opaque = (Tf != 0.f) ? 1u : 0u;  // leading zeros leave the accumulator at 0
             } else if (e_lo != e_hi || e_lo < -100 || e_lo > 100) {
               opaque = 1u;
@@ -793,7 +825,8 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
               // inside binade e: the 16 additions add A[parity of s_in's mantissa] ulps
               ef = (uint32_t)(e_lo + 127);
               const uint32_t b0 = ef << 23;
-              const float s0 = chain16(__uint_as_float(b0), t), s1 = chain16(__uint_as_float(b0 | 1u), t);
+              float s0 = __uint_as_float(b0), s1 = __uint_as_float(b0 | 1u);
+              chain16x2<NT>(s0, s1, tsc);
               Ae = __float_as_uint(s0) - b0;
               Ao = __float_as_uint(s1) - (b0 | 1u);
             }
@@ -801,11 +834,8 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
               const int idx = atomicAdd(&ctl->n_opq, 1);
               if (idx < kOpqCap) {
                 slot = (uint32_t)idx;
-                float4* o4 = reinterpret_cast<float4*>(opq + idx * 16);
-                o4[0] = make_float4(t[0], t[1], t[2], t[3]);
-                o4[1] = make_float4(t[4], t[5], t[6], t[7]);
-                o4[2] = make_float4(t[8], t[9], t[10], t[11]);
-                o4[3] = make_float4(t[12], t[13], t[14], t[15]);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) opq[idx * 16 + k] = tsc[k * NT];
               } else {
                 atomicOr(&ctl->chi2_flags, 1);
                 opaque = 0u;  // dropped from the exact chain; the walker falls back to the estimate
@@ -836,10 +866,10 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
           }
 #endif
         }
-        // ======== phase 1b: segment samples (:504-695).  Every segment owns a group of G = 2^k consecutive lanes
-        // of one warp (G >= its sample count, or the whole warp looping over samples), so the per-segment
-        // gate / weight (:640-688) is a few shuffles: no block barrier.  Warps take segment rounds from the top
-        // so they interleave with the point rounds. ========
+        // ======== segment samples (:504-695).  Every segment owns a group of G = 2^k consecutive lanes of one warp
+        // (G >= its sample count, or the whole warp looping over samples), so the per-segment gate / weight
+        // (:640-688) is a few shuffles: no block barrier.  Warps take segment rounds from the top so they interleave
+        // with the point rounds. ========
         for (int base = (NW - 1 - warp) * 32; base < n_seg_slots; base += NT) {
           const int q = base + lane;
           const int j = slot_seg[q];
@@ -852,7 +882,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
           int G = 1;
           while (G < Ns && G < 32) G <<= 1;
           const int gbase = lane - n0;  // first lane of this lane's group
-          int trips = (Ns + G - 1) / G, gmax = seg_ok ? G : 0;
+          int trips = seg_ok ? (Ns + G - 1) / G : 0, gmax = seg_ok ? G : 0;
 #pragma unroll
           for (int d = 16; d >= 1; d >>= 1) {
             trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, d));
@@ -860,40 +890,46 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
           }
           float s_tok = 0.f;  // the reference's res_ accumulator (:643-646) handed from sample to sample
           int first_bad = 0x7fffffff;
+          unsigned ok_trips = 0u;  // bit t: this lane's sample of trip t was evaluated
+          double S[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+          int p = 0;
           for (int trip = 0; trip < trips; ++trip) {
             const int n = n0 + trip * G;
             const bool active = n < N;
-            float t[16];
+            float Tf = 0.f;
             bool ok = false;
             if (active) {
-              const int p = np + off + n;
+              p = np + off + n;
               const double xn = xyz[0 * MP + p], yn = xyz[1 * MP + p], zi = xyz[2 * MP + p];
               const double xc = R0 * xn + R1 * yn + (R2 + t0 * zi);
               const double yc = R3 * xn + R4 * yn + (R5 + t1 * zi);
               const double zc = R6 * xn + R7 * yn + (R8 + t2 * zi);
-              const double izc = 1.0 / zc;
+              const double izc = __drcp_rn(zc);
               const double u = (a.fx * (xc * izc) + a.cx) * dscale;
               const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-              double S[5];
-              ok = eval_patch<false>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, t);
-              if (ok && n_rec >= a.rec_cap) ok = false, atomicOr(&ctl->chi2_flags, 4);
+              ok = eval_patch<false, NT>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, tsc, Tf);
               if (ok) {
-                double* rp = rec + n_rec * NT + tid;
+                ok_trips |= 1u << (trip & 31);
+                if (trips > 1) {  // segment longer than a warp: park the sums until its weight is known
+                  if (trip < a.rec_cap) {
+                    double* rp = rec + trip * NT + tid;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) rp[k * RS] = S[k];
-                rec_ok |= 1ull << n_rec;
+                    for (int k = 0; k < 5; ++k) rp[k * RS] = S[k];
+                  } else {
+                    atomicOr(&ctl->chi2_flags, 4);  // host plan violated (never)
+                  }
+                }
               } else {
                 first_bad = min(first_bad, n);
               }
             }
-            ++n_rec;
             // res_ += fabsf(res) over the samples in order, 16 pixels each (:643-646): the accumulator walks the
             // group's lanes; a lane without an evaluated sample hands it on unchanged
             for (int g = 0; g < gmax; ++g) {
               const float prev = __shfl_sync(0xffffffffu, s_tok, gbase + ((n0 - 1) & (G - 1)));
               if (n0 == g) {
                 const float s_in = (g == 0 && trip == 0) ? 0.f : prev;
-                s_tok = (active && ok) ? chain16(s_in, t) : s_in;
+                s_tok = (active && ok) ? (s_in == 0.f ? Tf : chain16<NT>(s_in, tsc)) : s_in;
               }
             }
           }
@@ -904,57 +940,40 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             const int fb = __shfl_xor_sync(0xffffffffu, first_bad, d);
             if (d < G) first_bad = min(first_bad, fb);
           }
-          if (N == 0 || n0 != 0) continue;  // the group's first lane settles the segment
-          const bool good = first_bad >= N;
-          n_patch_acc += good ? N : first_bad;  // samples evaluated before the loop stops (:588-594)
-          res_ = (float)((double)res_ / (double)(unsigned long long)N);  // :647
-          if (good && (double)res_ < 200.0) {
-            const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
-            seg_scale[2 * j] = (double)w / (double)res_ * cJ2;    // H += H_*weight/res_ (:681)
-            seg_scale[2 * j + 1] = (double)w * cJ;                // Jres += Jres_*weight (:682)
-            seg_term[j] = __fmul_rn(__fmul_rn(res_, res_), w);    // chi2 += res_*res_*weight (:683)
+          double sH = 0.0, sJ = 0.0;
+          if (N > 0 && n0 == 0) {  // the group's first lane settles the segment
+            const bool good = first_bad >= N;
+            n_patch_acc += good ? N : first_bad;  // samples evaluated before the loop stops (:588-594)
+            res_ = (float)((double)res_ / (double)(unsigned long long)N);  // :647
+            if (good && (double)res_ < 200.0) {
+              const float w = (float)(1.0 / (1.0 + (double)res_));  // :675
+              sH = (double)w / (double)res_ * cJ2;                  // H += H_*weight/res_ (:681)
+              sJ = (double)w * cJ;                                  // Jres += Jres_*weight (:682)
+              seg_term[j] = __fmul_rn(__fmul_rn(res_, res_), w);    // chi2 += res_*res_*weight (:683)
 #ifdef PLSVO_TREE_CHI2
-            chi2_tree += (double)seg_term[j];
+              chi2_tree += (double)seg_term[j];
 #endif
-            n_meas_acc += 1;                                      // :684
-          } else {
-            seg_scale[2 * j] = 0.0;  // rejected: its samples are skipped in phase 2
-            seg_scale[2 * j + 1] = 0.0;
-            seg_term[j] = -1.f;
-            seg_alive[j] = 0;  // it->feat3D = NULL (:688); the group's lanes have all read it already
+              n_meas_acc += 1;                                      // :684
+            } else {
+              seg_term[j] = 0.f;
+              seg_alive[j] = 0;  // it->feat3D = NULL (:688); the group's lanes have all read it already
+            }
           }
-        }
-        __syncwarp();  // phase 2 reads back what lanes of this warp wrote (seg_scale)
-        // ======== phase 2: normal equations.  Rank-2 update of this thread's 21+6 accumulators per record. ========
-        double acc[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-        n_rec = 0;
-        for (int r = 0; r < rounds; ++r, ++n_rec) {
-          if (!((rec_ok >> n_rec) & 1ull)) continue;
-          const int p = (r * NW + warp) * 32 + lane;
-          const double* rp = rec + n_rec * NT + tid;
-          rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], rp[0] * cJ2, rp[RS] * cJ2, rp[2 * RS] * cJ2,
-                       rp[3 * RS] * cJ, rp[4 * RS] * cJ);
-        }
-        for (int base = (NW - 1 - warp) * 32; base < n_seg_slots; base += NT) {
-          const int q = base + lane;
-          const int j = slot_seg[q];
-          const bool has = j < ns;
-          const int N = has ? seg_N[j] : 0;
-          int G = 1;
-          while (G < N && G < 32) G <<= 1;
-          int trips = (N + G - 1) / G;
-#pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, d));
-          const double sH = has ? seg_scale[2 * j] : 0.0, sJ = has ? seg_scale[2 * j + 1] : 0.0;
-          const int n0 = has ? q - seg_slot[j] : 0;
-          for (int trip = 0; trip < trips; ++trip, ++n_rec) {
-            if (!((rec_ok >> n_rec) & 1ull) || (sH == 0.0 && sJ == 0.0)) continue;
-            const int p = np + seg_off[j] + n0 + trip * G;
-            const double* rp = rec + n_rec * NT + tid;
-            rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], rp[0] * sH, rp[RS] * sH, rp[2 * RS] * sH,
-                         rp[3 * RS] * sJ, rp[4 * RS] * sJ);
+          sH = __shfl_sync(0xffffffffu, sH, gbase);  // the segment's weight to all lanes of its group
+          sJ = __shfl_sync(0xffffffffu, sJ, gbase);
+          if (sH != 0.0 || sJ != 0.0) {  // accepted segment: its samples enter the normal equations
+            if (trips == 1) {
+              if (ok_trips) rank2_update(acc, xyz[0 * MP + p], xyz[1 * MP + p], xyz[2 * MP + p], S[0] * sH, S[1] * sH, S[2] * sH,
+                                         S[3] * sJ, S[4] * sJ);
+            } else {
+              for (int trip = 0; trip < trips && trip < a.rec_cap; ++trip) {
+                if (!((ok_trips >> (trip & 31)) & 1u)) continue;
+                const int pp = np + off + n0 + trip * G;
+                const double* rp = rec + trip * NT + tid;
+                rank2_update(acc, xyz[0 * MP + pp], xyz[1 * MP + pp], xyz[2 * MP + pp], rp[0] * sH, rp[RS] * sH, rp[2 * RS] * sH,
+                             rp[3 * RS] * sJ, rp[4 * RS] * sJ);
+              }
+            }
           }
         }
         acc[28] = (double)n_meas_acc;
@@ -983,36 +1002,59 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
           // ---- chi2 in the reference's order: chain the composed maps and the opaque patches ----
           float s = 0.f;
           uint32_t bad = 0;
-          for (int c = 0; c < n_chunks; ++c) {
-            const int cnt = item_cnt[c];
-            uint2 it = make_uint2(0u, 0u);
-            if (lane < cnt) it = items[c * 32 + lane];
-            for (int k = 0; k < cnt; ++k) {
-              const uint32_t ix = __shfl_sync(0xffffffffu, it.x, k), iy = __shfl_sync(0xffffffffu, it.y, k);
-              if ((iy >> 24) & 1u) {
-                const float tv = (lane < 16) ? opq[(iy >> 25) * 16 + lane] : 0.f;
+          for (int c = 0; c < n_chunks;) {
+            // gather the items of the next chunks (as many as fit 64 entries) into one list, in list order
+            const int cc = c + lane;
+            const int my_cnt = (cc < n_chunks) ? item_cnt[cc] : 0;
+            int incl = my_cnt;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) s = __fadd_rn(s, __shfl_sync(0xffffffffu, tv, i));
-              } else {
-                uint32_t bits = __float_as_uint(s);
-                const uint32_t ef = (iy >> 16) & 0xffu;
-                const uint32_t Ao = ix + (uint32_t)(int)(short)(iy & 0xffffu);
-                bad |= (bits >> 23) ^ ef;
-                bits += (bits & 1u) ? Ao : ix;
-                bad |= (bits >> 23) ^ ef;
-                s = __uint_as_float(bits);
+            for (int d = 1; d < 32; d <<= 1) {
+              const int n = __shfl_up_sync(0xffffffffu, incl, d);
+              if (lane >= d) incl += n;
+            }
+            const int nfit = max(1, __popc(__ballot_sync(0xffffffffu, cc < n_chunks && incl <= 64)));
+            for (int j = 0; j < nfit; ++j) {
+              const int cnt_j = __shfl_sync(0xffffffffu, my_cnt, j), off_j = __shfl_sync(0xffffffffu, incl - my_cnt, j);
+              if (lane < cnt_j) flat[off_j + lane] = items[(c + j) * 32 + lane];
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, nfit - 1);
+            __syncwarp();
+            for (int b0 = 0; b0 < total; b0 += 32) {
+              uint2 it = make_uint2(0u, 0u);
+              if (b0 + lane < total) it = flat[b0 + lane];
+              float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+              if ((it.y >> 24) & 1u) {  // this lane's item is an opaque patch: fetch its 16 terms now, off the chain
+                const float4* o4 = reinterpret_cast<const float4*>(opq + (it.y >> 25) * 16);
+                q0 = o4[0], q1 = o4[1], q2 = o4[2], q3 = o4[3];
+              }
+              const float tr[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+              const int m = min(32, total - b0);
+              for (int k = 0; k < m; ++k) {
+                const uint32_t ix = __shfl_sync(0xffffffffu, it.x, k), iy = __shfl_sync(0xffffffffu, it.y, k);
+                if ((iy >> 24) & 1u) {
+                  // opaque patch: its owner lane adds the 16 terms to the (warp-uniform) accumulator, then everyone
+                  // takes the owner's result
+                  float so = s;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) so = __fadd_rn(so, tr[i]);
+                  s = __shfl_sync(0xffffffffu, so, k);
+                } else {
+                  const uint32_t dA = (uint32_t)(int)(short)(iy & 0xffffu);
+                  if (ix | dA) {  // not the identity
+                    uint32_t bits = __float_as_uint(s);
+                    bad |= (bits >> 23) ^ ((iy >> 16) & 0xffu);
+                    bits += (bits & 1u) ? ix + dA : ix;
+                    s = __uint_as_float(bits);
+                  }
+                }
               }
             }
+            __syncwarp();
+            c += nfit;
           }
-          float s2 = 0.f;  // seg_chi2 (:683): one term per accepted segment, in list order
-          for (int base = 0; base < ns; base += 32) {
-            const float tv = (base + lane < ns && seg_N[base + lane] > 0) ? seg_term[base + lane] : -1.f;
-            const int m = min(32, ns - base);
-            for (int i = 0; i < m; ++i) {
-              const float x = __shfl_sync(0xffffffffu, tv, i);
-              if (x >= 0.f) s2 = __fadd_rn(s2, x);
-            }
-          }
+          float s2 = 0.f;  // seg_chi2 (:683): one term per accepted segment, in list order (others hold +0, a no-op)
+#pragma unroll 8
+          for (int j = 0; j < ns; ++j) s2 = __fadd_rn(s2, seg_term[j]);
           if (lane == 0) {
             if (ctl->n_opq > kOpqCap) {
               // opaque buffer overflowed (flag 1): fall back to the estimate of the point sum for this pass
@@ -1025,9 +1067,8 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             ctl->n_opq = 0;
           }
         }
-        if (NW > 1) {
-          if (warp <= 1) named_barrier_sync(1, 64);  // chi2 (warp 1) -> decision (warp 0)
-        }
+        // chi2 (walker warp) -> decision (thread 0); both warps arrive converged: a named barrier counts whole warps
+        if (NW > 1 && warp <= 1) named_barrier_sync(1, 64);
 #ifdef PLSVO_TREE_CHI2
         if (tid == 0) gn_decide(ctl, tot, (float)tot[27], a.n_iter, a.eps);
 #else
@@ -1100,8 +1141,8 @@ cudaError_t weight_selftest_launch(uint32_t n, uint32_t seed, unsigned long long
   return cudaGetLastError();
 }
 
-size_t align_smem_bytes(int n_pts, int n_segs, int max_seg_slots, int img_bytes, int threads) {
-  return make_layout(n_pts, n_segs, max_seg_slots, img_bytes, threads).total;
+size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_slots, int img_bytes, int threads) {
+  return make_layout(n_pts, n_segs, max_patches, max_seg_slots, img_bytes, threads).total;
 }
 
 // Kernel variants: CTA size x resident CTAs per SM the register budget is compiled for.  Small CTAs with many

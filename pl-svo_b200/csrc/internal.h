@@ -58,14 +58,13 @@ struct AlignArgs {
   int max_seg_slots;    // lane slots of the segment groups per pair (multiple of 32)
   int smem_img_bytes;   // bytes of the image staging buffer
   float4* ws_cache;     // [grid][kCacheRows][max_patches] reference-patch cache (ref, dx, dy rows), L2 resident
-  double* ws_xyz;       // [grid][3][max_patches] X/Z, Y/Z, 1/Z of every patch's 3-D point in the reference frame
   double* ws_segpx;     // [grid][2][max_seg_patches] 2-D centre of every segment sample (precompute only)
-  double* ws_rec;       // [grid][5][rec_cap*threads] in-patch sums of the current pass, one slot per thread and record
-  int rec_cap;          // records per thread and pass (point rounds + segment trips), <= 64
+  double* ws_rec;       // [grid][5][rec_cap*threads] parked in-patch sums of segments longer than a warp
+  int rec_cap;          // 32-sample trips of the longest segment, <= 32
 };
 
 // shared memory the kernel needs for a configuration (host + device agree through this)
-size_t align_smem_bytes(int n_pts, int n_segs, int max_seg_slots, int img_bytes, int threads);
+size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_slots, int img_bytes, int threads);
 // kernel variants are compiled per (threads per CTA, resident CTAs per SM the register budget allows):
 // (64,8) (96,7) (96,5) (128,5) (128,4) (256,2)
 cudaError_t align_kernel_prepare(int threads, int min_blocks, size_t smem_bytes, int* ctas_per_sm);

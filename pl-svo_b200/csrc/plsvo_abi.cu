@@ -535,17 +535,15 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
   int rc_last = PLSVO_ERR_INVALID;
   for (auto& v : order) {
     const int threads = v[0], min_blocks = v[1];
-    // records per thread and pass: point rounds + segment rounds x trips of the longest segment
-    const int rounds = (a.n_pts + threads - 1) / threads;
-    const int seg_rounds = (a.max_seg_slots + threads - 1) / threads;
-    const int rec_cap = std::max(1, rounds + seg_rounds * ((maxN + 31) / 32));
-    if (rec_cap > 64) {
-      rc_last = fail(c, PLSVO_ERR_INVALID, "feature counts exceed the per-thread record plan");
+    // parked in-patch sums of a segment longer than a warp (one record per thread and 32-sample trip)
+    const int rec_cap = std::max(1, (maxN + 31) / 32);
+    if (rec_cap > 32) {
+      rc_last = fail(c, PLSVO_ERR_INVALID, "a segment has more than 1024 samples");
       continue;
     }
     // shared-memory plan: stage the current image level when the CTA still fits min_blocks times per SM next to
     // the per-pair state; bigger levels are read through L2 with the same aligned-word loads.
-    const int other = (int)align_smem_bytes(a.n_pts, a.n_segs, a.max_seg_slots, 0, threads);
+    const int other = (int)align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_slots, 0, threads);
     int img_budget = (limit + 1024) / min_blocks - 1024 - other;
     if (img_budget < 0) img_budget = 0;
     img_budget = std::min(img_budget, 96 * 1024);
@@ -557,11 +555,11 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
       a.img_in_smem[l] = (bytes <= (size_t)img_budget && bytes < (1u << 20) && bytes % 16 == 0) ? 1 : 0;
       if (a.img_in_smem[l]) img_bytes = std::max(img_bytes, (int)bytes);
     }
-    size_t smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_seg_slots, img_bytes, threads);
+    size_t smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_slots, img_bytes, threads);
     if (smem > (size_t)limit) {  // drop image staging as a last resort
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.img_in_smem[l] = 0;
       img_bytes = 0;
-      smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_seg_slots, 0, threads);
+      smem = align_smem_bytes(a.n_pts, a.n_segs, a.max_patches, a.max_seg_slots, 0, threads);
       if (smem > (size_t)limit) {
         rc_last = fail(c, PLSVO_ERR_INVALID, "feature counts exceed the shared-memory plan");
         continue;
@@ -580,11 +578,9 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
     // per-CTA workspaces (L2 resident): reference-patch cache, patch geometry, segment sample centres, pass records
     const size_t grid_max = (size_t)std::min(a.B, c->num_sms * ctas_per_sm);
     CK(ensure(c->d_ws_cache, grid_max * kCacheRows * a.max_patches * sizeof(float4)));
-    CK(ensure(c->d_ws_xyz, grid_max * 3 * a.max_patches * sizeof(double)));
     CK(ensure(c->d_ws_segpx, grid_max * 2 * a.max_seg_patches * sizeof(double)));
     CK(ensure(c->d_ws_rec, grid_max * 5 * (size_t)rec_cap * threads * sizeof(double)));
     a.ws_cache = static_cast<float4*>(c->d_ws_cache.p);
-    a.ws_xyz = static_cast<double*>(c->d_ws_xyz.p);
     a.ws_segpx = static_cast<double*>(c->d_ws_segpx.p);
     a.ws_rec = static_cast<double*>(c->d_ws_rec.p);
     plan->threads = threads, plan->min_blocks = min_blocks, plan->ctas_per_sm = ctas_per_sm, plan->smem = smem;
