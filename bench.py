@@ -37,6 +37,7 @@ METRIC = "frame-pair aligns/sec (VGA 5-lvl pyr, ~300pt+80ln)"
 BYTES_PATCH_ITER = 241
 BYTES_PATCH_LEVEL = 281
 BYTES_PAIR_FIXED = 512
+DTYPE = "f32 residuals, weights and chi2 (the reference's summation order, bit-exact); f64 per-pixel normal equations, solve and SE3"
 
 
 def parse():
@@ -117,6 +118,30 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def kernel_source_hash():
+    """sha256 over the alignment kernel's sources: ties a committed ncu traffic capture to the code it measured."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in ("align_kernel.cu", "device_math.cuh", "internal.h"):
+        h.update(open(os.path.join(ROOT, "pl-svo_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
+def committed_traffic(args):
+    """DRAM bytes per launch of sparse_img_align_kernel from the committed `ncu --set full` capture of this exact
+    configuration — only if that capture was taken from the kernel source that is being timed now."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["sparse_img_align_kernel"]
+    except Exception:
+        return None, "no committed capture (profiles/r02_traffic.json)"
+    if not (args.batch == tj.get("batch") and args.n_pts == tj.get("n_pts") and args.n_segs == tj.get("n_segs")):
+        return None, "committed capture is for another configuration"
+    if tj.get("kernel_source_sha256") != kernel_source_hash():
+        return None, "STALE: kernel source changed since the committed capture " + str(tj.get("source"))
+    return tj["dram_bytes_per_launch"], tj["source"]
+
+
 def cpu_impl(abi, oracle_lib):
     """(align function, kind, description) of the CPU arm: oracle/_ref when built, else the oracle port."""
     if oracle_lib.ref_available():
@@ -127,11 +152,9 @@ def cpu_impl(abi, oracle_lib):
             "oracle restatement of sparse_img_align.cpp (oracle/_ref not built on this box)")
 
 
-def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
-    """pairs/s of the CPU arm with all host threads on the first n_pairs of `data`."""
+def subset(data, n_pairs):
+    """The first n_pairs of an AlignData batch (copies)."""
     import copy
-
-    align_fn, _, _ = cpu_impl(abi, oracle_lib)
 
     sub = copy.copy(data)
     sl = slice(0, n_pairs)
@@ -140,6 +163,13 @@ def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
         setattr(sub, name, np.ascontiguousarray(getattr(data, name)[sl]))
     sub.ref_pyr = {l: np.ascontiguousarray(v[sl]) for l, v in data.ref_pyr.items()}
     sub.cur_pyr = {l: np.ascontiguousarray(v[sl]) for l, v in data.cur_pyr.items()}
+    return sub
+
+
+def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
+    """pairs/s of the CPU arm with all host threads on the first n_pairs of `data`."""
+    align_fn, _, _ = cpu_impl(abi, oracle_lib)
+    sub = subset(data, n_pairs)
     hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
     # the box may expose more logical CPUs than it lets us run on: take the best of a few thread counts
     best = None
@@ -203,7 +233,7 @@ def main():
         line = {
             "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 residuals / f64 accumulate", "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": kind,
                              "sample": f"{n} pairs per step x {args.steps} steps; {what}"},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -327,13 +357,7 @@ def main():
     avg_kernel_s = (total_ms / args.steps) * 1e-3
     peak, peak_src = measured_hbm_peak()
     achieved = alg_bytes / avg_kernel_s / 1e9
-    traffic, traffic_src = None, None
-    try:  # DRAM bytes per launch of the same kernel/config, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["sparse_img_align_kernel"]
-        if args.batch == 1024 and args.n_pts == 300 and args.n_segs == 80:
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-    except Exception:
-        pass
+    traffic, traffic_src = committed_traffic(args)
 
     # ---- secondary: pose optimiser (BASELINE config 3: 300 pts + 80 lines, 10 iters, B = 4096 frames) ----
     poseopt = None
@@ -380,14 +404,23 @@ def main():
             ref = cpu_impl(abi, oracle_lib)[0](abi, data, n_threads=threads)
             ang, rel = synth.pose_error(out.T_cur_w, ref.T_cur_w)
             _, kind, what = cpu_impl(abi, oracle_lib)
+            # the reference's own call pattern, one pair at a time on one thread
+            n1 = min(48, B)
+            sub1 = subset(data, n1)
+            cpu_impl(abi, oracle_lib)[0](abi, sub1, n_threads=1)
+            t1 = time.perf_counter()
+            cpu_impl(abi, oracle_lib)[0](abi, sub1, n_threads=1)
+            single = n1 / (time.perf_counter() - t1)
             cpu = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": kind,
+                   "single_thread": {"value": single, "unit": "pairs/s", "cores": 1, "ms_per_pair": 1e3 / single, "pairs": n1},
+                   "iteration_counts_equal": int((out.iters == ref.iters).all(axis=1).sum()),
                    "sample": f"{min(n, B)} pairs x {reps} passes ({secs:.1f} s), all host threads; {what}",
                    "parity_vs_gpu": {"max_rot_rad": float(ang.max()), "max_rel_t": float(rel.max()),
                                      "pairs_within_tol": int(((ang <= 1e-5) & (rel <= 1e-4)).sum()), "pairs": int(B)}}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 residuals / f64 accumulate", "data": "synthetic", "config": workload_config(args, n_gpus),
+            "dtype": DTYPE, "data": "synthetic", "config": workload_config(args, n_gpus),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
                     "d2h_bytes_per_step": int(d2h) * n_gpus},
             "gpu_launches": int(launches),

@@ -240,7 +240,7 @@ __device__ __forceinline__ void load_row7(const uint8_t* row, int sh, float* g) 
 template <bool weighted, int NT>
 __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int pitch, int cols, int rows,
                                            const float4* __restrict__ cache, int MP, int p, double u, double v,
-                                           double* S /*[5]*/, float* __restrict__ tsc, float& tsum) {
+                                           double* S /*[5]*/, float* __restrict__ tsc, float& tsum, f32x2 one2) {
   int ui, vi;
   float wTL, wTR, wBL, wBR;
   if (!patch_setup(u, v, cols, rows, 2, ui, vi, wTL, wTR, wBL, wBR)) return false;
@@ -269,18 +269,49 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
     const float refv[4] = {ref4.x, ref4.y, ref4.z, ref4.w};
     const float dxv[4] = {dx4.x, dx4.y, dx4.z, dx4.w};
     const float dyv[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+#ifdef PLSVO_SCALAR_PIXELS
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       const float cur = bilin(wTL, wTR, wBL, wBR, ra[x], ra[x + 1], rb[x], rb[x + 1]);
       const float res = __fsub_rn(cur, refv[x]);
       const float dx = dxv[x], dy = dyv[x];
       const float ares = fabsf(res);
-      const float w = weighted ? weight_rcp(ares) : 1.0f;                          // :479
-      const float term = weighted ? __fmul_rn(__fmul_rn(res, res), w) : ares;      // :484 / :643
-      tsc[(y * 4 + x) * NT] = term;
-      acc_f = __fadd_rn(acc_f, term);
+      const float nw = weighted ? -weight_rcp(ares) : -1.0f;                           // :479 (negated)
+      const float nterm = weighted ? __fmul_rn(__fmul_rn(res, res), nw) : -ares;       // :484 / :643 (negated)
+#else
+    // two pixels per instruction (FMUL2 / FADD2 / FFMA2); every operation is the reference's, rounded on its own
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int x0 = 2 * h;
+      const f32x2 pa = pk2(ra[x0], ra[x0 + 1]), pb = pk2(ra[x0 + 1], ra[x0 + 2]);
+      const f32x2 pc = pk2(rb[x0], rb[x0 + 1]), pd = pk2(rb[x0 + 1], rb[x0 + 2]);
+      // ((wTL*a + wTR*b) + wBL*c) + wBR*d  (:458)
+      f32x2 cur2 = add2_after_mul(mul2(pk2(wTL, wTL), pa), mul2(pk2(wTR, wTR), pb), one2);
+      cur2 = add2_after_mul(cur2, mul2(pk2(wBL, wBL), pc), one2);
+      cur2 = add2_after_mul(cur2, mul2(pk2(wBR, wBR), pd), one2);
+      const f32x2 res2 = sub2(cur2, pk2(refv[x0], refv[x0 + 1]));
+      float resv[2], nwv[2], ntv[2];
+      upk2(res2, resv[0], resv[1]);
+      if (weighted) {
+        const f32x2 nw2 = neg_weight_rcp2(res2);                 // -1/(1+|r|)  (:479)
+        const f32x2 nt2 = mul2(mul2(res2, res2), nw2);           // -(r*r*w)    (:484)
+        upk2(nw2, nwv[0], nwv[1]);
+        upk2(nt2, ntv[0], ntv[1]);
+      } else {
+        nwv[0] = nwv[1] = -1.0f;
+        ntv[0] = -fabsf(resv[0]), ntv[1] = -fabsf(resv[1]);      // -|r|        (:643)
+      }
+#pragma unroll
+      for (int xx = 0; xx < 2; ++xx) {
+      const int x = x0 + xx;
+      const float res = resv[xx], nw = nwv[xx], nterm = ntv[xx];
+      const float dx = dxv[x], dy = dyv[x];
+#endif
+      // the scratch keeps the NEGATED term (its consumers subtract it): the sign costs nothing there, here it would
+      tsc[(y * 4 + x) * NT] = nterm;
+      acc_f = __fsub_rn(acc_f, nterm);
 #ifdef PLSVO_FP32_SUMS
-      const float wdx = __fmul_rn(w, dx), wdy = __fmul_rn(w, dy);
+      const float wdx = weighted ? __fmul_rn(-nw, dx) : dx, wdy = weighted ? __fmul_rn(-nw, dy) : dy;
       Sxx = fmaf(wdx, dx, Sxx);
       Sxy = fmaf(wdx, dy, Sxy);
       Syy = fmaf(wdy, dy, Syy);
@@ -288,20 +319,23 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
       Syr = fmaf(wdy, res, Syr);
 #else
       const double dxd = (double)dx, dyd = (double)dy, rd = (double)res;
-      const double wdx = weighted ? (double)w * dxd : dxd;  // exact products (24+24 bits)
-      const double wdy = weighted ? (double)w * dyd : dyd;
-      Sxx = fma(wdx, dxd, Sxx);
-      Sxy = fma(wdx, dyd, Sxy);
-      Syy = fma(wdy, dyd, Syy);
-      Sxr = fma(wdx, rd, Sxr);
-      Syr = fma(wdy, rd, Syr);
+      const double nwdx = weighted ? (double)nw * dxd : -dxd;  // exact products (24+24 bits), negated
+      const double nwdy = weighted ? (double)nw * dyd : -dyd;
+      Sxx = fma(-nwdx, dxd, Sxx);
+      Sxy = fma(-nwdx, dyd, Sxy);
+      Syy = fma(-nwdy, dyd, Syy);
+      Sxr = fma(-nwdx, rd, Sxr);
+      Syr = fma(-nwdy, rd, Syr);
+#endif
+#ifndef PLSVO_SCALAR_PIXELS
+      }
 #endif
     }
 #pragma unroll
     for (int c = 0; c < 5; ++c) ra[c] = rb[c];
   }
   S[0] = (double)Sxx, S[1] = (double)Sxy, S[2] = (double)Syy, S[3] = (double)Sxr, S[4] = (double)Syr;
-  tsum = acc_f;  // fl-sum of the 16 terms started from zero: the estimate of this patch's contribution
+  tsum = acc_f;  // fl-sum of the 16 (positive) terms started from zero: the estimate of this patch's contribution
   return true;
 }
 
@@ -310,7 +344,7 @@ __device__ __forceinline__ bool eval_patch(const uint8_t* __restrict__ img, int 
 template <int NT>
 __device__ __forceinline__ float chain16(float s, const float* tsc) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) s = __fadd_rn(s, tsc[k * NT]);
+  for (int k = 0; k < 16; ++k) s = __fsub_rn(s, tsc[k * NT]);  // the scratch holds negated terms
   return s;
 }
 // the same walk from two starting values at once (even / odd mantissa at the bottom of a binade)
@@ -318,9 +352,9 @@ template <int NT>
 __device__ __forceinline__ void chain16x2(float& s0, float& s1, const float* tsc) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const float t = tsc[k * NT];
-    s0 = __fadd_rn(s0, t);
-    s1 = __fadd_rn(s1, t);
+    const float t = tsc[k * NT];  // negated term
+    s0 = __fsub_rn(s0, t);
+    s1 = __fsub_rn(s1, t);
   }
 }
 
@@ -503,6 +537,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
   double* seg_px = a.ws_segpx + (size_t)blockIdx.x * 2 * a.max_seg_patches;  // 2-D centre of every segment sample
   const int RS = a.rec_cap * NT;                                     // record slots per component
   double* rec = a.ws_rec + (size_t)blockIdx.x * 5 * RS;               // five in-patch sums of this pass, per thread slot
+  const f32x2 one2 = pk2(a.one, a.one);  // 1.0f from the host (see add2_after_mul)
   uint64_t* bar = reinterpret_cast<uint64_t*>(&ctl->mbar);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -776,7 +811,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             const double u = (a.fx * (xc * izc) + a.cx) * dscale;  // world2cam(xyz)*scale (:425)
             const double v = (a.fy * (yc * izc) + a.cy) * dscale;
             double S[5];
-            ok = eval_patch<true, NT>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, tsc, Tf);
+            ok = eval_patch<true, NT>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, tsc, Tf, one2);
             if (ok) {
               // normal equations: rank-2 update with the two projection-Jacobian rows of the patch
               rank2_update(acc, xn, yn, zi, S[0] * cJ2, S[1] * cJ2, S[2] * cJ2, S[3] * cJ, S[4] * cJ);
@@ -907,7 +942,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
               const double izc = __drcp_rn(zc);
               const double u = (a.fx * (xc * izc) + a.cx) * dscale;
               const double v = (a.fy * (yc * izc) + a.cy) * dscale;
-              ok = eval_patch<false, NT>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, tsc, Tf);
+              ok = eval_patch<false, NT>(cur_img, pitch, cols, rows, cache, MP, p, u, v, S, tsc, Tf, one2);
               if (ok) {
                 ok_trips |= 1u << (trip & 31);
                 if (trips > 1) {  // segment longer than a warp: park the sums until its weight is known
@@ -1036,7 +1071,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
                   // takes the owner's result
                   float so = s;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) so = __fadd_rn(so, tr[i]);
+                  for (int i = 0; i < 16; ++i) so = __fsub_rn(so, tr[i]);  // negated terms
                   s = __shfl_sync(0xffffffffu, so, k);
                 } else {
                   const uint32_t dA = (uint32_t)(int)(short)(iy & 0xffffu);
@@ -1131,6 +1166,10 @@ __global__ void weight_selftest_kernel(uint32_t n, uint32_t seed, unsigned long 
     const float fast = weight_rcp(a);
     const float ref = (float)(1.0 / (1.0 + (double)a));
     if (__float_as_uint(fast) != __float_as_uint(ref)) ++bad;
+    // the packed form used by the kernel (both halves, either sign of the residual): exactly -w
+    float n0, n1;
+    upk2(neg_weight_rcp2(pk2(a, -a)), n0, n1);
+    if (__float_as_uint(-n0) != __float_as_uint(ref) || __float_as_uint(-n1) != __float_as_uint(ref)) ++bad;
   }
   if (bad) atomicAdd(mismatch, bad);
 }

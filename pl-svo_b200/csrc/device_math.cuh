@@ -374,6 +374,59 @@ __device__ __forceinline__ float weight_rcp(float a) {
   return __fmaf_rn(e, q0, q0);
 }
 
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest operations per instruction) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// a + b for a pair whose first operand is a product: ptxas (12.9) contracts mul.rn.f32x2 followed by add.rn.f32x2
+// into one FFMA2, which would change the rounding.  Writing the sum as fma(a, one, b) with `one` == 1.0f taken from
+// a kernel argument (not a compile-time constant) keeps the product rounded on its own: a*1+b is a+b, rounded once.
+__device__ __forceinline__ f32x2 add2_after_mul(f32x2 a, f32x2 b, f32x2 one) { return fma2(a, one, b); }
+
+// -RN_float(1/(1+|r|)) for a pair of residuals, the packed form of weight_rcp below (same operations in the same
+// order; the reciprocal seed is taken of -(1+|r|), so every later term carries the opposite sign exactly).
+__device__ __forceinline__ f32x2 neg_weight_rcp2(f32x2 res) {
+  float r0, r1;
+  upk2(res, r0, r1);
+  const f32x2 one = pk2(1.0f, 1.0f);
+  const f32x2 a = pk2(fabsf(r0), fabsf(r1));
+  const f32x2 sh = add2(one, a);
+  const f32x2 bb = sub2(sh, one);
+  const f32x2 sl = add2(sub2(one, sub2(sh, bb)), sub2(a, bb));
+  float s0, s1, q0, q1;
+  upk2(sh, s0, s1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(-s0));  // MUFU.RCP of the negated sum: -q, refined below
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(-s1));
+  const f32x2 nq = pk2(q0, q1);
+  f32x2 e = fma2(sh, nq, one);
+  e = fma2(sl, nq, e);
+  return fma2(e, nq, nq);
+}
+
 // byte k of w as float, via PRMT + FADD (keeps the XU conversion pipe free): 0x4B0000bb = 2^23 + bb
 __device__ __forceinline__ float byte_to_float(uint32_t w, int k) {
   return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k)), 8388608.0f);

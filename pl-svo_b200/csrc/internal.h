@@ -61,6 +61,7 @@ struct AlignArgs {
   double* ws_segpx;     // [grid][2][max_seg_patches] 2-D centre of every segment sample (precompute only)
   double* ws_rec;       // [grid][5][rec_cap*threads] parked in-patch sums of segments longer than a warp
   int rec_cap;          // 32-sample trips of the longest segment, <= 32
+  float one;            // 1.0f, deliberately a run-time value (device_math.cuh: add2_after_mul)
 };
 
 // shared memory the kernel needs for a configuration (host + device agree through this)

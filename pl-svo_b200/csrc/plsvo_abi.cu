@@ -567,6 +567,7 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
     }
     a.smem_img_bytes = img_bytes;
     a.rec_cap = rec_cap;
+    a.one = 1.0f;
     int ctas_per_sm = 0;
     CK(align_kernel_prepare(threads, min_blocks, smem, &ctas_per_sm));
     if (ctas_per_sm < 1) {

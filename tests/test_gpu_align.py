@@ -1,7 +1,10 @@
 """GPU parity of the alignment kernel against the CPU oracle, through the C ABI.
 
 Tolerance (BASELINE.json north_star): rotation <= 1e-5 rad, relative translation <= 1e-4 on
-identical inputs.  Integer outputs (n_tracked, killed segments, iteration counts) must be equal.
+identical inputs.  Integer outputs (n_tracked, killed segments, per-level iteration counts, status)
+must be equal on EVERY pair: the kernel reproduces the reference's sequential float chi2 bit for bit
+and accumulates the normal equations per pixel in double, so the accept / rollback decision of the
+Gauss-Newton loop never depends on summation order.
 """
 import numpy as np
 import pytest
@@ -29,25 +32,36 @@ def _check(synth, gpu, ref, exact_iters=True, mask=None):
     np.testing.assert_array_equal(gpu.seg_killed[m], ref.seg_killed[m])
     np.testing.assert_array_equal(gpu.status[m], ref.status[m])
     if exact_iters:
-        # iteration counts may differ only where the chi2 comparison is decided by summation order
-        same = (gpu.iters == ref.iters).all(axis=1).mean()
-        assert same >= 0.9, f"only {same:.2%} of pairs have identical iteration counts"
+        np.testing.assert_array_equal(gpu.iters[m], ref.iters[m])
     scale = np.abs(ref.H).max(axis=1, keepdims=True) + 1e-300
     same_it = (gpu.iters == ref.iters).all(axis=1)
     if mask is not None:
         same_it &= mask
     if same_it.any():
-        # H is evaluated at the last model; a 1e-7 difference in that model moves H by ~1e-5 relative
-        assert (np.abs(gpu.H - ref.H)[same_it] / scale[same_it]).max() < 1e-4
+        assert (np.abs(gpu.H - ref.H)[same_it] / scale[same_it]).max() < 1e-9
 
 
 def test_align_vga_points_and_segments(pkg, abi, synth, oracle, gen_device):
     data = synth.make_align_batch(batch=32, n_pts=300, n_segs=80, device=gen_device, seed=3000)
     gpu, ref = _run_both(pkg, abi, synth, oracle, data)
     _check(synth, gpu, ref)
-    same = (gpu.iters == ref.iters).all(axis=1)
     np.testing.assert_array_equal(gpu.patch_levels, ref.patch_levels)
-    np.testing.assert_array_equal(gpu.patch_iters[same], ref.patch_iters[same])
+    np.testing.assert_array_equal(gpu.patch_iters, ref.patch_iters)
+
+
+@pytest.mark.parametrize("seed", [4100, 4101, 4102, 4103, 4104, 4105, 4106, 4107])
+def test_align_parity_campaign_1024_pairs_per_seed(pkg, abi, synth, oracle, gen_device, seed):
+    """8 seeds x 1024 C2-shaped pairs = 8192 pairs: every pair inside the tolerance, identical per-level iteration
+    counts, n_tracked, killed segments and status; no chi2-order flag raised (status bits 2-4)."""
+    data = synth.make_align_batch(batch=1024, n_pts=300, n_segs=80, device=gen_device, seed=seed)
+    gpu = pkg.SparseImgAlign(4, 2, 30).run(data)
+    ref = (oracle.ref_align if oracle.ref_available() else oracle.align)(abi, data, n_threads=64)
+    ang, rel = synth.pose_error(gpu.T_cur_w, ref.T_cur_w)
+    assert ang.max() <= ROT_TOL and rel.max() <= TRANS_TOL, (float(ang.max()), float(rel.max()))
+    np.testing.assert_array_equal(gpu.iters, ref.iters)
+    np.testing.assert_array_equal(gpu.n_tracked, ref.n_tracked)
+    np.testing.assert_array_equal(gpu.seg_killed, ref.seg_killed)
+    np.testing.assert_array_equal(gpu.status, ref.status)
 
 
 def test_align_points_only(pkg, abi, synth, oracle, gen_device):
@@ -67,7 +81,8 @@ def test_align_segments_only(pkg, abi, synth, oracle, gen_device):
     moved, _ = synth.pose_error(ref.T_cur_w, data.T_cur_w)
     sane = moved < 0.02
     assert sane.sum() >= 4
-    _check(synth, gpu, ref, exact_iters=False, mask=sane)
+    _check(synth, gpu, ref, exact_iters=True, mask=sane)
+    np.testing.assert_array_equal(gpu.iters, ref.iters)  # same decisions on every pair, also the diverging ones
 
 
 def test_align_converges_to_ground_truth(pkg, synth, gen_device):
@@ -92,7 +107,7 @@ def test_align_edge_cases(pkg, abi, synth, oracle, gen_device):
     data.pt_count[5] = 0   # segments only
     data.seg_count[7] = 0  # points only
     gpu, ref = _run_both(pkg, abi, synth, oracle, data)
-    _check(synth, gpu, ref, exact_iters=False)
+    _check(synth, gpu, ref)
     assert gpu.status[3] == 1 and gpu.n_tracked[3] == 0
     np.testing.assert_array_equal(gpu.T_cur_w[3], data.T_cur_w[3])
 
@@ -104,7 +119,7 @@ def test_align_other_level_ranges(pkg, abi, synth, oracle, gen_device, levels):
                                   device=gen_device, seed=3500 + max_level,
                                   motion_t=0.03 / (1 << (4 - min(4, max_level))), motion_r=0.01 / (1 << (4 - min(4, max_level))))
     gpu, ref = _run_both(pkg, abi, synth, oracle, data, max_level, min_level)
-    _check(synth, gpu, ref, exact_iters=False)
+    _check(synth, gpu, ref)
 
 
 def test_align_three_leg_api_matches_batch_run(pkg, synth, gen_device):
@@ -128,7 +143,7 @@ def test_fp32_weight_matches_reference_expression(pkg):
     bad = C.c_uint64(0)
     n = 1 << 26
     ctx.check(ctx.lib.plsvo_selftest_weight(ctx.handle, n, 12345, C.byref(bad)), "selftest")
-    assert bad.value <= n * 1e-6, f"{bad.value} of {n} weights differ"
+    assert bad.value == 0, f"{bad.value} of {n} weights differ (scalar or packed form)"
 
 
 def test_align_zero_residual_segment_raises_stop(pkg, abi, synth, oracle, gen_device):
@@ -162,7 +177,7 @@ def test_align_720p_combined_config(pkg, abi, synth, oracle, gen_device):
     the finest level is no longer staged in shared memory."""
     data = synth.make_align_batch(cam=synth.HD720, batch=6, n_pts=500, n_segs=150, device=gen_device, seed=3800)
     gpu, ref = _run_both(pkg, abi, synth, oracle, data)
-    _check(synth, gpu, ref, exact_iters=False)
+    _check(synth, gpu, ref)
 
 
 def test_align_segments_longer_than_a_warp(pkg, abi, synth, oracle, gen_device):
@@ -191,7 +206,7 @@ def test_align_segments_longer_than_a_warp(pkg, abi, synth, oracle, gen_device):
     data.seg_length = np.ascontiguousarray(np.linalg.norm(epx - spx, axis=-1))
     gpu, ref = _run_both(pkg, abi, synth, oracle, data, 2, 0)
     assert (data.seg_length / 16 > 32).any()
-    _check(synth, gpu, ref, exact_iters=False)
+    _check(synth, gpu, ref)
 
 
 def test_align_gated_host_pipeline_matches_single_shot(pkg, synth, gen_device, monkeypatch):

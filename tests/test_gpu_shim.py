@@ -97,18 +97,20 @@ def test_reference_typed_frames_through_the_shim_align(shimref, pkg, abi, synth,
     direct = pkg.SparseImgAlign(4, 2, 30).run(d)        # the C ABI called directly on the whole batch
     cpu = shimref.align(abi, d, n_threads=4)            # the oracle
     # same kernel, same arrays — except that the poses make a trip through the reference's SE3 (the quaternion is
-    # re-normalised: last-bit input differences), so agreement is to round-off, not bit for bit; a last-bit difference can
-    # flip one pair's termination test, hence "all but at most one pair" for the exact quantities
-    same = (got.n_tracked == direct.n_tracked) & (got.seg_killed == direct.seg_killed).all(axis=1)
-    assert same.sum() >= d.batch - 1
+    # re-normalised: last-bit input differences), so the poses agree to round-off, not bit for bit.  The kernel's
+    # accept / rollback decisions are taken on the reference's own float chi2, so the exact
+    # quantities agree on every pair.
+    np.testing.assert_array_equal(got.n_tracked, direct.n_tracked)
+    np.testing.assert_array_equal(got.seg_killed, direct.seg_killed)
     ang, rel = synth.pose_error(got.T_cur_w, direct.T_cur_w)
-    assert ang.max() <= 1e-5 and rel.max() <= 1e-4 and np.median(ang) < 1e-8
+    assert ang.max() <= 1e-9 and rel.max() <= 1e-8
     Hs = got.H * (5e-4 * 255 * 255)
-    close = np.array([np.allclose(Hs[b], direct.H[b], rtol=1e-4, atol=1e-5 * np.abs(direct.H[b]).max()) for b in range(d.batch)])
-    assert close.sum() >= d.batch - 1
+    for b in range(d.batch):
+        assert np.allclose(Hs[b], direct.H[b], rtol=1e-6, atol=1e-9 * np.abs(direct.H[b]).max())
     ang, rel = synth.pose_error(got.T_cur_w, cpu.T_cur_w)
     assert ang.max() <= 1e-5 and rel.max() <= 1e-4
-    assert ((got.n_tracked == cpu.n_tracked) & (got.seg_killed == cpu.seg_killed).all(axis=1)).sum() >= d.batch - 1
+    np.testing.assert_array_equal(got.n_tracked, cpu.n_tracked)
+    np.testing.assert_array_equal(got.seg_killed, cpu.seg_killed)
 
 
 @pytest.mark.parametrize("n_ref", [-1, 3])
