@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs per CPU-baseline pass (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only, compact output (tuning)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
+                    help="c2: BASELINE configs[1] + the metric's 80 lines (headline); c4: configs[3], chained align -> pose-opt at 720p")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: patch count x pyramid depth sweep (JSON list)")
+    ap.add_argument("--sweep-out", default="", help="also write the sweep's JSON to this file (rank 0)")
     return ap.parse_args()
 
 
@@ -166,6 +170,39 @@ def subset(data, n_pairs):
     return sub
 
 
+def lean_copy(data, torch):
+    """What the end-to-end leg ships: the finest level used only (coarser levels are halfSample'd on the device) and the
+    distance of every 3-D feature from the reference camera centre instead of its position (include/plsvo_b200.h).
+    Returns (AlignData, bytes, keepalive); every array is pinned."""
+    import copy
+
+    from plsvo_b200 import synth
+
+    lean = copy.copy(data)
+    R, t = synth.pose7_to_Rt(torch.tensor(data.T_ref_w))
+    centre = -(R.transpose(1, 2) @ t[..., None])[..., 0].numpy()  # Frame::pos(), frame.h:131
+    lean.pt_depth = np.ascontiguousarray(np.linalg.norm(data.pt_pos - centre[:, None, :], axis=-1))
+    lean.seg_sdepth = np.ascontiguousarray(np.linalg.norm(data.seg_spos - centre[:, None, :], axis=-1))
+    lean.seg_edepth = np.ascontiguousarray(np.linalg.norm(data.seg_epos - centre[:, None, :], axis=-1))
+    lean.pt_pos = lean.seg_spos = lean.seg_epos = None
+    lean.ref_pyr = {data.min_level: data.ref_pyr[data.min_level]}
+    lean.cur_pyr = {data.min_level: data.cur_pyr[data.min_level]}
+    keep, nbytes = [], 0
+    for name in ("T_ref_w", "T_cur_w", "pt_px", "pt_f", "pt_depth", "seg_spx", "seg_epx", "seg_sf", "seg_ef", "seg_sdepth",
+                 "seg_edepth", "seg_length"):
+        tt = torch.from_numpy(getattr(lean, name)).pin_memory()
+        setattr(lean, name, tt.numpy())
+        keep.append(tt)
+        nbytes += tt.numpy().nbytes
+    for pyr in (lean.ref_pyr, lean.cur_pyr):
+        for l in list(pyr):
+            tt = torch.from_numpy(pyr[l]).pin_memory()
+            pyr[l] = tt.numpy()
+            keep.append(tt)
+            nbytes += tt.numpy().nbytes
+    return lean, nbytes, keep
+
+
 def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
     """pairs/s of the CPU arm with all host threads on the first n_pairs of `data`."""
     align_fn, _, _ = cpu_impl(abi, oracle_lib)
@@ -192,6 +229,280 @@ def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
     return reps * n_pairs / dt, threads, dt, reps
 
 
+def _events(torch, stream, n):
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def poseopt_alg_bytes(pout, n_pts, n_segs):
+    """52 B per (point, pass) + 76 B per (line, pass); passes = MAD + executed GN iterations + outlier pass."""
+    passes = 2.0 + pout.iters[:, 0].astype(np.float64)
+    return float((passes * (52 * n_pts + 76 * n_segs)).sum())
+
+
+def run_c4(args, rank, world, local_rank):
+    """BASELINE configs[3]: combined align + pose path, 720p 5-level pyramid, 500 points + 150 lines, batch sharded across
+    the GPUs.  One step = SparseImgAlign::run followed by pose_optimizer::optimizeGaussNewton on every frame of the
+    rank's batch, the pose staying on the device in between (plsvo_track_*)."""
+    import ctypes as C
+
+    import torch
+
+    import plsvo_b200
+    from plsvo_b200 import abi, synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    n_pts, n_segs = (500, 150) if (args.n_pts, args.n_segs) == (300, 80) else (args.n_pts, args.n_segs)
+    al, po = synth.make_track_batch(cam=synth.HD720, batch=B, n_pts=n_pts, n_segs=n_segs, seed=3000 + 100000 * rank, device=dev)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx = plsvo_b200.Context(local_rank, stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ap, pp = abi.align_params(4, 2, 30), abi.poseopt_params(2.0, 10, -1)
+    ab, keep_a = abi.make_align_batch(al)
+    pb, keep_p = abi.make_poseopt_batch(po)
+    pb.T_f_w = abi._f64p()  # chained: start from the aligned pose on the device
+    ao, pout = abi.AlignOut(B, n_segs), abi.PoseOptOut(B, n_pts, n_segs)
+    L = ctx.lib
+    ctx.check(L.plsvo_track_upload(ctx.handle, C.byref(ab), C.byref(pb)), "track upload")
+    for _ in range(args.warmup):
+        ctx.check(L.plsvo_track_launch(ctx.handle, C.byref(ap), C.byref(pp)), "track launch")
+    ctx.sync()
+    launches0 = ctx.launch_count()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clk = ClockSampler(local_rank)
+    clk.__enter__()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for s0, s1, s2 in ev:
+        flush.fill_(1)
+        s0.record(stream)
+        ctx.check(L.plsvo_align_launch(ctx.handle, C.byref(ap)), "align launch")
+        s1.record(stream)
+        ctx.check(L.plsvo_poseopt_launch(ctx.handle, C.byref(pp)), "poseopt launch")  # reads the aligned poses on the device
+        s2.record(stream)
+    torch.cuda.synchronize(dev)
+    launches = ctx.launch_count() - launches0
+    al_ms = [a.elapsed_time(b) for a, b, _ in ev]
+    po_ms = [b.elapsed_time(c) for _, b, c in ev]
+    total_ms = float(sum(a.elapsed_time(c) for a, _, c in ev))
+    ctx.check(L.plsvo_align_download(ctx.handle, C.byref(ao.struct)), "align download")
+    ctx.check(L.plsvo_poseopt_download(ctx.handle, C.byref(pout.struct)), "poseopt download")
+    t_total = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        from plsvo_b200 import dist as pdist
+
+        all_poses = pdist.gather_rows(pout.T_f_w, world * B, device=dev)
+        assert all_poses.shape == (world * B, 7)
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    max_ms = float(t_total.item())
+    value = world * B * args.steps / (max_ms * 1e-3)
+    # ---- end to end through the chained C-ABI call, pinned host buffers in, host results out ----
+    pins = []
+    for obj, names in ((al, ("T_ref_w", "T_cur_w", "pt_px", "pt_f", "pt_pos", "seg_spx", "seg_epx", "seg_sf", "seg_ef", "seg_spos",
+                             "seg_epos", "seg_length")),
+                       (po, ("pt_f", "pt_pos", "pt_level", "seg_line", "seg_spos", "seg_epos", "seg_level"))):
+        for name in names:
+            tt = torch.from_numpy(getattr(obj, name)).pin_memory()
+            setattr(obj, name, tt.numpy())
+            pins.append(tt)
+    lean, h2d_al, keep_l = lean_copy(al, torch)
+    h2d = h2d_al + sum(getattr(po, n).nbytes for n in ("pt_f", "pt_pos", "pt_level", "seg_line", "seg_spos", "seg_epos", "seg_level"))
+    for _ in range(2):
+        ao_e, po_e = plsvo_b200.api.track(lean, po, ctx=ctx)
+    assert np.array_equal(ao_e.iters, ao.iters) and np.array_equal(po_e.pt_outlier, pout.pt_outlier)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ao_e, po_e = plsvo_b200.api.track(lean, po, ctx=ctx)
+    torch.cuda.synchronize(dev)
+    e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    clk.__exit__(None, None, None)
+    e2e_value = world * B * args.steps / (float(e2e_ms.item()) * 1e-3)
+    d2h = sum(getattr(ao_e, n).nbytes for n in ("T_cur_w", "n_tracked", "H", "seg_killed", "iters", "status", "patch_iters", "patch_levels"))
+    d2h += sum(getattr(po_e, n).nbytes for n in ("T_f_w", "cov", "estimated_scale", "error_init", "error_final", "num_obs_pt",
+                                                 "num_obs_ls", "pt_outlier", "seg_outlier", "iters", "status"))
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        al_bytes = float(ao.patch_iters.astype(np.float64).sum() * BYTES_PATCH_ITER
+                         + ao.patch_levels.astype(np.float64).sum() * BYTES_PATCH_LEVEL + B * BYTES_PAIR_FIXED)
+        po_bytes = poseopt_alg_bytes(pout, n_pts, n_segs)
+        al_s, po_s = float(np.mean(al_ms)) * 1e-3, float(np.mean(po_ms)) * 1e-3
+        cpu = None
+        if not args.no_cpu_baseline:
+            import copy
+
+            import oracle_lib
+
+            n = min(args.cpu_sample or 256, B)
+            sub = subset(al, n)
+            have_ref = oracle_lib.ref_available()
+            align_fn = oracle_lib.ref_align if have_ref else oracle_lib.align
+            po_fn = oracle_lib.ref_poseopt if have_ref else oracle_lib.poseopt
+            hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+            threads = max(1, min(64, hw // 2))
+            psub = copy.copy(po)
+            for name in ("T_f_w", "T_f_w_gt", "pt_f", "pt_pos", "pt_level", "seg_line", "seg_spos", "seg_epos", "seg_level"):
+                setattr(psub, name, np.ascontiguousarray(getattr(po, name)[:n]))
+
+            def chain():
+                ra = align_fn(abi, sub, n_threads=threads)
+                psub.T_f_w = np.ascontiguousarray(ra.T_cur_w)
+                return ra, po_fn(abi, psub, abi.poseopt_params(2.0, 10, -1), n_threads=threads)
+
+            chain()
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 3.0:
+                ra, rp = chain()
+                reps += 1
+            dt = time.perf_counter() - t0
+            ang, rel = synth.pose_error(pout.T_f_w[:n], rp.T_f_w)
+            cpu = {"value": reps * n / dt, "unit": "frames/s", "cores": threads, "kind": "reference" if have_ref else "port",
+                   "sample": f"{n} frames x {reps} passes ({dt:.1f} s): SparseImgAlign::run then optimizeGaussNewton from its result, "
+                             f"{threads} host threads",
+                   "parity_vs_gpu": {"max_rot_rad": float(ang.max()), "max_rel_t": float(rel.max()),
+                                     "frames_within_tol": int(((ang <= 1e-5) & (rel <= 1e-4)).sum()), "frames": n,
+                                     "align_iteration_counts_equal": int((ao.iters[:n] == ra.iters).all(axis=1).sum()),
+                                     "outlier_flags_equal": bool(np.array_equal(pout.pt_outlier[:n], rp.pt_outlier)
+                                                                 and np.array_equal(pout.seg_outlier[:n], rp.seg_outlier))}}
+        line = {
+            "metric": "frames/s through align + pose-opt (720p 5-lvl pyr, 500pt+150ln), chained on the device",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: SparseImgAlign::run (levels 4->2, <=30 GN iters/level) then "
+                                   f"pose_optimizer::optimizeGaussNewton (<=10 iters) from the aligned pose, 1280x720, "
+                                   f"{n_pts} points + {n_segs} line segments per frame", "frames_per_gpu_per_step": B,
+                       "global_batch": B * world, "parallelism": f"dp{world} (independent frames, no data-path collective)",
+                       "l2": "flushed between timed steps (256 MiB write)"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "sparse_img_align_kernel", "achieved": al_bytes / al_s / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": al_bytes / al_s / 1e9 / peak, "traffic": None,
+                         "traffic_source": "not captured for this configuration", "peak_source": peak_src,
+                         "avg_kernel_ms": al_s * 1e3, "share_of_step": al_s / (al_s + po_s),
+                         "second_kernel": {"kernel": "pose_optimizer_kernel", "avg_kernel_ms": po_s * 1e3,
+                                           "achieved": po_bytes / po_s / 1e9, "frac": po_bytes / po_s / 1e9 / peak}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+SWEEP_N = (64, 128, 256, 512, 1024, 2048)
+SWEEP_L = (3, 4, 5, 6)
+
+
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE configs[4]: patch count 64 -> 2048 x pyramid depth 3 -> 6 (max_level = L-1, min_level = max(L-3, 0): the
+    reference's three-level schedule), every cell with pairs/s, the algorithmic roofline fraction, parity
+    against the CPU arm on a sample and that arm's rate.  Under torchrun every rank runs its own batches (weak scaling)."""
+    import torch
+
+    import plsvo_b200
+    from plsvo_b200 import abi, synth
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx = plsvo_b200.Context(local_rank, stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    peak, _ = measured_hbm_peak()
+    cells = []
+    import oracle_lib
+
+    have_ref = oracle_lib.ref_available()
+    align_fn = oracle_lib.ref_align if have_ref else oracle_lib.align
+    hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+    threads = max(1, min(64, hw // 2))
+    for L in SWEEP_L:
+        max_level, min_level = L - 1, max(L - 3, 0)
+        for N in SWEEP_N:
+            n_segs = int(round(N * 80 / 300))
+            B = args.batch if N <= 512 else max(148, args.batch // (N // 512 * 2))
+            shrink = 1 << max(0, 4 - max_level)
+            data = synth.make_align_batch(batch=B, n_pts=N, n_segs=n_segs, max_level=max_level, min_level=min_level,
+                                          seed=7000 + 17 * N + L + 100000 * rank, device=dev, motion_t=0.03 / shrink, motion_r=0.01 / shrink)
+            al = plsvo_b200.SparseImgAlign(max_level, min_level, 30, ctx=ctx)
+            cell = {"n_pts": N, "n_segs": n_segs, "pyramid_levels": L, "max_level": max_level, "min_level": min_level, "pairs_per_gpu": B}
+            try:
+                al.upload(data)
+                for _ in range(2):
+                    al.launch()
+                ctx.sync()
+                ts = []
+                for _ in range(max(3, args.steps // 2)):
+                    flush.fill_(1)
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(stream)
+                    al.launch()
+                    e.record(stream)
+                    torch.cuda.synchronize(dev)
+                    ts.append(s.elapsed_time(e))
+                out = al.download()
+                ms = float(np.median(ts))
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                if dist:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_max = float(t.item())
+                alg = float(out.patch_iters.astype(np.float64).sum() * BYTES_PATCH_ITER
+                            + out.patch_levels.astype(np.float64).sum() * BYTES_PATCH_LEVEL + B * BYTES_PAIR_FIXED)
+                cell.update({"ms_per_step": ms_max, "pairs_per_s": world * B / (ms_max * 1e-3), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
+                             "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "mean_gn_passes": float(out.iters.sum(axis=1).mean()),
+                             "status_flags": int((out.status >> 2).astype(bool).sum())})
+                if rank == 0:
+                    n = min(96 if N <= 512 else 48, B)
+                    sub = subset(data, n)
+                    align_fn(abi, sub, n_threads=threads)
+                    t0 = time.perf_counter()
+                    ref = align_fn(abi, sub, n_threads=threads)
+                    dt = time.perf_counter() - t0
+                    ang, rel = synth.pose_error(out.T_cur_w[:n], ref.T_cur_w)
+                    cell["cpu"] = {"pairs_per_s": n / dt, "threads": threads, "kind": "reference" if have_ref else "port", "pairs": n}
+                    cell["parity"] = {"pairs": n, "within_tol": int(((ang <= 1e-5) & (rel <= 1e-4)).sum()),
+                                      "iteration_counts_equal": int((out.iters[:n] == ref.iters).all(axis=1).sum()),
+                                      "max_rot_rad": float(ang.max()), "max_rel_t": float(rel.max())}
+            except Exception as ex:
+                cell["error"] = str(ex)
+            cells.append(cell)
+            if rank == 0:
+                print(json.dumps(cell), file=sys.stderr, flush=True)
+            del data, al
+    if rank == 0:
+        doc = {"sweep": "BASELINE configs[4]: patch count x pyramid depth", "n_gpus": world, "unit": "pairs/s",
+               "peak_GBps": peak, "cells": cells}
+        print(json.dumps(doc))
+        if args.sweep_out:
+            json.dump(doc, open(args.sweep_out, "w"), indent=1)
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -202,6 +513,10 @@ def main():
     import plsvo_b200
     from plsvo_b200 import abi, synth
 
+    if args.impl != "reference" and args.sweep:
+        return run_sweep(args, rank, world, local_rank)
+    if args.impl != "reference" and args.config == "c4":
+        return run_c4(args, rank, world, local_rank)
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -331,9 +646,14 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- end-to-end leg: host buffers -> C ABI -> host results, every step ----
+    # ---- end-to-end leg: pinned host buffers -> C ABI -> host results, every step ----
+    # ships what the reference-facing call needs at minimum (lean_copy): finest used level + feature depths
+    data_full = data
+    data, h2d, keep_lean = lean_copy(data_full, torch)
     for _ in range(2):
-        al.run(data)
+        out_e2e = al.run(data)
+    assert np.array_equal(out_e2e.iters, out.iters), "lean host inputs changed the result"
+    data_lean = data
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -350,6 +670,7 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * B * args.steps / (float(e2e_ms.item()) * 1e-3)
     clk.__exit__(None, None, None)
+    data = data_full
 
     # ---- roofline of the alignment kernel (the only kernel in the step) ----
     alg_bytes = float(out.patch_iters.astype(np.float64).sum() * BYTES_PATCH_ITER
@@ -383,11 +704,36 @@ def main():
             pts.append(s_.elapsed_time(e_))
         ctx.check(ctx.lib.plsvo_poseopt_download(ctx.handle, C.byref(pout.struct)), "poseopt download")
         pms = float(np.median(pts))
-        passes = 2.0 + pout.iters[:, 0].astype(np.float64)
-        pbytes = float((passes * (52 * pdata.n_pts + 76 * pdata.n_segs)).sum())
+        pbytes = poseopt_alg_bytes(pout, pdata.n_pts, pdata.n_segs)
+        # end to end through the host-buffer call, and the CPU arm with parity on the same frames (rank 0)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.check(ctx.lib.plsvo_poseopt_batch_run(ctx.handle, C.byref(pbatch), C.byref(pparams), C.byref(pout.struct)), "poseopt run")
+        pe2e = 3 * pdata.batch / (time.perf_counter() - t0)
+        pcpu = None
+        if rank == 0 and not args.no_cpu_baseline:
+            import oracle_lib
+
+            have_ref = oracle_lib.ref_available()
+            pfn = oracle_lib.ref_poseopt if have_ref else oracle_lib.poseopt
+            hw = max(1, oracle_lib.load(abi).plsvo_oracle_hardware_threads())
+            pth = max(1, min(64, hw // 2))
+            pfn(abi, pdata, pparams, n_threads=pth)
+            t0 = time.perf_counter()
+            pref = pfn(abi, pdata, pparams, n_threads=pth)
+            pdt = time.perf_counter() - t0
+            pang, prel = synth.pose_error(pout.T_f_w, pref.T_f_w)
+            pcpu = {"value": pdata.batch / pdt, "unit": "frames/s", "cores": pth, "kind": "reference" if have_ref else "port",
+                    "sample": f"{pdata.batch} frames, one pass",
+                    "parity_vs_gpu": {"max_rot_rad": float(pang.max()), "max_rel_t": float(prel.max()),
+                                      "frames_within_tol": int(((pang <= 1e-5) & (prel <= 1e-4)).sum()), "frames": int(pdata.batch),
+                                      "outlier_flags_equal": bool(np.array_equal(pout.pt_outlier, pref.pt_outlier)
+                                                                  and np.array_equal(pout.seg_outlier, pref.seg_outlier))}}
         poseopt = {"metric": "pose-optimiser frames/s (300 pts + 80 lines, <=10 GN iters, B=4096)",
                    "value": pdata.batch / (pms * 1e-3), "unit": "frames/s", "ms_per_batch": pms,
                    "note": "includes the per-launch clearing of 6 small output arrays (memsets)",
+                   "e2e": {"value": pe2e, "unit": "frames/s", "note": "plsvo_poseopt_batch_run from pageable host arrays, results to host"},
+                   "cpu_baseline": pcpu,
                    "roofline": {"bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "unit": "GB/s",
                                 "frac": pbytes / (pms * 1e-3) / 1e9 / measured_hbm_peak()[0]}}
     except Exception as ex:  # secondary number: never take the headline line down

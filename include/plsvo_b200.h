@@ -78,6 +78,15 @@ typedef struct plsvo_align_params {
  * Images: for pyramid level l in [min_level,max_level], image of pair b starts at
  * ref_img[l] + b*img_stride[l] with row pitch img_pitch[l] bytes and (width>>l) x (height>>l)
  * u8 pixels (Frame::img_pyr_, include/plsvo/frame.h:64).  Levels outside the range may be NULL.
+ * Levels ABOVE the lowest provided one may also be NULL inside the range: they are then derived on the device by
+ * repeated vk::halfSample (the truncating 2x2 mean of frame_utils::createImgPyramid, src/frame.cpp:171-180 —
+ * bit-identical to the host pyramid), which saves their host->device copy; this needs 16-byte aligned, 16-byte
+ * pitched rows of the source level.
+ *
+ * The reference only ever uses the distance of a 3-D feature from the reference camera centre
+ * (`(pos_ - ref_pos).norm()`, sparse_img_align.cpp:229,337-340).  A caller that already holds these distances may pass
+ * them in pt_depth / seg_sdepth / seg_edepth and leave pt_pos / seg_spos / seg_epos NULL (16 bytes less per point,
+ * 32 per segment over PCIe).
  */
 typedef struct plsvo_align_batch {
   int32_t batch;   /* B */
@@ -109,6 +118,10 @@ typedef struct plsvo_align_batch {
   const double* seg_epos;   /* [B][n_segs][3] LineFeat::feat3D->epos_ */
   const double* seg_length; /* [B][n_segs]    LineFeat::length */
   const uint8_t* seg_valid; /* [B][n_segs] or NULL: feat3D != NULL */
+
+  const double* pt_depth;   /* [B][n_pts]  or NULL: |pos_ - ref_frame->pos()| (then pt_pos may be NULL) */
+  const double* seg_sdepth; /* [B][n_segs] or NULL: |spos_ - ref_frame->pos()| (then seg_spos may be NULL) */
+  const double* seg_edepth; /* [B][n_segs] or NULL: |epos_ - ref_frame->pos()| (then seg_epos may be NULL) */
 } plsvo_align_batch;
 
 /* Caller-allocated outputs; any pointer may be NULL to skip that output. */
@@ -205,6 +218,19 @@ int plsvo_poseopt_launch(plsvo_ctx* ctx, const plsvo_poseopt_params* params);
 int plsvo_poseopt_download(plsvo_ctx* ctx, const plsvo_poseopt_result* out);
 int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* batch,
                             const plsvo_poseopt_params* params, const plsvo_poseopt_result* out);
+
+/* The two hot-path calls of FrameHandlerMono::processFrame back to back (src/frame_handler_mono.cpp:272-274 sparse
+ * image alignment, :327-329 pose optimisation) for a batch of frames, with the pose staying on the device in between:
+ * frame b of `po_batch` starts from the alignment result of pair b of `al_batch` when po_batch->T_f_w is NULL
+ * (otherwise from the poses given).  `al_out` may be NULL.  Equivalent to plsvo_align_batch_run followed by
+ * plsvo_poseopt_batch_run with T_f_w = the aligned poses, minus one device->host->device trip and one sync.
+ * plsvo_track_upload / plsvo_track_launch are its two device-side legs (results: plsvo_align_download and
+ * plsvo_poseopt_download). */
+int plsvo_track_upload(plsvo_ctx* ctx, const plsvo_align_batch* al_batch, const plsvo_poseopt_batch* po_batch);
+int plsvo_track_launch(plsvo_ctx* ctx, const plsvo_align_params* al_params, const plsvo_poseopt_params* po_params);
+int plsvo_track_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* al_batch, const plsvo_align_params* al_params,
+                          const plsvo_poseopt_batch* po_batch, const plsvo_poseopt_params* po_params,
+                          const plsvo_align_result* al_out, const plsvo_poseopt_result* po_out);
 
 /* ------------------------------------------------------------------------------------------
  * Image pyramid (SURVEY.md §8f "next", rank 2): frame_utils::createImgPyramid, src/frame.cpp:171-180,

@@ -76,6 +76,9 @@ class AlignBatch(C.Structure):
         ("seg_epos", _f64p),
         ("seg_length", _f64p),
         ("seg_valid", _u8p),
+        ("pt_depth", _f64p),
+        ("seg_sdepth", _f64p),
+        ("seg_edepth", _f64p),
     ]
 
 
@@ -265,7 +268,8 @@ def make_align_batch(d):
     b.pt_count = _ptr(d.pt_count, np.int32)
     b.pt_px = _ptr(d.pt_px, np.float64)
     b.pt_f = _ptr(d.pt_f, np.float64)
-    b.pt_pos = _ptr(d.pt_pos, np.float64)
+    b.pt_pos = _ptr(getattr(d, "pt_pos", None), np.float64)
+    b.pt_depth = _ptr(getattr(d, "pt_depth", None), np.float64)
     b.pt_valid = _ptr(d.pt_valid, np.uint8)
     b.seg_count = _ptr(d.seg_count, np.int32)
     if d.n_segs > 0:
@@ -273,8 +277,10 @@ def make_align_batch(d):
         b.seg_epx = _ptr(d.seg_epx, np.float64)
         b.seg_sf = _ptr(d.seg_sf, np.float64)
         b.seg_ef = _ptr(d.seg_ef, np.float64)
-        b.seg_spos = _ptr(d.seg_spos, np.float64)
-        b.seg_epos = _ptr(d.seg_epos, np.float64)
+        b.seg_spos = _ptr(getattr(d, "seg_spos", None), np.float64)
+        b.seg_epos = _ptr(getattr(d, "seg_epos", None), np.float64)
+        b.seg_sdepth = _ptr(getattr(d, "seg_sdepth", None), np.float64)
+        b.seg_edepth = _ptr(getattr(d, "seg_edepth", None), np.float64)
         b.seg_length = _ptr(d.seg_length, np.float64)
         b.seg_valid = _ptr(d.seg_valid, np.uint8)
     return b, keep
@@ -319,8 +325,10 @@ def make_poseopt_batch(d):
     b.seg_count = _ptr(d.seg_count, np.int32)
     if d.n_segs > 0:
         b.seg_line = _ptr(d.seg_line, np.float64)
-        b.seg_spos = _ptr(d.seg_spos, np.float64)
-        b.seg_epos = _ptr(d.seg_epos, np.float64)
+        b.seg_spos = _ptr(getattr(d, "seg_spos", None), np.float64)
+        b.seg_epos = _ptr(getattr(d, "seg_epos", None), np.float64)
+        b.seg_sdepth = _ptr(getattr(d, "seg_sdepth", None), np.float64)
+        b.seg_edepth = _ptr(getattr(d, "seg_edepth", None), np.float64)
         b.seg_level = _ptr(d.seg_level, np.int32)
         b.seg_valid = _ptr(d.seg_valid, np.uint8)
     return b, [d]
@@ -381,6 +389,10 @@ ABI_SYMBOLS = [
     ("plsvo_poseopt_launch", C.c_int, [C.c_void_p, _P(PoseOptParams)]),
     ("plsvo_poseopt_download", C.c_int, [C.c_void_p, _P(PoseOptResult)]),
     ("plsvo_poseopt_batch_run", C.c_int, [C.c_void_p, _P(PoseOptBatch), _P(PoseOptParams), _P(PoseOptResult)]),
+    ("plsvo_track_upload", C.c_int, [C.c_void_p, _P(AlignBatch), _P(PoseOptBatch)]),
+    ("plsvo_track_launch", C.c_int, [C.c_void_p, _P(AlignParams), _P(PoseOptParams)]),
+    ("plsvo_track_batch_run", C.c_int, [C.c_void_p, _P(AlignBatch), _P(AlignParams), _P(PoseOptBatch), _P(PoseOptParams),
+                                        _P(AlignResult), _P(PoseOptResult)]),
     ("plsvo_pyramid_batch_run", C.c_int, [C.c_void_p, _P(PyramidBatch), _P(PyramidResult)]),
     ("plsvo_align2d_batch_run", C.c_int, [C.c_void_p, _P(Align2DBatch), _P(Align2DResult)]),
     ("plsvo_align1d_batch_run", C.c_int, [C.c_void_p, _P(Align1DBatch), _P(Align1DResult)]),

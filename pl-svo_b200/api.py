@@ -144,6 +144,26 @@ class pose_optimizer:
         return out
 
 
+def track(align_data, poseopt_data, max_level: int = 4, min_level: int = 2, n_iter: int = 30, reproj_thresh: float = 2.0,
+          po_n_iter: int = 10, po_n_iter_ref: int | None = None, chained: bool = True, ctx: Context | None = None):
+    """FrameHandlerMono::processFrame's two hot-path calls back to back (src/frame_handler_mono.cpp:272-274, :327-329):
+    SparseImgAlign::run on every pair, then pose_optimizer::optimizeGaussNewton on every frame, the pose staying on the
+    device in between (chained=True: the pose optimiser starts from the aligned pose of the same batch index).
+    Returns (AlignOut, PoseOptOut)."""
+    ctx = ctx or default_context()
+    ap = abi.align_params(max_level, min_level, n_iter)
+    pp = abi.poseopt_params(reproj_thresh, po_n_iter, -1 if po_n_iter_ref is None else po_n_iter_ref)
+    ab, keep_a = abi.make_align_batch(align_data)
+    pb, keep_p = abi.make_poseopt_batch(poseopt_data)
+    if chained:
+        pb.T_f_w = abi._f64p()
+    ao = abi.AlignOut(align_data.batch, align_data.n_segs)
+    po = abi.PoseOptOut(poseopt_data.batch, poseopt_data.n_pts, poseopt_data.n_segs)
+    ctx.check(ctx.lib.plsvo_track_batch_run(ctx.handle, C.byref(ab), C.byref(ap), C.byref(pb), C.byref(pp), C.byref(ao.struct),
+                                            C.byref(po.struct)), "plsvo_track_batch_run")
+    return ao, po
+
+
 def createImgPyramid(img_level_0, n_levels: int, ctx: Context | None = None):
     """Batched frame_utils::createImgPyramid (src/frame.cpp:171-180): u8 images [B,H,W] -> list of levels
     (level 0 is the input array itself), each the truncating 2x2 half-sample of the previous one."""

@@ -603,16 +603,44 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
       for (int i = 0; i < 36; ++i) ctl->H_last[i] = 0.0;
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) ctl->iters_level[l] = 0;
     }
+    // Host-buffer pipeline with lean inputs: pyramid levels above a.derive_from were not shipped; this CTA forms them
+    // for its own pair by vk::halfSample (truncating 2x2 mean, frame_utils::createImgPyramid, src/frame.cpp:171-180)
+    // right where the pair's finest level has just landed.  (A separate pyramid kernel could not become resident next
+    // to the persistent grid that is waiting for it.)
+    if (a.derive_from >= 0) {
+      for (int l = a.derive_from + 1; l <= a.max_level; ++l) {
+        const int cols = a.width >> l, rows = a.height >> l;
+        const int pin = (int)a.pitch[l - 1], pout = (int)a.pitch[l];
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint8_t* src = (which ? a.cur_img[l - 1] : a.ref_img[l - 1]) + (size_t)b * a.stride[l - 1];
+          uint8_t* dst = const_cast<uint8_t*>(which ? a.cur_img[l] : a.ref_img[l]) + (size_t)b * a.stride[l];
+          for (int y = warp; y < rows; y += NW) {
+            const uint8_t* r0 = src + (size_t)(2 * y) * pin;
+            for (int x = lane; x < cols; x += 32)
+              dst[(size_t)y * pout + x] = (uint8_t)(((int)r0[2 * x] + (int)r0[2 * x + 1] + (int)r0[pin + 2 * x] + (int)r0[pin + 2 * x + 1]) >> 2);
+          }
+        }
+        __syncthreads();  // level l is the source of level l+1
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies of the level loop read what was written here
+      __syncthreads();
+    }
     __syncthreads();
     const double rpx = ctl->ref_pos[0], rpy = ctl->ref_pos[1], rpz = ctl->ref_pos[2];
 
     // per-pair point setup: xyz_ref = f * |pos - ref_pos| (:229-230), kept as (X/Z, Y/Z, 1/Z); visibility cleared
     for (int i = tid; i < np; i += NT) {
       pt_vis[i] = 0;
-      const double* pos = a.pt_pos + (po + i) * 3;
       const double* f = a.pt_f + (po + i) * 3;
-      const double dx = pos[0] - rpx, dy = pos[1] - rpy, dz = pos[2] - rpz;
-      const double depth = sqrt(dx * dx + dy * dy + dz * dz);
+      double depth;
+      if (a.pt_depth) {
+        depth = a.pt_depth[po + i];
+      } else {
+        const double* pos = a.pt_pos + (po + i) * 3;
+        const double dx = pos[0] - rpx, dy = pos[1] - rpy, dz = pos[2] - rpz;
+        depth = sqrt(dx * dx + dy * dy + dz * dz);
+      }
       const double zi = 1.0 / (f[2] * depth);  // z_inv of Frame::jacobian_xyz2uv (frame.h:144), constant per pair
       xyz[0 * MP + i] = (f[0] * depth) * zi;
       xyz[1 * MP + i] = (f[1] * depth) * zi;
@@ -715,14 +743,23 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
         const double nm1 = (double)(unsigned long long)(N - 1);
         const double inc2d0 = dif[0] * dscale / nm1, inc2d1 = dif[1] * dscale / nm1;
         double px0 = spx[0] * dscale, px1 = spx[1] * dscale;
-        const double* sp = a.seg_spos + (so + j) * 3;
-        const double* ep = a.seg_epos + (so + j) * 3;
         const double* sf = a.seg_sf + (so + j) * 3;
         const double* ef = a.seg_ef + (so + j) * 3;
-        double d0 = sp[0] - rpx, d1 = sp[1] - rpy, d2 = sp[2] - rpz;
-        const double p_depth = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-        d0 = ep[0] - rpx, d1 = ep[1] - rpy, d2 = ep[2] - rpz;
-        const double q_depth = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        double p_depth, q_depth;
+        if (a.seg_sdepth) {
+          p_depth = a.seg_sdepth[so + j];
+        } else {
+          const double* sp = a.seg_spos + (so + j) * 3;
+          const double d0 = sp[0] - rpx, d1 = sp[1] - rpy, d2 = sp[2] - rpz;
+          p_depth = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        }
+        if (a.seg_edepth) {
+          q_depth = a.seg_edepth[so + j];
+        } else {
+          const double* ep = a.seg_epos + (so + j) * 3;
+          const double d0 = ep[0] - rpx, d1 = ep[1] - rpy, d2 = ep[2] - rpz;
+          q_depth = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        }
         const double P0 = sf[0] * p_depth, P1 = sf[1] * p_depth, P2 = sf[2] * p_depth;
         const double Q0 = ef[0] * q_depth, Q1 = ef[1] * q_depth, Q2 = ef[2] * q_depth;
         const double i0 = (Q0 - P0) / nm1, i1 = (Q1 - P1) / nm1, i2 = (Q2 - P2) / nm1;

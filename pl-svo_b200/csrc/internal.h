@@ -38,6 +38,9 @@ struct AlignArgs {
   const double* seg_epos;
   const double* seg_length;
   const uint8_t* seg_valid;
+  const double* pt_depth;    // optional: |pos - ref_pos| per point (then pt_pos may be null)
+  const double* seg_sdepth;  // optional: per segment start / end point
+  const double* seg_edepth;
   // outputs
   double* out_T;
   long long* out_n_tracked;
@@ -61,6 +64,7 @@ struct AlignArgs {
   double* ws_segpx;     // [grid][2][max_seg_patches] 2-D centre of every segment sample (precompute only)
   double* ws_rec;       // [grid][5][rec_cap*threads] parked in-patch sums of segments longer than a warp
   int rec_cap;          // 32-sample trips of the longest segment, <= 32
+  int derive_from;      // >= 0: the CTA forms levels (derive_from, max_level] of its pair by halfSample (gated pipeline)
   float one;            // 1.0f, deliberately a run-time value (device_math.cuh: add2_after_mul)
 };
 

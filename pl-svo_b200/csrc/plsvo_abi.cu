@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -52,6 +53,10 @@ struct plsvo_ctx_impl {
   std::vector<int> seg_patch_bound;  // per level: max over pairs of the number of segment samples
   std::vector<int> seg_slot_bound;   // per level: max over pairs of the lane slots of the segment groups
   std::vector<int> seg_maxN;         // per level: most samples of any one segment
+  DevBuf d_ref_der, d_cur_der;       // pyramid levels derived on the device (vk::halfSample) instead of uploaded
+  int der_src = -1, der_top = -1;    // derived levels are (der_src, der_top], built from uploaded level der_src
+  bool lvl_uploaded[PLSVO_MAX_LEVELS] = {false};
+  DevBuf d_pt_depth, d_seg_sdepth, d_seg_edepth;
   DevBuf d_ref_img, d_cur_img, d_T_ref, d_T_cur, d_pt_count, d_pt_px, d_pt_f, d_pt_pos, d_pt_valid, d_seg_count,
       d_seg_spx, d_seg_epx, d_seg_sf, d_seg_ef, d_seg_spos, d_seg_epos, d_seg_length, d_seg_valid;
   DevBuf d_out_T, d_out_ntr, d_out_H, d_out_killed, d_out_iters, d_out_status, d_out_pi, d_out_pl, d_counter,
@@ -192,7 +197,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
-                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_ws_segpx,  &c->d_ws_rec,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_ref_der,   &c->d_cur_der,   &c->d_pt_depth,  &c->d_seg_sdepth, &c->d_seg_edepth, &c->d_ws_segpx,  &c->d_ws_rec,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
                     &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->m_ref_img,   &c->m_cur_img,   &c->m_T_ref,     &c->m_T_cur,
                     &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
                     &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
@@ -323,9 +328,10 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0 || h->n_segs > 32767)
       return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
     if (!h->T_ref_w || !h->T_cur_w) return fail(c, PLSVO_ERR_INVALID, "T_ref_w/T_cur_w missing");
-    if (h->n_pts > 0 && (!h->pt_px || !h->pt_f || !h->pt_pos)) return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
-    if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || !h->seg_sf || !h->seg_ef || !h->seg_spos || !h->seg_epos ||
-                          !h->seg_length))
+    if (h->n_pts > 0 && (!h->pt_px || !h->pt_f || (!h->pt_pos && !h->pt_depth)))
+      return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
+    if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || !h->seg_sf || !h->seg_ef || (!h->seg_spos && !h->seg_sdepth) ||
+                          (!h->seg_epos && !h->seg_edepth) || !h->seg_length))
       return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
     if (h->cam.width <= 0 || h->cam.height <= 0) return fail(c, PLSVO_ERR_INVALID, "camera size");
     CK(cudaSetDevice(c->device));
@@ -339,7 +345,9 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       a.ref_img[l] = a.cur_img[l] = nullptr;
       a.pitch[l] = 0, a.stride[l] = 0;
       c->level_off[l] = 0;
+      c->lvl_uploaded[l] = false;
       if (!h->ref_img[l] || !h->cur_img[l]) continue;
+      c->lvl_uploaded[l] = true;
       const int cols = h->cam.width >> l, rows = h->cam.height >> l;
       if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
       if (h->img_pitch[l] < (size_t)cols) return fail(c, PLSVO_ERR_INVALID, "img_pitch smaller than the level width");
@@ -358,6 +366,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     }
     CK(ensure(c->d_ref_img, total + 256));
     CK(ensure(c->d_cur_img, total + 256));
+    c->der_src = c->der_top = -1;
     size_t stage = 0;
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
       if (a.pitch[l] && h->img_pitch[l] != a.pitch[l]) stage = std::max(stage, 2 * h->img_stride[l] * B);
@@ -365,7 +374,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   }
   const size_t nb = b1 - b0;
   for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
-    if (!a.pitch[l]) continue;
+    if (!c->lvl_uploaded[l]) continue;
     const int cols = h->cam.width >> l, rows = h->cam.height >> l;
     uint8_t* dr = static_cast<uint8_t*>(c->d_ref_img.p) + c->level_off[l];
     uint8_t* dc = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
@@ -404,15 +413,18 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   CK(up_range(c->d_pt_count, h->pt_count, 1, B, b0, b1, pick_copy_stream(c, s), &a.pt_count, prepare));
   CK(up_range(c->d_pt_px, h->pt_px, np * 2, B, b0, b1, pick_copy_stream(c, s), &a.pt_px, prepare));
   CK(up_range(c->d_pt_f, h->pt_f, np * 3, B, b0, b1, pick_copy_stream(c, s), &a.pt_f, prepare));
-  CK(up_range(c->d_pt_pos, h->pt_pos, np * 3, B, b0, b1, pick_copy_stream(c, s), &a.pt_pos, prepare));
+  CK(up_range(c->d_pt_pos, h->pt_depth ? nullptr : h->pt_pos, np * 3, B, b0, b1, pick_copy_stream(c, s), &a.pt_pos, prepare));
+  CK(up_range(c->d_pt_depth, h->pt_depth, np, B, b0, b1, pick_copy_stream(c, s), &a.pt_depth, prepare));
   CK(up_range(c->d_pt_valid, h->pt_valid, np, B, b0, b1, pick_copy_stream(c, s), &a.pt_valid, prepare));
   CK(up_range(c->d_seg_count, h->seg_count, 1, B, b0, b1, pick_copy_stream(c, s), &a.seg_count, prepare));
   CK(up_range(c->d_seg_spx, h->seg_spx, ns * 2, B, b0, b1, pick_copy_stream(c, s), &a.seg_spx, prepare));
   CK(up_range(c->d_seg_epx, h->seg_epx, ns * 2, B, b0, b1, pick_copy_stream(c, s), &a.seg_epx, prepare));
   CK(up_range(c->d_seg_sf, h->seg_sf, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_sf, prepare));
   CK(up_range(c->d_seg_ef, h->seg_ef, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_ef, prepare));
-  CK(up_range(c->d_seg_spos, h->seg_spos, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_spos, prepare));
-  CK(up_range(c->d_seg_epos, h->seg_epos, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_epos, prepare));
+  CK(up_range(c->d_seg_spos, h->seg_sdepth ? nullptr : h->seg_spos, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_spos, prepare));
+  CK(up_range(c->d_seg_epos, h->seg_edepth ? nullptr : h->seg_epos, ns * 3, B, b0, b1, pick_copy_stream(c, s), &a.seg_epos, prepare));
+  CK(up_range(c->d_seg_sdepth, h->seg_sdepth, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_sdepth, prepare));
+  CK(up_range(c->d_seg_edepth, h->seg_edepth, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_edepth, prepare));
   CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_length, prepare));
   CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_valid, prepare));
   }  // mode != 3
@@ -432,26 +444,51 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   c->seg_slot_bound.assign(PLSVO_MAX_LEVELS, 0);
   c->seg_maxN.assign(PLSVO_MAX_LEVELS, 0);
   if (h->n_segs > 0) {
-    for (size_t b = 0; b < B; ++b) {
-      const int nsb = h->seg_count ? h->seg_count[b] : h->n_segs;
-      int sum[PLSVO_MAX_LEVELS] = {0}, slots[PLSVO_MAX_LEVELS] = {0};
-      for (int j = 0; j < nsb; ++j) {
-        const size_t k = b * h->n_segs + j;
-        const int n0 = host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], 0);
+    // a few host threads: the sizing sits between the enqueued copies and the kernel launch of the host-buffer path
+    struct Bounds {
+      int patches[PLSVO_MAX_LEVELS], slots[PLSVO_MAX_LEVELS], maxN[PLSVO_MAX_LEVELS];
+    };
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, B * (size_t)h->n_segs / 8192));
+    std::vector<Bounds> part(nt);
+    auto work = [&](int t) {
+      Bounds bd;
+      memset(&bd, 0, sizeof bd);
+      for (size_t b = B * t / nt; b < B * (t + 1) / nt; ++b) {
+        const int nsb = h->seg_count ? h->seg_count[b] : h->n_segs;
+        int sum[PLSVO_MAX_LEVELS] = {0}, slots[PLSVO_MAX_LEVELS] = {0};
+        for (int j = 0; j < nsb; ++j) {
+          const size_t k = b * h->n_segs + j;
+          const int n0 = host_seg_samples(h->seg_spx + 2 * k, h->seg_epx + 2 * k, h->seg_length[k], 0);
+          for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+            const int N = 1 + ((n0 - 1) >> l);
+            int g = 1;
+            while (g < N && g < 32) g <<= 1;
+            sum[l] += N;
+            slots[l] += g;
+            bd.maxN[l] = std::max(bd.maxN[l], N);
+          }
+        }
         for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
-          const int N = 1 + ((n0 - 1) >> l);
-          int g = 1;
-          while (g < N && g < 32) g <<= 1;
-          sum[l] += N;
-          slots[l] += g;
-          c->seg_maxN[l] = std::max(c->seg_maxN[l], N);
+          bd.patches[l] = std::max(bd.patches[l], sum[l]);
+          bd.slots[l] = std::max(bd.slots[l], slots[l]);
         }
       }
-      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
-        c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], sum[l]);
-        c->seg_slot_bound[l] = std::max(c->seg_slot_bound[l], slots[l]);
-      }
+      part[t] = bd;
+    };
+    if (nt == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+      work(0);
+      for (auto& th : pool) th.join();
     }
+    for (const Bounds& bd : part)
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+        c->seg_patch_bound[l] = std::max(c->seg_patch_bound[l], bd.patches[l]);
+        c->seg_slot_bound[l] = std::max(c->seg_slot_bound[l], bd.slots[l]);
+        c->seg_maxN[l] = std::max(c->seg_maxN[l], bd.maxN[l]);
+      }
   }
   // all outputs live in one device block so that the download is a single D2H into pinned staging
   {
@@ -490,6 +527,77 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   return PLSVO_OK;
 }
 
+// Pyramid levels that were not uploaded are derived on the device from the highest uploaded level below them by
+// repeated vk::halfSample (pyramid_kernel.cu; bit-identical to frame_utils::createImgPyramid), for pairs [b0,b1).
+// prepare: size the buffers and describe the derived levels in AlignArgs (once per batch).
+int align_derive_levels(plsvo_ctx_impl* c, int min_level, int max_level, size_t b0, size_t b1, cudaStream_t s, bool prepare,
+                        bool in_kernel = false) {
+  AlignArgs& a = c->aa;
+  a.derive_from = -1;
+  int first_missing = -1;
+  for (int l = min_level; l <= max_level; ++l)
+    if (!c->lvl_uploaded[l]) {
+      first_missing = l;
+      break;
+    }
+  if (first_missing < 0) return PLSVO_OK;
+  int src = -1;
+  for (int l = first_missing - 1; l >= 0; --l)
+    if (c->lvl_uploaded[l]) {
+      src = l;
+      break;
+    }
+  if (src < 0) return fail(c, PLSVO_ERR_INVALID, "a pyramid level in [min_level,max_level] was not uploaded and no lower level is there to derive it from");
+  for (int l = first_missing; l <= max_level; ++l)
+    if (c->lvl_uploaded[l]) return fail(c, PLSVO_ERR_INVALID, "derived pyramid levels must be contiguous above the uploaded ones");
+  if (a.pitch[src] % 16 != 0 || a.stride[src] % 16 != 0)
+    return fail(c, PLSVO_ERR_INVALID, "deriving pyramid levels on the device needs 16-byte pitched rows of the source level");
+  const size_t B = (size_t)a.B;
+  if (prepare || c->der_src != src || c->der_top < max_level) {
+    size_t total = 0, off[PLSVO_MAX_LEVELS] = {0};
+    for (int l = src + 1; l <= max_level; ++l) {
+      const int cols = a.width >> l, rows = a.height >> l;
+      if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
+      a.pitch[l] = (uint32_t)((cols + 15) / 16 * 16);
+      a.stride[l] = (size_t)rows * a.pitch[l];
+      off[l] = total;
+      total += (a.stride[l] * B + 255) / 256 * 256;
+    }
+    CK(ensure(c->d_ref_der, total + 256));
+    CK(ensure(c->d_cur_der, total + 256));
+    for (int l = src + 1; l <= max_level; ++l) {
+      a.ref_img[l] = static_cast<uint8_t*>(c->d_ref_der.p) + off[l];
+      a.cur_img[l] = static_cast<uint8_t*>(c->d_cur_der.p) + off[l];
+    }
+    c->der_src = src, c->der_top = max_level;
+  }
+  if (in_kernel) {  // the persistent alignment kernel derives the levels pair by pair (gated host pipeline)
+    a.derive_from = src;
+    return PLSVO_OK;
+  }
+  if (b1 <= b0) return PLSVO_OK;
+  for (int which = 0; which < 2; ++which) {
+    PyramidArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.B = (int)(b1 - b0), pa.width = a.width >> src, pa.height = a.height >> src, pa.n_levels = max_level - src + 1;
+    for (int l = src; l <= max_level; ++l) {
+      const uint8_t* base = which ? a.cur_img[l] : a.ref_img[l];
+      pa.level[l - src] = const_cast<uint8_t*>(base) + b0 * a.stride[l];
+      pa.pitch[l - src] = a.pitch[l];
+      pa.stride[l - src] = a.stride[l];
+    }
+    // the kernel indexes images with blockIdx.z
+    for (int z0 = 0; z0 < pa.B; z0 += 32768) {
+      PyramidArgs q = pa;
+      q.B = std::min(32768, pa.B - z0);
+      for (int k = 0; k < pa.n_levels; ++k) q.level[k] = pa.level[k] + (size_t)z0 * pa.stride[k];
+      CK(pyramid_kernel_launch(q, s));
+    }
+    c->launches += 1;
+  }
+  return PLSVO_OK;
+}
+
 // launch plan of the alignment kernel for the uploaded batch (shared memory, CTA size, grid)
 struct AlignPlan {
   int threads, min_blocks, ctas_per_sm;
@@ -505,7 +613,8 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
     return fail(c, PLSVO_ERR_INVALID, "level range / n_iter");
   AlignArgs& a = c->aa;
   for (int l = p->min_level; l <= p->max_level; ++l)
-    if (!a.pitch[l]) return fail(c, PLSVO_ERR_INVALID, "a pyramid level in [min_level,max_level] was not uploaded");
+    if (!a.pitch[l] || !a.ref_img[l])
+      return fail(c, PLSVO_ERR_INVALID, "a pyramid level in [min_level,max_level] was neither uploaded nor derived");
   CK(cudaSetDevice(c->device));
   a.max_level = p->max_level, a.min_level = p->min_level, a.n_iter = p->n_iter, a.eps = p->eps;
   a.max_seg_patches = std::max(c->seg_patch_bound[p->min_level], 1);
@@ -619,6 +728,9 @@ int align_launch_range(plsvo_ctx_impl* c, const AlignPlan& plan, size_t b0, size
   REBASE(seg_epos, ns * 3);
   REBASE(seg_length, ns);
   REBASE(seg_valid, ns);
+  REBASE(pt_depth, np);
+  REBASE(seg_sdepth, ns);
+  REBASE(seg_edepth, ns);
   REBASE(out_T, 7);
   REBASE(out_n_tracked, 1);
   REBASE(out_H, 36);
@@ -651,8 +763,13 @@ int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* h) {
 int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* p) {
   if (!ctx || !p) return PLSVO_ERR_INVALID;
   plsvo_ctx_impl* c = CTX(ctx);
+  if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_launch before plsvo_align_upload");
+  if (p->min_level < 0 || p->max_level < p->min_level || p->max_level >= PLSVO_MAX_LEVELS)
+    return fail(c, PLSVO_ERR_INVALID, "level range / n_iter");
   AlignPlan plan;
-  int rc = align_plan(c, p, c->aa.B, &plan);
+  int rc = align_derive_levels(c, p->min_level, p->max_level, 0, (size_t)c->aa.B, c->stream, false);
+  if (rc != PLSVO_OK) return rc;
+  rc = align_plan(c, p, c->aa.B, &plan);
   if (rc != PLSVO_OK) return rc;
   return align_launch_range(c, plan, 0, (size_t)c->aa.B, 0, c->stream);
 }
@@ -700,6 +817,7 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
   if (gated) {
     for (int l = p->min_level; l <= p->max_level && l < PLSVO_MAX_LEVELS && l >= 0; ++l) {
       const int rows = b->cam.height >> l;
+      if (!b->ref_img[l] && l > p->min_level) continue;  // derived on the device after each chunk has landed
       const bool direct = b->ref_img[l] && b->img_stride[l] == (size_t)rows * b->img_pitch[l] && b->img_pitch[l] % 4 == 0 &&
                           b->img_stride[l] % 16 == 0;
       if (!direct) gated = false;  // padded layouts need a device-side repack kernel: not under the gate
@@ -758,13 +876,26 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
         CK(cudaEventRecord(c->rr_ev[j], c->rr_stream[j]));
         CK(cudaStreamWaitEvent(c->copy_stream, c->rr_ev[j], 0));
       }
+      // coarser levels that were not shipped: the persistent kernel halfSamples them pair by pair (a pyramid kernel
+      // behind this chunk's copies could not become resident next to the grid that waits for it)
+      rc = align_derive_levels(c, p->min_level, p->max_level, (size_t)k * chunk, std::min<size_t>((size_t)(k + 1) * chunk, B), c->copy_stream,
+                               k == 0, /*in_kernel=*/true);
+      if (rc != PLSVO_OK) {
+        cudaStreamSynchronize(c->copy_stream);  // the caller's host arrays must not be read after we return
+        return rc;
+      }
       CK(cudaMemcpyAsync(d_arrived, &c->h_flags[k], sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream));
     }
     rc = align_upload_impl(c, b, 0, 0, c->copy_stream, 3);  // host-side sizing (segment-sample bound, outputs)
-    if (rc != PLSVO_OK) return rc;
     AlignPlan plan;
-    rc = align_plan(c, p, (int)B, &plan);
-    if (rc != PLSVO_OK) return rc;
+    if (rc == PLSVO_OK) rc = align_plan(c, p, (int)B, &plan);
+    if (rc != PLSVO_OK) {
+      // copies are in flight: the caller's host arrays must not be read after we return
+      cudaStreamSynchronize(c->copy_stream);
+      for (int j = 0; j < 4; ++j)
+        if (c->rr_stream[j]) cudaStreamSynchronize(c->rr_stream[j]);
+      return rc;
+    }
     rc = align_launch_range(c, plan, 0, B, 0, c->stream, chunk);  // gated on arrivals
     if (rc != PLSVO_OK) return rc;
     return plsvo_align_download(ctx, o);
@@ -794,6 +925,8 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
     const size_t b0 = B * k / chunks, b1 = B * (k + 1) / chunks;
     int rc = align_upload_impl(c, b, b0, b1, c->copy_stream, k == 0 ? 1 : 0);
     if (rc != PLSVO_OK) return rc;
+    rc = align_derive_levels(c, p->min_level, p->max_level, b0, b1, c->copy_stream, k == 0);
+    if (rc != PLSVO_OK) return rc;
     CK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
     if (k == 0) {
       rc = align_plan(c, p, (int)(b1 - b0), &plan);
@@ -809,12 +942,19 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
 // ------------------------------------------------------------------------------------------------
 // pose optimiser
 // ------------------------------------------------------------------------------------------------
-int plsvo_poseopt_upload(plsvo_ctx* ctx, const plsvo_poseopt_batch* h) {
-  if (!ctx || !h) return PLSVO_ERR_INVALID;
-  plsvo_ctx_impl* c = CTX(ctx);
+}  // extern "C"
+
+namespace {
+// device_T: poses already on the device (the chained call), instead of h->T_f_w
+int poseopt_upload_impl(plsvo_ctx_impl* c, const plsvo_poseopt_batch* h, const double* device_T) {
   c->po_ready = false;
   if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0) return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
-  if (!h->T_f_w) return fail(c, PLSVO_ERR_INVALID, "T_f_w missing");
+  if (!h->T_f_w && !device_T) return fail(c, PLSVO_ERR_INVALID, "T_f_w missing");
+  for (int b = 0; b < h->batch; ++b) {  // the counts index shared memory in the kernel
+    if (h->pt_count && (h->pt_count[b] < 0 || h->pt_count[b] > h->n_pts)) return fail(c, PLSVO_ERR_INVALID, "pt_count[b] outside [0, n_pts]");
+    if (h->seg_count && (h->seg_count[b] < 0 || h->seg_count[b] > h->n_segs))
+      return fail(c, PLSVO_ERR_INVALID, "seg_count[b] outside [0, n_segs]");
+  }
   if (h->n_pts > 0 && (!h->pt_f || !h->pt_pos || !h->pt_level)) return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
   if (h->n_segs > 0 && (!h->seg_line || !h->seg_spos || !h->seg_epos || !h->seg_level))
     return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
@@ -823,7 +963,11 @@ int plsvo_poseopt_upload(plsvo_ctx* ctx, const plsvo_poseopt_batch* h) {
   PoseOptArgs& a = c->pa;
   const size_t B = (size_t)h->batch;
   a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs, a.fx = h->fx;
-  CK(up(c->p_T, h->T_f_w, B * 7, s, &a.T_f_w));
+  if (device_T) {
+    a.T_f_w = device_T;
+  } else {
+    CK(up(c->p_T, h->T_f_w, B * 7, s, &a.T_f_w));
+  }
   CK(up(c->p_pt_count, h->pt_count, B, s, &a.pt_count));
   CK(up(c->p_pt_f, h->pt_f, B * h->n_pts * 3, s, &a.pt_f));
   CK(up(c->p_pt_pos, h->pt_pos, B * h->n_pts * 3, s, &a.pt_pos));
@@ -859,6 +1003,14 @@ int plsvo_poseopt_upload(plsvo_ctx* ctx, const plsvo_poseopt_batch* h) {
   a.out_status = static_cast<int32_t*>(c->p_out_status.p);
   c->po_ready = true;
   return PLSVO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int plsvo_poseopt_upload(plsvo_ctx* ctx, const plsvo_poseopt_batch* h) {
+  if (!ctx || !h) return PLSVO_ERR_INVALID;
+  return poseopt_upload_impl(CTX(ctx), h, nullptr);
 }
 
 int plsvo_poseopt_launch(plsvo_ctx* ctx, const plsvo_poseopt_params* p) {
@@ -906,6 +1058,42 @@ int plsvo_poseopt_download(plsvo_ctx* ctx, const plsvo_poseopt_result* o) {
   if (o->status) CK(cudaMemcpyAsync(o->status, a.out_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
+}
+
+// FrameHandlerMono::processFrame's two hot-path calls back to back (src/frame_handler_mono.cpp:272-274 and :327-329) for
+// a batch of frames, without the pose leaving the device: sparse image alignment of (ref, cur), then the pose optimiser
+// on cur's matched features starting from the aligned pose.  pb->T_f_w may be NULL (the usual case): frame b of the
+// pose-optimiser batch then starts from the alignment result of pair b, read on the device.
+int plsvo_track_upload(plsvo_ctx* ctx, const plsvo_align_batch* ab, const plsvo_poseopt_batch* pb) {
+  if (!ctx || !ab || !pb) return PLSVO_ERR_INVALID;
+  plsvo_ctx_impl* c = CTX(ctx);
+  if (pb->batch != ab->batch) return fail(c, PLSVO_ERR_INVALID, "alignment and pose-optimiser batches differ in size");
+  int rc = plsvo_align_upload(ctx, ab);
+  if (rc != PLSVO_OK) return rc;
+  // the pose optimiser reads the aligned poses where the alignment kernel leaves them (unless poses are given)
+  return poseopt_upload_impl(c, pb, pb->T_f_w ? nullptr : c->aa.out_T);
+}
+
+int plsvo_track_launch(plsvo_ctx* ctx, const plsvo_align_params* ap, const plsvo_poseopt_params* pp) {
+  if (!ctx || !ap || !pp) return PLSVO_ERR_INVALID;
+  int rc = plsvo_align_launch(ctx, ap);  // the two kernels back to back on the context's stream
+  if (rc != PLSVO_OK) return rc;
+  return plsvo_poseopt_launch(ctx, pp);
+}
+
+int plsvo_track_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* ab, const plsvo_align_params* ap,
+                          const plsvo_poseopt_batch* pb, const plsvo_poseopt_params* pp, const plsvo_align_result* ao,
+                          const plsvo_poseopt_result* po) {
+  if (!ctx || !ab || !ap || !pb || !pp || !po) return PLSVO_ERR_INVALID;
+  int rc = plsvo_track_upload(ctx, ab, pb);
+  if (rc != PLSVO_OK) return rc;
+  rc = plsvo_track_launch(ctx, ap, pp);
+  if (rc != PLSVO_OK) return rc;
+  if (ao) {
+    rc = plsvo_align_download(ctx, ao);
+    if (rc != PLSVO_OK) return rc;
+  }
+  return plsvo_poseopt_download(ctx, po);
 }
 
 int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* b, const plsvo_poseopt_params* p,

@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(kPoThreads) pose_optimizer_kernel(const PoseOp
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     __syncthreads();
     Feat F;
-    F.np = a.pt_count ? a.pt_count[b] : a.n_pts;
-    F.ns = a.seg_count ? a.seg_count[b] : a.n_segs;
+    // validated on upload; the clamp keeps a corrupted count from indexing shared memory out of bounds
+    F.np = min(max(a.pt_count ? a.pt_count[b] : a.n_pts, 0), a.n_pts);
+    F.ns = min(max(a.seg_count ? a.seg_count[b] : a.n_segs, 0), a.n_segs);
     const size_t po = (size_t)b * a.n_pts, so = (size_t)b * a.n_segs;
     F.pt_f = a.pt_f + 3 * po;
     F.pt_pos = a.pt_pos + 3 * po;

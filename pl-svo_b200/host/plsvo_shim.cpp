@@ -154,6 +154,12 @@ namespace {
 void run(double reproj_thresh, size_t n_iter, int n_iter_ref, FramePtr& frame, double& estimated_scale,
          double& error_init, double& error_final, size_t& num_obs_pt, size_t& num_obs_ls) {
   std::lock_guard<std::mutex> lk(g_mu);
+  // The caller (frame_handler_mono.cpp:325-336) declares the observation counts uninitialised and then tests
+  // `pt + ls < 10`.  The reference assigns num_obs_pt (= 0) before its "no observations" return (pose_optimizer.cpp:
+  // 72,88-89); here every exit without a result — no device, a failed call, no observations — leaves both counts and
+  // the errors at zero, so that test deterministically reports RESULT_FAILURE instead of reading garbage.
+  num_obs_pt = 0, num_obs_ls = 0;
+  error_init = 0.0, error_final = 0.0;
   plsvo_ctx* c = ctx();
   if (!c) return;
   plsvo_poseopt_batch b;

@@ -396,14 +396,19 @@ def make_poseopt_batch(
     pert_t: float = 0.02,
     pert_r: float = 0.01,
     scene: Scene | None = None,
+    T_gt: np.ndarray | None = None,
 ) -> PoseOptData:
     """B frames; observations = GT projection + N(0,(noise_px/fx)^2) on the unit plane, 10 % outliers
-    (U[5,30] px), level in {0,1,2}; initial pose = exp(delta) * T_gt."""
+    (U[5,30] px), level in {0,1,2}; initial pose = exp(delta) * T_gt.  T_gt [B,7]: ground-truth poses to use (the
+    chained align -> pose-opt case observes the features in the alignment's current frame)."""
     scene = scene or Scene()
     rng = np.random.Generator(np.random.PCG64(seed))
     f64 = dict(dtype=torch.float64)
     xi_gt = np.concatenate([rng.uniform(-0.2, 0.2, (batch, 3)), rng.uniform(-0.03, 0.03, (batch, 3))], -1)
     R_gt, t_gt = se3_exp_Rt(torch.tensor(xi_gt, **f64))
+    if T_gt is not None:
+        assert T_gt.shape == (batch, 7)
+        R_gt, t_gt = pose7_to_Rt(torch.tensor(np.asarray(T_gt), **f64))
     xi_d = np.concatenate([rng.uniform(-pert_t, pert_t, (batch, 3)), rng.uniform(-pert_r, pert_r, (batch, 3))], -1)
     R_d, t_d = se3_exp_Rt(torch.tensor(xi_d, **f64))
     R0 = R_d @ R_gt
@@ -459,6 +464,16 @@ def make_poseopt_batch(
         seg_epos=npy(seg_epos),
         seg_level=seg_level,
     )
+
+
+def make_track_batch(cam: Camera = VGA, batch: int = 8, n_pts: int = 300, n_segs: int = 80, seed: int = 3000,
+                     device: str | torch.device = "cpu", **align_kw):
+    """BASELINE config 4 ("combined align+pose path"): an alignment batch and, for every pair's current frame, a
+    pose-optimiser batch whose features are observed at that frame's ground-truth pose (noise + outliers as in C3).
+    Chained use: the pose optimiser starts from the alignment's result (frame_handler_mono.cpp:272-274 -> :327-329)."""
+    al = make_align_batch(cam=cam, batch=batch, n_pts=n_pts, n_segs=n_segs, seed=seed, device=device, **align_kw)
+    po = make_poseopt_batch(cam=cam, batch=batch, n_pts=n_pts, n_segs=n_segs, seed=seed + 7919, T_gt=al.T_cur_w_gt)
+    return al, po
 
 
 # ---- Matcher::findMatchDirect candidates (SURVEY §8f rank 1) -----------------------------------------
