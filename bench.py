@@ -672,6 +672,39 @@ def main():
     clk.__exit__(None, None, None)
     data = data_full
 
+    # ---- multi-GPU product path: ONE host batch on rank 0 -> NCCL scatter -> align on every GPU -> all_gather ----
+    e2e_scatter = None
+    if dist:
+        from plsvo_b200 import dist as pdist
+
+        glob = None
+        if rank == 0:
+            import copy
+
+            glob = copy.copy(data_lean)  # rank 0's lean batch, tiled: world x B pairs owned by one process
+            for name in pdist._ALIGN_ARRAYS:
+                a = getattr(data_lean, name, None)
+                if a is not None:
+                    setattr(glob, name, np.concatenate([a] * world, 0))
+            glob.ref_pyr = {l: np.concatenate([v] * world, 0) for l, v in data_lean.ref_pyr.items()}
+            glob.cur_pyr = {l: np.concatenate([v] * world, 0) for l, v in data_lean.cur_pyr.items()}
+        pdist.align_sharded(glob, 4, 2, 30, src=0, device=dev)  # warm
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n_sc = 2
+        for _ in range(n_sc):
+            full = pdist.align_sharded(glob, 4, 2, 30, src=0, device=dev)
+        torch.cuda.synchronize(dev)
+        sc_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / n_sc], dtype=torch.float64, device=dev)
+        dist.all_reduce(sc_ms, op=dist.ReduceOp.MAX)
+        assert full["T_cur_w"].shape == (world * B, 7)
+        assert np.array_equal(full["iters"][:B], out.iters), "sharded path changed the result"
+        e2e_scatter = {"value": world * B / (float(sc_ms.item()) * 1e-3), "unit": "pairs/s", "ms_per_step": float(sc_ms.item()),
+                       "what": "plsvo_b200.dist.align_sharded: one host batch of n_gpus x %d pairs on rank 0 (rank 0's batch tiled), "
+                               "packed per shard, NCCL scatter, align on every GPU, all_gather of all outputs; timed wall clock "
+                               "including the Python-side packing" % B}
+
     # ---- roofline of the alignment kernel (the only kernel in the step) ----
     alg_bytes = float(out.patch_iters.astype(np.float64).sum() * BYTES_PATCH_ITER
                       + out.patch_levels.astype(np.float64).sum() * BYTES_PATCH_LEVEL + B * BYTES_PAIR_FIXED)
@@ -769,6 +802,7 @@ def main():
             "dtype": DTYPE, "data": "synthetic", "config": workload_config(args, n_gpus),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
                     "d2h_bytes_per_step": int(d2h) * n_gpus},
+            "e2e_scatter": e2e_scatter,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -17,6 +17,7 @@
 #include <vikit/pinhole_camera.h>
 
 #include <cstring>
+#include <chrono>
 #include <memory>
 #include <vector>
 
@@ -54,13 +55,22 @@ Vector3d v3(const double* p) { return Vector3d(p[0], p[1], p[2]); }
 Vector2d v2(const double* p) { return Vector2d(p[0], p[1]); }
 }  // namespace
 
+// wall time of every SparseImgAlign::run call of the last plsvo_shimref_align_batch (B = 1 latency, tools/b1_latency.py)
+static std::vector<double> g_run_seconds;
+
 extern "C" {
 
 int plsvo_shimref_set_device(int device) { return plsvo::shim_set_device(device); }
+int plsvo_shimref_run_seconds(double* out, int n) {
+  const int m = std::min<int>(n, (int)g_run_seconds.size());
+  for (int i = 0; i < m; ++i) out[i] = g_run_seconds[i];
+  return m;
+}
 
 // SparseImgAlign(max, min, n_iter, GaussNewton, false, false).run(ref, cur) on reference-typed frames, pair by pair
 int plsvo_shimref_align_batch(const plsvo_align_batch* B, const plsvo_align_params* P, const plsvo_align_result* out) {
   if (!B || !P || !out) return PLSVO_ERR_INVALID;
+  g_run_seconds.clear();
   for (int b = 0; b < B->batch; ++b) {
     const int np = B->pt_count ? B->pt_count[b] : B->n_pts;
     const int ns = B->seg_count ? B->seg_count[b] : B->n_segs;
@@ -101,7 +111,9 @@ int plsvo_shimref_align_batch(const plsvo_align_batch* B, const plsvo_align_para
     }
     // src/frame_handler_mono.cpp:272-274, verbatim but for the Config:: constants
     plsvo::SparseImgAlign img_align(P->max_level, P->min_level, P->n_iter, plsvo::SparseImgAlign::GaussNewton, false, false);
+    const auto t_run0 = std::chrono::steady_clock::now();
     const size_t img_align_n_tracked = img_align.run(ref, cur);
+    g_run_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run0).count());
     pose_to7(cur->T_f_w_, out->T_cur_w + 7 * (size_t)b);
     out->n_tracked[b] = (int64_t)img_align_n_tracked;
     if (out->H) img_align.getFisherInformation(out->H + 36 * (size_t)b);  // H / (5e-4 * 255^2)

@@ -24,6 +24,10 @@ def gather_rows(local: np.ndarray, n_items: int, device: torch.device | str = "c
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
+    unsigned = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}
+    if local.dtype in unsigned:  # the collectives carry signed integers; same bits
+        back = local.dtype
+        return gather_rows(np.ascontiguousarray(local).view(unsigned[local.dtype]), n_items, device).view(back)
     sizes = [shard_range(n_items, r, world) for r in range(world)]
     cap = max(e - b for b, e in sizes)
     row = local.shape[1:]
@@ -33,3 +37,118 @@ def gather_rows(local: np.ndarray, n_items: int, device: torch.device | str = "c
     dist.all_gather_into_tensor(out, buf)
     out = out.cpu().numpy().reshape((world, cap) + row)
     return np.concatenate([out[r, : e - b] for r, (b, e) in enumerate(sizes)], axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# One host batch on G GPUs: scatter -> align -> gather
+# ------------------------------------------------------------------------------------------------
+_ALIGN_ARRAYS = ("T_ref_w", "T_cur_w", "T_cur_w_gt", "pt_px", "pt_f", "pt_pos", "seg_spx", "seg_epx", "seg_sf", "seg_ef", "seg_spos",
+                 "seg_epos", "seg_length", "pt_valid", "seg_valid", "pt_count", "seg_count", "pt_depth", "seg_sdepth", "seg_edepth")
+_RESULT_FIELDS = ("T_cur_w", "n_tracked", "H", "seg_killed", "iters", "status", "patch_iters", "patch_levels")
+
+
+def _pack(arrays):
+    """[(name, ndarray)] -> (uint8 buffer, manifest): every array 256-byte aligned inside one contiguous block."""
+    manifest, off = [], 0
+    for name, a in arrays:
+        a = np.ascontiguousarray(a)
+        manifest.append((name, str(a.dtype), a.shape, off, a.nbytes))
+        off = (off + a.nbytes + 255) // 256 * 256
+    buf = np.zeros(max(off, 256), np.uint8)
+    for (name, dt, shape, o, nb), (_, a) in zip(manifest, arrays):
+        buf[o:o + nb] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return buf, manifest
+
+
+def _unpack(buf, manifest):
+    return {name: buf[o:o + nb].view(np.dtype(dt)).reshape(shape) for name, dt, shape, o, nb in manifest}
+
+
+def _shard_arrays(data, b, e):
+    out = []
+    for name in _ALIGN_ARRAYS:
+        a = getattr(data, name, None)
+        if a is not None:
+            out.append((name, a[b:e]))
+    for l, v in data.ref_pyr.items():
+        out.append((f"ref_pyr/{l}", v[b:e]))
+    for l, v in data.cur_pyr.items():
+        out.append((f"cur_pyr/{l}", v[b:e]))
+    return out
+
+
+def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30, src: int = 0, device=None, run_fn=None):
+    """plsvo::SparseImgAlign::run over ONE host batch that lives on rank `src`, on all GPUs of the process group:
+    rank `src` cuts the batch into contiguous shards (shard_range), packs each shard's inputs into one block and
+    scatters the blocks (NCCL over NVLink on the GPUs, gloo in the CPU tests); every rank aligns its shard; the per-pair
+    results come back with one all_gather per output, in batch order, on every rank.  Pairs are independent: there is no
+    collective on the data path between the scatter and the gather.
+
+    data: an AlignData on rank `src` (ignored elsewhere, may be None).  run_fn(shard AlignData) -> AlignOut defaults to the
+    CUDA path (SparseImgAlign.run through the C ABI); the CPU test injects its own.  Returns a dict of result arrays."""
+    from . import synth
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        out = (run_fn or _default_run(max_level, min_level, n_iter))(data)
+        return {f: getattr(out, f) for f in _RESULT_FIELDS}
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    # 1. what every rank needs to know before the scatter: shard sizes, manifests, camera
+    meta = [None]
+    bufs = None
+    if rank == src:
+        n = data.batch
+        packed = [_pack(_shard_arrays(data, *shard_range(n, r, world))) for r in range(world)]
+        cap = max(p[0].nbytes for p in packed)
+        meta = [{"n": n, "cap": cap, "manifests": [p[1] for p in packed],
+                 "cam": (data.cam.width, data.cam.height, data.cam.fx, data.cam.fy, data.cam.cx, data.cam.cy),
+                 "levels": (data.max_level, data.min_level)}]
+        bufs = []
+        for p in packed:
+            t = torch.zeros(cap, dtype=torch.uint8)
+            t[: p[0].nbytes] = torch.from_numpy(p[0])
+            bufs.append(t.to(dev))
+    dist.broadcast_object_list(meta, src=src)
+    m = meta[0]
+    # 2. scatter of the packed shards
+    mine = torch.empty(m["cap"], dtype=torch.uint8, device=dev)
+    dist.scatter(mine, bufs if rank == src else None, src=src)
+    arrays = _unpack(mine.cpu().numpy(), m["manifests"][rank])
+    b, e = shard_range(m["n"], rank, world)
+    shard = synth.AlignData(
+        cam=synth.Camera(*m["cam"]), max_level=m["levels"][0], min_level=m["levels"][1],
+        ref_pyr={int(k.split("/")[1]): np.ascontiguousarray(v) for k, v in arrays.items() if k.startswith("ref_pyr/")},
+        cur_pyr={int(k.split("/")[1]): np.ascontiguousarray(v) for k, v in arrays.items() if k.startswith("cur_pyr/")},
+        **{k: np.ascontiguousarray(arrays[k]) if k in arrays else None for k in _ALIGN_ARRAYS[:13]})
+    for k in _ALIGN_ARRAYS[13:]:
+        if k in arrays:
+            setattr(shard, k, np.ascontiguousarray(arrays[k]))
+    # 3. every rank aligns its shard (empty shards run nothing)
+    res = {}
+    if e > b:
+        out = (run_fn or _default_run(max_level, min_level, n_iter))(shard)
+        res = {f: np.asarray(getattr(out, f)) for f in _RESULT_FIELDS}
+    # 4. gather, in batch order, on every rank
+    shapes = [None]
+    if rank == src:
+        pass
+    full = {}
+    for f in _RESULT_FIELDS:
+        proto = [None]
+        if e > b:
+            proto = [(str(res[f].dtype), res[f].shape[1:])]
+        protos = [None] * world
+        dist.all_gather_object(protos, proto[0])
+        dt, row = next(p for p in protos if p is not None)
+        local = res[f] if e > b else np.zeros((0,) + tuple(row), np.dtype(dt))
+        full[f] = gather_rows(np.ascontiguousarray(local), m["n"], device=dev)
+    return full
+
+
+def _default_run(max_level, min_level, n_iter):
+    from .api import SparseImgAlign
+
+    def run(shard):
+        return SparseImgAlign(max_level, min_level, n_iter).run(shard)
+
+    return run

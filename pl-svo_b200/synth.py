@@ -274,6 +274,8 @@ def make_align_batch(
     margin: int | None = None,
     scene: Scene | None = None,
     keep_levels_only: bool = True,
+    T_ref_w_gt: np.ndarray | None = None,
+    T_cur_w_gt: np.ndarray | None = None,
 ) -> AlignData:
     """SURVEY.md §8d config C2 generator: B independent frame pairs, each with its own reference view,
     features and motion (seeds derived from `seed`)."""
@@ -291,6 +293,9 @@ def make_align_batch(
     R_m, t_m = se3_exp_Rt(torch.tensor(xi_mot, **f64))
     R_cur = R_m @ R_ref  # T_cur_w = T_cur_from_ref * T_ref_w
     t_cur = (R_m @ t_ref[..., None])[..., 0] + t_m
+    if T_ref_w_gt is not None:  # given poses (frame sequences): the random draws above keep the stream position
+        R_ref, t_ref = pose7_to_Rt(torch.tensor(np.asarray(T_ref_w_gt), **f64))
+        R_cur, t_cur = pose7_to_Rt(torch.tensor(np.asarray(T_cur_w_gt), **f64))
     T_ref_w = pose7_from_Rt(R_ref, t_ref)
     T_cur_w_gt = pose7_from_Rt(R_cur, t_cur)
 
@@ -474,6 +479,57 @@ def make_track_batch(cam: Camera = VGA, batch: int = 8, n_pts: int = 300, n_segs
     al = make_align_batch(cam=cam, batch=batch, n_pts=n_pts, n_segs=n_segs, seed=seed, device=device, **align_kw)
     po = make_poseopt_batch(cam=cam, batch=batch, n_pts=n_pts, n_segs=n_segs, seed=seed + 7919, T_gt=al.T_cur_w_gt)
     return al, po
+
+
+def make_sequence(cam: Camera = VGA, n_seq: int = 4, n_frames: int = 20, n_pts: int = 300, n_segs: int = 80, seed: int = 1000,
+                  device: str | torch.device = "cpu", noise_px: float = 0.3, outlier_frac: float = 0.05):
+    """BASELINE config 1 / SURVEY 8d C1: n_seq independent sequences of n_frames views along the smooth trajectory
+    T_k = exp(k * (0.02, 0.005, 0.01, 0.004, -0.006, 0.002)) * T_0.  Returns the ground-truth poses [n_seq, n_frames, 7] and,
+    for every step k = 1..n_frames-1, (AlignData, PoseOptData): the alignment of frame k-1 (reference, with its features)
+    against frame k, and frame k's matched features for the pose optimiser.  A sequence driver overwrites the poses of
+    each step with its own estimates (run_sequence)."""
+    f64 = dict(dtype=torch.float64)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xi0 = np.concatenate([rng.uniform(-0.15, 0.15, (n_seq, 3)), rng.uniform(-0.02, 0.02, (n_seq, 3))], -1)
+    R0, t0 = se3_exp_Rt(torch.tensor(xi0, **f64))
+    step = np.array([0.02, 0.005, 0.01, 0.004, -0.006, 0.002])
+    poses = np.zeros((n_seq, n_frames, 7))
+    for k in range(n_frames):
+        Rk, tk = se3_exp_Rt(torch.tensor(np.tile(k * step, (n_seq, 1)), **f64))
+        poses[:, k] = pose7_from_Rt(Rk @ R0, (Rk @ t0[..., None])[..., 0] + tk).numpy()
+    steps = []
+    for k in range(1, n_frames):
+        al = make_align_batch(cam=cam, batch=n_seq, n_pts=n_pts, n_segs=n_segs, seed=seed + 31 * k, device=device,
+                              T_ref_w_gt=poses[:, k - 1], T_cur_w_gt=poses[:, k])
+        po = make_poseopt_batch(cam=cam, batch=n_seq, n_pts=n_pts, n_segs=n_segs, seed=seed + 31 * k + 7, noise_px=noise_px,
+                                outlier_frac=outlier_frac, T_gt=poses[:, k])
+        steps.append((al, po))
+    return poses, steps
+
+
+def run_sequence(poses, steps, track_fn):
+    """The frame-to-frame chain of FrameHandlerMono::processFrame (src/frame_handler_mono.cpp:263-340) over a sequence:
+    new_frame.T_f_w = last_frame.T_f_w (:266), sparse image alignment, pose optimisation, and the result becomes the
+    reference pose of the next step.  track_fn(AlignData, PoseOptData) -> (AlignOut, PoseOptOut) runs one step (chained
+    on the GPU, or the two reference calls on the CPU).  Returns estimated poses [n_seq, n_frames, 7], the per-step
+    alignment iteration counts and pose-optimiser outlier flags."""
+    import copy
+
+    n_seq, n_frames = poses.shape[:2]
+    est = np.zeros_like(poses)
+    est[:, 0] = poses[:, 0]  # the first frame's pose is given
+    iters, outliers = [], []
+    for k, (al, po) in enumerate(steps, start=1):
+        al = copy.copy(al)
+        po = copy.copy(po)
+        al.T_ref_w = np.ascontiguousarray(est[:, k - 1])
+        al.T_cur_w = np.ascontiguousarray(est[:, k - 1])  # initial guess = last frame's pose (:266)
+        po.T_f_w = np.ascontiguousarray(est[:, k - 1])    # placeholder; the step function starts from the aligned pose
+        ao, pout = track_fn(al, po)
+        est[:, k] = pout.T_f_w
+        iters.append(ao.iters.copy())
+        outliers.append(pout.pt_outlier.copy())
+    return est, np.stack(iters, 1), np.stack(outliers, 1)
 
 
 # ---- Matcher::findMatchDirect candidates (SURVEY §8f rank 1) -----------------------------------------
