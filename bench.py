@@ -688,18 +688,18 @@ def main():
                     setattr(glob, name, np.concatenate([a] * world, 0))
             glob.ref_pyr = {l: np.concatenate([v] * world, 0) for l, v in data_lean.ref_pyr.items()}
             glob.cur_pyr = {l: np.concatenate([v] * world, 0) for l, v in data_lean.cur_pyr.items()}
-        pdist.align_sharded(glob, 4, 2, 30, src=0, device=dev)  # warm
+        pdist.align_sharded(glob, 4, 2, 30, src=0, device=dev, ctx=ctx)  # warm
         dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         n_sc = 2
         for _ in range(n_sc):
-            full = pdist.align_sharded(glob, 4, 2, 30, src=0, device=dev)
+            full = pdist.align_sharded(glob, 4, 2, 30, src=0, device=dev, ctx=ctx)
         torch.cuda.synchronize(dev)
         sc_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / n_sc], dtype=torch.float64, device=dev)
         dist.all_reduce(sc_ms, op=dist.ReduceOp.MAX)
         assert full["T_cur_w"].shape == (world * B, 7)
-        assert np.array_equal(full["iters"][:B], out.iters), "sharded path changed the result"
+        assert rank != 0 or np.array_equal(full["iters"][:B], out.iters), "sharded path changed the result"
         e2e_scatter = {"value": world * B / (float(sc_ms.item()) * 1e-3), "unit": "pairs/s", "ms_per_step": float(sc_ms.item()),
                        "what": "plsvo_b200.dist.align_sharded: one host batch of n_gpus x %d pairs on rank 0 (rank 0's batch tiled), "
                                "packed per shard, NCCL scatter, align on every GPU, all_gather of all outputs; timed wall clock "

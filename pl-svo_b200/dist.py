@@ -47,17 +47,30 @@ _ALIGN_ARRAYS = ("T_ref_w", "T_cur_w", "T_cur_w_gt", "pt_px", "pt_f", "pt_pos", 
 _RESULT_FIELDS = ("T_cur_w", "n_tracked", "H", "seg_killed", "iters", "status", "patch_iters", "patch_levels")
 
 
-def _pack(arrays):
-    """[(name, ndarray)] -> (uint8 buffer, manifest): every array 256-byte aligned inside one contiguous block."""
+_pinned = {}
+
+
+def _staging(key, nbytes, pin):
+    """A reusable (pinned when CUDA is in play) uint8 staging tensor of at least nbytes."""
+    t = _pinned.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, pin_memory=pin)
+        _pinned[key] = t
+    return t
+
+
+def _manifest(arrays):
     manifest, off = [], 0
     for name, a in arrays:
-        a = np.ascontiguousarray(a)
         manifest.append((name, str(a.dtype), a.shape, off, a.nbytes))
         off = (off + a.nbytes + 255) // 256 * 256
-    buf = np.zeros(max(off, 256), np.uint8)
+    return manifest, max(off, 256)
+
+
+def _pack_into(buf, arrays, manifest):
+    """Copy every array to its 256-byte aligned place inside the uint8 block `buf` (a numpy view)."""
     for (name, dt, shape, o, nb), (_, a) in zip(manifest, arrays):
         buf[o:o + nb] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-    return buf, manifest
 
 
 def _unpack(buf, manifest):
@@ -77,7 +90,7 @@ def _shard_arrays(data, b, e):
     return out
 
 
-def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30, src: int = 0, device=None, run_fn=None):
+def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30, src: int = 0, device=None, run_fn=None, ctx=None):
     """plsvo::SparseImgAlign::run over ONE host batch that lives on rank `src`, on all GPUs of the process group:
     rank `src` cuts the batch into contiguous shards (shard_range), packs each shard's inputs into one block and
     scatters the blocks (NCCL over NVLink on the GPUs, gloo in the CPU tests); every rank aligns its shard; the per-pair
@@ -85,35 +98,43 @@ def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30
     collective on the data path between the scatter and the gather.
 
     data: an AlignData on rank `src` (ignored elsewhere, may be None).  run_fn(shard AlignData) -> AlignOut defaults to the
-    CUDA path (SparseImgAlign.run through the C ABI); the CPU test injects its own.  Returns a dict of result arrays."""
+    CUDA path (SparseImgAlign.run through the C ABI, on `ctx` or on a context of this rank's device); the CPU test
+    injects its own.  Returns a dict of result arrays."""
     from . import synth
 
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        out = (run_fn or _default_run(max_level, min_level, n_iter))(data)
+        out = (run_fn or _default_run(max_level, min_level, n_iter, ctx, device))(data)
         return {f: getattr(out, f) for f in _RESULT_FIELDS}
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device(device) if device is not None else torch.device("cpu")
     # 1. what every rank needs to know before the scatter: shard sizes, manifests, camera
     meta = [None]
     bufs = None
+    pin = dev.type == "cuda"
     if rank == src:
         n = data.batch
-        packed = [_pack(_shard_arrays(data, *shard_range(n, r, world))) for r in range(world)]
-        cap = max(p[0].nbytes for p in packed)
-        meta = [{"n": n, "cap": cap, "manifests": [p[1] for p in packed],
+        shards = [_shard_arrays(data, *shard_range(n, r, world)) for r in range(world)]
+        mans = [_manifest(sh) for sh in shards]
+        cap = max(sz for _, sz in mans)
+        meta = [{"n": n, "cap": cap, "manifests": [mf for mf, _ in mans],
                  "cam": (data.cam.width, data.cam.height, data.cam.fx, data.cam.fy, data.cam.cx, data.cam.cy),
                  "levels": (data.max_level, data.min_level)}]
-        bufs = []
-        for p in packed:
-            t = torch.zeros(cap, dtype=torch.uint8)
-            t[: p[0].nbytes] = torch.from_numpy(p[0])
-            bufs.append(t.to(dev))
+        stage = _staging("src", cap * world, pin)  # one pinned block, one H2D copy for all shards
+        host = stage.numpy()
+        for r, (sh, (mf, _)) in enumerate(zip(shards, mans)):
+            _pack_into(host[r * cap:(r + 1) * cap], sh, mf)
+        dev_all = stage[: cap * world].to(dev, non_blocking=True)
+        bufs = list(dev_all.split(cap))
     dist.broadcast_object_list(meta, src=src)
     m = meta[0]
     # 2. scatter of the packed shards
     mine = torch.empty(m["cap"], dtype=torch.uint8, device=dev)
     dist.scatter(mine, bufs if rank == src else None, src=src)
-    arrays = _unpack(mine.cpu().numpy(), m["manifests"][rank])
+    back = _staging("dst", m["cap"], pin)  # the C ABI reads host buffers: pinned, so its own H2D runs at full PCIe speed
+    back[: m["cap"]].copy_(mine)
+    if pin:
+        torch.cuda.synchronize(dev)
+    arrays = _unpack(back.numpy(), m["manifests"][rank])
     b, e = shard_range(m["n"], rank, world)
     shard = synth.AlignData(
         cam=synth.Camera(*m["cam"]), max_level=m["levels"][0], min_level=m["levels"][1],
@@ -126,29 +147,36 @@ def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30
     # 3. every rank aligns its shard (empty shards run nothing)
     res = {}
     if e > b:
-        out = (run_fn or _default_run(max_level, min_level, n_iter))(shard)
+        out = (run_fn or _default_run(max_level, min_level, n_iter, ctx, dev))(shard)
         res = {f: np.asarray(getattr(out, f)) for f in _RESULT_FIELDS}
-    # 4. gather, in batch order, on every rank
-    shapes = [None]
-    if rank == src:
-        pass
+    # 4. gather, in batch order, on every rank (row shapes are fixed by the ABI: include/plsvo_b200.h plsvo_align_result)
+    from . import abi
+
+    n_segs = shard.n_segs
+    spec = {"T_cur_w": (np.float64, (7,)), "n_tracked": (np.int64, ()), "H": (np.float64, (36,)), "seg_killed": (np.uint8, (n_segs,)),
+            "iters": (np.int32, (abi.MAX_LEVELS,)), "status": (np.int32, ()), "patch_iters": (np.uint32, ()), "patch_levels": (np.uint32, ())}
     full = {}
     for f in _RESULT_FIELDS:
-        proto = [None]
-        if e > b:
-            proto = [(str(res[f].dtype), res[f].shape[1:])]
-        protos = [None] * world
-        dist.all_gather_object(protos, proto[0])
-        dt, row = next(p for p in protos if p is not None)
-        local = res[f] if e > b else np.zeros((0,) + tuple(row), np.dtype(dt))
+        dt, row = spec[f]
+        local = res[f].astype(dt, copy=False) if e > b else np.zeros((0,) + row, dt)
         full[f] = gather_rows(np.ascontiguousarray(local), m["n"], device=dev)
     return full
 
 
-def _default_run(max_level, min_level, n_iter):
-    from .api import SparseImgAlign
+_ctx_cache = {}
+
+
+def _default_run(max_level, min_level, n_iter, ctx=None, device=None):
+    from .api import Context, SparseImgAlign
+
+    if ctx is None:
+        index = torch.device(device).index if device is not None and torch.device(device).type == "cuda" else 0
+        index = 0 if index is None else index
+        if index not in _ctx_cache:
+            _ctx_cache[index] = Context(index)
+        ctx = _ctx_cache[index]
 
     def run(shard):
-        return SparseImgAlign(max_level, min_level, n_iter).run(shard)
+        return SparseImgAlign(max_level, min_level, n_iter, ctx=ctx).run(shard)
 
     return run
