@@ -68,6 +68,7 @@ struct PairCtl {
   double cand[7];  // candidate model T*exp(-x) of the current pass and its rotation matrix / step norm
   double candR[9];
   double cand_nm;
+  float seg_chi2f; // seg_chi2 of the current pass (:683), summed by a third warp while the walker chains the points
   float chi2f;     // chi2 of the current pass, summed in the reference's order (walker warp -> thread 0)
   int n_opq;       // opaque patches of the current pass
   int chi2_flags;  // sticky per pair: 1 = opaque buffer overflowed (order approximated), 2 = binade check failed
@@ -508,6 +509,8 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignArgs a) {
   constexpr int NW = NT / 32;
   constexpr int WALK = NW > 1 ? 1 : 0;  // warp that chains the chi2 items while thread 0 solves
+  constexpr int SEGW = NW > 2 ? 2 : WALK;  // warp that sums the segments' chi2 terms meanwhile
+  constexpr int kSerialThreads = 32 * (NW > 2 ? 3 : (NW > 1 ? 2 : 1));
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int MP = a.max_patches;
@@ -1124,9 +1127,6 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             __syncwarp();
             c += nfit;
           }
-          float s2 = 0.f;  // seg_chi2 (:683): one term per accepted segment, in list order (others hold +0, a no-op)
-#pragma unroll 8
-          for (int j = 0; j < ns; ++j) s2 = __fadd_rn(s2, seg_term[j]);
           if (lane == 0) {
             if (ctl->n_opq > kOpqCap) {
               // opaque buffer overflowed (flag 1): fall back to the estimate of the point sum for this pass
@@ -1135,16 +1135,23 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
               s = (float)e;
             }
             if (bad) atomicOr(&ctl->chi2_flags, 2);
-            ctl->chi2f = __fadd_rn(s, s2);  // float chi2 = pt_chi2 + seg_chi2 (:171)
+            ctl->chi2f = s;  // pt_chi2 (:484); seg_chi2 is added by the decision (:171)
             ctl->n_opq = 0;
           }
         }
-        // chi2 (walker warp) -> decision (thread 0); both warps arrive converged: a named barrier counts whole warps
-        if (NW > 1 && warp <= 1) named_barrier_sync(1, 64);
+        if (warp == SEGW) {
+          float s2 = 0.f;  // seg_chi2 (:683): one term per accepted segment, in list order (others hold +0, a no-op)
+#pragma unroll 8
+          for (int j = 0; j < ns; ++j) s2 = __fadd_rn(s2, seg_term[j]);
+          if (lane == 0) ctl->seg_chi2f = s2;
+        }
+        // chi2 (walker warp, segment warp) -> decision (thread 0); the warps arrive converged: a named barrier counts
+        // whole warps
+        if (NW > 1 && warp * 32 < kSerialThreads) named_barrier_sync(1, kSerialThreads);
 #ifdef PLSVO_TREE_CHI2
         if (tid == 0) gn_decide(ctl, tot, (float)tot[27], a.n_iter, a.eps);
 #else
-        if (tid == 0) gn_decide(ctl, tot, ctl->chi2f, a.n_iter, a.eps);
+        if (tid == 0) gn_decide(ctl, tot, __fadd_rn(ctl->chi2f, ctl->seg_chi2f), a.n_iter, a.eps);  // pt_chi2 + seg_chi2 (:171)
 #endif
         __syncthreads();
         if (ctl->flag) break;
