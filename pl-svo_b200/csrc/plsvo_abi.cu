@@ -803,7 +803,7 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
   if (!ctx || !b || !p || !o) return PLSVO_ERR_INVALID;
   plsvo_ctx_impl* c = CTX(ctx);
   // Host-buffer pipeline.  Default for large batches: ONE persistent kernel over the whole batch is
-  // launched immediately while a second stream copies the batch to the device in chunks of 128 pairs
+  // launched immediately while a second stream copies the batch to the device in chunks of 256 pairs
   // and bumps an arrival counter after each chunk; the kernel's work queue hands a pair out only once
   // its chunk has landed (arrival gate), so the PCIe leg and the compute leg overlap without cutting
   // the batch into under-filled kernels.  Chunks of 128 pairs keep every array's chunk boundary
@@ -831,7 +831,7 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
       CK(cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming));
     }
     const size_t B = (size_t)b->batch;
-    int chunk = 512;  // multiple of 128 pairs: every array's chunk boundary stays 128-byte aligned
+    int chunk = 256;  // multiple of 128 pairs: every array's chunk boundary stays 128-byte aligned (tools/tune_e2e.py)
     const char* genv = getenv("PLSVO_GATE_CHUNK");
     if (genv && atoi(genv) >= 128) chunk = atoi(genv) / 128 * 128;
     const int n_chunks = (int)((B + chunk - 1) / chunk);

@@ -15,6 +15,11 @@ for name in ("T_ref_w", "T_cur_w", "pt_px", "pt_f", "pt_pos", "seg_spx", "seg_ep
     setattr(data, name, pin(getattr(data, name)))
 for pyr in (data.ref_pyr, data.cur_pyr):
     for l in list(pyr): pyr[l] = pin(pyr[l])
+if os.environ.get("TUNE_LEAN", "1") == "1":  # what bench.py's e2e leg ships: finest level only + feature depths
+    sys.path.insert(0, ROOT)
+    import bench
+    data, nbytes, keep2 = bench.lean_copy(data, torch)
+    print(json.dumps({"lean_bytes_per_step": nbytes}))
 ctx = plsvo_b200.Context(0)
 al = plsvo_b200.SparseImgAlign(4, 2, 30, ctx=ctx)
 for chunks, gate, rr in ((0, 512, 1), (0, 512, 2), (0, 512, 3), (0, 512, 4), (0, 256, 1), (0, 256, 2), (0, 256, 3), (0, 256, 4),
