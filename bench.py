@@ -171,8 +171,9 @@ def subset(data, n_pairs):
 
 
 def lean_copy(data, torch):
-    """What the end-to-end leg ships: the finest level used only (coarser levels are halfSample'd on the device) and the
-    distance of every 3-D feature from the reference camera centre instead of its position (include/plsvo_b200.h).
+    """What the end-to-end leg ships: the finest level used only (coarser levels are halfSample'd on the device), the
+    distance of every 3-D feature from the reference camera centre instead of its position, and no bearing vectors (they
+    are cam2world(px) for the undistorted pinhole camera; include/plsvo_b200.h).
     Returns (AlignData, bytes, keepalive); every array is pinned."""
     import copy
 
@@ -185,11 +186,11 @@ def lean_copy(data, torch):
     lean.seg_sdepth = np.ascontiguousarray(np.linalg.norm(data.seg_spos - centre[:, None, :], axis=-1))
     lean.seg_edepth = np.ascontiguousarray(np.linalg.norm(data.seg_epos - centre[:, None, :], axis=-1))
     lean.pt_pos = lean.seg_spos = lean.seg_epos = None
+    lean.pt_f = lean.seg_sf = lean.seg_ef = None  # undistorted pinhole: cam2world(px) on the device (feature.cpp:42,98-99)
     lean.ref_pyr = {data.min_level: data.ref_pyr[data.min_level]}
     lean.cur_pyr = {data.min_level: data.cur_pyr[data.min_level]}
     keep, nbytes = [], 0
-    for name in ("T_ref_w", "T_cur_w", "pt_px", "pt_f", "pt_depth", "seg_spx", "seg_epx", "seg_sf", "seg_ef", "seg_sdepth",
-                 "seg_edepth", "seg_length"):
+    for name in ("T_ref_w", "T_cur_w", "pt_px", "pt_depth", "seg_spx", "seg_epx", "seg_sdepth", "seg_edepth", "seg_length"):
         tt = torch.from_numpy(getattr(lean, name)).pin_memory()
         setattr(lean, name, tt.numpy())
         keep.append(tt)
@@ -652,7 +653,9 @@ def main():
     data, h2d, keep_lean = lean_copy(data_full, torch)
     for _ in range(2):
         out_e2e = al.run(data)
-    assert np.array_equal(out_e2e.iters, out.iters), "lean host inputs changed the result"
+    assert np.array_equal(out_e2e.iters, out.iters), "lean host inputs changed the decisions"
+    _a, _r = synth.pose_error(out_e2e.T_cur_w, out.T_cur_w)
+    assert _a.max() < 1e-9 and _r.max() < 1e-8, "lean host inputs changed the result"
     data_lean = data
     if dist:
         dist.barrier()

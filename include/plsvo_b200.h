@@ -87,6 +87,11 @@ typedef struct plsvo_align_params {
  * (`(pos_ - ref_pos).norm()`, sparse_img_align.cpp:229,337-340).  A caller that already holds these distances may pass
  * them in pt_depth / seg_sdepth / seg_edepth and leave pt_pos / seg_spos / seg_epos NULL (16 bytes less per point,
  * 32 per segment over PCIe).
+ *
+ * pt_f / seg_sf / seg_ef may be NULL when the camera is the undistorted pinhole `cam`: the bearing vectors are then
+ * formed on the device exactly as the reference's feature constructors form them, `cam_->cam2world(px)`
+ * (src/feature.cpp:42,98-99; vk::PinholeCamera::cam2world = ((u-cx)/fx, (v-cy)/fy, 1).normalized()).  24 bytes less
+ * per point, 48 per segment.
  */
 typedef struct plsvo_align_batch {
   int32_t batch;   /* B */
@@ -105,15 +110,15 @@ typedef struct plsvo_align_batch {
 
   const int32_t* pt_count;  /* [B] or NULL (= n_pts)  : pt_fts_.size() */
   const double* pt_px;      /* [B][n_pts][2]  PointFeat::px  (level-0 pixels) */
-  const double* pt_f;       /* [B][n_pts][3]  PointFeat::f   (unit bearing)   */
+  const double* pt_f;       /* [B][n_pts][3]  PointFeat::f   (unit bearing), or NULL = cam2world(px) */
   const double* pt_pos;     /* [B][n_pts][3]  PointFeat::feat3D->pos_ (world) */
   const uint8_t* pt_valid;  /* [B][n_pts] or NULL (= all valid): feat3D != NULL */
 
   const int32_t* seg_count; /* [B] or NULL (= n_segs) : seg_fts_.size() */
   const double* seg_spx;    /* [B][n_segs][2] LineFeat::spx */
   const double* seg_epx;    /* [B][n_segs][2] LineFeat::epx */
-  const double* seg_sf;     /* [B][n_segs][3] LineFeat::sf  */
-  const double* seg_ef;     /* [B][n_segs][3] LineFeat::ef  */
+  const double* seg_sf;     /* [B][n_segs][3] LineFeat::sf, or NULL = cam2world(spx) */
+  const double* seg_ef;     /* [B][n_segs][3] LineFeat::ef, or NULL = cam2world(epx) */
   const double* seg_spos;   /* [B][n_segs][3] LineFeat::feat3D->spos_ */
   const double* seg_epos;   /* [B][n_segs][3] LineFeat::feat3D->epos_ */
   const double* seg_length; /* [B][n_segs]    LineFeat::length */

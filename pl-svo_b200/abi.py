@@ -267,7 +267,7 @@ def make_align_batch(d):
     b.T_cur_w = _ptr(d.T_cur_w, np.float64)
     b.pt_count = _ptr(d.pt_count, np.int32)
     b.pt_px = _ptr(d.pt_px, np.float64)
-    b.pt_f = _ptr(d.pt_f, np.float64)
+    b.pt_f = _ptr(getattr(d, "pt_f", None), np.float64)
     b.pt_pos = _ptr(getattr(d, "pt_pos", None), np.float64)
     b.pt_depth = _ptr(getattr(d, "pt_depth", None), np.float64)
     b.pt_valid = _ptr(d.pt_valid, np.uint8)
@@ -275,8 +275,8 @@ def make_align_batch(d):
     if d.n_segs > 0:
         b.seg_spx = _ptr(d.seg_spx, np.float64)
         b.seg_epx = _ptr(d.seg_epx, np.float64)
-        b.seg_sf = _ptr(d.seg_sf, np.float64)
-        b.seg_ef = _ptr(d.seg_ef, np.float64)
+        b.seg_sf = _ptr(getattr(d, "seg_sf", None), np.float64)
+        b.seg_ef = _ptr(getattr(d, "seg_ef", None), np.float64)
         b.seg_spos = _ptr(getattr(d, "seg_spos", None), np.float64)
         b.seg_epos = _ptr(getattr(d, "seg_epos", None), np.float64)
         b.seg_sdepth = _ptr(getattr(d, "seg_sdepth", None), np.float64)
@@ -318,7 +318,7 @@ def make_poseopt_batch(d):
     b.fx = d.fx
     b.T_f_w = _ptr(d.T_f_w, np.float64)
     b.pt_count = _ptr(d.pt_count, np.int32)
-    b.pt_f = _ptr(d.pt_f, np.float64)
+    b.pt_f = _ptr(getattr(d, "pt_f", None), np.float64)
     b.pt_pos = _ptr(d.pt_pos, np.float64)
     b.pt_level = _ptr(d.pt_level, np.int32)
     b.pt_valid = _ptr(d.pt_valid, np.uint8)

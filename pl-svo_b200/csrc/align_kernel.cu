@@ -178,6 +178,15 @@ __device__ __forceinline__ bool cam_in_frame(int ox, int oy, int boundary, int l
          oy < height / (1 << level) - boundary;
 }
 
+// vk::PinholeCamera::cam2world without distortion (rpg_vikit pinhole_camera.cpp; the constructors of PointFeat / LineFeat
+// derive their bearing vectors this way, src/feature.cpp:42,98-99): ((u-cx)/fx, (v-cy)/fy, 1).normalized(), every
+// operation rounded on its own (Eigen: x / sqrt(x.x)).
+__device__ __forceinline__ void cam2world(const AlignArgs& a, const double* px, double* f) {
+  const double x = __ddiv_rn(__dsub_rn(px[0], a.cx), a.fx), y = __ddiv_rn(__dsub_rn(px[1], a.cy), a.fy);
+  const double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), 1.0));
+  f[0] = __ddiv_rn(x, n), f[1] = __ddiv_rn(y, n), f[2] = __ddiv_rn(1.0, n);
+}
+
 // Rank-2 update of the 21 (upper-triangular H) + 6 (Jres) accumulators of one thread for a patch whose 3-D
 // point has normalised coordinates (xn, yn) = (X/Z, Y/Z) and inverse depth zi = 1/Z:
 //   H += Sxx r0 r0^T + Sxy (r0 r1^T + r1 r0^T) + Syy r1 r1^T ,  Jres -= Sxr r0 + Syr r1
@@ -635,7 +644,10 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
     // per-pair point setup: xyz_ref = f * |pos - ref_pos| (:229-230), kept as (X/Z, Y/Z, 1/Z); visibility cleared
     for (int i = tid; i < np; i += NT) {
       pt_vis[i] = 0;
-      const double* f = a.pt_f + (po + i) * 3;
+      double fd[3];
+      const double* f = fd;
+      if (a.pt_f) f = a.pt_f + (po + i) * 3;
+      else cam2world(a, a.pt_px + (po + i) * 2, fd);  // bearing not shipped: PointFeat's own construction (feature.cpp:42)
       double depth;
       if (a.pt_depth) {
         depth = a.pt_depth[po + i];
@@ -746,8 +758,12 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
         const double nm1 = (double)(unsigned long long)(N - 1);
         const double inc2d0 = dif[0] * dscale / nm1, inc2d1 = dif[1] * dscale / nm1;
         double px0 = spx[0] * dscale, px1 = spx[1] * dscale;
-        const double* sf = a.seg_sf + (so + j) * 3;
-        const double* ef = a.seg_ef + (so + j) * 3;
+        double sfd[3], efd[3];
+        const double *sf = sfd, *ef = efd;
+        if (a.seg_sf) sf = a.seg_sf + (so + j) * 3;
+        else cam2world(a, spx, sfd);  // LineFeat's own construction (feature.cpp:98-99)
+        if (a.seg_ef) ef = a.seg_ef + (so + j) * 3;
+        else cam2world(a, epx, efd);
         double p_depth, q_depth;
         if (a.seg_sdepth) {
           p_depth = a.seg_sdepth[so + j];

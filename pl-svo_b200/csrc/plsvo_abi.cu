@@ -328,9 +328,9 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     if (h->batch <= 0 || h->n_pts < 0 || h->n_segs < 0 || h->n_segs > 32767)
       return fail(c, PLSVO_ERR_INVALID, "batch/n_pts/n_segs out of range");
     if (!h->T_ref_w || !h->T_cur_w) return fail(c, PLSVO_ERR_INVALID, "T_ref_w/T_cur_w missing");
-    if (h->n_pts > 0 && (!h->pt_px || !h->pt_f || (!h->pt_pos && !h->pt_depth)))
+    if (h->n_pts > 0 && (!h->pt_px || (!h->pt_pos && !h->pt_depth)))
       return fail(c, PLSVO_ERR_INVALID, "point arrays missing");
-    if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || !h->seg_sf || !h->seg_ef || (!h->seg_spos && !h->seg_sdepth) ||
+    if (h->n_segs > 0 && (!h->seg_spx || !h->seg_epx || (!h->seg_spos && !h->seg_sdepth) ||
                           (!h->seg_epos && !h->seg_edepth) || !h->seg_length))
       return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
     if (h->cam.width <= 0 || h->cam.height <= 0) return fail(c, PLSVO_ERR_INVALID, "camera size");

@@ -87,6 +87,21 @@ def test_depths_instead_of_positions(pkg, abi, synth, oracle, gen_device):
     assert ang.max() < 1e-10 and rel.max() < 1e-9
 
 
+def test_bearings_derived_from_pixels_on_the_device(pkg, synth, gen_device):
+    """pt_f / seg_sf / seg_ef = NULL: the device forms cam2world(px) as the reference's feature constructors do
+    (feature.cpp:42,98-99).  Same decisions; poses equal to round-off (the generator normalises with torch)."""
+    data = synth.make_align_batch(batch=16, n_pts=200, n_segs=48, device=gen_device, seed=6450)
+    full = pkg.SparseImgAlign(4, 2, 30).run(data)
+    lean = copy.copy(data)
+    lean.pt_f = lean.seg_sf = lean.seg_ef = None
+    got = pkg.SparseImgAlign(4, 2, 30).run(lean)
+    np.testing.assert_array_equal(got.iters, full.iters)
+    np.testing.assert_array_equal(got.n_tracked, full.n_tracked)
+    np.testing.assert_array_equal(got.seg_killed, full.seg_killed)
+    ang, rel = synth.pose_error(got.T_cur_w, full.T_cur_w)
+    assert ang.max() < 1e-10 and rel.max() < 1e-9
+
+
 def test_feature_counts_out_of_range_are_rejected(pkg, synth, gen_device):
     data = synth.make_align_batch(batch=4, n_pts=32, n_segs=8, device=gen_device, seed=6500)
     data.pt_count = np.array([32, 33, 1, 2], np.int32)
