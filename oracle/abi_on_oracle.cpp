@@ -1,4 +1,4 @@
-// abi_on_oracle.cpp — TEST INFRASTRUCTURE ONLY: the five C-ABI entry points the C++ shim calls, answered by the CPU oracle.
+// abi_on_oracle.cpp — TEST INFRASTRUCTURE ONLY: the six C-ABI entry points the C++ shim calls, answered by the CPU oracle.
 //
 // This is NOT a CPU fallback of the product (the product library, pl-svo_b200/csrc/libplsvo_b200.so, has none and is not
 // involved here).  It exists so that the shim's packing / unpacking of the reference's own Frame / Feature / SE3 objects
@@ -13,6 +13,7 @@
 extern "C" {
 int plsvo_oracle_align_batch(const plsvo_align_batch*, const plsvo_align_params*, const plsvo_align_result*, int, int);
 int plsvo_oracle_poseopt_batch(const plsvo_poseopt_batch*, const plsvo_poseopt_params*, const plsvo_poseopt_result*, int);
+int plsvo_oracle_structopt_batch(const plsvo_structopt_batch*, const plsvo_structopt_result*, int);
 
 struct plsvo_ctx {
   int unused;
@@ -29,5 +30,8 @@ int plsvo_align_batch_run(plsvo_ctx*, const plsvo_align_batch* b, const plsvo_al
 }
 int plsvo_poseopt_batch_run(plsvo_ctx*, const plsvo_poseopt_batch* b, const plsvo_poseopt_params* p, const plsvo_poseopt_result* o) {
   return plsvo_oracle_poseopt_batch(b, p, o, 1);
+}
+int plsvo_structopt_batch_run(plsvo_ctx*, const plsvo_structopt_batch* b, const plsvo_structopt_result* o) {
+  return plsvo_oracle_structopt_batch(b, o, 1);
 }
 }

@@ -418,3 +418,32 @@ def ref_line_seed_update(abi, data):
     if rc != 0:
         raise RuntimeError(f"reference line_seed_update failed rc={rc}")
     return out
+
+
+def _optimize_structure(fn, abi, data, pt_last, seg_last, max_n_pts, max_n_segs, frame_id):
+    from plsvo_b200 import abi as _abi  # noqa: F401
+
+    batch, keep = abi.make_structopt_batch(data)
+    out = abi.StructOptOut(data.pt_pos.shape[0], data.seg_spos.shape[0])
+    pl = np.ascontiguousarray(pt_last, dtype=np.int32).copy()
+    sl = np.ascontiguousarray(seg_last, dtype=np.int32).copy()
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(abi.StructOptBatch), C.POINTER(abi.StructOptResult), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                   C.c_int, C.c_int, C.c_int]
+    rc = fn(C.byref(batch), C.byref(out.struct), pl.ctypes.data_as(C.POINTER(C.c_int32)), sl.ctypes.data_as(C.POINTER(C.c_int32)),
+            max_n_pts, max_n_segs, frame_id)
+    if rc != 0:
+        raise RuntimeError(f"optimize_structure failed rc={rc}")
+    return out, pl, sl
+
+
+def ref_optimize_structure(abi, data, pt_last, seg_last, max_n_pts, max_n_segs, frame_id=77):
+    """FrameHandlerBase::optimizeStructure with the reference's own Point::optimize / LineSeg::optimize (oracle/_ref)."""
+    return _optimize_structure(load_ref(abi).plsvo_ref_optimize_structure, abi, data, pt_last, seg_last, max_n_pts, max_n_segs, frame_id)
+
+
+def shimref_optimize_structure(abi, data, pt_last, seg_last, max_n_pts, max_n_segs, frame_id=77, cpu: bool = False):
+    """The same call on reference-typed objects through the shim's plsvo::b200::optimizeStructure (C ABI: GPU, or the
+    oracle-backed adapter with cpu=True)."""
+    return _optimize_structure(load_shimref(abi, cpu).plsvo_shimref_optimize_structure, abi, data, pt_last, seg_last, max_n_pts,
+                               max_n_segs, frame_id)

@@ -36,6 +36,8 @@
 
 #include <atomic>
 #include <cstring>
+#include <algorithm>
+#include <deque>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -397,6 +399,98 @@ int plsvo_ref_structopt_batch(const plsvo_structopt_batch* in, const plsvo_struc
     ls.optimize((size_t)in->n_iter_segs);
     for (int k = 0; k < 3; ++k) out->seg_spos[3 * (size_t)i + k] = ls.spos_[k], out->seg_epos[3 * (size_t)i + k] = ls.epos_[k];
   }
+  return PLSVO_OK;
+}
+
+
+// Builds, from the flat CSR batch, the reference's own objects: keyframes, Points / LineSegs with their obs_ lists, and a
+// current frame whose pt_fts_ / seg_fts_ reference every 3-D feature; `last` carries last_structure_optim_.
+namespace {
+struct StructScene {
+  vk::PinholeCamera cam{640, 480, 300, 300, 320, 240};  // not read by optimize()
+  std::vector<FramePtr> keyframes;
+  FramePtr cur;
+  std::vector<std::unique_ptr<plsvo::Point>> pts;
+  std::vector<std::unique_ptr<plsvo::LineSeg>> segs;
+  StructScene(const plsvo_structopt_batch* in, const int32_t* pt_last, const int32_t* seg_last, int frame_id) {
+    for (int k = 0; k < in->n_frames; ++k) {
+      FramePtr f(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+      f->T_f_w_ = pose_from7(in->T_f_w + 7 * (size_t)k);
+      keyframes.push_back(f);
+    }
+    cur.reset(new plsvo::Frame(&cam, cv::Mat(), 1.0));
+    cur->id_ = frame_id;
+    for (int i = 0; i < in->n_points; ++i) {
+      pts.emplace_back(new plsvo::Point(v3(in->pt_pos + 3 * (size_t)i)));
+      plsvo::Point* pt = pts.back().get();
+      pt->last_structure_optim_ = pt_last ? pt_last[i] : 0;
+      for (int o = in->pt_obs_begin[i + 1] - 1; o >= in->pt_obs_begin[i]; --o) {  // addFrameRef pushes to the front
+        plsvo::Frame* kf = keyframes[in->pt_obs_frame[o]].get();
+        plsvo::PointFeat* ft = new plsvo::PointFeat(kf, pt, Vector2d(0, 0), v3(in->pt_obs_f + 3 * (size_t)o), 0);
+        kf->pt_fts_.push_back(ft);  // owned by the keyframe
+        pt->addFrameRef(ft);
+      }
+      cur->pt_fts_.push_back(new plsvo::PointFeat(cur.get(), pt, Vector2d(0, 0), Vector3d(0, 0, 1), 0));
+    }
+    for (int i = 0; i < in->n_segs; ++i) {
+      segs.emplace_back(new plsvo::LineSeg(v3(in->seg_spos + 3 * (size_t)i), v3(in->seg_epos + 3 * (size_t)i)));
+      plsvo::LineSeg* ls = segs.back().get();
+      ls->last_structure_optim_ = seg_last ? seg_last[i] : 0;
+      for (int o = in->seg_obs_begin[i + 1] - 1; o >= in->seg_obs_begin[i]; --o) {
+        plsvo::Frame* kf = keyframes[in->seg_obs_frame[o]].get();
+        plsvo::LineFeat* ft = new plsvo::LineFeat(kf, ls, Vector2d(0, 0), Vector2d(1, 0), v3(in->seg_obs_sf + 3 * (size_t)o),
+                                                  v3(in->seg_obs_ef + 3 * (size_t)o), 0);
+        kf->seg_fts_.push_back(ft);
+        ls->addFrameRef(ft);
+      }
+      cur->seg_fts_.push_back(new plsvo::LineFeat(cur.get(), ls, Vector2d(0, 0), Vector2d(1, 0), Vector3d(0, 0, 1), Vector3d(0, 0, 1), 0));
+    }
+  }
+  void read_back(const plsvo_structopt_batch* in, const plsvo_structopt_result* out, int32_t* pt_last, int32_t* seg_last) const {
+    for (int i = 0; i < in->n_points; ++i) {
+      for (int k = 0; k < 3; ++k) out->pt_pos[3 * (size_t)i + k] = pts[i]->pos_[k];
+      if (pt_last) pt_last[i] = pts[i]->last_structure_optim_;
+    }
+    for (int i = 0; i < in->n_segs; ++i) {
+      for (int k = 0; k < 3; ++k) out->seg_spos[3 * (size_t)i + k] = segs[i]->spos_[k], out->seg_epos[3 * (size_t)i + k] = segs[i]->epos_[k];
+      if (seg_last) seg_last[i] = segs[i]->last_structure_optim_;
+    }
+  }
+};
+}  // namespace
+
+// FrameHandlerBase::optimizeStructure (src/frame_handler_base.cpp:202-237) with the reference's own Point::optimize /
+// LineSeg::optimize (src/feature3D_impl.cpp, compiled in place).  frame_handler_base.cpp itself needs the whole
+// front end (detector, map, config), so its 30 lines of selection logic are restated here, line for line.
+extern "C" int plsvo_ref_optimize_structure(const plsvo_structopt_batch* in, const plsvo_structopt_result* out, int32_t* pt_last,
+                                            int32_t* seg_last, int max_n_pts_, int max_n_segs_, int frame_id) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  StructScene sc(in, pt_last, seg_last, frame_id);
+  FramePtr frame = sc.cur;
+  size_t max_n_pts = (size_t)max_n_pts_, max_n_segs = (size_t)max_n_segs_;
+  std::deque<plsvo::Point*> pts;  // :209-213
+  for (auto it = frame->pt_fts_.begin(); it != frame->pt_fts_.end(); ++it)
+    if ((*it)->feat3D != NULL) pts.push_back((*it)->feat3D);
+  max_n_pts = std::min(max_n_pts, pts.size());  // :214
+  std::nth_element(pts.begin(), pts.begin() + max_n_pts, pts.end(),
+                   [](plsvo::Point* l, plsvo::Point* r) { return l->last_structure_optim_ < r->last_structure_optim_; });  // :215, :192-195
+  for (auto it = pts.begin(); it != pts.begin() + max_n_pts; ++it) {  // :216-220
+    (*it)->optimize(in->n_iter_pts);
+    (*it)->last_structure_optim_ = frame->id_;
+  }
+  std::deque<plsvo::LineSeg*> segs;  // :222-226
+  for (auto it = frame->seg_fts_.begin(); it != frame->seg_fts_.end(); ++it) {
+    plsvo::LineFeat* f = static_cast<plsvo::LineFeat*>(*it);
+    if (f->feat3D != NULL) segs.push_back(f->feat3D);
+  }
+  max_n_segs = std::min(max_n_segs, segs.size());  // :227
+  std::nth_element(segs.begin(), segs.begin() + max_n_segs, segs.end(),
+                   [](plsvo::LineSeg* l, plsvo::LineSeg* r) { return l->last_structure_optim_ < r->last_structure_optim_; });  // :228
+  for (auto it = segs.begin(); it != segs.begin() + max_n_segs; ++it) {  // :229-233
+    (*it)->optimize(in->n_iter_segs);
+    (*it)->last_structure_optim_ = frame->id_;
+  }
+  sc.read_back(in, out, pt_last, seg_last);
   return PLSVO_OK;
 }
 

@@ -55,6 +55,63 @@ Vector3d v3(const double* p) { return Vector3d(p[0], p[1], p[2]); }
 Vector2d v2(const double* p) { return Vector2d(p[0], p[1]); }
 }  // namespace
 
+
+// Builds, from the flat CSR batch, the reference's own objects: keyframes, Points / LineSegs with their obs_ lists, and a
+// current frame whose pt_fts_ / seg_fts_ reference every 3-D feature; `last` carries last_structure_optim_.
+namespace {
+struct StructScene {
+  vk::PinholeCamera cam{640, 480, 300, 300, 320, 240};  // not read by optimize()
+  std::vector<FramePtr> keyframes;
+  FramePtr cur;
+  std::vector<std::unique_ptr<plsvo::Point>> pts;
+  std::vector<std::unique_ptr<plsvo::LineSeg>> segs;
+  StructScene(const plsvo_structopt_batch* in, const int32_t* pt_last, const int32_t* seg_last, int frame_id) {
+    for (int k = 0; k < in->n_frames; ++k) {
+      FramePtr f(new plsvo::Frame(&cam, cv::Mat(), 0.0));
+      f->T_f_w_ = pose_from7(in->T_f_w + 7 * (size_t)k);
+      keyframes.push_back(f);
+    }
+    cur.reset(new plsvo::Frame(&cam, cv::Mat(), 1.0));
+    cur->id_ = frame_id;
+    for (int i = 0; i < in->n_points; ++i) {
+      pts.emplace_back(new plsvo::Point(v3(in->pt_pos + 3 * (size_t)i)));
+      plsvo::Point* pt = pts.back().get();
+      pt->last_structure_optim_ = pt_last ? pt_last[i] : 0;
+      for (int o = in->pt_obs_begin[i + 1] - 1; o >= in->pt_obs_begin[i]; --o) {  // addFrameRef pushes to the front
+        plsvo::Frame* kf = keyframes[in->pt_obs_frame[o]].get();
+        plsvo::PointFeat* ft = new plsvo::PointFeat(kf, pt, Vector2d(0, 0), v3(in->pt_obs_f + 3 * (size_t)o), 0);
+        kf->pt_fts_.push_back(ft);  // owned by the keyframe
+        pt->addFrameRef(ft);
+      }
+      cur->pt_fts_.push_back(new plsvo::PointFeat(cur.get(), pt, Vector2d(0, 0), Vector3d(0, 0, 1), 0));
+    }
+    for (int i = 0; i < in->n_segs; ++i) {
+      segs.emplace_back(new plsvo::LineSeg(v3(in->seg_spos + 3 * (size_t)i), v3(in->seg_epos + 3 * (size_t)i)));
+      plsvo::LineSeg* ls = segs.back().get();
+      ls->last_structure_optim_ = seg_last ? seg_last[i] : 0;
+      for (int o = in->seg_obs_begin[i + 1] - 1; o >= in->seg_obs_begin[i]; --o) {
+        plsvo::Frame* kf = keyframes[in->seg_obs_frame[o]].get();
+        plsvo::LineFeat* ft = new plsvo::LineFeat(kf, ls, Vector2d(0, 0), Vector2d(1, 0), v3(in->seg_obs_sf + 3 * (size_t)o),
+                                                  v3(in->seg_obs_ef + 3 * (size_t)o), 0);
+        kf->seg_fts_.push_back(ft);
+        ls->addFrameRef(ft);
+      }
+      cur->seg_fts_.push_back(new plsvo::LineFeat(cur.get(), ls, Vector2d(0, 0), Vector2d(1, 0), Vector3d(0, 0, 1), Vector3d(0, 0, 1), 0));
+    }
+  }
+  void read_back(const plsvo_structopt_batch* in, const plsvo_structopt_result* out, int32_t* pt_last, int32_t* seg_last) const {
+    for (int i = 0; i < in->n_points; ++i) {
+      for (int k = 0; k < 3; ++k) out->pt_pos[3 * (size_t)i + k] = pts[i]->pos_[k];
+      if (pt_last) pt_last[i] = pts[i]->last_structure_optim_;
+    }
+    for (int i = 0; i < in->n_segs; ++i) {
+      for (int k = 0; k < 3; ++k) out->seg_spos[3 * (size_t)i + k] = segs[i]->spos_[k], out->seg_epos[3 * (size_t)i + k] = segs[i]->epos_[k];
+      if (seg_last) seg_last[i] = segs[i]->last_structure_optim_;
+    }
+  }
+};
+}  // namespace
+
 // wall time of every SparseImgAlign::run call of the last plsvo_shimref_align_batch (B = 1 latency, tools/b1_latency.py)
 static std::vector<double> g_run_seconds;
 
@@ -123,6 +180,19 @@ int plsvo_shimref_align_batch(const plsvo_align_batch* B, const plsvo_align_para
         out->seg_killed[so + j] = ((!B->seg_valid || B->seg_valid[so + j]) && segs[j]->feat3D == NULL) ? 1 : 0;
     }
   }
+  return PLSVO_OK;
+}
+
+// FrameHandlerBase::optimizeStructure(frame, max_n_pts, max_iter, max_n_segs, max_iter_segs) (frame_handler_base.cpp:
+// 202-237) on reference-typed objects through plsvo::b200::optimizeStructure (the shim's drop-in body): pt_last / seg_last
+// = last_structure_optim_ on entry and on return, out = every feature's position afterwards (optimised or not).
+int plsvo_shimref_optimize_structure(const plsvo_structopt_batch* in, const plsvo_structopt_result* out, int32_t* pt_last,
+                                     int32_t* seg_last, int max_n_pts, int max_n_segs, int frame_id) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  StructScene sc(in, pt_last, seg_last, frame_id);
+  const int rc = plsvo::b200::optimizeStructure(sc.cur, (size_t)max_n_pts, in->n_iter_pts, (size_t)max_n_segs, in->n_iter_segs);
+  if (rc != PLSVO_OK) return rc;
+  sc.read_back(in, out, pt_last, seg_last);
   return PLSVO_OK;
 }
 

@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -236,4 +238,89 @@ void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter, const 
   run(reproj_thresh, n_iter, (int)n_iter_ref, frame, estimated_scale, error_init, error_final, num_obs_pt, num_obs_ls);
 }
 }  // namespace pose_optimizer
+
+#ifdef PLSVO_SHIM_WITH_REFERENCE_HEADERS
+namespace b200 {
+int optimizeStructure(FramePtr frame, size_t max_n_pts, int max_iter, size_t max_n_segs, int max_iter_segs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  plsvo_ctx* c = ctx();
+  if (!c) return PLSVO_ERR_NO_DEVICE;
+  // selection: frame_handler_base.cpp:209-218 and :221-230, verbatim
+  std::deque<Point*> pts;
+  for (PointFeat* f : frame->pt_fts_)
+    if (f->feat3D != NULL) pts.push_back(f->feat3D);
+  max_n_pts = std::min(max_n_pts, pts.size());
+  std::nth_element(pts.begin(), pts.begin() + max_n_pts, pts.end(),
+                   [](Point* l, Point* r) { return l->last_structure_optim_ < r->last_structure_optim_; });
+  std::deque<LineSeg*> segs;
+  for (auto* f0 : frame->seg_fts_) {
+    LineFeat* f = static_cast<LineFeat*>(f0);
+    if (f->feat3D != NULL) segs.push_back(f->feat3D);
+  }
+  max_n_segs = std::min(max_n_segs, segs.size());
+  std::nth_element(segs.begin(), segs.begin() + max_n_segs, segs.end(),
+                   [](LineSeg* l, LineSeg* r) { return l->last_structure_optim_ < r->last_structure_optim_; });
+  // observation lists -> CSR in obs_ order (the reference's summation order), keyframe poses de-duplicated
+  std::vector<Frame*> frames;
+  std::vector<double> T;
+  auto frame_index = [&](Frame* f) {
+    for (size_t k = 0; k < frames.size(); ++k)
+      if (frames[k] == f) return (int32_t)k;
+    frames.push_back(f);
+    double p7[7];
+    pose7_of(f->T_f_w_, p7);
+    T.insert(T.end(), p7, p7 + 7);
+    return (int32_t)(frames.size() - 1);
+  };
+  std::vector<int32_t> pb(1, 0), pfr, sb(1, 0), sfr;
+  std::vector<double> pf, ppos, ssf, sef, sspos, sepos;
+  for (size_t i = 0; i < max_n_pts; ++i) {
+    for (PointFeat* o : pts[i]->obs_) {
+      pfr.push_back(frame_index(o->frame));
+      put(pf, o->f, 3);
+    }
+    pb.push_back((int32_t)pfr.size());
+    put(ppos, pts[i]->pos_, 3);
+  }
+  for (size_t i = 0; i < max_n_segs; ++i) {
+    for (LineFeat* o : segs[i]->obs_) {
+      sfr.push_back(frame_index(o->frame));
+      put(ssf, o->sf, 3);
+      put(sef, o->ef, 3);
+    }
+    sb.push_back((int32_t)sfr.size());
+    put(sspos, segs[i]->spos_, 3);
+    put(sepos, segs[i]->epos_, 3);
+  }
+  if (max_n_pts == 0 && max_n_segs == 0) return PLSVO_OK;
+  plsvo_structopt_batch b;
+  std::memset(&b, 0, sizeof b);
+  b.n_points = (int32_t)max_n_pts, b.n_segs = (int32_t)max_n_segs, b.n_frames = (int32_t)frames.size();
+  b.n_iter_pts = max_iter, b.n_iter_segs = max_iter_segs;
+  b.T_f_w = T.data();
+  b.pt_obs_begin = pb.data(), b.pt_obs_frame = pfr.data(), b.pt_obs_f = pf.data(), b.pt_pos = ppos.data();
+  b.seg_obs_begin = sb.data(), b.seg_obs_frame = sfr.data(), b.seg_obs_sf = ssf.data(), b.seg_obs_ef = sef.data();
+  b.seg_spos = sspos.data(), b.seg_epos = sepos.data();
+  std::vector<double> opos(3 * max_n_pts + 3), ospos(3 * max_n_segs + 3), oepos(3 * max_n_segs + 3);
+  plsvo_structopt_result r;
+  std::memset(&r, 0, sizeof r);
+  r.pt_pos = opos.data(), r.seg_spos = ospos.data(), r.seg_epos = oepos.data();
+  const int rc = plsvo_structopt_batch_run(c, &b, &r);
+  if (rc != PLSVO_OK) {
+    g_err = plsvo_last_error(c);
+    std::fprintf(stderr, "[plsvo_b200] optimizeStructure failed: %s\n", g_err.c_str());
+    return rc;
+  }
+  for (size_t i = 0; i < max_n_pts; ++i) {
+    for (int k = 0; k < 3; ++k) pts[i]->pos_[k] = opos[3 * i + k];
+    pts[i]->last_structure_optim_ = frame->id_;  // :217
+  }
+  for (size_t i = 0; i < max_n_segs; ++i) {
+    for (int k = 0; k < 3; ++k) segs[i]->spos_[k] = ospos[3 * i + k], segs[i]->epos_[k] = oepos[3 * i + k];
+    segs[i]->last_structure_optim_ = frame->id_;  // :229
+  }
+  return PLSVO_OK;
+}
+}  // namespace b200
+#endif
 }  // namespace plsvo

@@ -52,6 +52,19 @@ void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter, const 
                          size_t& num_obs_pt, size_t& num_obs_ls);
 }  // namespace pose_optimizer
 
+#ifdef PLSVO_SHIM_WITH_REFERENCE_HEADERS
+namespace b200 {
+/// Drop-in body of FrameHandlerBase::optimizeStructure (src/frame_handler_base.cpp:202-237; called at
+/// src/frame_handler_mono.cpp:340): the same selection of the max_n_pts / max_n_segs least recently optimised 3-D
+/// features of `frame` (nth_element on last_structure_optim_), then ALL their Point::optimize / LineSeg::optimize
+/// calls (src/feature3D_impl.cpp:36-174) in one plsvo_structopt_batch_run instead of a loop, and the write-back of
+/// pos_ / spos_ / epos_ / last_structure_optim_.  The reference function becomes the one line
+///     plsvo::b200::optimizeStructure(frame, max_n_pts, max_iter, max_n_segs, max_iter_segs);
+/// Returns the C-ABI status (PLSVO_OK = 0); on failure the map is left untouched.
+int optimizeStructure(FramePtr frame, size_t max_n_pts, int max_iter, size_t max_n_segs, int max_iter_segs);
+}  // namespace b200
+#endif
+
 /// process-wide device context used by the shim (SparseImgAlign is stack-constructed per call at
 /// frame_handler_mono.cpp:272, so the device state cannot live in the object)
 int shim_set_device(int device);

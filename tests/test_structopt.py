@@ -61,3 +61,42 @@ def test_gpu_structopt_points_only_segments_only_and_bad_input(pkg, oracle, abi,
     b, keep = abi.make_structopt_batch(d)
     out = abi.StructOptOut(50, 10)
     assert ctx.lib.plsvo_structopt_batch_run(ctx.handle, C.byref(b), C.byref(out.struct)) == abi.ERR_INVALID
+
+
+def _structure_case(synth):
+    d = synth.make_structopt_batch(n_points=300, n_segs=90, n_frames=9, seed=8123)
+    rng = np.random.default_rng(3)
+    return d, rng.integers(0, 50, 300).astype(np.int32), rng.integers(0, 50, 90).astype(np.int32)
+
+
+def _same_structure_result(a, b):
+    (oa, pa, sa), (ob, pb, sb) = a, b
+    np.testing.assert_array_equal(pa, pb)  # last_structure_optim_: the same features were selected
+    np.testing.assert_array_equal(sa, sb)
+    np.testing.assert_array_equal(oa.pt_pos, ob.pt_pos)
+    np.testing.assert_array_equal(oa.seg_spos, ob.seg_spos)
+    np.testing.assert_array_equal(oa.seg_epos, ob.seg_epos)
+
+
+def test_shim_optimize_structure_packs_reference_objects_like_the_reference_cpu(abi, synth, oracle):
+    """plsvo::b200::optimizeStructure (the drop-in body of FrameHandlerBase::optimizeStructure, frame_handler_base.cpp:
+    202-237) on the reference's own Point / LineSeg / Frame objects, its C-ABI call answered by the oracle (no GPU):
+    same selection, same positions, same last_structure_optim_ as the reference's own loop over Point::optimize."""
+    if not oracle.ref_available() or oracle.build_shimref_cpu() is None:
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    d, pl, sl = _structure_case(synth)
+    ref = oracle.ref_optimize_structure(abi, d, pl, sl, 20, 10)   # Config defaults: structureoptim_max_pts = 20
+    got = oracle.shimref_optimize_structure(abi, d, pl, sl, 20, 10, cpu=True)
+    _same_structure_result(got, ref)
+    assert (got[1] == 77).sum() == 20 and (got[2] == 77).sum() == 10
+
+
+@pytest.mark.gpu
+def test_shim_optimize_structure_on_the_gpu_is_bit_identical_to_the_reference(abi, synth, oracle):
+    if not oracle.ref_available() or oracle.build_shimref() is None:
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    d, pl, sl = _structure_case(synth)
+    for n_pts, n_segs in ((20, 10), (300, 90), (0, 5)):
+        ref = oracle.ref_optimize_structure(abi, d, pl, sl, n_pts, n_segs)
+        got = oracle.shimref_optimize_structure(abi, d, pl, sl, n_pts, n_segs)
+        _same_structure_result(got, ref)
