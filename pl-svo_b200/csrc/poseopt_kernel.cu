@@ -224,14 +224,18 @@ __device__ __forceinline__ void gn_loop(const PoseOptArgs& a, const Feat& F, PoC
       tot[lane] = s;
       __syncwarp();
       if (lane == 0) {
-        int idx = 0;
-        for (int i = 0; i < 6; ++i)
-          for (int j = i; j < 6; ++j) {
-            ctl->A[i * 6 + j] = tot[idx];
-            ctl->A[j * 6 + i] = tot[idx];
-            ++idx;
-          }
-        for (int i = 0; i < 6; ++i) ctl->b[i] = tot[21 + i];
+        // A (for Cov_ = (A*fx^2)^-1, :199, and for the pivoted fallback) is only unpacked where it is read: on the last
+        // evaluated pass and on a degenerate system — not on every pass of this serial section
+        auto unpack_A = [&]() {
+          int idx = 0;
+          for (int i = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j) {
+              ctl->A[i * 6 + j] = tot[idx];
+              ctl->A[j * 6 + i] = tot[idx];
+              ++idx;
+            }
+          for (int i = 0; i < 6; ++i) ctl->b[i] = tot[21 + i];
+        };
         const double new_chi2 = tot[27];
         {  // :170 — register LDL^T; the pivoted Eigen-style routine handles degenerate systems
           double Hu[21], gg[6], xx[6];
@@ -243,6 +247,7 @@ __device__ __forceinline__ void gn_loop(const PoseOptArgs& a, const Feat& F, PoC
 #pragma unroll
             for (int i = 0; i < 6; ++i) ctl->dT[i] = xx[i];
           } else {
+            unpack_A();
             ldlt6_solve(ctl->A, ctl->b, ctl->dT, ctl->scratch);
           }
         }
@@ -264,6 +269,7 @@ __device__ __forceinline__ void gn_loop(const PoseOptArgs& a, const Feat& F, PoC
         }
         ctl->iter += 1;
         if (ctl->iter >= n_iter) flag = 1;
+        if (flag) unpack_A();
         ctl->flag = flag;
       }
     }
