@@ -504,6 +504,10 @@ __device__ __noinline__ void gn_decide(PairCtl* ctl, const double* tot, float ch
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// producer side of a named barrier: counts this warp's threads in, does not wait
+__device__ __forceinline__ void named_barrier_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---- chi2 items (shared memory, 8 bytes): x = A_even (ulps added when the running sum's mantissa is even),
 // y = [15:0] A_odd - A_even (signed) | [23:16] biased float exponent of the binade | [24] opaque | [31:25] opaque slot
@@ -879,6 +883,12 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
 #ifdef PLSVO_TREE_CHI2
           chi2_tree += (double)Tf;
 #else
+          if (c >= n_chunks) {
+            // a warp whose chunk lies beyond the point list (last round only) signals the round barrier without waiting
+            // and goes on to its segment rounds: it needs none of the totals the others are about to exchange
+            named_barrier_arrive(2, NT);
+            continue;
+          }
           // -- estimate of the accumulator before this patch: exact prefix sum of the patch totals --
           double incl = (double)Tf;
 #pragma unroll
@@ -887,11 +897,11 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             if (lane >= d) incl += n;
           }
           if (lane == 31) chunk_tot[c] = incl;
-          __syncthreads();
+          named_barrier_sync(2, NT);  // every chunk total of this round is published (empty chunks only arrive)
           double P = prefix_rounds;
 #pragma unroll
           for (int w = 0; w < NW; ++w) {
-            const double tw = chunk_tot[r * NW + w];
+            const double tw = (r * NW + w < n_chunks) ? chunk_tot[r * NW + w] : 0.0;
             if (w < warp) P += tw;
             prefix_rounds += tw;
           }
@@ -1147,7 +1157,7 @@ __global__ void __launch_bounds__(NT, MINB) sparse_img_align_kernel(const AlignA
             if (ctl->n_opq > kOpqCap) {
               // opaque buffer overflowed (flag 1): fall back to the estimate of the point sum for this pass
               double e = 0.0;
-              for (int c = 0; c < rounds * NW; ++c) e += chunk_tot[c];
+              for (int c = 0; c < n_chunks; ++c) e += chunk_tot[c];
               s = (float)e;
             }
             if (bad) atomicOr(&ctl->chi2_flags, 2);
@@ -1247,7 +1257,7 @@ size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_slot
 // Kernel variants: CTA size x resident CTAs per SM the register budget is compiled for.  Small CTAs with many
 // resident pairs hide each pair's serial solve and barriers behind the other pairs and let a batch of ~7 pairs per
 // SM run in a single wave; big CTAs cut the latency of a pair when the batch is small.
-#define PLSVO_ALIGN_VARIANTS(X) X(64, 8) X(96, 7) X(96, 5) X(128, 5) X(128, 4) X(256, 2)
+#define PLSVO_ALIGN_VARIANTS(X) X(64, 8) X(96, 7) X(96, 5) X(128, 5) X(128, 4) X(160, 3) X(192, 2) X(256, 2)
 
 namespace {
 template <int NT, int MINB>

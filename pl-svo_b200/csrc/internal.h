@@ -71,7 +71,7 @@ struct AlignArgs {
 // shared memory the kernel needs for a configuration (host + device agree through this)
 size_t align_smem_bytes(int n_pts, int n_segs, int max_patches, int max_seg_slots, int img_bytes, int threads);
 // kernel variants are compiled per (threads per CTA, resident CTAs per SM the register budget allows):
-// (64,8) (96,7) (96,5) (128,5) (128,4) (256,2)
+// (64,8) (96,7) (96,5) (128,5) (128,4) (160,3) (192,2) (256,2)
 cudaError_t align_kernel_prepare(int threads, int min_blocks, size_t smem_bytes, int* ctas_per_sm);
 cudaError_t weight_selftest_launch(uint32_t n, uint32_t seed, unsigned long long* d_mismatch, cudaStream_t s);
 cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, int min_blocks, size_t smem_bytes,

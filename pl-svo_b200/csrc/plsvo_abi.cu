@@ -605,7 +605,7 @@ struct AlignPlan {
 };
 
 // kernel variants (threads per CTA, resident CTAs per SM the register budget is compiled for), see align_kernel.cu
-static const int kAlignVariants[][2] = {{128, 4}, {128, 5}, {96, 5}, {96, 7}, {64, 8}, {256, 2}};
+static const int kAlignVariants[][2] = {{128, 4}, {128, 5}, {96, 5}, {96, 7}, {64, 8}, {160, 3}, {192, 2}, {256, 2}};
 
 int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, AlignPlan* plan) {
   if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_launch before plsvo_align_upload");
