@@ -278,7 +278,10 @@ __device__ __forceinline__ void gn_loop(const PoseOptArgs& a, const Feat& F, PoC
   }
 }
 
-__global__ void __launch_bounds__(kPoThreads) pose_optimizer_kernel(const PoseOptArgs a) {
+#ifndef PLSVO_PO_MINB
+#define PLSVO_PO_MINB 3  // resident CTAs per SM the register budget is compiled for (168 registers fit three)
+#endif
+__global__ void __launch_bounds__(kPoThreads, PLSVO_PO_MINB) pose_optimizer_kernel(const PoseOptArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int n_tot = a.n_pts + a.n_segs;

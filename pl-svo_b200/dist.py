@@ -67,10 +67,13 @@ def _manifest(arrays):
     return manifest, max(off, 256)
 
 
-def _pack_into(buf, arrays, manifest):
-    """Copy every array to its 256-byte aligned place inside the uint8 block `buf` (a numpy view)."""
-    for (name, dt, shape, o, nb), (_, a) in zip(manifest, arrays):
-        buf[o:o + nb] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+def _pack_jobs(buf, arrays, manifest):
+    """One copy job per array: to its 256-byte aligned place inside the uint8 block `buf` (a numpy view)."""
+    def job(o, nb, a):
+        def run():
+            buf[o:o + nb] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        return run
+    return [job(o, nb, a) for (name, dt, shape, o, nb), (_, a) in zip(manifest, arrays)]
 
 
 def _unpack(buf, manifest):
@@ -121,8 +124,14 @@ def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30
                  "levels": (data.max_level, data.min_level)}]
         stage = _staging("src", cap * world, pin)  # one pinned block, one H2D copy for all shards
         host = stage.numpy()
+        jobs = []
         for r, (sh, (mf, _)) in enumerate(zip(shards, mans)):
-            _pack_into(host[r * cap:(r + 1) * cap], sh, mf)
+            jobs += _pack_jobs(host[r * cap:(r + 1) * cap], sh, mf)
+        # the packing is plain memory copies (NumPy releases the GIL): spread them over a few host threads
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=8) as pool:
+            list(pool.map(lambda j: j(), jobs))
         dev_all = stage[: cap * world].to(dev, non_blocking=True)
         bufs = list(dev_all.split(cap))
     dist.broadcast_object_list(meta, src=src)
