@@ -195,3 +195,28 @@ def test_shim_packs_reference_objects_like_the_reference_reads_them(ref, abi, sy
         np.testing.assert_allclose(got.cov, want.cov, rtol=1e-9, atol=1e-15)
         for f in ("estimated_scale", "error_init", "error_final"):
             np.testing.assert_allclose(getattr(got, f), getattr(want, f), rtol=1e-12, err_msg=f)
+
+
+def test_sequence_chain_oracle_equals_reference_chain(abi, synth, oracle):
+    """BASELINE config 1 on the CPU: frame-to-frame chain (align -> pose-opt, the estimate seeds the next frame,
+    frame_handler_mono.cpp:263-340) over short QVGA sequences — the oracle restatement and the reference's own
+    translation units give bit-identical poses, iteration counts and outlier flags at every frame, and the chain tracks
+    the ground-truth trajectory."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    poses, steps = synth.make_sequence(cam=synth.QVGA, n_seq=2, n_frames=6, n_pts=120, n_segs=30, seed=1000)
+
+    def chain(align_fn, po_fn):
+        def step(al, po):
+            ra = align_fn(abi, al, abi.align_params(al.max_level, al.min_level, 30), n_threads=4)
+            po.T_f_w = np.ascontiguousarray(ra.T_cur_w)
+            return ra, po_fn(abi, po, abi.poseopt_params(2.0, 10, -1), n_threads=4)
+        return synth.run_sequence(poses, steps, step)
+
+    est_o, it_o, out_o = chain(oracle.align, oracle.poseopt)
+    est_r, it_r, out_r = chain(oracle.ref_align, oracle.ref_poseopt)
+    np.testing.assert_array_equal(est_o, est_r)
+    np.testing.assert_array_equal(it_o, it_r)
+    np.testing.assert_array_equal(out_o, out_r)
+    ang, rel = synth.pose_error(est_r[:, -1], poses[:, -1])
+    assert ang.max() < 1e-2
