@@ -57,6 +57,10 @@ struct plsvo_ctx_impl {
   int der_src = -1, der_top = -1;    // derived levels are (der_src, der_top], built from uploaded level der_src
   bool lvl_uploaded[PLSVO_MAX_LEVELS] = {false};
   DevBuf d_pt_depth, d_seg_sdepth, d_seg_edepth;
+  DevBuf d_feat;                     // small batches: every feature array in one block (one host->device copy)
+  char* h_in = nullptr;              // pinned staging of the small-batch upload
+  size_t h_in_cap = 0, img_total = 0;
+  cudaEvent_t h_in_ev = nullptr;     // the staged copies of the previous small upload
   DevBuf d_ref_img, d_cur_img, d_T_ref, d_T_cur, d_pt_count, d_pt_px, d_pt_f, d_pt_pos, d_pt_valid, d_seg_count,
       d_seg_spx, d_seg_epx, d_seg_sf, d_seg_ef, d_seg_spos, d_seg_epos, d_seg_length, d_seg_valid;
   DevBuf d_out_T, d_out_ntr, d_out_H, d_out_killed, d_out_iters, d_out_status, d_out_pi, d_out_pl, d_counter,
@@ -197,7 +201,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
                     &c->d_seg_sf,    &c->d_seg_ef,   &c->d_seg_spos,  &c->d_seg_epos,   &c->d_seg_length, &c->d_seg_valid,
                     &c->d_out_T,     &c->d_out_ntr,  &c->d_out_H,     &c->d_out_killed, &c->d_out_iters, &c->d_out_status,
-                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_ref_der,   &c->d_cur_der,   &c->d_pt_depth,  &c->d_seg_sdepth, &c->d_seg_edepth, &c->d_ws_segpx,  &c->d_ws_rec,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
+                    &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_ref_der,   &c->d_cur_der,   &c->d_pt_depth,  &c->d_seg_sdepth, &c->d_seg_edepth, &c->d_feat, &c->d_ws_segpx,  &c->d_ws_rec,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
                     &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->m_ref_img,   &c->m_cur_img,   &c->m_T_ref,     &c->m_T_cur,
                     &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
                     &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
@@ -211,6 +215,8 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
   for (DevBuf* b : bufs) release(*b);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_in) cudaFreeHost(c->h_in);
+  if (c->h_in_ev) cudaEventDestroy(c->h_in_ev);
   for (int k = 0; k < 4; ++k) {
     if (c->rr_stream[k]) cudaStreamDestroy(c->rr_stream[k]);
     if (c->rr_ev[k]) cudaEventDestroy(c->rr_ev[k]);
@@ -366,12 +372,95 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     }
     CK(ensure(c->d_ref_img, total + 256));
     CK(ensure(c->d_cur_img, total + 256));
+    c->img_total = total;
     c->der_src = c->der_top = -1;
     size_t stage = 0;
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
       if (a.pitch[l] && h->img_pitch[l] != a.pitch[l]) stage = std::max(stage, 2 * h->img_stride[l] * B);
     if (stage) CK(ensure(c->d_stage, stage));
   }
+  // ---- small batches (the reference's own call is B = 1, frame_handler_mono.cpp:272): every input is packed into one
+  // pinned staging block and moves with three copies (reference images, current images, all feature arrays) instead of
+  // ~20 separate copies from pageable memory, each of which costs more than the kernel of a single pair ----
+  {
+    const size_t np_ = (size_t)h->n_pts, ns_ = (size_t)h->n_segs;
+    struct Item {
+      const void* host;
+      size_t bytes;
+      const void** dev;
+    };
+    const Item items[] = {
+        {h->T_ref_w, B * 7 * 8, (const void**)&a.T_ref_w},
+        {h->T_cur_w, B * 7 * 8, (const void**)&a.T_cur_w},
+        {h->pt_count, B * 4, (const void**)&a.pt_count},
+        {h->pt_px, B * np_ * 16, (const void**)&a.pt_px},
+        {h->pt_f, B * np_ * 24, (const void**)&a.pt_f},
+        {h->pt_depth ? nullptr : h->pt_pos, B * np_ * 24, (const void**)&a.pt_pos},
+        {h->pt_depth, B * np_ * 8, (const void**)&a.pt_depth},
+        {h->pt_valid, B * np_, (const void**)&a.pt_valid},
+        {h->seg_count, B * 4, (const void**)&a.seg_count},
+        {h->seg_spx, B * ns_ * 16, (const void**)&a.seg_spx},
+        {h->seg_epx, B * ns_ * 16, (const void**)&a.seg_epx},
+        {h->seg_sf, B * ns_ * 24, (const void**)&a.seg_sf},
+        {h->seg_ef, B * ns_ * 24, (const void**)&a.seg_ef},
+        {h->seg_sdepth ? nullptr : h->seg_spos, B * ns_ * 24, (const void**)&a.seg_spos},
+        {h->seg_edepth ? nullptr : h->seg_epos, B * ns_ * 24, (const void**)&a.seg_epos},
+        {h->seg_sdepth, B * ns_ * 8, (const void**)&a.seg_sdepth},
+        {h->seg_edepth, B * ns_ * 8, (const void**)&a.seg_edepth},
+        {h->seg_length, B * ns_ * 8, (const void**)&a.seg_length},
+        {h->seg_valid, B * ns_, (const void**)&a.seg_valid},
+    };
+    size_t feat_total = 0;
+    for (const Item& it : items)
+      if (it.host && it.bytes) feat_total += (it.bytes + 255) / 256 * 256;
+    bool small = prepare && b0 == 0 && b1 == B && c->rr_n == 0 && s == c->stream && !getenv("PLSVO_NO_SMALL_UPLOAD") &&
+                 2 * c->img_total + feat_total <= (size_t)4 << 20;
+    for (int l = 0; l < PLSVO_MAX_LEVELS && small; ++l) {
+      if (!c->lvl_uploaded[l]) continue;
+      const int rows = h->cam.height >> l;
+      if (!(h->img_stride[l] == (size_t)rows * h->img_pitch[l] && h->img_pitch[l] == a.pitch[l])) small = false;  // needs the repack path
+    }
+    if (small) {
+      const size_t need = 2 * c->img_total + feat_total + 256;
+      if (c->h_in_cap < need) {
+        if (c->h_in) cudaFreeHost(c->h_in);
+        c->h_in = nullptr, c->h_in_cap = 0;
+        CK(cudaHostAlloc((void**)&c->h_in, need, cudaHostAllocDefault));
+        c->h_in_cap = need;
+      }
+      if (!c->h_in_ev) CK(cudaEventCreateWithFlags(&c->h_in_ev, cudaEventDisableTiming));
+      else CK(cudaEventSynchronize(c->h_in_ev));  // the previous upload's copies have left the staging block
+      CK(ensure(c->d_feat, feat_total + 256));
+      char* hr = c->h_in;
+      char* hc = c->h_in + c->img_total;
+      char* hf = c->h_in + 2 * c->img_total;
+      for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+        if (!c->lvl_uploaded[l]) continue;
+        memcpy(hr + c->level_off[l], h->ref_img[l], a.stride[l] * B);
+        memcpy(hc + c->level_off[l], h->cur_img[l], a.stride[l] * B);
+        a.ref_img[l] = static_cast<uint8_t*>(c->d_ref_img.p) + c->level_off[l];
+        a.cur_img[l] = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
+      }
+      size_t off = 0;
+      for (const Item& it : items) {
+        if (!it.host || !it.bytes) {
+          *it.dev = nullptr;
+          continue;
+        }
+        memcpy(hf + off, it.host, it.bytes);
+        *it.dev = static_cast<char*>(c->d_feat.p) + off;
+        off += (it.bytes + 255) / 256 * 256;
+      }
+      if (c->img_total) {
+        CK(cudaMemcpyAsync(c->d_ref_img.p, hr, c->img_total, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(c->d_cur_img.p, hc, c->img_total, cudaMemcpyHostToDevice, s));
+      }
+      if (feat_total) CK(cudaMemcpyAsync(c->d_feat.p, hf, feat_total, cudaMemcpyHostToDevice, s));
+      CK(cudaEventRecord(c->h_in_ev, s));
+      goto copies_done;
+    }
+  }
+  {
   const size_t nb = b1 - b0;
   for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
     if (!c->lvl_uploaded[l]) continue;
@@ -427,6 +516,8 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   CK(up_range(c->d_seg_edepth, h->seg_edepth, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_edepth, prepare));
   CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_length, prepare));
   CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_valid, prepare));
+  }
+copies_done:;
   }  // mode != 3
   if (mode == 0 || mode == 2) return PLSVO_OK;
 
