@@ -123,12 +123,17 @@ def measured_hbm_peak():
 
 
 def kernel_source_hash():
-    """sha256 over the alignment kernel's sources: ties a committed ncu traffic capture to the code it measured."""
+    """sha256 over the alignment kernel's sources (align_kernel.cu, device_math.cuh, the AlignArgs block of internal.h): ties a committed ncu traffic capture to the code it measured."""
     import hashlib
 
     h = hashlib.sha256()
-    for f in ("align_kernel.cu", "device_math.cuh", "internal.h"):
-        h.update(open(os.path.join(ROOT, "pl-svo_b200", "csrc", f), "rb").read())
+    csrc = os.path.join(ROOT, "pl-svo_b200", "csrc")
+    for f in ("align_kernel.cu", "device_math.cuh"):
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    # internal.h: only the alignment kernel's argument block (everything before the first separator line; the other
+    # kernels' argument structs follow it and do not enter this kernel)
+    head = open(os.path.join(csrc, "internal.h"), "rb").read().split(b"\n// -----", 1)[0]
+    h.update(head)
     return h.hexdigest()
 
 

@@ -346,6 +346,8 @@ typedef struct plsvo_match_result {
   double* px_cur;        /* [n][2] px_cur on return (untouched where the in-frame test fails) */
   uint8_t* success;      /* [n]    return value of findMatchDirect */
   int32_t* search_level; /* [n]    Matcher::search_level_ (-1 where the in-frame test fails) */
+  double* A_cur_ref;     /* [n][4] or NULL: Matcher::A_cur_ref_ row-major (A00 A01 A10 A11), which Reprojector::refine reads for
+                          *        edgelets (src/reprojector.cpp:318-320); untouched where the in-frame test fails */
 } plsvo_match_result;
 
 int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out);
@@ -471,6 +473,9 @@ typedef struct plsvo_line_seed_result {
   float* mu_e;             /* [n] */
   float* sigma2_e;         /* [n] */
   double* depth_e;         /* [n] z_e (NaN unless status == UPDATED) */
+  double* px_cur_e;        /* [n][2] or NULL: Matcher::px_cur_ of the end-point search — what matcherls_.px_cur_ holds when
+                            *        DepthFilter::updateLineSeeds marks the detector grid on keyframes (:426-430); NaN where the
+                            *        end-point search did not run or computed no position */
 } plsvo_line_seed_result;
 
 int plsvo_line_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_line_seed_batch* in, const plsvo_line_seed_result* out);

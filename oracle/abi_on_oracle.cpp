@@ -1,4 +1,4 @@
-// abi_on_oracle.cpp — TEST INFRASTRUCTURE ONLY: the six C-ABI entry points the C++ shim calls, answered by the CPU oracle.
+// abi_on_oracle.cpp — TEST INFRASTRUCTURE ONLY: the C-ABI entry points the C++ shim calls, answered by the CPU oracle.
 //
 // This is NOT a CPU fallback of the product (the product library, pl-svo_b200/csrc/libplsvo_b200.so, has none and is not
 // involved here).  It exists so that the shim's packing / unpacking of the reference's own Frame / Feature / SE3 objects
@@ -14,6 +14,9 @@ extern "C" {
 int plsvo_oracle_align_batch(const plsvo_align_batch*, const plsvo_align_params*, const plsvo_align_result*, int, int);
 int plsvo_oracle_poseopt_batch(const plsvo_poseopt_batch*, const plsvo_poseopt_params*, const plsvo_poseopt_result*, int);
 int plsvo_oracle_structopt_batch(const plsvo_structopt_batch*, const plsvo_structopt_result*, int);
+int plsvo_oracle_match_direct_batch(const plsvo_match_batch*, const plsvo_match_result*, int);
+int plsvo_oracle_seed_update_batch(const plsvo_seed_batch*, const plsvo_seed_result*, int);
+int plsvo_oracle_line_seed_update_batch(const plsvo_line_seed_batch*, const plsvo_line_seed_result*, int);
 
 struct plsvo_ctx {
   int unused;
@@ -33,5 +36,14 @@ int plsvo_poseopt_batch_run(plsvo_ctx*, const plsvo_poseopt_batch* b, const plsv
 }
 int plsvo_structopt_batch_run(plsvo_ctx*, const plsvo_structopt_batch* b, const plsvo_structopt_result* o) {
   return plsvo_oracle_structopt_batch(b, o, 1);
+}
+int plsvo_match_direct_batch_run(plsvo_ctx*, const plsvo_match_batch* b, const plsvo_match_result* o) {
+  return plsvo_oracle_match_direct_batch(b, o, 4);
+}
+int plsvo_seed_update_batch_run(plsvo_ctx*, const plsvo_seed_batch* b, const plsvo_seed_result* o) {
+  return plsvo_oracle_seed_update_batch(b, o, 4);
+}
+int plsvo_line_seed_update_batch_run(plsvo_ctx*, const plsvo_line_seed_batch* b, const plsvo_line_seed_result* o) {
+  return plsvo_oracle_line_seed_update_batch(b, o, 4);
 }
 }

@@ -447,3 +447,92 @@ def shimref_optimize_structure(abi, data, pt_last, seg_last, max_n_pts, max_n_se
     oracle-backed adapter with cpu=True)."""
     return _optimize_structure(load_shimref(abi, cpu).plsvo_shimref_optimize_structure, abi, data, pt_last, seg_last, max_n_pts,
                                max_n_segs, frame_id)
+
+
+# ---- reference-typed scenes for the loops either side of the hot path (oracle/next_scenes.h) ---------------------------
+class SceneMatchOut(C.Structure):
+    _fields_ = [("pt_found", C.POINTER(C.c_uint8)), ("pt_px", C.POINTER(C.c_double)), ("pt_level", C.POINTER(C.c_int32)),
+                ("pt_A", C.POINTER(C.c_double)), ("pt_ref", C.POINTER(C.c_int32)), ("seg_found", C.POINTER(C.c_uint8)),
+                ("seg_spx", C.POINTER(C.c_double)), ("seg_epx", C.POINTER(C.c_double)), ("seg_level", C.POINTER(C.c_int32)),
+                ("seg_A", C.POINTER(C.c_double)), ("seg_ref", C.POINTER(C.c_int32))]
+
+
+class SceneSeedOut(C.Structure):
+    _fields_ = [("pt_fate", C.POINTER(C.c_int32)), ("pt_state", C.POINTER(C.c_float)), ("pt_xyz", C.POINTER(C.c_double)),
+                ("pt_cb_sigma2", C.POINTER(C.c_double)), ("n_pt_marks", C.POINTER(C.c_int32)), ("pt_marks", C.POINTER(C.c_double)),
+                ("seg_fate", C.POINTER(C.c_int32)), ("seg_state", C.POINTER(C.c_float)), ("seg_xyz", C.POINTER(C.c_double)),
+                ("seg_cb_sigma2", C.POINTER(C.c_double)), ("n_seg_marks", C.POINTER(C.c_int32)), ("seg_marks", C.POINTER(C.c_double))]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class _Rec:
+    pass
+
+
+def _match_scene(fn, abi, data, n_obs):
+    n, m = data.n, data.n // 2
+    r = _Rec()
+    r.pt_found, r.pt_px, r.pt_level = np.zeros(n, np.uint8), np.full((n, 2), np.nan), np.full(n, -99, np.int32)
+    r.pt_A, r.pt_ref = np.full((n, 4), np.nan), np.full(n, -99, np.int32)
+    r.seg_found, r.seg_spx, r.seg_epx = np.zeros(m, np.uint8), np.full((m, 2), np.nan), np.full((m, 2), np.nan)
+    r.seg_level, r.seg_A, r.seg_ref = np.full(m, -99, np.int32), np.full((m, 4), np.nan), np.full(m, -99, np.int32)
+    out = SceneMatchOut(_p(r.pt_found, C.c_uint8), _p(r.pt_px, C.c_double), _p(r.pt_level, C.c_int32), _p(r.pt_A, C.c_double),
+                        _p(r.pt_ref, C.c_int32), _p(r.seg_found, C.c_uint8), _p(r.seg_spx, C.c_double), _p(r.seg_epx, C.c_double),
+                        _p(r.seg_level, C.c_int32), _p(r.seg_A, C.c_double), _p(r.seg_ref, C.c_int32))
+    b, keep = abi.make_match_batch(data)
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(abi.MatchBatch), C.c_int, C.POINTER(SceneMatchOut)]
+    rc = fn(C.byref(b), n_obs, C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"match scene failed rc={rc}")
+    return r
+
+
+def ref_match_scene(abi, data, n_obs=3):
+    """Reprojector-style pass with the reference's own Matcher::findMatchDirect + Point/LineSeg::getCloseViewObs (oracle/_ref)
+    over map points / segments observed in n_obs keyframes."""
+    return _match_scene(load_ref(abi).plsvo_ref_match_scene, abi, data, n_obs)
+
+
+def shimref_match_scene(abi, data, n_obs=3, cpu: bool = False):
+    """The same pass answered by plsvo::b200::DirectMatcher (one C-ABI call per frame: GPU, or the oracle-backed adapter)."""
+    return _match_scene(load_shimref(abi, cpu).plsvo_shimref_match_scene, abi, data, n_obs)
+
+
+def _seed_scene(fn, abi, pts, lines, pt_age, seg_age, is_keyframe):
+    n, m = pts.n, (lines.n if lines is not None else 0)
+    r = _Rec()
+    r.pt_fate, r.pt_state, r.pt_xyz = np.full(n, -1, np.int32), np.full((n, 4), np.nan, np.float32), np.full((n, 3), np.nan)
+    r.pt_cb_sigma2, r.n_pt_marks, r.pt_marks = np.full(n, np.nan), np.zeros(1, np.int32), np.full((n + 1, 2), np.nan)
+    r.seg_fate, r.seg_state, r.seg_xyz = np.full(m + 1, -1, np.int32), np.full((m + 1, 6), np.nan, np.float32), np.full((m + 1, 6), np.nan)
+    r.seg_cb_sigma2, r.n_seg_marks, r.seg_marks = np.full((m + 1, 2), np.nan), np.zeros(1, np.int32), np.full((m + 1, 4), np.nan)
+    out = SceneSeedOut(_p(r.pt_fate, C.c_int32), _p(r.pt_state, C.c_float), _p(r.pt_xyz, C.c_double), _p(r.pt_cb_sigma2, C.c_double),
+                       _p(r.n_pt_marks, C.c_int32), _p(r.pt_marks, C.c_double), _p(r.seg_fate, C.c_int32), _p(r.seg_state, C.c_float),
+                       _p(r.seg_xyz, C.c_double), _p(r.seg_cb_sigma2, C.c_double), _p(r.n_seg_marks, C.c_int32), _p(r.seg_marks, C.c_double))
+    pb, keep = abi.make_seed_batch(pts)
+    lb, lkeep = abi.make_line_seed_batch(lines) if lines is not None else (None, None)
+    pa = np.ascontiguousarray(pt_age, np.int32) if pt_age is not None else None
+    sa = np.ascontiguousarray(seg_age, np.int32) if seg_age is not None else None
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(abi.SeedBatch), C.POINTER(abi.LineSeedBatch), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
+                   C.POINTER(SceneSeedOut)]
+    rc = fn(C.byref(pb), C.byref(lb) if lb is not None else None, _p(pa, C.c_int32) if pa is not None else None,
+            _p(sa, C.c_int32) if sa is not None else None, int(is_keyframe), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"seed scene failed rc={rc}")
+    r.seg_fate, r.seg_state, r.seg_xyz, r.seg_cb_sigma2 = r.seg_fate[:m], r.seg_state[:m], r.seg_xyz[:m], r.seg_cb_sigma2[:m]
+    r.pt_marks, r.seg_marks = r.pt_marks[: r.n_pt_marks[0]], r.seg_marks[: r.n_seg_marks[0]]
+    return r
+
+
+def ref_seed_scene(abi, pts, lines=None, pt_age=None, seg_age=None, is_keyframe=False):
+    """DepthFilter::updateSeeds of the reference's own depth_filter.cpp (real ageing, convergence, callbacks, detector marks)."""
+    return _seed_scene(load_ref(abi).plsvo_ref_seed_scene, abi, pts, lines, pt_age, seg_age, is_keyframe)
+
+
+def shimref_seed_scene(abi, pts, lines=None, pt_age=None, seg_age=None, is_keyframe=False, cpu: bool = False):
+    """The same update through plsvo::b200::DepthFilterB200 (two C-ABI calls per frame: GPU, or the oracle-backed adapter)."""
+    return _seed_scene(load_shimref(abi, cpu).plsvo_shimref_seed_scene, abi, pts, lines, pt_age, seg_age, is_keyframe)

@@ -1406,6 +1406,7 @@ static void match_direct_one(const plsvo_match_batch* in, const plsvo_match_resu
   warp_matrix_affine(cam, px_ref, f_ref, depth_ref, T_cur_ref, level_ref, A);
   const int search_level = best_search_level(A, in->n_pyr_levels - 1);
   if (out->search_level) out->search_level[i] = search_level;
+  if (out->A_cur_ref) out->A_cur_ref[4 * I] = A[0][0], out->A_cur_ref[4 * I + 1] = A[0][1], out->A_cur_ref[4 * I + 2] = A[1][0], out->A_cur_ref[4 * I + 3] = A[1][1];
   uint8_t patch_with_border[100] = {0};
   uint8_t patch[64];
   warp_affine_patches(A, in->ref_img[level_ref] + (size_t)in->ref_index[i] * in->ref_stride[level_ref], (int)in->ref_pitch[level_ref],
@@ -1941,6 +1942,7 @@ static void line_seed_update_one(const plsvo_line_seed_batch* inl, const plsvo_l
   if (out->depth) out->depth[i] = z_s;
   if (outl->depth_e) outl->depth_e[i] = z_e;
   if (out->px_cur) out->px_cur[2 * I] = er_s.px_cur[0], out->px_cur[2 * I + 1] = er_s.px_cur[1];
+  if (outl->px_cur_e) outl->px_cur_e[2 * I] = er_e.px_cur[0], outl->px_cur_e[2 * I + 1] = er_e.px_cur[1];
 }
 
 int plsvo_oracle_line_seed_update_batch(const plsvo_line_seed_batch* in, const plsvo_line_seed_result* out, int n_threads) {

@@ -43,6 +43,7 @@
 #include <vector>
 
 #include "../include/plsvo_b200.h"
+#include "next_scenes.h"
 
 // ---- out-of-line members the unbuilt reference sources would provide --------------------------
 namespace plsvo {
@@ -59,27 +60,8 @@ Frame::~Frame() {
   for (LineFeat* f : seg_fts_) delete f;
 }
 
-Point::Point(const Vector3d& pos) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {}
-Point::Point(const Vector3d& pos, PointFeat* ftr) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {
-  obs_.push_front(ftr);
-  ++n_obs_;
-}
-// src/feature3D_impl.cpp picks, among obs_, the observation with the closest viewing direction (list logic that
-// stays on the host side of the ABI); the harness hands over exactly one observation per point.
-bool Point::getCloseViewObs(const Vector3d&, Feature*& obs) const {
-  if (obs_.empty()) return false;
-  obs = obs_.front();
-  return true;
-}
-
-LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos)
-    : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {}
-LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos, LineFeat* ftr)
-    : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {
-  obs_.push_front(ftr);
-  ++n_obs_;
-}
-bool LineSeg::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
+// Point / LineSeg constructors and getCloseViewObs (closest viewing direction among obs_, > 60 degrees rejected) are the
+// reference's own: src/feature3D.cpp is compiled in (oracle/Makefile, REF_SRCS).
 
 }  // namespace plsvo
 
@@ -364,6 +346,9 @@ int plsvo_ref_match_direct_batch(const plsvo_match_batch* in, const plsvo_match_
     out->px_cur[2 * (size_t)i] = px[0], out->px_cur[2 * (size_t)i + 1] = px[1];
     out->success[i] = ok ? 1 : 0;
     if (out->search_level) out->search_level[i] = matcher.search_level_;
+    if (out->A_cur_ref && matcher.search_level_ >= 0)  // rows whose in-frame test failed stay as the caller passed them
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 2; ++k) out->A_cur_ref[4 * (size_t)i + 2 * r + k] = matcher.A_cur_ref_(r, k);
   }
   return PLSVO_OK;
 }
@@ -629,6 +614,63 @@ int plsvo_ref_line_seed_update_batch(const plsvo_line_seed_batch* inl, const pls
     }
   }
   return PLSVO_OK;
+}
+
+// ---- the loops either side of the hot path on multi-observation scenes (oracle/next_scenes.h) ----
+// Reprojector::refineBestCandidate -> refine (src/reprojector.cpp:236-387): one Matcher member answers every candidate of a
+// frame in turn; what Reprojector::refine reads afterwards (return value, px, search_level_, A_cur_ref_, ref_ftr_) is recorded.
+int plsvo_ref_match_scene(const plsvo_match_batch* in, int n_obs, const plsvo_scene_match_out* out) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  plsvo::Config::nPyrLevels() = (size_t)in->n_pyr_levels;
+  plsvo_scenes::MatchScene sc(in, n_obs);
+  plsvo::Matcher m{};
+  m.search_level_ = -1, m.ref_ftr_ = NULL;
+  m.A_cur_ref_.setZero();
+  m.options_.align_max_iter = in->n_iter;
+  for (int c = 0; c < in->n_cur_images; ++c) {
+    for (int i = 0; i < in->n_features; ++i) {
+      if (in->cur_index[i] != c) continue;
+      const size_t I = (size_t)i;
+      Vector2d px(in->px_cur[2 * I], in->px_cur[2 * I + 1]);
+      out->pt_found[i] = m.findMatchDirect(*sc.points[i], *sc.curs[c], px) ? 1 : 0;
+      out->pt_px[2 * I] = px[0], out->pt_px[2 * I + 1] = px[1];
+      out->pt_level[i] = m.search_level_;
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 2; ++k) out->pt_A[4 * I + 2 * r + k] = m.A_cur_ref_(r, k);
+      out->pt_ref[i] = m.ref_ftr_ ? plsvo_scenes::frame_slot(sc.refs, m.ref_ftr_->frame) : -1;
+    }
+    for (size_t j = 0; j < sc.segs.size(); ++j) {
+      if (!sc.segs[j] || in->cur_index[2 * j] != c) continue;
+      Vector2d spx(in->px_cur[4 * j], in->px_cur[4 * j + 1]), epx(in->px_cur[4 * j + 2], in->px_cur[4 * j + 3]);
+      out->seg_found[j] = m.findMatchDirect(*sc.segs[j], *sc.curs[c], spx, epx) ? 1 : 0;
+      out->seg_spx[2 * j] = spx[0], out->seg_spx[2 * j + 1] = spx[1], out->seg_epx[2 * j] = epx[0], out->seg_epx[2 * j + 1] = epx[1];
+      out->seg_level[j] = m.search_level_;
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 2; ++k) out->seg_A[4 * j + 2 * r + k] = m.A_cur_ref_(r, k);
+      out->seg_ref[j] = m.ref_ftr_ ? plsvo_scenes::frame_slot(sc.refs, m.ref_ftr_->frame) : -1;
+    }
+  }
+  return PLSVO_OK;
+}
+
+// DepthFilter::updateSeeds (src/depth_filter.cpp:262-471) — the reference class itself with its real convergence threshold,
+// seed ageing, callbacks and detector marks.
+namespace {
+struct DepthFilterSceneProbe : plsvo::DepthFilter {
+  using plsvo::DepthFilter::DepthFilter;
+  using plsvo::DepthFilter::pt_seeds_;
+  using plsvo::DepthFilter::seg_seeds_;
+  using plsvo::DepthFilter::matcher_;
+  using plsvo::DepthFilter::matcherls_;
+  int update(FramePtr f) {
+    updateSeeds(f);
+    return PLSVO_OK;
+  }
+};
+}  // namespace
+int plsvo_ref_seed_scene(const plsvo_seed_batch* in, const plsvo_line_seed_batch* lin, const int32_t* pt_age, const int32_t* seg_age,
+                         int is_keyframe, const plsvo_scene_seed_out* out) {
+  return plsvo_scenes::run_seed_scene<DepthFilterSceneProbe>(in, lin, pt_age, seg_age, is_keyframe, out);
 }
 
 const char* plsvo_ref_describe(void) {

@@ -22,6 +22,8 @@
 #include <vector>
 
 #include "../include/plsvo_b200.h"
+#include "next_scenes.h"
+#include "plsvo_shim_next.h"
 
 namespace plsvo {
 int Frame::frame_counter_ = 0;
@@ -31,12 +33,8 @@ Frame::~Frame() {
   for (PointFeat* f : pt_fts_) delete f;
   for (LineFeat* f : seg_fts_) delete f;
 }
-Point::Point(const Vector3d& pos) : Feature3D<PointFeat>(0), pos_(pos), normal_set_(false), v_g2o_(NULL) {}
-bool Point::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
-void Point::optimize(const size_t) {}
-LineSeg::LineSeg(const Vector3d& spos, const Vector3d& epos) : Feature3D<LineFeat>(0), spos_(spos), epos_(epos), v_g2o_(NULL) {}
-bool LineSeg::getCloseViewObs(const Vector3d&, Feature*&) const { return false; }
-void LineSeg::optimize(const size_t) {}
+// Point / LineSeg (constructors, getCloseViewObs, optimize) are the reference's own: src/feature3D.cpp and
+// src/feature3D_impl.cpp are compiled in (oracle/Makefile, SHIMREF_REF_SRCS).
 }  // namespace plsvo
 
 namespace {
@@ -259,5 +257,67 @@ int plsvo_shimref_poseopt_batch(const plsvo_poseopt_batch* B, const plsvo_poseop
     }
   }
   return PLSVO_OK;
+}
+// Reprojector-style pass (see plsvo_ref_match_scene in ref_harness.cpp) answered by plsvo::b200::DirectMatcher: every
+// candidate of a frame is enqueued, ONE device call, then the same per-candidate reads in the same order.
+int plsvo_shimref_match_scene(const plsvo_match_batch* in, int n_obs, const plsvo_scene_match_out* out) {
+  if (!in || !out) return PLSVO_ERR_INVALID;
+  plsvo::Config::nPyrLevels() = (size_t)in->n_pyr_levels;
+  plsvo_scenes::MatchScene sc(in, n_obs);
+  plsvo::b200::DirectMatcher m(in->n_iter);
+  m.search_level_ = -1, m.ref_ftr_ = NULL;
+  m.A_cur_ref_.setZero();
+  for (int c = 0; c < in->n_cur_images; ++c) {
+    m.reset(*sc.curs[c]);
+    std::vector<size_t> kp(in->n_features, 0), ks(sc.segs.size(), 0);
+    for (int i = 0; i < in->n_features; ++i)
+      if (in->cur_index[i] == c) kp[i] = m.enqueue(sc.points[i].get(), Vector2d(in->px_cur[2 * (size_t)i], in->px_cur[2 * (size_t)i + 1]));
+    for (size_t j = 0; j < sc.segs.size(); ++j)
+      if (sc.segs[j] && in->cur_index[2 * j] == c)
+        ks[j] = m.enqueue(sc.segs[j].get(), Vector2d(in->px_cur[4 * j], in->px_cur[4 * j + 1]), Vector2d(in->px_cur[4 * j + 2], in->px_cur[4 * j + 3]));
+    const int rc = m.run();
+    if (rc != PLSVO_OK) return rc;
+    for (int i = 0; i < in->n_features; ++i) {
+      if (in->cur_index[i] != c) continue;
+      const size_t I = (size_t)i;
+      Vector2d px(in->px_cur[2 * I], in->px_cur[2 * I + 1]);
+      out->pt_found[i] = m.findMatchDirect(kp[i], px) ? 1 : 0;
+      out->pt_px[2 * I] = px[0], out->pt_px[2 * I + 1] = px[1];
+      out->pt_level[i] = m.search_level_;
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 2; ++k) out->pt_A[4 * I + 2 * r + k] = m.A_cur_ref_(r, k);
+      out->pt_ref[i] = m.ref_ftr_ ? plsvo_scenes::frame_slot(sc.refs, m.ref_ftr_->frame) : -1;
+    }
+    for (size_t j = 0; j < sc.segs.size(); ++j) {
+      if (!sc.segs[j] || in->cur_index[2 * j] != c) continue;
+      Vector2d spx(in->px_cur[4 * j], in->px_cur[4 * j + 1]), epx(in->px_cur[4 * j + 2], in->px_cur[4 * j + 3]);
+      out->seg_found[j] = m.findMatchDirect(ks[j], spx, epx) ? 1 : 0;
+      out->seg_spx[2 * j] = spx[0], out->seg_spx[2 * j + 1] = spx[1], out->seg_epx[2 * j] = epx[0], out->seg_epx[2 * j + 1] = epx[1];
+      out->seg_level[j] = m.search_level_;
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 2; ++k) out->seg_A[4 * j + 2 * r + k] = m.A_cur_ref_(r, k);
+      out->seg_ref[j] = m.ref_ftr_ ? plsvo_scenes::frame_slot(sc.refs, m.ref_ftr_->frame) : -1;
+    }
+  }
+  return PLSVO_OK;
+}
+
+// DepthFilter::updateSeeds answered by plsvo::b200::DepthFilterB200 (see plsvo_ref_seed_scene in ref_harness.cpp)
+namespace {
+struct DepthFilterB200SceneProbe : plsvo::b200::DepthFilterB200 {
+  using plsvo::b200::DepthFilterB200::DepthFilterB200;
+  using plsvo::DepthFilter::pt_seeds_;
+  using plsvo::DepthFilter::seg_seeds_;
+  using plsvo::DepthFilter::matcher_;
+  using plsvo::DepthFilter::matcherls_;
+  int update(FramePtr f) {
+    updateSeeds(f);
+    return last_status();
+  }
+};
+}  // namespace
+int plsvo_shimref_seed_scene(const plsvo_seed_batch* in, const plsvo_line_seed_batch* lin, const int32_t* pt_age, const int32_t* seg_age,
+                             int is_keyframe, const plsvo_scene_seed_out* out) {
+  return plsvo_scenes::run_seed_scene<DepthFilterB200SceneProbe>(in, lin, pt_age, seg_age, is_keyframe, out);
 }
 }

@@ -212,14 +212,14 @@ class LineSeedBatch(C.Structure):
 
 
 class LineSeedResult(C.Structure):
-    _fields_ = [("seeds", SeedResult), ("mu_e", _f32p), ("sigma2_e", _f32p), ("depth_e", _f64p)]
+    _fields_ = [("seeds", SeedResult), ("mu_e", _f32p), ("sigma2_e", _f32p), ("depth_e", _f64p), ("px_cur_e", _f64p)]
 
 
 SEED_NOT_VISIBLE, SEED_NO_MATCH, SEED_UPDATED = 0, 1, 2
 
 
 class MatchResult(C.Structure):
-    _fields_ = [("px_cur", _f64p), ("success", _u8p), ("search_level", _i32p)]
+    _fields_ = [("px_cur", _f64p), ("success", _u8p), ("search_level", _i32p), ("A_cur_ref", _f64p)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -477,7 +477,9 @@ class MatchOut:
         self.px_cur = np.zeros((n, 2))
         self.success = np.zeros(n, np.uint8)
         self.search_level = np.zeros(n, np.int32)
-        self.struct = MatchResult(_ptr(self.px_cur, np.float64), _ptr(self.success, np.uint8), _ptr(self.search_level, np.int32))
+        self.A_cur_ref = np.full((n, 4), np.nan)  # Matcher::A_cur_ref_ row-major; NaN where the in-frame test fails
+        self.struct = MatchResult(_ptr(self.px_cur, np.float64), _ptr(self.success, np.uint8), _ptr(self.search_level, np.int32),
+                                  _ptr(self.A_cur_ref, np.float64))
 
 
 def make_structopt_batch(d):
@@ -559,5 +561,6 @@ class LineSeedOut(SeedOut):
         super().__init__(n)
         self.mu_e, self.sigma2_e = np.zeros(n, np.float32), np.zeros(n, np.float32)
         self.depth_e = np.zeros(n)
+        self.px_cur_e = np.zeros((n, 2))  # Matcher::px_cur_ of the end-point search
         self.line_struct = LineSeedResult(self.struct, _ptr(self.mu_e, np.float32), _ptr(self.sigma2_e, np.float32),
-                                          _ptr(self.depth_e, np.float64))
+                                          _ptr(self.depth_e, np.float64), _ptr(self.px_cur_e, np.float64))

@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(kA2Threads) match_direct_kernel(const MatchArg
   const double det = DS(DM(A00, A11), DM(A10, A01));
   const int search_level = best_search_level(det, a.n_pyr_levels - 1);
   a.out_level[i] = search_level;
+  if (a.out_A) a.out_A[4 * I] = A00, a.out_A[4 * I + 1] = A01, a.out_A[4 * I + 2] = A10, a.out_A[4 * I + 3] = A11;
   uint8_t* border = s_border[tid];
   warp_affine_patch(A00, A01, A10, A11, det, a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref], (int)a.ref_pitch[level_ref],
                     a.width >> level_ref, a.height >> level_ref, px_ref0, px_ref1, level_ref, search_level, border);
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(kA2Threads) line_seed_update_kernel(const Seed
   const float zr_s = a.z_range[i], zr_e = a.z_range_e[i];
   int status = 0;
   const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
-  double z_s = kNaN, z_e = kNaN, pxc0 = kNaN, pxc1 = kNaN;
+  double z_s = kNaN, z_e = kNaN, pxc0 = kNaN, pxc1 = kNaN, pxe0 = kNaN, pxe1 = kNaN;
   const int r = a.ref_index[i], c = a.cur_index[i];
   const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
   const V3 f{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kA2Threads) line_seed_update_kernel(const Seed
       if (e == 0)
         z_s = zz, pxc0 = q0, pxc1 = q1;
       else
-        z_e = zz;
+        z_e = zz, pxe0 = q0, pxe1 = q1;
     }
     status = ok ? 2 : 1;
   }
@@ -781,6 +782,7 @@ __global__ void __launch_bounds__(kA2Threads) line_seed_update_kernel(const Seed
                            : 0;
   a.out_depth[i] = z_s, a.out_depth_e[i] = z_e;
   a.out_px_cur[2 * I] = pxc0, a.out_px_cur[2 * I + 1] = pxc1;
+  a.out_px_cur_e[2 * I] = pxe0, a.out_px_cur_e[2 * I + 1] = pxe1;
 }
 
 }  // namespace

@@ -163,6 +163,7 @@ struct MatchArgs {
   double* out_px;
   uint8_t* out_success;
   int32_t* out_level;
+  double* out_A;  // [n][4] or null
 };
 cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s);
 
@@ -201,6 +202,7 @@ struct SeedArgs {
   float* out_mu_e;
   float* out_sigma2_e;
   double* out_depth_e;
+  double* out_px_cur_e;  // [n][2]
   float* out_a;
   float* out_b;
   float* out_mu;

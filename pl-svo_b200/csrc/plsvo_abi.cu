@@ -75,7 +75,7 @@ struct plsvo_ctx_impl {
   DevBuf y_img;  // pyramid levels
   DevBuf f_img, f_idx, f_lvl, f_border, f_ref, f_px, f_opx, f_oconv, f_dir, f_ohinv;  // align2D / align1D
   DevBuf m_ref_img, m_cur_img, m_T_ref, m_T_cur, m_ridx, m_cidx, m_px, m_f, m_lvl, m_edge, m_grad, m_pos, m_pxc, m_opx, m_osucc,
-      m_olvl;  // findMatchDirect
+      m_olvl, m_oA;  // findMatchDirect
   DevBuf d_sa, d_sb, d_smu, d_szr, d_ssig, d_smu_e, d_szr_e, d_ssig_e, d_sout;  // depth-filter seeds
   DevBuf s_T, s_pb, s_pf, s_pof, s_pp, s_sb, s_sf, s_ssf, s_sef, s_sp, s_ep, s_out;  // structure optimisation
   DevBuf p_out_T, p_out_cov, p_out_scale, p_out_ei, p_out_ef, p_out_npt, p_out_nls, p_out_pto, p_out_sgo, p_out_iters,
@@ -204,7 +204,7 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
                     &c->d_out_pi,    &c->d_out_pl,   &c->d_counter,   &c->d_ws_cache,   &c->d_ws_xyz,    &c->d_ref_der,   &c->d_cur_der,   &c->d_pt_depth,  &c->d_seg_sdepth, &c->d_seg_edepth, &c->d_feat, &c->d_ws_segpx,  &c->d_ws_rec,    &c->d_stage,     &c->y_img,       &c->f_img,       &c->f_idx,       &c->f_lvl,      &c->f_border,
                     &c->f_ref,       &c->f_px,        &c->f_opx,       &c->f_oconv,     &c->f_dir,       &c->f_ohinv,     &c->m_ref_img,   &c->m_cur_img,   &c->m_T_ref,     &c->m_T_cur,
                     &c->m_ridx,      &c->m_cidx,     &c->m_px,        &c->m_f,          &c->m_lvl,       &c->m_edge,
-                    &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
+                    &c->m_grad,      &c->m_pos,      &c->m_pxc,       &c->m_opx,        &c->m_osucc,     &c->m_olvl,      &c->m_oA,        &c->s_T,         &c->s_pb,        &c->s_pf,        &c->s_pof,
                     &c->s_pp,        &c->s_sb,       &c->s_sf,        &c->s_ssf,        &c->s_sef,       &c->s_sp,
                     &c->s_ep,        &c->s_out,      &c->d_sa,        &c->d_sb,         &c->d_smu,       &c->d_szr,
                     &c->d_ssig,      &c->d_smu_e,    &c->d_szr_e,     &c->d_ssig_e,     &c->d_sout,      &c->p_T,
@@ -1415,6 +1415,12 @@ extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_ba
   a.out_px = static_cast<double*>(c->m_opx.p);
   a.out_success = static_cast<uint8_t*>(c->m_osucc.p);
   a.out_level = static_cast<int32_t*>(c->m_olvl.p);
+  if (out->A_cur_ref) {
+    CK(ensure(c->m_oA, n * 4 * sizeof(double)));
+    a.out_A = static_cast<double*>(c->m_oA.p);
+    // rows the kernel leaves untouched (in-frame test failed) must come back as the caller passed them
+    CK(cudaMemcpyAsync(a.out_A, out->A_cur_ref, n * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
   CK(kernel_timer(c, 0, s));
   CK(match_direct_kernel_launch(a, s));
   CK(kernel_timer(c, 1, s));
@@ -1422,6 +1428,7 @@ extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_ba
   CK(cudaMemcpyAsync(out->px_cur, a.out_px, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(out->success, a.out_success, n, cudaMemcpyDeviceToHost, s));
   if (out->search_level) CK(cudaMemcpyAsync(out->search_level, a.out_level, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (out->A_cur_ref) CK(cudaMemcpyAsync(out->A_cur_ref, a.out_A, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;
 }
@@ -1547,9 +1554,10 @@ int seed_update_run(plsvo_ctx_impl* c, const plsvo_seed_batch* in, const plsvo_s
   CK(up(c->d_smu, in->mu, n, s, &a.mu));
   CK(up(c->d_szr, in->z_range, n, s, &a.z_range));
   CK(up(c->d_ssig, in->sigma2, n, s, &a.sigma2));
-  // outputs: [px_cur 2n f64][depth n f64][depth_e n f64][a b mu sigma2 mu_e sigma2_e n f32 each][status n i32][converged n u8]
-  CK(ensure(c->d_sout, n * (16 + 8 + 8 + 24 + 4 + 1) + 64));
-  a.out_px_cur = static_cast<double*>(c->d_sout.p);
+  // outputs: [px_cur_e 2n f64][px_cur 2n f64][depth n f64][depth_e n f64][a b mu sigma2 mu_e sigma2_e n f32 each][status n i32][converged n u8]
+  CK(ensure(c->d_sout, n * (16 + 16 + 8 + 8 + 24 + 4 + 1) + 64));
+  a.out_px_cur_e = static_cast<double*>(c->d_sout.p);
+  a.out_px_cur = a.out_px_cur_e + 2 * n;
   a.out_depth = a.out_px_cur + 2 * n;
   a.out_depth_e = a.out_depth + n;
   a.out_a = reinterpret_cast<float*>(a.out_depth_e + n);
@@ -1573,6 +1581,7 @@ int seed_update_run(plsvo_ctx_impl* c, const plsvo_seed_batch* in, const plsvo_s
     CK(cudaMemcpyAsync(lout->mu_e, a.out_mu_e, n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(lout->sigma2_e, a.out_sigma2_e, n * 4, cudaMemcpyDeviceToHost, s));
     if (lout->depth_e) CK(cudaMemcpyAsync(lout->depth_e, a.out_depth_e, n * 8, cudaMemcpyDeviceToHost, s));
+    if (lout->px_cur_e) CK(cudaMemcpyAsync(lout->px_cur_e, a.out_px_cur_e, n * 16, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
   return PLSVO_OK;

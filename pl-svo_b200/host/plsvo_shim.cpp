@@ -69,6 +69,17 @@ int shim_set_device(int device) {
 }
 const char* shim_last_error() { return g_err.c_str(); }
 
+ShimSession::ShimSession() {
+  g_mu.lock();
+  ctx_ = plsvo::ctx();
+}
+ShimSession::~ShimSession() { g_mu.unlock(); }
+int ShimSession::fail(int rc, const char* what) {
+  g_err = ctx_ ? plsvo_last_error(ctx_) : "no device context";
+  std::fprintf(stderr, "[plsvo_b200] %s failed: %s\n", what, g_err.c_str());
+  return rc;
+}
+
 SparseImgAlign::SparseImgAlign(int max_level, int min_level, int n_iter, Method method, bool display, bool verbose)
     : max_level_(max_level), min_level_(min_level), n_iter_(n_iter) {
   (void)method, (void)display, (void)verbose;

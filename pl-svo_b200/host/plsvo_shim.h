@@ -19,6 +19,8 @@
 #endif
 #include <cstddef>
 
+struct plsvo_ctx;  // include/plsvo_b200.h
+
 namespace plsvo {
 
 /// Optimize the pose of the frame by minimizing the photometric error of feature patches.
@@ -69,5 +71,21 @@ int optimizeStructure(FramePtr frame, size_t max_n_pts, int max_iter, size_t max
 /// frame_handler_mono.cpp:272, so the device state cannot live in the object)
 int shim_set_device(int device);
 const char* shim_last_error();
+
+/// The shim's process-wide device context under the shim's lock, for the shim's own translation units
+/// (plsvo_shim.cpp, plsvo_shim_next.cpp): holds the lock for its lifetime; ctx() is NULL without a device.
+class ShimSession {
+ public:
+  ShimSession();
+  ~ShimSession();
+  ShimSession(const ShimSession&) = delete;
+  ShimSession& operator=(const ShimSession&) = delete;
+  ::plsvo_ctx* ctx() const { return ctx_; }
+  /// records plsvo_last_error(ctx) for shim_last_error() and prints it with `what`; returns rc
+  int fail(int rc, const char* what);
+
+ private:
+  ::plsvo_ctx* ctx_;
+};
 
 }  // namespace plsvo

@@ -146,6 +146,12 @@ def test_gpu_line_seed_update_matches_the_oracle(pkg, oracle, abi, synth, gen_de
     np.testing.assert_array_equal(out.depth[up], ref.depth[up])      # z_s: exact
     np.testing.assert_array_equal(out.depth_e[up], ref.depth_e[up])  # z_e: exact
     assert np.isnan(out.depth[~up]).all() and np.isnan(out.depth_e[~up]).all()
+    for f in ("px_cur", "px_cur_e"):  # Matcher::px_cur_ after the start / end search: exact, NaN in the same places
+        o, r = getattr(out, f), getattr(ref, f)
+        fin = np.isfinite(r).all(axis=1)
+        np.testing.assert_array_equal(np.isfinite(o).all(axis=1), fin, err_msg=f)
+        np.testing.assert_array_equal(o[fin], r[fin], err_msg=f)
+    assert np.isfinite(ref.px_cur_e[up]).all()
     for f in LINE_FIELDS:
         np.testing.assert_array_equal(getattr(out, f)[~up], getattr(ref, f)[~up], err_msg=f)
     ok = up & np.isfinite(ref.a) & np.isfinite(ref.sigma2) & np.isfinite(ref.sigma2_e)

@@ -15,6 +15,8 @@ def test_oracle_find_match_direct_is_bit_identical_to_the_reference_tu(oracle, a
     np.testing.assert_array_equal(o.success, r.success)
     np.testing.assert_array_equal(o.search_level, r.search_level)
     np.testing.assert_array_equal(o.px_cur, r.px_cur)
+    np.testing.assert_array_equal(o.A_cur_ref, r.A_cur_ref)  # Matcher::A_cur_ref_ (NaN = untouched on both sides)
+    assert np.isfinite(o.A_cur_ref[o.search_level >= 0]).all()
     # the generator plants candidates on the image border: the in-frame test must reject them untouched
     assert (o.search_level < 0).any()
     skipped = o.search_level < 0
@@ -40,6 +42,7 @@ def test_gpu_find_match_direct_is_bit_identical_to_the_oracle(pkg, oracle, abi, 
     out = pkg.Matcher(10).findMatchDirect(d)
     np.testing.assert_array_equal(out.search_level, ref.search_level)
     np.testing.assert_array_equal(out.success, ref.success)
+    np.testing.assert_array_equal(out.A_cur_ref, ref.A_cur_ref)
     finite = np.isfinite(ref.px_cur).all(axis=1)
     np.testing.assert_array_equal(out.px_cur[finite], ref.px_cur[finite])
     assert (np.isnan(out.px_cur[~finite]) == np.isnan(ref.px_cur[~finite])).all()
