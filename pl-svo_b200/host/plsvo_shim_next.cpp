@@ -143,7 +143,9 @@ int32_t DirectMatcher::add_row(Feature* ref, const Vector2d& px, const Vector3d&
 size_t DirectMatcher::enqueue(Point* pt, const Vector2d& px_est) {
   Cand c;
   c.ref_ftr = NULL, c.is_segment = false, c.row = -1;
-  c.close_view = cur_ && pt->getCloseViewObs(cur_->pos(), c.ref_ftr);
+  // a point without observations (deleted from the map) has nothing to match against; Reprojector::refine returns before the
+  // matcher for TYPE_DELETED points (:280-281), and getCloseViewObs must not be run on an empty list
+  c.close_view = cur_ && !pt->obs_.empty() && pt->getCloseViewObs(cur_->pos(), c.ref_ftr);
   if (c.close_view) {
     PointFeat* pf = static_cast<PointFeat*>(c.ref_ftr);
     const bool edgelet = pf->type == PointFeat::EDGELET;
@@ -157,7 +159,7 @@ size_t DirectMatcher::enqueue(Point* pt, const Vector2d& px_est) {
 size_t DirectMatcher::enqueue(LineSeg* ls, const Vector2d& spx_est, const Vector2d& epx_est) {
   Cand c;
   c.ref_ftr = NULL, c.is_segment = true, c.row = -1;
-  c.close_view = cur_ && ls->getCloseViewObs(cur_->pos(), c.ref_ftr);
+  c.close_view = cur_ && !ls->obs_.empty() && ls->getCloseViewObs(cur_->pos(), c.ref_ftr);
   if (c.close_view) {
     LineFeat* lf = static_cast<LineFeat*>(c.ref_ftr);
     c.row = add_row(c.ref_ftr, lf->spx, lf->sf, ls->spos_, spx_est, false, Vector2d(0, 0));  // :251-260

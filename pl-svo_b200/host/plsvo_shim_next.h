@@ -93,7 +93,7 @@ class DirectMatcher {
 };
 
 /// DepthFilter whose seed updates run on the device: same constructor, same callbacks, same seed lists.
-/// `depth_filter_ = new DepthFilter(pt_detector, seg_detector, cb, cb_ls)` (src/frame_handler_mono.cpp:79-86) becomes
+/// `depth_filter_ = new DepthFilter(pt_detector, seg_detector, cb, cb_ls)` (src/frame_handler_mono.cpp:97) becomes
 /// `depth_filter_ = new b200::DepthFilterB200(pt_detector, seg_detector, cb, cb_ls)`; nothing else changes
 /// (updateSeeds is virtual, include/plsvo/depth_filter.h:214).
 ///
