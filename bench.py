@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs per CPU-baseline pass (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only, compact output (tuning)")
+    ap.add_argument("--no-next", action="store_true", help="skip the SURVEY 8f (next-row) kernel block of the line")
     ap.add_argument("--config", default="c2", choices=["c2", "c4"],
                     help="c2: BASELINE configs[1] + the metric's 80 lines (headline); c4: configs[3], chained align -> pose-opt at 720p")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: patch count x pyramid depth sweep (JSON list)")
@@ -578,6 +579,14 @@ def main():
     B = args.batch
     data = synth.make_align_batch(batch=B, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=3000 + 100000 * rank)
 
+    # every rank runs on the CPUs of its own GPU's NUMA node while it allocates and fills its page-locked buffers and drives
+    # the GPU legs (plsvo_b200.numa); the affinity is handed back before any CPU arm is timed
+    from plsvo_b200 import numa
+
+    placement = numa.describe(local_rank)
+    saved_affinity = numa.bind_to_device(local_rank)
+    placement["bound"] = saved_affinity is not None
+
     # pinned host copies of every input array (the e2e leg copies from these every step)
     def pin(a):
         t = torch.from_numpy(a).pin_memory()
@@ -683,6 +692,7 @@ def main():
     e2e_value = n_gpus * B * args.steps / (float(e2e_ms.item()) * 1e-3)
     clk.__exit__(None, None, None)
     data = data_full
+    numa.restore(saved_affinity)  # the CPU arms below get every host thread back
 
     # ---- multi-GPU product path: ONE host batch on rank 0 -> NCCL scatter -> align on every GPU -> all_gather ----
     e2e_scatter = None
@@ -785,6 +795,28 @@ def main():
     except Exception as ex:  # secondary number: never take the headline line down
         poseopt = {"error": str(ex)}
 
+    # ---- SURVEY 8f next-row kernels (N = 1 only): kernel rate, host-in/host-out rate from pinned memory, CPU oracle beside
+    # them on all host threads, exactness against it on the timed inputs (tools/bench_next.py holds the full accounting) ----
+    next_rows = None
+    if rank == 0 and n_gpus == 1 and not args.no_next and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_next
+
+            nr = bench_next.measure(reps=5, images=64, features=100000, struct_points=50000, ctx=ctx, dev=dev)
+            next_rows = {"host_memory": nr.get("host_memory"), "detail": "python tools/bench_next.py (full sizes) -> profiles/r02_next_kernels.json"}
+            for name, row in nr.items():
+                if not isinstance(row, dict):
+                    continue
+                k = next((x for x in row if x.endswith("_per_s_kernel")), None)
+                unit = k[: -len("_per_s_kernel")] + "/s"
+                exact = next((row[x] for x in row if "exact" in x), None)
+                next_rows[name] = {"unit": unit, "kernel": row[k], "e2e": row[k.replace("_kernel", "_e2e")],
+                                   "cpu": next(row[x] for x in row if x.startswith("cpu_oracle_")), "cpu_threads": row["cpu_threads"],
+                                   "exact_vs_oracle": exact, "workload": row["workload"]}
+        except Exception as ex:  # secondary block: never take the headline line down
+            next_rows = {"error": repr(ex)}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -816,6 +848,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
                     "d2h_bytes_per_step": int(d2h) * n_gpus, "check": e2e_check},
             "e2e_scatter": e2e_scatter,
+            "host_placement": placement,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -824,6 +857,7 @@ def main():
                          "mean_gn_passes_per_pair": float(out.iters.sum(axis=1).mean())},
             "cpu_baseline": cpu,
             "poseopt": poseopt,
+            "next_rows": next_rows,
         }
         print(json.dumps(line))
     if dist:

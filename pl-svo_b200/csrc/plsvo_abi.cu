@@ -1,6 +1,7 @@
 // plsvo_abi.cu — the C ABI of include/plsvo_b200.h: context, host<->device staging, launches.
 // Host-side only; the kernels are in align_kernel.cu and poseopt_kernel.cu.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -322,9 +323,12 @@ static inline cudaStream_t pick_copy_stream(plsvo_ctx_impl* c, cudaStream_t s) {
   return c->rr_stream[c->rr_i++ % c->rr_n];
 }
 
-int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, size_t b1, cudaStream_t s, int mode) {
+int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, size_t b1, cudaStream_t s, int mode,
+                      int what = 3, int size_level = -1) {
   // mode 0: copy [b0,b1) only; 1: validate + lay out + copy + host-side sizing; 2: validate + lay out + copy;
-  // 3: host-side sizing only
+  // 3: host-side sizing only.  what: bit 0 = the image levels, bit 1 = the feature arrays (the streamed host path sends
+  // every feature array of the batch first and then the images chunk by chunk).  size_level >= 0: the sizing is wanted for
+  // that pyramid level only and may be a cheap upper bound (it sits on the launch path of the streamed host call).
   AlignArgs& a = c->aa;
   const size_t B = (size_t)h->batch;
   const bool prepare = (mode == 1 || mode == 2);
@@ -413,7 +417,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     size_t feat_total = 0;
     for (const Item& it : items)
       if (it.host && it.bytes) feat_total += (it.bytes + 255) / 256 * 256;
-    bool small = prepare && b0 == 0 && b1 == B && c->rr_n == 0 && s == c->stream && !getenv("PLSVO_NO_SMALL_UPLOAD") &&
+    bool small = prepare && what == 3 && b0 == 0 && b1 == B && c->rr_n == 0 && s == c->stream && !getenv("PLSVO_NO_SMALL_UPLOAD") &&
                  2 * c->img_total + feat_total <= (size_t)4 << 20;
     for (int l = 0; l < PLSVO_MAX_LEVELS && small; ++l) {
       if (!c->lvl_uploaded[l]) continue;
@@ -473,6 +477,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     const uint8_t* hc = h->cur_img[l] + b0 * h->img_stride[l];
     dr += b0 * a.stride[l];
     dc += b0 * a.stride[l];
+    if (!(what & 1) || nb == 0) continue;
     const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
     if (uniform && h->img_pitch[l] == a.pitch[l]) {
       // host stack already has the device layout: one linear copy per frame set
@@ -497,6 +502,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     }
   }
   const size_t np = (size_t)h->n_pts, ns = (size_t)h->n_segs;
+  if (what & 2) {
   CK(up_range(c->d_T_ref, h->T_ref_w, 7, B, b0, b1, pick_copy_stream(c, s), &a.T_ref_w, prepare));
   CK(up_range(c->d_T_cur, h->T_cur_w, 7, B, b0, b1, pick_copy_stream(c, s), &a.T_cur_w, prepare));
   CK(up_range(c->d_pt_count, h->pt_count, 1, B, b0, b1, pick_copy_stream(c, s), &a.pt_count, prepare));
@@ -516,6 +522,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
   CK(up_range(c->d_seg_edepth, h->seg_edepth, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_edepth, prepare));
   CK(up_range(c->d_seg_length, h->seg_length, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_length, prepare));
   CK(up_range(c->d_seg_valid, h->seg_valid, ns, B, b0, b1, pick_copy_stream(c, s), &a.seg_valid, prepare));
+  }
   }
 copies_done:;
   }  // mode != 3
@@ -539,11 +546,37 @@ copies_done:;
     struct Bounds {
       int patches[PLSVO_MAX_LEVELS], slots[PLSVO_MAX_LEVELS], maxN[PLSVO_MAX_LEVELS];
     };
-    const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, B * (size_t)h->n_segs / 8192));
+    const bool fast = size_level >= 0 && size_level < PLSVO_MAX_LEVELS;
+    const int nt = fast ? (int)std::max<size_t>(1, std::min<size_t>(4, B * (size_t)h->n_segs / 262144))
+                        : (int)std::max<size_t>(1, std::min<size_t>(8, B * (size_t)h->n_segs / 8192));
     std::vector<Bounds> part(nt);
     auto work = [&](int t) {
       Bounds bd;
       memset(&bd, 0, sizeof bd);
+      if (fast) {
+        // Upper bound without the square roots and divisions of setupSampling: correction = 2 sqrt(1 + sin^2) >= 2, so the
+        // sample count length / (2 * 4 * correction) is at most length / 16 (NaN or tiny lengths give 1, as on the device).
+        const int l = size_level;
+        int best_sum = 0, best_slots = 0, best_N = 0;
+        for (size_t b = B * t / nt; b < B * (t + 1) / nt; ++b) {
+          const int nsb = h->seg_count ? h->seg_count[b] : h->n_segs;
+          const double* len = h->seg_length + b * (size_t)h->n_segs;
+          int sum = 0, slots = 0;
+          for (int j = 0; j < nsb; ++j) {
+            double nd = len[j] * 0.0625;
+            nd = nd >= 1.0 ? nd : 1.0;  // also catches NaN
+            nd = nd > 1e6 ? 1e6 : nd;
+            const int N = 1 + (((int)nd - 1) >> l);
+            const int g = 2 * N - 1;  // the group of a segment has 2^k >= min(N, 32) lanes: at most min(2N - 1, 32)
+            sum += N, slots += g < 32 ? g : 32;
+            best_N = N > best_N ? N : best_N;
+          }
+          best_sum = std::max(best_sum, sum), best_slots = std::max(best_slots, slots);
+        }
+        bd.patches[l] = best_sum, bd.slots[l] = best_slots, bd.maxN[l] = best_N;
+        part[t] = bd;
+        return;
+      }
       for (size_t b = B * t / nt; b < B * (t + 1) / nt; ++b) {
         const int nsb = h->seg_count ? h->seg_count[b] : h->n_segs;
         int sum[PLSVO_MAX_LEVELS] = {0}, slots[PLSVO_MAX_LEVELS] = {0};
@@ -698,7 +731,7 @@ struct AlignPlan {
 // kernel variants (threads per CTA, resident CTAs per SM the register budget is compiled for), see align_kernel.cu
 static const int kAlignVariants[][2] = {{128, 4}, {128, 5}, {96, 5}, {96, 7}, {64, 8}, {160, 3}, {192, 2}, {256, 2}};
 
-int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, AlignPlan* plan) {
+int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, AlignPlan* plan, bool streamed = false) {
   if (!c->align_ready) return fail(c, PLSVO_ERR_STATE, "plsvo_align_launch before plsvo_align_upload");
   if (p->min_level < 0 || p->max_level < p->min_level || p->max_level >= PLSVO_MAX_LEVELS || p->n_iter < 1)
     return fail(c, PLSVO_ERR_INVALID, "level range / n_iter");
@@ -720,6 +753,9 @@ int align_plan(plsvo_ctx_impl* c, const plsvo_align_params* p, int chunk_pairs, 
   // PLSVO_VARIANT="threads,ctas" selects another compiled variant (tuning / the A-B runs in profiles/).
   int want_t = 128, want_b = 4;
   if (chunk_pairs <= c->num_sms) want_t = 256, want_b = 2;
+  // streamed host path: pairs trickle in at the rate of the host link, so fewer are in flight than the grid has room for
+  // and the call ends one pair-latency after the last chunk lands — bigger CTAs shorten that tail (tools/e2e_trace.py)
+  else if (streamed) want_t = 192, want_b = 2;
   if (const char* v = getenv("PLSVO_VARIANT")) {
     int t = 0, mb = 0;
     if (sscanf(v, "%d,%d", &t, &mb) == 2) {
@@ -938,6 +974,15 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
     CK(ensure(c->d_counter, 256));
     unsigned int* d_arrived = static_cast<unsigned int*>(c->d_counter.p) + 32;
     CK(cudaMemsetAsync(d_arrived, 0, sizeof(unsigned int), c->stream));
+    // PLSVO_TRACE_E2E=1: timeline of this call on stderr (chunk arrival times, kernel end, download end) — measurement aid
+    const bool trace = getenv("PLSVO_TRACE_E2E") != nullptr;
+    cudaEvent_t tr_start = nullptr, tr_chunk[64] = {nullptr}, tr_kernel = nullptr;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    if (trace) {
+      cudaEventCreate(&tr_start), cudaEventCreate(&tr_kernel);
+      for (int k = 0; k < n_chunks && k < 64; ++k) cudaEventCreate(&tr_chunk[k]);
+      cudaEventRecord(tr_start, c->stream);
+    }
     CK(cudaEventRecord(c->start_ev, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->start_ev, 0));
     // extra copy streams (PLSVO_COPY_STREAMS, default 1 = the copy stream alone): a chunk's ~24 array copies go
@@ -957,12 +1002,26 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
     // enqueue every chunk copy first (asynchronous from pinned memory): the host-side sizing below and
     // the kernel launch then overlap with the DMA
     int rc = PLSVO_OK;
+    // every feature array of the whole batch first (a dozen large copies, ~a quarter of the bytes), then the images chunk
+    // by chunk (two copies per chunk and level): few, large transfers keep the link near its peak rate and the arrival
+    // flags then track the image stream alone.  PLSVO_GATE_INTERLEAVED=1 restores the per-chunk slices of every array.
+    const bool features_first = !getenv("PLSVO_GATE_INTERLEAVED");
+    if (features_first) {
+      rc = align_upload_impl(c, b, 0, B, c->copy_stream, 2, /*what=*/2);
+      if (rc != PLSVO_OK) {
+        cudaStreamSynchronize(c->copy_stream);
+        return rc;
+      }
+    }
     for (int k = 0; k < n_chunks; ++k) {
       c->rr_n = n_rr > 1 ? n_rr : 0, c->rr_i = 0;
       rc = align_upload_impl(c, b, (size_t)k * chunk, std::min<size_t>((size_t)(k + 1) * chunk, B), c->copy_stream,
-                             k == 0 ? 2 : 0);
+                             (k == 0 && !features_first) ? 2 : 0, features_first ? 1 : 3);
       c->rr_n = 0;
-      if (rc != PLSVO_OK) return rc;
+      if (rc != PLSVO_OK) {
+        cudaStreamSynchronize(c->copy_stream);
+        return rc;
+      }
       for (int j = 0; j < (n_rr > 1 ? n_rr : 0); ++j) {
         CK(cudaEventRecord(c->rr_ev[j], c->rr_stream[j]));
         CK(cudaStreamWaitEvent(c->copy_stream, c->rr_ev[j], 0));
@@ -976,10 +1035,13 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
         return rc;
       }
       CK(cudaMemcpyAsync(d_arrived, &c->h_flags[k], sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream));
+      if (trace && k < 64) cudaEventRecord(tr_chunk[k], c->copy_stream);
     }
-    rc = align_upload_impl(c, b, 0, 0, c->copy_stream, 3);  // host-side sizing (segment-sample bound, outputs)
+    const auto t_host1 = std::chrono::steady_clock::now();
+    // host-side sizing (segment-sample bound of the finest level, outputs): on the launch path, so the cheap bound
+    rc = align_upload_impl(c, b, 0, 0, c->copy_stream, 3, 3, getenv("PLSVO_EXACT_SIZING") ? -1 : p->min_level);
     AlignPlan plan;
-    if (rc == PLSVO_OK) rc = align_plan(c, p, (int)B, &plan);
+    if (rc == PLSVO_OK) rc = align_plan(c, p, (int)B, &plan, /*streamed=*/true);
     if (rc != PLSVO_OK) {
       // copies are in flight: the caller's host arrays must not be read after we return
       cudaStreamSynchronize(c->copy_stream);
@@ -987,9 +1049,29 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
         if (c->rr_stream[j]) cudaStreamSynchronize(c->rr_stream[j]);
       return rc;
     }
+    const auto t_host2 = std::chrono::steady_clock::now();
     rc = align_launch_range(c, plan, 0, B, 0, c->stream, chunk);  // gated on arrivals
     if (rc != PLSVO_OK) return rc;
-    return plsvo_align_download(ctx, o);
+    if (trace) cudaEventRecord(tr_kernel, c->stream);
+    const auto t_host3 = std::chrono::steady_clock::now();
+    rc = plsvo_align_download(ctx, o);
+    if (trace) {
+      const auto t_host4 = std::chrono::steady_clock::now();
+      auto ms = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - t_host0).count(); };
+      std::fprintf(stderr, "[plsvo e2e trace] host: copies enqueued %.3f, sized+planned %.3f, launched %.3f, returned %.3f ms | device:", ms(t_host1),
+                   ms(t_host2), ms(t_host3), ms(t_host4));
+      for (int k = 0; k < n_chunks && k < 64; ++k) {
+        float t = 0;
+        cudaEventElapsedTime(&t, tr_start, tr_chunk[k]);
+        std::fprintf(stderr, " chunk%d %.3f", k, t);
+        cudaEventDestroy(tr_chunk[k]);
+      }
+      float t = 0;
+      cudaEventElapsedTime(&t, tr_start, tr_kernel);
+      std::fprintf(stderr, " kernel_end %.3f ms\n", t);
+      cudaEventDestroy(tr_start), cudaEventDestroy(tr_kernel);
+    }
+    return rc;
   }
   if (chunks == 0) chunks = 1;
   if (chunks > b->batch) chunks = 1;

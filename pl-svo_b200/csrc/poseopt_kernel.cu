@@ -18,7 +18,10 @@ namespace plsvo {
 
 namespace {
 
-constexpr int kPoThreads = 128;
+#ifndef PLSVO_PO_THREADS
+#define PLSVO_PO_THREADS 128
+#endif
+constexpr int kPoThreads = PLSVO_PO_THREADS;
 constexpr int kPoWarps = kPoThreads / 32;
 
 struct PoCtl {

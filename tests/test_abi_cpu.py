@@ -86,3 +86,21 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in text and "libplsvo_oracle" not in text and "plsvo_oracle_" not in text, f
+
+
+def test_numa_helper_degrades_to_a_no_op_without_a_gpu():
+    """plsvo_b200.numa: CPU-list parsing, and no affinity change when the GPU's topology cannot be read (this container)."""
+    import os
+
+    from plsvo_b200 import numa
+
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    saved = numa.bind_to_device(0)
+    if saved is None:  # nothing readable: untouched
+        assert os.sched_getaffinity(0) == before
+    numa.restore(saved)
+    assert os.sched_getaffinity(0) == before
+    d = numa.describe(0)
+    assert set(d) == {"pci_bus_id", "numa_node", "local_cpus", "process_cpus"}

@@ -90,15 +90,35 @@ def feature_case(n, seed, dev):
     return cam, pyr, idx, lvl, border, ref, px0, dirs
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--images", type=int, default=256)
-    ap.add_argument("--features", type=int, default=400000)
-    args = ap.parse_args()
+_PINNED = []
+
+
+def pin(a):
+    """Page-locked copy of a numpy array (kept alive for the life of the process): the host-in/host-out calls below are
+    timed from pinned memory, as an integrating caller that cares about the copy would hold its frames."""
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    _PINNED.append(t)
+    return t.numpy()
+
+
+def pin_obj(d):
+    """Every numpy array attribute (and dict-of-arrays attribute) of a synth data object, replaced by a pinned copy."""
+    for k, v in list(vars(d).items()):
+        if isinstance(v, np.ndarray) and v.size:
+            setattr(d, k, pin(v))
+        elif isinstance(v, dict) and v and all(isinstance(x, np.ndarray) for x in v.values()):
+            setattr(d, k, {kk: pin(x) for kk, x in v.items()})
+    return d
+
+
+def measure(reps=10, images=256, features=400000, struct_points=200000, ctx=None, dev=None):
+    """All §8f kernels once; returns the result dict (see the module docstring)."""
+    import types
+
+    args = types.SimpleNamespace(reps=reps, images=images, features=features)
     assert torch.cuda.is_available(), "needs a CUDA device"
-    dev = torch.device("cuda", 0)
-    ctx = api.default_context()
+    dev = dev or torch.device("cuda", 0)
+    ctx = ctx or api.default_context()
     olib = oracle_lib.load(abi)
     olib.plsvo_oracle_pyramid_batch.restype = C.c_int
     olib.plsvo_oracle_align2d_batch.restype = C.c_int
@@ -110,7 +130,7 @@ def main():
     cam = synth.VGA
     B, L = args.images, 5
     rng = np.random.default_rng(1)
-    img0 = rng.integers(0, 256, (B, cam.height, cam.width), dtype=np.uint8)
+    img0 = pin(rng.integers(0, 256, (B, cam.height, cam.width), dtype=np.uint8))
     levels = {}
 
     def run_pyr():
@@ -138,6 +158,8 @@ def main():
     # ---- align2D / align1D -----------------------------------------------------------------------------
     n = args.features
     cam, pyr, idx, lvl, border, ref, px0, dirs = feature_case(n, 2, dev)
+    pyr = {l: pin(v) for l, v in pyr.items()}
+    idx, lvl, border, ref, px0, dirs = pin(idx), pin(lvl), pin(border), pin(ref), pin(px0), pin(dirs)
     feats, keep = abi.make_align2d_batch(pyr, idx, lvl, border, ref, np.ascontiguousarray(px0), 10, cam.width, cam.height)
     o_px = np.zeros((n, 2))
     o_cv = np.zeros(n, np.uint8)
@@ -174,7 +196,7 @@ def main():
             "converged_frac": float(got[0].mean()), "cpu_oracle_features_per_s": rate, "cpu_threads": th}
     # ---- Matcher::findMatchDirect (affine warp + patch + align) --------------------------------------------
     m = args.features // 2
-    md = synth.make_match_batch(n=m, n_ref=8, n_cur=8, n_pyr_levels=3, seed=3, device=dev)
+    md = pin_obj(synth.make_match_batch(n=m, n_ref=8, n_cur=8, n_pyr_levels=3, seed=3, device=dev))
     matcher = api.Matcher(10, ctx)
     mo = {}
 
@@ -199,7 +221,7 @@ def main():
         "roofline_frac_upper_bound": alg / (k_ms * 1e-3) / 1e9 / peak, "bit_exact_vs_oracle": bool(exact),
         "success_frac": float(cpu_out.success.mean()), "cpu_oracle_candidates_per_s": rate, "cpu_threads": th}
     # ---- structure optimisation (Point::optimize / LineSeg::optimize) ------------------------------------
-    sd = synth.make_structopt_batch(n_points=200000, n_segs=50000, n_frames=32, seed=4)
+    sd = pin_obj(synth.make_structopt_batch(n_points=struct_points, n_segs=struct_points // 4, n_frames=32, seed=4))
     so = {}
 
     def run_s():
@@ -226,7 +248,7 @@ def main():
         "bit_exact_vs_oracle": bool(exact), "mean_iterations": passes_pt, "cpu_oracle_features_per_s": rate, "cpu_threads": th}
     # ---- depth-filter point-seed update (epipolar ZMSSD search + Bayesian update) ------------------------------
     ns = args.features // 4
-    sdd = synth.make_seed_batch(n=ns, n_ref=8, n_cur=8, n_pyr_levels=3, seed=5, device=dev)
+    sdd = pin_obj(synth.make_seed_batch(n=ns, n_ref=8, n_cur=8, n_pyr_levels=3, seed=5, device=dev))
     dfilt = api.DepthFilter(ctx)
     dfo = {}
 
@@ -250,7 +272,7 @@ def main():
         "status_hist_not_visible_no_match_updated": np.bincount(cpu_sd.status, minlength=3).tolist(),
         "cpu_oracle_seeds_per_s": rate, "cpu_threads": th}
     # ---- line seeds -------------------------------------------------------------------------------------------
-    ls = synth.make_line_seed_batch(n=ns // 2, n_ref=8, n_cur=8, n_pyr_levels=3, seed=6, device=dev)
+    ls = pin_obj(synth.make_line_seed_batch(n=ns // 2, n_ref=8, n_cur=8, n_pyr_levels=3, seed=6, device=dev))
     lo = {}
 
     def run_ls():
@@ -270,7 +292,17 @@ def main():
         "status_and_depths_bit_exact_vs_oracle": exact,
         "status_hist_not_visible_no_match_updated": np.bincount(cpu_ls.status, minlength=3).tolist(),
         "cpu_oracle_seeds_per_s": rate, "cpu_threads": th}
-    print(json.dumps(res, indent=1))
+    res["host_memory"] = "pinned (page-locked) inputs for every e2e_ms"
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--images", type=int, default=256)
+    ap.add_argument("--features", type=int, default=400000)
+    args = ap.parse_args()
+    print(json.dumps(measure(args.reps, args.images, args.features), indent=1))
 
 
 if __name__ == "__main__":
