@@ -125,6 +125,7 @@ def test_gate_with_several_chunks_and_copy_streams(pkg, synth, gen_device, monke
     monkeypatch.delenv("PLSVO_E2E_CHUNKS")
     monkeypatch.setenv("PLSVO_GATE_CHUNK", "128")
     monkeypatch.setenv("PLSVO_COPY_STREAMS", "2")
+    monkeypatch.setenv("PLSVO_VARIANT", "128,4")  # the CTA shape of the single-shot call: bitwise comparison of the gate alone
     for _ in range(2):
         gated = pkg.SparseImgAlign(4, 2, 30).run(data)
         for f in ("T_cur_w", "n_tracked", "iters", "H"):

@@ -26,3 +26,12 @@ os.environ.pop("PLSVO_VARIANT")
 al, po = synth.make_track_batch(batch=3, n_pts=120, n_segs=24, seed=14, device="cuda")
 ao, pout = plsvo_b200.api.track(al, po)
 print("track ok", ao.iters.sum(), pout.num_obs_pt.tolist(), flush=True)
+# next-row kernels whose outputs grew in round 2 (Matcher::A_cur_ref_, end-point px_cur of the line seeds)
+md = synth.make_match_batch(n=300, seed=15, device="cuda")
+mo = plsvo_b200.api.Matcher(10).findMatchDirect(md)
+mr = oracle_lib.match_direct(abi, md, 4)
+print("match_direct A equal", bool(np.array_equal(mo.A_cur_ref, mr.A_cur_ref, equal_nan=True)), "success equal", bool(np.array_equal(mo.success, mr.success)), flush=True)
+ls = synth.make_line_seed_batch(n=200, seed=16, device="cuda")
+lo = plsvo_b200.api.DepthFilter().updateLineSeeds(ls)
+lr = oracle_lib.line_seed_update(abi, ls, 4)
+print("line seeds status equal", bool(np.array_equal(lo.status, lr.status)), "px_cur_e equal", bool(np.array_equal(lo.px_cur_e, lr.px_cur_e, equal_nan=True)), flush=True)
