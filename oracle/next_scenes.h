@@ -12,6 +12,7 @@
 #include <plsvo/frame.h>
 #include <vikit/pinhole_camera.h>
 
+#include <chrono>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -53,6 +54,15 @@ typedef struct plsvo_scene_seed_out {
 }
 
 namespace plsvo_scenes {
+// wall-clock seconds the last scene driver spent in the loop under test (scene construction and read-back excluded)
+inline double& last_loop_seconds() {
+  static double s = 0.0;
+  return s;
+}
+struct LoopTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~LoopTimer() { last_loop_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 using Eigen::Quaterniond;
 using Eigen::Vector2d;
 using Eigen::Vector3d;
@@ -293,12 +303,17 @@ int run_seed_scene(const plsvo_seed_batch* in, const plsvo_line_seed_batch* lin,
   if (lin && lin->seeds.n_cur_images != in->n_cur_images) return PLSVO_ERR_INVALID;
   plsvo::Config::nPyrLevels() = (size_t)in->n_pyr_levels;
   *out->n_pt_marks = 0, *out->n_seg_marks = 0;
+  last_loop_seconds() = 0.0;
   SeedScene<DF> sc(in, lin, out);
   for (int c = 0; c < in->n_cur_images; ++c) {
     sc.load(in, lin, c, pt_age, seg_age);
     FramePtr frame = sc.curs[c];  // one frame serves both seed kinds: the two batches must describe the same current views
     frame->is_keyframe_ = is_keyframe != 0;
-    const int rc = sc.df->update(frame);  // DepthFilter::updateSeeds(frame)
+    int rc;
+    {
+      LoopTimer timer;
+      rc = sc.df->update(frame);  // DepthFilter::updateSeeds(frame)
+    }
     if (rc != PLSVO_OK) return rc;
     sc.read_back();
   }

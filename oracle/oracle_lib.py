@@ -536,3 +536,14 @@ def ref_seed_scene(abi, pts, lines=None, pt_age=None, seg_age=None, is_keyframe=
 def shimref_seed_scene(abi, pts, lines=None, pt_age=None, seg_age=None, is_keyframe=False, cpu: bool = False):
     """The same update through plsvo::b200::DepthFilterB200 (two C-ABI calls per frame: GPU, or the oracle-backed adapter)."""
     return _seed_scene(load_shimref(abi, cpu).plsvo_shimref_seed_scene, abi, pts, lines, pt_age, seg_age, is_keyframe)
+
+
+def last_loop_seconds(abi, shim: bool, cpu: bool = False) -> float:
+    """Wall-clock seconds of the loop under test in the last *_match_scene / *_seed_scene call (scene construction excluded)."""
+    if shim:
+        fn = load_shimref(abi, cpu).plsvo_shimref_last_loop_seconds
+    else:
+        fn = load_ref(abi).plsvo_ref_last_loop_seconds
+    fn.restype = C.c_double
+    fn.argtypes = []
+    return float(fn())

@@ -627,6 +627,8 @@ int plsvo_ref_match_scene(const plsvo_match_batch* in, int n_obs, const plsvo_sc
   m.search_level_ = -1, m.ref_ftr_ = NULL;
   m.A_cur_ref_.setZero();
   m.options_.align_max_iter = in->n_iter;
+  plsvo_scenes::last_loop_seconds() = 0.0;
+  plsvo_scenes::LoopTimer timer;
   for (int c = 0; c < in->n_cur_images; ++c) {
     for (int i = 0; i < in->n_features; ++i) {
       if (in->cur_index[i] != c) continue;
@@ -672,6 +674,8 @@ int plsvo_ref_seed_scene(const plsvo_seed_batch* in, const plsvo_line_seed_batch
                          int is_keyframe, const plsvo_scene_seed_out* out) {
   return plsvo_scenes::run_seed_scene<DepthFilterSceneProbe>(in, lin, pt_age, seg_age, is_keyframe, out);
 }
+
+double plsvo_ref_last_loop_seconds(void) { return plsvo_scenes::last_loop_seconds(); }
 
 const char* plsvo_ref_describe(void) {
   return "rubengooj/pl-svo src/{sparse_img_align,pose_optimizer,feature,feature_alignment,matcher,config,feature3D_impl,depth_filter}.cpp compiled unmodified against stand-in "

@@ -267,6 +267,8 @@ int plsvo_shimref_match_scene(const plsvo_match_batch* in, int n_obs, const plsv
   plsvo::b200::DirectMatcher m(in->n_iter);
   m.search_level_ = -1, m.ref_ftr_ = NULL;
   m.A_cur_ref_.setZero();
+  plsvo_scenes::last_loop_seconds() = 0.0;
+  plsvo_scenes::LoopTimer timer;
   for (int c = 0; c < in->n_cur_images; ++c) {
     m.reset(*sc.curs[c]);
     std::vector<size_t> kp(in->n_features, 0), ks(sc.segs.size(), 0);
@@ -320,4 +322,5 @@ int plsvo_shimref_seed_scene(const plsvo_seed_batch* in, const plsvo_line_seed_b
                              int is_keyframe, const plsvo_scene_seed_out* out) {
   return plsvo_scenes::run_seed_scene<DepthFilterB200SceneProbe>(in, lin, pt_age, seg_age, is_keyframe, out);
 }
+double plsvo_shimref_last_loop_seconds(void) { return plsvo_scenes::last_loop_seconds(); }
 }
