@@ -6,6 +6,7 @@
 // without a GPU: `make -C oracle shimref-cpu` links shimref_harness.cpp + the shim + this file + plsvo_oracle.cpp into
 // oracle/_ref/libplsvo_shimref_cpu.so, and tests/test_reference_tu_cpu.py requires that reference objects pushed through the
 // shim come back exactly as the reference's own sparse_img_align.cpp / pose_optimizer.cpp leave them.
+#include <cstdlib>
 #include <cstring>
 
 #include "../include/plsvo_b200.h"
@@ -27,6 +28,14 @@ int plsvo_ctx_create(int, void*, plsvo_ctx** out) {
   return PLSVO_OK;
 }
 void plsvo_ctx_destroy(plsvo_ctx*) {}
+int plsvo_host_alloc(void** ptr, size_t bytes) {  // plain memory: nothing is copied to a device here
+  *ptr = malloc(bytes);
+  return *ptr ? PLSVO_OK : PLSVO_ERR_INVALID;
+}
+int plsvo_host_free(void* ptr) {
+  free(ptr);
+  return PLSVO_OK;
+}
 const char* plsvo_last_error(const plsvo_ctx*) { return "oracle-backed test adapter"; }
 int plsvo_align_batch_run(plsvo_ctx*, const plsvo_align_batch* b, const plsvo_align_params* p, const plsvo_align_result* o) {
   return plsvo_oracle_align_batch(b, p, o, 1, 0);

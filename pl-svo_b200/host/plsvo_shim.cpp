@@ -74,6 +74,27 @@ ShimSession::ShimSession() {
   ctx_ = plsvo::ctx();
 }
 ShimSession::~ShimSession() { g_mu.unlock(); }
+namespace {
+char* g_scratch = nullptr;
+size_t g_scratch_cap = 0, g_scratch_off = 0;
+}  // namespace
+bool ShimSession::scratch_reserve(size_t bytes) {
+  g_scratch_off = 0;
+  if (bytes <= g_scratch_cap) return true;
+  if (g_scratch) plsvo_host_free(g_scratch);
+  g_scratch = nullptr, g_scratch_cap = 0;
+  void* p = nullptr;
+  const size_t cap = bytes + bytes / 4 + 4096;
+  if (plsvo_host_alloc(&p, cap) != PLSVO_OK || !p) return false;
+  g_scratch = static_cast<char*>(p), g_scratch_cap = cap;
+  return true;
+}
+void* ShimSession::scratch_take(size_t bytes) {
+  const size_t at = (g_scratch_off + 255) / 256 * 256;
+  if (!g_scratch || at + bytes > g_scratch_cap) return nullptr;
+  g_scratch_off = at + bytes;
+  return g_scratch + at;
+}
 int ShimSession::fail(int rc, const char* what) {
   g_err = ctx_ ? plsvo_last_error(ctx_) : "no device context";
   std::fprintf(stderr, "[plsvo_b200] %s failed: %s\n", what, g_err.c_str());

@@ -83,6 +83,12 @@ class ShimSession {
   ::plsvo_ctx* ctx() const { return ctx_; }
   /// records plsvo_last_error(ctx) for shim_last_error() and prints it with `what`; returns rc
   int fail(int rc, const char* what);
+  /// Page-locked scratch shared by the shim's calls (plsvo_host_alloc): what a call packs for the device goes here, so that
+  /// the library's host<->device copies are asynchronous DMA instead of staged pageable copies.  reserve() makes room for
+  /// `bytes` and rewinds; take() hands out 256-byte aligned pieces (NULL when the reservation is exhausted).  The
+  /// contents are only valid while this session is alive.
+  bool scratch_reserve(size_t bytes);
+  void* scratch_take(size_t bytes);
 
  private:
   ::plsvo_ctx* ctx_;

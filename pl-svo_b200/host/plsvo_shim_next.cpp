@@ -36,69 +36,93 @@ void put(std::vector<double>& dst, const V& v, int n) {
   for (int i = 0; i < n; ++i) dst.push_back(v[i]);
 }
 
+// Everything a call sends to the device is packed into the shim's page-locked scratch (ShimSession::scratch_*), so that
+// the library's copies are asynchronous DMA.  Sizes are summed first (Need), the scratch is reserved once, then carved.
+struct Need {
+  size_t bytes = 0;
+  void add(size_t n) { bytes += (n + 255) / 256 * 256 + 256; }
+};
+template <class T>
+const T* pinned_copy(ShimSession& ss, const std::vector<T>& v) {
+  if (v.empty()) return nullptr;
+  T* p = static_cast<T*>(ss.scratch_take(v.size() * sizeof(T)));
+  if (p) std::memcpy(p, v.data(), v.size() * sizeof(T));
+  return p;
+}
+template <class T>
+T* pinned_out(ShimSession& ss, size_t n) {
+  return static_cast<T*>(ss.scratch_take(std::max<size_t>(n, 1) * sizeof(T)));
+}
+
 // The reference observations of one call live in several keyframes, each with its own pyramid allocation; the ABI takes
 // one block per level holding all of them ([n_frames][rows_l][cols_l], dense).  Only the levels some row refers to are
 // packed (the kernels read a keyframe at the level of its feature only).
 struct PackedPyramids {
-  std::vector<uint8_t> store;
+  bool used[PLSVO_MAX_LEVELS];
   const uint8_t* img[PLSVO_MAX_LEVELS];
   size_t pitch[PLSVO_MAX_LEVELS], stride[PLSVO_MAX_LEVELS];
-  bool pack(const std::vector<Frame*>& frames, const std::vector<int32_t>& level_of_row, int width, int height) {
-    bool used[PLSVO_MAX_LEVELS] = {false};
+  size_t n_frames;
+  bool plan(const std::vector<Frame*>& frames, const std::vector<int32_t>& level_of_row, int width, int height, Need& need) {
+    n_frames = frames.size();
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) used[l] = false, img[l] = nullptr, pitch[l] = stride[l] = 0;
     for (int32_t l : level_of_row) {
       if (l < 0 || l >= PLSVO_MAX_LEVELS) return false;
       used[l] = true;
     }
-    size_t off[PLSVO_MAX_LEVELS] = {0}, total = 0;
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
-      img[l] = nullptr, pitch[l] = stride[l] = 0;
       if (!used[l]) continue;
       pitch[l] = (size_t)(width >> l), stride[l] = pitch[l] * (size_t)(height >> l);
-      off[l] = total, total += stride[l] * frames.size();
+      need.add(stride[l] * n_frames);
     }
-    store.resize(total);
+    return true;
+  }
+  bool pack(ShimSession& ss, const std::vector<Frame*>& frames, int width, int height) {
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
       if (!used[l]) continue;
-      img[l] = store.data() + off[l];
+      uint8_t* base = static_cast<uint8_t*>(ss.scratch_take(stride[l] * n_frames));
+      if (!base) return false;
+      img[l] = base;
       for (size_t r = 0; r < frames.size(); ++r) {
         if ((int)frames[r]->img_pyr_.size() <= l) return false;
         const cv::Mat& m = frames[r]->img_pyr_[l];
         if (m.rows != (height >> l) || m.cols != (width >> l) || !m.data) return false;
-        uint8_t* d = store.data() + off[l] + r * stride[l];
-        for (int y = 0; y < m.rows; ++y) std::memcpy(d + (size_t)y * pitch[l], m.data + (size_t)y * m.step[0], (size_t)m.cols);
+        uint8_t* d = base + r * stride[l];
+        if (m.step[0] == pitch[l])
+          std::memcpy(d, m.data, stride[l]);
+        else
+          for (int y = 0; y < m.rows; ++y) std::memcpy(d + (size_t)y * pitch[l], m.data + (size_t)y * m.step[0], (size_t)m.cols);
       }
     }
     return true;
   }
 };
 
-// the current frame: one image per level, used where it lies unless its rows are padded and `dense` is required
+// the current frame: its levels 0 .. n_levels-1, copied densely into the scratch
 struct CurPyramid {
-  std::vector<uint8_t> store;
   const uint8_t* img[PLSVO_MAX_LEVELS];
   size_t pitch[PLSVO_MAX_LEVELS], stride[PLSVO_MAX_LEVELS];
-  bool wrap(const Frame& f, int n_levels, int width, int height, bool dense) {
-    size_t total = 0, off[PLSVO_MAX_LEVELS] = {0};
-    bool copy[PLSVO_MAX_LEVELS] = {false};
+  bool plan(const Frame& f, int n_levels, int width, int height, Need& need) {
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
       img[l] = nullptr, pitch[l] = stride[l] = 0;
       if (l >= n_levels) continue;
       if ((int)f.img_pyr_.size() <= l) return false;
       const cv::Mat& m = f.img_pyr_[l];
       if (m.rows != (height >> l) || m.cols != (width >> l) || !m.data) return false;
-      if (dense && m.step[0] != (size_t)m.cols) copy[l] = true, off[l] = total, total += (size_t)m.rows * m.cols;
+      pitch[l] = (size_t)m.cols, stride[l] = pitch[l] * (size_t)m.rows;
+      need.add(stride[l]);
     }
-    store.resize(total);
+    return true;
+  }
+  bool pack(ShimSession& ss, const Frame& f, int n_levels) {
     for (int l = 0; l < n_levels && l < PLSVO_MAX_LEVELS; ++l) {
       const cv::Mat& m = f.img_pyr_[l];
-      if (copy[l]) {
-        uint8_t* d = store.data() + off[l];
-        for (int y = 0; y < m.rows; ++y) std::memcpy(d + (size_t)y * m.cols, m.data + (size_t)y * m.step[0], (size_t)m.cols);
-        img[l] = d, pitch[l] = (size_t)m.cols;
-      } else {
-        img[l] = m.data, pitch[l] = m.step[0];
-      }
-      stride[l] = pitch[l] * (size_t)m.rows;
+      uint8_t* d = static_cast<uint8_t*>(ss.scratch_take(stride[l]));
+      if (!d) return false;
+      if (m.step[0] == pitch[l])
+        std::memcpy(d, m.data, stride[l]);
+      else
+        for (int y = 0; y < m.rows; ++y) std::memcpy(d + (size_t)y * pitch[l], m.data + (size_t)y * m.step[0], (size_t)m.cols);
+      img[l] = d;
     }
     return true;
   }
@@ -185,31 +209,47 @@ int DirectMatcher::run() {
   if (!camera_of(cur_frame, &b.cam)) return PLSVO_ERR_INVALID;
   b.n_features = (int32_t)n, b.n_ref_images = (int32_t)ref_frames_.size(), b.n_cur_images = 1;
   b.n_pyr_levels = (int32_t)Config::nPyrLevels(), b.n_iter = align_max_iter_;
+  std::vector<double> T_ref(7 * ref_frames_.size()), T_cur(7);
+  for (size_t r = 0; r < ref_frames_.size(); ++r) pose7_of(ref_frames_[r]->T_f_w_, &T_ref[7 * r]);
+  pose7_of(cur_frame.T_f_w_, T_cur.data());
+  std::vector<int32_t> cur_index(n, 0);
   PackedPyramids refs;
   CurPyramid cur;
-  if (!refs.pack(ref_frames_, ref_level_, b.cam.width, b.cam.height) || !cur.wrap(cur_frame, b.n_pyr_levels, b.cam.width, b.cam.height, false))
+  Need need;
+  if (!refs.plan(ref_frames_, ref_level_, b.cam.width, b.cam.height, need) ||
+      !cur.plan(cur_frame, b.n_pyr_levels, b.cam.width, b.cam.height, need))
     return PLSVO_ERR_INVALID;
+  for (size_t bytes : {T_ref.size() * 8, T_cur.size() * 8, n * 4, n * 4, n * 4, n, ref_px_.size() * 8, ref_f_.size() * 8, ref_grad_.size() * 8,
+                       pos_.size() * 8, px_in_.size() * 8, /* outputs */ n * 16, n, n * 4, n * 32})
+    need.add(bytes);
+  ShimSession session;
+  if (!session.ctx()) return PLSVO_ERR_NO_DEVICE;
+  if (!session.scratch_reserve(need.bytes) || !refs.pack(session, ref_frames_, b.cam.width, b.cam.height) ||
+      !cur.pack(session, cur_frame, b.n_pyr_levels))
+    return session.fail(PLSVO_ERR_INVALID, "DirectMatcher::run (packing)");
   for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
     b.ref_img[l] = refs.img[l], b.ref_pitch[l] = refs.pitch[l], b.ref_stride[l] = refs.stride[l];
     b.cur_img[l] = cur.img[l], b.cur_pitch[l] = cur.pitch[l], b.cur_stride[l] = cur.stride[l];
   }
-  std::vector<double> T_ref(7 * ref_frames_.size());
-  for (size_t r = 0; r < ref_frames_.size(); ++r) pose7_of(ref_frames_[r]->T_f_w_, &T_ref[7 * r]);
-  double T_cur[7];
-  pose7_of(cur_frame.T_f_w_, T_cur);
-  std::vector<int32_t> cur_index(n, 0);
-  b.T_ref_w = T_ref.data(), b.T_cur_w = T_cur;
-  b.ref_index = ref_index_.data(), b.cur_index = cur_index.data();
-  b.ref_px = ref_px_.data(), b.ref_f = ref_f_.data(), b.ref_level = ref_level_.data();
-  b.is_edgelet = is_edgelet_.data(), b.ref_grad = ref_grad_.data();
-  b.pos = pos_.data(), b.px_cur = px_in_.data();
+  b.T_ref_w = pinned_copy(session, T_ref), b.T_cur_w = pinned_copy(session, T_cur);
+  b.ref_index = pinned_copy(session, ref_index_), b.cur_index = pinned_copy(session, cur_index);
+  b.ref_px = pinned_copy(session, ref_px_), b.ref_f = pinned_copy(session, ref_f_), b.ref_level = pinned_copy(session, ref_level_);
+  b.is_edgelet = pinned_copy(session, is_edgelet_), b.ref_grad = pinned_copy(session, ref_grad_);
+  b.pos = pinned_copy(session, pos_), b.px_cur = pinned_copy(session, px_in_);
   plsvo_match_result r;
   std::memset(&r, 0, sizeof r);
-  r.px_cur = px_out_.data(), r.success = success_.data(), r.search_level = level_out_.data(), r.A_cur_ref = A_out_.data();
-  ShimSession session;
-  if (!session.ctx()) return PLSVO_ERR_NO_DEVICE;
+  r.px_cur = pinned_out<double>(session, 2 * n), r.success = pinned_out<uint8_t>(session, n);
+  r.search_level = pinned_out<int32_t>(session, n), r.A_cur_ref = pinned_out<double>(session, 4 * n);
+  if (!b.T_ref_w || !b.T_cur_w || !b.ref_index || !b.cur_index || !b.ref_px || !b.ref_f || !b.ref_level || !b.is_edgelet || !b.ref_grad ||
+      !b.pos || !b.px_cur || !r.px_cur || !r.success || !r.search_level || !r.A_cur_ref)
+    return session.fail(PLSVO_ERR_INVALID, "DirectMatcher::run (scratch)");
+  std::memset(r.A_cur_ref, 0, 4 * n * sizeof(double));  // rows the kernel leaves untouched come back as sent
   const int rc = plsvo_match_direct_batch_run(session.ctx(), &b, &r);
   if (rc != PLSVO_OK) return session.fail(rc, "DirectMatcher::run");
+  std::memcpy(px_out_.data(), r.px_cur, 2 * n * sizeof(double));
+  std::memcpy(success_.data(), r.success, n);
+  std::memcpy(level_out_.data(), r.search_level, n * sizeof(int32_t));
+  std::memcpy(A_out_.data(), r.A_cur_ref, 4 * n * sizeof(double));
   ran_ = true;
   return PLSVO_OK;
 }
@@ -266,7 +306,6 @@ struct SeedPack {
   std::vector<uint8_t> is_edgelet;
   std::vector<double> ref_px, ref_f, ref_grad, T_ref;
   std::vector<float> a, b, mu, z_range, sigma2;
-  double T_cur[7];
   PackedPyramids refs;
   CurPyramid cur;
   void add(Feature* ftr, const Vector2d& px, const Vector3d& f, bool edgelet, const Vector2d& grad, float sa, float sb, float smu,
@@ -278,32 +317,42 @@ struct SeedPack {
     put(ref_px, px, 2), put(ref_f, f, 3), put(ref_grad, grad, 2);
     a.push_back(sa), b.push_back(sb), mu.push_back(smu), z_range.push_back(szr), sigma2.push_back(ssig);
   }
-  bool fill(plsvo_seed_batch* sb, const Frame& frame, const Matcher::Options& mo, double convergence_thresh) {
+  // describe the batch and pack it into the session's page-locked scratch; `extra` = bytes the caller will take afterwards
+  bool fill(ShimSession& ss, plsvo_seed_batch* sb, const Frame& frame, const Matcher::Options& mo, double convergence_thresh, size_t extra) {
     std::memset(sb, 0, sizeof *sb);
     if (!camera_of(frame, &sb->cam)) return false;
-    sb->n_seeds = (int32_t)ref_index.size(), sb->n_ref_images = (int32_t)ref_frames.size(), sb->n_cur_images = 1;
+    const size_t n = ref_index.size();
+    sb->n_seeds = (int32_t)n, sb->n_ref_images = (int32_t)ref_frames.size(), sb->n_cur_images = 1;
     sb->n_pyr_levels = (int32_t)Config::nPyrLevels();
     sb->n_iter = mo.align_max_iter, sb->max_epi_search_steps = (int32_t)mo.max_epi_search_steps;
     sb->align_1d = mo.align_1d, sb->subpix_refinement = mo.subpix_refinement;
     sb->epi_search_edgelet_filtering = mo.epi_search_edgelet_filtering;
     sb->epi_search_edgelet_max_angle = mo.epi_search_edgelet_max_angle;
     sb->seed_convergence_sigma2_thresh = convergence_thresh;
-    if (!refs.pack(ref_frames, ref_level, sb->cam.width, sb->cam.height) ||
-        !cur.wrap(frame, sb->n_pyr_levels, sb->cam.width, sb->cam.height, true))
+    T_ref.resize(7 * ref_frames.size());
+    for (size_t r = 0; r < ref_frames.size(); ++r) pose7_of(ref_frames[r]->T_f_w_, &T_ref[7 * r]);
+    std::vector<double> T_cur(7);
+    pose7_of(frame.T_f_w_, T_cur.data());
+    Need need;
+    if (!refs.plan(ref_frames, ref_level, sb->cam.width, sb->cam.height, need) ||
+        !cur.plan(frame, sb->n_pyr_levels, sb->cam.width, sb->cam.height, need))
+      return false;
+    for (size_t bytes : {T_ref.size() * 8, (size_t)56, n * 4, n * 4, n * 4, n, n * 16, n * 24, n * 16, n * 4, n * 4, n * 4, n * 4, n * 4}) need.add(bytes);
+    need.bytes += extra;
+    if (!ss.scratch_reserve(need.bytes) || !refs.pack(ss, ref_frames, sb->cam.width, sb->cam.height) || !cur.pack(ss, frame, sb->n_pyr_levels))
       return false;
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
       sb->ref_img[l] = refs.img[l], sb->ref_pitch[l] = refs.pitch[l], sb->ref_stride[l] = refs.stride[l];
       sb->cur_img[l] = cur.img[l], sb->cur_pitch[l] = cur.pitch[l], sb->cur_stride[l] = cur.stride[l];
     }
-    T_ref.resize(7 * ref_frames.size());
-    for (size_t r = 0; r < ref_frames.size(); ++r) pose7_of(ref_frames[r]->T_f_w_, &T_ref[7 * r]);
-    pose7_of(frame.T_f_w_, T_cur);
-    sb->T_ref_w = T_ref.data(), sb->T_cur_w = T_cur;
-    sb->ref_index = ref_index.data(), sb->cur_index = cur_index.data();
-    sb->ref_px = ref_px.data(), sb->ref_f = ref_f.data(), sb->ref_level = ref_level.data();
-    sb->is_edgelet = is_edgelet.data(), sb->ref_grad = ref_grad.data();
-    sb->a = a.data(), sb->b = b.data(), sb->mu = mu.data(), sb->z_range = z_range.data(), sb->sigma2 = sigma2.data();
-    return true;
+    sb->T_ref_w = pinned_copy(ss, T_ref), sb->T_cur_w = pinned_copy(ss, T_cur);
+    sb->ref_index = pinned_copy(ss, ref_index), sb->cur_index = pinned_copy(ss, cur_index);
+    sb->ref_px = pinned_copy(ss, ref_px), sb->ref_f = pinned_copy(ss, ref_f), sb->ref_level = pinned_copy(ss, ref_level);
+    sb->is_edgelet = pinned_copy(ss, is_edgelet), sb->ref_grad = pinned_copy(ss, ref_grad);
+    sb->a = pinned_copy(ss, a), sb->b = pinned_copy(ss, b), sb->mu = pinned_copy(ss, mu), sb->z_range = pinned_copy(ss, z_range);
+    sb->sigma2 = pinned_copy(ss, sigma2);
+    return sb->T_ref_w && sb->T_cur_w && sb->ref_index && sb->cur_index && sb->ref_px && sb->ref_f && sb->ref_level && sb->is_edgelet &&
+           sb->ref_grad && sb->a && sb->b && sb->mu && sb->z_range && sb->sigma2;
   }
 };
 }  // namespace
@@ -324,20 +373,26 @@ int DepthFilterB200::update_point_seeds(FramePtr frame) {  // depth_filter.cpp:2
     const bool edgelet = sd.ftr->type == PointFeat::EDGELET;
     pk.add(sd.ftr, sd.ftr->px, sd.ftr->f, edgelet, edgelet ? sd.ftr->grad : Vector2d(0, 0), sd.a, sd.b, sd.mu, sd.z_range, sd.sigma2);
   }
-  plsvo_seed_batch sb;
-  if (!pk.fill(&sb, *frame, matcher_.options_, options_.seed_convergence_sigma2_thresh)) return PLSVO_ERR_INVALID;
   const size_t n = pk.ref_index.size();
   std::vector<float> oa(n), ob(n), omu(n), osig(n);
   std::vector<int32_t> status(n);
   std::vector<double> px(2 * n);
-  plsvo_seed_result sr;
-  std::memset(&sr, 0, sizeof sr);
-  sr.a = oa.data(), sr.b = ob.data(), sr.mu = omu.data(), sr.sigma2 = osig.data(), sr.status = status.data(), sr.px_cur = px.data();
   {
     ShimSession session;
     if (!session.ctx()) return PLSVO_ERR_NO_DEVICE;
+    plsvo_seed_batch sb;
+    if (!pk.fill(session, &sb, *frame, matcher_.options_, options_.seed_convergence_sigma2_thresh, 8 * (n * 16 + 512)))
+      return session.fail(PLSVO_ERR_INVALID, "DepthFilterB200::updatePointSeeds (packing)");
+    plsvo_seed_result sr;
+    std::memset(&sr, 0, sizeof sr);
+    sr.a = pinned_out<float>(session, n), sr.b = pinned_out<float>(session, n), sr.mu = pinned_out<float>(session, n);
+    sr.sigma2 = pinned_out<float>(session, n), sr.status = pinned_out<int32_t>(session, n), sr.px_cur = pinned_out<double>(session, 2 * n);
+    if (!sr.a || !sr.b || !sr.mu || !sr.sigma2 || !sr.status || !sr.px_cur)
+      return session.fail(PLSVO_ERR_INVALID, "DepthFilterB200::updatePointSeeds (scratch)");
     const int rc = plsvo_seed_update_batch_run(session.ctx(), &sb, &sr);
     if (rc != PLSVO_OK) return session.fail(rc, "DepthFilterB200::updatePointSeeds");
+    std::memcpy(oa.data(), sr.a, n * 4), std::memcpy(ob.data(), sr.b, n * 4), std::memcpy(omu.data(), sr.mu, n * 4);
+    std::memcpy(osig.data(), sr.sigma2, n * 4), std::memcpy(status.data(), sr.status, n * 4), std::memcpy(px.data(), sr.px_cur, n * 16);
   }
   // ---- replay of the list logic, in list order ----
   size_t i = 0;
@@ -390,24 +445,33 @@ int DepthFilterB200::update_line_seeds(FramePtr frame) {  // depth_filter.cpp:36
     put(sf, sd.ftr->sf, 3), put(ef, sd.ftr->ef, 3);
     mu_e.push_back(sd.mu_e), zr_e.push_back(sd.z_range_e), sig_e.push_back(sd.sigma2_e);
   }
-  plsvo_line_seed_batch lb;
-  std::memset(&lb, 0, sizeof lb);
-  if (!pk.fill(&lb.seeds, *frame, matcherls_.options_, options_.seed_convergence_sigma2_thresh)) return PLSVO_ERR_INVALID;
-  lb.seeds.is_edgelet = NULL, lb.seeds.ref_grad = NULL;
-  lb.ref_sf = sf.data(), lb.ref_ef = ef.data(), lb.mu_e = mu_e.data(), lb.z_range_e = zr_e.data(), lb.sigma2_e = sig_e.data();
   const size_t n = pk.ref_index.size();
   std::vector<float> oa(n), ob(n), omu(n), osig(n), omu_e(n), osig_e(n);
   std::vector<int32_t> status(n);
   std::vector<double> pxe(2 * n);
-  plsvo_line_seed_result lr;
-  std::memset(&lr, 0, sizeof lr);
-  lr.seeds.a = oa.data(), lr.seeds.b = ob.data(), lr.seeds.mu = omu.data(), lr.seeds.sigma2 = osig.data(), lr.seeds.status = status.data();
-  lr.mu_e = omu_e.data(), lr.sigma2_e = osig_e.data(), lr.px_cur_e = pxe.data();
   {
     ShimSession session;
     if (!session.ctx()) return PLSVO_ERR_NO_DEVICE;
+    plsvo_line_seed_batch lb;
+    std::memset(&lb, 0, sizeof lb);
+    if (!pk.fill(session, &lb.seeds, *frame, matcherls_.options_, options_.seed_convergence_sigma2_thresh, 16 * (n * 24 + 512)))
+      return session.fail(PLSVO_ERR_INVALID, "DepthFilterB200::updateLineSeeds (packing)");
+    lb.seeds.is_edgelet = NULL, lb.seeds.ref_grad = NULL;
+    lb.ref_sf = pinned_copy(session, sf), lb.ref_ef = pinned_copy(session, ef);
+    lb.mu_e = pinned_copy(session, mu_e), lb.z_range_e = pinned_copy(session, zr_e), lb.sigma2_e = pinned_copy(session, sig_e);
+    plsvo_line_seed_result lr;
+    std::memset(&lr, 0, sizeof lr);
+    lr.seeds.a = pinned_out<float>(session, n), lr.seeds.b = pinned_out<float>(session, n), lr.seeds.mu = pinned_out<float>(session, n);
+    lr.seeds.sigma2 = pinned_out<float>(session, n), lr.seeds.status = pinned_out<int32_t>(session, n);
+    lr.mu_e = pinned_out<float>(session, n), lr.sigma2_e = pinned_out<float>(session, n), lr.px_cur_e = pinned_out<double>(session, 2 * n);
+    if (!lb.ref_sf || !lb.ref_ef || !lb.mu_e || !lb.z_range_e || !lb.sigma2_e || !lr.seeds.a || !lr.seeds.b || !lr.seeds.mu ||
+        !lr.seeds.sigma2 || !lr.seeds.status || !lr.mu_e || !lr.sigma2_e || !lr.px_cur_e)
+      return session.fail(PLSVO_ERR_INVALID, "DepthFilterB200::updateLineSeeds (scratch)");
     const int rc = plsvo_line_seed_update_batch_run(session.ctx(), &lb, &lr);
     if (rc != PLSVO_OK) return session.fail(rc, "DepthFilterB200::updateLineSeeds");
+    std::memcpy(oa.data(), lr.seeds.a, n * 4), std::memcpy(ob.data(), lr.seeds.b, n * 4), std::memcpy(omu.data(), lr.seeds.mu, n * 4);
+    std::memcpy(osig.data(), lr.seeds.sigma2, n * 4), std::memcpy(status.data(), lr.seeds.status, n * 4);
+    std::memcpy(omu_e.data(), lr.mu_e, n * 4), std::memcpy(osig_e.data(), lr.sigma2_e, n * 4), std::memcpy(pxe.data(), lr.px_cur_e, n * 16);
   }
   size_t i = 0;
   for (auto it = seg_seeds_.begin(); it != seg_seeds_.end(); ++i) {
