@@ -469,12 +469,50 @@ __device__ __forceinline__ bool depth_from_triangulation(const Pose& T, V3 f_ref
 // Matcher::findEpipolarMatchDirectSegmentEndpoint (:420-588): NaN depth ranges and NaN / infinite epipolar lengths are
 // rejected up front and there is no edgelet pre-selection.  Returns false where the reference returns false; on success z is
 // the triangulated depth and (pxc0, pxc1) the matched position (also set, as Matcher::px_cur_, on some failure paths).
-__device__ __forceinline__ bool epipolar_match(const SeedArgs& a, const CamP& cam, const int i, const int r, const int c, const Pose& T_cur_ref,
-                                            const double px_ref0, const double px_ref1, const V3 f, const int level_ref,
-                                            const double d_estimate, const double d_min, const double d_max, const bool segment_endpoint,
-                                            uint8_t* border, double& z, double& pxc0, double& pxc1) {
+//
+// The match runs in three phases so that the one long loop in it — up to max_epi_search_steps ZMSSD evaluations along the
+// epipolar line, whose count differs from seed to seed by orders of magnitude — is not walked by one thread while the 31
+// other lanes of its warp wait for the longest line among them:
+//   epi_begin   (per thread)   everything up to the search: epipolar segment, affine warp, edgelet gate, warped patch, the
+//                              short-segment shortcut (direct alignment); hands out the search description;
+//   warp_epipolar_search (all 32 lanes, one seed at a time)  32 consecutive steps per pass, one per lane;
+//   epi_end     (per thread)   sub-pixel refinement at the best step and triangulation.
+// The search is bit-identical to the sequential loop: uv is advanced by repeated addition exactly as the loop does (lane j
+// applies j additions to the pass's first value), the "same pixel as the previous step" test is a comparison with the
+// neighbouring lane, scores are integers, and ties go to the lowest step as `zmssd < zmssd_best` does.
+struct EpiCtx {
+  double scale, uv0, uv1, step0, step1, uvb0, uvb1;
+  const uint8_t* cur;
+  int ccols, crows, cur_step, search_level, zmssd_best;
+  unsigned int n_iters;
+  float dir0, dir1;
+  uint32_t refw[16], sumA, sumAA;
+};
+enum { EPI_FALSE = 0, EPI_TRUE = 1, EPI_SEARCH = 2 };
+
+// sub-pixel refinement at the search level followed by triangulation (matcher.cpp:326-342, :396-413)
+__device__ __forceinline__ bool epi_refine(const SeedArgs& a, const CamP& cam, const EpiCtx& E, const uint8_t* border, const Pose& T_cur_ref,
+                                           const V3 f, const double start0, const double start1, double& z, double& pxc0, double& pxc1) {
+  float u = (float)DD(start0, E.scale), v = (float)DD(start1, E.scale);
+  const uint8_t* ref = border + 11;
+  bool res;
+  if (a.align_1d) {
+    double h_inv;
+    res = align1d_core(border, ref, 10, E.cur, E.cur_step, E.ccols, E.crows, a.n_iter, E.dir0, E.dir1, u, v, h_inv);
+  } else {
+    res = align2d_core(border, ref, 10, E.cur, E.cur_step, E.ccols, E.crows, a.n_iter, u, v);
+  }
+  if (!res) return false;
+  pxc0 = DM((double)u, E.scale), pxc1 = DM((double)v, E.scale);
+  return depth_from_triangulation(T_cur_ref, f, cam2world(cam, pxc0, pxc1), z);
+}
+
+__device__ __forceinline__ int epi_begin(const SeedArgs& a, const CamP& cam, const int i, const int r, const int c, const Pose& T_cur_ref,
+                                         const double px_ref0, const double px_ref1, const V3 f, const int level_ref, const double d_estimate,
+                                         const double d_min, const double d_max, const bool segment_endpoint, uint8_t* border, EpiCtx& E,
+                                         double& z, double& pxc0, double& pxc1) {
   const size_t I = (size_t)i;
-  if (segment_endpoint && (isnan(d_min) || isnan(d_max))) return false;  // matcher.cpp:434-438
+  if (segment_endpoint && (isnan(d_min) || isnan(d_max))) return EPI_FALSE;  // matcher.cpp:434-438
   const V3 pa = pose_act(T_cur_ref, v_scale(f, d_min)), pb = pose_act(T_cur_ref, v_scale(f, d_max));
   const double Au = DD(pa.x, pa.z), Av = DD(pa.y, pa.z), Bu = DD(pb.x, pb.z), Bv = DD(pb.y, pb.z);
   const double epi0 = DS(Au, Bu), epi1 = DS(Av, Bv);
@@ -487,7 +525,7 @@ __device__ __forceinline__ bool epipolar_match(const SeedArgs& a, const CamP& ca
     c0 = DD(c0, nc), c1 = DD(c1, nc);
     const double ne = __dsqrt_rn(DA(DM(epi0, epi0), DM(epi1, epi1)));
     const double cosangle = fabs(DA(DM(c0, DD(epi0, ne)), DM(c1, DD(epi1, ne))));
-    if (cosangle < a.edgelet_max_angle) return false;
+    if (cosangle < a.edgelet_max_angle) return EPI_FALSE;
   }
   const double det = DS(DM(A00, A11), DM(A10, A01));
   const int search_level = best_search_level(det, a.n_pyr_levels - 1);
@@ -496,90 +534,162 @@ __device__ __forceinline__ bool epipolar_match(const SeedArgs& a, const CamP& ca
   const double dAB0 = DS(pxA0, pxB0), dAB1 = DS(pxA1, pxB1);
   const double scale = (double)(1 << search_level);
   const double epi_length = DD(__dsqrt_rn(DA(DM(dAB0, dAB0), DM(dAB1, dAB1))), scale);
-  if (segment_endpoint && (isnan(epi_length) || isinf(epi_length))) return false;  // matcher.cpp:481-485
+  if (segment_endpoint && (isnan(epi_length) || isinf(epi_length))) return EPI_FALSE;  // matcher.cpp:481-485
   warp_affine_patch(A00, A01, A10, A11, det, a.ref_img[level_ref] + (size_t)r * a.ref_stride[level_ref], (int)a.ref_pitch[level_ref],
                     a.width >> level_ref, a.height >> level_ref, px_ref0, px_ref1, level_ref, search_level, border);
-  const uint8_t* cur = a.cur_img[search_level] + (size_t)c * a.cur_stride[search_level];
-  const int ccols = a.width >> search_level, crows = a.height >> search_level;
-  const int cur_step = (int)a.cur_pitch[search_level];
-  const uint8_t* ref = border + 11;
-  float dir0, dir1;
+  E.scale = scale, E.search_level = search_level;
+  E.cur = a.cur_img[search_level] + (size_t)c * a.cur_stride[search_level];
+  E.ccols = a.width >> search_level, E.crows = a.height >> search_level;
+  E.cur_step = (int)a.cur_pitch[search_level];
   {  // (px_A - px_B).cast<float>().normalized()
     const float fx_ = (float)dAB0, fy_ = (float)dAB1;
     const float n = __fsqrt_rn(__fadd_rn(__fmul_rn(fx_, fx_), __fmul_rn(fy_, fy_)));
-    dir0 = __fdiv_rn(fx_, n), dir1 = __fdiv_rn(fy_, n);
+    E.dir0 = __fdiv_rn(fx_, n), E.dir1 = __fdiv_rn(fy_, n);
   }
-  // sub-pixel refinement at the search level followed by triangulation (:326-342, :396-413)
-  auto refine_and_triangulate = [&](double start0, double start1) -> bool {
-    float u = (float)DD(start0, scale), v = (float)DD(start1, scale);
-    bool res;
-    if (a.align_1d) {
-      double h_inv;
-      res = align1d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, dir0, dir1, u, v, h_inv);
-    } else {
-      res = align2d_core(border, ref, 10, cur, cur_step, ccols, crows, a.n_iter, u, v);
-    }
-    if (!res) return false;
-    pxc0 = DM((double)u, scale), pxc1 = DM((double)v, scale);
-    return depth_from_triangulation(T_cur_ref, f, cam2world(cam, pxc0, pxc1), z);
-  };
   const float elf = fabsf((float)epi_length);
   if (epi_length < 2.0 && (segment_endpoint || (!isnan(elf) && !isinf(elf)))) {
     pxc0 = DD(DA(pxA0, pxB0), 2.0), pxc1 = DD(DA(pxA1, pxB1), 2.0);
-    return refine_and_triangulate(pxc0, pxc1);
+    return epi_refine(a, cam, E, border, T_cur_ref, f, pxc0, pxc1, z, pxc0, pxc1) ? EPI_TRUE : EPI_FALSE;
   }
   const double qsteps = DD(epi_length, 0.7);
-  if (!(qsteps < 9.0e18)) return false;  // NaN / beyond size_t: the x86 conversion yields 2^63, i.e. "too many steps"
-  unsigned long long n_steps = (unsigned long long)qsteps;
-  if (n_steps > (unsigned long long)a.max_epi_search_steps) return false;
-  const double step0 = DD(epi0, (double)n_steps), step1 = DD(epi1, (double)n_steps);
+  if (!(qsteps < 9.0e18)) return EPI_FALSE;  // NaN / beyond size_t: the x86 conversion yields 2^63, i.e. "too many steps"
+  const unsigned long long n_steps = (unsigned long long)qsteps;
+  if (n_steps > (unsigned long long)a.max_epi_search_steps) return EPI_FALSE;
+  E.step0 = DD(epi0, (double)n_steps), E.step1 = DD(epi1, (double)n_steps);
   // ZMSSD of the warped 8x8 patch against the integer-pixel patches along the epipolar line (:354-391)
-  uint32_t refw[16];
+  const uint8_t* ref = border + 11;
   uint32_t sumA = 0, sumAA = 0;
 #pragma unroll
   for (int y = 0; y < 8; ++y) {
     const uint8_t* p = ref + y * 10;
     const uint32_t w0 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
     const uint32_t w1 = p[4] | (p[5] << 8) | (p[6] << 16) | ((uint32_t)p[7] << 24);
-    refw[2 * y] = w0, refw[2 * y + 1] = w1;
+    E.refw[2 * y] = w0, E.refw[2 * y + 1] = w1;
     sumA = __dp4a(w0, 0x01010101u, sumA), sumA = __dp4a(w1, 0x01010101u, sumA);
     sumAA = __dp4a(w0, w0, sumAA), sumAA = __dp4a(w1, w1, sumAA);
   }
-  int zmssd_best = 2000 * 64;
-  double uvb0 = 0.0, uvb1 = 0.0;
-  double uv0 = DS(Bu, step0), uv1 = DS(Bv, step1);
+  E.sumA = sumA, E.sumAA = sumAA;
+  E.uv0 = DS(Bu, E.step0), E.uv1 = DS(Bv, E.step1);
+  E.n_iters = (unsigned int)n_steps + 1u;
+  E.zmssd_best = 2000 * 64, E.uvb0 = 0.0, E.uvb1 = 0.0;
+  return EPI_SEARCH;
+}
+
+// ZMSSD of the reference words against the 8x8 patch whose top-left pixel is p (any alignment)
+__device__ __forceinline__ int zmssd_at(const uint8_t* p, const int cur_step, const uint32_t (&refw)[16], const uint32_t sumA, const uint32_t sumAA) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+  uint32_t sumB = 0, sumBB = 0, sumAB = 0;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    const uint32_t* wr = w + (size_t)y * (cur_step >> 2);
+    const uint32_t x0 = __ldg(wr), x1 = __ldg(wr + 1), x2 = __ldg(wr + 2);
+    const uint32_t c0 = __funnelshift_r(x0, x1, sh), c1 = __funnelshift_r(x1, x2, sh);
+    sumB = __dp4a(c0, 0x01010101u, sumB), sumB = __dp4a(c1, 0x01010101u, sumB);
+    sumBB = __dp4a(c0, c0, sumBB), sumBB = __dp4a(c1, c1, sumBB);
+    sumAB = __dp4a(c0, refw[2 * y], sumAB), sumAB = __dp4a(c1, refw[2 * y + 1], sumAB);
+  }
+  const int iA = (int)sumA, iAA = (int)sumAA, iB = (int)sumB, iBB = (int)sumBB, iAB = (int)sumAB;
+  return iAA - 2 * iAB + iBB - (iA * iA - 2 * iA * iB + iB * iB) / 64;
+}
+
+#ifdef PLSVO_SERIAL_EPI_SEARCH
+// A/B build: the search of a seed walked by its own thread, step by step (the scalar loop of matcher.cpp:354-391)
+__device__ __forceinline__ void warp_epipolar_search(const CamP& cam, const bool mine, EpiCtx& E, const unsigned int) {
+  if (!mine) return;
+  double uv0 = E.uv0, uv1 = E.uv1;
   int last0 = 0, last1 = 0;
-  ++n_steps;
-  for (unsigned long long k = 0; k < n_steps; ++k, uv0 = DA(uv0, step0), uv1 = DA(uv1, step1)) {
+  for (unsigned int k = 0; k < E.n_iters; ++k, uv0 = DA(uv0, E.step0), uv1 = DA(uv1, E.step1)) {
     const double px0 = DA(DM(cam.fx, uv0), cam.cx), px1 = DA(DM(cam.fy, uv1), cam.cy);
-    const int pxi0 = d2i_x86(DA(DD(px0, scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, scale), 0.5));
+    const int pxi0 = d2i_x86(DA(DD(px0, E.scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, E.scale), 0.5));
     if (pxi0 == last0 && pxi1 == last1) continue;
     last0 = pxi0, last1 = pxi1;
-    if (!cam_in_frame(cam, pxi0, pxi1, 8, search_level)) continue;
-    const uint8_t* p = cur + (size_t)(pxi1 - 4) * cur_step + (pxi0 - 4);
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-    const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
-    uint32_t sumB = 0, sumBB = 0, sumAB = 0;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      const uint32_t* wr = w + (size_t)y * (cur_step >> 2);
-      const uint32_t x0 = __ldg(wr), x1 = __ldg(wr + 1), x2 = __ldg(wr + 2);
-      const uint32_t c0 = __funnelshift_r(x0, x1, sh), c1 = __funnelshift_r(x1, x2, sh);
-      sumB = __dp4a(c0, 0x01010101u, sumB), sumB = __dp4a(c1, 0x01010101u, sumB);
-      sumBB = __dp4a(c0, c0, sumBB), sumBB = __dp4a(c1, c1, sumBB);
-      sumAB = __dp4a(c0, refw[2 * y], sumAB), sumAB = __dp4a(c1, refw[2 * y + 1], sumAB);
-    }
-    const int iA = (int)sumA, iAA = (int)sumAA, iB = (int)sumB, iBB = (int)sumBB, iAB = (int)sumAB;
-    const int zmssd = iAA - 2 * iAB + iBB - (iA * iA - 2 * iA * iB + iB * iB) / 64;
-    if (zmssd < zmssd_best) zmssd_best = zmssd, uvb0 = uv0, uvb1 = uv1;
+    if (!cam_in_frame(cam, pxi0, pxi1, 8, E.search_level)) continue;
+    const int zmssd = zmssd_at(E.cur + (size_t)(pxi1 - 4) * E.cur_step + (pxi0 - 4), E.cur_step, E.refw, E.sumA, E.sumAA);
+    if (zmssd < E.zmssd_best) E.zmssd_best = zmssd, E.uvb0 = uv0, E.uvb1 = uv1;
   }
-  if (zmssd_best < 2000 * 64) {
-    pxc0 = DA(DM(cam.fx, uvb0), cam.cx), pxc1 = DA(DM(cam.fy, uvb1), cam.cy);
+}
+#else
+__device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
+// Every lane of the warp calls this; `mine` says whether the lane's own seed needs a search (described by its E).
+// Hybrid schedule: the first `serial_steps` steps of every search are walked by the seed's own thread (all lanes busy side
+// by side: most epipolar segments are that short), what lies beyond is taken over by the whole warp, 32 steps per pass,
+// seed after seed — so a warp never waits for one long line with 31 lanes idle.  serial_steps = 0 when a warp holds few seeds.
+__device__ __forceinline__ void warp_epipolar_search(const CamP& cam, const bool mine, EpiCtx& E, const unsigned int serial_steps) {
+  const int lane = threadIdx.x & 31;
+  // ---- own thread: steps [0, min(n, serial_steps)) ----
+  double uv0 = E.uv0, uv1 = E.uv1;
+  int last0 = 0, last1 = 0;  // `last_checked_pxi` starts at (0, 0)
+  unsigned int k_done = 0;
+  if (mine) {
+    const unsigned int n_own = E.n_iters < serial_steps ? E.n_iters : serial_steps;
+    for (; k_done < n_own; ++k_done, uv0 = DA(uv0, E.step0), uv1 = DA(uv1, E.step1)) {
+      const double px0 = DA(DM(cam.fx, uv0), cam.cx), px1 = DA(DM(cam.fy, uv1), cam.cy);
+      const int pxi0 = d2i_x86(DA(DD(px0, E.scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, E.scale), 0.5));
+      if (pxi0 == last0 && pxi1 == last1) continue;
+      last0 = pxi0, last1 = pxi1;
+      if (!cam_in_frame(cam, pxi0, pxi1, 8, E.search_level)) continue;
+      const int zmssd = zmssd_at(E.cur + (size_t)(pxi1 - 4) * E.cur_step + (pxi0 - 4), E.cur_step, E.refw, E.sumA, E.sumAA);
+      if (zmssd < E.zmssd_best) E.zmssd_best = zmssd, E.uvb0 = uv0, E.uvb1 = uv1;
+    }
+  }
+  // ---- whole warp: the steps beyond, one seed at a time ----
+  unsigned int todo = __ballot_sync(0xffffffffu, mine && k_done < E.n_iters);
+  while (todo) {
+    const int s = __ffs(todo) - 1;
+    todo &= todo - 1;
+    // the owner's search state, broadcast
+    const double st0 = shfl_d(E.step0, s), st1 = shfl_d(E.step1, s), scale = shfl_d(E.scale, s);
+    double base0 = shfl_d(uv0, s), base1 = shfl_d(uv1, s);
+    const unsigned int n = __shfl_sync(0xffffffffu, E.n_iters, s), k_first = __shfl_sync(0xffffffffu, k_done, s);
+    const int cur_step = __shfl_sync(0xffffffffu, E.cur_step, s), level = __shfl_sync(0xffffffffu, E.search_level, s);
+    const uint8_t* cur = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(E.cur), s));
+    const uint32_t sumA = __shfl_sync(0xffffffffu, E.sumA, s), sumAA = __shfl_sync(0xffffffffu, E.sumAA, s);
+    uint32_t rw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rw[j] = __shfl_sync(0xffffffffu, E.refw[j], s);
+    int best = __shfl_sync(0xffffffffu, E.zmssd_best, s);
+    int prev0 = __shfl_sync(0xffffffffu, last0, s), prev1 = __shfl_sync(0xffffffffu, last1, s);
+    double bu0 = shfl_d(E.uvb0, s), bu1 = shfl_d(E.uvb1, s);
+    for (unsigned int k0 = k_first; k0 < n; k0 += 32) {
+      // uv of step k0 + lane: the pass's first value advanced `lane` times, one rounded addition at a time
+      double u0 = base0, u1 = base1;
+#pragma unroll 1
+      for (int t = 0; t < 31; ++t)
+        if (t < lane) u0 = DA(u0, st0), u1 = DA(u1, st1);
+      base0 = DA(shfl_d(u0, 31), st0), base1 = DA(shfl_d(u1, 31), st1);
+      const double px0 = DA(DM(cam.fx, u0), cam.cx), px1 = DA(DM(cam.fy, u1), cam.cy);
+      const int pxi0 = d2i_x86(DA(DD(px0, scale), 0.5)), pxi1 = d2i_x86(DA(DD(px1, scale), 0.5));
+      int q0 = __shfl_up_sync(0xffffffffu, pxi0, 1), q1 = __shfl_up_sync(0xffffffffu, pxi1, 1);
+      if (lane == 0) q0 = prev0, q1 = prev1;
+      prev0 = __shfl_sync(0xffffffffu, pxi0, 31), prev1 = __shfl_sync(0xffffffffu, pxi1, 31);
+      const bool eval = (k0 + (unsigned int)lane < n) && !(pxi0 == q0 && pxi1 == q1) && cam_in_frame(cam, pxi0, pxi1, 8, level);
+      int zm = 0x7fffffff;
+      if (eval) zm = zmssd_at(cur + (size_t)(pxi1 - 4) * cur_step + (pxi0 - 4), cur_step, rw, sumA, sumAA);
+      // lowest score of the pass, ties to the lowest lane (= the lowest step, as `zmssd < zmssd_best` keeps the first)
+      int zmin = zm, lmin = lane;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        const int oz = __shfl_xor_sync(0xffffffffu, zmin, d), ol = __shfl_xor_sync(0xffffffffu, lmin, d);
+        if (oz < zmin || (oz == zmin && ol < lmin)) zmin = oz, lmin = ol;
+      }
+      if (zmin < best) best = zmin, bu0 = shfl_d(u0, lmin), bu1 = shfl_d(u1, lmin);
+    }
+    if (lane == s) E.zmssd_best = best, E.uvb0 = bu0, E.uvb1 = bu1;
+  }
+}
+#endif
+
+// after the search (matcher.cpp:393-413)
+__device__ __forceinline__ bool epi_end(const SeedArgs& a, const CamP& cam, const EpiCtx& E, const uint8_t* border, const Pose& T_cur_ref,
+                                        const V3 f, double& z, double& pxc0, double& pxc1) {
+  if (E.zmssd_best < 2000 * 64) {
+    pxc0 = DA(DM(cam.fx, E.uvb0), cam.cx), pxc1 = DA(DM(cam.fy, E.uvb1), cam.cy);
     if (a.subpix_refinement) {
-      return refine_and_triangulate(pxc0, pxc1);
+      return epi_refine(a, cam, E, border, T_cur_ref, f, pxc0, pxc1, z, pxc0, pxc1);
     } else {
-      const V3 u3{uvb0, uvb1, 1.0};
+      const V3 u3{E.uvb0, E.uvb1, 1.0};
       const double n = v_norm(u3);
       return depth_from_triangulation(T_cur_ref, f, V3{DD(u3.x, n), DD(u3.y, n), DD(u3.z, n)}, z);
     }
@@ -651,31 +761,42 @@ __device__ __forceinline__ void depth_range(const float mu, const float sigma2, 
   d_estimate = DD(1.0, (double)mu), d_min = DD(1.0, (double)z_inv_min), d_max = DD(1.0, (double)z_inv_max);
 }
 
+// a.spw seeds per warp (lanes >= spw idle outside the search): 32 when the batch fills the GPU, fewer for the few hundred
+// seeds of one frame, so that their searches run side by side instead of one after the other inside a warp
 __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs a) {
   __shared__ __align__(4) uint8_t s_border[kA2Threads][108];
-  const int tid = threadIdx.x;
-  const int i = blockIdx.x * kA2Threads + tid;
-  if (i >= a.n) return;
-  const size_t I = (size_t)i;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i = (blockIdx.x * (kA2Threads / 32) + (tid >> 5)) * a.spw + lane;
+  const bool live = lane < a.spw && i < a.n;
+  const size_t I = (size_t)(live ? i : 0);
   const CamP cam{a.fx, a.fy, a.cx, a.cy, a.width, a.height};
-  float sa = a.a[i], sb = a.b[i], smu = a.mu[i], ssig = a.sigma2[i];
-  const float z_range = a.z_range[i];
-  int status = 0;
+  float sa = 0.f, sb = 0.f, smu = 1.f, ssig = 1.f, z_range = 1.f;
+  int status = 0, code = EPI_FALSE;
   const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
   double z = kNaN, pxc0 = kNaN, pxc1 = kNaN;
-  const int r = a.ref_index[i], c = a.cur_index[i];
-  const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
-  const V3 f{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
-  const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // depth_filter.cpp:291
-  if (seed_visible(cam, pose_inverse(T_ref_cur), f, smu)) {
-    double d_estimate, d_min, d_max;
-    depth_range(smu, ssig, d_estimate, d_min, d_max);
-    const Pose T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
-    status = epipolar_match(a, cam, i, r, c, T_cur_ref, a.ref_px[2 * I], a.ref_px[2 * I + 1], f, a.ref_level[i], d_estimate, d_min, d_max,
-                            false, s_border[tid], z, pxc0, pxc1)
-                 ? 2
-                 : 1;
+  Pose T_ref_cur, T_cur_ref;
+  V3 f{0.0, 0.0, 1.0};
+  EpiCtx E;
+  E.n_iters = 0;
+  if (live) {
+    sa = a.a[i], sb = a.b[i], smu = a.mu[i], ssig = a.sigma2[i], z_range = a.z_range[i];
+    const int r = a.ref_index[i], c = a.cur_index[i];
+    const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
+    f = V3{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
+    T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // depth_filter.cpp:291
+    if (seed_visible(cam, pose_inverse(T_ref_cur), f, smu)) {
+      double d_estimate, d_min, d_max;
+      depth_range(smu, ssig, d_estimate, d_min, d_max);
+      T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
+      code = epi_begin(a, cam, i, r, c, T_cur_ref, a.ref_px[2 * I], a.ref_px[2 * I + 1], f, a.ref_level[i], d_estimate, d_min, d_max, false,
+                       s_border[tid], E, z, pxc0, pxc1);
+      status = 1;  // visible: failed unless the match below succeeds
+    }
   }
+  warp_epipolar_search(cam, code == EPI_SEARCH, E, (unsigned int)a.serial_steps);
+  if (!live) return;
+  if (code == EPI_SEARCH) code = epi_end(a, cam, E, s_border[tid], T_cur_ref, f, z, pxc0, pxc1) ? EPI_TRUE : EPI_FALSE;
+  if (status == 1 && code == EPI_TRUE) status = 2;
   if (status == 2) {  // computeTau (:568-584) and updatePointSeed (:489-512)
     float x, tau2, fq, eq;
     seed_measurement(cam, T_ref_cur, f, z, x, tau2);
@@ -702,57 +823,76 @@ __global__ void __launch_bounds__(kA2Threads) seed_update_kernel(const SeedArgs 
 // shared Beta takes a = max(a_s, a_e), b = min(b_s, b_e) (updateLineSeed, :514-565).
 __global__ void __launch_bounds__(kA2Threads) line_seed_update_kernel(const SeedArgs a) {
   __shared__ __align__(4) uint8_t s_border[kA2Threads][108];
-  const int tid = threadIdx.x;
-  const int i = blockIdx.x * kA2Threads + tid;
-  if (i >= a.n) return;
-  const size_t I = (size_t)i;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i = (blockIdx.x * (kA2Threads / 32) + (tid >> 5)) * a.spw + lane;
+  const bool live = lane < a.spw && i < a.n;
+  const size_t I = (size_t)(live ? i : 0);
   const CamP cam{a.fx, a.fy, a.cx, a.cy, a.width, a.height};
-  float sa = a.a[i], sb = a.b[i];
-  float mu_s = a.mu[i], sig_s = a.sigma2[i], mu_e = a.mu_e[i], sig_e = a.sigma2_e[i];
-  const float zr_s = a.z_range[i], zr_e = a.z_range_e[i];
+  float sa = 0.f, sb = 0.f, mu_s = 1.f, sig_s = 1.f, mu_e = 1.f, sig_e = 1.f, zr_s = 1.f, zr_e = 1.f;
   int status = 0;
   const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
   double z_s = kNaN, z_e = kNaN, pxc0 = kNaN, pxc1 = kNaN, pxe0 = kNaN, pxe1 = kNaN;
-  const int r = a.ref_index[i], c = a.cur_index[i];
-  const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
-  const V3 f{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
-  const V3 sf{a.ref_sf[3 * I], a.ref_sf[3 * I + 1], a.ref_sf[3 * I + 2]}, ef{a.ref_ef[3 * I], a.ref_ef[3 * I + 1], a.ref_ef[3 * I + 2]};
-  const Pose T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // :388
-  const Pose T_vis = pose_inverse(T_ref_cur);
-  // :389-400: both hypotheses in front of the camera, then both inside the image
-  bool visible;
-  {
-    const V3 ps = pose_act(T_vis, v_scale(sf, DD(1.0, (double)mu_s))), pe = pose_act(T_vis, v_scale(ef, DD(1.0, (double)mu_e)));
-    visible = !(ps.z < 0.0 || pe.z < 0.0);
-    if (visible) {
-      double u, v;
-      world2cam(cam, ps, u, v);
-      int ox = d2i_x86(u), oy = d2i_x86(v);
-      visible = ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+  Pose T_ref_cur, T_cur_ref;
+  V3 f{0.0, 0.0, 1.0}, sf{0.0, 0.0, 1.0}, ef{0.0, 0.0, 1.0};
+  double px0 = 0.0, px1 = 0.0;
+  int r = 0, c = 0, level_ref = 0;
+  bool visible = false;
+  if (live) {
+    sa = a.a[i], sb = a.b[i];
+    mu_s = a.mu[i], sig_s = a.sigma2[i], mu_e = a.mu_e[i], sig_e = a.sigma2_e[i];
+    zr_s = a.z_range[i], zr_e = a.z_range_e[i];
+    r = a.ref_index[i], c = a.cur_index[i];
+    const Pose T_ref_w = pose_load(a.T_ref_w + 7 * (size_t)r), T_cur_w = pose_load(a.T_cur_w + 7 * (size_t)c);
+    f = V3{a.ref_f[3 * I], a.ref_f[3 * I + 1], a.ref_f[3 * I + 2]};
+    sf = V3{a.ref_sf[3 * I], a.ref_sf[3 * I + 1], a.ref_sf[3 * I + 2]}, ef = V3{a.ref_ef[3 * I], a.ref_ef[3 * I + 1], a.ref_ef[3 * I + 2]};
+    T_ref_cur = pose_mul(T_ref_w, pose_inverse(T_cur_w));  // :388
+    const Pose T_vis = pose_inverse(T_ref_cur);
+    // :389-400: both hypotheses in front of the camera, then both inside the image
+    {
+      const V3 ps = pose_act(T_vis, v_scale(sf, DD(1.0, (double)mu_s))), pe = pose_act(T_vis, v_scale(ef, DD(1.0, (double)mu_e)));
+      visible = !(ps.z < 0.0 || pe.z < 0.0);
       if (visible) {
-        world2cam(cam, pe, u, v);
-        ox = d2i_x86(u), oy = d2i_x86(v);
+        double u, v;
+        world2cam(cam, ps, u, v);
+        int ox = d2i_x86(u), oy = d2i_x86(v);
         visible = ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+        if (visible) {
+          world2cam(cam, pe, u, v);
+          ox = d2i_x86(u), oy = d2i_x86(v);
+          visible = ox >= 0 && ox < cam.width && oy >= 0 && oy < cam.height;
+        }
       }
     }
+    if (visible) {
+      T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
+      px0 = a.ref_px[2 * I], px1 = a.ref_px[2 * I + 1];
+      level_ref = a.ref_level[i];
+    }
   }
-  if (visible) {
-    const Pose T_cur_ref = pose_mul(T_cur_w, pose_inverse(T_ref_w));
-    const double px0 = a.ref_px[2 * I], px1 = a.ref_px[2 * I + 1];
-    const int level_ref = a.ref_level[i];
-    bool ok = true;
+  bool ok = visible;
 #pragma unroll 1
-    for (int e = 0; e < 2 && ok; ++e) {  // start point, then (only if it matched) end point: one inlined copy of the search
-      double de, dmin, dmax, zz = kNaN, q0 = kNaN, q1 = kNaN;
+  for (int e = 0; e < 2; ++e) {  // start point, then (only if it matched) end point; the search is shared by the warp
+    EpiCtx E;
+    E.n_iters = 0;
+    int code = EPI_FALSE;
+    double zz = kNaN, q0 = kNaN, q1 = kNaN;
+    if (ok) {
+      double de, dmin, dmax;
       depth_range(e ? mu_e : mu_s, e ? sig_e : sig_s, de, dmin, dmax);
-      ok = epipolar_match(a, cam, i, r, c, T_cur_ref, px0, px1, f, level_ref, de, dmin, dmax, true, s_border[tid], zz, q0, q1);
+      code = epi_begin(a, cam, i, r, c, T_cur_ref, px0, px1, f, level_ref, de, dmin, dmax, true, s_border[tid], E, zz, q0, q1);
+    }
+    warp_epipolar_search(cam, code == EPI_SEARCH, E, (unsigned int)a.serial_steps);
+    if (ok) {
+      if (code == EPI_SEARCH) code = epi_end(a, cam, E, s_border[tid], T_cur_ref, f, zz, q0, q1) ? EPI_TRUE : EPI_FALSE;
+      ok = code == EPI_TRUE;
       if (e == 0)
         z_s = zz, pxc0 = q0, pxc1 = q1;
       else
         z_e = zz, pxe0 = q0, pxe1 = q1;
     }
-    status = ok ? 2 : 1;
   }
+  if (!live) return;
+  if (visible) status = ok ? 2 : 1;
   if (status == 2) {
     float x_s, tau2_s, x_e, tau2_e;
     seed_measurement(cam, T_ref_cur, sf, z_s, x_s, tau2_s);
@@ -793,15 +933,50 @@ cudaError_t match_direct_kernel_launch(const MatchArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t line_seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s) {
-  if (a.n <= 0) return cudaSuccess;
-  line_seed_update_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+// seeds per warp: as many as keeps ~8 warps on every SM (a power of two between 1 and 32); PLSVO_SEEDS_PER_WARP overrides
+static int seeds_per_warp(int n) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int spw = 1;
+  while (spw < 32 && (long long)n > (long long)spw * sms * 8) spw <<= 1;
+  if (const char* e = getenv("PLSVO_SEEDS_PER_WARP")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 32) spw = v;
+  }
+  return spw;
+}
+// steps of a search its own thread walks before the warp takes over: worth it only when most lanes hold a seed
+static int own_thread_steps(int spw) {
+  int t = spw >= 16 ? 16 : 0;
+  if (const char* e = getenv("PLSVO_EPI_SERIAL_STEPS")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 100000) t = v;
+  }
+  return t;
+}
+
+cudaError_t line_seed_update_kernel_launch(const SeedArgs& a0, cudaStream_t s) {
+  if (a0.n <= 0) return cudaSuccess;
+  SeedArgs a = a0;
+  a.spw = seeds_per_warp(a.n);
+  a.serial_steps = own_thread_steps(a.spw);
+  const int per_cta = a.spw * (kA2Threads / 32);
+  line_seed_update_kernel<<<(a.n + per_cta - 1) / per_cta, kA2Threads, 0, s>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t seed_update_kernel_launch(const SeedArgs& a, cudaStream_t s) {
-  if (a.n <= 0) return cudaSuccess;
-  seed_update_kernel<<<(a.n + kA2Threads - 1) / kA2Threads, kA2Threads, 0, s>>>(a);
+cudaError_t seed_update_kernel_launch(const SeedArgs& a0, cudaStream_t s) {
+  if (a0.n <= 0) return cudaSuccess;
+  SeedArgs a = a0;
+  a.spw = seeds_per_warp(a.n);
+  a.serial_steps = own_thread_steps(a.spw);
+  const int per_cta = a.spw * (kA2Threads / 32);
+  seed_update_kernel<<<(a.n + per_cta - 1) / per_cta, kA2Threads, 0, s>>>(a);
   return cudaGetLastError();
 }
 
