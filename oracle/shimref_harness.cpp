@@ -112,6 +112,7 @@ struct StructScene {
 
 // wall time of every SparseImgAlign::run call of the last plsvo_shimref_align_batch (B = 1 latency, tools/b1_latency.py)
 static std::vector<double> g_run_seconds;
+static std::vector<double> g_po_seconds;  // per frame: the optimizeGaussNewton call alone
 
 extern "C" {
 
@@ -232,12 +233,15 @@ int plsvo_shimref_poseopt_batch(const plsvo_poseopt_batch* B, const plsvo_poseop
     }
     double estimated_scale = 0, error_init = 0, error_final = 0;
     size_t num_obs_pt = 0, num_obs_ls = 0;
+    if (b == 0) g_po_seconds.clear();
+    const auto t_po0 = std::chrono::steady_clock::now();
     if (P->n_iter_ref < 0)  // src/frame_handler_mono.cpp:327-329
       plsvo::pose_optimizer::optimizeGaussNewton(P->reproj_thresh, (size_t)P->n_iter, false, frame, estimated_scale, error_init,
                                                  error_final, num_obs_pt, num_obs_ls);
     else
       plsvo::pose_optimizer::optimizeGaussNewton(P->reproj_thresh, (size_t)P->n_iter, (size_t)P->n_iter_ref, false, frame,
                                                  estimated_scale, error_init, error_final, num_obs_pt, num_obs_ls);
+    g_po_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_po0).count());
     pose_to7(frame->T_f_w_, out->T_f_w + 7 * (size_t)b);
     if (out->cov)
       for (int i = 0; i < 6; ++i)
@@ -323,4 +327,9 @@ int plsvo_shimref_seed_scene(const plsvo_seed_batch* in, const plsvo_line_seed_b
   return plsvo_scenes::run_seed_scene<DepthFilterB200SceneProbe>(in, lin, pt_age, seg_age, is_keyframe, out);
 }
 double plsvo_shimref_last_loop_seconds(void) { return plsvo_scenes::last_loop_seconds(); }
+int plsvo_shimref_poseopt_seconds(double* out, int n) {
+  const int m = std::min<int>(n, (int)g_po_seconds.size());
+  for (int i = 0; i < m; ++i) out[i] = g_po_seconds[i];
+  return m;
+}
 }

@@ -54,6 +54,40 @@ def main():
         "oracle/_ref" if oracle_lib.ref_available() else "oracle port") + pct(cpu))
     print("speed-up at B = 1 (p50): %.1fx; parity: %d / %d pairs inside 1e-5 rad / 1e-4 rel-t, n_tracked equal: %s" % (
         np.percentile(cpu, 50) / np.percentile(secs, 50), int(((ang <= 1e-5) & (rel <= 1e-4)).sum()), n, "n/a"))
+    pose_optimizer(n, lib)
+
+
+def pose_optimizer(n, lib):
+    """The second call of the per-frame path, pose_optimizer::optimizeGaussNewton(2.0, 10, false, frame, ...)
+    (src/frame_handler_mono.cpp:327-329), one frame per call."""
+    pd = synth.make_poseopt_batch(batch=n, n_pts=300, n_segs=80, seed=5200)
+    pp = abi.poseopt_params(2.0, 10, -1)
+    lib.plsvo_shimref_poseopt_seconds.restype = C.c_int
+    lib.plsvo_shimref_poseopt_seconds.argtypes = [C.POINTER(C.c_double), C.c_int]
+    oracle_lib.shimref_poseopt(abi, pd, pp)  # warm
+    got = oracle_lib.shimref_poseopt(abi, pd, pp)
+    secs = np.zeros(n)
+    assert lib.plsvo_shimref_poseopt_seconds(secs.ctypes.data_as(C.POINTER(C.c_double)), n) == n
+    fn = oracle_lib.ref_poseopt if oracle_lib.ref_available() else oracle_lib.poseopt
+    cpu, ref_T = [], np.zeros((n, 7))
+    import copy
+
+    for b in range(n):
+        one = copy.copy(pd)
+        for name, v in vars(pd).items():
+            if isinstance(v, np.ndarray) and v.shape[:1] == (n,):
+                setattr(one, name, np.ascontiguousarray(v[b:b + 1]))
+        t0 = time.perf_counter()
+        r = fn(abi, one, pp, n_threads=1)
+        cpu.append(time.perf_counter() - t0)
+        ref_T[b] = r.T_f_w[0]
+    cpu = np.array(cpu)
+    ang, rel = synth.pose_error(got.T_f_w, ref_T)
+    print("\nworkload: 300 point + 80 line observations, <= 10 Gauss-Newton iterations, one frame per call (B = 1), %d calls" % n)
+    print("B200, plsvo::pose_optimizer::optimizeGaussNewton via the shim: " + pct(secs))
+    print("CPU, the reference's pose_optimizer.cpp, one thread:           " + pct(cpu))
+    print("speed-up at B = 1 (p50): %.1fx; parity: %d / %d frames inside 1e-5 rad / 1e-4 rel-t" % (
+        np.percentile(cpu, 50) / np.percentile(secs, 50), int(((ang <= 1e-5) & (rel <= 1e-4)).sum()), n))
 
 
 def _last(sub):
