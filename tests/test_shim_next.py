@@ -133,3 +133,30 @@ def test_depth_filter_b200_replays_update_seeds_gpu(pkg, oracle, abi, synth, see
     r = oracle.ref_seed_scene(abi, pts, lines, pt_age, seg_age, keyframe)
     s = oracle.shimref_seed_scene(abi, pts, lines, pt_age, seg_age, keyframe)
     _check_seed_scene(s, r, False, pt_age, seg_age)
+
+
+def test_depth_filter_b200_with_every_seed_aged_out_makes_no_device_call(oracle, abi, synth):
+    """Seeds older than max_n_kfs are erased before anything is packed: same fates as the reference, nothing updated."""
+    _need_ref(oracle, cpu=True)
+    pts, lines, _, _ = _seed_data(synth, 9720, n=120)
+    old_p, old_s = np.full(pts.n, 9, np.int32), np.full(lines.n, 9, np.int32)
+    r = oracle.ref_seed_scene(abi, pts, lines, old_p, old_s, True)
+    s = oracle.shimref_seed_scene(abi, pts, lines, old_p, old_s, True, cpu=True)
+    assert (r.pt_fate == 2).all() and (r.seg_fate == 2).all()
+    np.testing.assert_array_equal(s.pt_fate, r.pt_fate)
+    np.testing.assert_array_equal(s.seg_fate, r.seg_fate)
+    assert len(s.pt_marks) == 0 and len(s.seg_marks) == 0
+
+
+def test_direct_matcher_single_keyframe_single_observation(oracle, abi, synth):
+    """One keyframe, one observation per map feature: getCloseViewObs has nothing to choose from."""
+    _need_ref(oracle, cpu=True)
+    d = synth.make_match_batch(n=200, n_ref=1, n_cur=2, seed=7330)
+    r = oracle.ref_match_scene(abi, d, 1)
+    s = oracle.shimref_match_scene(abi, d, 1, cpu=True)
+    for f in ("pt_found", "pt_level", "pt_ref", "seg_found", "seg_level", "seg_ref"):
+        np.testing.assert_array_equal(getattr(s, f), getattr(r, f), err_msg=f)
+    for f in ("pt_px", "seg_spx", "seg_epx"):
+        a, b = getattr(s, f), getattr(r, f)
+        np.testing.assert_array_equal(a[~np.isnan(b)], b[~np.isnan(b)], err_msg=f)
+    assert set(np.unique(r.pt_ref)) <= {-1, 0}
