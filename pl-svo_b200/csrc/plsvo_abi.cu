@@ -59,6 +59,9 @@ struct plsvo_ctx_impl {
   bool lvl_uploaded[PLSVO_MAX_LEVELS] = {false};
   DevBuf d_pt_depth, d_seg_sdepth, d_seg_edepth;
   DevBuf d_feat;                     // small batches: every feature array in one block (one host->device copy)
+  char* h_po_out = nullptr;          // pinned staging of the pose-optimiser outputs (one D2H per download)
+  size_t h_po_out_cap = 0, po_out_bytes = 0, po_zero_off = 0, po_zero_bytes = 0;
+  DevBuf p_in;                       // packed inputs of a small pose-optimiser batch
   char* h_in = nullptr;              // pinned staging of the small-batch upload
   size_t h_in_cap = 0, img_total = 0;
   cudaEvent_t h_in_ev = nullptr;     // the staged copies of the previous small upload
@@ -217,6 +220,8 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_in) cudaFreeHost(c->h_in);
+  if (c->h_po_out) cudaFreeHost(c->h_po_out);
+  release(c->p_in);
   if (c->h_in_ev) cudaEventDestroy(c->h_in_ev);
   for (int k = 0; k < 4; ++k) {
     if (c->rr_stream[k]) cudaStreamDestroy(c->rr_stream[k]);
@@ -1136,44 +1141,106 @@ int poseopt_upload_impl(plsvo_ctx_impl* c, const plsvo_poseopt_batch* h, const d
   PoseOptArgs& a = c->pa;
   const size_t B = (size_t)h->batch;
   a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs, a.fx = h->fx;
-  if (device_T) {
-    a.T_f_w = device_T;
-  } else {
-    CK(up(c->p_T, h->T_f_w, B * 7, s, &a.T_f_w));
+  {
+    const size_t np_ = (size_t)h->n_pts, ns_ = (size_t)h->n_segs;
+    struct Item {
+      const void* host;
+      size_t bytes;
+      const void** dev;
+      DevBuf* buf;
+    };
+    const Item items[] = {
+        {device_T ? nullptr : h->T_f_w, B * 7 * 8, (const void**)&a.T_f_w, &c->p_T},
+        {h->pt_count, B * 4, (const void**)&a.pt_count, &c->p_pt_count},
+        {h->pt_f, B * np_ * 24, (const void**)&a.pt_f, &c->p_pt_f},
+        {h->pt_pos, B * np_ * 24, (const void**)&a.pt_pos, &c->p_pt_pos},
+        {h->pt_level, B * np_ * 4, (const void**)&a.pt_level, &c->p_pt_level},
+        {h->pt_valid, B * np_, (const void**)&a.pt_valid, &c->p_pt_valid},
+        {h->seg_count, B * 4, (const void**)&a.seg_count, &c->p_seg_count},
+        {h->seg_line, B * ns_ * 24, (const void**)&a.seg_line, &c->p_seg_line},
+        {h->seg_spos, B * ns_ * 24, (const void**)&a.seg_spos, &c->p_seg_spos},
+        {h->seg_epos, B * ns_ * 24, (const void**)&a.seg_epos, &c->p_seg_epos},
+        {h->seg_level, B * ns_ * 4, (const void**)&a.seg_level, &c->p_seg_level},
+        {h->seg_valid, B * ns_, (const void**)&a.seg_valid, &c->p_seg_valid},
+    };
+    size_t total = 0;
+    for (const Item& it : items)
+      if (it.host && it.bytes) total += (it.bytes + 255) / 256 * 256;
+    // small batches (the reference's own call is one frame, frame_handler_mono.cpp:327-329): every input packed into one
+    // pinned block and moved with ONE copy instead of a dozen staged pageable ones
+    const bool small = total > 0 && total <= ((size_t)4 << 20) && !getenv("PLSVO_NO_SMALL_UPLOAD");
+    if (small) {
+      if (c->h_in_cap < total + 256) {
+        if (c->h_in_ev) CK(cudaEventSynchronize(c->h_in_ev));
+        if (c->h_in) cudaFreeHost(c->h_in);
+        c->h_in = nullptr, c->h_in_cap = 0;
+        CK(cudaHostAlloc((void**)&c->h_in, total + 256, cudaHostAllocDefault));
+        c->h_in_cap = total + 256;
+      }
+      if (!c->h_in_ev) CK(cudaEventCreateWithFlags(&c->h_in_ev, cudaEventDisableTiming));
+      else CK(cudaEventSynchronize(c->h_in_ev));  // the previous packed upload has left the staging block
+      CK(ensure(c->p_in, total + 256));
+      size_t off = 0;
+      for (const Item& it : items) {
+        if (!it.host || !it.bytes) {
+          if (!(it.dev == (const void**)&a.T_f_w && device_T)) *it.dev = nullptr;
+          continue;
+        }
+        memcpy(c->h_in + off, it.host, it.bytes);
+        *it.dev = static_cast<char*>(c->p_in.p) + off;
+        off += (it.bytes + 255) / 256 * 256;
+      }
+      CK(cudaMemcpyAsync(c->p_in.p, c->h_in, total, cudaMemcpyHostToDevice, s));
+      CK(cudaEventRecord(c->h_in_ev, s));
+    } else {
+      for (const Item& it : items) {
+        if (!it.host || !it.bytes) {
+          if (!(it.dev == (const void**)&a.T_f_w && device_T)) *it.dev = nullptr;
+          continue;
+        }
+        CK(ensure(*it.buf, it.bytes));
+        *it.dev = it.buf->p;
+        CK(cudaMemcpyAsync(it.buf->p, it.host, it.bytes, cudaMemcpyHostToDevice, s));
+      }
+    }
+    if (device_T) a.T_f_w = device_T;
   }
-  CK(up(c->p_pt_count, h->pt_count, B, s, &a.pt_count));
-  CK(up(c->p_pt_f, h->pt_f, B * h->n_pts * 3, s, &a.pt_f));
-  CK(up(c->p_pt_pos, h->pt_pos, B * h->n_pts * 3, s, &a.pt_pos));
-  CK(up(c->p_pt_level, h->pt_level, B * h->n_pts, s, &a.pt_level));
-  CK(up(c->p_pt_valid, h->pt_valid, B * h->n_pts, s, &a.pt_valid));
-  CK(up(c->p_seg_count, h->seg_count, B, s, &a.seg_count));
-  CK(up(c->p_seg_line, h->seg_line, B * h->n_segs * 3, s, &a.seg_line));
-  CK(up(c->p_seg_spos, h->seg_spos, B * h->n_segs * 3, s, &a.seg_spos));
-  CK(up(c->p_seg_epos, h->seg_epos, B * h->n_segs * 3, s, &a.seg_epos));
-  CK(up(c->p_seg_level, h->seg_level, B * h->n_segs, s, &a.seg_level));
-  CK(up(c->p_seg_valid, h->seg_valid, B * h->n_segs, s, &a.seg_valid));
-  CK(ensure(c->p_out_T, B * 7 * sizeof(double)));
-  CK(ensure(c->p_out_cov, B * 36 * sizeof(double)));
-  CK(ensure(c->p_out_scale, B * sizeof(double)));
-  CK(ensure(c->p_out_ei, B * sizeof(double)));
-  CK(ensure(c->p_out_ef, B * sizeof(double)));
-  CK(ensure(c->p_out_npt, B * sizeof(long long)));
-  CK(ensure(c->p_out_nls, B * sizeof(long long)));
-  CK(ensure(c->p_out_pto, B * std::max(1, h->n_pts)));
-  CK(ensure(c->p_out_sgo, B * std::max(1, h->n_segs)));
-  CK(ensure(c->p_out_iters, B * 2 * sizeof(int32_t)));
-  CK(ensure(c->p_out_status, B * sizeof(int32_t)));
-  a.out_T = static_cast<double*>(c->p_out_T.p);
-  a.out_cov = static_cast<double*>(c->p_out_cov.p);
-  a.out_scale = static_cast<double*>(c->p_out_scale.p);
-  a.out_err_init = static_cast<double*>(c->p_out_ei.p);
-  a.out_err_final = static_cast<double*>(c->p_out_ef.p);
-  a.out_num_pt = static_cast<long long*>(c->p_out_npt.p);
-  a.out_num_ls = static_cast<long long*>(c->p_out_nls.p);
-  a.out_pt_outlier = static_cast<uint8_t*>(c->p_out_pto.p);
-  a.out_seg_outlier = static_cast<uint8_t*>(c->p_out_sgo.p);
-  a.out_iters = static_cast<int32_t*>(c->p_out_iters.p);
-  a.out_status = static_cast<int32_t*>(c->p_out_status.p);
+  // all outputs live in one device block: cleared with one memset where the kernel may leave them untouched, and brought
+  // back with a single D2H into pinned staging
+  {
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+      const size_t at = o;
+      o = (o + bytes + 255) / 256 * 256;
+      return at;
+    };
+    const size_t oT = take(B * 7 * sizeof(double));
+    const size_t ocov = take(B * 36 * sizeof(double)), oscale = take(B * sizeof(double)), oei = take(B * sizeof(double));
+    const size_t oef = take(B * sizeof(double)), onpt = take(B * sizeof(long long)), onls = take(B * sizeof(long long));
+    const size_t zero_end = o;
+    const size_t opto = take(B * (size_t)std::max(1, h->n_pts)), osgo = take(B * (size_t)std::max(1, h->n_segs));
+    const size_t oit = take(B * 2 * sizeof(int32_t)), ost = take(B * sizeof(int32_t));
+    c->po_out_bytes = o, c->po_zero_off = ocov, c->po_zero_bytes = zero_end - ocov;
+    CK(ensure(c->p_out_T, o));
+    if (c->h_po_out_cap < o) {
+      if (c->h_po_out) cudaFreeHost(c->h_po_out);
+      c->h_po_out = nullptr, c->h_po_out_cap = 0;
+      CK(cudaHostAlloc((void**)&c->h_po_out, o, cudaHostAllocDefault));
+      c->h_po_out_cap = o;
+    }
+    char* base = static_cast<char*>(c->p_out_T.p);
+    a.out_T = reinterpret_cast<double*>(base + oT);
+    a.out_cov = reinterpret_cast<double*>(base + ocov);
+    a.out_scale = reinterpret_cast<double*>(base + oscale);
+    a.out_err_init = reinterpret_cast<double*>(base + oei);
+    a.out_err_final = reinterpret_cast<double*>(base + oef);
+    a.out_num_pt = reinterpret_cast<long long*>(base + onpt);
+    a.out_num_ls = reinterpret_cast<long long*>(base + onls);
+    a.out_pt_outlier = reinterpret_cast<uint8_t*>(base + opto);
+    a.out_seg_outlier = reinterpret_cast<uint8_t*>(base + osgo);
+    a.out_iters = reinterpret_cast<int32_t*>(base + oit);
+    a.out_status = reinterpret_cast<int32_t*>(base + ost);
+  }
   c->po_ready = true;
   return PLSVO_OK;
 }
@@ -1198,12 +1265,7 @@ int plsvo_poseopt_launch(plsvo_ctx* ctx, const plsvo_poseopt_params* p) {
   if (smem > (size_t)c->smem_optin) return fail(c, PLSVO_ERR_INVALID, "feature counts exceed shared memory");
   // outputs of frames that return early keep their previous contents: clear the ones we always report
   const size_t B = (size_t)a.B;
-  CK(cudaMemsetAsync(a.out_cov, 0, B * 36 * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(a.out_scale, 0, B * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(a.out_err_init, 0, B * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(a.out_err_final, 0, B * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(a.out_num_pt, 0, B * sizeof(long long), c->stream));
-  CK(cudaMemsetAsync(a.out_num_ls, 0, B * sizeof(long long), c->stream));
+  CK(cudaMemsetAsync(static_cast<char*>(c->p_out_T.p) + c->po_zero_off, 0, c->po_zero_bytes, c->stream));
   CK(poseopt_kernel_launch(a, smem, c->stream));
   c->launches += 1;
   return PLSVO_OK;
@@ -1217,19 +1279,23 @@ int plsvo_poseopt_download(plsvo_ctx* ctx, const plsvo_poseopt_result* o) {
   const PoseOptArgs& a = c->pa;
   const size_t B = (size_t)a.B;
   cudaStream_t s = c->stream;
-  if (o->T_f_w) CK(cudaMemcpyAsync(o->T_f_w, a.out_T, B * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->cov) CK(cudaMemcpyAsync(o->cov, a.out_cov, B * 36 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->estimated_scale) CK(cudaMemcpyAsync(o->estimated_scale, a.out_scale, B * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->error_init) CK(cudaMemcpyAsync(o->error_init, a.out_err_init, B * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->error_final) CK(cudaMemcpyAsync(o->error_final, a.out_err_final, B * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (o->num_obs_pt) CK(cudaMemcpyAsync(o->num_obs_pt, a.out_num_pt, B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  if (o->num_obs_ls) CK(cudaMemcpyAsync(o->num_obs_ls, a.out_num_ls, B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  if (o->pt_outlier && a.n_pts > 0) CK(cudaMemcpyAsync(o->pt_outlier, a.out_pt_outlier, B * a.n_pts, cudaMemcpyDeviceToHost, s));
-  if (o->seg_outlier && a.n_segs > 0)
-    CK(cudaMemcpyAsync(o->seg_outlier, a.out_seg_outlier, B * a.n_segs, cudaMemcpyDeviceToHost, s));
-  if (o->iters) CK(cudaMemcpyAsync(o->iters, a.out_iters, B * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (o->status) CK(cudaMemcpyAsync(o->status, a.out_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->h_po_out, c->p_out_T.p, c->po_out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  {
+    const char* dbase = static_cast<const char*>(c->p_out_T.p);
+    auto host_of = [&](const void* dev) { return c->h_po_out + (static_cast<const char*>(dev) - dbase); };
+    if (o->T_f_w) memcpy(o->T_f_w, host_of(a.out_T), B * 7 * sizeof(double));
+    if (o->cov) memcpy(o->cov, host_of(a.out_cov), B * 36 * sizeof(double));
+    if (o->estimated_scale) memcpy(o->estimated_scale, host_of(a.out_scale), B * sizeof(double));
+    if (o->error_init) memcpy(o->error_init, host_of(a.out_err_init), B * sizeof(double));
+    if (o->error_final) memcpy(o->error_final, host_of(a.out_err_final), B * sizeof(double));
+    if (o->num_obs_pt) memcpy(o->num_obs_pt, host_of(a.out_num_pt), B * sizeof(int64_t));
+    if (o->num_obs_ls) memcpy(o->num_obs_ls, host_of(a.out_num_ls), B * sizeof(int64_t));
+    if (o->pt_outlier && a.n_pts > 0) memcpy(o->pt_outlier, host_of(a.out_pt_outlier), B * (size_t)a.n_pts);
+    if (o->seg_outlier && a.n_segs > 0) memcpy(o->seg_outlier, host_of(a.out_seg_outlier), B * (size_t)a.n_segs);
+    if (o->iters) memcpy(o->iters, host_of(a.out_iters), B * 2 * sizeof(int32_t));
+    if (o->status) memcpy(o->status, host_of(a.out_status), B * sizeof(int32_t));
+  }
   return PLSVO_OK;
 }
 
