@@ -48,6 +48,17 @@ _RESULT_FIELDS = ("T_cur_w", "n_tracked", "H", "seg_killed", "iters", "status", 
 
 
 _pinned = {}
+_thread_pool = None
+
+
+def _pool():
+    """A process-wide pool of a few host threads for the packing copies (created once, not per call)."""
+    global _thread_pool
+    if _thread_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _thread_pool = ThreadPoolExecutor(max_workers=8)
+    return _thread_pool
 
 
 def _staging(key, nbytes, pin):
@@ -128,10 +139,7 @@ def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30
         for r, (sh, (mf, _)) in enumerate(zip(shards, mans)):
             jobs += _pack_jobs(host[r * cap:(r + 1) * cap], sh, mf)
         # the packing is plain memory copies (NumPy releases the GIL): spread them over a few host threads
-        from concurrent.futures import ThreadPoolExecutor
-
-        with ThreadPoolExecutor(max_workers=8) as pool:
-            list(pool.map(lambda j: j(), jobs))
+        list(_pool().map(lambda j: j(), jobs))
         dev_all = stage[: cap * world].to(dev, non_blocking=True)
         bufs = list(dev_all.split(cap))
     dist.broadcast_object_list(meta, src=src)
@@ -164,11 +172,21 @@ def align_sharded(data, max_level: int = 4, min_level: int = 2, n_iter: int = 30
     n_segs = shard.n_segs
     spec = {"T_cur_w": (np.float64, (7,)), "n_tracked": (np.int64, ()), "H": (np.float64, (36,)), "seg_killed": (np.uint8, (n_segs,)),
             "iters": (np.int32, (abi.MAX_LEVELS,)), "status": (np.int32, ()), "patch_iters": (np.uint32, ()), "patch_levels": (np.uint32, ())}
-    full = {}
-    for f in _RESULT_FIELDS:
+    # one record per pair holding every output field, so that the results travel in ONE all_gather
+    widths = [int(np.dtype(spec[f][0]).itemsize * int(np.prod(spec[f][1], dtype=np.int64))) for f in _RESULT_FIELDS]
+    rec = np.zeros((e - b, sum(widths)), np.uint8)
+    off = 0
+    for f, w in zip(_RESULT_FIELDS, widths):
         dt, row = spec[f]
-        local = res[f].astype(dt, copy=False) if e > b else np.zeros((0,) + row, dt)
-        full[f] = gather_rows(np.ascontiguousarray(local), m["n"], device=dev)
+        if e > b:
+            rec[:, off:off + w] = np.ascontiguousarray(res[f].astype(dt, copy=False)).reshape(e - b, -1).view(np.uint8)
+        off += w
+    allrec = gather_rows(rec, m["n"], device=dev)
+    full, off = {}, 0
+    for f, w in zip(_RESULT_FIELDS, widths):
+        dt, row = spec[f]
+        full[f] = np.ascontiguousarray(allrec[:, off:off + w]).view(dt).reshape((m["n"],) + row)
+        off += w
     return full
 
 
