@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only, compact output (tuning)")
     ap.add_argument("--no-next", action="store_true", help="skip the SURVEY 8f (next-row) kernel block of the line")
+    ap.add_argument("--no-chain", action="store_true", help="skip the frame-chain end-to-end leg (e2e_chain)")
     ap.add_argument("--config", default="c2", choices=["c2", "c4"],
                     help="c2: BASELINE configs[1] + the metric's 80 lines (headline); c4: configs[3], chained align -> pose-opt at 720p")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: patch count x pyramid depth sweep (JSON list)")
@@ -690,6 +691,53 @@ def main():
     if dist:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * B * args.steps / (float(e2e_ms.item()) * 1e-3)
+    # ---- end-to-end leg on a frame chain: the same call replaying ONE trajectory of B + 1 frames (pair b = frames b, b+1;
+    # src/frame_handler_mono.cpp:176,272) shipped as one stack, PLSVO_ALIGN_FRAME_CHAIN — every frame crosses the link once ----
+    e2e_chain = None
+    if not args.no_chain:
+        # the local work sits in a try (a secondary leg must not take the headline line down); the collectives sit outside it so
+        # that a rank that failed still meets the others
+        chain_err, chain_local_ms, chain_info = None, -1.0, None
+        try:
+            cfull = synth.make_chain_batch(batch=B, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=7000 + 100000 * rank)
+            clean, _h2d_two, keep_chain = lean_copy(cfull, torch)
+            two = al.run(clean)  # the same chain given as two stacks (ref, cur): the comparison for the one-stack call
+            ft = torch.from_numpy(synth.chain_frames(cfull, levels=[cfull.min_level])[cfull.min_level]).pin_memory()
+            keep_chain.append(ft)
+            clean.frame_pyr = {cfull.min_level: ft.numpy()}
+            h2d_chain = (_h2d_two - sum(v.nbytes for v in clean.ref_pyr.values()) - sum(v.nbytes for v in clean.cur_pyr.values())
+                         + ft.numpy().nbytes)
+            for _ in range(2):
+                out_c = al.run(clean)
+            _a, _r = synth.pose_error(out_c.T_cur_w, two.T_cur_w)
+            chain_check = {"iteration_counts_equal_to_two_stack_call": int((out_c.iters == two.iters).all(axis=1).sum()), "pairs": int(B),
+                           "max_rot_rad_vs_two_stack_call": float(_a.max()), "max_rel_t_vs_two_stack_call": float(_r.max())}
+            torch.cuda.synchronize(dev)
+            c_s, c_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            c_s.record(stream)
+            for _ in range(args.steps):
+                out_c = al.run(clean)
+            c_e.record(stream)
+            torch.cuda.synchronize(dev)
+            chain_local_ms = max(c_s.elapsed_time(c_e), 1e3 * (time.perf_counter() - t0))
+            chain_info = (cfull, out_c, h2d_chain, chain_check)
+        except Exception as ex:
+            chain_err = f"{type(ex).__name__}: {ex}"
+        chain_ms = torch.tensor([chain_local_ms, -1.0 if chain_err else 1.0], dtype=torch.float64, device=dev)
+        if dist:
+            worst = chain_ms.clone()
+            dist.all_reduce(chain_ms, op=dist.ReduceOp.MAX)   # slowest rank
+            dist.all_reduce(worst, op=dist.ReduceOp.MIN)      # any rank that failed
+            chain_ms[1] = worst[1]
+        if chain_err or float(chain_ms[1].item()) < 0:
+            e2e_chain = {"error": chain_err or "the leg failed on another rank"}
+        else:
+            e2e_chain = {"value": n_gpus * B * args.steps / (float(chain_ms[0].item()) * 1e-3), "unit": "pairs/s",
+                         "h2d_bytes_per_step": int(chain_info[2]) * n_gpus, "d2h_bytes_per_step": int(d2h) * n_gpus, "check": chain_info[3],
+                         "workload": "same call and feature mix on a frame chain: %d pairs replaying one trajectory of %d frames per GPU, "
+                                     "frames shipped once as one stack (PLSVO_ALIGN_FRAME_CHAIN)" % (B, B + 1),
+                         "_cpu_inputs": chain_info[:2] if rank == 0 else None}
     clk.__exit__(None, None, None)
     data = data_full
     numa.restore(saved_affinity)  # the CPU arms below get every host thread back
@@ -740,6 +788,13 @@ def main():
     poseopt = None
     try:
         pdata = synth.make_poseopt_batch(batch=4096, n_pts=args.n_pts, n_segs=args.n_segs, seed=5000 + rank)
+        # page-locked host arrays, as for the alignment legs (the end-to-end call copies straight from them)
+        ppin, p_h2d = [], 0
+        for name in ("T_f_w", "pt_f", "pt_pos", "pt_level", "seg_line", "seg_spos", "seg_epos", "seg_level"):
+            tt = torch.from_numpy(np.ascontiguousarray(getattr(pdata, name))).pin_memory()
+            setattr(pdata, name, tt.numpy())
+            ppin.append(tt)
+            p_h2d += tt.numpy().nbytes
         pbatch, pkeep = abi.make_poseopt_batch(pdata)
         pout = abi.PoseOptOut(pdata.batch, pdata.n_pts, pdata.n_segs)
         pparams = abi.poseopt_params(2.0, 10, -1)
@@ -762,10 +817,14 @@ def main():
         pms = float(np.median(pts))
         pbytes = poseopt_alg_bytes(pout, pdata.n_pts, pdata.n_segs)
         # end to end through the host-buffer call, and the CPU arm with parity on the same frames (rank 0)
+        ctx.check(ctx.lib.plsvo_poseopt_batch_run(ctx.handle, C.byref(pbatch), C.byref(pparams), C.byref(pout.struct)), "poseopt run")
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(5):
             ctx.check(ctx.lib.plsvo_poseopt_batch_run(ctx.handle, C.byref(pbatch), C.byref(pparams), C.byref(pout.struct)), "poseopt run")
-        pe2e = 3 * pdata.batch / (time.perf_counter() - t0)
+        pe2e = 5 * pdata.batch / (time.perf_counter() - t0)
+        p_d2h = sum(getattr(pout, n).nbytes for n in ("T_f_w", "cov", "estimated_scale", "error_init", "error_final", "num_obs_pt",
+                                                      "num_obs_ls", "pt_outlier", "seg_outlier", "iters", "status") if hasattr(pout, n))
         pcpu = None
         if rank == 0 and not args.no_cpu_baseline:
             import oracle_lib
@@ -788,7 +847,8 @@ def main():
         poseopt = {"metric": "pose-optimiser frames/s (300 pts + 80 lines, <=10 GN iters, B=4096)",
                    "value": pdata.batch / (pms * 1e-3), "unit": "frames/s", "ms_per_batch": pms,
                    "note": "includes the per-launch clearing of 6 small output arrays (memsets)",
-                   "e2e": {"value": pe2e, "unit": "frames/s", "note": "plsvo_poseopt_batch_run from pageable host arrays, results to host"},
+                   "e2e": {"value": pe2e, "unit": "frames/s", "h2d_bytes_per_step": int(p_h2d), "d2h_bytes_per_step": int(p_d2h),
+                           "note": "plsvo_poseopt_batch_run from page-locked host arrays, results to host (wall clock over 5 calls)"},
                    "cpu_baseline": pcpu,
                    "roofline": {"bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "unit": "GB/s",
                                 "frac": pbytes / (pms * 1e-3) / 1e9 / measured_hbm_peak()[0]}}
@@ -841,12 +901,24 @@ def main():
                    "sample": f"{min(n, B)} pairs x {reps} passes ({secs:.1f} s), all host threads; {what}",
                    "parity_vs_gpu": {"max_rot_rad": float(ang.max()), "max_rel_t": float(rel.max()),
                                      "pairs_within_tol": int(((ang <= 1e-5) & (rel <= 1e-4)).sum()), "pairs": int(B)}}
+        if e2e_chain and "_cpu_inputs" in e2e_chain:
+            cin = e2e_chain.pop("_cpu_inputs")
+            if cin is not None and not args.no_cpu_baseline:
+                import oracle_lib
+
+                n_c = min(128, B)  # bounded sample: the first pairs of the chain against the CPU arm
+                ref_c = cpu_impl(abi, oracle_lib)[0](abi, subset(cin[0], n_c), n_threads=cpu["cores"] if cpu else 8)
+                ang_c, rel_c = synth.pose_error(cin[1].T_cur_w[:n_c], ref_c.T_cur_w)
+                e2e_chain["parity_vs_cpu"] = {"pairs": int(n_c), "pairs_within_tol": int(((ang_c <= 1e-5) & (rel_c <= 1e-4)).sum()),
+                                              "iteration_counts_equal": int((cin[1].iters[:n_c] == ref_c.iters).all(axis=1).sum()),
+                                              "max_rot_rad": float(ang_c.max()), "max_rel_t": float(rel_c.max())}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE, "data": "synthetic", "config": workload_config(args, n_gpus),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
                     "d2h_bytes_per_step": int(d2h) * n_gpus, "check": e2e_check},
+            "e2e_chain": e2e_chain,
             "e2e_scatter": e2e_scatter,
             "host_placement": placement,
             "gpu_launches": int(launches),

@@ -92,12 +92,22 @@ typedef struct plsvo_align_params {
  * formed on the device exactly as the reference's feature constructors form them, `cam_->cam2world(px)`
  * (src/feature.cpp:42,98-99; vk::PinholeCamera::cam2world = ((u-cx)/fx, (v-cy)/fy, 1).normalized()).  24 bytes less
  * per point, 48 per segment.
+ *
+ * Frame chains (flags & PLSVO_ALIGN_FRAME_CHAIN).  FrameHandlerMono aligns consecutive frames: the current frame of
+ * one call is the reference frame of the next (src/frame_handler_mono.cpp:272 `run(last_frame_, new_frame_)`, :176
+ * `last_frame_ = new_frame_`).  A batch that replays such a sequence — pair b = (frame b, frame b+1) — gives
+ * ref_img[l] as a stack of B+1 frames (frame k at ref_img[l] + k*img_stride[l]) and leaves cur_img[l] NULL: every
+ * frame crosses the host link and sits in device memory once instead of twice (B+1 frames instead of 2B).  Everything
+ * else (poses, the features of each pair's reference frame, outputs) is per pair as before; results are bit-identical
+ * to the same batch given as two stacks.
  */
+#define PLSVO_ALIGN_FRAME_CHAIN 1 /* plsvo_align_batch.flags: ref_img holds B+1 chained frames, cur_img is ignored */
+
 typedef struct plsvo_align_batch {
   int32_t batch;   /* B */
   int32_t n_pts;   /* array stride: points per pair   (Frame::pt_fts_,  frame.h:65) */
   int32_t n_segs;  /* array stride: segments per pair (Frame::seg_fts_, frame.h:66) */
-  int32_t reserved;
+  int32_t flags;   /* 0 or PLSVO_ALIGN_FRAME_CHAIN (was `reserved`: zero keeps the two-stack layout) */
   plsvo_camera cam;
 
   const uint8_t* ref_img[PLSVO_MAX_LEVELS];

@@ -49,12 +49,15 @@ class AlignParams(C.Structure):
     ]
 
 
+ALIGN_FRAME_CHAIN = 1  # PLSVO_ALIGN_FRAME_CHAIN (include/plsvo_b200.h)
+
+
 class AlignBatch(C.Structure):
     _fields_ = [
         ("batch", C.c_int32),
         ("n_pts", C.c_int32),
         ("n_segs", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),  # 0 or ALIGN_FRAME_CHAIN
         ("cam", Camera),
         ("ref_img", _u8p * MAX_LEVELS),
         ("cur_img", _u8p * MAX_LEVELS),
@@ -254,8 +257,17 @@ def make_align_batch(d):
     b.batch, b.n_pts, b.n_segs = d.batch, d.n_pts, d.n_segs
     cam = d.cam
     b.cam = Camera(cam.width, cam.height, 0, 0, cam.fx, cam.fy, cam.cx, cam.cy)
+    frame_pyr = getattr(d, "frame_pyr", None)
+    if frame_pyr is not None:
+        # frame chain (PLSVO_ALIGN_FRAME_CHAIN): one stack of B+1 frames per level, pair b = (frame b, frame b+1)
+        b.flags = ALIGN_FRAME_CHAIN
+        for l, f in frame_pyr.items():
+            assert f.dtype == np.uint8 and f.ndim == 3 and f.shape[0] == d.batch + 1 and f.strides[2] == 1
+            b.ref_img[l] = f.ctypes.data_as(_u8p)
+            b.img_pitch[l] = f.strides[1]
+            b.img_stride[l] = f.strides[0]
     for l in range(MAX_LEVELS):
-        if l in d.ref_pyr:
+        if frame_pyr is None and l in d.ref_pyr:
             r, c = d.ref_pyr[l], d.cur_pyr[l]
             assert r.dtype == np.uint8 and r.ndim == 3 and r.shape == c.shape
             assert r.strides[2] == 1 and c.strides == r.strides

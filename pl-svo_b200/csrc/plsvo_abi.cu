@@ -57,6 +57,7 @@ struct plsvo_ctx_impl {
   DevBuf d_ref_der, d_cur_der;       // pyramid levels derived on the device (vk::halfSample) instead of uploaded
   int der_src = -1, der_top = -1;    // derived levels are (der_src, der_top], built from uploaded level der_src
   bool lvl_uploaded[PLSVO_MAX_LEVELS] = {false};
+  bool chain = false;              // PLSVO_ALIGN_FRAME_CHAIN: one stack of B+1 frames, cur(b) = frame b+1 = ref(b+1)
   DevBuf d_pt_depth, d_seg_sdepth, d_seg_edepth;
   DevBuf d_feat;                     // small batches: every feature array in one block (one host->device copy)
   char* h_po_out = nullptr;          // pinned staging of the pose-optimiser outputs (one D2H per download)
@@ -349,7 +350,12 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
                           (!h->seg_epos && !h->seg_edepth) || !h->seg_length))
       return fail(c, PLSVO_ERR_INVALID, "segment arrays missing");
     if (h->cam.width <= 0 || h->cam.height <= 0) return fail(c, PLSVO_ERR_INVALID, "camera size");
+    if (h->flags & ~PLSVO_ALIGN_FRAME_CHAIN) return fail(c, PLSVO_ERR_INVALID, "unknown bits in plsvo_align_batch.flags");
     CK(cudaSetDevice(c->device));
+    // frame chain: ref_img[l] is one stack of B+1 frames and the current image of pair b is frame b+1 — the kernel's
+    // `cur_img[l] + b*stride` then simply starts one frame further into the same stack
+    c->chain = (h->flags & PLSVO_ALIGN_FRAME_CHAIN) != 0;
+    const size_t n_frames = B + (c->chain ? 1 : 0);
     a.B = h->batch, a.n_pts = h->n_pts, a.n_segs = h->n_segs;
     a.width = h->cam.width, a.height = h->cam.height;
     a.fx = h->cam.fx, a.fy = h->cam.fy, a.cx = h->cam.cx, a.cy = h->cam.cy;
@@ -361,7 +367,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       a.pitch[l] = 0, a.stride[l] = 0;
       c->level_off[l] = 0;
       c->lvl_uploaded[l] = false;
-      if (!h->ref_img[l] || !h->cur_img[l]) continue;
+      if (!h->ref_img[l] || (!c->chain && !h->cur_img[l])) continue;
       c->lvl_uploaded[l] = true;
       const int cols = h->cam.width >> l, rows = h->cam.height >> l;
       if (cols <= 0 || rows <= 0) return fail(c, PLSVO_ERR_INVALID, "pyramid level smaller than one pixel");
@@ -377,15 +383,15 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       a.stride[l] = (size_t)rows * pitch;
       total = (total + 255) / 256 * 256;
       c->level_off[l] = total;
-      total += a.stride[l] * B;
+      total += a.stride[l] * n_frames;
     }
     CK(ensure(c->d_ref_img, total + 256));
-    CK(ensure(c->d_cur_img, total + 256));
+    if (!c->chain) CK(ensure(c->d_cur_img, total + 256));
     c->img_total = total;
     c->der_src = c->der_top = -1;
     size_t stage = 0;
     for (int l = 0; l < PLSVO_MAX_LEVELS; ++l)
-      if (a.pitch[l] && h->img_pitch[l] != a.pitch[l]) stage = std::max(stage, 2 * h->img_stride[l] * B);
+      if (a.pitch[l] && h->img_pitch[l] != a.pitch[l]) stage = std::max(stage, 2 * h->img_stride[l] * n_frames);
     if (stage) CK(ensure(c->d_stage, stage));
   }
   // ---- small batches (the reference's own call is B = 1, frame_handler_mono.cpp:272): every input is packed into one
@@ -445,9 +451,13 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       char* hf = c->h_in + 2 * c->img_total;
       for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
         if (!c->lvl_uploaded[l]) continue;
-        memcpy(hr + c->level_off[l], h->ref_img[l], a.stride[l] * B);
-        memcpy(hc + c->level_off[l], h->cur_img[l], a.stride[l] * B);
+        memcpy(hr + c->level_off[l], h->ref_img[l], a.stride[l] * (B + (c->chain ? 1 : 0)));
         a.ref_img[l] = static_cast<uint8_t*>(c->d_ref_img.p) + c->level_off[l];
+        if (c->chain) {
+          a.cur_img[l] = a.ref_img[l] + a.stride[l];
+          continue;
+        }
+        memcpy(hc + c->level_off[l], h->cur_img[l], a.stride[l] * B);
         a.cur_img[l] = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
       }
       size_t off = 0;
@@ -462,7 +472,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
       }
       if (c->img_total) {
         CK(cudaMemcpyAsync(c->d_ref_img.p, hr, c->img_total, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(c->d_cur_img.p, hc, c->img_total, cudaMemcpyHostToDevice, s));
+        if (!c->chain) CK(cudaMemcpyAsync(c->d_cur_img.p, hc, c->img_total, cudaMemcpyHostToDevice, s));
       }
       if (feat_total) CK(cudaMemcpyAsync(c->d_feat.p, hf, feat_total, cudaMemcpyHostToDevice, s));
       CK(cudaEventRecord(c->h_in_ev, s));
@@ -475,15 +485,35 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     if (!c->lvl_uploaded[l]) continue;
     const int cols = h->cam.width >> l, rows = h->cam.height >> l;
     uint8_t* dr = static_cast<uint8_t*>(c->d_ref_img.p) + c->level_off[l];
-    uint8_t* dc = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
     a.ref_img[l] = dr;
+    const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
+    if (c->chain) {
+      // pairs [b0,b1) read frames [b0, b1]: frame b0 came with the previous range (or is frame 0 of the first one)
+      a.cur_img[l] = dr + a.stride[l];
+      if (!(what & 1) || nb == 0) continue;
+      const size_t f0 = b0 ? b0 + 1 : 0, nf = b1 + 1 - f0;
+      const uint8_t* hf = h->ref_img[l] + f0 * h->img_stride[l];
+      uint8_t* df = dr + f0 * a.stride[l];
+      if (uniform && h->img_pitch[l] == a.pitch[l]) {
+        CK(cudaMemcpyAsync(df, hf, a.stride[l] * nf, cudaMemcpyHostToDevice, pick_copy_stream(c, s)));
+      } else if (uniform) {
+        uint8_t* st = static_cast<uint8_t*>(c->d_stage.p) + h->img_stride[l] * f0;
+        CK(cudaMemcpyAsync(st, hf, h->img_stride[l] * nf, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpy2DAsync(df, a.pitch[l], st, h->img_pitch[l], cols, (size_t)rows * nf, cudaMemcpyDeviceToDevice, s));
+      } else {
+        for (size_t k = 0; k < nf; ++k)
+          CK(cudaMemcpy2DAsync(df + k * a.stride[l], a.pitch[l], hf + k * h->img_stride[l], h->img_pitch[l], cols, rows,
+                               cudaMemcpyHostToDevice, s));
+      }
+      continue;
+    }
+    uint8_t* dc = static_cast<uint8_t*>(c->d_cur_img.p) + c->level_off[l];
     a.cur_img[l] = dc;
     const uint8_t* hr = h->ref_img[l] + b0 * h->img_stride[l];
     const uint8_t* hc = h->cur_img[l] + b0 * h->img_stride[l];
     dr += b0 * a.stride[l];
     dc += b0 * a.stride[l];
     if (!(what & 1) || nb == 0) continue;
-    const bool uniform = h->img_stride[l] == (size_t)rows * h->img_pitch[l];
     if (uniform && h->img_pitch[l] == a.pitch[l]) {
       // host stack already has the device layout: one linear copy per frame set
       CK(cudaMemcpyAsync(dr, hr, a.stride[l] * nb, cudaMemcpyHostToDevice, pick_copy_stream(c, s)));
@@ -690,13 +720,13 @@ int align_derive_levels(plsvo_ctx_impl* c, int min_level, int max_level, size_t 
       a.pitch[l] = (uint32_t)((cols + 15) / 16 * 16);
       a.stride[l] = (size_t)rows * a.pitch[l];
       off[l] = total;
-      total += (a.stride[l] * B + 255) / 256 * 256;
+      total += (a.stride[l] * (B + (c->chain ? 1 : 0)) + 255) / 256 * 256;
     }
     CK(ensure(c->d_ref_der, total + 256));
-    CK(ensure(c->d_cur_der, total + 256));
+    if (!c->chain) CK(ensure(c->d_cur_der, total + 256));
     for (int l = src + 1; l <= max_level; ++l) {
       a.ref_img[l] = static_cast<uint8_t*>(c->d_ref_der.p) + off[l];
-      a.cur_img[l] = static_cast<uint8_t*>(c->d_cur_der.p) + off[l];
+      a.cur_img[l] = c->chain ? a.ref_img[l] + a.stride[l] : static_cast<uint8_t*>(c->d_cur_der.p) + off[l];
     }
     c->der_src = src, c->der_top = max_level;
   }
@@ -705,13 +735,15 @@ int align_derive_levels(plsvo_ctx_impl* c, int min_level, int max_level, size_t 
     return PLSVO_OK;
   }
   if (b1 <= b0) return PLSVO_OK;
-  for (int which = 0; which < 2; ++which) {
+  // frame chain: one stack; pairs [b0,b1) need frames [b0, b1], of which frame b0 was derived with the previous range
+  const size_t f0 = c->chain ? (b0 ? b0 + 1 : 0) : b0, f1 = c->chain ? b1 + 1 : b1;
+  for (int which = 0; which < (c->chain ? 1 : 2); ++which) {
     PyramidArgs pa;
     memset(&pa, 0, sizeof pa);
-    pa.B = (int)(b1 - b0), pa.width = a.width >> src, pa.height = a.height >> src, pa.n_levels = max_level - src + 1;
+    pa.B = (int)(f1 - f0), pa.width = a.width >> src, pa.height = a.height >> src, pa.n_levels = max_level - src + 1;
     for (int l = src; l <= max_level; ++l) {
       const uint8_t* base = which ? a.cur_img[l] : a.ref_img[l];
-      pa.level[l - src] = const_cast<uint8_t*>(base) + b0 * a.stride[l];
+      pa.level[l - src] = const_cast<uint8_t*>(base) + f0 * a.stride[l];
       pa.pitch[l - src] = a.pitch[l];
       pa.stride[l - src] = a.stride[l];
     }
@@ -953,6 +985,9 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
       const bool direct = b->ref_img[l] && b->img_stride[l] == (size_t)rows * b->img_pitch[l] && b->img_pitch[l] % 4 == 0 &&
                           b->img_stride[l] % 16 == 0;
       if (!direct) gated = false;  // padded layouts need a device-side repack kernel: not under the gate
+      // frame chain: the last frame of an arrived chunk and the first frame of the chunk in flight are neighbours in one
+      // stack — they must not share a 128-byte line
+      if ((b->flags & PLSVO_ALIGN_FRAME_CHAIN) && b->img_stride[l] % 128 != 0) gated = false;
     }
   }
   if (gated) {

@@ -239,6 +239,9 @@ class AlignData:
     seg_valid: np.ndarray | None = None
     pt_count: np.ndarray | None = None
     seg_count: np.ndarray | None = None
+    # frame chain (PLSVO_ALIGN_FRAME_CHAIN, include/plsvo_b200.h): level -> u8 [B+1,h,w]; pair b = (frame b, frame b+1).
+    # When set, the ABI call ships this one stack instead of ref_pyr + cur_pyr.
+    frame_pyr: dict | None = None
 
     @property
     def batch(self):
@@ -505,6 +508,41 @@ def make_sequence(cam: Camera = VGA, n_seq: int = 4, n_frames: int = 20, n_pts: 
                                 outlier_frac=outlier_frac, T_gt=poses[:, k])
         steps.append((al, po))
     return poses, steps
+
+
+def chain_frames(data: AlignData, levels=None) -> dict:
+    """One stack of B+1 frames per level for a batch whose pairs are consecutive frames of one sequence
+    (cur of pair b is the same image as ref of pair b+1; src/frame_handler_mono.cpp:176,272): level -> u8 [B+1,h,w].
+    Raises if the batch is not such a chain."""
+    out = {}
+    for l in (levels if levels is not None else sorted(data.ref_pyr)):
+        r, c = data.ref_pyr[l], data.cur_pyr[l]
+        if not np.array_equal(c[:-1], r[1:]):
+            raise ValueError("not a frame chain: cur image of pair b differs from the ref image of pair b+1")
+        out[l] = np.ascontiguousarray(np.concatenate([r, c[-1:]], 0))
+    return out
+
+
+def make_chain_batch(cam: Camera = VGA, batch: int = 8, n_pts: int = 300, n_segs: int = 80, seed: int = 3000, step_t: float = 0.03,
+                     step_r: float = 0.01, device: str | torch.device = "cpu", **kw) -> AlignData:
+    """B pairs that replay ONE camera trajectory of B+1 frames: pair b aligns frame b+1 to frame b, starting (like
+    FrameHandlerMono::processFrame, src/frame_handler_mono.cpp:266) from the previous frame's pose.  The two-stack arrays
+    (ref_pyr / cur_pyr) are filled as usual, so the same object feeds the oracle; `chain_frames` gives the one-stack form."""
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    f64 = dict(dtype=torch.float64)
+    R, t = se3_exp_Rt(torch.tensor(np.concatenate([rng.uniform(-0.2, 0.2, 3), rng.uniform(-0.03, 0.03, 3)])[None], **f64))
+    poses = [pose7_from_Rt(R, t)]
+    # a bounded walk: steps of up to (step_t, step_r) whose drift is pulled back towards the start
+    drift = np.zeros(6)
+    for _ in range(batch):
+        xi = np.concatenate([rng.uniform(-step_t, step_t, 3), rng.uniform(-step_r, step_r, 3)]) - 0.1 * drift
+        drift += xi
+        Rm, tm = se3_exp_Rt(torch.tensor(xi[None], **f64))
+        R, t = Rm @ R, (Rm @ t[..., None])[..., 0] + tm
+        poses.append(pose7_from_Rt(R, t))
+    poses = torch.cat(poses, 0).numpy()
+    return make_align_batch(cam=cam, batch=batch, n_pts=n_pts, n_segs=n_segs, seed=seed, device=device,
+                            T_ref_w_gt=poses[:-1], T_cur_w_gt=poses[1:], **kw)
 
 
 def run_sequence(poses, steps, track_fn):
