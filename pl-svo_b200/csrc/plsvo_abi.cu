@@ -161,6 +161,19 @@ int host_seg_samples(const double* spx, const double* epx, double length, int le
   return (int)(1 + (n0 - 1) / (unsigned long long)(1 << level));
 }
 
+// The host-in/host-out entry points (plsvo_*_batch_run) promise that the caller's arrays are not read once they have
+// returned — also when they return an error after copies have been queued (a level that can neither be found nor derived, a
+// count out of range found by the sizing pass, ...).  Every such entry point passes its result through here: a non-OK
+// result first drains every stream of the context (tests/test_host_pipeline_cpu.py counts pending host reads).
+int settled(plsvo_ctx_impl* c, int rc) {
+  if (rc == PLSVO_OK || !c) return rc;
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int k = 0; k < 4; ++k)
+    if (c->rr_stream[k]) cudaStreamSynchronize(c->rr_stream[k]);
+  cudaStreamSynchronize(c->stream);
+  return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -201,6 +214,10 @@ void plsvo_ctx_destroy(plsvo_ctx* ctx) {
   if (!ctx) return;
   plsvo_ctx_impl* c = CTX(ctx);
   cudaSetDevice(c->device);
+  // nothing may still be writing into the buffers freed below: the copy streams first, then the main stream
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int k = 0; k < 4; ++k)
+    if (c->rr_stream[k]) cudaStreamSynchronize(c->rr_stream[k]);
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_ref_img,   &c->d_cur_img,  &c->d_T_ref,     &c->d_T_cur,      &c->d_pt_count,  &c->d_pt_px,
                     &c->d_pt_f,      &c->d_pt_pos,   &c->d_pt_valid,  &c->d_seg_count,  &c->d_seg_spx,   &c->d_seg_epx,
@@ -962,9 +979,8 @@ int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* o) {
   return PLSVO_OK;
 }
 
-int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsvo_align_params* p,
-                          const plsvo_align_result* o) {
-  if (!ctx || !b || !p || !o) return PLSVO_ERR_INVALID;
+static int align_batch_run_body(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsvo_align_params* p,
+                                const plsvo_align_result* o) {
   plsvo_ctx_impl* c = CTX(ctx);
   // Host-buffer pipeline.  Default for large batches: ONE persistent kernel over the whole batch is
   // launched immediately while a second stream copies the batch to the device in chunks of 256 pairs
@@ -1152,6 +1168,12 @@ int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsv
   return plsvo_align_download(ctx, o);
 }
 
+int plsvo_align_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* b, const plsvo_align_params* p,
+                          const plsvo_align_result* o) {
+  if (!ctx || !b || !p || !o) return PLSVO_ERR_INVALID;
+  return settled(CTX(ctx), align_batch_run_body(ctx, b, p, o));
+}
+
 // ------------------------------------------------------------------------------------------------
 // pose optimiser
 // ------------------------------------------------------------------------------------------------
@@ -1299,7 +1321,6 @@ int plsvo_poseopt_launch(plsvo_ctx* ctx, const plsvo_poseopt_params* p) {
   const size_t smem = poseopt_smem_bytes(a.n_pts, a.n_segs);
   if (smem > (size_t)c->smem_optin) return fail(c, PLSVO_ERR_INVALID, "feature counts exceed shared memory");
   // outputs of frames that return early keep their previous contents: clear the ones we always report
-  const size_t B = (size_t)a.B;
   CK(cudaMemsetAsync(static_cast<char*>(c->p_out_T.p) + c->po_zero_off, 0, c->po_zero_bytes, c->stream));
   CK(poseopt_kernel_launch(a, smem, c->stream));
   c->launches += 1;
@@ -1360,29 +1381,24 @@ int plsvo_track_batch_run(plsvo_ctx* ctx, const plsvo_align_batch* ab, const pls
                           const plsvo_poseopt_result* po) {
   if (!ctx || !ab || !ap || !pb || !pp || !po) return PLSVO_ERR_INVALID;
   int rc = plsvo_track_upload(ctx, ab, pb);
-  if (rc != PLSVO_OK) return rc;
-  rc = plsvo_track_launch(ctx, ap, pp);
-  if (rc != PLSVO_OK) return rc;
-  if (ao) {
-    rc = plsvo_align_download(ctx, ao);
-    if (rc != PLSVO_OK) return rc;
-  }
-  return plsvo_poseopt_download(ctx, po);
+  if (rc == PLSVO_OK) rc = plsvo_track_launch(ctx, ap, pp);
+  if (rc == PLSVO_OK && ao) rc = plsvo_align_download(ctx, ao);
+  if (rc == PLSVO_OK) rc = plsvo_poseopt_download(ctx, po);
+  return settled(CTX(ctx), rc);
 }
 
 int plsvo_poseopt_batch_run(plsvo_ctx* ctx, const plsvo_poseopt_batch* b, const plsvo_poseopt_params* p,
                             const plsvo_poseopt_result* o) {
+  if (!ctx || !b || !p || !o) return PLSVO_ERR_INVALID;
   int rc = plsvo_poseopt_upload(ctx, b);
-  if (rc != PLSVO_OK) return rc;
-  rc = plsvo_poseopt_launch(ctx, p);
-  if (rc != PLSVO_OK) return rc;
-  return plsvo_poseopt_download(ctx, o);
+  if (rc == PLSVO_OK) rc = plsvo_poseopt_launch(ctx, p);
+  if (rc == PLSVO_OK) rc = plsvo_poseopt_download(ctx, o);
+  return settled(CTX(ctx), rc);
 }
 
 }  // extern "C"
 
-extern "C" int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out) {
-  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+static int pyramid_batch_run_body(plsvo_ctx* ctx, const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out) {
   plsvo_ctx_impl* c = CTX(ctx);
   if (in->batch <= 0 || in->width <= 0 || in->height <= 0 || in->n_levels < 1 || in->n_levels > 7 || !in->img0 ||
       in->pitch0 < (size_t)in->width)
@@ -1505,13 +1521,13 @@ int feature_align_run(plsvo_ctx_impl* c, const plsvo_align2d_batch* in, const fl
 
 extern "C" int plsvo_align2d_batch_run(plsvo_ctx* ctx, const plsvo_align2d_batch* in, const plsvo_align2d_result* out) {
   if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
-  return feature_align_run(CTX(ctx), in, nullptr, out->px, out->converged, nullptr);
+  return settled(CTX(ctx), feature_align_run(CTX(ctx), in, nullptr, out->px, out->converged, nullptr));
 }
 
 extern "C" int plsvo_align1d_batch_run(plsvo_ctx* ctx, const plsvo_align1d_batch* in, const plsvo_align1d_result* out) {
   if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
   if (in->features.n_features > 0 && !in->dir) return fail(CTX(ctx), PLSVO_ERR_INVALID, "align1d directions missing");
-  return feature_align_run(CTX(ctx), &in->features, in->dir, out->px, out->converged, out->h_inv);
+  return settled(CTX(ctx), feature_align_run(CTX(ctx), &in->features, in->dir, out->px, out->converged, out->h_inv));
 }
 
 namespace {
@@ -1548,8 +1564,7 @@ int stage_pyramid(plsvo_ctx_impl* c, DevBuf& buf, const uint8_t* const* img, con
 }
 }  // namespace
 
-extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out) {
-  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+static int match_direct_batch_run_body(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out) {
   plsvo_ctx_impl* c = CTX(ctx);
   if (in->n_features < 0 || in->n_ref_images <= 0 || in->n_cur_images <= 0 || in->cam.width <= 0 || in->cam.height <= 0 ||
       in->n_iter < 0 || in->n_pyr_levels < 1 || in->n_pyr_levels > PLSVO_MAX_LEVELS)
@@ -1616,8 +1631,7 @@ extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_ba
   return PLSVO_OK;
 }
 
-extern "C" int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_batch* in, const plsvo_structopt_result* out) {
-  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+static int structopt_batch_run_body(plsvo_ctx* ctx, const plsvo_structopt_batch* in, const plsvo_structopt_result* out) {
   plsvo_ctx_impl* c = CTX(ctx);
   if (in->n_points < 0 || in->n_segs < 0 || in->n_frames <= 0 || in->n_iter_pts < 0 || in->n_iter_segs < 0 || !in->T_f_w)
     return fail(c, PLSVO_ERR_INVALID, "structopt batch description");
@@ -1773,10 +1787,26 @@ int seed_update_run(plsvo_ctx_impl* c, const plsvo_seed_batch* in, const plsvo_s
 
 extern "C" int plsvo_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_seed_batch* in, const plsvo_seed_result* out) {
   if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
-  return seed_update_run(CTX(ctx), in, out, nullptr, nullptr);
+  return settled(CTX(ctx), seed_update_run(CTX(ctx), in, out, nullptr, nullptr));
 }
 
 extern "C" int plsvo_line_seed_update_batch_run(plsvo_ctx* ctx, const plsvo_line_seed_batch* in, const plsvo_line_seed_result* out) {
   if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
-  return seed_update_run(CTX(ctx), &in->seeds, &out->seeds, in, out);
+  return settled(CTX(ctx), seed_update_run(CTX(ctx), &in->seeds, &out->seeds, in, out));
+}
+
+// exported forms of the three bodies above (see settled())
+extern "C" int plsvo_pyramid_batch_run(plsvo_ctx* ctx, const plsvo_pyramid_batch* in, const plsvo_pyramid_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  return settled(CTX(ctx), pyramid_batch_run_body(ctx, in, out));
+}
+
+extern "C" int plsvo_match_direct_batch_run(plsvo_ctx* ctx, const plsvo_match_batch* in, const plsvo_match_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  return settled(CTX(ctx), match_direct_batch_run_body(ctx, in, out));
+}
+
+extern "C" int plsvo_structopt_batch_run(plsvo_ctx* ctx, const plsvo_structopt_batch* in, const plsvo_structopt_result* out) {
+  if (!ctx || !in || !out) return PLSVO_ERR_INVALID;
+  return settled(CTX(ctx), structopt_batch_run_body(ctx, in, out));
 }

@@ -1,0 +1,394 @@
+"""Scenarios of the host-pipeline model (run by tests/test_host_pipeline_cpu.py in a subprocess with PLSVO_LIB pointing at
+libplsvo_hostmodel.so).  TEST INFRASTRUCTURE ONLY — see fake_cuda.h.
+
+Every scenario drives the product's unchanged Python mirror (plsvo_b200.SparseImgAlign, api.track, ...) through the
+product's unchanged host code; the model kernels return digests of the bytes they were given, which are compared with
+the same digests computed here, in NumPy, from the caller's arrays.  `python scenarios.py` prints one JSON object
+{scenario: "ok" | error text}."""
+from __future__ import annotations
+
+import contextlib
+import copy
+import ctypes as C
+import json
+import os
+import sys
+import traceback
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import plsvo_b200 as pkg  # noqa: E402
+from plsvo_b200 import abi, synth  # noqa: E402
+
+M64 = (1 << 64) - 1
+K = 0x9E3779B97F4A7C15
+LEVELS = (2, 3, 4)
+
+lib = abi.load_library()
+for _n, _r in (("fake_cuda_errors", C.c_char_p), ("fake_cuda_pending_host_reads", C.c_int), ("fake_cuda_pending_ops", C.c_int),
+               ("fake_cuda_h2d_bytes", C.c_ulonglong), ("fake_cuda_live_blocks", C.c_int)):
+    getattr(lib, _n).restype = _r
+
+
+# ---- the digest of fake_kernels.cpp, restated ----
+def dig_bytes(a) -> int:
+    b = np.frombuffer(np.ascontiguousarray(a).tobytes(), np.uint8).astype(np.uint64)
+    idx = (np.arange(b.size, dtype=np.uint64) + np.uint64(1)) * np.uint64(K)
+    with np.errstate(over="ignore"):
+        return int(((b + np.uint64(1)) * idx).sum(dtype=np.uint64))
+
+
+def mix(h: int, v: int) -> int:
+    return (h ^ ((v + K + ((h << 6) & M64) + (h >> 2)) & M64)) & M64
+
+
+def dig_array(h: int, arr, b: int, count: int) -> int:
+    if arr is None:
+        return mix(h, 0x5151)
+    return mix(h, dig_bytes(arr[b][:count]))
+
+
+def expected(data, shipped_levels=None):
+    """(n_tracked digests [B] as int64, per-level digests [B, 2*levels]) for the batch as the kernel must see it."""
+    B = data.batch
+    out = np.zeros(B, np.uint64)
+    lvl = np.zeros((B, 2 * len(LEVELS)), np.float64)
+    for b in range(B):
+        h = 0
+        for k, l in enumerate(LEVELS):
+            hr, hc = dig_bytes(data.ref_pyr[l][b]), dig_bytes(data.cur_pyr[l][b])
+            h = mix(mix(h, hr), hc)
+            lvl[b, 2 * k], lvl[b, 2 * k + 1] = float(hr >> 12), float(hc >> 12)
+        npt = int(data.pt_count[b]) if data.pt_count is not None else data.n_pts
+        nsg = int(data.seg_count[b]) if data.seg_count is not None else data.n_segs
+        h = mix(h, dig_bytes(data.T_ref_w[b]))
+        h = mix(h, dig_bytes(data.T_cur_w[b]))
+        h = mix(h, npt * 65536 + nsg)
+        for name in ("pt_px", "pt_f", "pt_pos", "pt_depth", "pt_valid"):
+            h = dig_array(h, getattr(data, name, None), b, npt)
+        if data.n_segs > 0:
+            for name in ("seg_spx", "seg_epx", "seg_sf", "seg_ef", "seg_spos", "seg_epos", "seg_sdepth", "seg_edepth", "seg_length", "seg_valid"):
+                h = dig_array(h, getattr(data, name, None), b, nsg)
+        else:
+            for _ in range(10):
+                h = mix(h, 0x5151)
+        out[b] = h
+    return out.view(np.int64), lvl
+
+
+# ---- inputs: random bytes are as good as rendered scenes for a kernel that only digests them ----
+def half(img):
+    a = img.astype(np.int32)
+    return ((a[:, 0::2, 0::2] + a[:, 0::2, 1::2] + a[:, 1::2, 0::2] + a[:, 1::2, 1::2]) >> 2).astype(np.uint8)
+
+
+def pyramid(rng, n, cam):
+    base = rng.integers(0, 256, (n, cam.height >> 2, cam.width >> 2), dtype=np.uint8)
+    return {2: base, 3: half(base), 4: half(half(base))}
+
+
+def make_batch(B, n_pts, n_segs, seed, cam=synth.VGA, chain=False, ragged=False, masks=False):
+    rng = np.random.default_rng(seed)
+    if chain:
+        frames = pyramid(rng, B + 1, cam)
+        ref = {l: np.ascontiguousarray(f[:-1]) for l, f in frames.items()}
+        cur = {l: np.ascontiguousarray(f[1:]) for l, f in frames.items()}
+    else:
+        ref, cur = pyramid(rng, B, cam), pyramid(rng, B, cam)
+
+    def r(*shape):
+        return rng.standard_normal(shape)
+
+    spx = rng.uniform(64, 400, (B, n_segs, 2))
+    epx = spx + rng.uniform(-120, 120, (B, n_segs, 2))
+    d = synth.AlignData(cam=cam, max_level=4, min_level=2, ref_pyr=ref, cur_pyr=cur, T_ref_w=r(B, 7), T_cur_w=r(B, 7), T_cur_w_gt=r(B, 7),
+                        pt_px=rng.uniform(64, 400, (B, n_pts, 2)), pt_f=r(B, n_pts, 3), pt_pos=r(B, n_pts, 3), seg_spx=spx, seg_epx=epx,
+                        seg_sf=r(B, n_segs, 3), seg_ef=r(B, n_segs, 3), seg_spos=r(B, n_segs, 3), seg_epos=r(B, n_segs, 3),
+                        seg_length=np.linalg.norm(epx - spx, axis=-1))
+    if ragged:
+        d.pt_count = rng.integers(0, n_pts + 1, B).astype(np.int32)
+        d.seg_count = rng.integers(0, n_segs + 1, B).astype(np.int32)
+        d.pt_count[0], d.seg_count[0] = 0, 0  # the reference's early-out pair
+    if masks:
+        d.pt_valid = rng.integers(0, 2, (B, n_pts)).astype(np.uint8)
+        d.seg_valid = rng.integers(0, 2, (B, n_segs)).astype(np.uint8)
+    return d
+
+
+def one_stack(data, levels=LEVELS):
+    """The frame-chain form of a chain batch (PLSVO_ALIGN_FRAME_CHAIN): one stack of B+1 frames per shipped level."""
+    o = copy.copy(data)
+    o.frame_pyr = synth.chain_frames(data, list(levels))
+    return o
+
+
+def shipped(data, levels):
+    """Same batch with only `levels` shipped (the rest is derived on the device)."""
+    o = copy.copy(data)
+    o.ref_pyr = {l: data.ref_pyr[l] for l in levels}
+    o.cur_pyr = {l: data.cur_pyr[l] for l in levels}
+    return o
+
+
+def lean_features(data, rng):
+    """Depth-only features without bearings (what bench.py's end-to-end leg ships)."""
+    o = copy.copy(data)
+    o.pt_depth = rng.uniform(1, 3, data.pt_px.shape[:2])
+    o.seg_sdepth = rng.uniform(1, 3, data.seg_spx.shape[:2])
+    o.seg_edepth = rng.uniform(1, 3, data.seg_spx.shape[:2])
+    o.pt_pos = o.seg_spos = o.seg_epos = None
+    o.pt_f = o.seg_sf = o.seg_ef = None
+    return o
+
+
+@contextlib.contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    for k, v in kw.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def clean():
+    err = lib.fake_cuda_errors()
+    assert not err, "model runtime recorded: " + err.decode()
+    assert lib.fake_cuda_pending_host_reads() == 0, "host->device copies still queued after the call returned"
+
+
+def check(out, data_as_kernel_sees_it, what=""):
+    clean()
+    want, lvl = expected(data_as_kernel_sees_it)
+    got_lvl = out.H[:, : lvl.shape[1]]
+    bad = np.nonzero(got_lvl != lvl)
+    assert bad[0].size == 0, f"{what}: image level digests differ at (pair, 2*level_index+ref/cur) {list(zip(*bad))[:6]}"
+    assert np.array_equal(out.n_tracked, want), f"{what}: pair digests differ at {np.nonzero(out.n_tracked != want)[0][:8]}"
+    assert np.array_equal(out.T_cur_w, data_as_kernel_sees_it.T_cur_w), what
+    npt = data_as_kernel_sees_it.pt_count if data_as_kernel_sees_it.pt_count is not None else data_as_kernel_sees_it.n_pts
+    assert np.array_equal(out.patch_iters, np.broadcast_to(npt, out.patch_iters.shape)), what
+
+
+def run(data, ctx=None, **envs):
+    with env(**envs):
+        al = pkg.SparseImgAlign(4, 2, 30, ctx=ctx or pkg.api.Context(0))
+        return al.run(data)
+
+
+# ---- scenarios ----
+def s_plain_upload_launch_download():
+    d = make_batch(5, 40, 9, 1)
+    check(run(d, PLSVO_E2E_CHUNKS=1, PLSVO_NO_SMALL_UPLOAD=1), d, "plain")
+    d = make_batch(6, 33, 0, 2)  # no segments at all
+    check(run(d, PLSVO_E2E_CHUNKS=1, PLSVO_NO_SMALL_UPLOAD=1), d, "points only")
+
+
+def s_small_batch_staging_block():
+    for B in (1, 3, 12):
+        d = make_batch(B, 40, 9, 10 + B, ragged=B > 1, masks=True)
+        check(run(d), d, f"small B={B}")
+    ctx = pkg.api.Context(0)  # staging block reused by consecutive calls of different sizes
+    for B in (2, 9, 1, 9):
+        d = make_batch(B, 25, 6, 20 + B)
+        check(run(d, ctx=ctx), d, f"small, reused context B={B}")
+
+
+def s_three_leg_api_and_relaunch():
+    d = make_batch(7, 30, 8, 30)
+    al = pkg.SparseImgAlign(4, 2, 30, ctx=pkg.api.Context(0))
+    al.upload(d)
+    al.launch()
+    check(al.download(), d, "three-leg")
+    al.launch()
+    check(al.download(), d, "relaunch")
+    d2 = shipped(d, [2])
+    al.upload(d2)
+    al.launch()
+    check(al.download(), d, "three-leg, derived levels")
+    al.launch()
+    check(al.download(), d, "relaunch, derived levels")
+
+
+def s_k_kernel_pipeline():
+    d = make_batch(26, 30, 8, 40, ragged=True)
+    for k in (2, 3, 8):
+        check(run(d, PLSVO_E2E_CHUNKS=k, PLSVO_NO_SMALL_UPLOAD=1), d, f"chunks={k}")
+        check(run(shipped(d, [2]), PLSVO_E2E_CHUNKS=k, PLSVO_NO_SMALL_UPLOAD=1), d, f"chunks={k}, derived levels")
+
+
+def s_arrival_gated_stream():
+    d = make_batch(300, 24, 6, 50, ragged=True)
+    full_bytes = None
+    for envs in ({}, {"PLSVO_GATE_CHUNK": 128}, {"PLSVO_GATE_CHUNK": 128, "PLSVO_COPY_STREAMS": 2}, {"PLSVO_GATE_INTERLEAVED": 1},
+                 {"PLSVO_GATE_CHUNK": 128, "PLSVO_GATE_INTERLEAVED": 1, "PLSVO_COPY_STREAMS": 3}):
+        h0 = lib.fake_cuda_h2d_bytes()
+        check(run(d, **envs), d, f"gated {envs}")
+        n_chunks = -(-d.batch // int(envs.get("PLSVO_GATE_CHUNK", 256)))
+        moved = lib.fake_cuda_h2d_bytes() - h0 - 4 * n_chunks  # one 4-byte arrival flag per chunk
+        full_bytes = full_bytes or moved
+        assert moved == full_bytes, f"gated {envs}: {moved} bytes moved, {full_bytes} in the default configuration"
+        check(run(shipped(d, [2]), **envs), d, f"gated, levels derived in the kernel {envs}")
+    ctx = pkg.api.Context(0)  # consecutive calls on one context: buffers, flags and events are reused
+    for seed in (51, 52):
+        d = make_batch(257 + seed, 16, 4, seed)
+        check(run(d, ctx=ctx, PLSVO_GATE_CHUNK=128), d, f"gated, reused context seed={seed}")
+        check(run(make_batch(3, 16, 4, seed + 100), ctx=ctx), make_batch(3, 16, 4, seed + 100), "small call in between")
+
+
+def s_padded_host_layouts():
+    d = make_batch(10, 30, 8, 60)
+    for layout in ("row_padded", "frame_padded", "both"):
+        p = copy.copy(d)
+        p.ref_pyr, p.cur_pyr = {}, {}
+        for l in LEVELS:
+            for src, dst in ((d.ref_pyr, p.ref_pyr), (d.cur_pyr, p.cur_pyr)):
+                n, h, w = src[l].shape
+                big = np.full((n, h + (layout != "row_padded"), w + 3 * (layout != "frame_padded")), 255, np.uint8)
+                big[:, :h, :w] = src[l]
+                dst[l] = big[:, :h, :w]
+        for k in (1, 2):
+            check(run(p, PLSVO_E2E_CHUNKS=k), d, f"{layout}, chunks={k}")
+            check(run(p, PLSVO_E2E_CHUNKS=k, PLSVO_NO_SMALL_UPLOAD=1), d, f"{layout}, chunks={k}, plain copies")
+
+
+def s_lean_features():
+    d = lean_features(make_batch(9, 30, 8, 70), np.random.default_rng(71))
+    check(run(d), d, "lean small")
+    check(run(shipped(d, [2]), PLSVO_NO_SMALL_UPLOAD=1), d, "lean, derived levels")
+    d = lean_features(make_batch(260, 20, 5, 72), np.random.default_rng(73))
+    check(run(shipped(d, [2])), d, "lean gated (the end-to-end leg of bench.py)")
+
+
+def s_chain_every_host_path():
+    # small block / plain copies / k-kernel pipeline, all levels shipped or derived
+    d = make_batch(26, 30, 8, 80, chain=True, ragged=True)
+    for envs in ({}, {"PLSVO_NO_SMALL_UPLOAD": 1}, {"PLSVO_NO_SMALL_UPLOAD": 1, "PLSVO_E2E_CHUNKS": 1}, {"PLSVO_E2E_CHUNKS": 3},
+                 {"PLSVO_E2E_CHUNKS": 3, "PLSVO_NO_SMALL_UPLOAD": 1}, {"PLSVO_E2E_CHUNKS": 8, "PLSVO_NO_SMALL_UPLOAD": 1}):
+        check(run(one_stack(d), **envs), d, f"chain {envs}")
+        check(run(one_stack(d, [2]), **envs), d, f"chain, derived levels {envs}")
+    d = make_batch(3, 30, 8, 81, chain=True)
+    check(run(one_stack(d)), d, "chain B=3 small block")
+    d1 = make_batch(1, 30, 8, 82, chain=True)
+    check(run(one_stack(d1)), d1, "chain of one pair")
+    # three-leg form and relaunch
+    al = pkg.SparseImgAlign(4, 2, 30, ctx=pkg.api.Context(0))
+    al.upload(one_stack(d, [2]))
+    al.launch()
+    check(al.download(), d, "chain three-leg")
+    al.launch()
+    check(al.download(), d, "chain relaunch")
+
+
+def s_chain_arrival_gated_stream():
+    d = make_batch(300, 24, 6, 90, chain=True)
+    two_stack_bytes = None
+    for envs in ({}, {"PLSVO_GATE_CHUNK": 128}, {"PLSVO_GATE_CHUNK": 128, "PLSVO_COPY_STREAMS": 2}, {"PLSVO_GATE_INTERLEAVED": 1}):
+        for levels in (LEVELS, (2,)):
+            h0 = lib.fake_cuda_h2d_bytes()
+            check(run(shipped(d, levels), **envs), d, f"two stacks {envs} {levels}")
+            h1 = lib.fake_cuda_h2d_bytes()
+            check(run(one_stack(d, levels), **envs), d, f"chain gated {envs} {levels}")
+            h2 = lib.fake_cuda_h2d_bytes()
+            frame_bytes = sum(d.ref_pyr[l][0].nbytes for l in levels)
+            # every frame crosses the link once: B+1 frames instead of 2B (the arrival flags, 4 bytes per chunk, are the slack:
+            # VGA level 4 is not a multiple of 128 bytes, so a chain that ships it takes the ungated path)
+            saved = (h1 - h0) - (h2 - h1) - (d.batch - 1) * frame_bytes
+            assert 0 <= saved <= 16, f"chain {envs} {levels}: bytes moved {h1 - h0} vs {h2 - h1}"
+    ctx = pkg.api.Context(0)  # chain and two-stack calls alternate on one context (the bench does exactly this)
+    for seed in (91, 92):
+        d = make_batch(256 + seed, 16, 4, seed, chain=True)
+        check(run(shipped(d, [2]), ctx=ctx), d, "two stacks, reused context")
+        check(run(one_stack(d, [2]), ctx=ctx), d, "chain, reused context")
+        check(run(one_stack(d), ctx=ctx), d, "chain with all levels shipped, reused context")
+
+
+def s_chain_padded_host_layouts():
+    d = make_batch(10, 30, 8, 100, chain=True)
+    for layout in ("row_padded", "frame_padded"):
+        o = one_stack(d)
+        for l, f in list(o.frame_pyr.items()):
+            n, h, w = f.shape
+            big = np.full((n, h + (layout == "frame_padded"), w + 3 * (layout == "row_padded")), 255, np.uint8)
+            big[:, :h, :w] = f
+            o.frame_pyr[l] = big[:, :h, :w]
+        for k in (1, 2, 3):
+            check(run(o, PLSVO_E2E_CHUNKS=k), d, f"chain {layout} chunks={k}")
+    # a chain whose frames are not 128-byte multiples must leave the gated path (QVGA level 4: 20 x 15 bytes)
+    q = make_batch(260, 12, 3, 101, cam=synth.QVGA, chain=True)
+    check(run(one_stack(q)), q, "chain with unaligned frames")
+
+
+def s_rejected_inputs_leave_nothing_in_flight():
+    d = make_batch(4, 10, 3, 110, chain=True)
+    batch, keep = abi.make_align_batch(one_stack(d))
+    ctx = pkg.api.Context(0)
+    batch.flags = 6
+    assert ctx.lib.plsvo_align_upload(ctx.handle, C.byref(batch)) == abi.ERR_INVALID
+    assert b"flags" in ctx.lib.plsvo_last_error(ctx.handle)
+    big = make_batch(300, 10, 3, 111, ragged=True)
+    big.pt_count[299] = 11  # beyond n_pts: found by the sizing pass, after the gated copies have been queued
+    b2, keep2 = abi.make_align_batch(big)
+    out = abi.AlignOut(300, 3)
+    rc = ctx.lib.plsvo_align_batch_run(ctx.handle, C.byref(b2), C.byref(abi.align_params(4, 2, 30)), C.byref(out.struct))
+    assert rc == abi.ERR_INVALID, rc
+    assert lib.fake_cuda_pending_host_reads() == 0, "the caller's arrays may still be read after an error return"
+    missing = shipped(make_batch(300, 10, 3, 112), [3, 4])  # finest level neither shipped nor derivable
+    b3, keep3 = abi.make_align_batch(missing)
+    rc = ctx.lib.plsvo_align_batch_run(ctx.handle, C.byref(b3), C.byref(abi.align_params(4, 2, 30)), C.byref(out.struct))
+    assert rc != abi.OK
+    assert lib.fake_cuda_pending_host_reads() == 0
+    ok = make_batch(300, 10, 3, 113)  # the context is still usable
+    check(run(ok, ctx=ctx), ok, "after rejected calls")
+
+
+def s_track_chained_call():
+    """plsvo_track_batch_run: the pose optimiser starts from the aligned poses on the device (here: T_cur_w passed through)."""
+    d = make_batch(20, 30, 8, 120)
+    B, n_pts, n_segs = 20, 30, 8
+    po = synth.make_poseopt_batch(batch=B, n_pts=n_pts, n_segs=n_segs, seed=122)
+    ao, pout = pkg.api.track(d, po, ctx=pkg.api.Context(0))
+    check(ao, d, "track: alignment leg")
+    for b in range(B):
+        npt = int(po.pt_count[b]) if getattr(po, "pt_count", None) is not None else n_pts
+        nsg = int(po.seg_count[b]) if getattr(po, "seg_count", None) is not None else n_segs
+        h = mix(0, dig_bytes(d.T_cur_w[b]))
+        h = mix(h, npt * 65536 + nsg)
+        for name, cnt in (("pt_f", npt), ("pt_pos", npt), ("pt_level", npt), ("pt_valid", npt), ("seg_line", nsg), ("seg_spos", nsg),
+                          ("seg_epos", nsg), ("seg_level", nsg), ("seg_valid", nsg)):
+            h = dig_array(h, getattr(po, name, None), b, cnt)
+        assert int(np.array([h], np.uint64).view(np.int64)[0]) == int(pout.num_obs_pt[b]), f"track: pose-opt frame {b}"
+    assert np.array_equal(pout.T_f_w, d.T_cur_w)
+    clean()
+
+
+SCENARIOS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("s_") and callable(v)}
+
+
+def main(names):
+    res = {}
+    for name in names or SCENARIOS:
+        try:
+            lib.fake_cuda_clear_errors()
+            SCENARIOS[name]()
+            res[name] = "ok"
+        except Exception:
+            res[name] = traceback.format_exc(limit=6)
+            lib.fake_cuda_drop_pending()  # whatever is still queued may point at arrays of the failed scenario
+    print("RESULT " + json.dumps(res), flush=True)
+    lib.fake_cuda_drop_pending()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
