@@ -455,6 +455,7 @@ int align_upload_impl(plsvo_ctx_impl* c, const plsvo_align_batch* h, size_t b0, 
     if (small) {
       const size_t need = 2 * c->img_total + feat_total + 256;
       if (c->h_in_cap < need) {
+        if (c->h_in_ev) CK(cudaEventSynchronize(c->h_in_ev));  // a copy out of the old block may still be queued
         if (c->h_in) cudaFreeHost(c->h_in);
         c->h_in = nullptr, c->h_in_cap = 0;
         CK(cudaHostAlloc((void**)&c->h_in, need, cudaHostAllocDefault));

@@ -221,8 +221,10 @@ cudaError_t cudaMalloc(void** p, size_t size) {
   *p = block_alloc(size);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
+// cudaFree and cudaFreeHost synchronise the device before they release the block (everything queued that can run, runs)
 cudaError_t cudaFree(void* p) {
   if (!p) return cudaSuccess;
+  pump_all();
   if (!block_free(p)) {
     fakecuda::error("cudaFree of a pointer that is not a live device block");
     return cudaErrorInvalidValue;
@@ -235,6 +237,7 @@ cudaError_t cudaHostAlloc(void** p, size_t size, unsigned int) {
 }
 cudaError_t cudaFreeHost(void* p) {
   if (!p) return cudaSuccess;
+  pump_all();
   if (!block_free(p)) {
     fakecuda::error("cudaFreeHost of a pointer that is not a live pinned block");
     return cudaErrorInvalidValue;
@@ -305,7 +308,7 @@ cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, enum cudaMemcp
   const bool h2d = kind == cudaMemcpyHostToDevice;
   const bool dst_tracked = fakecuda::in_bounds(dst, n), src_tracked = fakecuda::in_bounds(src, n);
   return fakecuda::enqueue(s, [=]() {
-    // a block may have been freed while the copy was queued (cudaFree does not wait for other streams' work here)
+    // cudaFree waits for everything that can run; a copy that was still blocked then has lost its block
     if ((dst_tracked && !fakecuda::in_bounds(dst, n)) || (src_tracked && !fakecuda::in_bounds(src, n))) {
       fakecuda::error("a queued copy ran after one of its device / pinned blocks had been freed");
       return true;

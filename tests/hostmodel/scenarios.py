@@ -205,6 +205,24 @@ def s_small_batch_staging_block():
         check(run(d, ctx=ctx), d, f"small, reused context B={B}")
 
 
+def s_staging_block_grows_while_a_copy_is_queued():
+    """upload() does not synchronise: a second, bigger upload must not free or refill the pinned staging block while the
+    first upload's copy out of it is still queued (alignment and pose-optimiser uploads share the block)."""
+    ctx = pkg.api.Context(0)
+    al = pkg.SparseImgAlign(4, 2, 30, ctx=ctx)
+    small, big = make_batch(1, 10, 2, 130), make_batch(14, 60, 12, 131)
+    al.upload(small)
+    al.upload(big)
+    al.launch()
+    check(al.download(), big, "second upload")
+    al.upload(small)
+    po = synth.make_poseopt_batch(batch=64, n_pts=60, n_segs=12, seed=132)
+    out = pkg.pose_optimizer.optimizeGaussNewton(2.0, 10, False, po, ctx=ctx)  # refills (and grows) the shared block
+    assert np.array_equal(out.T_f_w, po.T_f_w)
+    al.launch()
+    check(al.download(), small, "alignment upload before a pose-optimiser call")
+
+
 def s_three_leg_api_and_relaunch():
     d = make_batch(7, 30, 8, 30)
     al = pkg.SparseImgAlign(4, 2, 30, ctx=pkg.api.Context(0))
@@ -353,6 +371,54 @@ def s_rejected_inputs_leave_nothing_in_flight():
     check(run(ok, ctx=ctx), ok, "after rejected calls")
 
 
+def poseopt_expected(po, T=None):
+    B = po.batch
+    want = np.zeros(B, np.uint64)
+    for b in range(B):
+        npt = int(po.pt_count[b]) if getattr(po, "pt_count", None) is not None else po.n_pts
+        nsg = int(po.seg_count[b]) if getattr(po, "seg_count", None) is not None else po.n_segs
+        h = mix(0, dig_bytes((po.T_f_w if T is None else T)[b]))
+        h = mix(h, npt * 65536 + nsg)
+        for name, cnt in (("pt_f", npt), ("pt_pos", npt), ("pt_level", npt), ("pt_valid", npt), ("seg_line", nsg), ("seg_spos", nsg),
+                          ("seg_epos", nsg), ("seg_level", nsg), ("seg_valid", nsg)):
+            arr = getattr(po, name, None)
+            if arr is not None and arr.shape[1] == 0:
+                arr = None  # an empty array is not shipped
+            h = dig_array(h, arr, b, cnt)
+        want[b] = h
+    return want.view(np.int64)
+
+
+def s_pose_optimiser_host_paths():
+    """plsvo_poseopt_batch_run: one packed pinned block for small batches (the reference's own call is one frame), one copy
+    per array for large ones; outputs come back in one block."""
+    ctx = pkg.api.Context(0)
+    for B, n_pts, n_segs, envs in ((1, 300, 80, {}), (7, 40, 9, {}), (7, 40, 0, {}), (64, 300, 80, {"PLSVO_NO_SMALL_UPLOAD": 1}),
+                                   (2048, 300, 80, {}), (3, 20, 5, {})):
+        po = synth.make_poseopt_batch(batch=B, n_pts=n_pts, n_segs=n_segs, seed=140 + B)
+        with env(**envs):
+            out = pkg.pose_optimizer.optimizeGaussNewton(2.0, 10, False, po, ctx=ctx)
+        clean()
+        assert np.array_equal(out.num_obs_pt, poseopt_expected(po)), f"pose-opt digests B={B}"
+        assert np.array_equal(out.T_f_w, po.T_f_w)
+        assert not out.status.any()
+
+
+def s_pyramid_call():
+    """plsvo_pyramid_batch_run with contiguous and padded level-0 stacks; the model kernel is the real truncating 2x2 mean."""
+    rng = np.random.default_rng(150)
+    for (B, h, w) in ((3, 480, 640), (2, 90, 161), (1, 64, 64)):
+        img = rng.integers(0, 256, (B, h, w), dtype=np.uint8)
+        want = [img]
+        for _ in range(4):
+            a = want[-1][:, : want[-1].shape[1] // 2 * 2, : want[-1].shape[2] // 2 * 2]
+            want.append(half(a))
+        got = pkg.api.createImgPyramid(img, 5, ctx=pkg.api.Context(0))
+        clean()
+        for l in range(5):
+            assert np.array_equal(got[l], want[l]), f"pyramid level {l} of a {h}x{w} stack"
+
+
 def s_track_chained_call():
     """plsvo_track_batch_run: the pose optimiser starts from the aligned poses on the device (here: T_cur_w passed through)."""
     d = make_batch(20, 30, 8, 120)
@@ -360,15 +426,7 @@ def s_track_chained_call():
     po = synth.make_poseopt_batch(batch=B, n_pts=n_pts, n_segs=n_segs, seed=122)
     ao, pout = pkg.api.track(d, po, ctx=pkg.api.Context(0))
     check(ao, d, "track: alignment leg")
-    for b in range(B):
-        npt = int(po.pt_count[b]) if getattr(po, "pt_count", None) is not None else n_pts
-        nsg = int(po.seg_count[b]) if getattr(po, "seg_count", None) is not None else n_segs
-        h = mix(0, dig_bytes(d.T_cur_w[b]))
-        h = mix(h, npt * 65536 + nsg)
-        for name, cnt in (("pt_f", npt), ("pt_pos", npt), ("pt_level", npt), ("pt_valid", npt), ("seg_line", nsg), ("seg_spos", nsg),
-                          ("seg_epos", nsg), ("seg_level", nsg), ("seg_valid", nsg)):
-            h = dig_array(h, getattr(po, name, None), b, cnt)
-        assert int(np.array([h], np.uint64).view(np.int64)[0]) == int(pout.num_obs_pt[b]), f"track: pose-opt frame {b}"
+    assert np.array_equal(pout.num_obs_pt, poseopt_expected(po, T=d.T_cur_w)), "track: pose-opt digests"
     assert np.array_equal(pout.T_f_w, d.T_cur_w)
     clean()
 

@@ -27,9 +27,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HM = os.path.join(HERE, "hostmodel")
 ABI_SOURCE = os.path.join(os.path.dirname(HERE), "pl-svo_b200", "csrc", "plsvo_abi.cu")
 
-SCENARIOS = ["plain_upload_launch_download", "small_batch_staging_block", "three_leg_api_and_relaunch", "k_kernel_pipeline",
+SCENARIOS = ["plain_upload_launch_download", "small_batch_staging_block", "staging_block_grows_while_a_copy_is_queued", "three_leg_api_and_relaunch",
+             "k_kernel_pipeline",
              "arrival_gated_stream", "padded_host_layouts", "lean_features", "chain_every_host_path", "chain_arrival_gated_stream",
-             "chain_padded_host_layouts", "rejected_inputs_leave_nothing_in_flight", "track_chained_call"]
+             "chain_padded_host_layouts", "rejected_inputs_leave_nothing_in_flight", "pose_optimiser_host_paths", "pyramid_call",
+             "track_chained_call"]
 
 
 def _builder():
