@@ -220,7 +220,9 @@ int plsvo_host_free(void* ptr);
 
 /* Alignment.  upload: host arrays -> device layout (async).  launch: the whole coarse-to-fine
  * optimisation of every pair, device-resident in and out (async).  download: device -> host
- * outputs, then synchronise.  plsvo_align_batch_run = upload + launch + download. */
+ * outputs, then synchronise.  plsvo_align_batch_run = upload + launch + download.
+ * Every one-call form (plsvo_*_batch_run) has finished with the caller's arrays when it returns, whatever it returns:
+ * an error found after copies had been queued first drains every stream of the context. */
 int plsvo_align_upload(plsvo_ctx* ctx, const plsvo_align_batch* batch);
 int plsvo_align_launch(plsvo_ctx* ctx, const plsvo_align_params* params);
 int plsvo_align_download(plsvo_ctx* ctx, const plsvo_align_result* out);
