@@ -5,7 +5,7 @@
 // and folds those bytes into a digest per work item.  The digest comes back through the ordinary output arrays, so a test
 // sees — through the unchanged C ABI and Python mirror — exactly which bytes the host code presented to the kernel:
 //
-//   alignment : out_n_tracked[b] = digest of pair b (image levels min..max of both frames, poses, counts, every feature
+//   alignment : out_n_tracked[b] = digest of pair b, as (h >> 1) | 1 (image levels min..max of both frames, poses, counts, every feature
 //               array that was shipped); out_H[b][2*(l-min_level)+{0,1}] = digest of the ref / cur level l alone (top 52
 //               bits, exact in a double); out_T[b] = T_cur_w[b]; out_patch_iters/levels = the pair's feature counts.
 //               Levels that the real kernel derives itself (AlignArgs::derive_from) are derived here the same way; the
@@ -136,7 +136,7 @@ bool align_pair(const plsvo::AlignArgs& a, int b) {
   if (a.n_segs > 0) ok &= check(a.out_seg_killed + b * ns_, ns_, "out_seg_killed");
   if (!ok) return false;
   for (int i = 0; i < 7; ++i) a.out_T[(size_t)b * 7 + i] = a.T_cur_w ? a.T_cur_w[(size_t)b * 7 + i] : 0.0;
-  a.out_n_tracked[b] = (long long)h;
+  a.out_n_tracked[b] = (long long)((h >> 1) | 1u);  // positive, like a count of tracked patches
   for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) a.out_iters[(size_t)b * PLSVO_MAX_LEVELS + l] = (l >= a.min_level && l <= a.max_level) ? 1 : 0;
   a.out_status[b] = 0;
   a.out_patch_iters[b] = (uint32_t)np;
@@ -228,7 +228,7 @@ cudaError_t poseopt_kernel_launch(const PoseOptArgs& a0, size_t, cudaStream_t s)
           !fakecuda::check(a.out_status + b, 4, "poseopt out_status"))
         return true;
       for (int i = 0; i < 7; ++i) a.out_T[(size_t)b * 7 + i] = a.T_f_w[(size_t)b * 7 + i];
-      a.out_num_pt[b] = (long long)h;
+      a.out_num_pt[b] = (long long)((h >> 1) | 1u);
       a.out_status[b] = 0;
     }
     return true;

@@ -76,7 +76,7 @@ def expected(data, shipped_levels=None):
         else:
             for _ in range(10):
                 h = mix(h, 0x5151)
-        out[b] = h
+        out[b] = (h >> 1) | 1
     return out.view(np.int64), lvl
 
 
@@ -385,7 +385,7 @@ def poseopt_expected(po, T=None):
             if arr is not None and arr.shape[1] == 0:
                 arr = None  # an empty array is not shipped
             h = dig_array(h, arr, b, cnt)
-        want[b] = h
+        want[b] = (h >> 1) | 1
     return want.view(np.int64)
 
 

@@ -80,6 +80,15 @@ def test_host_pipeline(results, scenario, mode):
     assert results(mode)[scenario] == "ok", results(mode)[scenario]
 
 
+def test_abi_misuse_tests_of_the_gpu_tier_against_the_host_model(hostmodel):
+    """tests/test_gpu_abi_errors.py (state and argument errors, pinned allocation) needs no kernel result: here it runs
+    against the host model, so the CPU tier sees the same return codes and messages the GPU tier checks."""
+    env = dict(os.environ, PLSVO_LIB=hostmodel, PLSVO_FAKE_CUDA="lazy")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_abi_errors.py"), "-q", "-m", "gpu", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+
+
 # ---- the model must notice seeded faults -------------------------------------------------------------------------------
 FAULTS = {
     # the k-kernel pipeline forgets to make the kernel of a chunk wait for that chunk's copies
