@@ -211,6 +211,37 @@ def lean_copy(data, torch):
     return lean, nbytes, keep
 
 
+def chain_leg(args, al, synth, torch, dev, stream, B, rank):
+    """The local part of the `e2e_chain` leg: B pairs replaying one trajectory of B + 1 frames, shipped as two stacks once
+    (the comparison) and then as one stack (PLSVO_ALIGN_FRAME_CHAIN), warm-up + args.steps timed calls from page-locked
+    arrays.  Returns (ms over the timed calls, (full batch, last result, H2D bytes per call, check against the two-stack
+    call)).  Kept free of collectives so that the caller can wrap it in a try; tests/hostmodel/scenarios.py runs it against
+    the host model."""
+    cfull = synth.make_chain_batch(batch=B, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=7000 + 100000 * rank)
+    clean, _h2d_two, keep_chain = lean_copy(cfull, torch)
+    two = al.run(clean)  # the same chain given as two stacks (ref, cur): the comparison for the one-stack call
+    ft = torch.from_numpy(synth.chain_frames(cfull, levels=[cfull.min_level])[cfull.min_level]).pin_memory()
+    keep_chain.append(ft)
+    clean.frame_pyr = {cfull.min_level: ft.numpy()}
+    h2d_chain = (_h2d_two - sum(v.nbytes for v in clean.ref_pyr.values()) - sum(v.nbytes for v in clean.cur_pyr.values())
+                 + ft.numpy().nbytes)
+    for _ in range(2):
+        out_c = al.run(clean)
+    _a, _r = synth.pose_error(out_c.T_cur_w, two.T_cur_w)
+    chain_check = {"iteration_counts_equal_to_two_stack_call": int((out_c.iters == two.iters).all(axis=1).sum()), "pairs": int(B),
+                   "max_rot_rad_vs_two_stack_call": float(_a.max()), "max_rel_t_vs_two_stack_call": float(_r.max())}
+    torch.cuda.synchronize(dev)
+    c_s, c_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    c_s.record(stream)
+    for _ in range(args.steps):
+        out_c = al.run(clean)
+    c_e.record(stream)
+    torch.cuda.synchronize(dev)
+    chain_local_ms = max(c_s.elapsed_time(c_e), 1e3 * (time.perf_counter() - t0))
+    return chain_local_ms, (cfull, out_c, h2d_chain, chain_check)
+
+
 def cpu_oracle_rate(abi, oracle_lib, data, n_pairs, min_seconds=3.0):
     """pairs/s of the CPU arm with all host threads on the first n_pairs of `data`."""
     align_fn, _, _ = cpu_impl(abi, oracle_lib)
@@ -699,29 +730,7 @@ def main():
         # that a rank that failed still meets the others
         chain_err, chain_local_ms, chain_info = None, -1.0, None
         try:
-            cfull = synth.make_chain_batch(batch=B, n_pts=args.n_pts, n_segs=args.n_segs, device=dev, seed=7000 + 100000 * rank)
-            clean, _h2d_two, keep_chain = lean_copy(cfull, torch)
-            two = al.run(clean)  # the same chain given as two stacks (ref, cur): the comparison for the one-stack call
-            ft = torch.from_numpy(synth.chain_frames(cfull, levels=[cfull.min_level])[cfull.min_level]).pin_memory()
-            keep_chain.append(ft)
-            clean.frame_pyr = {cfull.min_level: ft.numpy()}
-            h2d_chain = (_h2d_two - sum(v.nbytes for v in clean.ref_pyr.values()) - sum(v.nbytes for v in clean.cur_pyr.values())
-                         + ft.numpy().nbytes)
-            for _ in range(2):
-                out_c = al.run(clean)
-            _a, _r = synth.pose_error(out_c.T_cur_w, two.T_cur_w)
-            chain_check = {"iteration_counts_equal_to_two_stack_call": int((out_c.iters == two.iters).all(axis=1).sum()), "pairs": int(B),
-                           "max_rot_rad_vs_two_stack_call": float(_a.max()), "max_rel_t_vs_two_stack_call": float(_r.max())}
-            torch.cuda.synchronize(dev)
-            c_s, c_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            c_s.record(stream)
-            for _ in range(args.steps):
-                out_c = al.run(clean)
-            c_e.record(stream)
-            torch.cuda.synchronize(dev)
-            chain_local_ms = max(c_s.elapsed_time(c_e), 1e3 * (time.perf_counter() - t0))
-            chain_info = (cfull, out_c, h2d_chain, chain_check)
+            chain_local_ms, chain_info = chain_leg(args, al, synth, torch, dev, stream, B, rank)
         except Exception as ex:
             chain_err = f"{type(ex).__name__}: {ex}"
         chain_ms = torch.tensor([chain_local_ms, -1.0 if chain_err else 1.0], dtype=torch.float64, device=dev)

@@ -31,7 +31,7 @@ def build(force: bool = False, abi_source: str | None = None, out: str | None = 
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-I" + cuda_include(),
            "-I" + os.path.join(ROOT, "pl-svo_b200", "csrc"),  # a mutated copy lives elsewhere but includes "internal.h"
-           "-x", "c++", *sources, "-o", out + ".tmp", "-lpthread",
+           "-x", "c++", *sources, "-o", out + ".tmp", "-lpthread", "-ldl",
            "-Wl,-Bsymbolic"]  # bind the model runtime inside the library even when a real libcudart is already loaded (torch)
     subprocess.run(cmd, check=True)
     os.replace(out + ".tmp", out)

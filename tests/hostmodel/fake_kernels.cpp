@@ -12,10 +12,20 @@
 //               arrival gate is honoured pair by pair, advancing the other streams only as far as the gate requires.
 //   pyramid   : the real computation (truncating 2x2 mean), it is the producer of derived levels.
 //   pose-opt  : out_num_pt[b] = digest of frame b's inputs; out_T[b] = T_f_w[b].
-//   the next-row kernels report cudaErrorNotSupported (their host code is plain upload -> launch -> download).
+//   the next-row kernels exist in the oracle-backed mode only (below); otherwise they report cudaErrorNotSupported.
 //
-// The same digest is restated in NumPy in tests/test_host_pipeline_cpu.py, from the caller's arrays.
+// The same digest is restated in NumPy in tests/hostmodel/scenarios.py, from the caller's arrays.
+//
+// Second mode, PLSVO_FAKE_ORACLE=<path of oracle/libplsvo_oracle.so>: every "kernel" hands its
+// device-layout arguments to the CPU oracle instead of digesting them, so that the GPU tier's own test files can be run
+// here against the unchanged host code (a pre-flight of those files and of the host paths they take, never a parity
+// statement: oracle is compared with oracle).  Inputs the oracle cannot take (depth-only features, bearings not shipped)
+// are refused with cudaErrorNotSupported.
+#include <dlfcn.h>
 #include <string.h>
+
+#include <thread>
+#include <vector>
 
 #include <memory>
 
@@ -68,23 +78,26 @@ struct AlignRun {
   int next = 0;
 };
 
+// device-side level derivation of pair b (what the real kernel does before it touches the pair)
+void derive_pair_levels(const plsvo::AlignArgs& a, int b) {
+  if (a.derive_from < 0) return;
+  for (int l = a.derive_from + 1; l <= a.max_level; ++l) {
+    const int cols = a.width >> l, rows = a.height >> l;
+    for (int which = 0; which < 2; ++which) {
+      const uint8_t* src = (which ? a.cur_img[l - 1] : a.ref_img[l - 1]) + (size_t)b * a.stride[l - 1];
+      uint8_t* dst = const_cast<uint8_t*>(which ? a.cur_img[l] : a.ref_img[l]) + (size_t)b * a.stride[l];
+      if (!fakecuda::check(src, a.stride[l - 1], "align kernel: source level of a derived level") ||
+          !fakecuda::check(dst, a.stride[l], "align kernel: derived level"))
+        return;
+      half_sample(src, a.pitch[l - 1], dst, a.pitch[l], rows, cols);
+    }
+  }
+}
+
 bool align_pair(const plsvo::AlignArgs& a, int b) {
   using fakecuda::check;
   bool ok = true;
-  // levels the kernel forms itself from the finest shipped one (gated host pipeline)
-  if (a.derive_from >= 0) {
-    for (int l = a.derive_from + 1; l <= a.max_level; ++l) {
-      const int cols = a.width >> l, rows = a.height >> l;
-      for (int which = 0; which < 2; ++which) {
-        const uint8_t* src = (which ? a.cur_img[l - 1] : a.ref_img[l - 1]) + (size_t)b * a.stride[l - 1];
-        uint8_t* dst = const_cast<uint8_t*>(which ? a.cur_img[l] : a.ref_img[l]) + (size_t)b * a.stride[l];
-        if (!check(src, a.stride[l - 1], "align kernel: source level of a derived level") ||
-            !check(dst, a.stride[l], "align kernel: derived level"))
-          return false;
-        half_sample(src, a.pitch[l - 1], dst, a.pitch[l], rows, cols);
-      }
-    }
-  }
+  derive_pair_levels(a, b);  // levels the kernel forms itself from the finest shipped one (gated host pipeline)
   uint64_t h = 0;
   for (int i = 0; i < 36; ++i) a.out_H[(size_t)b * 36 + i] = 0.0;
   for (int l = a.min_level; l <= a.max_level; ++l) {
@@ -145,6 +158,100 @@ bool align_pair(const plsvo::AlignArgs& a, int b) {
   return true;
 }
 
+// ---- PLSVO_FAKE_ORACLE: the CPU oracle behind the launch entry points ----
+struct OracleApi {
+  int (*align)(const plsvo_align_batch*, const plsvo_align_params*, const plsvo_align_result*, int, int) = nullptr;
+  int (*poseopt)(const plsvo_poseopt_batch*, const plsvo_poseopt_params*, const plsvo_poseopt_result*, int) = nullptr;
+  int (*align2d)(const plsvo_align2d_batch*, const plsvo_align2d_result*, int) = nullptr;
+  int (*align1d)(const plsvo_align1d_batch*, const plsvo_align1d_result*, int) = nullptr;
+  int (*match)(const plsvo_match_batch*, const plsvo_match_result*, int) = nullptr;
+  int (*structopt)(const plsvo_structopt_batch*, const plsvo_structopt_result*, int) = nullptr;
+  int (*seed)(const plsvo_seed_batch*, const plsvo_seed_result*, int) = nullptr;
+  int (*line_seed)(const plsvo_line_seed_batch*, const plsvo_line_seed_result*, int) = nullptr;
+};
+
+const OracleApi* oracle() {
+  static OracleApi api;
+  static int state = 0;  // 0: not looked up, 1: loaded, -1: digest mode
+  if (state == 0) {
+    state = -1;
+    const char* path = getenv("PLSVO_FAKE_ORACLE");
+    if (path && *path) {
+      void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+      if (h) {
+        api.align = reinterpret_cast<decltype(api.align)>(dlsym(h, "plsvo_oracle_align_batch"));
+        api.poseopt = reinterpret_cast<decltype(api.poseopt)>(dlsym(h, "plsvo_oracle_poseopt_batch"));
+        api.align2d = reinterpret_cast<decltype(api.align2d)>(dlsym(h, "plsvo_oracle_align2d_batch"));
+        api.align1d = reinterpret_cast<decltype(api.align1d)>(dlsym(h, "plsvo_oracle_align1d_batch"));
+        api.match = reinterpret_cast<decltype(api.match)>(dlsym(h, "plsvo_oracle_match_direct_batch"));
+        api.structopt = reinterpret_cast<decltype(api.structopt)>(dlsym(h, "plsvo_oracle_structopt_batch"));
+        api.seed = reinterpret_cast<decltype(api.seed)>(dlsym(h, "plsvo_oracle_seed_update_batch"));
+        api.line_seed = reinterpret_cast<decltype(api.line_seed)>(dlsym(h, "plsvo_oracle_line_seed_update_batch"));
+      }
+      if (api.align && api.poseopt && api.align2d && api.align1d && api.match && api.structopt && api.seed && api.line_seed) state = 1;
+      else fakecuda::error(std::string("PLSVO_FAKE_ORACLE: cannot load the oracle from ") + path);
+    }
+  }
+  return state == 1 ? &api : nullptr;
+}
+
+int host_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+void align_by_oracle(const OracleApi* o, const plsvo::AlignArgs& a) {
+  plsvo_align_batch b;
+  memset(&b, 0, sizeof b);
+  b.batch = a.B, b.n_pts = a.n_pts, b.n_segs = a.n_segs;
+  b.cam.width = a.width, b.cam.height = a.height, b.cam.fx = a.fx, b.cam.fy = a.fy, b.cam.cx = a.cx, b.cam.cy = a.cy;
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    if (!a.pitch[l] || !a.ref_img[l] || !a.cur_img[l]) continue;
+    b.ref_img[l] = a.ref_img[l], b.cur_img[l] = a.cur_img[l], b.img_pitch[l] = a.pitch[l], b.img_stride[l] = a.stride[l];
+  }
+  b.T_ref_w = a.T_ref_w, b.T_cur_w = a.T_cur_w;
+  b.pt_count = a.pt_count, b.pt_px = a.pt_px, b.pt_f = a.pt_f, b.pt_pos = a.pt_pos, b.pt_valid = a.pt_valid;
+  b.seg_count = a.seg_count, b.seg_spx = a.seg_spx, b.seg_epx = a.seg_epx, b.seg_sf = a.seg_sf, b.seg_ef = a.seg_ef;
+  b.seg_spos = a.seg_spos, b.seg_epos = a.seg_epos, b.seg_length = a.seg_length, b.seg_valid = a.seg_valid;
+  plsvo_align_params p;
+  memset(&p, 0, sizeof p);
+  p.max_level = a.max_level, p.min_level = a.min_level, p.n_iter = a.n_iter, p.eps = a.eps;
+  plsvo_align_result r;
+  memset(&r, 0, sizeof r);
+  r.T_cur_w = a.out_T, r.n_tracked = reinterpret_cast<int64_t*>(a.out_n_tracked), r.H = a.out_H;
+  r.seg_killed = a.n_segs > 0 ? a.out_seg_killed : nullptr, r.iters = a.out_iters, r.status = a.out_status;
+  r.patch_iters = a.out_patch_iters, r.patch_levels = a.out_patch_levels;
+  const size_t B = (size_t)a.B;
+  // the oracle's callers hand it zeroed outputs (abi.AlignOut)
+  memset(a.out_T, 0, B * 56), memset(a.out_n_tracked, 0, B * 8), memset(a.out_H, 0, B * 288);
+  memset(a.out_iters, 0, B * 4 * PLSVO_MAX_LEVELS), memset(a.out_status, 0, B * 4);
+  memset(a.out_patch_iters, 0, B * 4), memset(a.out_patch_levels, 0, B * 4);
+  if (a.n_segs > 0) memset(a.out_seg_killed, 0, B * (size_t)a.n_segs);
+  const int rc = o->align(&b, &p, &r, host_threads(), 0);
+  if (rc != PLSVO_OK) fakecuda::error("the oracle refused the alignment batch the host code built");
+}
+
+void poseopt_by_oracle(const OracleApi* o, const plsvo::PoseOptArgs& a) {
+  plsvo_poseopt_batch b;
+  memset(&b, 0, sizeof b);
+  b.batch = a.B, b.n_pts = a.n_pts, b.n_segs = a.n_segs, b.fx = a.fx;
+  b.T_f_w = a.T_f_w, b.pt_count = a.pt_count, b.pt_f = a.pt_f, b.pt_pos = a.pt_pos, b.pt_level = a.pt_level, b.pt_valid = a.pt_valid;
+  b.seg_count = a.seg_count, b.seg_line = a.seg_line, b.seg_spos = a.seg_spos, b.seg_epos = a.seg_epos, b.seg_level = a.seg_level;
+  b.seg_valid = a.seg_valid;
+  plsvo_poseopt_params p;
+  memset(&p, 0, sizeof p);
+  p.reproj_thresh = a.reproj_thresh, p.n_iter = a.n_iter, p.n_iter_ref = a.n_iter_ref;
+  plsvo_poseopt_result r;
+  memset(&r, 0, sizeof r);
+  r.T_f_w = a.out_T, r.cov = a.out_cov, r.estimated_scale = a.out_scale, r.error_init = a.out_err_init, r.error_final = a.out_err_final;
+  r.num_obs_pt = reinterpret_cast<int64_t*>(a.out_num_pt), r.num_obs_ls = reinterpret_cast<int64_t*>(a.out_num_ls);
+  r.pt_outlier = a.out_pt_outlier, r.seg_outlier = a.n_segs > 0 ? a.out_seg_outlier : nullptr, r.iters = a.out_iters, r.status = a.out_status;
+  const size_t B = (size_t)a.B;
+  // what the real kernel always writes and the oracle may leave alone: start from zeros (abi.PoseOptOut) and the input pose
+  memcpy(a.out_T, a.T_f_w, B * 56);
+  memset(a.out_pt_outlier, 0, B * (size_t)std::max(1, a.n_pts)), memset(a.out_seg_outlier, 0, B * (size_t)std::max(1, a.n_segs));
+  memset(a.out_iters, 0, B * 8), memset(a.out_status, 0, B * 4);
+  const int rc = o->poseopt(&b, &p, &r, host_threads());
+  if (rc != PLSVO_OK) fakecuda::error("the oracle refused the pose-optimiser batch the host code built");
+}
+
 }  // namespace
 
 namespace plsvo {
@@ -181,9 +288,14 @@ cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, int m
     fakecuda::error("align_kernel_launch: launch configuration out of range");
     return cudaErrorInvalidConfiguration;
   }
+  const OracleApi* orc = oracle();
+  if (orc && ((a.n_pts > 0 && (!a.pt_f || !a.pt_pos)) || (a.n_segs > 0 && (!a.seg_sf || !a.seg_ef || !a.seg_spos || !a.seg_epos)))) {
+    fakecuda::error("oracle-backed model kernel: depth-only features / bearings not shipped are outside the oracle's inputs");
+    return cudaErrorNotSupported;
+  }
   auto run = std::make_shared<AlignRun>();
   run->a = a, run->stream = s;
-  return fakecuda::enqueue(s, [run]() {
+  return fakecuda::enqueue(s, [run, orc]() {
     const AlignArgs& a = run->a;
     if (run->next == 0) {
       if (!fakecuda::check(a.work_counter, 4, "work counter")) return true;
@@ -197,10 +309,12 @@ cudaError_t align_kernel_launch(const AlignArgs& a, int grid, int threads, int m
         while (*a.arrived < need)
           if (!fakecuda::advance_others(run->stream)) return false;  // blocked: this pair's chunk is still in flight
       }
-      align_pair(a, b);
+      if (orc) derive_pair_levels(a, b);
+      else align_pair(a, b);
       run->next = b + 1;
       *a.work_counter = (unsigned)run->next;
     }
+    if (orc) align_by_oracle(orc, a);
     return true;
   });
 }
@@ -209,6 +323,11 @@ size_t poseopt_smem_bytes(int n_pts, int n_segs) { return 4096 + 24 * ((size_t)n
 
 cudaError_t poseopt_kernel_launch(const PoseOptArgs& a0, size_t, cudaStream_t s) {
   const PoseOptArgs a = a0;
+  if (const OracleApi* orc = oracle())
+    return fakecuda::enqueue(s, [a, orc]() {
+      poseopt_by_oracle(orc, a);
+      return true;
+    });
   return fakecuda::enqueue(s, [a]() {
     const size_t np_ = (size_t)a.n_pts, ns_ = (size_t)a.n_segs;
     for (int b = 0; b < a.B; ++b) {
@@ -254,11 +373,161 @@ cudaError_t pyramid_kernel_launch(const PyramidArgs& a0, cudaStream_t s) {
   });
 }
 
-cudaError_t align2d_kernel_launch(const Align2DArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t align1d_kernel_launch(const Align2DArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t match_direct_kernel_launch(const MatchArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t seed_update_kernel_launch(const SeedArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t line_seed_update_kernel_launch(const SeedArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t structopt_kernel_launch(const StructOptArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+// ---- the next-row kernels: oracle-backed only (their host code is plain upload -> launch -> download) ----
+static void fill_align2d(const Align2DArgs& a, plsvo_align2d_batch* b) {
+  memset(b, 0, sizeof *b);
+  b->n_features = a.n, b->n_images = 1 << 30, b->width = a.width, b->height = a.height, b->n_iter = a.n_iter;
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) b->img[l] = a.img[l], b->img_pitch[l] = a.pitch[l], b->img_stride[l] = a.stride[l];
+  b->image_index = a.image_index, b->level = a.level, b->ref_patch_with_border = a.ref_patch_with_border, b->ref_patch = a.ref_patch;
+  b->px = a.px;
+}
+
+cudaError_t align2d_kernel_launch(const Align2DArgs& a0, cudaStream_t s) {
+  const OracleApi* o = oracle();
+  if (!o) return cudaErrorNotSupported;
+  const Align2DArgs a = a0;
+  return fakecuda::enqueue(s, [a, o]() {
+    plsvo_align2d_batch b;
+    fill_align2d(a, &b);
+    memset(a.out_px, 0, (size_t)a.n * 16), memset(a.out_converged, 0, (size_t)a.n);
+    plsvo_align2d_result r{a.out_px, a.out_converged};
+    if (o->align2d(&b, &r, host_threads()) != PLSVO_OK) fakecuda::error("the oracle refused the align2D batch the host code built");
+    return true;
+  });
+}
+
+cudaError_t align1d_kernel_launch(const Align2DArgs& a0, cudaStream_t s) {
+  const OracleApi* o = oracle();
+  if (!o) return cudaErrorNotSupported;
+  const Align2DArgs a = a0;
+  return fakecuda::enqueue(s, [a, o]() {
+    plsvo_align1d_batch b;
+    memset(&b, 0, sizeof b);
+    fill_align2d(a, &b.features);
+    b.dir = a.dir;
+    memset(a.out_px, 0, (size_t)a.n * 16), memset(a.out_converged, 0, (size_t)a.n), memset(a.out_h_inv, 0, (size_t)a.n * 8);
+    plsvo_align1d_result r{a.out_px, a.out_converged, a.out_h_inv};
+    if (o->align1d(&b, &r, host_threads()) != PLSVO_OK) fakecuda::error("the oracle refused the align1D batch the host code built");
+    return true;
+  });
+}
+
+cudaError_t match_direct_kernel_launch(const MatchArgs& a0, cudaStream_t s) {
+  const OracleApi* o = oracle();
+  if (!o) return cudaErrorNotSupported;
+  const MatchArgs a = a0;
+  return fakecuda::enqueue(s, [a, o]() {
+    plsvo_match_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_features = a.n, b.n_ref_images = 1 << 30, b.n_cur_images = 1 << 30, b.n_pyr_levels = a.n_pyr_levels, b.n_iter = a.n_iter;
+    b.cam.width = a.width, b.cam.height = a.height, b.cam.fx = a.fx, b.cam.fy = a.fy, b.cam.cx = a.cx, b.cam.cy = a.cy;
+    for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+      b.ref_img[l] = a.ref_img[l], b.ref_pitch[l] = a.ref_pitch[l], b.ref_stride[l] = a.ref_stride[l];
+      b.cur_img[l] = a.cur_img[l], b.cur_pitch[l] = a.cur_pitch[l], b.cur_stride[l] = a.cur_stride[l];
+    }
+    b.T_ref_w = a.T_ref_w, b.T_cur_w = a.T_cur_w, b.ref_index = a.ref_index, b.cur_index = a.cur_index, b.ref_px = a.ref_px;
+    b.ref_f = a.ref_f, b.ref_level = a.ref_level, b.is_edgelet = a.is_edgelet, b.ref_grad = a.ref_grad, b.pos = a.pos, b.px_cur = a.px_cur;
+    memset(a.out_px, 0, (size_t)a.n * 16), memset(a.out_success, 0, (size_t)a.n), memset(a.out_level, 0, (size_t)a.n * 4);
+    plsvo_match_result r{a.out_px, a.out_success, a.out_level, a.out_A};
+    if (o->match(&b, &r, host_threads()) != PLSVO_OK) fakecuda::error("the oracle refused the match batch the host code built");
+    return true;
+  });
+}
+
+// The oracle's epipolar ZMSSD search strides the current image with its width, as the reference does with Mat::cols
+// (src/matcher.cpp:380-382; "images are dense"), while the device layout pads rows to 16 bytes: levels whose pitch is not
+// their width are handed over as dense copies.
+static void densify_cur_levels(const SeedArgs& a, plsvo_seed_batch* b, std::vector<std::vector<uint8_t>>* keep) {
+  int n_cur = 0;
+  for (int i = 0; i < a.n; ++i) n_cur = std::max(n_cur, a.cur_index[i] + 1);
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    const int cols = a.width >> l, rows = a.height >> l;
+    if (!a.cur_img[l] || cols <= 0 || rows <= 0 || a.cur_pitch[l] == (uint32_t)cols) continue;
+    if (!fakecuda::check(a.cur_img[l], (size_t)n_cur * a.cur_stride[l], "seed kernel: current image level")) continue;
+    keep->emplace_back((size_t)n_cur * rows * cols);
+    uint8_t* d = keep->back().data();
+    for (int f = 0; f < n_cur; ++f)
+      for (int y = 0; y < rows; ++y)
+        memcpy(d + ((size_t)f * rows + y) * cols, a.cur_img[l] + (size_t)f * a.cur_stride[l] + (size_t)y * a.cur_pitch[l], (size_t)cols);
+    b->cur_img[l] = d, b->cur_pitch[l] = (size_t)cols, b->cur_stride[l] = (size_t)rows * cols;
+  }
+}
+
+static void fill_seed(const SeedArgs& a, plsvo_seed_batch* b, plsvo_seed_result* r) {
+  memset(b, 0, sizeof *b);
+  b->n_seeds = a.n, b->n_ref_images = 1 << 30, b->n_cur_images = 1 << 30, b->n_pyr_levels = a.n_pyr_levels, b->n_iter = a.n_iter;
+  b->max_epi_search_steps = a.max_epi_search_steps, b->align_1d = (uint8_t)a.align_1d, b->subpix_refinement = (uint8_t)a.subpix_refinement;
+  b->epi_search_edgelet_filtering = (uint8_t)a.edgelet_filtering, b->epi_search_edgelet_max_angle = a.edgelet_max_angle;
+  b->seed_convergence_sigma2_thresh = a.convergence_thresh;
+  b->cam.width = a.width, b->cam.height = a.height, b->cam.fx = a.fx, b->cam.fy = a.fy, b->cam.cx = a.cx, b->cam.cy = a.cy;
+  for (int l = 0; l < PLSVO_MAX_LEVELS; ++l) {
+    b->ref_img[l] = a.ref_img[l], b->ref_pitch[l] = a.ref_pitch[l], b->ref_stride[l] = a.ref_stride[l];
+    b->cur_img[l] = a.cur_img[l], b->cur_pitch[l] = a.cur_pitch[l], b->cur_stride[l] = a.cur_stride[l];
+  }
+  b->T_ref_w = a.T_ref_w, b->T_cur_w = a.T_cur_w, b->ref_index = a.ref_index, b->cur_index = a.cur_index, b->ref_px = a.ref_px;
+  b->ref_f = a.ref_f, b->ref_level = a.ref_level, b->is_edgelet = a.is_edgelet, b->ref_grad = a.ref_grad;
+  b->a = a.a, b->b = a.b, b->mu = a.mu, b->z_range = a.z_range, b->sigma2 = a.sigma2;
+  const size_t n = (size_t)a.n;
+  memset(a.out_a, 0, n * 4), memset(a.out_b, 0, n * 4), memset(a.out_mu, 0, n * 4), memset(a.out_sigma2, 0, n * 4);
+  memset(a.out_status, 0, n * 4), memset(a.out_converged, 0, n), memset(a.out_depth, 0, n * 8), memset(a.out_px_cur, 0, n * 16);
+  *r = plsvo_seed_result{a.out_a, a.out_b, a.out_mu, a.out_sigma2, a.out_status, a.out_converged, a.out_depth, a.out_px_cur};
+}
+
+cudaError_t seed_update_kernel_launch(const SeedArgs& a0, cudaStream_t s) {
+  const OracleApi* o = oracle();
+  if (!o) return cudaErrorNotSupported;
+  const SeedArgs a = a0;
+  return fakecuda::enqueue(s, [a, o]() {
+    plsvo_seed_batch b;
+    plsvo_seed_result r;
+    std::vector<std::vector<uint8_t>> dense;
+    fill_seed(a, &b, &r);
+    densify_cur_levels(a, &b, &dense);
+    if (o->seed(&b, &r, host_threads()) != PLSVO_OK) fakecuda::error("the oracle refused the seed batch the host code built");
+    return true;
+  });
+}
+
+cudaError_t line_seed_update_kernel_launch(const SeedArgs& a0, cudaStream_t s) {
+  const OracleApi* o = oracle();
+  if (!o) return cudaErrorNotSupported;
+  const SeedArgs a = a0;
+  return fakecuda::enqueue(s, [a, o]() {
+    plsvo_line_seed_batch b;
+    plsvo_line_seed_result r;
+    memset(&b, 0, sizeof b), memset(&r, 0, sizeof r);
+    std::vector<std::vector<uint8_t>> dense;
+    fill_seed(a, &b.seeds, &r.seeds);
+    densify_cur_levels(a, &b.seeds, &dense);
+    b.ref_sf = a.ref_sf, b.ref_ef = a.ref_ef, b.mu_e = a.mu_e, b.z_range_e = a.z_range_e, b.sigma2_e = a.sigma2_e;
+    const size_t n = (size_t)a.n;
+    memset(a.out_mu_e, 0, n * 4), memset(a.out_sigma2_e, 0, n * 4), memset(a.out_depth_e, 0, n * 8), memset(a.out_px_cur_e, 0, n * 16);
+    r.mu_e = a.out_mu_e, r.sigma2_e = a.out_sigma2_e, r.depth_e = a.out_depth_e, r.px_cur_e = a.out_px_cur_e;
+    if (o->line_seed(&b, &r, host_threads()) != PLSVO_OK) fakecuda::error("the oracle refused the line-seed batch the host code built");
+    return true;
+  });
+}
+
+cudaError_t structopt_kernel_launch(const StructOptArgs& a0, cudaStream_t s) {
+  const OracleApi* o = oracle();
+  if (!o) return cudaErrorNotSupported;
+  const StructOptArgs a = a0;
+  return fakecuda::enqueue(s, [a, o]() {
+    plsvo_structopt_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_points = a.n_points, b.n_segs = a.n_segs, b.n_iter_pts = a.n_iter_pts, b.n_iter_segs = a.n_iter_segs;
+    int n_frames = 0;  // not part of the kernel arguments: the highest frame any observation names
+    const int npo = a.n_points ? a.pt_obs_begin[a.n_points] : 0, nso = a.n_segs ? a.seg_obs_begin[a.n_segs] : 0;
+    for (int i = 0; i < npo; ++i) n_frames = std::max(n_frames, a.pt_obs_frame[i] + 1);
+    for (int i = 0; i < nso; ++i) n_frames = std::max(n_frames, a.seg_obs_frame[i] + 1);
+    b.n_frames = n_frames;
+    b.T_f_w = a.T_f_w, b.pt_obs_begin = a.pt_obs_begin, b.pt_obs_frame = a.pt_obs_frame, b.pt_obs_f = a.pt_obs_f, b.pt_pos = a.pt_pos;
+    b.seg_obs_begin = a.seg_obs_begin, b.seg_obs_frame = a.seg_obs_frame, b.seg_obs_sf = a.seg_obs_sf, b.seg_obs_ef = a.seg_obs_ef;
+    b.seg_spos = a.seg_spos, b.seg_epos = a.seg_epos;
+    plsvo_structopt_result r{a.out_pt_pos, a.out_seg_spos, a.out_seg_epos, a.out_pt_iters, a.out_seg_iters};
+    if (o->structopt(&b, &r, host_threads()) != PLSVO_OK) fakecuda::error("the oracle refused the structure-optimisation batch the host code built");
+    return true;
+  });
+}
 
 }  // namespace plsvo

@@ -431,6 +431,80 @@ def s_track_chained_call():
     clean()
 
 
+def s_bench_chain_leg():
+    """bench.py's `e2e_chain` leg (chain_leg, lean_copy, subset) against the host model: the leg's own bookkeeping — lean
+    inputs, the one-stack view, bytes per call — on a cheap stand-in for the rendered trajectory."""
+    import time as _time
+    import types
+
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Event:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self, stream):
+            self.t = _time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t)
+
+    class Pinned:  # what torch.from_numpy(a).pin_memory() is used for: .numpy() and being kept alive
+        def __init__(self, a):
+            self.a = a
+
+        def pin_memory(self):
+            return self
+
+        def numpy(self):
+            return self.a
+
+    fake_torch = types.SimpleNamespace(tensor=torch.tensor, from_numpy=Pinned,
+                                       cuda=types.SimpleNamespace(synchronize=lambda dev: None, Event=Event))
+    made = {}
+
+    def cheap_chain(batch, n_pts, n_segs, device, seed):
+        d = make_batch(batch, n_pts, n_segs, seed, chain=True)
+        q = np.random.default_rng(seed).standard_normal((batch, 4))
+        d.T_ref_w[:, :4] = q / np.linalg.norm(q, axis=1, keepdims=True)  # lean_copy turns the pose into a camera centre
+        made["d"] = d
+        return d
+
+    fake_synth = types.SimpleNamespace(make_chain_batch=cheap_chain, chain_frames=synth.chain_frames, pose_error=synth.pose_error,
+                                       pose7_to_Rt=synth.pose7_to_Rt)
+    real_synth = bench.__dict__.get("synth")
+    args = types.SimpleNamespace(n_pts=30, n_segs=8, steps=2)
+    B = 260  # the streamed host path (>= 256 pairs), as in the bench
+    al = pkg.SparseImgAlign(4, 2, 30, ctx=pkg.api.Context(0))
+    import plsvo_b200.synth as real
+
+    saved = real.pose7_to_Rt
+    h0 = lib.fake_cuda_h2d_bytes()
+    ms, (cfull, out_c, h2d_chain, chk) = bench.chain_leg(args, al, fake_synth, fake_torch, "cpu", None, B, 0)
+    clean()
+    assert cfull is made["d"] and ms > 0 and real.pose7_to_Rt is saved and real_synth is bench.__dict__.get("synth")
+    assert chk["pairs"] == B and chk["iteration_counts_equal_to_two_stack_call"] == B
+    assert chk["max_rot_rad_vs_two_stack_call"] == 0.0 and chk["max_rel_t_vs_two_stack_call"] == 0.0
+    # what the kernel saw in the one-stack calls = the lean form of the batch (digest of the last call)
+    lean, lean_bytes, _keep = bench.lean_copy(cfull, fake_torch)
+    seen = copy.copy(lean)
+    seen.ref_pyr, seen.cur_pyr = cfull.ref_pyr, cfull.cur_pyr  # levels 3 and 4 are derived on the device from the shipped one
+    want, _lvl = expected(seen)
+    assert np.array_equal(out_c.n_tracked, want), "chain leg: the kernel did not see the lean batch"
+    # the leg's byte accounting equals what crossed the model link in one one-stack call (plus the arrival flags)
+    moved = lib.fake_cuda_h2d_bytes() - h0
+    two_stack, one_stack = lean_bytes, h2d_chain
+    assert two_stack - one_stack == (B - 1) * cfull.ref_pyr[2][0].nbytes
+    calls_one = 2 + args.steps
+    assert 0 <= moved - (two_stack + calls_one * one_stack) <= 8 * (1 + calls_one), (moved, two_stack, one_stack)
+    # the CPU-arm sample the bench takes afterwards
+    sub = bench.subset(cfull, 16)
+    assert sub.batch == 16 and np.array_equal(sub.ref_pyr[3], cfull.ref_pyr[3][:16])
+
+
 SCENARIOS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("s_") and callable(v)}
 
 
