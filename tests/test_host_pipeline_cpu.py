@@ -89,6 +89,23 @@ def test_abi_misuse_tests_of_the_gpu_tier_against_the_host_model(hostmodel):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
 
 
+def test_fast_gpu_tier_files_against_the_host_model_with_oracle_backed_kernels(hostmodel, oracle):
+    """The quick files of the GPU tier (golden fixtures, pose optimiser, and every next-row entry point: pyramid, align2D /
+    align1D, findMatchDirect, structure optimisation, depth-filter seeds) run here against the host model with every model
+    kernel answered by the CPU oracle (PLSVO_FAKE_ORACLE): a check of those test files, of the Python mirror and of the
+    host code of those entry points — the oracle is compared with the oracle, so not of the kernels.  The slower files are
+    run the same way by tools/preflight_gpu_tests.py."""
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, PLSVO_LIB=hostmodel, PLSVO_FAKE_CUDA="lazy", PLSVO_FAKE_ORACLE=os.path.join(root, "oracle", "libplsvo_oracle.so"))
+    files = [os.path.join(HERE, f) for f in ("test_gpu_golden.py", "test_gpu_poseopt.py", "test_pyramid.py", "test_align2d.py", "test_matcher.py",
+                                             "test_structopt.py", "test_depth_filter.py")]
+    p = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                        "not shim_optimize_structure_on_the_gpu"],  # that case links the CUDA library directly
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert " passed" in p.stdout and "failed" not in p.stdout
+
+
 # ---- the model must notice seeded faults -------------------------------------------------------------------------------
 FAULTS = {
     # the k-kernel pipeline forgets to make the kernel of a chunk wait for that chunk's copies
