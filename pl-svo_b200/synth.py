@@ -279,6 +279,7 @@ def make_align_batch(
     keep_levels_only: bool = True,
     T_ref_w_gt: np.ndarray | None = None,
     T_cur_w_gt: np.ndarray | None = None,
+    chain: bool = False,
 ) -> AlignData:
     """SURVEY.md §8d config C2 generator: B independent frame pairs, each with its own reference view,
     features and motion (seeds derived from `seed`)."""
@@ -302,10 +303,18 @@ def make_align_batch(
     T_ref_w = pose7_from_Rt(R_ref, t_ref)
     T_cur_w_gt = pose7_from_Rt(R_cur, t_cur)
 
-    ref0 = scene.render(cam, T_ref_w)
-    cur0 = scene.render(cam, T_cur_w_gt)
-    ref_pyr = build_pyramid(ref0, n_pyr_levels)
-    cur_pyr = build_pyramid(cur0, n_pyr_levels)
+    if chain:
+        # one trajectory (the given poses satisfy T_ref_w_gt[b+1] == T_cur_w_gt[b]): every frame is rendered ONCE and the two
+        # stacks are views of the one sequence, so "cur of pair b" and "ref of pair b+1" are the same bytes by construction
+        # rather than by the renderer happening to be bit-reproducible across batch positions
+        frames = build_pyramid(scene.render(cam, torch.cat([T_ref_w, T_cur_w_gt[-1:]], 0)), n_pyr_levels)
+        ref_pyr = [f[:-1] for f in frames]
+        cur_pyr = [f[1:] for f in frames]
+    else:
+        ref0 = scene.render(cam, T_ref_w)
+        cur0 = scene.render(cam, T_cur_w_gt)
+        ref_pyr = build_pyramid(ref0, n_pyr_levels)
+        cur_pyr = build_pyramid(cur0, n_pyr_levels)
     levels = range(min_level, max_level + 1) if keep_levels_only else range(n_pyr_levels)
 
     lo_u, hi_u = margin, cam.width - margin
@@ -542,7 +551,7 @@ def make_chain_batch(cam: Camera = VGA, batch: int = 8, n_pts: int = 300, n_segs
         poses.append(pose7_from_Rt(R, t))
     poses = torch.cat(poses, 0).numpy()
     return make_align_batch(cam=cam, batch=batch, n_pts=n_pts, n_segs=n_segs, seed=seed, device=device,
-                            T_ref_w_gt=poses[:-1], T_cur_w_gt=poses[1:], **kw)
+                            T_ref_w_gt=poses[:-1], T_cur_w_gt=poses[1:], chain=True, **kw)
 
 
 def run_sequence(poses, steps, track_fn):
