@@ -727,8 +727,10 @@ int align_derive_levels(plsvo_ctx_impl* c, int min_level, int max_level, size_t 
   if (src < 0) return fail(c, PLSVO_ERR_INVALID, "a pyramid level in [min_level,max_level] was not uploaded and no lower level is there to derive it from");
   for (int l = first_missing; l <= max_level; ++l)
     if (c->lvl_uploaded[l]) return fail(c, PLSVO_ERR_INVALID, "derived pyramid levels must be contiguous above the uploaded ones");
-  if (a.pitch[src] % 16 != 0 || a.stride[src] % 16 != 0)
-    return fail(c, PLSVO_ERR_INVALID, "deriving pyramid levels on the device needs 16-byte pitched rows of the source level");
+  // the pyramid kernel reads 16-byte rows; a source level whose host layout was kept with a pitch that is only word aligned
+  // (e.g. 188-byte rows: level 2 of a 752-pixel-wide camera) is halfSampled by the alignment kernel itself, pair by pair,
+  // byte by byte — the same code the arrival-gated stream uses
+  if (a.pitch[src] % 16 != 0 || a.stride[src] % 16 != 0) in_kernel = true;
   const size_t B = (size_t)a.B;
   if (prepare || c->der_src != src || c->der_top < max_level) {
     size_t total = 0, off[PLSVO_MAX_LEVELS] = {0};

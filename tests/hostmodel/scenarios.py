@@ -47,7 +47,7 @@ def mix(h: int, v: int) -> int:
 
 
 def dig_array(h: int, arr, b: int, count: int) -> int:
-    if arr is None:
+    if arr is None or arr.shape[1] == 0:  # not shipped (an empty array is not shipped either)
         return mix(h, 0x5151)
     return mix(h, dig_bytes(arr[b][:count]))
 
@@ -56,10 +56,11 @@ def expected(data, shipped_levels=None):
     """(n_tracked digests [B] as int64, per-level digests [B, 2*levels]) for the batch as the kernel must see it."""
     B = data.batch
     out = np.zeros(B, np.uint64)
-    lvl = np.zeros((B, 2 * len(LEVELS)), np.float64)
+    levels = range(data.min_level, data.max_level + 1)
+    lvl = np.zeros((B, 2 * len(levels)), np.float64)
     for b in range(B):
         h = 0
-        for k, l in enumerate(LEVELS):
+        for k, l in enumerate(levels):
             hr, hc = dig_bytes(data.ref_pyr[l][b]), dig_bytes(data.cur_pyr[l][b])
             h = mix(mix(h, hr), hc)
             lvl[b, 2 * k], lvl[b, 2 * k + 1] = float(hr >> 12), float(hc >> 12)
@@ -86,26 +87,28 @@ def half(img):
     return ((a[:, 0::2, 0::2] + a[:, 0::2, 1::2] + a[:, 1::2, 0::2] + a[:, 1::2, 1::2]) >> 2).astype(np.uint8)
 
 
-def pyramid(rng, n, cam):
-    base = rng.integers(0, 256, (n, cam.height >> 2, cam.width >> 2), dtype=np.uint8)
-    return {2: base, 3: half(base), 4: half(half(base))}
+def pyramid(rng, n, cam, min_level=2, max_level=4):
+    pyr = {min_level: rng.integers(0, 256, (n, cam.height >> min_level, cam.width >> min_level), dtype=np.uint8)}
+    for l in range(min_level + 1, max_level + 1):
+        pyr[l] = half(pyr[l - 1])
+    return pyr
 
 
-def make_batch(B, n_pts, n_segs, seed, cam=synth.VGA, chain=False, ragged=False, masks=False):
+def make_batch(B, n_pts, n_segs, seed, cam=synth.VGA, chain=False, ragged=False, masks=False, min_level=2, max_level=4):
     rng = np.random.default_rng(seed)
     if chain:
-        frames = pyramid(rng, B + 1, cam)
+        frames = pyramid(rng, B + 1, cam, min_level, max_level)
         ref = {l: np.ascontiguousarray(f[:-1]) for l, f in frames.items()}
         cur = {l: np.ascontiguousarray(f[1:]) for l, f in frames.items()}
     else:
-        ref, cur = pyramid(rng, B, cam), pyramid(rng, B, cam)
+        ref, cur = pyramid(rng, B, cam, min_level, max_level), pyramid(rng, B, cam, min_level, max_level)
 
     def r(*shape):
         return rng.standard_normal(shape)
 
     spx = rng.uniform(64, 400, (B, n_segs, 2))
     epx = spx + rng.uniform(-120, 120, (B, n_segs, 2))
-    d = synth.AlignData(cam=cam, max_level=4, min_level=2, ref_pyr=ref, cur_pyr=cur, T_ref_w=r(B, 7), T_cur_w=r(B, 7), T_cur_w_gt=r(B, 7),
+    d = synth.AlignData(cam=cam, max_level=max_level, min_level=min_level, ref_pyr=ref, cur_pyr=cur, T_ref_w=r(B, 7), T_cur_w=r(B, 7), T_cur_w_gt=r(B, 7),
                         pt_px=rng.uniform(64, 400, (B, n_pts, 2)), pt_f=r(B, n_pts, 3), pt_pos=r(B, n_pts, 3), seg_spx=spx, seg_epx=epx,
                         seg_sf=r(B, n_segs, 3), seg_ef=r(B, n_segs, 3), seg_spos=r(B, n_segs, 3), seg_epos=r(B, n_segs, 3),
                         seg_length=np.linalg.norm(epx - spx, axis=-1))
@@ -183,7 +186,7 @@ def check(out, data_as_kernel_sees_it, what=""):
 
 def run(data, ctx=None, **envs):
     with env(**envs):
-        al = pkg.SparseImgAlign(4, 2, 30, ctx=ctx or pkg.api.Context(0))
+        al = pkg.SparseImgAlign(data.max_level, data.min_level, 30, ctx=ctx or pkg.api.Context(0))
         return al.run(data)
 
 
@@ -381,10 +384,7 @@ def poseopt_expected(po, T=None):
         h = mix(h, npt * 65536 + nsg)
         for name, cnt in (("pt_f", npt), ("pt_pos", npt), ("pt_level", npt), ("pt_valid", npt), ("seg_line", nsg), ("seg_spos", nsg),
                           ("seg_epos", nsg), ("seg_level", nsg), ("seg_valid", nsg)):
-            arr = getattr(po, name, None)
-            if arr is not None and arr.shape[1] == 0:
-                arr = None  # an empty array is not shipped
-            h = dig_array(h, arr, b, cnt)
+            h = dig_array(h, getattr(po, name, None), b, cnt)
         want[b] = (h >> 1) | 1
     return want.view(np.int64)
 
@@ -429,6 +429,62 @@ def s_track_chained_call():
     assert np.array_equal(pout.num_obs_pt, poseopt_expected(po, T=d.T_cur_w)), "track: pose-opt digests"
     assert np.array_equal(pout.T_f_w, d.T_cur_w)
     clean()
+
+
+def padded_view(stack, layout, rng):
+    """The same images inside a bigger allocation: rows and / or frames padded with bytes the kernel must never see."""
+    n, h, w = stack.shape
+    pad_r = int(rng.integers(1, 5)) if layout in ("row", "both") else 0
+    pad_f = int(rng.integers(1, 3)) if layout in ("frame", "both") else 0
+    big = np.full((n, h + pad_f, w + pad_r), 255, np.uint8)
+    big[:, :h, :w] = stack
+    return big[:, :h, :w]
+
+
+def s_randomised_configurations():
+    """Differential test over random corners of the configuration space: camera size, level range, which levels are shipped,
+    batch size on either side of the streaming threshold, feature counts down to none, ragged counts, masks, lean features,
+    frame chains, padded host layouts, and the environment switches that select the host path."""
+    rng = np.random.default_rng(int(os.environ.get("PLSVO_FUZZ_SEED", 2024)))  # PLSVO_FUZZ_SEED / _ITERS: longer hunts by hand
+    cams = [synth.Camera(w, h, 0.7 * w, 0.7 * w, w / 2 - 0.5, h / 2 - 0.5) for w, h in ((128, 96), (256, 192), (384, 128), (640, 480))]
+    ctx = pkg.api.Context(0)  # one context for everything: every call inherits the buffers of a differently shaped one
+    for it in range(int(os.environ.get("PLSVO_FUZZ_ITERS", 70))):
+        cam = cams[int(rng.integers(0, 3 if it % 4 else 4))]
+        min_level = int(rng.integers(0, 3))
+        max_level = min(4, min_level + int(rng.integers(0, 3)))
+        B = int(rng.integers(256, 400)) if it % 5 == 0 else int(rng.integers(1, 40))
+        n_pts, n_segs = int(rng.integers(0, 50)), int(rng.integers(0, 12))
+        if B >= 256:
+            n_pts, n_segs = min(n_pts, 12), min(n_segs, 4)
+            if cam.width == 640:
+                cam = cams[1]
+        chain = bool(rng.integers(0, 2))
+        d = make_batch(B, n_pts, n_segs, 5000 + it, cam=cam, chain=chain, ragged=bool(rng.integers(0, 2)), masks=bool(rng.integers(0, 2)),
+                       min_level=min_level, max_level=max_level)
+        seen = d
+        if rng.integers(0, 3) == 0 and n_pts + n_segs > 0:
+            seen = d = lean_features(d, rng)
+        top = int(rng.integers(min_level, max_level + 1))  # levels min..top are shipped, the rest derived on the device
+        levels = list(range(min_level, top + 1))
+        call = one_stack(d, levels) if chain else shipped(d, levels)
+        layout = ["dense", "dense", "row", "frame", "both"][int(rng.integers(0, 5))]
+        if layout != "dense":
+            if chain:
+                call.frame_pyr = {l: padded_view(f, layout, rng) for l, f in call.frame_pyr.items()}
+            else:
+                seed_pad = int(rng.integers(0, 1 << 30))
+                call.ref_pyr = {l: padded_view(f, layout, np.random.default_rng(seed_pad + l)) for l, f in call.ref_pyr.items()}
+                call.cur_pyr = {l: padded_view(f, layout, np.random.default_rng(seed_pad + l)) for l, f in call.cur_pyr.items()}
+        envs = [{}, {}, {"PLSVO_NO_SMALL_UPLOAD": 1}, {"PLSVO_E2E_CHUNKS": int(rng.integers(1, 6))},
+                {"PLSVO_E2E_CHUNKS": int(rng.integers(2, 9)), "PLSVO_NO_SMALL_UPLOAD": 1}, {"PLSVO_GATE_CHUNK": 128},
+                {"PLSVO_GATE_CHUNK": 128, "PLSVO_COPY_STREAMS": int(rng.integers(2, 5))}, {"PLSVO_GATE_INTERLEAVED": 1}][int(rng.integers(0, 8))]
+        what = (f"#{it}: {cam.width}x{cam.height} levels {min_level}..{max_level} shipped {levels} B={B} pts={n_pts} segs={n_segs} chain={chain} "
+                f"layout={layout} lean={seen is not d or hasattr(d, 'pt_depth') and d.pt_depth is not None} env={envs}")
+        try:
+            out = run(call, ctx=ctx, **envs)
+        except pkg.api.PlsvoError as ex:
+            raise AssertionError(f"{what}: {ex}") from None
+        check(out, seen, what)
 
 
 def s_bench_chain_leg():

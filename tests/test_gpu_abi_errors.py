@@ -35,9 +35,11 @@ def test_state_and_argument_errors(pkg, abi, synth, gen_device):
     assert b"point arrays" in lib.plsvo_last_error(ctx.handle)
     batch.pt_px = C.cast(C.c_void_p(saved), C.POINTER(C.c_double))
     assert lib.plsvo_align_upload(ctx.handle, C.byref(batch)) == abi.OK
-    # level range that was not uploaded / nonsense parameters
-    bad = abi.align_params(5, 1, 30)
+    # level range that was neither uploaded nor derivable (level 0 has nothing below it to be derived from; levels above
+    # the uploaded ones would simply be derived on the device) / nonsense parameters
+    bad = abi.align_params(3, 0, 30)
     assert lib.plsvo_align_launch(ctx.handle, C.byref(bad)) == abi.ERR_INVALID
+    assert b"no lower level" in lib.plsvo_last_error(ctx.handle)
     bad = abi.align_params(1, 3, 30)
     assert lib.plsvo_align_launch(ctx.handle, C.byref(bad)) == abi.ERR_INVALID
     bad = abi.align_params(3, 1, 0)

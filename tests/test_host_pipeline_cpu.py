@@ -31,7 +31,7 @@ SCENARIOS = ["plain_upload_launch_download", "small_batch_staging_block", "stagi
              "k_kernel_pipeline",
              "arrival_gated_stream", "padded_host_layouts", "lean_features", "chain_every_host_path", "chain_arrival_gated_stream",
              "chain_padded_host_layouts", "rejected_inputs_leave_nothing_in_flight", "pose_optimiser_host_paths", "pyramid_call",
-             "track_chained_call", "bench_chain_leg"]
+             "track_chained_call", "randomised_configurations", "bench_chain_leg"]
 
 
 def _builder():

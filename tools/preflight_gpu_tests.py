@@ -24,7 +24,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEFAULT_FILES = ["test_gpu_abi_errors.py", "test_gpu_golden.py", "test_gpu_poseopt.py", "test_gpu_track.py", "test_gpu_align.py", "test_pyramid.py",
-                 "test_align2d.py", "test_matcher.py", "test_structopt.py", "test_depth_filter.py", "test_zz_gpu_chain.py"]
+                 "test_align2d.py", "test_matcher.py", "test_structopt.py", "test_depth_filter.py", "test_zz_gpu_chain.py", "test_zz_gpu_word_pitch.py"]
 NEEDS_REAL_KERNELS = "not depths_instead and not bearings_derived and not shim_optimize_structure_on_the_gpu"
 
 
