@@ -52,7 +52,7 @@ def dig_array(h: int, arr, b: int, count: int) -> int:
     return mix(h, dig_bytes(arr[b][:count]))
 
 
-def expected(data, shipped_levels=None):
+def expected(data):
     """(n_tracked digests [B] as int64, per-level digests [B, 2*levels]) for the batch as the kernel must see it."""
     B = data.batch
     out = np.zeros(B, np.uint64)
@@ -531,17 +531,13 @@ def s_bench_chain_leg():
 
     fake_synth = types.SimpleNamespace(make_chain_batch=cheap_chain, chain_frames=synth.chain_frames, pose_error=synth.pose_error,
                                        pose7_to_Rt=synth.pose7_to_Rt)
-    real_synth = bench.__dict__.get("synth")
     args = types.SimpleNamespace(n_pts=30, n_segs=8, steps=2)
     B = 260  # the streamed host path (>= 256 pairs), as in the bench
     al = pkg.SparseImgAlign(4, 2, 30, ctx=pkg.api.Context(0))
-    import plsvo_b200.synth as real
-
-    saved = real.pose7_to_Rt
     h0 = lib.fake_cuda_h2d_bytes()
     ms, (cfull, out_c, h2d_chain, chk) = bench.chain_leg(args, al, fake_synth, fake_torch, "cpu", None, B, 0)
     clean()
-    assert cfull is made["d"] and ms > 0 and real.pose7_to_Rt is saved and real_synth is bench.__dict__.get("synth")
+    assert cfull is made["d"] and ms > 0
     assert chk["pairs"] == B and chk["iteration_counts_equal_to_two_stack_call"] == B
     assert chk["max_rot_rad_vs_two_stack_call"] == 0.0 and chk["max_rel_t_vs_two_stack_call"] == 0.0
     # what the kernel saw in the one-stack calls = the lean form of the batch (digest of the last call)
