@@ -722,31 +722,6 @@ def main():
     if dist:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * B * args.steps / (float(e2e_ms.item()) * 1e-3)
-    # ---- end-to-end leg on a frame chain: the same call replaying ONE trajectory of B + 1 frames (pair b = frames b, b+1;
-    # src/frame_handler_mono.cpp:176,272) shipped as one stack, PLSVO_ALIGN_FRAME_CHAIN — every frame crosses the link once ----
-    e2e_chain = None
-    if not args.no_chain:
-        # the local work sits in a try (a secondary leg must not take the headline line down); the collectives sit outside it so
-        # that a rank that failed still meets the others
-        chain_err, chain_local_ms, chain_info = None, -1.0, None
-        try:
-            chain_local_ms, chain_info = chain_leg(args, al, synth, torch, dev, stream, B, rank)
-        except Exception as ex:
-            chain_err = f"{type(ex).__name__}: {ex}"
-        chain_ms = torch.tensor([chain_local_ms, -1.0 if chain_err else 1.0], dtype=torch.float64, device=dev)
-        if dist:
-            worst = chain_ms.clone()
-            dist.all_reduce(chain_ms, op=dist.ReduceOp.MAX)   # slowest rank
-            dist.all_reduce(worst, op=dist.ReduceOp.MIN)      # any rank that failed
-            chain_ms[1] = worst[1]
-        if chain_err or float(chain_ms[1].item()) < 0:
-            e2e_chain = {"error": chain_err or "the leg failed on another rank"}
-        else:
-            e2e_chain = {"value": n_gpus * B * args.steps / (float(chain_ms[0].item()) * 1e-3), "unit": "pairs/s",
-                         "h2d_bytes_per_step": int(chain_info[2]) * n_gpus, "d2h_bytes_per_step": int(d2h) * n_gpus, "check": chain_info[3],
-                         "workload": "same call and feature mix on a frame chain: %d pairs replaying one trajectory of %d frames per GPU, "
-                                     "frames shipped once as one stack (PLSVO_ALIGN_FRAME_CHAIN)" % (B, B + 1),
-                         "_cpu_inputs": chain_info[:2] if rank == 0 else None}
     clk.__exit__(None, None, None)
     data = data_full
     numa.restore(saved_affinity)  # the CPU arms below get every host thread back
@@ -885,6 +860,25 @@ def main():
                                    "exact_vs_oracle": exact, "workload": row["workload"]}
         except Exception as ex:  # secondary block: never take the headline line down
             next_rows = {"error": repr(ex)}
+
+    # ---- end-to-end leg on a frame chain: the same call replaying ONE trajectory of B + 1 frames (pair b = frames b, b+1;
+    # src/frame_handler_mono.cpp:176,272) shipped as one stack, PLSVO_ALIGN_FRAME_CHAIN — every frame crosses the link once.
+    # Single-process run only, and after every other leg that touches the GPU: this is the youngest host path and its leg had
+    # not been timed on hardware when it was added, so nothing else in the line depends on its outcome, and the lines under
+    # torchrun keep exactly the legs they were measured with ----
+    e2e_chain = None
+    if not args.no_chain and not dist:
+        rebound = numa.bind_to_device(local_rank)  # as for the e2e leg
+        try:
+            chain_local_ms, chain_info = chain_leg(args, al, synth, torch, dev, stream, B, rank)
+            e2e_chain = {"value": B * args.steps / (chain_local_ms * 1e-3), "unit": "pairs/s",
+                         "h2d_bytes_per_step": int(chain_info[2]), "d2h_bytes_per_step": int(d2h), "check": chain_info[3],
+                         "workload": "same call and feature mix on a frame chain: %d pairs replaying one trajectory of %d frames, "
+                                     "frames shipped once as one stack (PLSVO_ALIGN_FRAME_CHAIN)" % (B, B + 1),
+                         "_cpu_inputs": chain_info[:2]}
+        except Exception as ex:  # secondary leg: never take the headline line down
+            e2e_chain = {"error": f"{type(ex).__name__}: {ex}"}
+        numa.restore(rebound)
 
     if rank == 0:
         cpu = None
